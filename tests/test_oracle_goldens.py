@@ -1,0 +1,269 @@
+"""Pins oracle/ (the CPU restatement) against the reference's own golden vectors.
+
+CPU only.  Every expectation cites the reference test it is transcribed from.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import kats
+import oracle_py as O
+from kats import assert_double_eq
+
+
+def _normal(kind, const_x=False, const_sigma=False):
+    e = O.OracleExpr()
+    xv = kats.N_VX if kind[0] == "v" else kats.N_X
+    mv = kats.N_VMU if kind[1] == "v" else kats.N_MU
+    sv = kats.N_VSIGMA if kind[2] == "v" else kats.N_SIGMA
+    x = e.const(xv) if const_x else e.var(xv)
+    mu = e.var(mv)
+    s = e.const(sv) if const_sigma else e.var(sv)
+    root = e.normal(x, mu, s)
+    e.bind(root)
+    return e, x, mu, s
+
+
+@pytest.mark.parametrize("kind", ["sss", "vss", "vvs", "vsv", "vvv"])
+def test_normal_goldens(kind):
+    # test/reverse/stat/normal_unittest.cpp:105-297
+    val, xa, ma, sa = kats.NORMAL_KAT[kind]
+    e, x, mu, s = _normal(kind)
+    assert_double_eq(e.feval(), [val], what=kind + " feval")
+    e.beval(1.0)
+    assert_double_eq(e.adj(x), xa, what=kind + " x_adj")
+    assert_double_eq(e.adj(mu), ma, what=kind + " mu_adj")
+    assert_double_eq(e.adj(s), sa, what=kind + " sigma_adj")
+
+
+def test_normal_constant_operand_paths():
+    # normal_unittest.cpp:151-172 (vss, x constant) and :237-257 (vsv, x and sigma constant)
+    val, _, ma, sa = kats.NORMAL_KAT["vss"]
+    e, x, mu, s = _normal("vss", const_x=True)
+    assert_double_eq(e.feval(), [val])
+    e.beval(1.0)
+    assert_double_eq(e.adj(mu), ma)
+    assert_double_eq(e.adj(s), sa)
+    val, _, ma, _ = kats.NORMAL_KAT["vsv"]
+    e, x, mu, s = _normal("vsv", const_x=True, const_sigma=True)
+    assert_double_eq(e.feval(), [val])
+    e.beval(1.0)
+    assert_double_eq(e.adj(mu), ma)
+
+
+@pytest.mark.parametrize("kind,bad", [("vsv", -1.0), ("vvv", 0.0)])
+def test_normal_not_pos_def(kind, bad):
+    # normal_unittest.cpp:207-213, 266-272
+    e = O.OracleExpr()
+    sig = kats.N_VSIGMA.copy()
+    sig[0] = bad
+    x = e.var(kats.N_VX)
+    mu = e.var(kats.N_VMU if kind[1] == "v" else kats.N_MU)
+    s = e.var(sig)
+    e.bind(e.normal(x, mu, s))
+    assert e.feval()[0] == -math.inf
+    e.beval(1.0)
+    assert np.all(e.adj(x) == 0)
+
+
+def test_erf_kat():
+    # test/reverse/core/unary_unittest.cpp:320-324
+    x0, f, df = kats.ERF_KAT
+    e = O.OracleExpr()
+    x = e.var(x0)
+    e.bind(e.unary("erf", x))
+    assert_double_eq(e.feval(), [f])
+    e.beval(3.14)
+    assert_double_eq(e.adj(x), [3.14 * df])
+
+
+def test_eval_mock_unary_accumulates():
+    # test/reverse/core/eval_unittest.cpp:32-48
+    e = O.OracleExpr()
+    x = e.var(kats.FIX_SCL)
+    e.bind(e.unary("mock2x", x))
+    assert_double_eq(e.autodiff(), [4.62])
+    assert_double_eq(e.adj(x), [2.0])
+    e.beval(1.0)
+    assert_double_eq(e.adj(x), [4.0])
+
+
+def test_bind_placeholders():
+    # test/reverse/core/bind_unittest.cpp:13-35
+    e = O.OracleExpr()
+    w1, w2, w3, w4 = e.var(1.0), e.var(2.0), e.var(0.0), e.var(0.0)
+    root = e.glue(e.eq(w3, e.binary("mul", w1, w2)), e.eq(w4, e.binary("mul", w3, w3)))
+    sizes = e.bind(root)
+    assert sizes == (0, 0)   # both roots alias their placeholders (eq.hpp:141-145)
+    for _ in range(2):
+        assert_double_eq(e.autodiff(), [4.0])
+        assert_double_eq(e.adj(w4), [1.0])
+        assert_double_eq(e.adj(w3), [4.0])
+        assert_double_eq(e.adj(w2), [4.0])
+        assert_double_eq(e.adj(w1), [8.0])
+        e.reset_adj()
+
+
+def test_integration_chains():
+    # test/integration/node_inttest.cpp:27-159
+    e = O.OracleExpr()
+    x = e.var(3.1)
+    e.bind(e.unary("sin", e.unary("log", x)))
+    assert_double_eq(e.autodiff(), [math.sin(math.log(3.1))])
+    assert_double_eq(e.adj(x), [math.cos(math.log(3.1)) / 3.1])
+
+    x1, x2, x3 = 1.5928, -0.291, 5.1023
+    e = O.OracleExpr()
+    l1, l2, l3 = e.var(x1), e.var(x2), e.var(x3)
+    root = e.binary("sub",
+                    e.binary("add", e.binary("mul", l1, l3),
+                             e.binary("mul", e.unary("sin", e.unary("cos", e.binary("add", l1, l2))), l2)),
+                    e.binary("div", l1, e.unary("exp", l3)))
+    e.bind(root)
+    assert_double_eq(e.feval(), [x1 * x3 + math.sin(math.cos(x1 + x2)) * x2 - x1 / math.exp(x3)])
+    e.beval(1.0)
+    assert_double_eq(e.adj(l1), [x3 - x2 * math.cos(math.cos(x1 + x2)) * math.sin(x1 + x2) - math.exp(-x3)])
+    assert_double_eq(e.adj(l2), [math.sin(math.cos(x1 + x2)) - x2 * math.cos(math.cos(x1 + x2)) * math.sin(x1 + x2)])
+    assert_double_eq(e.adj(l3), [x1 + x1 * math.exp(-x3)])
+
+
+def test_sum_iter_reevaluate():
+    # node_inttest.cpp:299-341: sum over 3 vars of cos(sin(v)*v), evaluated twice
+    vals = [0.203104, 1.4231, -1.231]
+    e = O.OracleExpr()
+    vs = [e.var(v) for v in vals]
+    root = e.sum_iter([e.unary("cos", e.binary("mul", e.unary("sin", v), v)) for v in vs])
+    e.bind(root)
+    want = sum(math.cos(math.sin(v) * v) for v in vals)
+    for _ in range(2):
+        assert_double_eq(e.autodiff(), [want])
+        for v, nid in zip(vals, vs):
+            d = -math.sin(math.sin(v) * v) * (math.cos(v) * v + math.sin(v))
+            assert_double_eq(e.adj(nid), [d])
+        e.reset_adj()
+
+
+def test_mat_sum_of_squares():
+    # node_inttest.cpp:380-400: sum(v*v) == 29 over a 3x2 matrix
+    m = np.array([[1.0, 2.0], [-1.0, 3.0], [2.0, -3.0]])
+    e = O.OracleExpr()
+    v = e.var(m)
+    e.bind(e.sum(e.binary("mul", v, v)))
+    assert_double_eq(e.autodiff(), [float((m * m).sum())])
+    assert_double_eq(e.adj(v), (2 * m).reshape(-1, order="F"))
+
+
+def test_prod_with_zero_element():
+    # test/reverse/core/prod_unittest.cpp (fixture vec has an exact zero, base_fixture.hpp:113)
+    e = O.OracleExpr()
+    v = e.var(kats.FIX_VEC)
+    e.bind(e.prod(v))
+    assert_double_eq(e.autodiff(2.0), [0.0])
+    others = np.prod(np.delete(kats.FIX_VEC, 3))
+    assert_double_eq(e.adj(v), [0, 0, 0, 2.0 * others, 0])
+
+
+def test_pow_zero_guards():
+    # pow.hpp:125-160 via test/reverse/core/pow_unittest.cpp
+    e = O.OracleExpr()
+    v = e.var(kats.FIX_VEC)
+    e.bind(e.sum(e.pow(2, v)))
+    assert_double_eq(e.autodiff(), [float((kats.FIX_VEC ** 2).sum())])
+    assert_double_eq(e.adj(v), 2 * kats.FIX_VEC)
+    e = O.OracleExpr()
+    x = e.var(0.0)
+    e.bind(e.pow(-2, x))
+    assert e.autodiff()[0] == math.inf
+    assert e.adj(x)[0] == -math.inf
+
+
+def test_quadratic_form_readme():
+    # README.md:582-607: x^T Sigma x, x=[0.5,0.6], Sigma=[[2,3],[3,6]] -> 4.46, adj [5.6,10.2]
+    e = O.OracleExpr()
+    x = e.var(np.array([[0.5], [0.6]]))      # 2x1 mat
+    xt = e.var(np.array([[0.5, 0.6]]))       # 1x2 mat standing for transpose(x)
+    S = e.const(np.array([[2.0, 3.0], [3.0, 6.0]]))
+    e.bind(e.dot(e.dot(xt, S), x))
+    assert_double_eq(e.autodiff(np.ones((1, 1))), [4.46])
+    assert_double_eq(e.adj(x) + e.adj(xt), [5.6, 10.2])
+
+
+def test_linreg_readme():
+    # README.md:623-662, GenTestData.nb:216-221: loss 6655, adj [-1210, -12100]
+    e = O.OracleExpr()
+    theta = e.var(kats.LINREG_THETA.reshape(2, 1))
+    loss = 0.0
+    for i in range(5):
+        g = O.OracleExpr()
+        th = g.var(kats.LINREG_THETA.reshape(2, 1))
+        xi = g.const(kats.LINREG_X[i].reshape(1, 2))
+        yi = g.const(kats.LINREG_Y[i].reshape(1, 1))
+        g.bind(g.pow(2, g.binary("sub", yi, g.dot(xi, th))))
+        loss += g.autodiff(np.ones((1, 1)))[0]
+        e.adj(theta)[:] += g.adj(th)
+    assert_double_eq([loss], [kats.LINREG_LOSS])
+    assert_double_eq(e.adj(theta), kats.LINREG_ADJ)
+
+
+def test_linreg_workload_matches_row_loop():
+    # the C4 workload (normal_adj_log_pdf(y, dot(X,w), sigma)) equals -0.5*loss/sigma^2 - n log sigma
+    X = np.asfortranarray(kats.LINREG_X)
+    w = kats.LINREG_THETA.copy()
+    wa = np.zeros(2)
+    sg = np.array([1.0])
+    sa = np.zeros(1)
+    v = O.linreg(X, kats.LINREG_Y.copy(), w, wa, sg, sa)
+    assert_double_eq([v], [-0.5 * kats.LINREG_LOSS])
+    assert_double_eq(wa, -0.5 * kats.LINREG_ADJ)
+    assert_double_eq(sa, [kats.LINREG_LOSS - 5])
+
+
+def test_mlp3_mathematica_goldens():
+    # GenTestData.nb:691-700 (README.md:670-745 network)
+    X = np.asfortranarray(kats.NN_X)
+    grad = np.zeros(25)
+    loss = O.mlp3(X, kats.NN_Y.copy(), kats.NN_PARM.copy(), grad)
+    assert abs(loss - 92030.04305391687) <= 1e-12 * 92030.0
+    assert abs(grad[0] - kats.NN_GRAD_A1_11) <= 1e-12 * abs(kats.NN_GRAD_A1_11)
+    assert abs(grad[3] - kats.NN_GRAD_A1_12) <= 1e-12 * abs(kats.NN_GRAD_A1_12)
+    g2 = np.zeros(25)
+    loss2 = O.mlp3(X, kats.NN_Y.copy(), kats.NN_PARM.copy(), g2, nthreads=2)
+    np.testing.assert_allclose(g2, grad, rtol=1e-13)
+    assert abs(loss2 - loss) <= 1e-12 * abs(loss)
+
+
+def test_black_scholes_example_point():
+    # example/black_scholes.cpp:43-70; closed-form values from SURVEY.md §6
+    p = kats.BS_POINT
+    arr = lambda v: np.array([v, v])
+    out = O.black_scholes(arr(p["S"]), arr(p["K"]), arr(p["sigma"]), arr(p["tau"]), arr(p["r"]))
+    k = kats.BS_KAT
+    want = [k["call"], k["put"], k["delta_call"], k["vega"], k["rho_call"], k["delta_put"],
+            k["vega"], k["rho_put"]]
+    for got, w in zip(out, want):
+        assert abs(got[0] - w) <= 2e-14 * max(1.0, abs(w)) * 8, (got[0], w)
+        assert got[0] == got[1]
+
+
+def test_threaded_workloads_agree_with_single_thread():
+    rng = np.random.default_rng(7)
+    n = 1000
+    x = rng.normal(size=n); mu = rng.normal(size=n); s = rng.uniform(0.5, 2, size=n)
+    xa, ma, sa = np.zeros(n), np.zeros(n), np.zeros(n)
+    v1 = O.normal_lpdf(x, mu, s, xa, ma, sa)
+    xb, mb, sb = np.zeros(n), np.zeros(n), np.zeros(n)
+    v2 = O.normal_lpdf(x, mu, s, xb, mb, sb, nthreads=3)
+    assert abs(v1 - v2) <= 1e-12 * abs(v1)
+    np.testing.assert_array_equal(xa, xb)
+    # scipy cross-check of the value (constant -n/2 log 2pi dropped, normal.hpp:14-30)
+    from scipy.stats import norm
+    ref = norm.logpdf(x, mu, s).sum() + 0.5 * n * math.log(2 * math.pi)
+    assert abs(v1 - ref) <= 1e-12 * abs(ref)
+    xs = rng.uniform(0.5, 2, size=n)
+    a1, a2 = np.zeros(n), np.zeros(n)
+    s1 = O.sum_unary("exp", xs, a1)
+    s2 = O.sum_unary("exp", xs, a2, nthreads=4)
+    assert abs(s1 - s2) <= 1e-13 * abs(s1)
+    np.testing.assert_array_equal(a1, a2)
+    assert_double_eq(a1, np.exp(xs), ulps=1)
