@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FastAD reverse-mode hot path on B200.
+
+Headline (BASELINE.json `metric`: "gradient evals/sec (batched Black-Scholes; ...)"):
+one step = one pass of the hot path (price + reverse-mode greeks of call AND put,
+example/black_scholes.cpp) over one batch of 2^20 synthetic options; one gradient eval = one
+option.  `value` = whole-job options/s with inputs resident in HBM; `e2e` = the same metric
+through the host-buffer C-ABI call (H2D + D2H inside the timed region).  The other BASELINE
+configs (sum map-reduce, normal log-pdf, regression, 3-layer net) are timed the same way and
+reported under `workloads`, each with its own HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--quick]
+N > 1: launched by torchrun, one rank per GPU; the batch shards across ranks with no
+data-path collective (weak scaling); the normal log-pdf workload shards by element range with
+one 4-double NCCL all-reduce per evaluation.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+BS_N = 1 << 20            # BASELINE config 0/1: batch of 2^20 options
+BS_BYTES = 104            # algorithmic bytes per option: 5 in + 8 out doubles
+L2_BYTES = 126 * (1 << 20)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world):
+    import torch
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_loop(fn, steps, warmup, world):
+    """W untimed + exactly K timed calls of fn(i), CUDA events on the launching stream."""
+    import torch
+    for i in range(warmup):
+        fn(i)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores.
+    FastAD needs Eigen 3.3, absent from this image, so the real reference cannot be built
+    (oracle/Makefile `ref-probe`); the Eigen-free node-by-node port in oracle/ stands in
+    (kind "port"), built -O3 -march=native, batch split over all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_py as O
+    import synth
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    cores = os.cpu_count() or 1
+    n = 1 << 18 if args.quick else BS_N
+    inp = synth.black_scholes_inputs(n)
+    keys = ("S", "K", "sigma", "tau", "r")
+    call = lambda: O.black_scholes(*(inp[k] for k in keys), nthreads=cores, fast=True)
+    for _ in range(max(1, min(args.warmup, 2))):
+        call()
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    dt = time.perf_counter() - t0
+    v = n * steps / dt
+    line = {
+        "impl": "reference", "metric": "gradient evals/sec (batched Black-Scholes)", "value": v,
+        "unit": "options/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"black_scholes call+put price + delta/vega/rho, batch {n} options per step",
+                   "host": "CPU port of the reference path (FastAD+Eigen is not buildable here: no Eigen)"},
+        "cpu_baseline": {"value": v, "unit": "options/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {n} options, {cores} threads"},
+        "e2e": {"value": v, "unit": "options/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import fastad_b200 as F
+    import synth
+
+    rank, world, local = dist_setup(args.gpus)
+    F.load()
+    F.check(F.lib().fadb_init(local))
+    F.use_torch_stream()
+    L = F.lib()
+    peak_gbs, peak_src = load_peaks()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    zeros = lambda n: torch.zeros(n, dtype=torch.float64, device="cuda")
+    keys = ("S", "K", "sigma", "tau", "r")
+
+    # ---------------- headline: Black-Scholes, inputs resident, rotating buffer sets > L2
+    n = BS_N
+    nsets = 4                                     # 4 x 104 MiB = 416 MiB > 126 MiB L2
+    sets = []
+    for s in range(nsets):
+        inp = synth.black_scholes_inputs(n, seed=synth.SEED + 100 * rank + s)
+        sets.append(([dev(inp[k]) for k in keys], [zeros(n) for _ in range(8)], inp))
+
+    # parity gate before timing (oracle = test infrastructure, used only as the checker)
+    if rank == 0:
+        import oracle_py as O
+        m = 1 << 14
+        d_in, d_out, inp = sets[0]
+        out = F.black_scholes(*[t[:m].contiguous() for t in d_in])
+        ref = O.black_scholes(*(inp[k][:m] for k in keys))
+        for g, o in zip(out, ref):
+            err = np.abs(g.cpu().numpy() - o)
+            assert np.all(err <= 1e-11 * np.maximum(1.0, np.abs(o))), "parity gate failed"
+
+    def bs_step(i):
+        d_in, d_out, _ = sets[i % nsets]
+        F.black_scholes(*d_in, out=d_out, flags=F.OVERWRITE_ADJ)
+
+    launches0 = L.fadb_launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed_loop(bs_step, args.steps, args.warmup, world)
+    launches = L.fadb_launch_count() - launches0 - args.warmup
+    value = world * n * args.steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps                    # one kernel launch per step, back to back
+    achieved = BS_BYTES * n / (kernel_ms * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    # ---------------- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
+    h_in = [torch.from_numpy(sets[0][2][k]).pin_memory() for k in keys]
+    h_out = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(8)]
+    np_in = [t.numpy() for t in h_in]
+    np_out = [t.numpy() for t in h_out]
+    e2e_steps = max(3, min(args.steps, 30))
+
+    def e2e_step(i):
+        F.black_scholes_host(*np_in, np_out)
+
+    ms_e2e = timed_loop(e2e_step, e2e_steps, 3, world)
+    e2e_val = world * n * e2e_steps / (ms_e2e * 1e-3)
+    bs_step(0)
+    torch.cuda.synchronize()
+    for k in range(8):   # the host-buffer call returns the same bits as the resident call
+        np.testing.assert_array_equal(np_out[k], sets[0][1][k].cpu().numpy())
+
+    # ---------------- the other BASELINE configs (rank-local unless stated)
+    workloads = {}
+
+    def add(name, bytes_per_launch, ms_total, steps, units, unit_name, extra=None):
+        k_ms = ms_total / steps
+        gbs = bytes_per_launch / (k_ms * 1e-3) / 1e9
+        workloads[name] = {"ms_per_step": k_ms, "evals_per_s": world * steps / (ms_total * 1e-3),
+                           unit_name + "_per_s": world * units * steps / (ms_total * 1e-3),
+                           "hbm_gbs": gbs, "roofline_frac": gbs / peak_gbs,
+                           "algorithmic_bytes": bytes_per_launch}
+        if extra:
+            workloads[name].update(extra)
+
+    if not args.quick:
+        steps2 = max(5, min(args.steps, 50))
+        # C2: sum(exp(x)), sum(log(x)), sum(pow<2>(x)); N = 2^24; 24 B/elem (x read + adj RMW)
+        n2 = 1 << 24
+        xs = [dev(synth.sum_inputs(n2, seed=synth.SEED + s)) for s in range(2)]   # 2 x 128 MiB
+        adjs = [zeros(n2) for _ in range(2)]
+        for op in ("exp", "log", ("pow", 2)):
+            code = F._op_code(op)
+            dval = zeros(1)
+            import ctypes as C
+
+            def step(i, code=code):
+                F.check(L.fadb_sum_unary_async(code, n2, C.c_void_p(xs[i % 2].data_ptr()),
+                                               C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0,
+                                               C.c_void_p(dval.data_ptr())))
+            t = timed_loop(step, steps2, 3, world)
+            nm = op if isinstance(op, str) else f"pow{op[1]}"
+            add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements")
+        del xs, adjs
+
+        # C3: normal log-pdf, N = 2^26 per rank.  vvv 72 B/elem; vss (x var) 24; vss (x const) 8
+        n3 = 1 << 26
+        x, mu, sg = (dev(a) for a in synth.normal_inputs(n3, seed=synth.SEED + rank))
+        xa, ma, sa = zeros(n3), zeros(n3), zeros(n3)
+        part = zeros(4); inval = zeros(1)
+        import ctypes as C
+        P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        val = C.c_double()
+
+        def normal_step(shape, x_adj, mu_t, sg_t, mu_adj, sg_adj, flags=0):
+            def step(i):
+                inv = None
+                if (shape & 2) and not (flags & F.TRUST_SIGMA):
+                    F.check(L.fadb_sigma_check(n3, P(sg_t), P(inval)))
+                    if world > 1:
+                        torch.distributed.all_reduce(inval)
+                    inv = inval
+                F.check(L.fadb_normal_lpdf_partial(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj),
+                                                   P(sg_adj), 1.0, flags, P(inv), P(part)))
+                if world > 1:
+                    torch.distributed.all_reduce(part)      # the one scalar exchange (NCCL)
+                F.check(L.fadb_normal_lpdf_finish(shape, n3 * world, P(part), P(x), P(mu_t), P(sg_t), None,
+                                                  P(mu_adj), P(sg_adj), 1.0, flags, None))
+            return step
+
+        mu1, sg1, mua1, sga1 = dev([0.1]), dev([1.3]), zeros(1), zeros(1)
+        t = timed_loop(normal_step(3, xa, mu, sg, ma, sa), steps2, 3, world)
+        add("normal_vvv_2^26", 72 * n3, t, steps2, n3, "elements",
+            {"note": "exact semantics: +8 B/elem sigma validity pre-pass (80 B/elem traffic)"})
+        t = timed_loop(normal_step(3, xa, mu, sg, ma, sa, F.TRUST_SIGMA), steps2, 3, world)
+        add("normal_vvv_2^26_trust_sigma", 72 * n3, t, steps2, n3, "elements")
+        t = timed_loop(normal_step(0, xa, mu1, sg1, mua1, sga1), steps2, 3, world)
+        add("normal_vss_2^26", 24 * n3, t, steps2, n3, "elements")
+        t = timed_loop(normal_step(0, None, mu1, sg1, mua1, sga1), steps2, 3, world)
+        add("normal_vss_xconst_2^26", 8 * n3, t, steps2, n3, "elements")
+        del x, mu, sg, xa, ma, sa
+
+        # C4: regression, X 2^20 x 64 column-major; 520 B/row
+        rows, cols = 1 << 20, 64
+        Xs = []
+        for s in range(2):                          # 2 x 512 MiB > L2
+            Xn, yn, wt = synth.linreg_inputs(rows, cols, seed=synth.SEED + s)
+            Xs.append((torch.from_numpy(np.ascontiguousarray(Xn.T)).cuda(), dev(yn)))
+        w, wa, sg1, sga1 = zeros(cols), zeros(cols), dev([1.0]), zeros(1)
+        lpart = zeros(cols + 1)
+
+        def lin_step(i):
+            Xd, yd = Xs[i % 2]
+            F.check(L.fadb_linreg_partial(rows, cols, P(Xd), P(yd), P(w), P(lpart)))
+            F.check(L.fadb_linreg_finish(rows, cols, P(lpart), P(sg1), P(wa), P(sga1), 1.0, 0, None))
+        t = timed_loop(lin_step, steps2, 3, world)
+        add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows")
+        del Xs
+
+        # C5: 3-layer net, batch 2^16 (configured) and 2^22 (roofline-sized); 24 B/sample
+        for b in (1 << 16, 1 << 22):
+            Xn, yn = synth.mlp3_inputs(b)
+            Xd, yd = torch.from_numpy(np.ascontiguousarray(Xn.T)).cuda(), dev(yn)
+            import kats
+            parm, grad, dl = dev(kats.NN_PARM), zeros(25), zeros(1)
+
+            def mlp_step(i):
+                F.check(L.fadb_mlp3_async(b, P(Xd), P(yd), P(parm), P(grad), 0, P(dl)))
+            t = timed_loop(mlp_step, steps2, 3, world)
+            add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples",
+                {"bound": "fp64 pipe / launch latency, not HBM"})
+
+    # ---------------- CPU baseline beside it (rank 0, bounded sample)
+    cpu = None
+    if rank == 0:
+        import oracle_py as O
+        cores = os.cpu_count() or 1
+        m = 1 << 20 if not args.quick else 1 << 16
+        inp = sets[0][2]
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            O.black_scholes(*(inp[k][:m] for k in keys), nthreads=cores, fast=True)
+            reps += 1
+            if time.perf_counter() - t0 > 8.0 or reps >= 20:
+                break
+        dt = time.perf_counter() - t0
+        cpu = {"value": m * reps / dt, "unit": "options/s", "cores": cores, "kind": "port",
+               "sample": f"{reps} x {m} options, {cores} threads, oracle -O3 -march=native"}
+
+    if rank == 0:
+        line = {
+            "metric": "gradient evals/sec (batched Black-Scholes)", "value": value, "unit": "options/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"black_scholes call+put price + delta/vega/rho (example/black_scholes.cpp), "
+                                   f"batch 2^20 options per GPU per step",
+                       "l2": f"rotating {nsets} resident buffer sets ({nsets * BS_BYTES * n >> 20} MiB) > 126 MiB L2",
+                       "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "kernel": "bs_kernel<false>", "algorithmic_bytes_per_launch": BS_BYTES * n},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "options/s", "h2d_bytes_per_step": 40 * n,
+                    "d2h_bytes_per_step": 64 * n, "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "fadb_black_scholes_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "workloads": workloads,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline only, small CPU sample")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+"""fastad_b200 — ctypes front-end to libfastad_b200.so (the C ABI in include/fastad_b200.h).
+
+The product is the CUDA library; this module only binds it for the Python test and bench
+harness.  PyTorch supplies device memory, streams and torch.distributed.  There is NO CPU
+fallback: if the shared library is missing, or there is no CUDA device, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+__all__ = ["lib", "load", "FadbError", "OVERWRITE_ADJ", "TRUST_SIGMA", "UNARY", "BINARY",
+           "black_scholes", "sum_unary", "prod", "normal_lpdf", "linreg_nll", "mlp3"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfastad_b200.so")
+
+OVERWRITE_ADJ = 1
+TRUST_SIGMA = 2
+SCL, VEC, MAT = 0, 1, 2
+UNARY = dict(neg=0, sin=1, cos=2, tan=3, asin=4, acos=5, atan=6, exp=7, log=8, sqrt=9, erf=10,
+             sigmoid=11, sinh=12, cosh=13, tanh=14, mock2x=100)
+BINARY = dict(add=0, sub=1, mul=2, div=3, mockb=100)
+
+
+class FadbError(RuntimeError):
+    pass
+
+
+_vp, _sz, _i, _d, _u = C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_uint
+_dp = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); mirrors include/fastad_b200.h one to one
+SIGNATURES = {
+    "fadb_init": (_i, [_i]),
+    "fadb_shutdown": (None, []),
+    "fadb_device_count": (_i, []),
+    "fadb_set_stream": (_i, [_vp]),
+    "fadb_sync": (_i, []),
+    "fadb_last_error": (C.c_char_p, []),
+    "fadb_launch_count": (C.c_ulonglong, []),
+    "fadb_version": (C.c_char_p, []),
+    "fadb_malloc": (_i, [_sz, C.POINTER(_vp)]),
+    "fadb_free": (_i, [_vp]),
+    "fadb_h2d": (_i, [_vp, _vp, _sz]),
+    "fadb_d2h": (_i, [_vp, _vp, _sz]),
+    "fadb_memset_zero": (_i, [_vp, _sz]),
+    "fadb_host_alloc_pinned": (_i, [_sz, C.POINTER(_vp)]),
+    "fadb_host_free_pinned": (_i, [_vp]),
+    "fadb_black_scholes": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _u]),
+    "fadb_black_scholes_host": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "fadb_sum_unary": (_i, [_i, _sz, _vp, _vp, _d, _u, _dp]),
+    "fadb_sum_unary_async": (_i, [_i, _sz, _vp, _vp, _d, _u, _vp]),
+    "fadb_prod": (_i, [_sz, _vp, _vp, _d, _u, _dp]),
+    "fadb_normal_lpdf": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_sigma_check": (_i, [_sz, _vp, _vp]),
+    "fadb_normal_lpdf_partial": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp, _vp]),
+    "fadb_normal_lpdf_finish": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_linreg_partial": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
+    "fadb_linreg_finish": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_linreg_nll": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_mlp3": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _dp]),
+    "fadb_mlp3_async": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _vp]),
+}
+
+_lib = None
+
+
+def load(path=None):
+    """dlopen the shared library and attach signatures.  Raises if it is not built."""
+    global _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FadbError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  fastad_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)          # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def lib():
+    return _lib if _lib is not None else load()
+
+
+def check(rc):
+    if rc != 0:
+        raise FadbError(f"fastad_b200 error {rc}: {lib().fadb_last_error().decode()}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def use_torch_stream():
+    """Route the library's launches to torch's current CUDA stream on the current device."""
+    import torch
+    check(lib().fadb_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def _chk_f64(*ts):
+    import torch
+    for t in ts:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise FadbError("fastad_b200 expects contiguous float64 CUDA tensors")
+
+
+# ------------------------------------------------------------------------------------------
+# Thin helpers over torch CUDA tensors (float64, contiguous).  Values come back as floats.
+# ------------------------------------------------------------------------------------------
+
+def black_scholes(S, K, sigma, tau, r, out=None, flags=OVERWRITE_ADJ):
+    import torch
+    _chk_f64(S, K, sigma, tau, r)
+    n = S.numel()
+    if out is None:
+        out = [torch.zeros(n, dtype=torch.float64, device=S.device) for _ in range(8)]
+    _chk_f64(*out)
+    arr = (C.c_void_p * 8)(*[o.data_ptr() for o in out])
+    check(lib().fadb_black_scholes(n, _ptr(S), _ptr(K), _ptr(sigma), _ptr(tau), _ptr(r), arr, flags))
+    return out
+
+
+def black_scholes_host(S, K, sigma, tau, r, out):
+    """numpy (host) arrays in, numpy arrays out — the call a user of the reference makes."""
+    n = len(S)
+    arr = (C.c_void_p * 8)(*[o.ctypes.data for o in out])
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    check(lib().fadb_black_scholes_host(n, p(S), p(K), p(sigma), p(tau), p(r), arr))
+    return out
+
+
+def _op_code(op):
+    if isinstance(op, str):
+        return UNARY[op]
+    kind, n = op
+    assert kind == "pow"
+    return 1000 + int(n)
+
+
+def sum_unary(op, x, x_adj, seed=1.0, flags=0):
+    _chk_f64(x, x_adj)
+    v = C.c_double()
+    check(lib().fadb_sum_unary(_op_code(op), x.numel(), _ptr(x), _ptr(x_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+def prod(x, x_adj, seed=1.0, flags=0):
+    _chk_f64(x, x_adj)
+    v = C.c_double()
+    check(lib().fadb_prod(x.numel(), _ptr(x), _ptr(x_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+def normal_lpdf(x, mu, sigma, x_adj=None, mu_adj=None, sigma_adj=None, seed=1.0, flags=0):
+    """mu / sigma: 1-element tensors are scalars (ad::scl), n-element tensors vectors."""
+    _chk_f64(x, mu, sigma, x_adj, mu_adj, sigma_adj)
+    n = x.numel()
+    shape = (1 if (mu.numel() == n and n > 1) else 0) | (2 if (sigma.numel() == n and n > 1) else 0)
+    v = C.c_double()
+    check(lib().fadb_normal_lpdf(shape, n, _ptr(x), _ptr(mu), _ptr(sigma), _ptr(x_adj), _ptr(mu_adj),
+                                 _ptr(sigma_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+def linreg_nll(X, y, w, w_adj, sigma, sigma_adj, seed=1.0, flags=0):
+    """X: (cols, rows) contiguous torch tensor == rows x cols column-major."""
+    _chk_f64(X, y, w, w_adj, sigma, sigma_adj)
+    cols, rows = X.shape
+    v = C.c_double()
+    check(lib().fadb_linreg_nll(rows, cols, _ptr(X), _ptr(y), _ptr(w), _ptr(w_adj), _ptr(sigma),
+                                _ptr(sigma_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+def mlp3(X, y, parm, grad, flags=0):
+    """X: (2, batch) contiguous torch tensor == batch x 2 column-major."""
+    _chk_f64(X, y, parm, grad)
+    v = C.c_double()
+    check(lib().fadb_mlp3(y.numel(), _ptr(X), _ptr(y), _ptr(parm), _ptr(grad), flags, C.byref(v)))
+    return v.value

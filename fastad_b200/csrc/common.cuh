@@ -1,0 +1,168 @@
+// common.cuh — shared device/host helpers for the fastad_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/fastad_b200.h"
+
+namespace fadb {
+
+// ---------------------------------------------------------------------------------------
+// Error convention: every C-ABI entry returns 0 or a negative code; message is thread-local.
+// No C++ exception crosses the ABI.
+// ---------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FADB_CUDA(expr)                                                             \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return ::fadb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define FADB_REQUIRE(cond, msg)                                  \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::fadb::set_error(std::string("fastad_b200: ") + msg); \
+            return FADB_ERR_ARG;                                 \
+        }                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Per-device context: SM count, the stream every launch goes to, and a small workspace
+// (per-CTA partials + ticket counters) so that hot calls never allocate.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxGrid = 148 * 16;       // upper bound on CTAs of any reduction launch
+constexpr int kPartialSlots = 8;         // reduction channels per CTA
+constexpr int kMaxDevices = 16;
+constexpr int kScalarSlots = 256;        // device doubles for reduced values / deferred seeds
+
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    double* partials = nullptr;          // [kMaxGrid * kPartialSlots]
+    unsigned int* tickets = nullptr;     // [64] last-block tickets (self-resetting)
+    double* scalars = nullptr;           // [kScalarSlots] device result slots
+    double* host_scalars = nullptr;      // pinned mirror for D2H of results
+    unsigned long long launches = 0;     // kernels launched by this library on this device
+};
+
+int current_context(Context** out);
+
+inline int grid_for(const Context& c, size_t work_items, int per_sm, size_t items_per_cta)
+{
+    size_t want = (work_items + items_per_cta - 1) / items_per_cta;
+    size_t cap = (size_t)c.sms * per_sm;
+    if (want < 1) want = 1;
+    if (want > cap) want = cap;
+    if (want > (size_t)kMaxGrid) want = kMaxGrid;
+    return (int)want;
+}
+
+// ---------------------------------------------------------------------------------------
+// 256-bit global memory access (LDG.E.256 / STG.E.256 on sm_100a).
+// Streaming data is read once: bypass L1 allocation; adjoint RMW uses plain ld/st.
+// ---------------------------------------------------------------------------------------
+struct __align__(32) double4_t { double v[4]; };
+
+__device__ __forceinline__ double4_t ldg256_stream(const double* p)
+{
+    double4_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double4_t ld256(const double* p)
+{
+    double4_t r;
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st256(double* p, const double4_t& r)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+}
+
+__host__ __device__ inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
+// ---------------------------------------------------------------------------------------
+// Deterministic block reduction of NCH channels: warp shuffle tree, then shared memory,
+// result valid in thread 0.  Fixed tree => run-to-run identical bits.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_prod(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NCH>
+__device__ __forceinline__ void block_sum(double (&acc)[NCH], double* smem /* [32*NCH] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) smem[warp * NCH + c] = acc[c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            double v = lane < nwarp ? smem[lane * NCH + c] : 0.0;
+            acc[c] = warp_sum(v);
+        }
+    }
+    __syncthreads();
+}
+
+// Grid-level finish: every CTA stores its NCH partials; the last CTA to arrive (ticket)
+// sums all partials in CTA order with one warp-strided pass + fixed tree, then calls `fin`
+// from thread 0.  One launch, deterministic, no float atomics.
+template <int NCH, class Fin>
+__device__ __forceinline__ void grid_finish(double (&acc)[NCH], double* smem, double* partials,
+                                            unsigned int* ticket, Fin&& fin)
+{
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) partials[(size_t)blockIdx.x * NCH + c] = acc[c];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double tot[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tot[c] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tot[c] += __ldcg(&partials[(size_t)b * NCH + c]);
+    }
+    block_sum<NCH>(tot, smem);
+    if (threadIdx.x == 0) {
+        *ticket = 0u;   // self-reset for the next launch on this stream
+        fin(tot);
+    }
+}
+
+}  // namespace fadb

@@ -1,0 +1,221 @@
+// map_reduce.cu — K2/K3: root-level reductions over a VarView with the adjoint scatter fused.
+//
+// K2 replaces autodiff of ad::sum(f(x)):  SumElemNode::feval/beval (sum.hpp:156-173) over
+// UnaryNode::feval/beval (unary.hpp:63-89) or PowNode<n> (pow.hpp:91-162) and the leaf's
+// `adj += seed` (var_view.hpp:91-94).  The reference makes ~5 array passes (64-72 B/element);
+// here the root seed is known up front so one pass does it: read x (8 B) + RMW x_adj (16 B).
+//
+// K3 replaces autodiff of ad::prod(x): ProdElemNode::feval/beval (prod.hpp:172-212).  The
+// reference recomputes an O(N) product for every exact zero; here pass 1 reduces
+// (product of non-zeros, #zeros) and pass 2 scatters adj_i from those two numbers.
+#include "common.cuh"
+#include "functors.cuh"
+
+namespace fadb {
+
+template <class F>
+__global__ void __launch_bounds__(256)
+sum_map_kernel(size_t n, const double* __restrict__ x, double* x_adj, double seed, int overwrite,
+               F fun, double* partials, unsigned int* ticket, double* out_value)
+{
+    __shared__ double smem[32];
+    double acc[1] = {0.0};
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const bool vec = aligned32(x) && (!x_adj || aligned32(x_adj));
+    const size_t n4 = vec ? n / 4 : 0;
+    for (size_t q = tid; q < n4; q += nth) {
+        const size_t i = 4 * q;
+        const double4_t xv = ldg256_stream(x + i);
+        double4_t g;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double f = fun.f(xv.v[k]);
+            acc[0] += f;
+            g.v[k] = fun.b(seed, xv.v[k], f);
+        }
+        if (x_adj) {
+            if (!overwrite) {
+                const double4_t old = ld256(x_adj + i);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g.v[k] += old.v[k];
+            }
+            st256(x_adj + i, g);
+        }
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) {
+        const double f = fun.f(x[i]);
+        acc[0] += f;
+        if (x_adj) {
+            const double g = fun.b(seed, x[i], f);
+            x_adj[i] = overwrite ? g : x_adj[i] + g;
+        }
+    }
+    block_sum<1>(acc, smem);
+    grid_finish<1>(acc, smem, partials, ticket, [&](double (&tot)[1]) { out_value[0] = tot[0]; });
+}
+
+template <int OP>
+struct UnaryFun {
+    __device__ __forceinline__ double f(double x) const { return Unary<OP>::f(x); }
+    __device__ __forceinline__ double b(double s, double x, double f) const { return Unary<OP>::b(s, x, f); }
+};
+struct PowFun {
+    long n;
+    __device__ __forceinline__ double f(double x) const { return pow_int(n, x); }
+    __device__ __forceinline__ double b(double s, double x, double f) const { return pow_bmap(n, s, x, f); }
+};
+struct Pow2Fun {   // pow<2>: f = x*x, adj = 2*seed*(x==0 ? 0 : f/x)   (pow.hpp:125-140)
+    __device__ __forceinline__ double f(double x) const { return x * x; }
+    __device__ __forceinline__ double b(double s, double x, double f) const { return 2. * s * (x == 0 ? 0 : f / x); }
+};
+
+template <class F>
+static int launch_sum_map(Context& c, size_t n, const double* x, double* x_adj, double seed,
+                          unsigned flags, F fun, double* dval)
+{
+    const int threads = 256;
+    const int grid = grid_for(c, (n + 3) / 4, 8, threads);
+    sum_map_kernel<F><<<grid, threads, 0, c.stream>>>(n, x, x_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
+                                                      fun, c.partials, c.tickets + 2, dval);
+    c.launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+// ------------------------------------------------------------------ prod
+__global__ void __launch_bounds__(256)
+prod_reduce_kernel(size_t n, const double* __restrict__ x, double* partials, unsigned int* ticket,
+                   double* out /* {prod of non-zeros, #zeros, value} */)
+{
+    __shared__ double sp[32], sz[32];
+    __shared__ bool is_last;
+    double p = 1.0, z = 0.0;
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += nth) {
+        const double v = __ldg(x + i);
+        if (v == 0) z += 1.0; else p *= v;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    p = warp_prod(p); z = warp_sum(z);
+    if (lane == 0) { sp[warp] = p; sz[warp] = z; }
+    __syncthreads();
+    if (warp == 0) {
+        p = warp_prod(lane < nwarp ? sp[lane] : 1.0);
+        z = warp_sum(lane < nwarp ? sz[lane] : 0.0);
+    }
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = p;
+        partials[2 * blockIdx.x + 1] = z;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    p = 1.0; z = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        p *= __ldcg(&partials[2 * b]);
+        z += __ldcg(&partials[2 * b + 1]);
+    }
+    p = warp_prod(p); z = warp_sum(z);
+    if (lane == 0) { sp[warp] = p; sz[warp] = z; }
+    __syncthreads();
+    if (warp == 0) {
+        p = warp_prod(lane < nwarp ? sp[lane] : 1.0);
+        z = warp_sum(lane < nwarp ? sz[lane] : 0.0);
+        if (lane == 0) {
+            out[0] = p; out[1] = z; out[2] = (z > 0) ? 0.0 : p;   // prod.hpp:178
+            *ticket = 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+prod_scatter_kernel(size_t n, const double* __restrict__ x, double* x_adj, double seed, int overwrite,
+                    const double* red)
+{
+    const double pnz = red[0], zeros = red[1], val = red[2];
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += nth) {
+        const double v = __ldg(x + i);
+        double g;
+        // prod.hpp:194-207: zero element -> product of all the others; else seed * (prod / x_i)
+        if (v == 0) g = seed * ((zeros > 1) ? 0.0 : pnz);
+        else g = seed * (val / v);
+        x_adj[i] = overwrite ? g : x_adj[i] + g;
+    }
+}
+
+}  // namespace fadb
+
+using namespace fadb;
+
+static int read_back(Context& c, const double* dval, double* host_value)
+{
+    if (!host_value) return FADB_OK;
+    FADB_CUDA(cudaMemcpyAsync(c.host_scalars + 1, dval, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    FADB_CUDA(cudaStreamSynchronize(c.stream));
+    *host_value = c.host_scalars[1];
+    return FADB_OK;
+}
+
+extern "C" int fadb_sum_unary_async(int op, size_t n, const double* x, double* x_adj, double seed,
+                                    unsigned flags, double* dev_value)
+{
+    FADB_REQUIRE(n == 0 || x, "fadb_sum_unary: null x");
+    FADB_REQUIRE(dev_value != nullptr, "fadb_sum_unary: null value slot");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    if (op >= 1000 - 64 && op <= 1000 + 64) {
+        const long pw = op - 1000;
+        if (pw == 2) return launch_sum_map(*c, n, x, x_adj, seed, flags, Pow2Fun{}, dev_value);
+        return launch_sum_map(*c, n, x, x_adj, seed, flags, PowFun{pw}, dev_value);
+    }
+    switch (op) {
+#define C(OP) case OP: return launch_sum_map(*c, n, x, x_adj, seed, flags, UnaryFun<OP>{}, dev_value);
+        C(FADB_NEG) C(FADB_SIN) C(FADB_COS) C(FADB_TAN) C(FADB_ASIN) C(FADB_ACOS) C(FADB_ATAN)
+        C(FADB_EXP) C(FADB_LOG) C(FADB_SQRT) C(FADB_ERF) C(FADB_SIGMOID) C(FADB_SINH) C(FADB_COSH)
+        C(FADB_TANH) C(FADB_MOCK2X)
+#undef C
+    }
+    set_error("fadb_sum_unary: unknown op code " + std::to_string(op));
+    return FADB_ERR_ARG;
+}
+
+extern "C" int fadb_sum_unary(int op, size_t n, const double* x, double* x_adj, double seed,
+                              unsigned flags, double* host_value)
+{
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    double* dval = c->scalars + 1;
+    rc = fadb_sum_unary_async(op, n, x, x_adj, seed, flags, dval);
+    if (rc) return rc;
+    return read_back(*c, dval, host_value);
+}
+
+extern "C" int fadb_prod(size_t n, const double* x, double* x_adj, double seed, unsigned flags,
+                         double* host_value)
+{
+    FADB_REQUIRE(n == 0 || x, "fadb_prod: null x");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    double* red = c->scalars + 16;   // 3 doubles
+    const int threads = 256;
+    const int grid = grid_for(*c, n, 8, threads);
+    prod_reduce_kernel<<<grid, threads, 0, c->stream>>>(n, x, c->partials, c->tickets + 3, red);
+    c->launches++;
+    FADB_CUDA(cudaGetLastError());
+    if (x_adj && n > 0) {
+        prod_scatter_kernel<<<grid, threads, 0, c->stream>>>(n, x, x_adj, seed,
+                                                            (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, red);
+        c->launches++;
+        FADB_CUDA(cudaGetLastError());
+    }
+    return read_back(*c, red + 2, host_value);
+}

@@ -1,0 +1,164 @@
+// mlp3.cu — K6: 3-layer network with jump connection, batched forward + reverse sweep.
+//
+// Replaces the per-row loop `for each row: copy row; autodiff(expr, seed)` of
+// example/ceres_3layer_neural_net/src.cpp:48-55 over the expression of README.md:706-711
+// (src.cpp:38-40):   pow<2>(yi - (dot(A3, sigmoid(dot(A2, sigmoid(x1)) + b2) + x1) + b3)),
+// x1 = dot(A1, xi) + b1, i.e. DotNode (dot.hpp:89-104), UnaryNode<Sigmoid> (unary.hpp:273-278),
+// BinaryNode<Add/Sub> (binary.hpp:266-303), PowNode<2> (pow.hpp:91-140) feval + beval, with the
+// 25 parameter adjoints accumulated over rows by VarView::beval (var_view.hpp:91-94).
+// One thread owns one row: forward and adjoint sweep in registers; the 25 gradients + loss are
+// reduced across the CTA with warp shuffles and across CTAs by the last-arriving CTA.
+// The matrices are 3x2, 3x3 and 1x3: far below a DMMA tile, so the FP64 tensor path is not used.
+#include "common.cuh"
+
+namespace fadb {
+
+constexpr int NP = 25;            // parameters: A1(3x2) b1(3) A2(3x3) b2(3) A3(1x3) b3(1), column-major
+constexpr int NOUT = NP + 1;      // + loss
+
+__device__ __forceinline__ double sigmoid_f(double x) { return 1 / (1 + exp(-x)); }
+
+__global__ void __launch_bounds__(256)
+mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict__ y,
+            const double* __restrict__ parm, double* cta_partials, unsigned int* ticket,
+            double* grad, int overwrite, double* out_loss)
+{
+    __shared__ double p[NP];
+    __shared__ double red[8][NOUT];
+    __shared__ bool is_last;
+    if (threadIdx.x < NP) p[threadIdx.x] = parm[threadIdx.x];
+    __syncthreads();
+    const double* A1 = p;        // A1(i,j) = A1[i + 3j]
+    const double* b1 = p + 6;
+    const double* A2 = p + 9;    // A2(i,j) = A2[i + 3j]
+    const double* b2 = p + 18;
+    const double* A3 = p + 21;   // A3(0,j) = A3[j]
+    const double b3 = p[24];
+
+    double acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = 0.0;
+
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t row = tid; row < batch; row += nth) {
+        const double xa = __ldg(X + row), xb = __ldg(X + batch + row), yy = __ldg(y + row);
+        // ---- forward ----
+        double x1[3], e1[3], y1[3], h[3], e2[3], y2[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            x1[i] = (A1[i] * xa + A1[i + 3] * xb) + b1[i];          // dot(A1, xi) + b1
+            e1[i] = exp(-x1[i]);
+            y1[i] = 1 / (1 + e1[i]);                                // sigmoid, unary.hpp:273-275
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            h[i] = ((A2[i] * y1[0] + A2[i + 3] * y1[1]) + A2[i + 6] * y1[2]) + b2[i];
+            e2[i] = exp(-h[i]);
+            y2[i] = 1 / (1 + e2[i]) + x1[i];                        // sigmoid(...) + x1
+        }
+        const double y3 = ((A3[0] * y2[0] + A3[1] * y2[1]) + A3[2] * y2[2]) + b3;
+        const double d = yy - y3;
+        const double loss = d * d;                                  // pow<2>
+        acc[NP] += loss;
+        // ---- backward, seed 1 ----
+        const double g_d = 2. * (d == 0 ? 0 : loss / d);            // pow.hpp:125-140
+        const double g_y3 = -g_d;                                   // Sub::brmap
+        double g_y2[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            acc[21 + j] += g_y3 * y2[j];                            // A3_adj = adj * y2^T
+            g_y2[j] = A3[j] * g_y3;                                 // A3^T * adj
+        }
+        acc[24] += g_y3;                                            // b3
+        double g_h[3], g_y1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            g_h[i] = g_y2[i] * e2[i] / ((e2[i] + 1) * (e2[i] + 1)); // Sigmoid::bmap, unary.hpp:276-278
+            acc[18 + i] += g_h[i];                                  // b2
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                acc[9 + i + 3 * j] += g_h[i] * y1[j];               // A2_adj = adj * y1^T
+                g_y1[j] += A2[i + 3 * j] * g_h[i];                  // A2^T * adj
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            // x1 enters twice (README form has the sub-tree twice): through y1 and the jump
+            const double g_x1 = g_y1[i] * e1[i] / ((e1[i] + 1) * (e1[i] + 1)) + g_y2[i];
+            acc[i] += g_x1 * xa;                                    // A1_adj = adj * xi^T
+            acc[i + 3] += g_x1 * xb;
+            acc[6 + i] += g_x1;                                     // b1
+        }
+    }
+    // ---- CTA reduce of the 26 channels ----
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NOUT) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        cta_partials[(size_t)blockIdx.x * NOUT + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < NOUT) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&cta_partials[(size_t)b * NOUT + threadIdx.x]);
+        if (threadIdx.x == NP) out_loss[0] = v;
+        else if (grad) grad[threadIdx.x] = overwrite ? v : grad[threadIdx.x] + v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+static double* g_mlp_ws[kMaxDevices] = {nullptr};
+
+}  // namespace fadb
+
+using namespace fadb;
+
+extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, const double* parm,
+                               double* grad, unsigned flags, double* dev_loss)
+{
+    FADB_REQUIRE(batch == 0 || (X && y), "fadb_mlp3: null data");
+    FADB_REQUIRE(parm && dev_loss, "fadb_mlp3: null parameter / loss pointer");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    if (!g_mlp_ws[c->device]) FADB_CUDA(cudaMalloc(&g_mlp_ws[c->device], sizeof(double) * kMaxGrid * NOUT));
+    const int threads = 256;
+    const int grid = grid_for(*c, batch, 4, threads);
+    mlp3_kernel<<<grid, threads, 0, c->stream>>>(batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad,
+                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss);
+    c->launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+extern "C" int fadb_mlp3(size_t batch, const double* X, const double* y, const double* parm,
+                         double* grad, unsigned flags, double* host_loss)
+{
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    double* dval = c->scalars + 3;
+    rc = fadb_mlp3_async(batch, X, y, parm, grad, flags, dval);
+    if (rc) return rc;
+    if (host_loss) {
+        FADB_CUDA(cudaMemcpyAsync(c->host_scalars + 3, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FADB_CUDA(cudaStreamSynchronize(c->stream));
+        *host_loss = c->host_scalars[3];
+    }
+    return FADB_OK;
+}

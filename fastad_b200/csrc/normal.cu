@@ -1,0 +1,325 @@
+// normal.cu — K4: ad::normal_adj_log_pdf(x, mu, sigma) value + adjoints, leaf operands.
+//
+// Replaces NormalAdjLogPDFNode<..., tuple<scl|vec, scl|vec, scl|vec>>::feval/beval
+// (reverse/stat/normal.hpp: sss :108-180, vss :182-301, vvs :304-381, vsv :384-495,
+// vvv :498-578) and the VarView::beval `adj += seed` of its operands (var_view.hpp:91-94).
+//
+// The reference makes 2 passes over sigma (validity + log-sum), one over x,mu,sigma for the
+// value and three adjoint passes that each re-read x,mu,sigma (~160 B/element for vvv).
+// Here the root-level seed is known when the call is made, so value and all adjoints are
+// produced by ONE fused pass: 3 streaming reads + 3 read-modify-writes = 72 B/element (vvv).
+// A vector sigma that is a variable needs its validity known before the first adjoint is
+// written (normal.hpp:440-442,457: sigma<=0 => value -inf and NO adjoint update), which costs
+// one extra streaming read of sigma (8 B/element) unless the caller passes FADB_TRUST_SIGMA.
+#include "common.cuh"
+
+namespace fadb {
+
+constexpr int NCH = 4;  // channels: 0 = sum d^2 | z^2, 1 = sum log sigma_i, 2 = sum d | d/s^2, 3 = #invalid
+
+struct NormalArgs {
+    size_t n;
+    const double* x; const double* mu; const double* sigma;
+    double* x_adj; double* mu_adj; double* sigma_adj;
+    double seed;
+    int overwrite;
+    const double* invalid_in;   // device count of sigma_i <= 0 from the pre-pass (may be null)
+};
+
+// ------------------------------------------------------------------ sigma validity pre-pass
+__global__ void __launch_bounds__(512)
+sigma_check_kernel(size_t n, const double* __restrict__ sigma, double* partials,
+                   unsigned int* ticket, double* out_count)
+{
+    __shared__ double smem[32];
+    double acc[1] = {0.0};
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const bool vec = aligned32(sigma);
+    const size_t n4 = vec ? n / 4 : 0;
+    for (size_t q = tid; q < n4; q += nth) {
+        const double4_t s = ldg256_stream(sigma + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[0] += (s.v[k] > 0) ? 0.0 : 1.0;
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) acc[0] += (sigma[i] > 0) ? 0.0 : 1.0;
+    block_sum<1>(acc, smem);
+    grid_finish<1>(acc, smem, partials, ticket, [&](double (&tot)[1]) { out_count[0] = tot[0]; });
+}
+
+// ------------------------------------------------------------------ fused main pass
+template <bool MU_VEC, bool SIG_VEC>
+struct Elem {
+    // per-element forward terms + adjoints, formulas in the order the reference writes them
+    __device__ __forceinline__ static void run(double x, double m, double s, double seed,
+                                               double inv_s_sq /* scalar sigma only */,
+                                               double (&acc)[NCH], double& gx, double& gm, double& gs)
+    {
+        const double d = x - m;
+        if (SIG_VEC) {
+            const double z = d / s;                           // normal.hpp:449, 546
+            acc[0] += z * z;
+            acc[1] += log(s);                                 // normal.hpp:483, 572
+            const double s2 = s * s;
+            gx = seed * (m - x) / s2;                         // normal.hpp:474, 564 (vsv: (seed/s^2)*(m-x))
+            if (MU_VEC) gm = seed * d / s2;                   // normal.hpp:563
+            else { acc[2] += d / s2; gm = 0.0; }              // normal.hpp:471
+            gs = (seed / s) * (z * z - 1.);                   // normal.hpp:468, 560
+        } else {
+            acc[0] += d * d;                                  // squaredNorm, normal.hpp:244, 351
+            const double c = seed * inv_s_sq;
+            gx = c * (m - x);                                 // normal.hpp:282, 371
+            if (MU_VEC) gm = c * d;                           // normal.hpp:370
+            else { acc[2] += d; gm = 0.0; }                   // normal.hpp:277
+            gs = 0.0;
+        }
+    }
+};
+
+__device__ __forceinline__ void rmw4(double* p, const double (&g)[4], int overwrite)
+{
+    double4_t v;
+    if (overwrite) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.v[k] = g[k];
+    } else {
+        v = ld256(p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.v[k] += g[k];
+    }
+    st256(p, v);
+}
+
+template <bool MU_VEC, bool SIG_VEC>
+__global__ void __launch_bounds__(256)
+normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_partial)
+{
+    __shared__ double smem[32 * NCH];
+    double acc[NCH] = {0.0, 0.0, 0.0, 0.0};
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+
+    // Validity (uniform across the grid): scalar sigma is read by everyone; vector sigma uses
+    // the pre-pass count.  Invalid => forward sums still flow (finish() turns them into -inf)
+    // but no adjoint is touched.
+    double s_scl = 1.0, m_scl = 0.0, inv_s_sq = 1.0;
+    bool valid = true;
+    if (!SIG_VEC) {
+        s_scl = __ldg(a.sigma);
+        valid = s_scl > 0;
+        const double inv_s = 1. / s_scl;                      // normal.hpp:254-255
+        inv_s_sq = inv_s * inv_s;
+    } else if (a.invalid_in) {
+        valid = __ldcg(a.invalid_in) == 0.0;
+    }
+    if (!MU_VEC) m_scl = __ldg(a.mu);
+    const bool back = valid && a.seed != 0.0;                  // normal.hpp:160, 252, 457
+    const bool wx = back && a.x_adj, wm = back && MU_VEC && a.mu_adj,
+               ws = back && SIG_VEC && a.sigma_adj;
+
+    bool vec = aligned32(a.x) && (!MU_VEC || aligned32(a.mu)) && (!SIG_VEC || aligned32(a.sigma)) &&
+               (!a.x_adj || aligned32(a.x_adj)) && (!MU_VEC || !a.mu_adj || aligned32(a.mu_adj)) &&
+               (!SIG_VEC || !a.sigma_adj || aligned32(a.sigma_adj));
+    const size_t n4 = vec ? a.n / 4 : 0;
+    for (size_t q = tid; q < n4; q += nth) {
+        const size_t i = 4 * q;
+        const double4_t xv = ldg256_stream(a.x + i);
+        double4_t mv, sv;
+        if (MU_VEC) mv = ldg256_stream(a.mu + i);
+        if (SIG_VEC) sv = ldg256_stream(a.sigma + i);
+        double gx[4], gm[4], gs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double s = SIG_VEC ? sv.v[k] : s_scl;
+            if (SIG_VEC && !(s > 0)) acc[3] += 1.0;
+            Elem<MU_VEC, SIG_VEC>::run(xv.v[k], MU_VEC ? mv.v[k] : m_scl, s, a.seed, inv_s_sq, acc,
+                                       gx[k], gm[k], gs[k]);
+        }
+        if (wx) rmw4(a.x_adj + i, gx, a.overwrite);
+        if (wm) rmw4(a.mu_adj + i, gm, a.overwrite);
+        if (ws) rmw4(a.sigma_adj + i, gs, a.overwrite);
+    }
+    for (size_t i = n4 * 4 + tid; i < a.n; i += nth) {
+        const double s = SIG_VEC ? a.sigma[i] : s_scl;
+        if (SIG_VEC && !(s > 0)) acc[3] += 1.0;
+        double gx, gm, gs;
+        Elem<MU_VEC, SIG_VEC>::run(a.x[i], MU_VEC ? a.mu[i] : m_scl, s, a.seed, inv_s_sq, acc, gx, gm, gs);
+        if (wx) a.x_adj[i] = a.overwrite ? gx : a.x_adj[i] + gx;
+        if (wm) a.mu_adj[i] = a.overwrite ? gm : a.mu_adj[i] + gm;
+        if (ws) a.sigma_adj[i] = a.overwrite ? gs : a.sigma_adj[i] + gs;
+    }
+    if (!SIG_VEC && !valid && blockIdx.x == 0 && threadIdx.x == 0) acc[3] += 1.0;
+    block_sum<NCH>(acc, smem);
+    grid_finish<NCH>(acc, smem, partials, ticket, [&](double (&tot)[NCH]) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) out_partial[c] = tot[c];
+    });
+}
+
+// ------------------------------------------------------------------ scalar epilogue
+// Turns the (possibly all-reduced) partial sums into the node value and the adjoints of
+// scalar operands.  n_total is the global element count.
+__global__ void normal_finish_kernel(int shape_code, double n_total, const double* partial,
+                                     const double* x, const double* mu, const double* sigma,
+                                     double* x_adj, double* mu_adj, double* sigma_adj, double seed,
+                                     int overwrite, double* out_value)
+{
+    const bool mu_vec = shape_code & 1, sig_vec = shape_code & 2;
+    if (partial[3] != 0.0) { out_value[0] = -INFINITY; return; }   // normal.hpp:147, 440-442
+    if (n_total == 1.0 && shape_code == 0) {
+        // sss, normal.hpp:141-171
+        const double s = sigma[0], inv_s = 1. / s;
+        const double z = (x[0] - mu[0]) / s;
+        out_value[0] = -0.5 * z * z - log(s);
+        if (seed == 0.0) return;
+        const double zb = (x[0] - mu[0]) * inv_s;
+        if (sigma_adj) { const double g = seed * (zb * zb - 1) * inv_s; sigma_adj[0] = overwrite ? g : sigma_adj[0] + g; }
+        const double adj = seed * zb * inv_s;
+        if (mu_adj) mu_adj[0] = overwrite ? adj : mu_adj[0] + adj;
+        if (x_adj) x_adj[0] = overwrite ? -adj : x_adj[0] - adj;
+        return;
+    }
+    if (sig_vec) {
+        out_value[0] = -0.5 * partial[0] - partial[1];              // normal.hpp:451, 548
+        if (!mu_vec && mu_adj && seed != 0.0) {
+            const double g = seed * partial[2];                    // normal.hpp:471-472
+            mu_adj[0] = overwrite ? g : mu_adj[0] + g;
+        }
+    } else {
+        const double s = sigma[0];
+        const double inv_s = 1. / s, inv_s_sq = inv_s * inv_s;
+        const double z_sq = partial[0] / (s * s);                   // normal.hpp:245, 351
+        out_value[0] = -0.5 * z_sq - n_total * log(s);
+        if (seed == 0.0) return;
+        if (sigma_adj) {
+            const double g = seed * (z_sq - n_total) * inv_s;      // normal.hpp:273, 365
+            sigma_adj[0] = overwrite ? g : sigma_adj[0] + g;
+        }
+        if (!mu_vec && mu_adj) {
+            const double g = seed * (partial[2] * inv_s_sq);       // normal.hpp:277-278
+            mu_adj[0] = overwrite ? g : mu_adj[0] + g;
+        }
+    }
+}
+
+static int launch_partial(Context& c, int shape_code, const NormalArgs& a, double* out_partial)
+{
+    const int threads = 256;
+    const int grid = grid_for(c, (a.n + 3) / 4, 8, threads);
+    double* part = c.partials;
+    unsigned int* ticket = c.tickets + 1;
+    switch (shape_code & 3) {
+    case 0: normal_kernel<false, false><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
+    case 1: normal_kernel<true, false><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
+    case 2: normal_kernel<false, true><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
+    case 3: normal_kernel<true, true><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
+    }
+    c.launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+}  // namespace fadb
+
+using namespace fadb;
+
+static int check_normal_args(int shape_code, size_t n, const double* x, const double* mu,
+                             const double* sigma)
+{
+    FADB_REQUIRE(shape_code >= 0 && shape_code <= 3, "normal_lpdf: shape_code must be 0..3");
+    FADB_REQUIRE(n == 0 || (x && mu && sigma), "normal_lpdf: null operand");
+    return FADB_OK;
+}
+
+extern "C" int fadb_sigma_check(size_t n, const double* sigma, double* dev_count)
+{
+    FADB_REQUIRE(dev_count && (n == 0 || sigma), "fadb_sigma_check: null pointer");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    const int threads = 512;
+    const int grid = grid_for(*c, (n + 3) / 4, 4, threads);
+    sigma_check_kernel<<<grid, threads, 0, c->stream>>>(n, sigma, c->partials, c->tickets + 0, dev_count);
+    c->launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+extern "C" int fadb_normal_lpdf_partial(int shape_code, size_t n, const double* x,
+                                        const double* mu, const double* sigma, double* x_adj,
+                                        double* mu_adj, double* sigma_adj, double seed,
+                                        unsigned flags, const double* dev_invalid_in,
+                                        double* dev_partial4)
+{
+    int rc = check_normal_args(shape_code, n, x, mu, sigma);
+    if (rc) return rc;
+    FADB_REQUIRE(dev_partial4 != nullptr, "normal_lpdf_partial: null partial buffer");
+    Context* c;
+    rc = current_context(&c);
+    if (rc) return rc;
+    NormalArgs a{n, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
+                 dev_invalid_in};
+    return launch_partial(*c, shape_code, a, dev_partial4);
+}
+
+extern "C" int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_partial4,
+                                       const double* x, const double* mu, const double* sigma,
+                                       double* x_adj, double* mu_adj, double* sigma_adj,
+                                       double seed, unsigned flags, double* host_value)
+{
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    double* dval = c->scalars + 0;
+    normal_finish_kernel<<<1, 1, 0, c->stream>>>(shape_code, (double)n_total, dev_partial4, x, mu, sigma,
+                                                 x_adj, mu_adj, sigma_adj, seed,
+                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval);
+    c->launches++;
+    FADB_CUDA(cudaGetLastError());
+    if (host_value) {
+        FADB_CUDA(cudaMemcpyAsync(c->host_scalars, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FADB_CUDA(cudaStreamSynchronize(c->stream));
+        *host_value = c->host_scalars[0];
+    }
+    return FADB_OK;
+}
+
+extern "C" int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const double* mu,
+                                const double* sigma, double* x_adj, double* mu_adj,
+                                double* sigma_adj, double seed, unsigned flags, double* host_value)
+{
+    int rc = check_normal_args(shape_code, n, x, mu, sigma);
+    if (rc) return rc;
+    Context* c;
+    rc = current_context(&c);
+    if (rc) return rc;
+    double* partial = c->scalars + 8;     // 4 doubles
+    double* invalid = c->scalars + 12;    // 1 double
+    const bool sig_vec = shape_code & 2;
+    const bool any_adj = x_adj || mu_adj || sigma_adj;
+    const double* invalid_in = nullptr;
+    // A variable OR constant vector sigma must be known valid before adjoints are written.
+    if (sig_vec && any_adj && seed != 0.0 && !(flags & FADB_TRUST_SIGMA)) {
+        rc = fadb_sigma_check(n, sigma, invalid);
+        if (rc) return rc;
+        invalid_in = invalid;
+    }
+    NormalArgs a{n, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
+                 invalid_in};
+    const bool sss = (n == 1 && shape_code == 0);
+    if (sss) {
+        // single element: the epilogue does everything (normal.hpp:141-171)
+        FADB_CUDA(cudaMemsetAsync(partial, 0, 4 * sizeof(double), c->stream));
+        // sigma <= 0 is detected in the epilogue through partial[3]; compute it on device
+        a.x_adj = a.mu_adj = a.sigma_adj = nullptr;
+        rc = launch_partial(*c, shape_code, a, partial);
+        if (rc) return rc;
+        return fadb_normal_lpdf_finish(shape_code, n, partial, x, mu, sigma, x_adj, mu_adj, sigma_adj,
+                                       seed, flags, host_value);
+    }
+    rc = launch_partial(*c, shape_code, a, partial);
+    if (rc) return rc;
+    // vector adjoints are done; scalar operands and the value come from the partial sums
+    return fadb_normal_lpdf_finish(shape_code, n, partial, x, mu, sigma, nullptr, mu_adj, sigma_adj,
+                                   seed, flags, host_value);
+}

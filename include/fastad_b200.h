@@ -1,0 +1,171 @@
+/*
+ * fastad_b200.h — C ABI of libfastad_b200.so: the B200 (sm_100a) implementation of FastAD's
+ * reverse-mode hot path (ad::autodiff = feval + beval over Var/VarView expressions).
+ *
+ * The reference (JamesYang007/FastAD, header-only C++17) has no FFI surface: its hot path
+ * sits behind a C++ template concept (feval/beval/bind_cache).  Each entry point below
+ * names the reference interface it replaces, `file:line` relative to
+ * /root/reference/include/fastad_bits/ .  The C++17 host layer in include/fastad (ad::Var,
+ * ad::bind, ad::autodiff ...) is a thin front-end over this ABI; so is the ctypes
+ * front-end in fastad_b200/__init__.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `double*` below is a DEVICE pointer unless the
+ *     parameter name starts with `host_`;
+ *   - matrices are column-major (value_view.hpp:141-173);
+ *   - adjoints ACCUMULATE (`adj += seed`, var_view.hpp:91-94) unless FADB_OVERWRITE_ADJ;
+ *   - every function returns 0 on success or a negative FADB_ERR_* code; the message is
+ *     available from fadb_last_error() (thread-local).  No C++ exception crosses the ABI;
+ *   - calls are asynchronous on the library stream of the current CUDA device, except
+ *     those that return a host scalar (they synchronise that stream);
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with
+ *     FADB_ERR_CUDA.
+ */
+#ifndef FASTAD_B200_H
+#define FASTAD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FADB_OK 0
+#define FADB_ERR_ARG (-1)
+#define FADB_ERR_CUDA (-2)
+#define FADB_ERR_UNSUPPORTED (-3)
+#define FADB_ERR_STATE (-4)
+
+/* flags */
+#define FADB_OVERWRITE_ADJ 1u  /* adjoint outputs are stored, not accumulated ("fused reset") */
+#define FADB_TRUST_SIGMA 2u    /* caller guarantees sigma > 0: skip the validity pre-pass     */
+
+/* shapes: ad::scl / ad::vec / ad::mat (util/shape_traits.hpp:7-9) */
+enum { FADB_SCL = 0, FADB_VEC = 1, FADB_MAT = 2 };
+
+/* unary functors (reverse/core/unary.hpp:190-296) */
+enum {
+    FADB_NEG = 0, FADB_SIN, FADB_COS, FADB_TAN, FADB_ASIN, FADB_ACOS, FADB_ATAN, FADB_EXP,
+    FADB_LOG, FADB_SQRT, FADB_ERF, FADB_SIGMOID, FADB_SINH, FADB_COSH, FADB_TANH,
+    FADB_UNARY_COUNT,
+    FADB_MOCK2X = 100 /* test functor f(x)=2x (test/testutil/base_fixture.hpp:9-22) */
+};
+/* binary functors (reverse/core/binary.hpp:265-338) */
+enum { FADB_ADD = 0, FADB_SUB, FADB_MUL, FADB_DIV, FADB_BINARY_COUNT,
+       FADB_MOCKB = 100 /* test functor f(x,y)=x-2y (base_fixture.hpp:24-46) */ };
+
+/* ------------------------------------------------------------------ lifecycle / runtime */
+/* Binds the library to the current CUDA device (cudaSetDevice(device)), creates its stream
+ * and workspace.  Idempotent. */
+int fadb_init(int device);
+void fadb_shutdown(void);
+int fadb_device_count(void);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream) for all launches on the
+ * current device; NULL restores the library's own stream. */
+int fadb_set_stream(void* cuda_stream);
+int fadb_sync(void);
+const char* fadb_last_error(void);
+/* number of kernels this library has launched on the current device since fadb_init */
+unsigned long long fadb_launch_count(void);
+const char* fadb_version(void);
+
+/* ------------------------------------------------------------------ value/adjoint storage
+ * Replaces the host-heap value/adjoint storage of Var (var.hpp:23-220), the ExprBind caches
+ * (bind.hpp:38-40) and util::PtrPack (util/ptr_pack.hpp:13-25): buffers now live in HBM.
+ * The caller owns every buffer. */
+int fadb_malloc(size_t nbytes, void** out_dev);
+int fadb_free(void* dev);
+int fadb_h2d(void* dev_dst, const void* host_src, size_t nbytes);
+int fadb_d2h(void* host_dst, const void* dev_src, size_t nbytes);
+int fadb_memset_zero(void* dev, size_t nbytes);           /* reset_adj(), value_adj_view.hpp:57 */
+int fadb_host_alloc_pinned(size_t nbytes, void** out_host);
+int fadb_host_free_pinned(void* host);
+
+/* ------------------------------------------------------------------ K1: Black-Scholes
+ * The expression of example/black_scholes.cpp:16-39 (call and put, each bound and
+ * autodiff'ed as in :43-70) evaluated for n independent options, S/sigma/r as variables:
+ * forward pass + adjoint sweep in registers, SoA in / SoA out.
+ * out[8] = call, put, dcall/dS, dcall/dsigma, dcall/dr, dput/dS, dput/dsigma, dput/dr.
+ * Prices are stored; the six adjoints accumulate unless FADB_OVERWRITE_ADJ. */
+int fadb_black_scholes(size_t n, const double* S, const double* K, const double* sigma,
+                       const double* tau, const double* r, double* const out[8],
+                       unsigned flags);
+/* Same call through HOST buffers (host↔device copies inside, chunked and overlapped). */
+int fadb_black_scholes_host(size_t n, const double* host_S, const double* host_K,
+                            const double* host_sigma, const double* host_tau,
+                            const double* host_r, double* const host_out[8]);
+
+/* ------------------------------------------------------------------ K2: sum of a unary map
+ * autodiff of ad::sum(f(x)) for a VarView x (sum.hpp:129-203 over unary.hpp:32-120 /
+ * pow.hpp:67-196): value = sum_i f(x_i); x_adj_i += seed * f'(x_i); one pass.
+ * op = FADB_* unary code, or 1000+n for pow<n>.  *host_value receives the value. */
+int fadb_sum_unary(int op, size_t n, const double* x, double* x_adj, double seed,
+                   unsigned flags, double* host_value);
+/* same, value left in a device double (no host synchronisation) */
+int fadb_sum_unary_async(int op, size_t n, const double* x, double* x_adj, double seed,
+                         unsigned flags, double* dev_value);
+
+/* ------------------------------------------------------------------ K3: product
+ * autodiff of ad::prod(x) (prod.hpp:143-245) including the exact-zero cases. */
+int fadb_prod(size_t n, const double* x, double* x_adj, double seed, unsigned flags,
+              double* host_value);
+
+/* ------------------------------------------------------------------ K4: normal log-pdf
+ * autodiff of ad::normal_adj_log_pdf(x, mu, sigma) with leaf operands
+ * (reverse/stat/normal.hpp:108-578; builder :785-797).
+ *   shape_code: bit0 = mu is a vector, bit1 = sigma is a vector (x is a vector of n;
+ *               n == 1 with shape_code 0 is the sss case);
+ *   an operand is a CONSTANT (no adjoint) iff its *_adj pointer is NULL;
+ *   scalar mu/sigma are device scalars; their adjoints are device scalars too.
+ * Returns -inf in *host_value and leaves all adjoints untouched when any sigma <= 0
+ * (normal.hpp:147,160,440-442,457). */
+int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const double* mu,
+                     const double* sigma, double* x_adj, double* mu_adj, double* sigma_adj,
+                     double seed, unsigned flags, double* host_value);
+/* Multi-GPU building blocks (element-range shards).  Vector adjoints only need
+ * the seed, so each shard runs the same fused pass; what must cross GPUs are the partial sums
+ * dev_partial4 = {sum d^2 | z^2, sum log sigma_i, sum d | d/sigma_i^2, #sigma<=0}:
+ *   [fadb_sigma_check -> all-reduce count]   (vector sigma only, for the no-adjoint-on-invalid rule)
+ *   fadb_normal_lpdf_partial                 (fused value sums + vector adjoints of the shard)
+ *   all-reduce dev_partial4 (ncclSum)        (the caller's collective)
+ *   fadb_normal_lpdf_finish                  (value + adjoints of scalar operands, n_total global)
+ * fadb_normal_lpdf is exactly this chain on one device. */
+int fadb_sigma_check(size_t n, const double* sigma, double* dev_count);
+int fadb_normal_lpdf_partial(int shape_code, size_t n, const double* x, const double* mu,
+                             const double* sigma, double* x_adj, double* mu_adj,
+                             double* sigma_adj, double seed, unsigned flags,
+                             const double* dev_invalid_in, double* dev_partial4);
+int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_partial4,
+                            const double* x, const double* mu, const double* sigma,
+                            double* x_adj, double* mu_adj, double* sigma_adj, double seed,
+                            unsigned flags, double* host_value);
+
+/* ------------------------------------------------------------------ K5: regression
+ * autodiff of normal_adj_log_pdf(y, dot(X, w), sigma) (dot.hpp:54-129 feeding
+ * normal.hpp:304-372): X rows x cols column-major constant, y constant, w variable vector,
+ * sigma variable scalar.  One pass over X computes r = y - Xw, sum r^2 and X^T r.
+ * Row shards: fadb_linreg_partial -> all-reduce (cols+1 doubles: {sum r^2, X^T r}) ->
+ * fadb_linreg_finish with the global row count. */
+int fadb_linreg_partial(size_t rows, size_t cols, const double* X, const double* y,
+                        const double* w, double* dev_partial);
+int fadb_linreg_finish(size_t rows_total, size_t cols, const double* dev_partial,
+                       const double* sigma, double* w_adj, double* sigma_adj, double seed,
+                       unsigned flags, double* host_value);
+int fadb_linreg_nll(size_t rows, size_t cols, const double* X, const double* y,
+                    const double* w, double* w_adj, const double* sigma, double* sigma_adj,
+                    double seed, unsigned flags, double* host_value);
+
+/* ------------------------------------------------------------------ K6: 3-layer network
+ * The expression of README.md:676-726 / example/ceres_3layer_neural_net/src.cpp:38-40
+ * (2->3->3->1 with jump connection, squared error), summed over `batch` rows with the 25
+ * parameter adjoints accumulated (the per-row loop of src.cpp:48-55 as one launch).
+ * X is batch x 2 column-major, parm/grad are 25 device doubles. */
+int fadb_mlp3(size_t batch, const double* X, const double* y, const double* parm,
+              double* grad, unsigned flags, double* host_loss);
+int fadb_mlp3_async(size_t batch, const double* X, const double* y, const double* parm,
+                    double* grad, unsigned flags, double* dev_loss);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTAD_B200_H */

@@ -835,11 +835,12 @@ void parallel_ranges(size_t n, int nthreads, F&& f)
 }
 
 /* The Black-Scholes expression of example/black_scholes.cpp:16-39 over vec leaves.
- * S, sigma, r are variables (so delta/vega/rho exist); K, tau are constant views. */
+ * S, sigma, r are variables (so delta/vega/rho exist); K, tau and sqrt(tau) are constant
+ * views (the example computes std::sqrt(tau) on the host as a plain double, :28-30). */
 struct BSGraph {
     orc_graph* g;
-    int S, K, sigma, tau, r, c0, c1, c2, call_root, put_root;
-    std::vector<double> c0v, c0a, c1v, c1a, c2v, c2a;
+    int S, K, sigma, tau, sqrt_tau, r, c0, c1, c2, root;
+    std::vector<double> c0v, c0a, c1v, c1a, c2v, c2a, sq;
     size_t cap;
 
     int phi(int x)
@@ -848,38 +849,46 @@ struct BSGraph {
         return orc_binary(g, ORC_MUL, orc_const_scalar(g, 0.5),
                           orc_binary(g, ORC_ADD, e, orc_const_scalar(g, 1.)));
     }
-    int common()
-    {
-        int half = orc_const_scalar(g, 2.);
-        int sqrt_tau = orc_unary(g, ORC_SQRT, tau);   /* folded: tau is constant */
-        int e0 = orc_eq(g, c0, orc_unary(g, ORC_LOG, orc_binary(g, ORC_DIV, S, K)));
-        int drift = orc_binary(g, ORC_MUL,
-                        orc_binary(g, ORC_ADD, r,
-                            orc_binary(g, ORC_DIV, orc_binary(g, ORC_MUL, sigma, sigma), half)),
-                        tau);
-        int sst = orc_binary(g, ORC_MUL, sigma, sqrt_tau);
-        int e1 = orc_eq(g, c1, orc_binary(g, ORC_DIV, orc_binary(g, ORC_ADD, c0, drift), sst));
-        int sst2 = orc_binary(g, ORC_MUL, sigma, sqrt_tau);
-        int e2 = orc_eq(g, c2, orc_binary(g, ORC_SUB, c1, sst2));
-        return orc_glue(g, orc_glue(g, e0, e1), e2);
-    }
-    int pv()
-    {   /* PV = K * exp(-r * tau) with r a variable */
-        return orc_binary(g, ORC_MUL, K,
-                   orc_unary(g, ORC_EXP, orc_binary(g, ORC_MUL, orc_unary(g, ORC_NEG, r), tau)));
-    }
-    explicit BSGraph(size_t chunk) : cap(chunk)
+    BSGraph(size_t chunk, bool put) : cap(chunk)
     {
         g = orc_new();
         c0v.resize(cap); c0a.resize(cap); c1v.resize(cap); c1a.resize(cap); c2v.resize(cap); c2a.resize(cap);
+        sq.resize(cap);
         S = orc_var(g, ORC_VEC, cap, 1, nullptr, nullptr);
         sigma = orc_var(g, ORC_VEC, cap, 1, nullptr, nullptr);
         r = orc_var(g, ORC_VEC, cap, 1, nullptr, nullptr);
         K = orc_const_view(g, ORC_VEC, cap, 1, nullptr);
         tau = orc_const_view(g, ORC_VEC, cap, 1, nullptr);
+        sqrt_tau = orc_const_view(g, ORC_VEC, cap, 1, sq.data());
         c0 = orc_var(g, ORC_VEC, cap, 1, c0v.data(), c0a.data());
         c1 = orc_var(g, ORC_VEC, cap, 1, c1v.data(), c1a.data());
         c2 = orc_var(g, ORC_VEC, cap, 1, c2v.data(), c2a.data());
+        /* node construction never dereferences a non-constant leaf, and no constant-constant
+         * pair is combined below, so the views can be (re)bound afterwards */
+        int two = orc_const_scalar(g, 2.);
+        int e0 = orc_eq(g, c0, orc_unary(g, ORC_LOG, orc_binary(g, ORC_DIV, S, K)));
+        int drift = orc_binary(g, ORC_MUL,
+                        orc_binary(g, ORC_ADD, r,
+                            orc_binary(g, ORC_DIV, orc_binary(g, ORC_MUL, sigma, sigma), two)),
+                        tau);
+        int e1 = orc_eq(g, c1, orc_binary(g, ORC_DIV, orc_binary(g, ORC_ADD, c0, drift),
+                                          orc_binary(g, ORC_MUL, sigma, sqrt_tau)));
+        int e2 = orc_eq(g, c2, orc_binary(g, ORC_SUB, c1, orc_binary(g, ORC_MUL, sigma, sqrt_tau)));
+        int common = orc_glue(g, orc_glue(g, e0, e1), e2);
+        /* PV = K * exp(-r * tau) with r a variable */
+        int pv = orc_binary(g, ORC_MUL, K,
+                     orc_unary(g, ORC_EXP, orc_binary(g, ORC_MUL, orc_unary(g, ORC_NEG, r), tau)));
+        if (!put) {         /* Phi(c1)*S - Phi(c2)*PV */
+            root = orc_glue(g, common,
+                orc_binary(g, ORC_SUB, orc_binary(g, ORC_MUL, phi(c1), S),
+                                       orc_binary(g, ORC_MUL, phi(c2), pv)));
+        } else {            /* Phi(-c2)*PV - Phi(-c1)*S */
+            root = orc_glue(g, common,
+                orc_binary(g, ORC_SUB,
+                    orc_binary(g, ORC_MUL, phi(orc_unary(g, ORC_NEG, c2)), pv),
+                    orc_binary(g, ORC_MUL, phi(orc_unary(g, ORC_NEG, c1)), S)));
+        }
+        orc_bind(g, root, nullptr);
     }
     ~BSGraph() { orc_free(g); }
 };
@@ -892,45 +901,41 @@ void orc_black_scholes(size_t n, const double* S, const double* K, const double*
                        const double* tau, const double* r, double* const out[8], int nthreads)
 {
     /* out: call, put, dcall/dS, dcall/dsigma, dcall/dr, dput/dS, dput/dsigma, dput/dr */
-    const size_t CH = 2048;  /* chunk stays L1/L2 resident: the best way to batch the reference */
+    const size_t CH = 1024;  /* chunk stays cache resident: the best way to batch the reference */
     parallel_ranges(n, nthreads, [&](int, size_t b, size_t e) {
         std::vector<double> ones(CH, 1.0);
-        for (size_t off = b; off < e; off += CH) {
+        size_t off = b;
+        while (off < e) {
             const size_t m = std::min(CH, e - off);
-            for (int which = 0; which < 2; ++which) {
-                /* A fresh expression per (chunk, option type): tau-dependent constants are
-                 * folded at construction like the reference does (unary.hpp:182-184). */
-                BSGraph bs(m);
-                orc_graph* g = bs.g;
-                double* dS = out[which ? 5 : 2] + off;
-                double* dsg = out[which ? 6 : 3] + off;
-                double* dr = out[which ? 7 : 4] + off;
-                std::memset(dS, 0, m * sizeof(double));
-                std::memset(dsg, 0, m * sizeof(double));
-                std::memset(dr, 0, m * sizeof(double));
-                orc_rebind(g, bs.S, const_cast<double*>(S + off), dS, m, 1);
-                orc_rebind(g, bs.sigma, const_cast<double*>(sigma + off), dsg, m, 1);
-                orc_rebind(g, bs.r, const_cast<double*>(r + off), dr, m, 1);
-                orc_rebind(g, bs.K, const_cast<double*>(K + off), nullptr, m, 1);
-                orc_rebind(g, bs.tau, const_cast<double*>(tau + off), nullptr, m, 1);
-                int common = bs.common();
-                int pv = bs.pv();
-                int root;
-                if (which == 0) {   /* Phi(c1)*S - Phi(c2)*PV */
-                    root = orc_glue(g, common,
-                        orc_binary(g, ORC_SUB, orc_binary(g, ORC_MUL, bs.phi(bs.c1), bs.S),
-                                               orc_binary(g, ORC_MUL, bs.phi(bs.c2), pv)));
-                } else {            /* Phi(-c2)*PV - Phi(-c1)*S */
-                    root = orc_glue(g, common,
-                        orc_binary(g, ORC_SUB,
-                            orc_binary(g, ORC_MUL, bs.phi(orc_unary(g, ORC_NEG, bs.c2)), pv),
-                            orc_binary(g, ORC_MUL, bs.phi(orc_unary(g, ORC_NEG, bs.c1)), bs.S)));
+            /* one bound expression per option type, reused for every full chunk
+             * (ad::bind once, autodiff many times) */
+            BSGraph call(m, false), put(m, true);
+            for (; off + m <= e; off += m) {
+                for (int which = 0; which < 2; ++which) {
+                    BSGraph& bs = which ? put : call;
+                    orc_graph* g = bs.g;
+                    double* dS = out[which ? 5 : 2] + off;
+                    double* dsg = out[which ? 6 : 3] + off;
+                    double* dr = out[which ? 7 : 4] + off;
+                    std::memset(dS, 0, m * sizeof(double));
+                    std::memset(dsg, 0, m * sizeof(double));
+                    std::memset(dr, 0, m * sizeof(double));
+                    std::memset(bs.c0a.data(), 0, m * sizeof(double));   /* reset_adj() */
+                    std::memset(bs.c1a.data(), 0, m * sizeof(double));
+                    std::memset(bs.c2a.data(), 0, m * sizeof(double));
+                    for (size_t i = 0; i < m; ++i) bs.sq[i] = std::sqrt(tau[off + i]);
+                    orc_rebind(g, bs.S, const_cast<double*>(S + off), dS, m, 1);
+                    orc_rebind(g, bs.sigma, const_cast<double*>(sigma + off), dsg, m, 1);
+                    orc_rebind(g, bs.r, const_cast<double*>(r + off), dr, m, 1);
+                    orc_rebind(g, bs.K, const_cast<double*>(K + off), nullptr, m, 1);
+                    orc_rebind(g, bs.tau, const_cast<double*>(tau + off), nullptr, m, 1);
+                    const double* v = orc_feval(g, bs.root);
+                    std::memcpy(out[which] + off, v, m * sizeof(double));
+                    orc_beval(g, bs.root, 0., ones.data());
                 }
-                orc_bind(g, root, nullptr);
-                const double* v = orc_feval(g, root);
-                std::memcpy(out[which] + off, v, m * sizeof(double));
-                orc_beval(g, root, 0., ones.data());
+                if (m < CH) break;
             }
+            if (m < CH) { off = e; }
         }
     });
 }

@@ -1,0 +1,384 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+reference's golden vectors.  Run with `-m gpu` on a B200.
+
+Tolerances (BASELINE.json north_star):
+  * arithmetic-only per-element adjoints (+,-,*,/ are IEEE on both sides, kernels built
+    -fmad=false): BIT-EXACT;
+  * per-instance results through libdevice transcendentals (exp/log/erf, <=1-2 ulp vs glibc):
+    <= 4 ulp, plus a conditioning floor where the expression subtracts nearly equal terms;
+  * reordered reductions: <= 1e-12 relative.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import kats
+import oracle_py as O
+import synth
+from kats import assert_double_eq
+
+pytestmark = pytest.mark.gpu
+
+REL_REDUCE = 1e-12
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    import fastad_b200 as F
+    F.load()
+    F.check(F.lib().fadb_init(0))
+    F.use_torch_stream()
+    return F
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def zeros(n):
+    import torch
+    return torch.zeros(n, dtype=torch.float64, device="cuda")
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+# ------------------------------------------------------------------ K4 normal log-pdf
+def _normal_case(fb, kind, x, mu, sg, const_x=False, const_mu=False, const_sigma=False, seed=1.0,
+                 flags=0, adj0=None):
+    """Runs GPU and oracle on the same inputs; returns ((v, xa, ma, sa) gpu, same oracle)."""
+    x, mu, sg = np.atleast_1d(x), np.atleast_1d(mu), np.atleast_1d(sg)
+    init = (lambda n: np.zeros(n)) if adj0 is None else (lambda n: adj0(n))
+    xa0, ma0, sa0 = init(len(x)), init(len(mu)), init(len(sg))
+    dx, dm, ds = dev(x), dev(mu), dev(sg)
+    gxa = None if const_x else dev(xa0)
+    gma = None if const_mu else dev(ma0)
+    gsa = None if const_sigma else dev(sa0)
+    v = fb.normal_lpdf(dx, dm, ds, gxa, gma, gsa, seed=seed, flags=flags)
+    oxa = None if const_x else xa0.copy()
+    oma = None if const_mu else ma0.copy()
+    osa = None if const_sigma else sa0.copy()
+    ov = O.normal_lpdf(x, mu if len(mu) > 1 else mu, sg, oxa, oma, osa, seed=seed)
+    g = (v, None if gxa is None else host(gxa), None if gma is None else host(gma),
+         None if gsa is None else host(gsa))
+    return g, (ov, oxa, oma, osa)
+
+
+@pytest.mark.parametrize("kind", ["sss", "vss", "vvs", "vsv", "vvv"])
+def test_normal_reference_goldens(fb, kind):
+    # test/reverse/stat/normal_unittest.cpp:105-297 (EXPECT_DOUBLE_EQ = 4 ulp)
+    val, xa, ma, sa = kats.NORMAL_KAT[kind]
+    x = kats.N_VX if kind[0] == "v" else kats.N_X
+    mu = kats.N_VMU if kind[1] == "v" else kats.N_MU
+    sg = kats.N_VSIGMA if kind[2] == "v" else kats.N_SIGMA
+    g, o = _normal_case(fb, kind, x, mu, sg)
+    assert_double_eq([g[0]], [val], what=kind + " value")
+    assert_double_eq(g[1], xa, what=kind + " x_adj")
+    assert_double_eq(g[2], ma, what=kind + " mu_adj")
+    assert_double_eq(g[3], sa, what=kind + " sigma_adj")
+
+
+def test_normal_constant_operands(fb):
+    # normal_unittest.cpp:151-172, 237-257
+    val, _, ma, sa = kats.NORMAL_KAT["vss"]
+    g, _ = _normal_case(fb, "vss", kats.N_VX, kats.N_MU, kats.N_SIGMA, const_x=True)
+    assert_double_eq([g[0]], [val]); assert_double_eq(g[2], ma); assert_double_eq(g[3], sa)
+    val, _, ma, _ = kats.NORMAL_KAT["vsv"]
+    g, _ = _normal_case(fb, "vsv", kats.N_VX, kats.N_MU, kats.N_VSIGMA, const_x=True, const_sigma=True)
+    assert_double_eq([g[0]], [val]); assert_double_eq(g[2], ma)
+
+
+@pytest.mark.parametrize("kind,bad", [("vsv", -1.0), ("vvv", 0.0), ("vss", 0.0), ("vvs", -2.0), ("sss", 0.0)])
+def test_normal_invalid_sigma(fb, kind, bad):
+    # normal_unittest.cpp:207-213, 266-272: value -inf; normal.hpp:160,457: no adjoint update
+    n = 1000 if kind != "sss" else 1
+    x, mu, sg = synth.normal_inputs(n)
+    mu = mu if kind[1] == "v" else mu[:1]
+    sg = sg.copy() if kind[2] == "v" else sg[:1].copy()
+    sg[len(sg) // 2] = bad
+    g, o = _normal_case(fb, kind, x, mu, sg, adj0=lambda m: np.full(m, 0.25))
+    assert g[0] == -math.inf and o[0] == -math.inf
+    for a in g[1:]:
+        assert np.all(a == 0.25)
+
+
+@pytest.mark.parametrize("kind", ["vss", "vvs", "vsv", "vvv"])
+@pytest.mark.parametrize("n", [5, 1 << 10, (1 << 20) + 3])
+def test_normal_vs_oracle(fb, kind, n):
+    x, mu, sg = synth.normal_inputs(n)
+    mu = mu if kind[1] == "v" else mu[:1]
+    sg = sg if kind[2] == "v" else sg[:1]
+    g, o = _normal_case(fb, kind, x, mu, sg, seed=0.75, adj0=lambda m: np.linspace(-1, 1, m))
+    assert rel(g[0], o[0]) <= REL_REDUCE
+    # vector adjoints: arithmetic only -> bit exact; scalar adjoints: reductions -> 1e-12
+    for ga, oa in zip(g[1:], o[1:]):
+        if len(oa) == n:
+            np.testing.assert_array_equal(ga, oa)
+        else:
+            assert rel(ga[0], oa[0]) <= REL_REDUCE
+
+
+def test_normal_overwrite_and_trust_flags(fb):
+    n = 4099
+    x, mu, sg = synth.normal_inputs(n)
+    g0, o = _normal_case(fb, "vvv", x, mu, sg)
+    g1, _ = _normal_case(fb, "vvv", x, mu, sg, flags=fb.OVERWRITE_ADJ | fb.TRUST_SIGMA,
+                         adj0=lambda m: np.full(m, 123.0))
+    for a, b in zip(g0[1:], g1[1:]):
+        np.testing.assert_array_equal(a, b)
+    assert g0[0] == g1[0]
+
+
+def test_normal_seed_zero_is_noop_on_adjoints(fb):
+    x, mu, sg = synth.normal_inputs(100)
+    g, o = _normal_case(fb, "vvv", x, mu, sg, seed=0.0, adj0=lambda m: np.full(m, 2.0))
+    assert rel(g[0], o[0]) <= REL_REDUCE
+    for a in g[1:]:
+        assert np.all(a == 2.0)
+
+
+def test_normal_unaligned_and_empty(fb):
+    import torch
+    n = 1001
+    x, mu, sg = synth.normal_inputs(n + 1)
+    bx, bm, bs = dev(x), dev(mu), dev(sg)
+    xa, ma, sa = zeros(n + 1), zeros(n + 1), zeros(n + 1)
+    v = fb.normal_lpdf(bx[1:], bm[1:], bs[1:], xa[1:], ma[1:], sa[1:])   # 8-byte aligned only
+    oxa, oma, osa = np.zeros(n), np.zeros(n), np.zeros(n)
+    ov = O.normal_lpdf(x[1:].copy(), mu[1:].copy(), sg[1:].copy(), oxa, oma, osa)
+    assert rel(v, ov) <= REL_REDUCE
+    np.testing.assert_array_equal(host(xa)[1:], oxa)
+    np.testing.assert_array_equal(host(sa)[1:], osa)
+    e = torch.zeros(0, dtype=torch.float64, device="cuda")
+    one = dev([1.0])
+    assert fb.normal_lpdf(e, one, one, None, zeros(1), zeros(1)) == 0.0
+
+
+# ------------------------------------------------------------------ K2 sum of unary maps
+@pytest.mark.parametrize("op", ["exp", "log", "sqrt", "sin", "cos", "tan", "atan", "erf", "sigmoid",
+                                "sinh", "cosh", "tanh", "neg", ("pow", 2), ("pow", 3), ("pow", 5), ("pow", -2)])
+def test_sum_unary_vs_oracle(fb, op):
+    n = (1 << 16) + 5
+    x = synth.sum_inputs(n)
+    gx, ga = dev(x), dev(np.full(n, 0.5))
+    v = fb.sum_unary(op, gx, ga, seed=1.5)
+    oa = np.full(n, 0.5)
+    ov = O.sum_unary(op, x, oa, seed=1.5)
+    assert rel(v, ov) <= REL_REDUCE
+    # per-element adjoints: <= 4 ulp of the increment (libdevice vs glibc), bit-exact for pow/neg
+    inc_g, inc_o = host(ga) - 0.5, oa - 0.5
+    if isinstance(op, tuple) and op[1] in (2, 3) or op == "neg":
+        np.testing.assert_array_equal(host(ga), oa)
+    else:
+        tol = 4 * np.spacing(np.abs(inc_o)) + 2 * np.spacing(0.5 + np.abs(inc_o))
+        assert np.all(np.abs(inc_g - inc_o) <= tol), np.max(np.abs(inc_g - inc_o) / tol)
+
+
+@pytest.mark.parametrize("op", ["asin", "acos"])
+def test_sum_unary_inverse_trig(fb, op):
+    n = 4097
+    x = np.linspace(-0.95, 0.95, n)
+    gx, ga = dev(x), zeros(n)
+    v = fb.sum_unary(op, gx, ga)
+    oa = np.zeros(n)
+    ov = O.sum_unary(op, x, oa)
+    assert abs(v - ov) <= 1e-12 * max(1.0, np.abs(np.arcsin(x)).sum())
+    np.testing.assert_array_equal(host(ga), oa)     # seed/sqrt(1-x*x): arithmetic only
+
+
+def test_sum_fixture_vector_and_erf_kat(fb):
+    # unary_unittest.cpp:320-324 (erf KAT); fixture vector base_fixture.hpp:109-115
+    x0, f, df = kats.ERF_KAT
+    gx, ga = dev([x0]), zeros(1)
+    v = fb.sum_unary("erf", gx, ga, seed=3.14)
+    assert_double_eq([v], [f])
+    assert_double_eq(host(ga), [3.14 * df])
+    gx, ga = dev(kats.FIX_VEC), zeros(5)
+    v = fb.sum_unary(("pow", 2), gx, ga)
+    assert_double_eq([v], [float((kats.FIX_VEC ** 2).sum())])
+    assert_double_eq(host(ga), 2 * kats.FIX_VEC)
+
+
+def test_sum_full_size_properties(fb):
+    # BASELINE config 2 size (N = 2^24): linearity in the seed and accumulate semantics
+    n = 1 << 24
+    x = synth.sum_inputs(n)
+    gx, ga = dev(x), zeros(n)
+    v1 = fb.sum_unary("exp", gx, ga, seed=1.0)
+    a1 = ga.clone()
+    v2 = fb.sum_unary("exp", gx, ga, seed=1.0)          # second sweep doubles (eval_unittest.cpp:37-42)
+    assert v1 == v2
+    assert bool((ga == 2 * a1).all())
+    ref = float(np.exp(x).sum())
+    assert rel(v1, ref) <= REL_REDUCE
+    assert_double_eq(host(a1)[:4096], np.exp(x[:4096]), ulps=2)
+
+
+# ------------------------------------------------------------------ K3 prod
+@pytest.mark.parametrize("zeros_at", [[], [3], [3, 7]])
+def test_prod_vs_oracle(fb, zeros_at):
+    n = 300
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0.9, 1.1, n) * rng.choice([-1.0, 1.0], n)
+    for z in zeros_at:
+        x[z] = 0.0
+    gx, ga = dev(x), dev(np.ones(n))
+    v = fb.prod(gx, ga, seed=2.0)
+    e = O.OracleExpr()
+    xv = e.var(x)
+    e.adj(xv)[:] = 1.0
+    e.bind(e.prod(xv))
+    ov = e.autodiff(2.0)[0]
+    assert rel(v, ov) <= REL_REDUCE if ov != 0 else v == 0
+    np.testing.assert_allclose(host(ga), e.adj(xv), rtol=1e-12, atol=0)
+
+
+def test_prod_fixture_zero(fb):
+    # base_fixture.hpp:113 has an exact zero; prod.hpp:197-207
+    gx, ga = dev(kats.FIX_VEC), zeros(5)
+    v = fb.prod(gx, ga, seed=2.0)
+    assert v == 0.0
+    others = np.prod(np.delete(kats.FIX_VEC, 3))
+    np.testing.assert_allclose(host(ga), [0, 0, 0, 2.0 * others, 0], rtol=1e-15)
+
+
+# ------------------------------------------------------------------ K1 Black-Scholes
+def _bs_tol(inp, ref_out):
+    S, K, sig, tau, r = (inp[k] for k in ("S", "K", "sigma", "tau", "r"))
+    scale_price = np.maximum(S, K)
+    sst = sig * np.sqrt(tau)
+    # conditioning floors: prices subtract Phi1*S - Phi2*PV; the AD delta carries the residual
+    # (S*phi(d1) - PV*phi(d2)) / (S*sst); vega and rho scale with S*sqrt(tau) and K*tau.
+    floors = [1e-13 * scale_price, 1e-13 * scale_price,
+              1e-13 / sst, 1e-13 * scale_price * np.sqrt(tau) / sst, 1e-13 * K * tau / sst + 1e-13 * K * tau,
+              1e-13 / sst, 1e-13 * scale_price * np.sqrt(tau) / sst, 1e-13 * K * tau / sst + 1e-13 * K * tau]
+    return [4 * np.spacing(np.abs(o)) + f for o, f in zip(ref_out, floors)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 1001, 1 << 16])
+def test_black_scholes_vs_oracle(fb, n):
+    inp = synth.black_scholes_inputs(n)
+    ref = O.black_scholes(inp["S"], inp["K"], inp["sigma"], inp["tau"], inp["r"], nthreads=4)
+    out = fb.black_scholes(*(dev(inp[k]) for k in ("S", "K", "sigma", "tau", "r")))
+    for name, g, o, tol in zip(["call", "put", "dC/dS", "dC/dsig", "dC/dr", "dP/dS", "dP/dsig", "dP/dr"],
+                               out, ref, _bs_tol(inp, ref)):
+        err = np.abs(host(g) - o)
+        assert np.all(err <= tol), (name, float(np.max(err / tol)), int(np.argmax(err / tol)))
+
+
+def test_black_scholes_example_point(fb):
+    # example/black_scholes.cpp:43-70 inputs; closed form in SURVEY.md §6
+    p = kats.BS_POINT
+    out = fb.black_scholes(*(dev([p[k]]) for k in ("S", "K", "sigma", "tau", "r")))
+    k = kats.BS_KAT
+    want = [k["call"], k["put"], k["delta_call"], k["vega"], k["rho_call"], k["delta_put"], k["vega"], k["rho_put"]]
+    for g, w in zip(out, want):
+        assert abs(host(g)[0] - w) <= 1.6e-13 * max(1.0, abs(w)), (host(g)[0], w)
+
+
+def test_black_scholes_accumulate_and_host_entry(fb):
+    n = 3001
+    inp = synth.black_scholes_inputs(n)
+    d = [dev(inp[k]) for k in ("S", "K", "sigma", "tau", "r")]
+    out1 = fb.black_scholes(*d)
+    out2 = [o.clone() for o in out1]
+    fb.black_scholes(*d, out=out2, flags=0)                # accumulate: greeks double, prices stored
+    for k in range(2):
+        assert bool((out2[k] == out1[k]).all())
+    for k in range(2, 8):
+        assert bool((out2[k] == 2 * out1[k]).all())
+    hout = [np.zeros(n) for _ in range(8)]
+    fb.black_scholes_host(inp["S"], inp["K"], inp["sigma"], inp["tau"], inp["r"], hout)
+    for h, g in zip(hout, out1):
+        np.testing.assert_array_equal(h, host(g))
+
+
+def test_black_scholes_full_size_put_call_parity(fb):
+    # BASELINE config 1 size: 2^20 options; size-independent property C - P = S - PV
+    n = 1 << 20
+    inp = synth.black_scholes_inputs(n)
+    out = fb.black_scholes(*(dev(inp[k]) for k in ("S", "K", "sigma", "tau", "r")))
+    call, put = host(out[0]), host(out[1])
+    pv = inp["K"] * np.exp(-inp["r"] * inp["tau"])
+    assert np.max(np.abs((call - put) - (inp["S"] - pv))) <= 1e-11
+    dS_c, dS_p = host(out[2]), host(out[5])
+    assert np.max(np.abs(dS_c - dS_p - 1.0)) <= 1e-11     # delta_call - delta_put = 1
+    assert np.max(np.abs(host(out[3]) - host(out[6]))) == 0.0   # vega identical by construction
+
+
+# ------------------------------------------------------------------ K5 regression
+@pytest.mark.parametrize("rows,cols", [(5, 2), (1000, 64), (4097, 64), (777, 7), (300, 130)])
+def test_linreg_vs_oracle(fb, rows, cols):
+    import torch
+    if (rows, cols) == (5, 2):
+        X, y, w = np.asfortranarray(kats.LINREG_X), kats.LINREG_Y.copy(), kats.LINREG_THETA.copy()
+    else:
+        X, y, w_true = synth.linreg_inputs(rows, cols)
+        w = w_true + 0.01
+    sg = np.array([1.3])
+    gX = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()    # (cols, rows) C-order == col-major
+    gw_adj, gs_adj = zeros(cols), zeros(1)
+    v = fb.linreg_nll(gX, dev(y), dev(w), gw_adj, dev(sg), gs_adj, seed=1.0)
+    owa, osa = np.zeros(cols), np.zeros(1)
+    ov = O.linreg(X, y, w, owa, sg, osa)
+    assert rel(v, ov) <= REL_REDUCE
+    np.testing.assert_allclose(host(gw_adj), owa, rtol=1e-11, atol=1e-9 * np.abs(owa).max())
+    assert rel(host(gs_adj)[0], osa[0]) <= 1e-11
+
+
+def test_linreg_readme_golden(fb):
+    # README.md:623-662: loss 6655, adj [-1210, -12100]; here as -0.5*loss at sigma=1
+    import torch
+    gX = torch.from_numpy(np.ascontiguousarray(kats.LINREG_X.T)).cuda()
+    wa, sa = zeros(2), zeros(1)
+    v = fb.linreg_nll(gX, dev(kats.LINREG_Y), dev(kats.LINREG_THETA), wa, dev([1.0]), sa)
+    assert_double_eq([v], [-0.5 * kats.LINREG_LOSS])
+    assert_double_eq(host(wa), -0.5 * kats.LINREG_ADJ)
+
+
+# ------------------------------------------------------------------ K6 network
+def test_mlp3_mathematica_goldens(fb):
+    import torch
+    gX = torch.from_numpy(np.ascontiguousarray(kats.NN_X.T)).cuda()
+    grad = zeros(25)
+    loss = fb.mlp3(gX, dev(kats.NN_Y), dev(kats.NN_PARM), grad)
+    g = host(grad)
+    assert rel(loss, 92030.04305391687) <= REL_REDUCE
+    assert rel(g[0], kats.NN_GRAD_A1_11) <= REL_REDUCE      # GenTestData.nb:691-700
+    assert rel(g[3], kats.NN_GRAD_A1_12) <= REL_REDUCE
+
+
+@pytest.mark.parametrize("batch", [1, 257, 1 << 16])
+def test_mlp3_vs_oracle(fb, batch):
+    import torch
+    X, y = synth.mlp3_inputs(batch)
+    gX = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    grad = zeros(25)
+    loss = fb.mlp3(gX, dev(y), dev(kats.NN_PARM), grad)
+    og = np.zeros(25)
+    ol = O.mlp3(X, y, kats.NN_PARM.copy(), og, nthreads=4)
+    assert rel(loss, ol) <= REL_REDUCE
+    np.testing.assert_allclose(host(grad), og, rtol=1e-10, atol=1e-12 * np.abs(og).max())
+
+
+# ------------------------------------------------------------------ ABI behaviour
+def test_error_reporting(fb):
+    import ctypes as C
+    L = fb.lib()
+    v = C.c_double()
+    rc = L.fadb_sum_unary(12345, 4, None, None, 1.0, 0, C.byref(v))
+    assert rc == -1 and b"fadb_sum_unary" in L.fadb_last_error()
+    rc = L.fadb_normal_lpdf(9, 4, None, None, None, None, None, None, 1.0, 0, C.byref(v))
+    assert rc == -1
+    before = L.fadb_launch_count()
+    fb.sum_unary("exp", dev([1.0, 2.0]), zeros(2))
+    assert L.fadb_launch_count() == before + 1
