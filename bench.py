@@ -221,14 +221,14 @@ def run_ours(args):
         d_in, d_out, _ = sets[i % nsets]
         F.black_scholes(*d_in, out=d_out, flags=F.OVERWRITE_ADJ)
 
+    clk = ClockSampler(local)
+    clk.__enter__()
     launches0 = L.fadb_launch_count()
-    with ClockSampler(local) as clk:
-        ms = timed_loop(bs_step, args.steps, args.warmup, world)
+    ms = timed_loop(bs_step, args.steps, args.warmup, world)
     launches = L.fadb_launch_count() - launches0 - args.warmup
     value = world * n * args.steps / (ms * 1e-3)
     kernel_ms = ms / args.steps                    # one kernel launch per step, back to back
     achieved = BS_BYTES * n / (kernel_ms * 1e-3) / 1e9
-    clocks = clk.summary()
 
     # ---------------- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
     h_in = [torch.from_numpy(sets[0][2][k]).pin_memory() for k in keys]
@@ -260,8 +260,11 @@ def run_ours(args):
         if extra:
             workloads[name].update(extra)
 
-    if not args.quick:
-        steps2 = max(5, min(args.steps, 50))
+    wl = set() if args.quick else set(args.workloads.split(","))
+    steps2 = max(5, min(args.steps, 50))
+    import ctypes as C
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    if "sum" in wl:
         # C2: sum(exp(x)), sum(log(x)), sum(pow<2>(x)); N = 2^24; 24 B/elem (x read + adj RMW)
         n2 = 1 << 24
         xs = [dev(synth.sum_inputs(n2, seed=synth.SEED + s)) for s in range(2)]   # 2 x 128 MiB
@@ -269,7 +272,6 @@ def run_ours(args):
         for op in ("exp", "log", ("pow", 2)):
             code = F._op_code(op)
             dval = zeros(1)
-            import ctypes as C
 
             def step(i, code=code):
                 F.check(L.fadb_sum_unary_async(code, n2, C.c_void_p(xs[i % 2].data_ptr()),
@@ -280,14 +282,12 @@ def run_ours(args):
             add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements")
         del xs, adjs
 
+    if "normal" in wl:
         # C3: normal log-pdf, N = 2^26 per rank.  vvv 72 B/elem; vss (x var) 24; vss (x const) 8
         n3 = 1 << 26
         x, mu, sg = (dev(a) for a in synth.normal_inputs(n3, seed=synth.SEED + rank))
         xa, ma, sa = zeros(n3), zeros(n3), zeros(n3)
         part = zeros(4); inval = zeros(1)
-        import ctypes as C
-        P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        val = C.c_double()
 
         def normal_step(shape, x_adj, mu_t, sg_t, mu_adj, sg_adj, flags=0):
             def step(i):
@@ -317,6 +317,7 @@ def run_ours(args):
         add("normal_vss_xconst_2^26", 8 * n3, t, steps2, n3, "elements")
         del x, mu, sg, xa, ma, sa
 
+    if "linreg" in wl:
         # C4: regression, X 2^20 x 64 column-major; 520 B/row
         rows, cols = 1 << 20, 64
         Xs = []
@@ -334,6 +335,7 @@ def run_ours(args):
         add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows")
         del Xs
 
+    if "mlp3" in wl:
         # C5: 3-layer net, batch 2^16 (configured) and 2^22 (roofline-sized); 24 B/sample
         for b in (1 << 16, 1 << 22):
             Xn, yn = synth.mlp3_inputs(b)
@@ -347,9 +349,12 @@ def run_ours(args):
             add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples",
                 {"bound": "fp64 pipe / launch latency, not HBM"})
 
+    clk.__exit__()
+    clocks = clk.summary()     # sampled over every timed region above (headline first)
+
     # ---------------- CPU baseline beside it (rank 0, bounded sample)
     cpu = None
-    if rank == 0:
+    if rank == 0 and not args.no_cpu:
         import oracle_py as O
         cores = os.cpu_count() or 1
         m = 1 << 20 if not args.quick else 1 << 16
@@ -399,6 +404,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline only, small CPU sample")
+    ap.add_argument("--workloads", default="sum,normal,linreg,mlp3",
+                    help="secondary workloads to time besides the headline (comma list)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -96,7 +96,10 @@ def _ptr(t):
 def use_torch_stream():
     """Route the library's launches to torch's current CUDA stream on the current device."""
     import torch
-    check(lib().fadb_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    h = torch.cuda.current_stream().cuda_stream
+    # torch's default stream is the legacy NULL stream: name it explicitly (cudaStreamLegacy == 1),
+    # because NULL means "the library's own stream" to fadb_set_stream.
+    check(lib().fadb_set_stream(C.c_void_p(h if h else 1)))
 
 
 def _chk_f64(*ts):

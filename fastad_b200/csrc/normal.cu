@@ -61,9 +61,13 @@ struct Elem {
             acc[0] += z * z;
             acc[1] += log(s);                                 // normal.hpp:483, 572
             const double s2 = s * s;
-            gx = seed * (m - x) / s2;                         // normal.hpp:474, 564 (vsv: (seed/s^2)*(m-x))
-            if (MU_VEC) gm = seed * d / s2;                   // normal.hpp:563
-            else { acc[2] += d / s2; gm = 0.0; }              // normal.hpp:471
+            if (MU_VEC) {
+                gx = seed * (m - x) / s2;                     // vvv, normal.hpp:564
+                gm = seed * d / s2;                           // vvv, normal.hpp:563
+            } else {
+                gx = (seed / s2) * (m - x);                   // vsv, normal.hpp:474
+                acc[2] += d / s2; gm = 0.0;                   // vsv, normal.hpp:471
+            }
             gs = (seed / s) * (z * z - 1.);                   // normal.hpp:468, 560
         } else {
             acc[0] += d * d;                                  // squaredNorm, normal.hpp:244, 351

@@ -61,7 +61,8 @@ int fadb_init(int device);
 void fadb_shutdown(void);
 int fadb_device_count(void);
 /* Use a caller-owned cudaStream_t (e.g. torch's current stream) for all launches on the
- * current device; NULL restores the library's own stream. */
+ * current device; NULL restores the library's own stream (pass cudaStreamLegacy, (void*)1, to
+ * name the legacy default stream). */
 int fadb_set_stream(void* cuda_stream);
 int fadb_sync(void);
 const char* fadb_last_error(void);

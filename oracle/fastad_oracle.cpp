@@ -946,7 +946,7 @@ double orc_sum_unary(int op, size_t n, const double* x, double* x_adj, double se
     parallel_ranges(n, nthreads, [&](int t, size_t b, size_t e) {
         orc_graph* g = orc_new();
         int xv = orc_var(g, ORC_VEC, e - b, 1, const_cast<double*>(x + b), x_adj + b);
-        int root = orc_sum(g, op >= 1000 ? orc_pow(g, op - 1000, xv) : orc_unary(g, op, xv));
+        int root = orc_sum(g, op >= 900 ? orc_pow(g, op - 1000, xv) : orc_unary(g, op, xv));  /* 1000+n = pow<n> */
         orc_bind(g, root, nullptr);
         part[t] = orc_feval(g, root)[0];
         orc_beval(g, root, seed, nullptr);

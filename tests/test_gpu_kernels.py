@@ -174,12 +174,16 @@ def test_sum_unary_vs_oracle(fb, op):
     oa = np.full(n, 0.5)
     ov = O.sum_unary(op, x, oa, seed=1.5)
     assert rel(v, ov) <= REL_REDUCE
-    # per-element adjoints: <= 4 ulp of the increment (libdevice vs glibc), bit-exact for pow/neg
+    # per-element adjoints: <= 4 ulp of the increment (libdevice vs glibc; the reference's array
+    # pow is std::pow per element, pow.hpp:97, ours is the PowFunc multiplication tree), bit-exact
+    # for arithmetic-only maps.  tanh's 1 - f*f cancels: absolute floor of a few ulp(1)*seed.
     inc_g, inc_o = host(ga) - 0.5, oa - 0.5
-    if isinstance(op, tuple) and op[1] in (2, 3) or op == "neg":
+    if op == "neg":
         np.testing.assert_array_equal(host(ga), oa)
     else:
         tol = 4 * np.spacing(np.abs(inc_o)) + 2 * np.spacing(0.5 + np.abs(inc_o))
+        if op == "tanh":
+            tol = tol + 8 * 1.5 * np.finfo(float).eps
         assert np.all(np.abs(inc_g - inc_o) <= tol), np.max(np.abs(inc_g - inc_o) / tol)
 
 
