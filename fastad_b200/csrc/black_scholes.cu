@@ -10,6 +10,8 @@
 // placeholders cache[0..2] is identical for call and put and is swept once.
 //
 // HBM layout: SoA.  5 input streams, 8 output streams, 104 algorithmic bytes per option.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fadb {
@@ -87,8 +89,8 @@ __device__ __forceinline__ void bs_store1(const BSOut& out, size_t i, const BSRe
     }
 }
 
-template <bool ACC>
-__global__ void __launch_bounds__(256)
+template <bool ACC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 bs_kernel(size_t n, const double* __restrict__ S, const double* __restrict__ K,
           const double* __restrict__ sigma, const double* __restrict__ tau,
           const double* __restrict__ r, BSOut out, bool vec_ok)
@@ -123,6 +125,21 @@ bs_kernel(size_t n, const double* __restrict__ S, const double* __restrict__ K,
     }
 }
 
+// one option per thread (64-bit coalesced accesses): half the live registers, twice the warps
+template <bool ACC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bs_kernel1(size_t n, const double* __restrict__ S, const double* __restrict__ K,
+           const double* __restrict__ sigma, const double* __restrict__ tau,
+           const double* __restrict__ r, BSOut out)
+{
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += nthreads) {
+        const BSRes o = bs_eval(__ldg(S + i), __ldg(K + i), __ldg(sigma + i), __ldg(tau + i), __ldg(r + i));
+        bs_store1<ACC>(out, i, o);
+    }
+}
+
 int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S, const double* K,
                          const double* sigma, const double* tau, const double* r,
                          double* const out[8], unsigned flags)
@@ -136,11 +153,36 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     }
     if (n == 0) return FADB_OK;
     const int threads = 256;
-    const int grid = grid_for(c, (n + 1) / 2, 8, threads);
-    if (flags & FADB_OVERWRITE_ADJ)
-        bs_kernel<false><<<grid, threads, 0, st>>>(n, S, K, sigma, tau, r, o, vec_ok);
-    else
-        bs_kernel<true><<<grid, threads, 0, st>>>(n, S, K, sigma, tau, r, o, vec_ok);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 5; }
+#define FADB_BS2(MINB)                                                                                  \
+    do {                                                                                                \
+        if (flags & FADB_OVERWRITE_ADJ)                                                                 \
+            bs_kernel<false, MINB><<<resident_grid(c, bs_kernel<false, MINB>, threads, 0, (n + 1) / 2, threads), \
+                                     threads, 0, st>>>(n, S, K, sigma, tau, r, o, vec_ok);              \
+        else                                                                                            \
+            bs_kernel<true, MINB><<<resident_grid(c, bs_kernel<true, MINB>, threads, 0, (n + 1) / 2, threads),   \
+                                    threads, 0, st>>>(n, S, K, sigma, tau, r, o, vec_ok);               \
+    } while (0)
+#define FADB_BS1(MINB)                                                                                  \
+    do {                                                                                                \
+        if (flags & FADB_OVERWRITE_ADJ)                                                                 \
+            bs_kernel1<false, MINB><<<resident_grid(c, bs_kernel1<false, MINB>, threads, 0, n, threads), \
+                                      threads, 0, st>>>(n, S, K, sigma, tau, r, o);                     \
+        else                                                                                            \
+            bs_kernel1<true, MINB><<<resident_grid(c, bs_kernel1<true, MINB>, threads, 0, n, threads),  \
+                                     threads, 0, st>>>(n, S, K, sigma, tau, r, o);                      \
+    } while (0)
+    switch (variant) {
+    case 1: FADB_BS2(3); break;
+    case 2: FADB_BS2(4); break;
+    case 3: FADB_BS1(4); break;
+    case 4: FADB_BS1(6); break;
+    case 0: FADB_BS2(2); break;
+    default: FADB_BS1(3); break;   // measured best on B200: 1 option/thread, 60 regs, 4 CTAs/SM
+    }
+#undef FADB_BS2
+#undef FADB_BS1
     c.launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;

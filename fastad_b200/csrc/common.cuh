@@ -67,6 +67,19 @@ inline int grid_for(const Context& c, size_t work_items, int per_sm, size_t item
     return (int)want;
 }
 
+// One resident wave: grid = SMs x (CTAs that fit per SM for this kernel), capped by the work.
+// A grid-stride kernel launched like this has no second-wave tail.
+template <class Kernel>
+inline int resident_grid(const Context& c, Kernel kernel, int threads, size_t dyn_smem,
+                         size_t work_items, size_t items_per_cta)
+{
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    return grid_for(c, work_items, per_sm, items_per_cta);
+}
+
 // ---------------------------------------------------------------------------------------
 // 256-bit global memory access (LDG.E.256 / STG.E.256 on sm_100a).
 // Streaming data is read once: bypass L1 allocation; adjoint RMW uses plain ld/st.

@@ -75,7 +75,7 @@ static int launch_sum_map(Context& c, size_t n, const double* x, double* x_adj, 
                           unsigned flags, F fun, double* dval)
 {
     const int threads = 256;
-    const int grid = grid_for(c, (n + 3) / 4, 8, threads);
+    const int grid = resident_grid(c, sum_map_kernel<F>, threads, 0, (n + 3) / 4, threads);
     sum_map_kernel<F><<<grid, threads, 0, c.stream>>>(n, x, x_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
                                                       fun, c.partials, c.tickets + 2, dval);
     c.launches++;
@@ -207,7 +207,7 @@ extern "C" int fadb_prod(size_t n, const double* x, double* x_adj, double seed, 
     if (rc) return rc;
     double* red = c->scalars + 16;   // 3 doubles
     const int threads = 256;
-    const int grid = grid_for(*c, n, 8, threads);
+    const int grid = resident_grid(*c, prod_reduce_kernel, threads, 0, n, threads);
     prod_reduce_kernel<<<grid, threads, 0, c->stream>>>(n, x, c->partials, c->tickets + 3, red);
     c->launches++;
     FADB_CUDA(cudaGetLastError());

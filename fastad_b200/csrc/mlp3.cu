@@ -138,7 +138,7 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     if (rc) return rc;
     if (!g_mlp_ws[c->device]) FADB_CUDA(cudaMalloc(&g_mlp_ws[c->device], sizeof(double) * kMaxGrid * NOUT));
     const int threads = 256;
-    const int grid = grid_for(*c, batch, 4, threads);
+    const int grid = resident_grid(*c, mlp3_kernel, threads, 0, batch, threads);
     mlp3_kernel<<<grid, threads, 0, c->stream>>>(batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad,
                                                  (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss);
     c->launches++;

@@ -209,15 +209,19 @@ __global__ void normal_finish_kernel(int shape_code, double n_total, const doubl
 static int launch_partial(Context& c, int shape_code, const NormalArgs& a, double* out_partial)
 {
     const int threads = 256;
-    const int grid = grid_for(c, (a.n + 3) / 4, 8, threads);
+    const size_t work = (a.n + 3) / 4;
     double* part = c.partials;
     unsigned int* ticket = c.tickets + 1;
+#define FADB_LAUNCH_NORMAL(MV, SV)                                                               \
+    normal_kernel<MV, SV><<<resident_grid(c, normal_kernel<MV, SV>, threads, 0, work, threads),  \
+                            threads, 0, c.stream>>>(a, part, ticket, out_partial)
     switch (shape_code & 3) {
-    case 0: normal_kernel<false, false><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
-    case 1: normal_kernel<true, false><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
-    case 2: normal_kernel<false, true><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
-    case 3: normal_kernel<true, true><<<grid, threads, 0, c.stream>>>(a, part, ticket, out_partial); break;
+    case 0: FADB_LAUNCH_NORMAL(false, false); break;
+    case 1: FADB_LAUNCH_NORMAL(true, false); break;
+    case 2: FADB_LAUNCH_NORMAL(false, true); break;
+    case 3: FADB_LAUNCH_NORMAL(true, true); break;
     }
+#undef FADB_LAUNCH_NORMAL
     c.launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;
@@ -242,7 +246,7 @@ extern "C" int fadb_sigma_check(size_t n, const double* sigma, double* dev_count
     int rc = current_context(&c);
     if (rc) return rc;
     const int threads = 512;
-    const int grid = grid_for(*c, (n + 3) / 4, 4, threads);
+    const int grid = resident_grid(*c, sigma_check_kernel, threads, 0, (n + 3) / 4, threads);
     sigma_check_kernel<<<grid, threads, 0, c->stream>>>(n, sigma, c->partials, c->tickets + 0, dev_count);
     c->launches++;
     FADB_CUDA(cudaGetLastError());
