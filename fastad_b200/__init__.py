@@ -59,6 +59,32 @@ SIGNATURES = {
     "fadb_linreg_nll": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_mlp3": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _dp]),
     "fadb_mlp3_async": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _vp]),
+    "fadb_expr_create": (_i, [C.POINTER(_vp)]),
+    "fadb_expr_destroy": (None, [_vp]),
+    "fadb_expr_var": (_i, [_vp, _i, _sz, _sz, _vp, _vp]),
+    "fadb_expr_const_scalar": (_i, [_vp, _d]),
+    "fadb_expr_const_view": (_i, [_vp, _i, _sz, _sz, _vp]),
+    "fadb_expr_rebind": (_i, [_vp, _i, _vp, _vp]),
+    "fadb_expr_unary": (_i, [_vp, _i, _i]),
+    "fadb_expr_binary": (_i, [_vp, _i, _i, _i]),
+    "fadb_expr_pow": (_i, [_vp, C.c_long, _i]),
+    "fadb_expr_sum": (_i, [_vp, _i]),
+    "fadb_expr_sum_iter": (_i, [_vp, _i, C.POINTER(_i)]),
+    "fadb_expr_prod": (_i, [_vp, _i]),
+    "fadb_expr_prod_iter": (_i, [_vp, _i, C.POINTER(_i)]),
+    "fadb_expr_dot": (_i, [_vp, _i, _i]),
+    "fadb_expr_normal": (_i, [_vp, _i, _i, _i]),
+    "fadb_expr_eq": (_i, [_vp, _i, _i]),
+    "fadb_expr_glue": (_i, [_vp, _i, _i]),
+    "fadb_expr_node_size": (_i, [_vp, _i, C.POINTER(_sz), C.POINTER(_sz)]),
+    "fadb_expr_is_const": (_i, [_vp, _i]),
+    "fadb_expr_plan": (_i, [_vp, _i, C.POINTER(_sz)]),
+    "fadb_expr_describe": (_i, [_vp, C.c_char_p, _sz]),
+    "fadb_expr_bind": (_i, [_vp, _i, _u, C.POINTER(_sz)]),
+    "fadb_expr_feval": (_i, [_vp, _dp]),
+    "fadb_expr_beval": (_i, [_vp, _d, _vp]),
+    "fadb_expr_autodiff": (_i, [_vp, _d, _vp, _dp]),
+    "fadb_expr_value_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
 }
 
 _lib = None
@@ -185,3 +211,163 @@ def mlp3(X, y, parm, grad, flags=0):
     v = C.c_double()
     check(lib().fadb_mlp3(y.numel(), _ptr(X), _ptr(y), _ptr(parm), _ptr(grad), flags, C.byref(v)))
     return v.value
+
+
+# ------------------------------------------------------------------------------------------
+# Expr: the run-time expression builder of the C ABI (what include/fastad lowers ad:: expression
+# templates into at bind() time), with the same vocabulary as tests/oracle_py.OracleExpr.
+# device=False builds and plans on the host only (no CUDA call): used by the CPU tests.
+# ------------------------------------------------------------------------------------------
+class Expr:
+    def __init__(self, device=True):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.fadb_expr_create(C.byref(h)))
+        self.h = h
+        self.device = device
+        self.vars = {}
+        self.keep = []
+        self.root = None
+
+    def __del__(self):
+        try:
+            self.L.fadb_expr_destroy(self.h)
+        except Exception:
+            pass
+
+    def _id(self, rc):
+        if rc < 0:
+            check(rc)
+        return rc
+
+    def _buf(self, flat):
+        import numpy as np
+        if not self.device:
+            a = np.ascontiguousarray(flat, dtype=np.float64)
+            self.keep.append(a)
+            return a, a.ctypes.data
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)).cuda()
+        self.keep.append(t)
+        return t, t.data_ptr()
+
+    @staticmethod
+    def _shape_of(v):
+        import numpy as np
+        v = np.array(v, dtype=np.float64, order="F")
+        shape = (SCL, VEC, MAT)[v.ndim]
+        rows = v.shape[0] if v.ndim >= 1 else 1
+        cols = v.shape[1] if v.ndim == 2 else 1
+        return np.asfortranarray(v).reshape(-1, order="F").copy(), shape, rows, cols
+
+    def var(self, value):
+        import numpy as np
+        flat, shape, rows, cols = self._shape_of(value)
+        tv, pv = self._buf(flat)
+        ta, pa = self._buf(np.zeros_like(flat))
+        nid = self._id(self.L.fadb_expr_var(self.h, shape, rows, cols, C.c_void_p(pv), C.c_void_p(pa)))
+        self.vars[nid] = (tv, ta)
+        return nid
+
+    def const(self, value):
+        import numpy as np
+        if np.ndim(value) == 0:
+            return self._id(self.L.fadb_expr_const_scalar(self.h, float(value)))
+        flat, shape, rows, cols = self._shape_of(value)
+        tv, pv = self._buf(flat)
+        return self._id(self.L.fadb_expr_const_view(self.h, shape, rows, cols, C.c_void_p(pv)))
+
+    def unary(self, op, c):
+        return self._id(self.L.fadb_expr_unary(self.h, UNARY[op], c))
+
+    def binary(self, op, l, r):
+        return self._id(self.L.fadb_expr_binary(self.h, BINARY[op], l, r))
+
+    def pow(self, n, c):
+        return self._id(self.L.fadb_expr_pow(self.h, n, c))
+
+    def sum(self, c):
+        return self._id(self.L.fadb_expr_sum(self.h, c))
+
+    def prod(self, c):
+        return self._id(self.L.fadb_expr_prod(self.h, c))
+
+    def sum_iter(self, cs):
+        return self._id(self.L.fadb_expr_sum_iter(self.h, len(cs), (C.c_int * len(cs))(*cs)))
+
+    def prod_iter(self, cs):
+        return self._id(self.L.fadb_expr_prod_iter(self.h, len(cs), (C.c_int * len(cs))(*cs)))
+
+    def dot(self, l, r):
+        return self._id(self.L.fadb_expr_dot(self.h, l, r))
+
+    def normal(self, x, mu, sigma):
+        return self._id(self.L.fadb_expr_normal(self.h, x, mu, sigma))
+
+    def eq(self, w, c):
+        return self._id(self.L.fadb_expr_eq(self.h, w, c))
+
+    def glue(self, *ids):
+        out = ids[0]
+        for nxt in ids[1:]:
+            out = self._id(self.L.fadb_expr_glue(self.h, out, nxt))
+        return out
+
+    def plan(self, root):
+        out = (C.c_size_t * 2)()
+        check(self.L.fadb_expr_plan(self.h, root, out))
+        self.root = root
+        return int(out[0]), int(out[1])
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.L.fadb_expr_describe(self.h, buf, len(buf))
+        return buf.value.decode()
+
+    def bind(self, root, flags=0):
+        out = (C.c_size_t * 2)()
+        check(self.L.fadb_expr_bind(self.h, root, flags, out))
+        self.root = root
+        rows, cols = C.c_size_t(), C.c_size_t()
+        check(self.L.fadb_expr_node_size(self.h, root, C.byref(rows), C.byref(cols)))
+        self.root_size = rows.value * cols.value
+        return int(out[0]), int(out[1])
+
+    def _seed(self, seed):
+        import numpy as np
+        if np.ndim(seed) == 0:
+            return float(seed), None, None
+        import torch
+        flat = np.asfortranarray(np.asarray(seed, dtype=np.float64)).reshape(-1, order="F")
+        t = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
+        return 0.0, t, C.c_void_p(t.data_ptr())
+
+    def feval(self):
+        import numpy as np
+        out = np.zeros(self.root_size)
+        check(self.L.fadb_expr_feval(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    def beval(self, seed=1.0):
+        s, keep, p = self._seed(seed)
+        check(self.L.fadb_expr_beval(self.h, s, p))
+        check(self.L.fadb_sync())
+
+    def autodiff(self, seed=1.0):
+        import numpy as np
+        s, keep, p = self._seed(seed)
+        out = np.zeros(self.root_size)
+        check(self.L.fadb_expr_autodiff(self.h, s, p, out.ctypes.data_as(_dp)))
+        return out
+
+    def value(self, nid):
+        check(self.L.fadb_sync())
+        return self.vars[nid][0].cpu().numpy()
+
+    def adj(self, nid):
+        check(self.L.fadb_sync())
+        return self.vars[nid][1].cpu().numpy()
+
+    def reset_adj(self):
+        for v, a in self.vars.values():
+            a.zero_()

@@ -166,6 +166,57 @@ int fadb_mlp3(size_t batch, const double* X, const double* y, const double* parm
 int fadb_mlp3_async(size_t batch, const double* X, const double* y, const double* parm,
                     double* grad, unsigned flags, double* dev_loss);
 
+/* ------------------------------------------------------------------ generic expressions
+ * The run-time image of a FastAD expression template.  The C++17 host layer (include/fastad)
+ * lowers the static expression type into these calls at ad::bind() time; node constructors
+ * mirror the reference's builders one to one and return a node id >= 0 (or a negative error):
+ *   fadb_expr_var          VarView<T,Shape>(val, adj, rows, cols)     var_view.hpp:120-194
+ *   fadb_expr_const_*      ad::constant / ad::constant_view           constant.hpp:158-200
+ *   fadb_expr_unary        ad::sin ... ad::tanh, operator-            unary.hpp:299-330
+ *   fadb_expr_binary       operator+ - * /                            binary.hpp:472-498
+ *   fadb_expr_pow          ad::pow<n>                                 pow.hpp:205-231
+ *   fadb_expr_sum[_iter]   ad::sum(expr) / ad::sum(begin,end,f)       sum.hpp:216-261
+ *   fadb_expr_prod[_iter]  ad::prod(expr) / ad::prod(begin,end,f)     prod.hpp:259-306
+ *   fadb_expr_dot          ad::dot                                    dot.hpp:133-163
+ *   fadb_expr_normal       ad::normal_adj_log_pdf                     stat/normal.hpp:785-797
+ *   fadb_expr_eq           placeholder `w = expr`                     var_view.hpp:54-63, eq.hpp
+ *   fadb_expr_glue         operator,                                  glue.hpp:124-139
+ * Scalar constant operands are folded eagerly on the host like the reference does
+ * (unary.hpp:182-184, binary.hpp:251-256).  Leaf pointers are DEVICE pointers.
+ *   fadb_expr_plan         host-only: cut into fused stages (no CUDA call); cache sizes play the
+ *                          role of bind_cache_size() (bind.hpp:28) -- only stage boundaries count
+ *   fadb_expr_bind         ad::bind: plan + allocate boundary buffers in HBM   bind.hpp:24-33
+ *   fadb_expr_feval / _beval / _autodiff   ad::evaluate / evaluate_adj / autodiff   eval.hpp:18-153
+ * seed: scalar `seed` broadcast, or `seed_dev` (device array of the root's size) when non-NULL.
+ * host_value receives the root value (root-size doubles) when non-NULL. */
+typedef struct fadb_expr fadb_expr;
+int fadb_expr_create(fadb_expr** out);
+void fadb_expr_destroy(fadb_expr*);
+int fadb_expr_var(fadb_expr*, int shape, size_t rows, size_t cols, double* val, double* adj);
+int fadb_expr_const_scalar(fadb_expr*, double c);
+int fadb_expr_const_view(fadb_expr*, int shape, size_t rows, size_t cols, const double* val);
+int fadb_expr_rebind(fadb_expr*, int leaf, double* val, double* adj);
+int fadb_expr_unary(fadb_expr*, int op, int child);
+int fadb_expr_binary(fadb_expr*, int op, int lhs, int rhs);
+int fadb_expr_pow(fadb_expr*, long n, int child);
+int fadb_expr_sum(fadb_expr*, int child);
+int fadb_expr_sum_iter(fadb_expr*, int k, const int* children);
+int fadb_expr_prod(fadb_expr*, int child);
+int fadb_expr_prod_iter(fadb_expr*, int k, const int* children);
+int fadb_expr_dot(fadb_expr*, int lhs, int rhs);
+int fadb_expr_normal(fadb_expr*, int x, int mu, int sigma);
+int fadb_expr_eq(fadb_expr*, int var, int child);
+int fadb_expr_glue(fadb_expr*, int lhs, int rhs);
+int fadb_expr_node_size(fadb_expr*, int node, size_t* rows, size_t* cols);
+int fadb_expr_is_const(fadb_expr*, int node);
+int fadb_expr_plan(fadb_expr*, int root, size_t out_cache_size[2]);
+int fadb_expr_describe(fadb_expr*, char* buf, size_t cap);
+int fadb_expr_bind(fadb_expr*, int root, unsigned flags, size_t out_cache_size[2]);
+int fadb_expr_feval(fadb_expr*, double* host_value);
+int fadb_expr_beval(fadb_expr*, double seed, const double* seed_dev);
+int fadb_expr_autodiff(fadb_expr*, double seed, const double* seed_dev, double* host_value);
+int fadb_expr_value_ptr(fadb_expr*, const double** dev_value, size_t* size);
+
 #ifdef __cplusplus
 }
 #endif

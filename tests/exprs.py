@@ -1,0 +1,221 @@
+"""Expression cases shared by the oracle/product parity tests.  Each case builds the SAME
+expression through the common builder vocabulary (OracleExpr / fastad_b200.Expr) and returns
+(root, [variable node ids], seed)."""
+import numpy as np
+
+import kats
+
+RNG = np.random.default_rng(20261019)
+
+
+def _vec(n, lo=0.5, hi=2.0):
+    return RNG.uniform(lo, hi, n)
+
+
+def scalar_chain(e):   # node_inttest.cpp:129-159
+    l1, l2, l3 = e.var(1.5928), e.var(-0.291), e.var(5.1023)
+    root = e.binary("sub",
+                    e.binary("add", e.binary("mul", l1, l3),
+                             e.binary("mul", e.unary("sin", e.unary("cos", e.binary("add", l1, l2))), l2)),
+                    e.binary("div", l1, e.unary("exp", l3)))
+    return root, [l1, l2, l3], 1.0
+
+
+def placeholders(e):   # bind_unittest.cpp:13-35
+    w1, w2, w3, w4 = e.var(1.0), e.var(2.0), e.var(0.0), e.var(0.0)
+    root = e.glue(e.eq(w3, e.binary("mul", w1, w2)), e.eq(w4, e.binary("mul", w3, w3)))
+    return root, [w1, w2, w3, w4], 1.0
+
+
+def sumnode_benchmark(e):   # benchmark/sum_benchmark.cpp:46-61
+    vs = [e.var(float(i)) for i in range(10)]
+    w4, w5 = e.var(0.0), e.var(0.0)
+    s = e.sum_iter([e.binary("mul", v, v) for v in vs])
+    root = e.glue(e.eq(w4, s), e.eq(w5, e.binary("add", e.binary("mul", w4, w4), e.unary("sin", w4))))
+    return root, vs + [w4, w5], 1.0
+
+
+def prodnode_benchmark(e):   # benchmark/prod_benchmark.cpp:46-64 (values shifted off zero)
+    vs = [e.var(0.5 + 0.1 * i) for i in range(10)]
+    w4, w5 = e.var(0.0), e.var(0.0)
+    p = e.prod_iter([e.binary("mul", v, v) for v in vs])
+    root = e.glue(e.eq(w4, p), e.eq(w5, e.binary("add", e.binary("mul", w4, w4), e.unary("cos", w4))))
+    return root, vs + [w4, w5], 1.0
+
+
+def vec_sum_chain(n):
+    def build(e):   # cf. sum_benchmark.cpp:84-85: sum(-0.5 * pow<2>((x - c*w0) / w1))
+        x = e.var(_vec(n))
+        w0, w1 = e.var(2.0), e.var(1.3)
+        c = e.const(_vec(n))
+        z = e.binary("div", e.binary("sub", x, e.binary("mul", w0, c)), w1)
+        root = e.sum(e.binary("mul", e.const(-0.5), e.pow(2, z)))
+        return root, [x, w0, w1], 0.75
+    return build
+
+
+def vec_nested_sum(n):
+    def build(e):   # a reduction nested under scalar nodes: w4 = sum(exp(x)), w5 = w4*w4 + sin(w4)
+        x = e.var(_vec(n, 0.1, 0.9))
+        w4, w5 = e.var(0.0), e.var(0.0)
+        root = e.glue(e.eq(w4, e.sum(e.unary("exp", x))),
+                      e.eq(w5, e.binary("add", e.binary("mul", w4, w4), e.unary("sin", w4))))
+        return root, [x, w4, w5], 1.0
+    return build
+
+
+def vec_scalar_times_sum(n):
+    def build(e):   # scalar broadcast of a reduced value back into a vector map
+        x, y = e.var(_vec(n)), e.var(_vec(n))
+        root = e.sum(e.binary("mul", x, e.sum(e.unary("log", y))))
+        return root, [x, y], 1.0
+    return build
+
+
+def vec_prod(n, zeros=()):
+    def build(e):
+        v = _vec(n, 0.9, 1.1)
+        for z in zeros:
+            v[z] = 0.0
+        x = e.var(v)
+        root = e.prod(e.binary("mul", x, e.const(1.0 + 0 * v)))
+        return root, [x], 2.0
+    return build
+
+
+def vec_root_with_vector_seed(n):
+    def build(e):   # vector-valued root, vector seed (eval.hpp:68-73)
+        x, y = e.var(_vec(n)), e.var(_vec(n))
+        s = e.var(0.7)
+        root = e.binary("add", e.binary("mul", e.unary("tanh", x), y), e.binary("div", s, x))
+        return root, [x, y, s], _vec(n, -1, 1)
+    return build
+
+
+def vec_placeholder_chain(n):
+    def build(e):   # vector placeholders + glue, as the batched Black-Scholes expression uses them
+        x = e.var(_vec(n))
+        a, b = e.var(np.zeros(n)), e.var(np.zeros(n))
+        root = e.glue(e.eq(a, e.unary("log", x)),
+                      e.eq(b, e.binary("mul", a, a)),
+                      e.binary("sub", e.unary("exp", b), e.binary("mul", a, x)))
+        return root, [x, a, b], np.ones(n)
+    return build
+
+
+def normal_with_expr_mean(n):
+    def build(e):   # univariate regression: normal(y | alpha + beta * x, sigma)
+        y, x = e.const(_vec(n, -1, 1)), e.const(_vec(n))
+        alpha, beta, sigma = e.var(0.3), e.var(-0.2), e.var(1.7)
+        mu = e.binary("add", alpha, e.binary("mul", beta, x))
+        root = e.normal(y, mu, sigma)
+        return root, [alpha, beta, sigma], 1.0
+    return build
+
+
+def normal_vec_sigma_expr(n):
+    def build(e):   # vector sigma produced by an expression: normal(x | mu, exp(ls))
+        x, mu, ls = e.var(_vec(n, -1, 1)), e.var(_vec(n, -1, 1)), e.var(_vec(n, -0.5, 0.5))
+        root = e.normal(x, mu, e.unary("exp", ls))
+        return root, [x, mu, ls], 1.0
+    return build
+
+
+def sum_of_normals(n):
+    def build(e):   # log-posterior shape: normal(x|mu,sigma) + normal(mu|0,10)
+        x = e.const(_vec(n, -1, 1))
+        mu, sigma = e.var(0.1), e.var(1.3)
+        root = e.binary("add", e.normal(x, mu, sigma), e.normal(mu, e.const(0.0), e.const(10.0)))
+        return root, [mu, sigma], 1.0
+    return build
+
+
+def dot_norm_sum(e):   # node_inttest.cpp:402-442 shape: sum(dot(M, v) elementwise-squared)
+    M = e.var(np.array([[1.0, 2.0], [-1.0, 3.0], [2.0, -3.0]]))
+    v = e.var(np.array([[0.5], [-1.5]]))
+    d = e.dot(M, v)
+    root = e.sum(e.binary("mul", d, d))
+    return root, [M, v], 1.0
+
+
+def quadratic_form(e):   # README.md:582-607
+    x = e.var(np.array([[0.5], [0.6]]))
+    xt = e.var(np.array([[0.5, 0.6]]))
+    S = e.const(np.array([[2.0, 3.0], [3.0, 6.0]]))
+    return e.dot(e.dot(xt, S), x), [x, xt], np.ones((1, 1))
+
+
+def mlp3_row(e):   # README.md:676-726 for one data row
+    p = kats.NN_PARM
+    A1, b1 = e.var(p[0:6].reshape(3, 2, order="F")), e.var(p[6:9].reshape(3, 1))
+    A2, b2 = e.var(p[9:18].reshape(3, 3, order="F")), e.var(p[18:21].reshape(3, 1))
+    A3, b3 = e.var(p[21:24].reshape(1, 3)), e.var(p[24:25].reshape(1, 1))
+    xi, yi = e.const(kats.NN_X[2].reshape(2, 1)), e.const(kats.NN_Y[2].reshape(1, 1))
+    x1a = e.binary("add", e.dot(A1, xi), b1)
+    x1b = e.binary("add", e.dot(A1, xi), b1)
+    y1 = e.unary("sigmoid", x1a)
+    y2 = e.binary("add", e.unary("sigmoid", e.binary("add", e.dot(A2, y1), b2)), x1b)
+    y3 = e.binary("add", e.dot(A3, y2), b3)
+    return e.pow(2, e.binary("sub", yi, y3)), [A1, b1, A2, b2, A3, b3], np.ones((1, 1))
+
+
+def linreg_expr(rows, cols):
+    def build(e):   # the C4 expression: normal(y, dot(X, w), sigma)
+        import synth
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=7)
+        Xc, yc = e.const(X), e.const(y)
+        w, sigma = e.var(w_true + 0.01), e.var(1.3)
+        return e.normal(yc, e.dot(Xc, w), sigma), [w, sigma], 1.0
+    return build
+
+
+def black_scholes_vec(n, put=False):
+    def build(e):   # example/black_scholes.cpp:16-39 over vec leaves
+        import synth
+        inp = synth.black_scholes_inputs(n, seed=11)
+        S, sigma, r = e.var(inp["S"]), e.var(inp["sigma"]), e.var(inp["r"])
+        K, tau, sq = e.const(inp["K"]), e.const(inp["tau"]), e.const(np.sqrt(inp["tau"]))
+        c0, c1, c2 = e.var(np.zeros(n)), e.var(np.zeros(n)), e.var(np.zeros(n))
+
+        def phi(x):
+            er = e.unary("erf", e.binary("div", x, e.const(np.sqrt(2.0))))
+            return e.binary("mul", e.const(0.5), e.binary("add", er, e.const(1.0)))
+        e0 = e.eq(c0, e.unary("log", e.binary("div", S, K)))
+        drift = e.binary("mul", e.binary("add", r, e.binary("div", e.binary("mul", sigma, sigma), e.const(2.0))), tau)
+        e1 = e.eq(c1, e.binary("div", e.binary("add", c0, drift), e.binary("mul", sigma, sq)))
+        e2 = e.eq(c2, e.binary("sub", c1, e.binary("mul", sigma, sq)))
+        pv = e.binary("mul", K, e.unary("exp", e.binary("mul", e.unary("neg", r), tau)))
+        if not put:
+            price = e.binary("sub", e.binary("mul", phi(c1), S), e.binary("mul", phi(c2), pv))
+        else:
+            price = e.binary("sub", e.binary("mul", phi(e.unary("neg", c2)), pv),
+                             e.binary("mul", phi(e.unary("neg", c1)), S))
+        return e.glue(e0, e1, e2, price), [S, sigma, r, c0, c1, c2], np.ones(n)
+    return build
+
+
+CASES = {
+    "scalar_chain": scalar_chain,
+    "placeholders": placeholders,
+    "sumnode_benchmark": sumnode_benchmark,
+    "prodnode_benchmark": prodnode_benchmark,
+    "vec_sum_chain_5": vec_sum_chain(5),
+    "vec_sum_chain_100k": vec_sum_chain(100003),
+    "vec_nested_sum": vec_nested_sum(4099),
+    "vec_scalar_times_sum": vec_scalar_times_sum(3001),
+    "vec_prod": vec_prod(300),
+    "vec_prod_one_zero": vec_prod(300, zeros=(17,)),
+    "vec_prod_two_zeros": vec_prod(300, zeros=(17, 200)),
+    "vec_root_vector_seed": vec_root_with_vector_seed(2049),
+    "vec_placeholder_chain": vec_placeholder_chain(1025),
+    "normal_expr_mean": normal_with_expr_mean(5001),
+    "normal_vec_sigma_expr": normal_vec_sigma_expr(3000),
+    "sum_of_normals": sum_of_normals(2000),
+    "dot_norm_sum": dot_norm_sum,
+    "quadratic_form": quadratic_form,
+    "mlp3_row": mlp3_row,
+    "linreg_expr": linreg_expr(2000, 64),
+    "linreg_expr_small": linreg_expr(130, 5),
+    "black_scholes_call": black_scholes_vec(2001),
+    "black_scholes_put": black_scholes_vec(2001, put=True),
+}

@@ -1,0 +1,125 @@
+"""GPU parity of the generic expression path (builder -> planner -> interpreter kernels, and
+the fast-path dispatch) against the CPU oracle, on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import exprs
+import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import torch
+    assert torch.cuda.is_available()
+    import fastad_b200 as F
+    F.load()
+    F.check(F.lib().fadb_init(0))
+    F.use_torch_stream()
+    return F
+
+
+def _run(build, backend, twice=False):
+    exprs.RNG = np.random.default_rng(20261019)    # identical inputs for both backends
+    e = backend()
+    root, variables, seed = build(e)
+    e.bind(root)
+    val = e.autodiff(seed)
+    if twice:                                    # adjoints accumulate (eval_unittest.cpp:37-42)
+        val = e.autodiff(seed)
+    return val, [e.adj(v).copy() for v in variables], [e.value(v).copy() for v in variables], e
+
+
+def _close(a, b, rtol, what):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * max(scale, 1e-300), err_msg=what)
+
+
+@pytest.mark.parametrize("name", sorted(exprs.CASES))
+def test_expr_matches_oracle(fb, name):
+    build = exprs.CASES[name]
+    ov, oadj, oval, _ = _run(build, O.OracleExpr)
+    gv, gadj, gval, ge = _run(build, fb.Expr)
+    rtol = 1e-11 if name.startswith("black_scholes") else 1e-12
+    _close(gv, ov, rtol, name + " value")
+    for k, (g, o) in enumerate(zip(gadj, oadj)):
+        _close(g, o, 1e-10 if name.startswith(("black_scholes", "mlp3")) else 1e-11, f"{name} adj[{k}]")
+    for k, (g, o) in enumerate(zip(gval, oval)):          # placeholders hold their values
+        _close(g, o, 1e-12, f"{name} val[{k}]")
+
+
+@pytest.mark.parametrize("name", ["placeholders", "vec_sum_chain_100k", "normal_expr_mean", "dot_norm_sum"])
+def test_expr_adjoints_accumulate(fb, name):
+    build = exprs.CASES[name]
+    _, oadj, _, _ = _run(build, O.OracleExpr, twice=True)
+    _, gadj, _, _ = _run(build, fb.Expr, twice=True)
+    for g, o in zip(gadj, oadj):
+        _close(g, o, 1e-11, name)
+
+
+@pytest.mark.parametrize("name", ["scalar_chain", "vec_nested_sum", "vec_prod_one_zero", "normal_vec_sigma_expr"])
+def test_expr_feval_then_beval_equals_autodiff(fb, name):
+    build = exprs.CASES[name]
+    exprs.RNG = np.random.default_rng(20261019)
+    e = fb.Expr()
+    root, variables, seed = build(e)
+    e.bind(root)
+    v1 = e.feval()
+    e.beval(seed)
+    a1 = [e.adj(v).copy() for v in variables]
+    e.reset_adj()
+    v2 = e.autodiff(seed)
+    a2 = [e.adj(v).copy() for v in variables]
+    np.testing.assert_array_equal(v1, v2)
+    for x, y in zip(a1, a2):
+        np.testing.assert_allclose(x, y, rtol=1e-14, atol=0)
+
+
+def test_expr_normal_invalid_sigma_generic_path(fb):
+    # vector sigma from an expression with one non-positive element: value -inf, no adjoints
+    n = 500
+    rng = np.random.default_rng(3)
+    for backend in (O.OracleExpr, fb.Expr):
+        e = backend()
+        x, mu = e.var(rng.normal(size=n)), e.var(rng.normal(size=n))
+        sg = rng.uniform(0.5, 2, n); sg[123] = -0.3
+        s = e.var(sg)
+        root = e.normal(x, mu, e.binary("mul", s, e.const(1.0 + 0 * sg)))
+        e.bind(root)
+        v = e.autodiff(1.0)
+        assert v[0] == -np.inf
+        for leaf in (x, mu, s):
+            assert np.all(e.adj(leaf) == 0)
+        rng = np.random.default_rng(3)
+
+
+def test_expr_fast_paths_are_selected(fb):
+    e = fb.Expr()
+    x = e.var(np.linspace(0.5, 2, 1000))
+    e.bind(e.sum(e.unary("exp", x)))
+    assert "fast=1" in e.describe()
+    e = fb.Expr()
+    x, mu, s = e.var(np.zeros(100)), e.var(0.1), e.var(1.3)
+    e.bind(e.normal(x, mu, s))
+    assert "fast=2" in e.describe()
+    build = exprs.CASES["linreg_expr"]
+    e = fb.Expr()
+    root, _, _ = build(e)
+    e.bind(root)
+    assert "fast=3" in e.describe()
+
+
+def test_expr_rebind_leaf(fb):
+    import torch
+    e = fb.Expr()
+    x = e.var(np.array([1.0, 2.0, 3.0]))
+    e.bind(e.sum(e.binary("mul", x, x)))
+    assert e.autodiff()[0] == 14.0
+    nv = torch.tensor([2.0, 2.0, 2.0], dtype=torch.float64, device="cuda")
+    na = torch.zeros(3, dtype=torch.float64, device="cuda")
+    import ctypes as C
+    fb.check(fb.lib().fadb_expr_rebind(e.h, x, C.c_void_p(nv.data_ptr()), C.c_void_p(na.data_ptr())))
+    assert e.autodiff()[0] == 12.0
+    assert na.cpu().tolist() == [4.0, 4.0, 4.0]

@@ -1,0 +1,113 @@
+"""CPU-only tests: the C ABI loads and exports every declared symbol, and the host-side
+planner (expression -> fused stages) behaves as designed.  No CUDA call is made."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import exprs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fastad_b200 as F
+    if not os.path.exists(F.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    F.load()
+    return F
+
+
+def test_library_exports_every_declared_symbol(F):
+    hdr = open(os.path.join(ROOT, "include", "fastad_b200.h")).read()
+    declared = set(re.findall(r"\b(fadb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 50
+    L = F.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/fastad_b200.h but not exported"
+    assert declared == set(F.SIGNATURES), declared ^ set(F.SIGNATURES)
+    assert b"sm_100a" in L.fadb_version()
+
+
+def test_missing_library_fails_loudly(F, tmp_path):
+    with pytest.raises(F.FadbError, match="no CPU fallback"):
+        F.load(str(tmp_path / "libfastad_b200.so"))
+
+
+def _plan(F, build):
+    exprs.RNG = np.random.default_rng(1)
+    e = F.Expr(device=False)
+    root, _, _ = build(e)
+    sizes = e.plan(root)
+    return e.describe(), sizes
+
+
+def test_planner_fuses_elementwise_chain_into_one_stage(F):
+    d, sizes = _plan(F, exprs.CASES["vec_sum_chain_100k"])
+    assert d.startswith("stages=1"), d
+    assert "term=sum" in d and "channels=3" in d          # sum + adjoints of the two scalar leaves
+    # nothing but the root value is materialised (the reference needs ~6 N-sized caches)
+    assert sizes == (1, 0)
+
+
+def test_planner_black_scholes_is_one_stage(F):
+    d, sizes = _plan(F, exprs.CASES["black_scholes_call"])
+    assert d.startswith("stages=1"), d
+    assert d.count(":= %") == 3                            # the three placeholders
+    assert sizes[1] == 0
+
+
+def test_planner_nested_reduction_splits_stages(F):
+    d, _ = _plan(F, exprs.CASES["vec_nested_sum"])
+    assert d.startswith("stages=2"), d
+    assert "map N=4099 term=sum" in d and "map N=1 term=store" in d
+    assert "<- stage 0" in d
+
+
+def test_planner_scalar_broadcast_of_reduction(F):
+    d, _ = _plan(F, exprs.CASES["vec_scalar_times_sum"])
+    assert d.startswith("stages=2"), d
+    assert "(broadcast) <- stage 0" in d
+
+
+def test_planner_fast_paths(F):
+    e = F.Expr(device=False)
+    x = e.var(np.ones(64))
+    e.plan(e.sum(e.unary("log", x)))
+    assert "fast=1" in e.describe()
+    e = F.Expr(device=False)
+    x = e.var(np.ones(64))
+    e.plan(e.sum(e.pow(2, x)))
+    assert "fast=1" in e.describe()
+    d, _ = _plan(F, exprs.CASES["linreg_expr"])
+    assert "fast=3" in d and "dot 2000x64" in d
+    d, _ = _plan(F, exprs.CASES["normal_expr_mean"])
+    assert "fast=0" in d and "term=normal" in d
+
+
+def test_builder_folds_scalar_constants_on_host(F):
+    # unary.hpp:182-184, binary.hpp:251-256, pow.hpp:219-227, sum.hpp:250-252
+    import math
+    e = F.Expr(device=False)
+    c = e.unary("exp", e.const(2.0))
+    assert F.lib().fadb_expr_is_const(e.h, c)
+    c2 = e.binary("mul", c, e.pow(3, e.const(2.0)))
+    assert F.lib().fadb_expr_is_const(e.h, c2)
+    x = e.var(1.0)
+    e.plan(e.binary("add", x, e.sum(c2)))
+    assert f"const {math.exp(2.0) * 8:.4f}"[:12] in e.describe().replace("const 59.1124", "const 59.1124")
+
+
+def test_builder_rejects_bad_shapes(F):
+    e = F.Expr(device=False)
+    a, b = e.var(np.ones(3)), e.var(np.ones(4))
+    with pytest.raises(F.FadbError, match="shapes differ"):
+        e.binary("add", a, b)
+    M, v = e.var(np.ones((2, 3))), e.var(np.ones(2))
+    with pytest.raises(F.FadbError, match="dot"):
+        e.dot(M, v)
+    with pytest.raises(F.FadbError):
+        e.unary("exp", 12345)
