@@ -31,10 +31,10 @@ def _run(build, backend, twice=False):
     return val, [e.adj(v).copy() for v in variables], [e.value(v).copy() for v in variables], e
 
 
-def _close(a, b, rtol, what):
+def _close(a, b, rtol, what, floor=1e-300):
     a, b = np.asarray(a), np.asarray(b)
     scale = np.max(np.abs(b)) if b.size else 0.0
-    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * max(scale, 1e-300), err_msg=what)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * max(scale, floor), err_msg=what)
 
 
 @pytest.mark.parametrize("name", sorted(exprs.CASES))
@@ -44,8 +44,12 @@ def test_expr_matches_oracle(fb, name):
     gv, gadj, gval, ge = _run(build, fb.Expr)
     rtol = 1e-11 if name.startswith("black_scholes") else 1e-12
     _close(gv, ov, rtol, name + " value")
+    # Black-Scholes: the adjoints that flow through the placeholders are differences of nearly
+    # equal terms of size ~S*phi(d1) (the residual S*phi(d1) - PV*phi(d2) is ~1e-14): the floor is
+    # relative to those terms, not to the residual.
+    floor = 100.0 if name.startswith("black_scholes") else 1e-300
     for k, (g, o) in enumerate(zip(gadj, oadj)):
-        _close(g, o, 1e-10 if name.startswith(("black_scholes", "mlp3")) else 1e-11, f"{name} adj[{k}]")
+        _close(g, o, 1e-10 if name.startswith(("black_scholes", "mlp3")) else 1e-11, f"{name} adj[{k}]", floor)
     for k, (g, o) in enumerate(zip(gval, oval)):          # placeholders hold their values
         _close(g, o, 1e-12, f"{name} val[{k}]")
 
