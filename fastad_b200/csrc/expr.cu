@@ -83,6 +83,7 @@ struct StageArgs {
     int nch, term_ch;
     double* partials;
     unsigned int* ticket;
+    double* scratch;           // BIG programs (scalar stages only): v | g | lacc in global memory
 };
 
 __device__ __forceinline__ double block_prod_all(double p, double* sm)
@@ -97,16 +98,24 @@ __device__ __forceinline__ double block_prod_all(double p, double* sm)
     return r;   // valid in thread 0
 }
 
+// BIG = false: program and leaf table staged in shared memory, node values in thread-local
+// storage.  BIG = true (scalar stages with more than MAXS nodes, e.g. ad::sum over a thousand
+// scalar Vars, test/integration/ad_inttest.cpp:143-156): one thread, everything in global memory.
+template <bool BIG>
 __global__ void __launch_bounds__(128)
 stage_kernel(StageArgs a)
 {
-    __shared__ Ins s_prog[MAXS];
-    __shared__ LeafDesc s_leaf[MAXL];
+    __shared__ Ins s_prog_sm[BIG ? 1 : MAXS];
+    __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
     __shared__ double s_red[32 * MAXCH];
     __shared__ bool s_last;
-    for (int k = threadIdx.x; k < a.nins; k += blockDim.x) s_prog[k] = a.prog[k];
-    for (int k = threadIdx.x; k < a.nleaves; k += blockDim.x) s_leaf[k] = a.leaves[k];
-    __syncthreads();
+    const Ins* s_prog = BIG ? a.prog : s_prog_sm;
+    const LeafDesc* s_leaf = BIG ? a.leaves : s_leaf_sm;
+    if (!BIG) {
+        for (int k = threadIdx.x; k < a.nins; k += blockDim.x) s_prog_sm[k] = a.prog[k];
+        for (int k = threadIdx.x; k < a.nleaves; k += blockDim.x) s_leaf_sm[k] = a.leaves[k];
+        __syncthreads();
+    }
 
     const bool fwd_out = a.mode & M_F;     // forward results are stored in this launch
     bool back = a.mode & M_B;
@@ -126,7 +135,10 @@ stage_kernel(StageArgs a)
     for (int c = 0; c < MAXCH; ++c) acc[c] = 0.0;
     double p_nz = 1.0, p_zeros = 0.0;
 
-    double v[MAXS], g[MAXS], lacc[MAXL];
+    double v_loc[BIG ? 1 : MAXS], g_loc[BIG ? 1 : MAXS], l_loc[BIG ? 1 : MAXL];
+    double* v = BIG ? a.scratch : v_loc;
+    double* g = BIG ? a.scratch + a.nins : g_loc;
+    double* lacc = BIG ? a.scratch + 2 * (size_t)a.nins : l_loc;
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = tid; i < a.N; i += nth) {
@@ -395,6 +407,8 @@ struct Stage {
     LeafDesc* d_leaves = nullptr;
     double* d_red = nullptr;       // [8]
     double* d_sig = nullptr;       // device copy of a constant scalar sigma
+    bool big = false;              // scalar stage too large for the on-chip interpreter
+    double* d_scratch = nullptr;
     int fast = 0;                  // 0 interpreter, 1 sum_unary, 2 normal leaves, 3 linreg
     // fast-path operands
     int f_op = 0; const double* f_x = nullptr; double* f_xadj = nullptr;
@@ -534,8 +548,12 @@ struct fadb_expr {
 
     bool finish_stage(Stage& st)
     {
-        if ((int)st.prog.size() > MAXS) { err = "expression stage exceeds " + std::to_string(MAXS) + " nodes"; return false; }
-        if ((int)st.leaves.size() > MAXL) { err = "expression stage exceeds " + std::to_string(MAXL) + " leaves"; return false; }
+        st.big = (int)st.prog.size() > MAXS || (int)st.leaves.size() > MAXL;
+        if (st.big && st.N > 1) {
+            err = "a fused vector stage is limited to " + std::to_string(MAXS) + " nodes and " +
+                  std::to_string(MAXL) + " distinct leaves";
+            return false;
+        }
         st.term_ch = st.term == T_SUM ? 1 : st.term == T_NORMAL ? 3 : st.term == T_PROD ? 1 : 0;
         int ch = st.term_ch;
         for (auto& L : st.leaves)
@@ -723,8 +741,9 @@ struct fadb_expr {
             const Stage& st = *plan[k];
             if (st.type == 1) { o << "stage " << k << ": dot " << st.m << "x" << st.k << " * " << st.k << "x" << st.p << "\n"; continue; }
             o << "stage " << k << ": map N=" << st.N << " term=" << tn[st.term] << " ins=" << st.prog.size()
-              << " leaves=" << st.leaves.size() << " channels=" << st.nch << " fast=" << st.fast << "\n";
-            for (size_t i = 0; i < st.prog.size(); ++i) {
+              << " leaves=" << st.leaves.size() << " channels=" << st.nch << " fast=" << st.fast
+              << (st.big ? " big" : "") << "\n";
+            for (size_t i = 0; i < st.prog.size() && i < 256; ++i) {
                 const Ins& I = st.prog[i];
                 o << "  %" << i << " = " << opn[I.op];
                 if (I.op == I_LEAF) o << " L" << I.leaf << (st.leaves[I.leaf].scalar ? " (broadcast)" : "")
@@ -784,6 +803,9 @@ struct fadb_expr {
             if (st.fast == 3) {
                 if ((rc = dev_alloc((st.f_cols + 1) * sizeof(double), (void**)&st.f_part))) return rc;
             }
+            if (st.big) {
+                if ((rc = dev_alloc((2 * st.prog.size() + st.leaves.size()) * sizeof(double), (void**)&st.d_scratch))) return rc;
+            }
         }
         FADB_CUDA(cudaStreamSynchronize(c.stream));   // host vectors may be reallocated later
         bound = true;
@@ -827,10 +849,17 @@ struct fadb_expr {
         a.gate = (st.term == T_NORMAL && st.sig_vec && mode == M_B) ? st.d_red + 1 : nullptr;
         a.nch = st.nch; a.term_ch = st.term_ch;
         a.partials = c.partials; a.ticket = c.tickets + 8;
+        a.scratch = st.d_scratch;
+        if (st.big) {
+            stage_kernel<true><<<1, 32, 0, c.stream>>>(a);
+            c.launches++;
+            FADB_CUDA(cudaGetLastError());
+            return FADB_OK;
+        }
         const int threads = 128;
-        int grid = resident_grid(c, stage_kernel, threads, 0, st.N, threads);
+        int grid = resident_grid(c, stage_kernel<false>, threads, 0, st.N, threads);
         if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
-        stage_kernel<<<grid, threads, 0, c.stream>>>(a);
+        stage_kernel<false><<<grid, threads, 0, c.stream>>>(a);
         c.launches++;
         FADB_CUDA(cudaGetLastError());
         return FADB_OK;

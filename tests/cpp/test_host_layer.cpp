@@ -1,0 +1,325 @@
+// GPU: the ad:: host layer end to end, mirroring the reference's own tests
+// (test/reverse/core/{eval,bind}_unittest.cpp, test/integration/{node,ad}_inttest.cpp,
+// test/reverse/stat/normal_unittest.cpp) and the README worked examples.
+#include <fastad>
+#include <array>
+#include <random>
+
+#include "check.hpp"
+
+using namespace ad;
+
+static void eval_and_bind()
+{
+    // eval_unittest.cpp:32-48 with MockUnary f(x) = 2x
+    Var<double> x(2.31);
+    core::UnaryNode<core::MockUnary, VarView<double>> expr(x);
+    auto b = ad::bind(expr);
+    CHECK_DOUBLE_EQ(ad::autodiff(b), 4.62);
+    CHECK_DOUBLE_EQ(x.get_adj(), 2.);
+    ad::evaluate_adj(b);
+    CHECK_DOUBLE_EQ(x.get_adj(), 4.);       // adjoints accumulate
+
+    // bind_unittest.cpp:13-35
+    Var<double> w1(1.), w2(2.), w3, w4;
+    auto e = ad::bind((w3 = w1 * w2, w4 = w3 * w3));
+    for (int rep = 0; rep < 2; ++rep) {
+        CHECK_DOUBLE_EQ(ad::autodiff(e), 4.);
+        CHECK_DOUBLE_EQ(w4.get_adj(), 1.);
+        CHECK_DOUBLE_EQ(w3.get_adj(), 4.);
+        CHECK_DOUBLE_EQ(w2.get_adj(), 4.);
+        CHECK_DOUBLE_EQ(w1.get_adj(), 8.);
+        CHECK_DOUBLE_EQ(w3.get(), 2.);
+        CHECK_DOUBLE_EQ(w4.get(), 4.);
+        w1.reset_adj(); w2.reset_adj(); w3.reset_adj(); w4.reset_adj();
+    }
+    // changing a value through the host mirror is seen by the next evaluation
+    w1.get() = 3.;
+    CHECK_DOUBLE_EQ(ad::autodiff(e), 36.);
+}
+
+static void node_integration()
+{
+    // node_inttest.cpp:27-159
+    {
+        Var<double> x(3.1);
+        auto expr = ad::sin(x);
+        CHECK_DOUBLE_EQ(ad::autodiff(expr), std::sin(3.1));
+        CHECK_DOUBLE_EQ(x.get_adj(0, 0), std::cos(3.1));
+    }
+    {
+        Var<double> x(3.1);
+        auto expr = -x;
+        CHECK_DOUBLE_EQ(ad::autodiff(expr), -3.1);
+        CHECK_DOUBLE_EQ(x.get_adj(0, 0), -1.);
+    }
+    {
+        Var<double> x(3.1);
+        auto expr = ad::sin(ad::log(x));
+        CHECK_DOUBLE_EQ(ad::autodiff(expr), std::sin(std::log(3.1)));
+        CHECK_DOUBLE_EQ(x.get_adj(0, 0), std::cos(std::log(3.1)) / 3.1);
+    }
+    {
+        Var<double> x(1.), y(2.), z(3.);
+        auto expr = (x + y) - z;
+        CHECK_DOUBLE_EQ(ad::autodiff(expr), 0.);
+        CHECK_DOUBLE_EQ(x.get_adj(), 1.);
+        CHECK_DOUBLE_EQ(y.get_adj(), 1.);
+        CHECK_DOUBLE_EQ(z.get_adj(), -1.);
+    }
+    {
+        double x1 = 1.2041, x2 = -2.2314;
+        Var<double> leaf1(x1), leaf2(x2);
+        auto expr = leaf1 * leaf2 + ad::sin(leaf1 + leaf2) * leaf2 - leaf1 / leaf2;
+        auto b = ad::bind(expr);
+        CHECK_DOUBLE_EQ(ad::evaluate(b), x1 * x2 + std::sin(x1 + x2) * x2 - x1 / x2);
+        ad::evaluate_adj(b, 1);
+        CHECK_DOUBLE_EQ(leaf1.get_adj(), x2 + std::cos(x1 + x2) * x2 - 1. / x2);
+        CHECK_DOUBLE_EQ(leaf2.get_adj(), x1 + std::cos(x1 + x2) * x2 + std::sin(x1 + x2) + x1 / (x2 * x2));
+    }
+    {
+        double x1 = 1.5928, x2 = -0.291, x3 = 5.1023;
+        Var<double> leaf1(x1), leaf2(x2), leaf3(x3);
+        auto expr = leaf1 * leaf3 + ad::sin(ad::cos(leaf1 + leaf2)) * leaf2 - leaf1 / ad::exp(leaf3);
+        CHECK_DOUBLE_EQ(ad::autodiff(expr), x1 * x3 + std::sin(std::cos(x1 + x2)) * x2 - x1 / std::exp(x3));
+        CHECK_DOUBLE_EQ(leaf1.get_adj(), x3 - x2 * std::cos(std::cos(x1 + x2)) * std::sin(x1 + x2) - std::exp(-x3));
+        CHECK_DOUBLE_EQ(leaf2.get_adj(), std::sin(std::cos(x1 + x2)) - x2 * std::cos(std::cos(x1 + x2)) * std::sin(x1 + x2));
+        CHECK_DOUBLE_EQ(leaf3.get_adj(), x1 + x1 * std::exp(-x3));
+    }
+    {   // node_inttest.cpp:380-400: sum(v * v) over a 3x2 matrix == 29 (1+4+1+9+4+9 = 28? data below)
+        Var<double, mat> v(3, 2);
+        v.get() = {1., -1., 2., 2., 3., -3.};
+        auto expr = ad::sum(v * v);
+        CHECK_DOUBLE_EQ(ad::autodiff(expr), 28.);
+        for (size_t j = 0; j < 2; ++j)
+            for (size_t i = 0; i < 3; ++i) CHECK_DOUBLE_EQ(v.get_adj(i, j), 2 * v.get(i, j));
+    }
+}
+
+static void ad_integration()
+{
+    // ad_inttest.cpp:10-22, 66-140: F, G, H over x = [0.1, 2.3, -1, 4.1, -5.21]
+    std::array<double, 5> val = {0.1, 2.3, -1., 4.1, -5.21};
+    auto fresh = [&](std::vector<Var<double>>& v) {
+        v.clear();
+        for (double x : val) v.emplace_back(x);
+    };
+    std::vector<Var<double>> v;
+    std::array<Var<double>, 10> w;
+    {
+        fresh(v);
+        auto expr = (w[0] = ad::sin(v[0]) * ad::cos(v[1]), w[1] = v[2] + v[3] * v[4], w[2] = w[0] + w[1] + ad::constant(3.14));
+        ad::autodiff(expr);
+        CHECK_DOUBLE_EQ(v[0].get_adj(), std::cos(val[0]) * std::cos(val[1]));
+        CHECK_DOUBLE_EQ(v[1].get_adj(), -std::sin(val[0]) * std::sin(val[1]));
+        CHECK_DOUBLE_EQ(v[2].get_adj(), 1);
+        CHECK_DOUBLE_EQ(v[3].get_adj(), val[4]);
+        CHECK_DOUBLE_EQ(v[4].get_adj(), val[3]);
+    }
+    {
+        fresh(v);
+        for (auto& wi : w) wi.reset_adj();
+        auto expr = (w[0] = ad::sum(v.begin(), v.end(), [](const auto& var) { return ad::sin(var); }),
+                     w[1] = w[0] * w[0] - ad::sum(v.begin(), v.end(), [](const auto& var) { return ad::cos(var); }));
+        ad::autodiff(expr);
+        double sum = 0;
+        for (double x : val) sum += std::sin(x);
+        for (size_t j = 0; j < 5; ++j) CHECK_DOUBLE_EQ(v[j].get_adj(), 2 * sum * std::cos(val[j]) + std::sin(val[j]));
+    }
+    {
+        fresh(v);
+        for (auto& wi : w) wi.reset_adj();
+        auto expr = (w[0] = v[0] * v[4]);
+        ad::autodiff(expr);
+        CHECK_DOUBLE_EQ(v[0].get_adj(), val[4]);
+        CHECK_DOUBLE_EQ(v[1].get_adj(), 0);
+        CHECK_DOUBLE_EQ(v[4].get_adj(), val[0]);
+    }
+    {   // ad_inttest.cpp:143-156: 1000 scalar variables through sum/prod lambdas (crash test)
+        constexpr size_t n = 1000;
+        std::vector<Var<double>> x;
+        std::default_random_engine gen;
+        std::normal_distribution<double> dist(0., 1.);
+        x.reserve(n);
+        for (size_t i = 0; i < n; ++i) x.emplace_back(dist(gen));
+        for (auto& wi : w) wi.reset_adj();
+        auto expr = ad::bind((
+            w[0] = ad::sin(x[0]) * ad::cos(ad::exp(x[1])) + ad::exp(x[0]) - x[1],
+            w[1] = ad::sin(w[0]) - ad::sum(x.begin(), x.end(), [](const auto& var) { return ad::cos(var) * ad::exp(var); }),
+            w[2] = ad::sin(w[1]) + ad::sum(x.begin(), x.end(), [](const auto& var) { return ad::sin(var) * ad::exp(var); }),
+            w[3] = ad::sin(w[2]) + ad::prod(x.begin(), x.end(), [](const auto& var) { return ad::cos(var); })));
+        double f = ad::autodiff(expr);
+        CHECK(std::isfinite(f));
+        // d/dx_k of the last sum term alone, through sin(w2): spot-check one adjoint by finite differences
+        const size_t k = 17;
+        const double g = x[k].get_adj(), x0 = x[k].get(), h = 1e-6;
+        for (auto& xi : x) xi.reset_adj();
+        for (auto& wi : w) wi.reset_adj();
+        x[k].get() = x0 + h; double fp = ad::autodiff(expr);
+        x[k].get() = x0 - h; double fm = ad::autodiff(expr);
+        CHECK_NEAR(g, (fp - fm) / (2 * h), 1e-6 * std::max(1.0, std::fabs(g)));
+    }
+}
+
+static void stat_normal()
+{
+    // normal_unittest.cpp:105-297 through Var-owned storage
+    Var<double> sx(2.31), smu(-0.2), ssig(0.01);
+    Var<double, vec> vx(3), vmu(3), vsig(3);
+    vx.get() = {3.1, -2.3, 1.3};
+    vmu.get() = {-0.3, -2.3, -1.2};
+    vsig.get() = {0.01, 1.03, 2.41};
+    {
+        auto b = ad::bind(ad::normal_adj_log_pdf(sx, smu, ssig));
+        CHECK_DOUBLE_EQ(ad::autodiff(b), -31495.8948298140203406);
+        CHECK_DOUBLE_EQ(sx.get_adj(), -25100.);
+        CHECK_DOUBLE_EQ(smu.get_adj(), 25100.);
+        CHECK_DOUBLE_EQ(ssig.get_adj(), 6300000.0000000009313226);
+        sx.reset_adj(); smu.reset_adj(); ssig.reset_adj();
+    }
+    {
+        auto b = ad::bind(ad::normal_adj_log_pdf(vx, smu, ssig));
+        CHECK_DOUBLE_EQ(ad::autodiff(b), -87736.1844894420355558);
+        CHECK_DOUBLE_EQ(vx.get_adj(0, 0), -33000.);
+        CHECK_DOUBLE_EQ(vx.get_adj(1, 0), 20999.9999999999963620);
+        CHECK_DOUBLE_EQ(vx.get_adj(2, 0), -15000.);
+        CHECK_DOUBLE_EQ(smu.get_adj(), 27000.0000000000036380);
+        CHECK_DOUBLE_EQ(ssig.get_adj(), 17549700.);
+        vx.reset_adj(); smu.reset_adj(); ssig.reset_adj();
+    }
+    {
+        auto b = ad::bind(ad::normal_adj_log_pdf(vx, vmu, vsig));
+        CHECK_DOUBLE_EQ(ad::autodiff(b), -57796.8420570641465019);
+        CHECK_DOUBLE_EQ(vx.get_adj(0, 0), -34000.);
+        CHECK_DOUBLE_EQ(vx.get_adj(2, 0), -0.4304333603071572);
+        CHECK_DOUBLE_EQ(vmu.get_adj(2, 0), 0.4304333603071572);
+        CHECK_DOUBLE_EQ(vsig.get_adj(0, 0), 11559900.);
+        CHECK_DOUBLE_EQ(vsig.get_adj(1, 0), -0.9708737864077670);
+        CHECK_DOUBLE_EQ(vsig.get_adj(2, 0), 0.0315698758372999);
+        vx.reset_adj(); vmu.reset_adj(); vsig.reset_adj();
+        // not positive definite => -inf and no adjoint update (normal_unittest.cpp:266-272)
+        vsig.get()(0) = 0;
+        CHECK(ad::autodiff(b) == -std::numeric_limits<double>::infinity());
+        CHECK(vx.get_adj(0, 0) == 0. && vsig.get_adj(1, 0) == 0.);
+    }
+}
+
+static void readme_examples()
+{
+    // README.md:582-607 quadratic form x^T Sigma x (transpose node is out of scope: x^T is a 1x2 Var)
+    {
+        Var<double, mat> x(2, 1), xt(1, 2);
+        x.get() = {0.5, 0.6};
+        xt.get() = {0.5, 0.6};
+        auto Sigma = ad::constant({2., 3., 3., 6.}, 2, 2);
+        auto b = ad::bind(ad::dot(ad::dot(xt, Sigma), x));
+        auto f = ad::autodiff(b, std::vector<double>{1.});
+        CHECK_DOUBLE_EQ(f[0], 4.46);
+        CHECK_DOUBLE_EQ(x.get_adj(0, 0) + xt.get_adj(0, 0), 5.6);
+        CHECK_DOUBLE_EQ(x.get_adj(1, 0) + xt.get_adj(0, 1), 10.2);
+    }
+    // README.md:623-662 linear regression, row loop: loss 6655, adj [-1210, -12100]
+    {
+        const double X[5][2] = {{1, 10}, {2, 20}, {3, 30}, {4, 40}, {5, 50}};
+        const double y[5] = {32, 64, 96, 128, 160};
+        Var<double, mat> theta(2, 1);
+        theta.get() = {1., 2.};
+        Var<double, mat> xrow(1, 2), yrow(1, 1);      // device-resident row buffers
+        auto xi = ad::constant_view(xrow.data(), 1, 2);
+        auto yi = ad::constant_view(yrow.data(), 1, 1);
+        auto expr = ad::bind(ad::pow<2>(yi - ad::dot(xi, theta)));
+        double loss = 0;
+        for (int i = 0; i < 5; ++i) {
+            xrow.get() = {X[i][0], X[i][1]};
+            yrow.get() = {y[i]};
+            xrow.upload(); yrow.upload();
+            loss += ad::autodiff(expr, std::vector<double>{1.})[0];
+        }
+        CHECK_DOUBLE_EQ(loss, 6655.);
+        CHECK_DOUBLE_EQ(theta.get_adj(0, 0), -1210.);
+        CHECK_DOUBLE_EQ(theta.get_adj(1, 0), -12100.);
+    }
+    // README.md:676-745 3-layer network, row loop; goldens test/util/GenTestData.nb:691-700
+    {
+        const double parm[25] = {
+            0.04398400506863087, 0.9601256114996133, -0.5209410945118056, -0.8005256013595985,
+            -0.028791364112533024, 0.6358093220436887, 0.5846033162880331, -0.4433822901819533,
+            0.2243037009072486, 0.9750495768482685, -0.8240837134824699, 0.23629950009691214,
+            0.6663923726986263, -0.4988280521070929, -0.7814276530077855, -0.9110531473087247,
+            -0.23015593969194725, -0.13636652333316235, 0.26342534615305047, 0.8415352118678241,
+            0.9203421214171716, 0.6562896796607487, 0.848247693352548, -0.7486969470512386,
+            0.21522047772523667};
+        Var<double, vec> P(25);
+        for (int i = 0; i < 25; ++i) P.get()(i) = parm[i];
+        P.upload();
+        auto view = [&](size_t off, size_t r, size_t c) { return VarView<double, mat>(P.data() + off, P.data_adj() + off, r, c); };
+        auto A1 = view(0, 3, 2), b1 = view(6, 3, 1), A2 = view(9, 3, 3), b2 = view(18, 3, 1), A3 = view(21, 1, 3), b3 = view(24, 1, 1);
+        Var<double, mat> xrow(2, 1), yrow(1, 1);
+        auto xi = ad::constant_view(xrow.data(), 2, 1);
+        auto yi = ad::constant_view(yrow.data(), 1, 1);
+        auto x1 = ad::dot(A1, xi) + b1;
+        auto y1 = ad::sigmoid(x1);
+        auto y2 = ad::sigmoid(ad::dot(A2, y1) + b2) + x1;
+        auto y3 = ad::dot(A3, y2) + b3;
+        auto expr = ad::bind(ad::pow<2>(yi - y3));
+        double loss = 0;
+        for (int i = 1; i <= 5; ++i) {
+            xrow.get() = {1. * i, 10. * i};
+            yrow.get() = {32. * i};
+            xrow.upload(); yrow.upload();
+            loss += ad::autodiff(expr, std::vector<double>{1.})[0];
+        }
+        P.invalidate_host();      // the adjoints were written through views of P's device buffers
+        CHECK_REL(loss, 92030.04305391687, 1e-12);
+        CHECK_REL(P.get_adj()(0), -2953.051309234279, 1e-12);
+        CHECK_REL(P.get_adj()(3), -29530.51309234279, 1e-12);
+    }
+}
+
+static void vectors_and_seeds()
+{
+    // batched expression over vec Vars with a vector seed (eval.hpp:68-73); head/tail sub-views
+    const size_t n = 1000;
+    Var<double, vec> x(n), y(n);
+    for (size_t i = 0; i < n; ++i) { x.get()(i) = 0.5 + 1e-3 * i; y.get()(i) = 2.0 - 1e-3 * i; }
+    auto b = ad::bind(ad::exp(x) * y);
+    auto f = ad::autodiff(b, std::vector<double>(n, 2.0));
+    CHECK_DOUBLE_EQ(f[10], std::exp(x.get()(10)) * y.get()(10));
+    CHECK_DOUBLE_EQ(x.get_adj()(10), 2.0 * std::exp(x.get()(10)) * y.get()(10));
+    CHECK_DOUBLE_EQ(y.get_adj()(999), 2.0 * std::exp(x.get()(999)));
+    x.reset_adj(); y.reset_adj();
+    auto s = ad::bind(ad::sum(x.head(10) * x.tail(10)));
+    double v = ad::autodiff(s);
+    double ref = 0;
+    for (size_t i = 0; i < 10; ++i) ref += x.get()(i) * x.get()(n - 10 + i);
+    CHECK_REL(v, ref, 1e-14);
+    CHECK_DOUBLE_EQ(x.get_adj()(0), x.get()(n - 10));
+    CHECK_DOUBLE_EQ(x.get_adj()(n - 1), x.get()(9));
+    CHECK(x.get_adj()(500) == 0.);
+    // ad::prod with an exact zero (prod.hpp:197-207; fixture vector base_fixture.hpp:109-115)
+    Var<double, vec> p(5);
+    p.get() = {3.1, -2.3, 1.3, 0., 5.1};
+    CHECK(ad::autodiff(ad::prod(p), 2.0) == 0.);
+    CHECK_REL(p.get_adj()(3), 2.0 * 3.1 * -2.3 * 1.3 * 5.1, 1e-15);
+    CHECK(p.get_adj()(0) == 0.);
+    // Var copies are deep (var.hpp:45-55); VarView copies alias
+    Var<double> a(1.5);
+    Var<double> c = a;
+    c.get() = 2.5;
+    CHECK(a.get() == 1.5);
+    VarView<double> av = a;
+    ad::autodiff(av * av);
+    CHECK_DOUBLE_EQ(a.get_adj(), 3.0);
+}
+
+int main()
+{
+    if (fadb_init(0) != 0) { std::printf("no CUDA device: %s\n", fadb_last_error()); return 2; }
+    eval_and_bind();
+    node_integration();
+    ad_integration();
+    stat_normal();
+    readme_examples();
+    vectors_and_seeds();
+    return report("test_host_layer");
+}
