@@ -124,7 +124,10 @@ static void ad_integration()
         ad::autodiff(expr);
         double sum = 0;
         for (double x : val) sum += std::sin(x);
-        for (size_t j = 0; j < 5; ++j) CHECK_DOUBLE_EQ(v[j].get_adj(), 2 * sum * std::cos(val[j]) + std::sin(val[j]));
+        // the two terms cancel: 4 ulp of the TERMS (libdevice sin/cos differ from glibc's by <= 1 ulp)
+        for (size_t j = 0; j < 5; ++j)
+            CHECK_NEAR(v[j].get_adj(), 2 * sum * std::cos(val[j]) + std::sin(val[j]),
+                       4 * 2.3e-16 * (std::fabs(2 * sum * std::cos(val[j])) + std::fabs(std::sin(val[j]))));
     }
     {
         fresh(v);
