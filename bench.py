@@ -289,20 +289,29 @@ def run_ours(args):
         xa, ma, sa = zeros(n3), zeros(n3), zeros(n3)
         part = zeros(4); inval = zeros(1)
 
+        from fastad_b200 import sharding
+        all_reduce = (lambda t: torch.distributed.all_reduce(t)) if world > 1 else (lambda t: None)
+
         def normal_step(shape, x_adj, mu_t, sg_t, mu_adj, sg_adj, flags=0):
-            def step(i):
-                inv = None
-                if (shape & 2) and not (flags & F.TRUST_SIGMA):
+            # rank-local shard of n3 elements; N > 1: one 4-double NCCL all-reduce per evaluation
+            class Ops:
+                def sigma_check(self):
                     F.check(L.fadb_sigma_check(n3, P(sg_t), P(inval)))
-                    if world > 1:
-                        torch.distributed.all_reduce(inval)
-                    inv = inval
-                F.check(L.fadb_normal_lpdf_partial(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj),
-                                                   P(sg_adj), 1.0, flags, P(inv), P(part)))
-                if world > 1:
-                    torch.distributed.all_reduce(part)      # the one scalar exchange (NCCL)
-                F.check(L.fadb_normal_lpdf_finish(shape, n3 * world, P(part), P(x), P(mu_t), P(sg_t), None,
-                                                  P(mu_adj), P(sg_adj), 1.0, flags, None))
+                    return inval
+
+                def partial(self, cnt, seed):
+                    F.check(L.fadb_normal_lpdf_partial(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj),
+                                                       P(sg_adj), seed, flags, P(cnt), P(part)))
+                    return part
+
+                def finish(self, prt, n_total, seed):
+                    F.check(L.fadb_normal_lpdf_finish(shape, n_total, P(prt), P(x), P(mu_t), P(sg_t), None,
+                                                      P(mu_adj), P(sg_adj), seed, flags, None))
+            ops = Ops()
+
+            def step(i):
+                sharding.sharded_normal_autodiff(ops, all_reduce, shape, n3 * world, 1.0,
+                                                 not (flags & F.TRUST_SIGMA))
             return step
 
         mu1, sg1, mua1, sga1 = dev([0.1]), dev([1.3]), zeros(1), zeros(1)
@@ -327,10 +336,20 @@ def run_ours(args):
         w, wa, sg1, sga1 = zeros(cols), zeros(cols), dev([1.0]), zeros(1)
         lpart = zeros(cols + 1)
 
+        from fastad_b200 import sharding
+        all_reduce = (lambda t: torch.distributed.all_reduce(t)) if world > 1 else (lambda t: None)
+
         def lin_step(i):
             Xd, yd = Xs[i % 2]
-            F.check(L.fadb_linreg_partial(rows, cols, P(Xd), P(yd), P(w), P(lpart)))
-            F.check(L.fadb_linreg_finish(rows, cols, P(lpart), P(sg1), P(wa), P(sga1), 1.0, 0, None))
+
+            class Ops:      # rank-local row shard; N > 1: one (cols+1)-double all-reduce
+                def partial(self):
+                    F.check(L.fadb_linreg_partial(rows, cols, P(Xd), P(yd), P(w), P(lpart)))
+                    return lpart
+
+                def finish(self, prt, rows_total, seed):
+                    F.check(L.fadb_linreg_finish(rows_total, cols, P(prt), P(sg1), P(wa), P(sga1), seed, 0, None))
+            sharding.sharded_linreg_autodiff(Ops(), all_reduce, rows * world, 1.0)
         t = timed_loop(lin_step, steps2, 3, world)
         add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows")
         del Xs
