@@ -9,7 +9,10 @@
 // owns columns [16q, 16q+16), lane l owns rows {2l, 2l+1} (one 128-bit load per column).  The
 // 64x64 tile is held in REGISTERS between the forward product (t = X w) and the transposed
 // product (X^T r), so X crosses HBM exactly once: 520 algorithmic bytes per row for cols=64.
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -141,6 +144,179 @@ linreg_kernel(LinregArgs a, double* cta_partials, unsigned int* ticket, double* 
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA variant (cols <= 64, even rows, 16-byte aligned X and y): a producer thread streams 64-row
+// tiles of X (ONE cp.async.bulk.tensor.2d per 32 KB tile through a tensor map; per-column 512 B
+// bulk copies were measured issue-bound) and of y into a 3-stage shared-memory ring guarded by
+// full/empty mbarriers; four consumer warps do the two products.  Memory
+// latency is hidden by the ring instead of by occupancy (the register kernel above sits at 214
+// registers and 12 % occupancy), and each stage is released as soon as its tile is in registers.
+// ---------------------------------------------------------------------------------------
+constexpr int LT_STAGES = 3;
+constexpr int LT_CONSUMERS = 128;
+constexpr int LT_THREADS = LT_CONSUMERS + 32;
+constexpr int LT_STAGE_BYTES = 64 * LR_ROWS * 8 + LR_ROWS * 8;   // X tile [64 cols][64 rows] + y tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(LT_CONSUMERS) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(LT_THREADS)
+linreg_tma_kernel(LinregArgs a, const __grid_constant__ CUtensorMap xmap, int box_cols, double* cta_partials,
+                  unsigned int* ticket, double* out /* cols+1 */)
+{
+    extern __shared__ __align__(128) unsigned char lt_smem[];
+    unsigned char* stages = lt_smem;                                       // [LT_STAGES][LT_STAGE_BYTES]
+    double* w_s = reinterpret_cast<double*>(lt_smem + LT_STAGES * LT_STAGE_BYTES);   // [64]
+    double* pt_s = w_s + 64;                                               // [2][4][LR_ROWS]
+    double* g_s = pt_s + 2 * 4 * LR_ROWS;                                  // [64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(g_s + 64);                // [LT_STAGES]
+    uint64_t* empty = full + LT_STAGES;                                    // [LT_STAGES]
+    __shared__ bool is_last;
+    __shared__ double rr_s;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cols = (int)a.cols;
+    if (threadIdx.x < 64) w_s[threadIdx.x] = threadIdx.x < cols ? a.w[threadIdx.x] : 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const size_t ntiles = (a.rows + LR_ROWS - 1) / LR_ROWS;
+    if (warp == 4) {
+        // ------------------------------------------------ producer warp
+        int stage = 0;
+        unsigned phase = 0;
+        for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            const size_t r0 = tile * LR_ROWS;
+            const unsigned nrow = (unsigned)((a.rows - r0 < (size_t)LR_ROWS) ? a.rows - r0 : LR_ROWS);
+            unsigned char* base = stages + (size_t)stage * LT_STAGE_BYTES;
+            if (lane == 0) {
+                // one TMA tensor copy per tile (box = 64 rows x box_cols columns, rows beyond the
+                // matrix are zero-filled by the TMA unit) + one bulk copy for the y segment
+                mbar_arrive_expect_tx(&full[stage], (unsigned)box_cols * LR_ROWS * 8u + nrow * 8u);
+                tma_load_2d(base, &xmap, (int)r0, 0, &full[stage]);
+                bulk_g2s(base + 64 * LR_ROWS * 8, a.y + r0, nrow * 8u, &full[stage]);
+            }
+            if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+        }
+        return;
+    }
+    // ---------------------------------------------------- consumer warps
+    double g[LR_CPW];
+#pragma unroll
+    for (int c = 0; c < LR_CPW; ++c) g[c] = 0.0;
+    double rr = 0.0;
+    int stage = 0;
+    unsigned phase = 0, par = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t r0 = tile * LR_ROWS + 2 * lane;
+        const bool in0 = r0 < a.rows, in1 = r0 + 1 < a.rows;
+        mbar_wait(&full[stage], phase);
+        const unsigned char* base = stages + (size_t)stage * LT_STAGE_BYTES;
+        double2 xv[LR_CPW];
+#pragma unroll
+        for (int c = 0; c < LR_CPW; ++c) {
+            const int j = warp * LR_CPW + c;
+            double2 v = make_double2(0.0, 0.0);
+            if (j < cols) v = *reinterpret_cast<const double2*>(base + (size_t)j * LR_ROWS * 8 + lane * 16);
+            if (!in0) v.x = 0.0;
+            if (!in1) v.y = 0.0;
+            xv[c] = v;
+        }
+        const double2 yv = *reinterpret_cast<const double2*>(base + 64 * LR_ROWS * 8 + lane * 16);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);     // the tile is in registers: free the slot
+        if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+
+        double s0a = 0.0, s0b = 0.0, s1a = 0.0, s1b = 0.0;
+#pragma unroll
+        for (int c = 0; c < LR_CPW; c += 2) {
+            const double wa = w_s[warp * LR_CPW + c], wb = w_s[warp * LR_CPW + c + 1];
+            s0a += xv[c].x * wa; s0b += xv[c + 1].x * wb;
+            s1a += xv[c].y * wa; s1b += xv[c + 1].y * wb;
+        }
+        double* pt = pt_s + par * 4 * LR_ROWS;
+        *reinterpret_cast<double2*>(pt + warp * LR_ROWS + 2 * lane) = make_double2(s0a + s0b, s1a + s1b);
+        consumer_bar();
+        const double2 p0 = *reinterpret_cast<const double2*>(pt + 2 * lane);
+        const double2 p1 = *reinterpret_cast<const double2*>(pt + LR_ROWS + 2 * lane);
+        const double2 p2 = *reinterpret_cast<const double2*>(pt + 2 * LR_ROWS + 2 * lane);
+        const double2 p3 = *reinterpret_cast<const double2*>(pt + 3 * LR_ROWS + 2 * lane);
+        par ^= 1;
+        const double r_0 = in0 ? yv.x - ((p0.x + p1.x) + (p2.x + p3.x)) : 0.0;
+        const double r_1 = in1 ? yv.y - ((p0.y + p1.y) + (p2.y + p3.y)) : 0.0;
+        if (warp == 0) rr += r_0 * r_0 + r_1 * r_1;
+#pragma unroll
+        for (int c = 0; c < LR_CPW; ++c) g[c] += xv[c].x * r_0 + xv[c].y * r_1;
+    }
+    // ---- CTA reduce: lanes -> column totals (consumer threads only from here on)
+#pragma unroll
+    for (int c = 0; c < LR_CPW; ++c) {
+        const double v = warp_sum(g[c]);
+        if (lane == 0) g_s[warp * LR_CPW + c] = v;
+    }
+    rr = warp_sum(rr);
+    if (threadIdx.x == 0) rr_s = rr;
+    consumer_bar();
+    double* mine = cta_partials + (size_t)blockIdx.x * (a.cols + 1);
+    if (threadIdx.x == 0) mine[0] = rr_s;
+    if ((int)threadIdx.x < cols) mine[1 + threadIdx.x] = g_s[threadIdx.x];
+    __threadfence();
+    consumer_bar();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    consumer_bar();
+    if (!is_last) return;
+    __threadfence();
+    if ((int)threadIdx.x < cols + 1) {
+        double acc = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(&cta_partials[(size_t)b * (a.cols + 1) + threadIdx.x]);
+        out[threadIdx.x] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // scalar epilogue: value + w_adj + sigma_adj from {sum r^2, X^T r} (normal.hpp:350-371, dot.hpp:96-104)
 __global__ void linreg_finish_kernel(double n_total, size_t cols, const double* partial,
                                      const double* sigma, double* w_adj, double* sigma_adj,
@@ -166,6 +342,37 @@ __global__ void linreg_finish_kernel(double n_total, size_t cols, const double* 
         const double g = c * partial[1 + j];
         w_adj[j] = overwrite ? g : w_adj[j] + g;
     }
+}
+
+// rank-2 tensor map over the column-major X: dim0 = rows (contiguous), dim1 = cols
+static int encode_xmap(CUtensorMap* map, const double* X, size_t rows, size_t cols)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FADB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) {
+            set_error("fastad_b200: cuTensorMapEncodeTiled is not available from this driver");
+            return FADB_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    const cuuint64_t gstride[1] = {(cuuint64_t)rows * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)LR_ROWS, (cuuint32_t)cols};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(X), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("fastad_b200: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return FADB_ERR_CUDA;
+    }
+    return FADB_OK;
 }
 
 static double* g_ws[kMaxDevices] = {nullptr};
@@ -201,6 +408,30 @@ extern "C" int fadb_linreg_partial(size_t rows, size_t cols, const double* X, co
     double* ws;
     rc = ensure_ws(*c, (size_t)grid * (cols + 1) + cols + 1, &ws);
     if (rc) return rc;
+    static const bool no_tma = getenv("FADB_LINREG_NO_TMA") != nullptr;
+    const bool tma_ok = !no_tma && cols <= 64 && rows % 2 == 0 && rows >= LR_ROWS &&
+                        ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
+    if (tma_ok) {
+        const size_t smem = (size_t)LT_STAGES * LT_STAGE_BYTES + (64 + 2 * 4 * LR_ROWS + 64) * sizeof(double) +
+                            2 * LT_STAGES * sizeof(uint64_t);
+        static bool attr_set[kMaxDevices] = {false};
+        if (!attr_set[c->device]) {
+            FADB_CUDA(cudaFuncSetAttribute(linreg_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[c->device] = true;
+        }
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linreg_tma_kernel, LT_THREADS, smem);
+        if (per_sm < 1) per_sm = 1;
+        const int g2 = (int)std::min<size_t>(ntiles, (size_t)c->sms * std::min(per_sm, 4));
+        LinregArgs a{rows, cols, X, y, w};
+        CUtensorMap xmap;
+        rc = encode_xmap(&xmap, X, rows, cols);
+        if (rc) return rc;
+        linreg_tma_kernel<<<g2, LT_THREADS, smem, c->stream>>>(a, xmap, (int)cols, ws, c->tickets + 4, dev_partial);
+        c->launches++;
+        FADB_CUDA(cudaGetLastError());
+        return FADB_OK;
+    }
     const size_t cols_pad = ((cols + 63) / 64) * 64;
     const size_t smem = (2 * cols_pad + 4 * LR_ROWS) * sizeof(double);
     if (smem > 48 * 1024)
