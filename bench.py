@@ -102,6 +102,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (no version banner)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -401,7 +402,7 @@ def run_ours(args):
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                         "kernel": "bs_kernel<false>", "algorithmic_bytes_per_launch": BS_BYTES * n},
+                         "kernel": "bs_kernel_fast_pf<false>", "algorithmic_bytes_per_launch": BS_BYTES * n},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "options/s", "h2d_bytes_per_step": 40 * n,
                     "d2h_bytes_per_step": 64 * n, "ms_per_step": ms_e2e / e2e_steps,

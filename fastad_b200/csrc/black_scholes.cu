@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace fadb {
 
@@ -76,6 +77,53 @@ __device__ __forceinline__ BSRes bs_eval(double S, double K, double sigma, doubl
     return o;
 }
 
+// Same forward pass and adjoint sweep with the constant-bank / Newton math of fastmath.cuh:
+// one shared reciprocal per division, exp(-u^2) shared between Phi(d) and its derivative.
+__device__ __forceinline__ BSRes bs_eval_fast(double S, double K, double sigma, double tau, double r)
+{
+    constexpr double inv_sqrt2 = 0.70710678118654752440;
+    constexpr double dphi_c = 0.5 * 1.1283791670955126 * inv_sqrt2;
+
+    // ---- forward (feval) ----
+    const double sqrt_tau = fm::sqrt_(tau);
+    const double inv_K = fm::rcp_(K);
+    const double x = fm::div_(S, K, inv_K);                    // S / K
+    const double c0 = fm::log_(x);                             // cache[0]
+    const double sst = sigma * sqrt_tau;
+    const double drift = (r + sigma * sigma * 0.5) * tau;
+    const double inv_sst = fm::rcp_(sst);
+    const double c1 = fm::div_(c0 + drift, sst, inv_sst);      // cache[1]
+    const double c2 = c1 - sst;                                // cache[2]
+    double Phi1, Phi1n, E1, Phi2, Phi2n, E2;
+    fm::phi_pair(c1, Phi1, Phi1n, E1);
+    fm::phi_pair(c2, Phi2, Phi2n, E2);
+    const double PV = K * fm::exp_(-r * tau);
+
+    BSRes o;
+    o.call = Phi1 * S - Phi2 * PV;
+    o.put = Phi2n * PV - Phi1n * S;
+
+    // ---- backward (beval, seed 1), shared sweep through cache[2..0] ----
+    const double g_c2 = -(PV * (dphi_c * E2));
+    double g_c1 = S * (dphi_c * E1);
+    g_c1 += g_c2;
+    double g_sst = -g_c2;
+    const double g_num = g_c1 * inv_sst;
+    g_sst += -g_c1 * c1 * inv_sst;
+    const double g_r_chain = g_num * tau;
+    const double g_sig = g_r_chain * sigma + g_sst * sqrt_tau;
+    const double g_S_chain = g_num * fm::rcp_(x) * inv_K;      // g_num / x / K
+    const double dPV_dr = -tau * PV;
+
+    o.cS = Phi1 + g_S_chain;
+    o.cSig = g_sig;
+    o.cR = g_r_chain - Phi2 * dPV_dr;
+    o.pS = g_S_chain - Phi1n;
+    o.pSig = g_sig;
+    o.pR = g_r_chain + Phi2n * dPV_dr;
+    return o;
+}
+
 template <bool ACC>
 __device__ __forceinline__ void bs_store1(const BSOut& out, size_t i, const BSRes& o)
 {
@@ -89,46 +137,10 @@ __device__ __forceinline__ void bs_store1(const BSOut& out, size_t i, const BSRe
     }
 }
 
-template <bool ACC, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-bs_kernel(size_t n, const double* __restrict__ S, const double* __restrict__ K,
-          const double* __restrict__ sigma, const double* __restrict__ tau,
-          const double* __restrict__ r, BSOut out, bool vec_ok)
-{
-    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-    const size_t npair = vec_ok ? n / 2 : 0;
-    for (size_t p = tid; p < npair; p += nthreads) {
-        const double2 s2 = __ldg(reinterpret_cast<const double2*>(S) + p);
-        const double2 k2 = __ldg(reinterpret_cast<const double2*>(K) + p);
-        const double2 g2 = __ldg(reinterpret_cast<const double2*>(sigma) + p);
-        const double2 t2 = __ldg(reinterpret_cast<const double2*>(tau) + p);
-        const double2 r2 = __ldg(reinterpret_cast<const double2*>(r) + p);
-        const BSRes a = bs_eval(s2.x, k2.x, g2.x, t2.x, r2.x);
-        const BSRes b = bs_eval(s2.y, k2.y, g2.y, t2.y, r2.y);
-        reinterpret_cast<double2*>(out.p[0])[p] = make_double2(a.call, b.call);
-        reinterpret_cast<double2*>(out.p[1])[p] = make_double2(a.put, b.put);
-        const double ga[6] = {a.cS, a.cSig, a.cR, a.pS, a.pSig, a.pR};
-        const double gb[6] = {b.cS, b.cSig, b.cR, b.pS, b.pSig, b.pR};
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            double2* q = reinterpret_cast<double2*>(out.p[2 + k]) + p;
-            double2 v = make_double2(ga[k], gb[k]);
-            if (ACC) { const double2 old = *q; v.x += old.x; v.y += old.y; }
-            *q = v;
-        }
-    }
-    // tail (odd n) or unaligned buffers: scalar path
-    for (size_t i = npair * 2 + tid; i < n; i += nthreads) {
-        const BSRes o = bs_eval(S[i], K[i], sigma[i], tau[i], r[i]);
-        bs_store1<ACC>(out, i, o);
-    }
-}
-
 // one option per thread (64-bit coalesced accesses): half the live registers, twice the warps
-template <bool ACC, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-bs_kernel1(size_t n, const double* __restrict__ S, const double* __restrict__ K,
+template <bool ACC>
+__global__ void __launch_bounds__(256, 3)
+bs_kernel_libdevice(size_t n, const double* __restrict__ S, const double* __restrict__ K,
            const double* __restrict__ sigma, const double* __restrict__ tau,
            const double* __restrict__ r, BSOut out)
 {
@@ -137,6 +149,45 @@ bs_kernel1(size_t n, const double* __restrict__ S, const double* __restrict__ K,
     for (size_t i = tid; i < n; i += nthreads) {
         const BSRes o = bs_eval(__ldg(S + i), __ldg(K + i), __ldg(sigma + i), __ldg(tau + i), __ldg(r + i));
         bs_store1<ACC>(out, i, o);
+    }
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256, 3)
+bs_kernel_fast(size_t n, const double* __restrict__ S, const double* __restrict__ K,
+               const double* __restrict__ sigma, const double* __restrict__ tau,
+               const double* __restrict__ r, BSOut out)
+{
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += nthreads) {
+        const BSRes o = bs_eval_fast(__ldg(S + i), __ldg(K + i), __ldg(sigma + i), __ldg(tau + i), __ldg(r + i));
+        bs_store1<ACC>(out, i, o);
+    }
+}
+
+// software-pipelined variant: the next option's inputs are loaded before the current one is
+// evaluated, so the ~800-cycle load latency overlaps the ~2000-cycle evaluation of the same thread
+template <bool ACC>
+__global__ void __launch_bounds__(256, 2)
+bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restrict__ K,
+                  const double* __restrict__ sigma, const double* __restrict__ tau,
+                  const double* __restrict__ r, BSOut out)
+{
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    size_t i = tid;
+    if (i >= n) return;
+    double s = __ldg(S + i), k = __ldg(K + i), g = __ldg(sigma + i), t = __ldg(tau + i), rr = __ldg(r + i);
+    while (true) {
+        const size_t j = i + nthreads;
+        const bool more = j < n;
+        double s2 = 0, k2 = 1, g2 = 1, t2 = 1, r2 = 0;
+        if (more) { s2 = __ldg(S + j); k2 = __ldg(K + j); g2 = __ldg(sigma + j); t2 = __ldg(tau + j); r2 = __ldg(r + j); }
+        const BSRes o = bs_eval_fast(s, k, g, t, rr);
+        bs_store1<ACC>(out, i, o);
+        if (!more) break;
+        i = j; s = s2; k = k2; g = g2; t = t2; rr = r2;
     }
 }
 
@@ -153,36 +204,23 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     }
     if (n == 0) return FADB_OK;
     const int threads = 256;
+    // Measured on B200, 2^20 options per launch (us per launch): libdevice math 29.2 (variant 5);
+    // fastmath 27.7 (variant 6); fastmath + software-pipelined loads, 128 registers, 2 CTAs/SM
+    // 25.8 (default).  Two options per thread, tighter launch bounds (spills) and atomic
+    // work-stealing were measured slower and removed.
     static int variant = -1;
-    if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 5; }
-#define FADB_BS2(MINB)                                                                                  \
+    if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 21; }
+    (void)vec_ok;
+    const bool ovw = flags & FADB_OVERWRITE_ADJ;
+#define FADB_BS_LAUNCH(KERNEL)                                                                          \
     do {                                                                                                \
-        if (flags & FADB_OVERWRITE_ADJ)                                                                 \
-            bs_kernel<false, MINB><<<resident_grid(c, bs_kernel<false, MINB>, threads, 0, (n + 1) / 2, threads), \
-                                     threads, 0, st>>>(n, S, K, sigma, tau, r, o, vec_ok);              \
-        else                                                                                            \
-            bs_kernel<true, MINB><<<resident_grid(c, bs_kernel<true, MINB>, threads, 0, (n + 1) / 2, threads),   \
-                                    threads, 0, st>>>(n, S, K, sigma, tau, r, o, vec_ok);               \
+        if (ovw) KERNEL<false><<<resident_grid(c, KERNEL<false>, threads, 0, n, threads), threads, 0, st>>>(n, S, K, sigma, tau, r, o); \
+        else KERNEL<true><<<resident_grid(c, KERNEL<true>, threads, 0, n, threads), threads, 0, st>>>(n, S, K, sigma, tau, r, o);       \
     } while (0)
-#define FADB_BS1(MINB)                                                                                  \
-    do {                                                                                                \
-        if (flags & FADB_OVERWRITE_ADJ)                                                                 \
-            bs_kernel1<false, MINB><<<resident_grid(c, bs_kernel1<false, MINB>, threads, 0, n, threads), \
-                                      threads, 0, st>>>(n, S, K, sigma, tau, r, o);                     \
-        else                                                                                            \
-            bs_kernel1<true, MINB><<<resident_grid(c, bs_kernel1<true, MINB>, threads, 0, n, threads),  \
-                                     threads, 0, st>>>(n, S, K, sigma, tau, r, o);                      \
-    } while (0)
-    switch (variant) {
-    case 1: FADB_BS2(3); break;
-    case 2: FADB_BS2(4); break;
-    case 3: FADB_BS1(4); break;
-    case 4: FADB_BS1(6); break;
-    case 0: FADB_BS2(2); break;
-    default: FADB_BS1(3); break;   // measured best on B200: 1 option/thread, 60 regs, 4 CTAs/SM
-    }
-#undef FADB_BS2
-#undef FADB_BS1
+    if (variant == 5) FADB_BS_LAUNCH(bs_kernel_libdevice);
+    else if (variant == 6) FADB_BS_LAUNCH(bs_kernel_fast);
+    else FADB_BS_LAUNCH(bs_kernel_fast_pf);
+#undef FADB_BS_LAUNCH
     c.launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;

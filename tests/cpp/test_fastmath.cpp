@@ -1,0 +1,51 @@
+// CPU-only: accuracy of fastad_b200/csrc/fastmath.cuh (host build of the same header that the
+// Black-Scholes kernel compiles for the device) against glibc.
+#include <random>
+
+#include "../../fastad_b200/csrc/fastmath.cuh"
+#include "check.hpp"
+
+int main()
+{
+    std::mt19937_64 gen(12345);
+    std::uniform_real_distribution<double> U(0., 1.);
+    double e_exp = 0, e_log = 0, e_div = 0, e_sqrt = 0, e_phi_abs = 0, e_phi_tail = 0, e_E = 0;
+    for (int i = 0; i < 2000000; ++i) {
+        const double a = U(gen), b = U(gen);
+        const double x = -60.0 * a * a + 2.0 * (b - 0.5);                 // exp arguments, mostly negative
+        e_exp = std::max(e_exp, ulp_diff(fm::exp_(x), std::exp(x)));
+        const double y = std::exp(8.0 * (a - 0.5));                       // log arguments 0.018 .. 55
+        e_log = std::max(e_log, ulp_diff(fm::log_(y), std::log(y)));
+        const double p = 0.01 + 300 * a, q = 0.01 + 300 * b;
+        e_div = std::max(e_div, ulp_diff(fm::div_(p, q), p / q));
+        e_sqrt = std::max(e_sqrt, ulp_diff(fm::sqrt_(p), std::sqrt(p)));
+        const double d = 16.0 * (a - 0.5);                                // d1/d2 range
+        double Phi, PhiN, E;
+        fm::phi_pair(d, Phi, PhiN, E);
+        const double u = d * 0.70710678118654752440;
+        const double ref = 0.5 * std::erfc(-u), refn = 0.5 * std::erfc(u);
+        e_phi_abs = std::max(e_phi_abs, std::max(std::fabs(Phi - ref), std::fabs(PhiN - refn)));
+        const double tail = d < 0 ? ulp_diff(Phi, ref) : ulp_diff(PhiN, refn);
+        e_phi_tail = std::max(e_phi_tail, tail);
+        e_E = std::max(e_E, ulp_diff(E, std::exp(-(u * u))));
+    }
+    std::printf("max ulp: exp %.2f log %.2f div %.2f sqrt %.2f gauss %.2f | Phi abs %.3g, tail ulp %.2f\n",
+                e_exp, e_log, e_div, e_sqrt, e_E, e_phi_abs, e_phi_tail);
+    CHECK(e_exp <= 1.0);
+    CHECK(e_log <= 1.0);
+    CHECK(e_div <= 1.0);
+    CHECK(e_sqrt <= 1.0);
+    CHECK(e_E <= 1.0);
+    CHECK(e_phi_abs <= 4e-16);
+    CHECK(e_phi_tail <= 8.0);   // far lower tail, relative; the reference's 0.5*(erf+1) is only ABSOLUTE-accurate there
+    // edge cases
+    CHECK(fm::exp_(-800.0) == 0.0);
+    CHECK(fm::exp_(0.0) == 1.0);
+    CHECK(fm::log_(1.0) == 0.0);
+    double P, N, E;
+    fm::phi_pair(0.0, P, N, E);
+    CHECK(std::fabs(P - 0.5) <= 1.2e-16 && std::fabs(N - 0.5) <= 1.2e-16 && E == 1.0);
+    fm::phi_pair(40.0, P, N, E);
+    CHECK(P == 1.0 && N == 0.0 && E == 0.0);
+    return report("test_fastmath");
+}

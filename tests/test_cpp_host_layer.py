@@ -31,6 +31,11 @@ def test_cpp_type_layer_and_planner(built):
     assert "test_types:" in out
 
 
+def test_cpp_fastmath_accuracy_against_glibc(built):
+    out = _run(built, "test_fastmath")
+    assert "test_fastmath:" in out
+
+
 @pytest.mark.gpu
 def test_cpp_host_layer_reference_tests(built):
     out = _run(built, "test_host_layer")
