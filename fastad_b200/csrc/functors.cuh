@@ -5,6 +5,7 @@
 // libdevice exp/log/erf differ from glibc's by <= 1-2 ulp).
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace fadb {
 
@@ -24,8 +25,21 @@ FADB_UNARY(FADB_TAN, tan(x), seed / (cos(x) * cos(x)))
 FADB_UNARY(FADB_ASIN, asin(x), seed / sqrt(1. - x * x))
 FADB_UNARY(FADB_ACOS, acos(x), -(seed / sqrt(1. - x * x)))
 FADB_UNARY(FADB_ATAN, atan(x), seed / (1. + x * x))
-FADB_UNARY(FADB_EXP, exp(x), seed * f)
-FADB_UNARY(FADB_LOG, log(x), seed / x)
+// exp / log: constant-bank polynomials of fastmath.cuh (<= 1 ulp, validated against glibc on the
+// host) on the ordinary range, libdevice for everything else (NaN, inf, overflow, subnormal
+// results, non-positive log arguments) so that IEEE special-case behaviour is unchanged.
+__device__ __forceinline__ double exp_guarded(double x)
+{
+    return (fabs(x) <= 700.0) ? fm::exp_(x) : exp(x);
+}
+__device__ __forceinline__ double log_guarded(double x)
+{
+    const unsigned long long ux = (unsigned long long)__double_as_longlong(x);
+    // normal, positive, finite
+    return (ux - 0x0010000000000000ull < 0x7fe0000000000000ull) ? fm::log_(x) : log(x);
+}
+FADB_UNARY(FADB_EXP, exp_guarded(x), seed * f)
+FADB_UNARY(FADB_LOG, log_guarded(x), seed / x)
 FADB_UNARY(FADB_SQRT, sqrt(x), 0.5 * seed / f)
 FADB_UNARY(FADB_ERF, erf(x), 1.1283791670955126 * seed * exp(-x * x))
 FADB_UNARY(FADB_SINH, sinh(x), seed * cosh(x))

@@ -10,13 +10,17 @@
 // reduced across the CTA with warp shuffles and across CTAs by the last-arriving CTA.
 // The matrices are 3x2, 3x3 and 1x3: far below a DMMA tile, so the FP64 tensor path is not used.
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace fadb {
 
 constexpr int NP = 25;            // parameters: A1(3x2) b1(3) A2(3x3) b2(3) A3(1x3) b3(1), column-major
 constexpr int NOUT = NP + 1;      // + loss
 
-__device__ __forceinline__ double sigmoid_f(double x) { return 1 / (1 + exp(-x)); }
+// exp on the ordinary range through fastmath.cuh (<= 1 ulp), libdevice otherwise
+// 1 / (1 + e) by Newton reciprocal; e = +inf (x < -709) gives 0 like the IEEE division would
+__device__ __forceinline__ double inv1p(double e) { return e > 1e300 ? 0.0 : fm::rcp_(1 + e); }
+__device__ __forceinline__ double exp_s(double x) { return (fabs(x) <= 700.0) ? fm::exp_(x) : exp(x); }
 
 __global__ void __launch_bounds__(256)
 mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict__ y,
@@ -44,18 +48,19 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
     for (size_t row = tid; row < batch; row += nth) {
         const double xa = __ldg(X + row), xb = __ldg(X + batch + row), yy = __ldg(y + row);
         // ---- forward ----
-        double x1[3], e1[3], y1[3], h[3], e2[3], y2[3];
+        double x1[3], e1[3], y1[3], h[3], e2[3], s2[3], y2[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             x1[i] = (A1[i] * xa + A1[i + 3] * xb) + b1[i];          // dot(A1, xi) + b1
-            e1[i] = exp(-x1[i]);
-            y1[i] = 1 / (1 + e1[i]);                                // sigmoid, unary.hpp:273-275
+            e1[i] = exp_s(-x1[i]);
+            y1[i] = inv1p(e1[i]);                            // sigmoid = 1/(1+exp(-x)), unary.hpp:273-275
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             h[i] = ((A2[i] * y1[0] + A2[i + 3] * y1[1]) + A2[i + 6] * y1[2]) + b2[i];
-            e2[i] = exp(-h[i]);
-            y2[i] = 1 / (1 + e2[i]) + x1[i];                        // sigmoid(...) + x1
+            e2[i] = exp_s(-h[i]);
+            s2[i] = inv1p(e2[i]);
+            y2[i] = s2[i] + x1[i];                                  // sigmoid(...) + x1
         }
         const double y3 = ((A3[0] * y2[0] + A3[1] * y2[1]) + A3[2] * y2[2]) + b3;
         const double d = yy - y3;
@@ -74,7 +79,7 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
         double g_h[3], g_y1[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            g_h[i] = g_y2[i] * e2[i] / ((e2[i] + 1) * (e2[i] + 1)); // Sigmoid::bmap, unary.hpp:276-278
+            g_h[i] = g_y2[i] * e2[i] * (s2[i] * s2[i]);             // Sigmoid::bmap seed*e/((e+1)(e+1)), unary.hpp:276-278
             acc[18 + i] += g_h[i];                                  // b2
         }
 #pragma unroll
@@ -88,7 +93,7 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             // x1 enters twice (README form has the sub-tree twice): through y1 and the jump
-            const double g_x1 = g_y1[i] * e1[i] / ((e1[i] + 1) * (e1[i] + 1)) + g_y2[i];
+            const double g_x1 = g_y1[i] * e1[i] * (y1[i] * y1[i]) + g_y2[i];
             acc[i] += g_x1 * xa;                                    // A1_adj = adj * xi^T
             acc[i + 3] += g_x1 * xb;
             acc[6 + i] += g_x1;                                     // b1

@@ -914,7 +914,7 @@ template <class E> struct is_bound<ExprBind<E>> : std::true_type {};
 template <class T> inline constexpr bool is_bound_v = is_bound<std::decay_t<T>>::value;
 
 template <class B>
-inline auto fetch(B& b, const std::vector<double>& v)
+inline auto fetch(B&, const std::vector<double>& v)
 {
     if constexpr (util::is_scl_v<B>) return v[0];
     else return v;
