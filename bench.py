@@ -369,6 +369,41 @@ def run_ours(args):
             add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples",
                 {"bound": "fp64 pipe / launch latency, not HBM"})
 
+    if "expr" in wl:
+        # the GENERIC path (ad::bind -> planner -> interpreter kernel), same C-ABI calls the C++
+        # host layer makes: (i) the 3-deep chain of SURVEY.md 8d C2, sum(-0.5*pow<2>((x - c*w0)/w1)),
+        # (ii) the batched Black-Scholes call expression with vec leaves and 3 vec placeholders
+        import exprs
+        n2 = 1 << 24
+        e = F.Expr()
+        x = e.var(synth.sum_inputs(n2))
+        w0, w1 = e.var(2.0), e.var(1.3)
+        cc = e.const(synth.sum_inputs(n2, seed=5))
+        z = e.binary("div", e.binary("sub", x, e.binary("mul", w0, cc)), w1)
+        e.bind(e.sum(e.binary("mul", e.const(-0.5), e.pow(2, z))))
+
+        def chain_step(i):
+            F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+        t = timed_loop(chain_step, steps2, 3, world)
+        add("expr_sum_chain_2^24_interpreter", 32 * n2, t, steps2, n2, "elements",
+            {"note": "x read + c read + x_adj RMW = 32 B/elem; 2 scalar adjoints by reduction channels"})
+        del e
+        nb = BS_N
+        exprs.RNG = np.random.default_rng(1)
+        e = F.Expr()
+        root, leaves, _ = exprs.black_scholes_vec(nb)(e)
+        e.bind(root)
+        ones = torch.ones(nb, dtype=torch.float64, device="cuda")
+
+        def bs_expr_step(i):
+            F.check(L.fadb_expr_autodiff(e.h, 0.0, P(ones), None))
+        t = timed_loop(bs_expr_step, steps2, 3, world)
+        # S,K,sigma,tau,sqrt_tau,r reads (48) + seed read (8) + price store (8) + 3 adj RMW (48)
+        # + 3 placeholders: value store + adjoint RMW (72) = 184 B/option
+        add("expr_black_scholes_call_2^20_interpreter", 184 * nb, t, steps2, nb, "options",
+            {"note": "one autodiff of the CALL expression only, reference placeholder semantics kept"})
+        del e
+
     clk.__exit__()
     clocks = clk.summary()     # sampled over every timed region above (headline first)
 
@@ -424,7 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline only, small CPU sample")
-    ap.add_argument("--workloads", default="sum,normal,linreg,mlp3",
+    ap.add_argument("--workloads", default="sum,normal,linreg,mlp3,expr",
                     help="secondary workloads to time besides the headline (comma list)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()

@@ -39,7 +39,15 @@ __device__ __forceinline__ double log_guarded(double x)
     return (ux - 0x0010000000000000ull < 0x7fe0000000000000ull) ? fm::log_(x) : log(x);
 }
 FADB_UNARY(FADB_EXP, exp_guarded(x), seed * f)
-FADB_UNARY(FADB_LOG, log_guarded(x), seed / x)
+// Log::bmap seed / x (unary.hpp:250-255): Newton reciprocal + residual correction (<= 1 ulp) when
+// both operands are ordinary, IEEE division otherwise
+__device__ __forceinline__ double div_guarded(double a, double d)
+{
+    const double ad = fabs(d), aa = fabs(a);
+    if (ad > 1e-290 && ad < 1e290 && aa < 1e290 && (aa > 1e-290 || aa == 0.0)) return fm::div_(a, d);
+    return a / d;
+}
+FADB_UNARY(FADB_LOG, log_guarded(x), div_guarded(seed, x))
 FADB_UNARY(FADB_SQRT, sqrt(x), 0.5 * seed / f)
 FADB_UNARY(FADB_ERF, erf(x), 1.1283791670955126 * seed * exp(-x * x))
 FADB_UNARY(FADB_SINH, sinh(x), seed * cosh(x))
