@@ -20,6 +20,7 @@
 // Hot expression shapes are recognised at bind time and routed to the hand-written kernels
 // (map_reduce.cu, normal.cu, linreg.cu); everything else runs on the interpreter below.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -101,10 +102,16 @@ __device__ __forceinline__ double block_prod_all(double p, double* sm)
 // BIG = false: program and leaf table staged in shared memory, node values in thread-local
 // storage.  BIG = true (scalar stages with more than MAXS nodes, e.g. ad::sum over a thousand
 // scalar Vars, test/integration/ad_inttest.cpp:143-156): one thread, everything in global memory.
-template <bool BIG>
+// STORE selects where a thread keeps its node values / adjoints / leaf accumulators:
+//   0 = thread-local arrays (fallback), 1 = dynamic shared memory, laid out [slot][thread] so
+//   that a warp access is conflict-free (default: local arrays of this size spill through L1 into
+//   L2/DRAM -- ncu showed 3.6x the algorithmic DRAM writes), 2 = global scratch (BIG programs).
+template <int STORE>
 __global__ void __launch_bounds__(128)
 stage_kernel(StageArgs a)
 {
+    constexpr bool BIG = STORE == 2;
+    extern __shared__ double s_dyn[];
     __shared__ Ins s_prog_sm[BIG ? 1 : MAXS];
     __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
     __shared__ double s_red[32 * MAXCH];
@@ -135,10 +142,14 @@ stage_kernel(StageArgs a)
     for (int c = 0; c < MAXCH; ++c) acc[c] = 0.0;
     double p_nz = 1.0, p_zeros = 0.0;
 
-    double v_loc[BIG ? 1 : MAXS], g_loc[BIG ? 1 : MAXS], l_loc[BIG ? 1 : MAXL];
-    double* v = BIG ? a.scratch : v_loc;
-    double* g = BIG ? a.scratch + a.nins : g_loc;
-    double* lacc = BIG ? a.scratch + 2 * (size_t)a.nins : l_loc;
+    double v_loc[STORE == 0 ? MAXS : 1], g_loc[STORE == 0 ? MAXS : 1], l_loc[STORE == 0 ? MAXL : 1];
+    const int vs = STORE == 1 ? (int)blockDim.x : 1;             // slot stride
+    double* vb = STORE == 0 ? v_loc : STORE == 1 ? s_dyn + threadIdx.x : a.scratch;
+    double* gb = STORE == 0 ? g_loc : vb + (size_t)a.nins * vs;
+    double* lb = STORE == 0 ? l_loc : gb + (size_t)a.nins * vs;
+#define V(k) vb[(k) * vs]
+#define G(k) gb[(k) * vs]
+#define LA(k) lb[(k) * vs]
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = tid; i < a.N; i += nth) {
@@ -149,25 +160,25 @@ stage_kernel(StageArgs a)
             switch (I.op) {
             case I_LEAF: { const LeafDesc& L = s_leaf[I.leaf]; r = L.scalar ? L.val[0] : L.val[i]; break; }
             case I_CONST: r = I.imm; break;
-            case I_UNARY: r = unary_f_rt(I.fn, v[I.a]); break;
-            case I_BINARY: r = binary_f_rt(I.fn, v[I.a], v[I.b]); break;
-            case I_POW: r = pow_int((long)I.fn, v[I.a]); break;
+            case I_UNARY: r = unary_f_rt(I.fn, V(I.a)); break;
+            case I_BINARY: r = binary_f_rt(I.fn, V(I.a), V(I.b)); break;
+            case I_POW: r = pow_int((long)I.fn, V(I.a)); break;
             case I_EQ: {                                       // eq.hpp:89-92
-                r = v[I.a];
+                r = V(I.a);
                 if (fwd_out) { const LeafDesc& L = s_leaf[I.leaf]; const_cast<double*>(L.val)[L.scalar ? 0 : i] = r; }
                 break;
             }
-            default: r = v[I.b]; break;                        // I_GLUE, glue.hpp:67-71
+            default: r = V(I.b); break;                        // I_GLUE, glue.hpp:67-71
             }
-            v[k] = r;
+            V(k) = r;
         }
         // ------------------------------------------------ terminal, forward part
         double nrm_d = 0, nrm_s = 1, nrm_z = 0;
-        if (a.term == T_SUM) acc[0] += v[a.root];
-        else if (a.term == T_PROD) { if (v[a.root] == 0) p_zeros += 1.0; else p_nz *= v[a.root]; }
+        if (a.term == T_SUM) acc[0] += V(a.root);
+        else if (a.term == T_PROD) { if (V(a.root) == 0) p_zeros += 1.0; else p_nz *= V(a.root); }
         else if (a.term == T_NORMAL) {
-            nrm_d = v[a.nx] - v[a.nm];
-            nrm_s = v[a.ns];
+            nrm_d = V(a.nx) - V(a.nm);
+            nrm_s = V(a.ns);
             if (a.sig_vec) {
                 if (!(nrm_s > 0)) acc[2] += 1.0;
                 nrm_z = nrm_d / nrm_s;
@@ -179,61 +190,61 @@ stage_kernel(StageArgs a)
             } else {
                 acc[0] += nrm_d * nrm_d;                       // squaredNorm, normal.hpp:244
             }
-        } else if (fwd_out && a.out_vec) a.out_vec[i] = v[a.root];
+        } else if (fwd_out && a.out_vec) a.out_vec[i] = V(a.root);
         if (!back) continue;
 
         // ------------------------------------------------ adjoint sweep (beval)
-        for (int k = 0; k < a.nins; ++k) g[k] = 0.0;
-        for (int k = 0; k < a.nleaves; ++k) lacc[k] = 0.0;
+        for (int k = 0; k < a.nins; ++k) G(k) = 0.0;
+        for (int k = 0; k < a.nleaves; ++k) LA(k) = 0.0;
         const double sd = a.seed_vec ? a.seed_vec[i] : seed_s;
         if (!gated) {
             if (a.term == T_NORMAL) {
-                const double x = v[a.nx], m = v[a.nm], s = nrm_s, d = nrm_d;
+                const double x = V(a.nx), m = V(a.nm), s = nrm_s, d = nrm_d;
                 if (a.sig_vec) {
                     const double s2 = s * s;
-                    if (a.mu_vec) { g[a.nx] += sd * (m - x) / s2; g[a.nm] += sd * d / s2; }      // :563-564
-                    else { g[a.nx] += (sd / s2) * (m - x); g[a.nm] += sd * (d / s2); }           // :471-474
-                    g[a.ns] += (sd / s) * (nrm_z * nrm_z - 1.);                                  // :468, 560
+                    if (a.mu_vec) { G(a.nx) += sd * (m - x) / s2; G(a.nm) += sd * d / s2; }      // :563-564
+                    else { G(a.nx) += (sd / s2) * (m - x); G(a.nm) += sd * (d / s2); }           // :471-474
+                    G(a.ns) += (sd / s) * (nrm_z * nrm_z - 1.);                                  // :468, 560
                 } else if (a.N == 1) {
                     const double inv_s = 1. / s, z = d * inv_s;                                  // :158-171
-                    g[a.ns] += sd * (z * z - 1) * inv_s;
+                    G(a.ns) += sd * (z * z - 1) * inv_s;
                     const double adj = sd * z * inv_s;
-                    g[a.nm] += adj;
-                    g[a.nx] += -adj;
+                    G(a.nm) += adj;
+                    G(a.nx) += -adj;
                 } else {
                     const double inv_s = 1. / s, inv_s_sq = inv_s * inv_s, c = sd * inv_s_sq;
-                    g[a.nx] += c * (m - x);                                                      // :282, 371
-                    g[a.nm] += a.mu_vec ? c * d : sd * (d * inv_s_sq);                           // :370, 277
-                    g[a.ns] += sd * ((d * d) / (s * s) - 1.) * inv_s;                            // :273 per element
+                    G(a.nx) += c * (m - x);                                                      // :282, 371
+                    G(a.nm) += a.mu_vec ? c * d : sd * (d * inv_s_sq);                           // :370, 277
+                    G(a.ns) += sd * ((d * d) / (s * s) - 1.) * inv_s;                            // :273 per element
                 }
             } else if (a.term == T_PROD) {
-                const double e = v[a.root];                                                      // prod.hpp:194-207
-                g[a.root] = (e == 0) ? sd * ((pr_zeros > 1) ? 0.0 : pr_pnz) : sd * (pr_val / e);
+                const double e = V(a.root);                                                      // prod.hpp:194-207
+                G(a.root) = (e == 0) ? sd * ((pr_zeros > 1) ? 0.0 : pr_pnz) : sd * (pr_val / e);
             } else {
-                g[a.root] = sd;
+                G(a.root) = sd;
             }
             for (int k = a.nins - 1; k >= 0; --k) {
                 const Ins I = s_prog[k];
-                const double s = g[k];
+                const double s = G(k);
                 switch (I.op) {
-                case I_LEAF: lacc[I.leaf] += s; break;
+                case I_LEAF: LA(I.leaf) += s; break;
                 case I_CONST: break;
-                case I_UNARY: g[I.a] += unary_b_rt(I.fn, s, v[I.a], v[k]); break;               // unary.hpp:81-89
+                case I_UNARY: G(I.a) += unary_b_rt(I.fn, s, V(I.a), V(k)); break;               // unary.hpp:81-89
                 case I_BINARY:                                                                    // binary.hpp:120-136
-                    g[I.b] += binary_br_rt(I.fn, s, v[I.a], v[I.b], v[k]);
-                    g[I.a] += binary_bl_rt(I.fn, s, v[I.a], v[I.b], v[k]);
+                    G(I.b) += binary_br_rt(I.fn, s, V(I.a), V(I.b), V(k));
+                    G(I.a) += binary_bl_rt(I.fn, s, V(I.a), V(I.b), V(k));
                     break;
-                case I_POW: g[I.a] += pow_bmap((long)I.fn, s, v[I.a], v[k]); break;             // pow.hpp:101-162
+                case I_POW: G(I.a) += pow_bmap((long)I.fn, s, V(I.a), V(k)); break;             // pow.hpp:101-162
                 case I_EQ: {                                                                      // eq.hpp:101-107
                     const LeafDesc& L = s_leaf[I.leaf];
-                    if (L.scalar && a.N > 1) { g[I.a] += s + lacc[I.leaf]; break; }              // not produced by the planner
-                    const double tot = (L.adj[i] + lacc[I.leaf]) + s;
+                    if (L.scalar && a.N > 1) { G(I.a) += s + LA(I.leaf); break; }              // not produced by the planner
+                    const double tot = (L.adj[i] + LA(I.leaf)) + s;
                     L.adj[i] = tot;
-                    lacc[I.leaf] = 0.0;
-                    g[I.a] += tot;
+                    LA(I.leaf) = 0.0;
+                    G(I.a) += tot;
                     break;
                 }
-                default: g[I.b] += s; break;                                                      // I_GLUE: lhs gets 0
+                default: G(I.b) += s; break;                                                      // I_GLUE: lhs gets 0
                 }
             }
         }
@@ -242,12 +253,12 @@ stage_kernel(StageArgs a)
             const LeafDesc& L = s_leaf[k];
             if (L.adj_mode == 0) continue;
             if (L.assigned) {          // reads that precede the assignment in program order
-                if (lacc[k] != 0.0) L.adj[i] += lacc[k];
+                if (LA(k) != 0.0) L.adj[i] += LA(k);
                 continue;
             }
-            if (L.scalar && a.N > 1) { acc[L.channel] += lacc[k]; continue; }
-            if (L.adj_mode == 2) L.adj[i] = lacc[k];
-            else if (!gated) L.adj[i] += lacc[k];
+            if (L.scalar && a.N > 1) { acc[L.channel] += LA(k); continue; }
+            if (L.adj_mode == 2) L.adj[i] = LA(k);
+            else if (!gated) L.adj[i] += LA(k);
         }
     }
 
@@ -325,6 +336,10 @@ stage_kernel(StageArgs a)
         }
     }
 }
+
+#undef V
+#undef G
+#undef LA
 
 // ------------------------------------------------------------------------ DotNode kernels
 // dot.hpp:89-104: V = L R; R_adj (+)= L^T A; L_adj (+)= A R^T.  Column-major, naive (one thread
@@ -851,15 +866,33 @@ struct fadb_expr {
         a.partials = c.partials; a.ticket = c.tickets + 8;
         a.scratch = st.d_scratch;
         if (st.big) {
-            stage_kernel<true><<<1, 32, 0, c.stream>>>(a);
+            stage_kernel<2><<<1, 32, 0, c.stream>>>(a);
             c.launches++;
             FADB_CUDA(cudaGetLastError());
             return FADB_OK;
         }
-        const int threads = 128;
-        int grid = resident_grid(c, stage_kernel<false>, threads, 0, st.N, threads);
-        if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
-        stage_kernel<false><<<grid, threads, 0, c.stream>>>(a);
+        const int threads = st.N >= 4096 ? 128 : 32;
+        const size_t smem = (2 * st.prog.size() + st.leaves.size()) * threads * sizeof(double);
+        // Measured on B200 (profiles/): shared-memory slots are NOT a win -- 0.99 vs 1.05 ms on a
+        // 10-node chain, and 3x slower on the 50-node Black-Scholes stage where 111 KB per CTA
+        // collapses occupancy; the interpreter is issue-bound, not local-memory-bound.  Local
+        // arrays stay the default; FADB_STAGE_SMEM=1 selects the shared-memory layout.
+        static const bool use_local = getenv("FADB_STAGE_SMEM") == nullptr;
+        if (use_local) {
+            int grid = resident_grid(c, stage_kernel<0>, threads, 0, st.N, threads);
+            if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
+            stage_kernel<0><<<grid, threads, 0, c.stream>>>(a);
+        } else {
+            static bool attr_set[kMaxDevices] = {false};
+            if (!attr_set[c.device]) {
+                FADB_CUDA(cudaFuncSetAttribute(stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)((2 * MAXS + MAXL) * 128 * sizeof(double))));
+                attr_set[c.device] = true;
+            }
+            int grid = resident_grid(c, stage_kernel<1>, threads, smem, st.N, threads);
+            if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
+            stage_kernel<1><<<grid, threads, smem, c.stream>>>(a);
+        }
         c.launches++;
         FADB_CUDA(cudaGetLastError());
         return FADB_OK;
