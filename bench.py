@@ -251,10 +251,12 @@ def run_ours(args):
     # ---------------- the other BASELINE configs (rank-local unless stated)
     workloads = {}
 
-    def add(name, bytes_per_launch, ms_total, steps, units, unit_name, extra=None):
+    def add(name, bytes_per_launch, ms_total, steps, units, unit_name, extra=None, sharded=False):
+        # sharded=True: ONE evaluation spans all ranks (element/row-range shards + all-reduce);
+        # otherwise every rank evaluates its own independent instance.
         k_ms = ms_total / steps
         gbs = bytes_per_launch / (k_ms * 1e-3) / 1e9
-        workloads[name] = {"ms_per_step": k_ms, "evals_per_s": world * steps / (ms_total * 1e-3),
+        workloads[name] = {"ms_per_step": k_ms, "evals_per_s": (1 if sharded else world) * steps / (ms_total * 1e-3),
                            unit_name + "_per_s": world * units * steps / (ms_total * 1e-3),
                            "hbm_gbs": gbs, "roofline_frac": gbs / peak_gbs,
                            "algorithmic_bytes": bytes_per_launch}
@@ -318,13 +320,14 @@ def run_ours(args):
         mu1, sg1, mua1, sga1 = dev([0.1]), dev([1.3]), zeros(1), zeros(1)
         t = timed_loop(normal_step(3, xa, mu, sg, ma, sa), steps2, 3, world)
         add("normal_vvv_2^26", 72 * n3, t, steps2, n3, "elements",
-            {"note": "exact semantics: +8 B/elem sigma validity pre-pass (80 B/elem traffic)"})
+            {"note": "exact semantics: +8 B/elem sigma validity pre-pass (80 B/elem traffic); per-GPU shard"},
+            sharded=True)
         t = timed_loop(normal_step(3, xa, mu, sg, ma, sa, F.TRUST_SIGMA), steps2, 3, world)
-        add("normal_vvv_2^26_trust_sigma", 72 * n3, t, steps2, n3, "elements")
+        add("normal_vvv_2^26_trust_sigma", 72 * n3, t, steps2, n3, "elements", sharded=True)
         t = timed_loop(normal_step(0, xa, mu1, sg1, mua1, sga1), steps2, 3, world)
-        add("normal_vss_2^26", 24 * n3, t, steps2, n3, "elements")
+        add("normal_vss_2^26", 24 * n3, t, steps2, n3, "elements", sharded=True)
         t = timed_loop(normal_step(0, None, mu1, sg1, mua1, sga1), steps2, 3, world)
-        add("normal_vss_xconst_2^26", 8 * n3, t, steps2, n3, "elements")
+        add("normal_vss_xconst_2^26", 8 * n3, t, steps2, n3, "elements", sharded=True)
         del x, mu, sg, xa, ma, sa
 
     if "linreg" in wl:
@@ -352,7 +355,7 @@ def run_ours(args):
                     F.check(L.fadb_linreg_finish(rows_total, cols, P(prt), P(sg1), P(wa), P(sga1), seed, 0, None))
             sharding.sharded_linreg_autodiff(Ops(), all_reduce, rows * world, 1.0)
         t = timed_loop(lin_step, steps2, 3, world)
-        add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows")
+        add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows", sharded=True)
         del Xs
 
     if "mlp3" in wl:
