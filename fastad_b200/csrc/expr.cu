@@ -52,6 +52,14 @@ struct Ins {
     int op, fn, a, b, leaf, pad;
     double imm;
 };
+// device encoding: 16 bytes (one LDS.128), a single flat opcode so that the interpreter has ONE
+// dense switch (a jump table) per direction instead of nested compare chains
+enum : short { F_LEAF_V = 0, F_LEAF_S, F_CONST, F_EQ, F_GLUE, F_POW, F_POW2, F_UNARY = 8 /* +fn, mock2x = +15 */,
+               F_BINARY = 24 /* +fn, mockb = +4 */ };
+struct DIns {
+    short code, a, b, leaf;   // POW: exponent in `leaf`
+    double imm;
+};
 struct LeafDesc {
     const double* val;
     double* adj;
@@ -66,7 +74,7 @@ constexpr int MAXL = 24;    // distinct leaves per stage
 constexpr int MAXCH = 8;    // reduction channels per stage
 
 struct StageArgs {
-    const Ins* prog;
+    const DIns* prog;
     const LeafDesc* leaves;
     int nins, nleaves;
     unsigned long long N;
@@ -112,11 +120,11 @@ stage_kernel(StageArgs a)
 {
     constexpr bool BIG = STORE == 2;
     extern __shared__ double s_dyn[];
-    __shared__ Ins s_prog_sm[BIG ? 1 : MAXS];
+    __shared__ DIns s_prog_sm[BIG ? 1 : MAXS];
     __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
     __shared__ double s_red[32 * MAXCH];
     __shared__ bool s_last;
-    const Ins* s_prog = BIG ? a.prog : s_prog_sm;
+    const DIns* s_prog = BIG ? a.prog : s_prog_sm;
     const LeafDesc* s_leaf = BIG ? a.leaves : s_leaf_sm;
     if (!BIG) {
         for (int k = threadIdx.x; k < a.nins; k += blockDim.x) s_prog_sm[k] = a.prog[k];
@@ -155,20 +163,30 @@ stage_kernel(StageArgs a)
     for (unsigned long long i = tid; i < a.N; i += nth) {
         // ------------------------------------------------ forward (feval)
         for (int k = 0; k < a.nins; ++k) {
-            const Ins I = s_prog[k];
+            const DIns I = s_prog[k];
             double r;
-            switch (I.op) {
-            case I_LEAF: { const LeafDesc& L = s_leaf[I.leaf]; r = L.scalar ? L.val[0] : L.val[i]; break; }
-            case I_CONST: r = I.imm; break;
-            case I_UNARY: r = unary_f_rt(I.fn, V(I.a)); break;
-            case I_BINARY: r = binary_f_rt(I.fn, V(I.a), V(I.b)); break;
-            case I_POW: r = pow_int((long)I.fn, V(I.a)); break;
-            case I_EQ: {                                       // eq.hpp:89-92
+            switch (I.code) {
+            case F_LEAF_V: r = s_leaf[I.leaf].val[i]; break;              // var_view.hpp:69
+            case F_LEAF_S: r = s_leaf[I.leaf].val[0]; break;
+            case F_CONST: r = I.imm; break;
+            case F_EQ: {                                                   // eq.hpp:89-92
                 r = V(I.a);
                 if (fwd_out) { const LeafDesc& L = s_leaf[I.leaf]; const_cast<double*>(L.val)[L.scalar ? 0 : i] = r; }
                 break;
             }
-            default: r = V(I.b); break;                        // I_GLUE, glue.hpp:67-71
+            case F_GLUE: r = V(I.b); break;                               // glue.hpp:67-71
+            case F_POW: r = pow_int((long)I.leaf, V(I.a)); break;
+            case F_POW2: { const double x = V(I.a); r = x * x; break; }
+#define U(FN) case F_UNARY + FN: r = Unary<FN>::f(V(I.a)); break;
+            U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
+            U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
+#undef U
+            case F_UNARY + 15: r = 2 * V(I.a); break;                     // MockUnary
+            case F_BINARY + FADB_ADD: r = V(I.a) + V(I.b); break;         // binary.hpp:265-338
+            case F_BINARY + FADB_SUB: r = V(I.a) - V(I.b); break;
+            case F_BINARY + FADB_MUL: r = V(I.a) * V(I.b); break;
+            case F_BINARY + FADB_DIV: r = V(I.a) / V(I.b); break;
+            default: r = V(I.a) - 2 * V(I.b); break;                      // MockBinary
             }
             V(k) = r;
         }
@@ -224,27 +242,34 @@ stage_kernel(StageArgs a)
                 G(a.root) = sd;
             }
             for (int k = a.nins - 1; k >= 0; --k) {
-                const Ins I = s_prog[k];
+                const DIns I = s_prog[k];
                 const double s = G(k);
-                switch (I.op) {
-                case I_LEAF: LA(I.leaf) += s; break;
-                case I_CONST: break;
-                case I_UNARY: G(I.a) += unary_b_rt(I.fn, s, V(I.a), V(k)); break;               // unary.hpp:81-89
-                case I_BINARY:                                                                    // binary.hpp:120-136
-                    G(I.b) += binary_br_rt(I.fn, s, V(I.a), V(I.b), V(k));
-                    G(I.a) += binary_bl_rt(I.fn, s, V(I.a), V(I.b), V(k));
-                    break;
-                case I_POW: G(I.a) += pow_bmap((long)I.fn, s, V(I.a), V(k)); break;             // pow.hpp:101-162
-                case I_EQ: {                                                                      // eq.hpp:101-107
+                switch (I.code) {
+                case F_LEAF_V: case F_LEAF_S: LA(I.leaf) += s; break;
+                case F_CONST: break;
+                case F_EQ: {                                                                      // eq.hpp:101-107
                     const LeafDesc& L = s_leaf[I.leaf];
-                    if (L.scalar && a.N > 1) { G(I.a) += s + LA(I.leaf); break; }              // not produced by the planner
+                    if (L.scalar && a.N > 1) { G(I.a) += s + LA(I.leaf); break; }                // not produced by the planner
                     const double tot = (L.adj[i] + LA(I.leaf)) + s;
                     L.adj[i] = tot;
                     LA(I.leaf) = 0.0;
                     G(I.a) += tot;
                     break;
                 }
-                default: G(I.b) += s; break;                                                      // I_GLUE: lhs gets 0
+                case F_GLUE: G(I.b) += s; break;                                                  // lhs gets 0, glue.hpp:81-86
+                case F_POW: G(I.a) += pow_bmap((long)I.leaf, s, V(I.a), V(k)); break;            // pow.hpp:101-162
+                case F_POW2: { const double x = V(I.a); G(I.a) += 2. * s * (x == 0 ? 0 : V(k) / x); break; }
+#define U(FN) case F_UNARY + FN: G(I.a) += Unary<FN>::b(s, V(I.a), V(k)); break;                 /* unary.hpp:81-89 */
+                U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
+                U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
+#undef U
+                case F_UNARY + 15: G(I.a) += s * 2; break;
+                // binary.hpp:120-136: rhs seed first, then lhs
+                case F_BINARY + FADB_ADD: G(I.b) += s; G(I.a) += s; break;
+                case F_BINARY + FADB_SUB: G(I.b) += -s; G(I.a) += s; break;
+                case F_BINARY + FADB_MUL: { const double x = V(I.a), y = V(I.b); G(I.b) += s * x; G(I.a) += s * y; break; }
+                case F_BINARY + FADB_DIV: { const double y = V(I.b); G(I.b) += -s * V(k) / y; G(I.a) += s / y; break; }
+                default: G(I.b) += -2. * s; G(I.a) += s; break;                                   // MockBinary
                 }
             }
         }
@@ -418,7 +443,7 @@ struct Stage {
     // device state
     double* mval = nullptr;        // materialised output value [out_size]
     double* madj = nullptr;        // materialised output adjoint [out_size] (inner stages)
-    Ins* d_prog = nullptr;
+    DIns* d_prog = nullptr;
     LeafDesc* d_leaves = nullptr;
     double* d_red = nullptr;       // [8]
     double* d_sig = nullptr;       // device copy of a constant scalar sigma
@@ -807,9 +832,25 @@ struct fadb_expr {
                     st.leaves[l].adj = plan[st.leaf_stage[l]]->madj;
                 }
             int rc;
-            if ((rc = dev_alloc(std::max<size_t>(1, st.prog.size()) * sizeof(Ins), (void**)&st.d_prog))) return rc;
+            if ((rc = dev_alloc(std::max<size_t>(1, st.prog.size()) * sizeof(DIns), (void**)&st.d_prog))) return rc;
             if ((rc = dev_alloc(std::max<size_t>(1, st.leaves.size()) * sizeof(LeafDesc), (void**)&st.d_leaves))) return rc;
-            FADB_CUDA(cudaMemcpyAsync(st.d_prog, st.prog.data(), st.prog.size() * sizeof(Ins), cudaMemcpyHostToDevice, c.stream));
+            std::vector<DIns> enc(st.prog.size());
+            for (size_t k = 0; k < st.prog.size(); ++k) {
+                const Ins& I = st.prog[k];
+                DIns D{0, (short)I.a, (short)I.b, (short)I.leaf, I.imm};
+                switch (I.op) {
+                case I_LEAF: D.code = st.leaves[I.leaf].scalar ? F_LEAF_S : F_LEAF_V; break;
+                case I_CONST: D.code = F_CONST; break;
+                case I_EQ: D.code = F_EQ; break;
+                case I_GLUE: D.code = F_GLUE; break;
+                case I_POW: D.code = I.fn == 2 ? F_POW2 : F_POW; D.leaf = (short)I.fn; break;
+                case I_UNARY: D.code = (short)(F_UNARY + (I.fn == FADB_MOCK2X ? 15 : I.fn)); break;
+                default: D.code = (short)(F_BINARY + (I.fn == FADB_MOCKB ? 4 : I.fn)); break;
+                }
+                enc[k] = D;
+            }
+            FADB_CUDA(cudaMemcpyAsync(st.d_prog, enc.data(), enc.size() * sizeof(DIns), cudaMemcpyHostToDevice, c.stream));
+            FADB_CUDA(cudaStreamSynchronize(c.stream));     // `enc` is a temporary
             FADB_CUDA(cudaMemcpyAsync(st.d_leaves, st.leaves.data(), st.leaves.size() * sizeof(LeafDesc), cudaMemcpyHostToDevice, c.stream));
             if (st.term == T_NORMAL && st.sig_is_const) {
                 if ((rc = dev_alloc(sizeof(double), (void**)&st.d_sig))) return rc;
@@ -1130,7 +1171,7 @@ int fadb_expr_binary(fadb_expr* e, int op, int lhs, int rhs)
 
 int fadb_expr_pow(fadb_expr* e, long pw, int child)
 {
-    EXPR_REQUIRE(e, e && e->ok(child) && pw > -(1L << 30) && pw < (1L << 30), "fadb_expr_pow: bad arguments");
+    EXPR_REQUIRE(e, e && e->ok(child) && pw > -32768 && pw < 32768, "fadb_expr_pow: exponent out of range");
     if (e->is_const_scalar(child)) return fadb_expr_const_scalar(e, host_pow(pw, e->nodes[child].cval));
     const ENode& c = e->nodes[child];
     ENode n; n.kind = N_POW; n.pw = pw; n.shape = c.shape; n.rows = c.rows; n.cols = c.cols; n.ch = {child};
