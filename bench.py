@@ -407,6 +407,30 @@ def run_ours(args):
             {"note": "one autodiff of the CALL expression only, reference placeholder semantics kept"})
         del e
 
+        # the same two expressions through the TYPE-FUSED path (include/fastad_b200/fused.cuh): the
+        # expression type instantiates the kernel in an nvcc-compiled TU (tests/cpp/fused_bench.cu)
+        fb_path = os.path.join(ROOT, "tests", "_build", "libfused_bench.so")
+        if os.path.exists(fb_path):
+            FB = C.CDLL(fb_path)
+            FB.fused_chain_setup.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+            FB.fused_bs_setup.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+            xs, xa, cs = dev(synth.sum_inputs(n2)), zeros(n2), dev(synth.sum_inputs(n2, seed=5))
+            assert FB.fused_chain_setup(n2, P(xs), P(xa), P(cs)) == 0
+            t = timed_loop(lambda i: FB.fused_chain_step(), steps2, 3, world)
+            add("expr_sum_chain_2^24_type_fused", 32 * n2, t, steps2, n2, "elements",
+                {"note": "same expression as the interpreter line; kernel instantiated from the expression type"})
+            del xs, xa, cs
+            inp = synth.black_scholes_inputs(nb, seed=11)
+            bufs = [dev(inp["S"]), zeros(nb), dev(inp["sigma"]), zeros(nb), dev(inp["r"]), zeros(nb), dev(inp["K"]),
+                    dev(inp["tau"]), dev(np.sqrt(inp["tau"])), zeros(nb), zeros(nb), zeros(nb), zeros(nb), zeros(nb),
+                    zeros(nb), ones]
+            arr = (C.c_void_p * 16)(*[b.data_ptr() for b in bufs])
+            assert FB.fused_bs_setup(nb, arr) == 0
+            t = timed_loop(lambda i: FB.fused_bs_step(), steps2, 3, world)
+            add("expr_black_scholes_call_2^20_type_fused", 184 * nb, t, steps2, nb, "options",
+                {"note": "CALL expression only, reference placeholder semantics kept (3 vec placeholders)"})
+            del bufs
+
     clk.__exit__()
     clocks = clk.summary()     # sampled over every timed region above (headline first)
 

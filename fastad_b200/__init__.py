@@ -34,6 +34,7 @@ SIGNATURES = {
     "fadb_shutdown": (None, []),
     "fadb_device_count": (_i, []),
     "fadb_set_stream": (_i, [_vp]),
+    "fadb_get_stream": (_i, [C.POINTER(_vp)]),
     "fadb_sync": (_i, []),
     "fadb_last_error": (C.c_char_p, []),
     "fadb_launch_count": (C.c_ulonglong, []),

@@ -13,7 +13,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
-#include "fastmath.cuh"
+#include "../../include/fastad_b200/fastmath.cuh"
 
 namespace fadb {
 

@@ -10,7 +10,7 @@
 // reduced across the CTA with warp shuffles and across CTAs by the last-arriving CTA.
 // The matrices are 3x2, 3x3 and 1x3: far below a DMMA tile, so the FP64 tensor path is not used.
 #include "common.cuh"
-#include "fastmath.cuh"
+#include "../../include/fastad_b200/fastmath.cuh"
 
 namespace fadb {
 

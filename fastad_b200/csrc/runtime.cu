@@ -123,6 +123,16 @@ int fadb_set_stream(void* cuda_stream)
     return FADB_OK;
 }
 
+int fadb_get_stream(void** out_cuda_stream)
+{
+    FADB_REQUIRE(out_cuda_stream != nullptr, "fadb_get_stream: null out pointer");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    *out_cuda_stream = reinterpret_cast<void*>(c->stream);
+    return FADB_OK;
+}
+
 int fadb_sync(void)
 {
     Context* c;

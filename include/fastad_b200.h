@@ -64,6 +64,7 @@ int fadb_device_count(void);
  * current device; NULL restores the library's own stream (pass cudaStreamLegacy, (void*)1, to
  * name the legacy default stream). */
 int fadb_set_stream(void* cuda_stream);
+int fadb_get_stream(void** out_cuda_stream);   /* the stream launches currently go to */
 int fadb_sync(void);
 const char* fadb_last_error(void);
 /* number of kernels this library has launched on the current device since fadb_init */

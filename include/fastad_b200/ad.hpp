@@ -437,6 +437,7 @@ struct Constant : ExprBase<Constant<ValueType, ShapeType>> {
         L.touch(st_);
         return detail::checked_id(fadb_expr_const_view(L.e, util::shape_code<ShapeType>(), rows_, cols_, st_->dval));
     }
+    const std::shared_ptr<detail::Storage>& storage() const { return st_; }
 private:
     std::shared_ptr<detail::Storage> st_;
     size_t rows_, cols_;
@@ -494,6 +495,7 @@ struct UnaryNode : ExprBase<UnaryNode<Unary, ExprType>> {
     size_t cols() const { return expr_.cols(); }
     size_t size() const { return expr_.size(); }
     int lower(detail::Lowering& L) const { return detail::checked_id(fadb_expr_unary(L.e, Unary::code, expr_.lower(L))); }
+    const ExprType& child() const { return expr_; }
 private:
     ExprType expr_;
 };
@@ -529,6 +531,8 @@ struct BinaryNode : ExprBase<BinaryNode<Binary, L, R>> {
         int b = r_.lower(Lw);
         return detail::checked_id(fadb_expr_binary(Lw.e, Binary::code, a, b));
     }
+    const L& lhs() const { return l_; }
+    const R& rhs() const { return r_; }
 private:
     L l_;
     R r_;
@@ -543,6 +547,7 @@ struct PowNode : ExprBase<PowNode<N, ExprType>> {
     size_t cols() const { return expr_.cols(); }
     size_t size() const { return expr_.size(); }
     int lower(detail::Lowering& L) const { return detail::checked_id(fadb_expr_pow(L.e, (long)N, expr_.lower(L))); }
+    const ExprType& child() const { return expr_; }
 private:
     ExprType expr_;
 };
@@ -560,6 +565,7 @@ struct ReduceElemNode : ExprBase<ReduceElemNode<IsProd, ExprType>> {
         int c = expr_.lower(L);
         return detail::checked_id(IsProd ? fadb_expr_prod(L.e, c) : fadb_expr_sum(L.e, c));
     }
+    const ExprType& child() const { return expr_; }
 private:
     ExprType expr_;
 };
@@ -623,6 +629,9 @@ struct NormalAdjLogPDFNode : ExprBase<NormalAdjLogPDFNode<X, M, S>> {
         int c = s_.lower(L);
         return detail::checked_id(fadb_expr_normal(L.e, a, b, c));
     }
+    const X& x() const { return x_; }
+    const M& mean() const { return m_; }
+    const S& sigma() const { return s_; }
 private:
     X x_;
     M m_;
@@ -645,6 +654,8 @@ struct EqNode : ExprBase<EqNode<VarViewType, ExprType>> {
         int w = v_.lower(L);
         return detail::checked_id(fadb_expr_eq(L.e, w, c));
     }
+    const VarViewType& var() const { return v_; }
+    const ExprType& expr() const { return e_; }
 private:
     VarViewType v_;
     ExprType e_;
@@ -664,6 +675,8 @@ struct GlueNode : ExprBase<GlueNode<L, R>> {
         int b = r_.lower(Lw);
         return detail::checked_id(fadb_expr_glue(Lw.e, a, b));
     }
+    const L& lhs() const { return l_; }
+    const R& rhs() const { return r_; }
 private:
     L l_;
     R r_;

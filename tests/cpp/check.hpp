@@ -33,7 +33,13 @@ inline double ulp_diff(double a, double b)
         double _a = (a), _b = (b);                                                   \
         if (!(std::fabs(_a - _b) <= (tol))) { ++g_failures; std::printf("FAIL %s:%d  %s = %.17g  vs  %s = %.17g\n", __FILE__, __LINE__, #a, _a, #b, _b); } \
     } while (0)
-#define CHECK_REL(a, b, rel) CHECK_NEAR(a, b, (rel) * std::fabs(b))
+// arguments are evaluated exactly once (they may be ad::autodiff calls, which accumulate adjoints)
+#define CHECK_REL(a, b, rel)                                                         \
+    do {                                                                             \
+        ++g_checks;                                                                  \
+        double _a = (a), _b = (b);                                                   \
+        if (!(std::fabs(_a - _b) <= (rel) * std::fabs(_b))) { ++g_failures; std::printf("FAIL %s:%d  %s = %.17g  vs  %s = %.17g\n", __FILE__, __LINE__, #a, _a, #b, _b); } \
+    } while (0)
 inline int report(const char* name)
 {
     std::printf("%s: %d checks, %d failures\n", name, g_checks, g_failures);

@@ -1,8 +1,8 @@
-// CPU-only: accuracy of fastad_b200/csrc/fastmath.cuh (host build of the same header that the
+// CPU-only: accuracy of include/fastad_b200/fastmath.cuh (host build of the same header that the
 // Black-Scholes kernel compiles for the device) against glibc.
 #include <random>
 
-#include "../../fastad_b200/csrc/fastmath.cuh"
+#include <fastad_b200/fastmath.cuh>
 #include "check.hpp"
 
 int main()

@@ -46,3 +46,9 @@ def test_cpp_host_layer_reference_tests(built):
 def test_cpp_reference_black_scholes_example_unchanged(built):
     out = _run(built, "example_black_scholes")
     assert "example_black_scholes:" in out
+
+
+@pytest.mark.gpu
+def test_cpp_type_fused_kernels_match_c_abi_path(built):
+    out = _run(built, "test_fused")
+    assert "test_fused:" in out

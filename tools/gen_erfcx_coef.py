@@ -1,4 +1,4 @@
-"""Generates the erfcx polynomial of fastad_b200/csrc/fastmath.cuh (mpmath, 40 digits)."""
+"""Generates the erfcx polynomial of include/fastad_b200/fastmath.cuh (mpmath, 40 digits)."""
 import mpmath as mp
 import mpmath as mp, numpy as np
 mp.mp.dps = 40
