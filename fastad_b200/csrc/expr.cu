@@ -185,7 +185,7 @@ stage_kernel(StageArgs a)
             case F_BINARY + FADB_ADD: r = V(I.a) + V(I.b); break;         // binary.hpp:265-338
             case F_BINARY + FADB_SUB: r = V(I.a) - V(I.b); break;
             case F_BINARY + FADB_MUL: r = V(I.a) * V(I.b); break;
-            case F_BINARY + FADB_DIV: r = V(I.a) / V(I.b); break;
+            case F_BINARY + FADB_DIV: r = div_guarded(V(I.a), V(I.b)); break;
             default: r = V(I.a) - 2 * V(I.b); break;                      // MockBinary
             }
             V(k) = r;
@@ -268,7 +268,7 @@ stage_kernel(StageArgs a)
                 case F_BINARY + FADB_ADD: G(I.b) += s; G(I.a) += s; break;
                 case F_BINARY + FADB_SUB: G(I.b) += -s; G(I.a) += s; break;
                 case F_BINARY + FADB_MUL: { const double x = V(I.a), y = V(I.b); G(I.b) += s * x; G(I.a) += s * y; break; }
-                case F_BINARY + FADB_DIV: { const double y = V(I.b); G(I.b) += -s * V(k) / y; G(I.a) += s / y; break; }
+                case F_BINARY + FADB_DIV: { const double y = V(I.b); G(I.b) += div_guarded(-s * V(k), y); G(I.a) += div_guarded(s, y); break; }
                 default: G(I.b) += -2. * s; G(I.a) += s; break;                                   // MockBinary
                 }
             }

@@ -81,7 +81,13 @@ struct Dev<VarView<double, S>> {
         }
         return d;
     }
-    __device__ __forceinline__ void fwd(size_t i, Tape& t, Acc&) const { t.v = val[bcast ? 0 : i]; }   // var_view.hpp:69
+    __device__ __forceinline__ void fwd(size_t i, Tape& t, Acc&) const                                // var_view.hpp:69
+    {
+        t.v = val[bcast ? 0 : i];
+        // the adjoint read-modify-write comes after the whole forward pass: start fetching its line
+        // now (a prefetch, not a load: the same leaf may occur twice or be a placeholder)
+        if (adj && !bcast) asm volatile("prefetch.global.L1 [%0];" ::"l"(adj + i));
+    }
     __device__ __forceinline__ void bwd(double s, size_t i, Tape&, Acc& a) const                      // var_view.hpp:91-94
     {
         if (!adj) return;
