@@ -18,7 +18,7 @@ TRUST_SIGMA = 2
 SCL, VEC, MAT = 0, 1, 2
 UNARY = dict(neg=0, sin=1, cos=2, tan=3, asin=4, acos=5, atan=6, exp=7, log=8, sqrt=9, erf=10,
              sigmoid=11, sinh=12, cosh=13, tanh=14, mock2x=100)
-BINARY = dict(add=0, sub=1, mul=2, div=3, mockb=100)
+BINARY = dict(add=0, sub=1, mul=2, div=3, lt=4, le=5, gt=6, ge=7, eq=8, ne=9, land=10, lor=11, mockb=100)
 
 
 class FadbError(RuntimeError):
@@ -77,6 +77,10 @@ SIGNATURES = {
     "fadb_expr_normal": (_i, [_vp, _i, _i, _i]),
     "fadb_expr_eq": (_i, [_vp, _i, _i]),
     "fadb_expr_glue": (_i, [_vp, _i, _i]),
+    "fadb_expr_norm": (_i, [_vp, _i]),
+    "fadb_expr_transpose": (_i, [_vp, _i]),
+    "fadb_expr_if_else": (_i, [_vp, _i, _i, _i]),
+    "fadb_expr_opeq": (_i, [_vp, _i, _i, _i]),
     "fadb_expr_node_size": (_i, [_vp, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     "fadb_expr_is_const": (_i, [_vp, _i]),
     "fadb_expr_plan": (_i, [_vp, _i, C.POINTER(_sz)]),
@@ -313,6 +317,18 @@ class Expr:
         for nxt in ids[1:]:
             out = self._id(self.L.fadb_expr_glue(self.h, out, nxt))
         return out
+
+    def norm(self, c):
+        return self._id(self.L.fadb_expr_norm(self.h, c))
+
+    def transpose(self, c):
+        return self._id(self.L.fadb_expr_transpose(self.h, c))
+
+    def if_else(self, c, a, b):
+        return self._id(self.L.fadb_expr_if_else(self.h, c, a, b))
+
+    def opeq(self, op, w, c):
+        return self._id(self.L.fadb_expr_opeq(self.h, BINARY[op], w, c))
 
     def plan(self, root):
         out = (C.c_size_t * 2)()

@@ -44,7 +44,7 @@ extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, 
 namespace fadb {
 
 // ======================================================================== device program
-enum : int { I_LEAF = 0, I_CONST, I_UNARY, I_BINARY, I_POW, I_EQ, I_GLUE };
+enum : int { I_LEAF = 0, I_CONST, I_UNARY, I_BINARY, I_POW, I_EQ, I_GLUE, I_JZ, I_JMP, I_PHI, I_OPEQ };
 enum : int { T_NONE = 0, T_SUM, T_PROD, T_NORMAL };
 enum : int { M_F = 1, M_B = 2, M_FB = 3 };
 
@@ -54,8 +54,8 @@ struct Ins {
 };
 // device encoding: 16 bytes (one LDS.128), a single flat opcode so that the interpreter has ONE
 // dense switch (a jump table) per direction instead of nested compare chains
-enum : short { F_LEAF_V = 0, F_LEAF_S, F_CONST, F_EQ, F_GLUE, F_POW, F_POW2, F_UNARY = 8 /* +fn, mock2x = +15 */,
-               F_BINARY = 24 /* +fn, mockb = +4 */ };
+enum : short { F_LEAF_V = 0, F_LEAF_S, F_CONST, F_EQ, F_GLUE, F_POW, F_POW2, F_UNARY = 8 /* +fn, mock2x = +16 */,
+               F_BINARY = 26 /* +fn, mockb = +12 */, F_JZ = 40, F_JMP = 41, F_PHI = 42, F_OPEQ = 44 /* +op */ };
 struct DIns {
     short code, a, b, leaf;   // POW: exponent in `leaf`
     double imm;
@@ -180,13 +180,33 @@ stage_kernel(StageArgs a)
 #define U(FN) case F_UNARY + FN: r = Unary<FN>::f(V(I.a)); break;
             U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
             U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
+            U(FADB_SQUARE)
 #undef U
-            case F_UNARY + 15: r = 2 * V(I.a); break;                     // MockUnary
+            case F_UNARY + 16: r = 2 * V(I.a); break;                     // MockUnary
             case F_BINARY + FADB_ADD: r = V(I.a) + V(I.b); break;         // binary.hpp:265-338
             case F_BINARY + FADB_SUB: r = V(I.a) - V(I.b); break;
             case F_BINARY + FADB_MUL: r = V(I.a) * V(I.b); break;
             case F_BINARY + FADB_DIV: r = div_guarded(V(I.a), V(I.b)); break;
-            default: r = V(I.a) - 2 * V(I.b); break;                      // MockBinary
+            case F_BINARY + FADB_LT: r = V(I.a) < V(I.b) ? 1.0 : 0.0; break;     // binary.hpp:347-470
+            case F_BINARY + FADB_LE: r = V(I.a) <= V(I.b) ? 1.0 : 0.0; break;
+            case F_BINARY + FADB_GT: r = V(I.a) > V(I.b) ? 1.0 : 0.0; break;
+            case F_BINARY + FADB_GE: r = V(I.a) >= V(I.b) ? 1.0 : 0.0; break;
+            case F_BINARY + FADB_EQ: r = V(I.a) == V(I.b) ? 1.0 : 0.0; break;
+            case F_BINARY + FADB_NE: r = V(I.a) != V(I.b) ? 1.0 : 0.0; break;
+            case F_BINARY + FADB_AND: r = (V(I.a) != 0 && V(I.b) != 0) ? 1.0 : 0.0; break;
+            case F_BINARY + FADB_OR: r = (V(I.a) != 0 || V(I.b) != 0) ? 1.0 : 0.0; break;
+            case F_BINARY + 12: r = V(I.a) - 2 * V(I.b); break;           // MockBinary
+            // IfElseNode (if_else.hpp:64-68): the condition is a scalar, so the jump is uniform
+            case F_JZ: r = 0.0; if (V(I.a) == 0.0) k = I.b - 1; break;
+            case F_JMP: r = 0.0; k = I.b - 1; break;
+            case F_PHI: r = V(I.leaf) != 0.0 ? V(I.a) : V(I.b); break;
+            default: {                                                     // OpEqNode::feval, eq.hpp:240-247
+                const double old = V(I.b), e = V(I.a);
+                const int op = I.code - F_OPEQ;
+                r = op == FADB_ADD ? old + e : op == FADB_SUB ? old - e : op == FADB_MUL ? old * e : old / e;
+                if (fwd_out) { const LeafDesc& L = s_leaf[I.leaf]; const_cast<double*>(L.val)[i] = r; }
+                break;
+            }
             }
             V(k) = r;
         }
@@ -262,14 +282,41 @@ stage_kernel(StageArgs a)
 #define U(FN) case F_UNARY + FN: G(I.a) += Unary<FN>::b(s, V(I.a), V(k)); break;                 /* unary.hpp:81-89 */
                 U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
                 U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
+                U(FADB_SQUARE)
 #undef U
-                case F_UNARY + 15: G(I.a) += s * 2; break;
+                case F_UNARY + 16: G(I.a) += s * 2; break;
                 // binary.hpp:120-136: rhs seed first, then lhs
                 case F_BINARY + FADB_ADD: G(I.b) += s; G(I.a) += s; break;
                 case F_BINARY + FADB_SUB: G(I.b) += -s; G(I.a) += s; break;
                 case F_BINARY + FADB_MUL: { const double x = V(I.a), y = V(I.b); G(I.b) += s * x; G(I.a) += s * y; break; }
                 case F_BINARY + FADB_DIV: { const double y = V(I.b); G(I.b) += div_guarded(-s * V(k), y); G(I.a) += div_guarded(s, y); break; }
-                default: G(I.b) += -2. * s; G(I.a) += s; break;                                   // MockBinary
+                case F_BINARY + 12: G(I.b) += -2. * s; G(I.a) += s; break;                        // MockBinary
+                // comparisons: no adjoint (binary.hpp:124)
+                case F_BINARY + FADB_LT: case F_BINARY + FADB_LE: case F_BINARY + FADB_GT: case F_BINARY + FADB_GE:
+                case F_BINARY + FADB_EQ: case F_BINARY + FADB_NE: case F_BINARY + FADB_AND: case F_BINARY + FADB_OR: break;
+                // IfElseNode::beval (if_else.hpp:70-78): only the taken branch is swept
+                case F_PHI:
+                    if (V(I.leaf) != 0.0) { G(I.a) += s; k = (int)I.imm + 1; }    // skip the else branch
+                    else G(I.b) += s;
+                    break;
+                case F_JMP: if (V(I.a) == 0.0) k = I.leaf + 1; break;             // else was taken: skip the if branch
+                case F_JZ: break;
+                default: {                                                         // OpEqNode::beval, eq.hpp:249-271
+                    const LeafDesc& L = s_leaf[I.leaf];
+                    const double tot = (L.adj[i] + LA(I.leaf)) + s;
+                    LA(I.leaf) = 0.0;
+                    const double old = V(I.b), e = V(I.a);
+                    const int op = I.code - F_OPEQ;
+                    double ls, rs;
+                    if (op == FADB_ADD) { ls = tot; rs = tot; }
+                    else if (op == FADB_SUB) { ls = tot; rs = -tot; }
+                    else if (op == FADB_MUL) { ls = tot * e; rs = tot * old; }
+                    else { ls = tot / e; rs = -tot * old / (e * e); }
+                    G(I.a) += rs;
+                    L.adj[i] = ls;                                                 // reset_adj(); beval(lseed)
+                    const_cast<double*>(L.val)[i] = old;                           // the previous value is restored
+                    break;
+                }
                 }
             }
         }
@@ -397,6 +444,22 @@ __global__ void dot_bwd_kernel(int m, int k, int p, const double* __restrict__ L
         Ladj[idx] = (lmode == 2) ? acc : Ladj[idx] + acc;
     }
 }
+// TransposeNode (transpose.hpp:32-41): V = X^T; X_adj (+)= A^T.  X is m x k column-major.
+__global__ void transpose_fwd_kernel(int m, int k, const double* __restrict__ X, double* V)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * k) return;
+    const int i = idx % m, j = idx / m;
+    V[j + (size_t)i * k] = X[idx];
+}
+__global__ void transpose_bwd_kernel(int m, int k, const double* __restrict__ A, double* Xadj, int mode)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * k) return;
+    const int i = idx % m, j = idx / m;
+    const double a = A[j + (size_t)i * k];
+    Xadj[idx] = (mode == 2) ? a : Xadj[idx] + a;
+}
 __global__ void fill_kernel(double* p, size_t n, double v)
 {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -405,7 +468,7 @@ __global__ void fill_kernel(double* p, size_t n, double v)
 
 // ======================================================================== host: builder + planner
 enum NodeKind { N_VAR, N_CONST_S, N_CONST_V, N_UNARY, N_BINARY, N_POW, N_SUM, N_SUM_ITER, N_PROD,
-                N_PROD_ITER, N_DOT, N_NORMAL, N_EQ, N_GLUE };
+                N_PROD_ITER, N_DOT, N_NORMAL, N_EQ, N_GLUE, N_TRANSPOSE, N_IF_ELSE, N_OPEQ };
 
 struct ENode {
     NodeKind kind;
@@ -423,7 +486,7 @@ struct ENode {
 struct OperandRef { const double* val = nullptr; double* adj = nullptr; int adj_mode = 0; int node = -1; int stage = -1; };
 
 struct Stage {
-    int type = 0;                  // 0 = MAP (interpreter), 1 = DOT
+    int type = 0;                  // 0 = MAP (interpreter), 1 = DOT, 2 = TRANSPOSE
     size_t N = 1;
     std::vector<Ins> prog;
     std::vector<LeafDesc> leaves;
@@ -476,7 +539,7 @@ struct fadb_expr {
     bool is_const_scalar(int id) const { return nodes[id].kind == N_CONST_S; }
 
     // ---------------------------------------------------------------- planning (host only)
-    static bool barrier(NodeKind k) { return k == N_SUM || k == N_PROD || k == N_NORMAL || k == N_DOT; }
+    static bool barrier(NodeKind k) { return k == N_SUM || k == N_PROD || k == N_NORMAL || k == N_DOT || k == N_TRANSPOSE; }
 
     int emit(Stage& st, Ins I)
     {
@@ -568,6 +631,28 @@ struct fadb_expr {
             int b = lower(n.ch[1], st); if (b < 0) return -1;
             return emit(st, Ins{I_GLUE, 0, a, b, 0, 0, 0.0});
         }
+        case N_IF_ELSE: {
+            // cond ; JZ else ; <if> ; JMP end ; else: <else> ; end: PHI    (if_else.hpp:64-78)
+            int c = lower(n.ch[0], st); if (c < 0) return -1;
+            int jz = emit(st, Ins{I_JZ, 0, c, 0, 0, 0, 0.0});
+            int a = lower(n.ch[1], st); if (a < 0) return -1;
+            int jmp = emit(st, Ins{I_JMP, 0, c, 0, jz, 0, 0.0});
+            st.prog[jz].b = (int)st.prog.size();
+            int b = lower(n.ch[2], st); if (b < 0) return -1;
+            st.prog[jmp].b = (int)st.prog.size();
+            return emit(st, Ins{I_PHI, 0, a, b, c, 0, (double)jmp});
+        }
+        case N_OPEQ: {
+            ENode& w = nodes[n.ch[0]];
+            int old = lower(n.ch[0], st); if (old < 0) return -1;      // previous value (leaf read or alias slot)
+            int a = lower(n.ch[1], st); if (a < 0) return -1;
+            int lf = leaf_index(st, n.ch[0], w.val, w.adj, false, 1, -1);
+            st.leaves[lf].assigned = 1;
+            int s = emit(st, Ins{I_OPEQ, n.fn, a, old, lf, 0, 0.0});
+            st.eq_slot[n.ch[0]] = s;
+            st.assigned.insert(n.ch[0]);
+            return s;
+        }
         default: break;
         }
         err = "internal: unhandled node kind in lower()";
@@ -618,6 +703,12 @@ struct fadb_expr {
             st->out_size = n.size();
             st->L = operand(n.ch[0]); if (!err.empty()) return -1;
             st->R = operand(n.ch[1]); if (!err.empty()) return -1;
+        } else if (n.kind == N_TRANSPOSE) {
+            ENode& x = nodes[n.ch[0]];
+            st->type = 2;
+            st->m = (int)x.rows; st->k = (int)x.cols; st->p = 0;
+            st->out_size = n.size();
+            st->L = operand(n.ch[0]); if (!err.empty()) return -1;
         } else if (n.kind == N_SUM || n.kind == N_PROD) {
             st->N = nodes[n.ch[0]].size();
             st->term = n.kind == N_SUM ? T_SUM : T_PROD;
@@ -773,12 +864,13 @@ struct fadb_expr {
 
     std::string describe() const
     {
-        static const char* opn[] = {"leaf", "const", "unary", "binary", "pow", "eq", "glue"};
+        static const char* opn[] = {"leaf", "const", "unary", "binary", "pow", "eq", "glue", "jz", "jmp", "phi", "opeq"};
         static const char* tn[] = {"store", "sum", "prod", "normal"};
         std::ostringstream o;
         o << "stages=" << plan.size() << " cache={" << cache_vals << "," << cache_adjs << "}\n";
         for (size_t k = 0; k < plan.size(); ++k) {
             const Stage& st = *plan[k];
+            if (st.type == 2) { o << "stage " << k << ": transpose " << st.m << "x" << st.k << "\n"; continue; }
             if (st.type == 1) { o << "stage " << k << ": dot " << st.m << "x" << st.k << " * " << st.k << "x" << st.p << "\n"; continue; }
             o << "stage " << k << ": map N=" << st.N << " term=" << tn[st.term] << " ins=" << st.prog.size()
               << " leaves=" << st.leaves.size() << " channels=" << st.nch << " fast=" << st.fast
@@ -793,6 +885,10 @@ struct fadb_expr {
                 else if (I.op == I_POW) o << "<" << I.fn << "> %" << I.a;
                 else if (I.op == I_BINARY) o << "[" << I.fn << "] %" << I.a << " %" << I.b;
                 else if (I.op == I_EQ) o << " L" << I.leaf << " := %" << I.a;
+                else if (I.op == I_OPEQ) o << "[" << I.fn << "] L" << I.leaf << " (old %" << I.b << ") op= %" << I.a;
+                else if (I.op == I_JZ) o << " %" << I.a << " -> @" << I.b;
+                else if (I.op == I_JMP) o << " -> @" << I.b;
+                else if (I.op == I_PHI) o << " %" << I.leaf << " ? %" << I.a << " : %" << I.b;
                 else o << " %" << I.a << " , %" << I.b;
                 o << "\n";
             }
@@ -821,9 +917,9 @@ struct fadb_expr {
         }
         for (auto& sp : plan) {
             Stage& st = *sp;
-            if (st.type == 1) {
+            if (st.type != 0) {
                 if (st.L.stage >= 0) { st.L.val = plan[st.L.stage]->mval; st.L.adj = plan[st.L.stage]->madj; }
-                if (st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
+                if (st.type == 1 && st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
                 continue;
             }
             for (size_t l = 0; l < st.leaves.size(); ++l)
@@ -844,8 +940,12 @@ struct fadb_expr {
                 case I_EQ: D.code = F_EQ; break;
                 case I_GLUE: D.code = F_GLUE; break;
                 case I_POW: D.code = I.fn == 2 ? F_POW2 : F_POW; D.leaf = (short)I.fn; break;
-                case I_UNARY: D.code = (short)(F_UNARY + (I.fn == FADB_MOCK2X ? 15 : I.fn)); break;
-                default: D.code = (short)(F_BINARY + (I.fn == FADB_MOCKB ? 4 : I.fn)); break;
+                case I_UNARY: D.code = (short)(F_UNARY + (I.fn == FADB_MOCK2X ? 16 : I.fn)); break;
+                case I_BINARY: D.code = (short)(F_BINARY + (I.fn == FADB_MOCKB ? 12 : I.fn)); break;
+                case I_JZ: D.code = F_JZ; break;
+                case I_JMP: D.code = F_JMP; break;
+                case I_PHI: D.code = F_PHI; break;
+                default: D.code = (short)(F_OPEQ + I.fn); break;
                 }
                 enc[k] = D;
             }
@@ -872,9 +972,9 @@ struct fadb_expr {
     {
         for (auto& sp : plan) {
             Stage& st = *sp;
-            if (st.type == 1) {
+            if (st.type != 0) {
                 if (st.L.stage < 0) { st.L.val = nodes[st.L.node].val; st.L.adj = nodes[st.L.node].adj; }
-                if (st.R.stage < 0) { st.R.val = nodes[st.R.node].val; st.R.adj = nodes[st.R.node].adj; }
+                if (st.type == 1 && st.R.stage < 0) { st.R.val = nodes[st.R.node].val; st.R.adj = nodes[st.R.node].adj; }
                 continue;
             }
             for (size_t l = 0; l < st.leaves.size(); ++l)
@@ -942,6 +1042,25 @@ struct fadb_expr {
     int run_dot(Context& c, Stage& st, int mode, const double* seed_vec, double seed)
     {
         const int threads = 128;
+        if (st.type == 2) {
+            const int n = st.m * st.k, blocks = (n + threads - 1) / threads;
+            if (n == 0) return FADB_OK;
+            if (mode & M_F) {
+                transpose_fwd_kernel<<<blocks, threads, 0, c.stream>>>(st.m, st.k, st.L.val, st.mval);
+                c.launches++;
+            }
+            if ((mode & M_B) && st.L.adj_mode) {
+                if (!seed_vec && mode == M_FB) {
+                    fill_kernel<<<blocks, threads, 0, c.stream>>>(st.madj, n, seed);
+                    c.launches++;
+                }
+                transpose_bwd_kernel<<<blocks, threads, 0, c.stream>>>(st.m, st.k, seed_vec ? seed_vec : st.madj, st.L.adj,
+                                                                        st.L.adj_mode);
+                c.launches++;
+            }
+            FADB_CUDA(cudaGetLastError());
+            return FADB_OK;
+        }
         if (mode & M_F) {
             int n = st.m * st.p;
             dot_fwd_kernel<<<(n + threads - 1) / threads, threads, 0, c.stream>>>(st.m, st.k, st.p, st.L.val, st.R.val, st.mval);
@@ -1008,23 +1127,23 @@ struct fadb_expr {
         if (what & 1) {
             for (size_t k = first; k + 1 < plan.size(); ++k) {
                 Stage& st = *plan[k];
-                int rc = st.type == 1 ? run_dot(c, st, M_F, nullptr, 0) : run_map(c, st, M_F, 0, nullptr, nullptr);
+                int rc = st.type != 0 ? run_dot(c, st, M_F, nullptr, 0) : run_map(c, st, M_F, 0, nullptr, nullptr);
                 if (rc) return rc;
             }
         }
         if (fast) return run_fast_root(c, rs, seed);
         // root stage: fused when the seed suffices (no global quantity needed before the sweep)
-        const bool fusable = rs.type == 1 || rs.term == T_NONE || rs.term == T_SUM ||
+        const bool fusable = rs.type != 0 || rs.term == T_NONE || rs.term == T_SUM ||
                              (rs.term == T_NORMAL && (!rs.sig_vec || (flags & FADB_TRUST_SIGMA)));
         int rc = 0;
         if (what == 3 && fusable) {
-            rc = rs.type == 1 ? run_dot(c, rs, M_FB, seed_vec, seed) : run_map(c, rs, M_FB, seed, seed_vec, nullptr);
+            rc = rs.type != 0 ? run_dot(c, rs, M_FB, seed_vec, seed) : run_map(c, rs, M_FB, seed, seed_vec, nullptr);
         } else {
-            if (what & 1) rc = rs.type == 1 ? run_dot(c, rs, M_F, nullptr, 0) : run_map(c, rs, M_F, 0, nullptr, nullptr);
+            if (what & 1) rc = rs.type != 0 ? run_dot(c, rs, M_F, nullptr, 0) : run_map(c, rs, M_F, 0, nullptr, nullptr);
             if (!rc && (what & 2)) {
-                if (rs.type == 1) {
+                if (rs.type != 0) {
                     if (!seed_vec) {
-                        int n = rs.m * rs.p;
+                        int n = (int)rs.out_size;
                         fill_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(rs.madj, n, seed);
                         c.launches++;
                     }
@@ -1036,7 +1155,7 @@ struct fadb_expr {
         if (what & 2) {
             for (int k = last - 1; k >= 0; --k) {
                 Stage& st = *plan[k];
-                if (st.type == 1) rc = run_dot(c, st, M_B, nullptr, 0);
+                if (st.type != 0) rc = run_dot(c, st, M_B, nullptr, 0);
                 else rc = run_map(c, st, M_B, 0, st.out_size > 1 ? st.madj : nullptr, st.out_size > 1 ? nullptr : st.madj);
                 if (rc) return rc;
             }
@@ -1063,6 +1182,7 @@ static double host_unary(int op, double x)
     case FADB_SQRT: return std::sqrt(x); case FADB_ERF: return std::erf(x);
     case FADB_SIGMOID: return 1 / (1 + std::exp(-x)); case FADB_SINH: return std::sinh(x);
     case FADB_COSH: return std::cosh(x); case FADB_TANH: return std::tanh(x); case FADB_MOCK2X: return 2 * x;
+    case FADB_SQUARE: return x * x;
     }
     return NAN;
 }
@@ -1071,6 +1191,9 @@ static double host_binary(int op, double x, double y)
     switch (op) {
     case FADB_ADD: return x + y; case FADB_SUB: return x - y; case FADB_MUL: return x * y;
     case FADB_DIV: return x / y; case FADB_MOCKB: return x - 2 * y;
+    case FADB_LT: return x < y; case FADB_LE: return x <= y; case FADB_GT: return x > y; case FADB_GE: return x >= y;
+    case FADB_EQ: return x == y; case FADB_NE: return x != y; case FADB_AND: return x != 0 && y != 0;
+    case FADB_OR: return x != 0 || y != 0;
     }
     return NAN;
 }
@@ -1249,6 +1372,46 @@ int fadb_expr_glue(fadb_expr* e, int lhs, int rhs)
     EXPR_REQUIRE(e, e && e->ok(lhs) && e->ok(rhs), "fadb_expr_glue: bad arguments");
     const ENode& r = e->nodes[rhs];
     ENode n; n.kind = N_GLUE; n.shape = r.shape; n.rows = r.rows; n.cols = r.cols; n.ch = {lhs, rhs};
+    return e->add(std::move(n));
+}
+
+int fadb_expr_norm(fadb_expr* e, int child)
+{   // squaredNorm = sum of x*x with child seed 2*seed*x (norm.hpp:47-57)
+    EXPR_REQUIRE(e, e && e->ok(child), "fadb_expr_norm: bad arguments");
+    int sq = fadb_expr_unary(e, FADB_SQUARE, child);
+    if (sq < 0) return sq;
+    return fadb_expr_sum(e, sq);
+}
+
+int fadb_expr_transpose(fadb_expr* e, int child)
+{
+    EXPR_REQUIRE(e, e && e->ok(child), "fadb_expr_transpose: bad arguments");
+    const ENode& c = e->nodes[child];
+    EXPR_REQUIRE(e, c.shape != FADB_SCL, "transpose of a scalar (transpose.hpp:25)");
+    ENode n; n.kind = N_TRANSPOSE; n.shape = FADB_MAT; n.rows = c.cols; n.cols = c.rows; n.ch = {child};
+    return e->add(std::move(n));
+}
+
+int fadb_expr_if_else(fadb_expr* e, int cond, int if_node, int else_node)
+{
+    EXPR_REQUIRE(e, e && e->ok(cond) && e->ok(if_node) && e->ok(else_node), "fadb_expr_if_else: bad arguments");
+    EXPR_REQUIRE(e, e->nodes[cond].size() == 1, "if_else: the condition must be a scalar (if_else.hpp:52-55)");
+    const ENode& a = e->nodes[if_node];
+    const ENode& b = e->nodes[else_node];
+    EXPR_REQUIRE(e, a.rows == b.rows && a.cols == b.cols, "if_else: branch shapes differ (if_else.hpp:71-72)");
+    if (e->is_const_scalar(cond)) return e->nodes[cond].cval != 0 ? if_node : else_node;
+    ENode n; n.kind = N_IF_ELSE; n.shape = a.shape; n.rows = a.rows; n.cols = a.cols; n.ch = {cond, if_node, else_node};
+    return e->add(std::move(n));
+}
+
+int fadb_expr_opeq(fadb_expr* e, int op, int var, int child)
+{
+    EXPR_REQUIRE(e, e && e->ok(var) && e->ok(child) && e->nodes[var].kind == N_VAR && op >= FADB_ADD && op <= FADB_DIV,
+                 "fadb_expr_opeq: target must be a Var and op one of + - * /");
+    const ENode& w = e->nodes[var];
+    const ENode& c = e->nodes[child];
+    EXPR_REQUIRE(e, c.size() == 1 || (w.rows == c.rows && w.cols == c.cols), "op=: shapes differ (eq.hpp:234-237)");
+    ENode n; n.kind = N_OPEQ; n.fn = op; n.shape = w.shape; n.rows = w.rows; n.cols = w.cols; n.ch = {var, child};
     return e->add(std::move(n));
 }
 

@@ -179,7 +179,7 @@ extern "C" int fadb_sum_unary_async(int op, size_t n, const double* x, double* x
 #define C(OP) case OP: return launch_sum_map(*c, n, x, x_adj, seed, flags, UnaryFun<OP>{}, dev_value);
         C(FADB_NEG) C(FADB_SIN) C(FADB_COS) C(FADB_TAN) C(FADB_ASIN) C(FADB_ACOS) C(FADB_ATAN)
         C(FADB_EXP) C(FADB_LOG) C(FADB_SQRT) C(FADB_ERF) C(FADB_SIGMOID) C(FADB_SINH) C(FADB_COSH)
-        C(FADB_TANH) C(FADB_MOCK2X)
+        C(FADB_TANH) C(FADB_MOCK2X) C(FADB_SQUARE)
 #undef C
     }
     set_error("fadb_sum_unary: unknown op code " + std::to_string(op));

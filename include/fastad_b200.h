@@ -47,11 +47,14 @@ enum { FADB_SCL = 0, FADB_VEC = 1, FADB_MAT = 2 };
 enum {
     FADB_NEG = 0, FADB_SIN, FADB_COS, FADB_TAN, FADB_ASIN, FADB_ACOS, FADB_ATAN, FADB_EXP,
     FADB_LOG, FADB_SQRT, FADB_ERF, FADB_SIGMOID, FADB_SINH, FADB_COSH, FADB_TANH,
+    FADB_SQUARE, /* x*x with adjoint seed*2*x: the map inside NormNode (reverse/core/norm.hpp:47-57) */
     FADB_UNARY_COUNT,
     FADB_MOCK2X = 100 /* test functor f(x)=2x (test/testutil/base_fixture.hpp:9-22) */
 };
 /* binary functors (reverse/core/binary.hpp:265-338) */
-enum { FADB_ADD = 0, FADB_SUB, FADB_MUL, FADB_DIV, FADB_BINARY_COUNT,
+enum { FADB_ADD = 0, FADB_SUB, FADB_MUL, FADB_DIV,
+       /* comparison / logical functors: value 0 or 1, no adjoint (binary.hpp:347-470) */
+       FADB_LT, FADB_LE, FADB_GT, FADB_GE, FADB_EQ, FADB_NE, FADB_AND, FADB_OR, FADB_BINARY_COUNT,
        FADB_MOCKB = 100 /* test functor f(x,y)=x-2y (base_fixture.hpp:24-46) */ };
 
 /* ------------------------------------------------------------------ lifecycle / runtime */
@@ -208,6 +211,16 @@ int fadb_expr_dot(fadb_expr*, int lhs, int rhs);
 int fadb_expr_normal(fadb_expr*, int x, int mu, int sigma);
 int fadb_expr_eq(fadb_expr*, int var, int child);
 int fadb_expr_glue(fadb_expr*, int lhs, int rhs);
+/* SURVEY.md 8f "next" rows:
+ *   fadb_expr_norm       ad::norm(expr), squared L2 / Frobenius norm          norm.hpp:24-108
+ *   fadb_expr_transpose  ad::transpose(expr)                                 transpose.hpp:17-81
+ *   fadb_expr_if_else    ad::if_else(cond, a, b), scalar condition           if_else.hpp:29-165
+ *   fadb_expr_opeq       w += / -= / *= / /= expr (op = FADB_ADD..FADB_DIV)   eq.hpp:194-413
+ * (ad::for_each is a chain of fadb_expr_glue, for_each.hpp:19-131.) */
+int fadb_expr_norm(fadb_expr*, int child);
+int fadb_expr_transpose(fadb_expr*, int child);
+int fadb_expr_if_else(fadb_expr*, int cond, int if_node, int else_node);
+int fadb_expr_opeq(fadb_expr*, int op, int var, int child);
 int fadb_expr_node_size(fadb_expr*, int node, size_t* rows, size_t* cols);
 int fadb_expr_is_const(fadb_expr*, int node);
 int fadb_expr_plan(fadb_expr*, int root, size_t out_cache_size[2]);

@@ -59,6 +59,7 @@ FADB_UNARY(FADB_SINH, sinh(x), seed * cosh(x))
 FADB_UNARY(FADB_COSH, cosh(x), seed * sinh(x))
 FADB_UNARY(FADB_TANH, tanh(x), seed * (1 - f * f))
 FADB_UNARY(FADB_MOCK2X, 2 * x, seed * 2)
+FADB_UNARY(FADB_SQUARE, x * x, seed * 2. * x)      // NormNode, norm.hpp:47-57
 #undef FADB_UNARY
 
 // Sigmoid: the reference evaluates exp(-x) three times in bmap (unary.hpp:273-278); the value
@@ -112,7 +113,7 @@ __device__ __forceinline__ double unary_f_rt(int op, double x)
 #define C(OP) case OP: return Unary<OP>::f(x);
         C(FADB_NEG) C(FADB_SIN) C(FADB_COS) C(FADB_TAN) C(FADB_ASIN) C(FADB_ACOS) C(FADB_ATAN)
         C(FADB_EXP) C(FADB_LOG) C(FADB_SQRT) C(FADB_ERF) C(FADB_SIGMOID) C(FADB_SINH) C(FADB_COSH)
-        C(FADB_TANH) C(FADB_MOCK2X)
+        C(FADB_TANH) C(FADB_MOCK2X) C(FADB_SQUARE)
 #undef C
     }
     return NAN;
@@ -123,7 +124,7 @@ __device__ __forceinline__ double unary_b_rt(int op, double seed, double x, doub
 #define C(OP) case OP: return Unary<OP>::b(seed, x, f);
         C(FADB_NEG) C(FADB_SIN) C(FADB_COS) C(FADB_TAN) C(FADB_ASIN) C(FADB_ACOS) C(FADB_ATAN)
         C(FADB_EXP) C(FADB_LOG) C(FADB_SQRT) C(FADB_ERF) C(FADB_SIGMOID) C(FADB_SINH) C(FADB_COSH)
-        C(FADB_TANH) C(FADB_MOCK2X)
+        C(FADB_TANH) C(FADB_MOCK2X) C(FADB_SQUARE)
 #undef C
     }
     return NAN;

@@ -21,7 +21,7 @@
 namespace {
 
 enum Kind { K_VAR, K_CONST, K_UNARY, K_BINARY, K_POW, K_SUM, K_SUM_ITER, K_PROD,
-            K_PROD_ITER, K_DOT, K_NORMAL, K_EQ, K_GLUE };
+            K_PROD_ITER, K_DOT, K_NORMAL, K_EQ, K_GLUE, K_NORM, K_TRANSPOSE, K_IF_ELSE, K_OPEQ };
 
 /* A seed is either a scalar (broadcast) or an array, as in the reference where the
  * seed type is a template parameter (var_view.hpp:91-94). */
@@ -104,9 +104,13 @@ inline double binary_f(int op, double x, double y)
     case ORC_MUL: return x * y;
     case ORC_DIV: return x / y;
     case ORC_MOCKB: return x - 2 * y;
+    case ORC_LT: return x < y; case ORC_LE: return x <= y; case ORC_GT: return x > y; case ORC_GE: return x >= y;
+    case ORC_EQ: return x == y; case ORC_NE: return x != y;
+    case ORC_AND: return x != 0 && y != 0; case ORC_OR: return x != 0 || y != 0;
     }
     return std::numeric_limits<double>::quiet_NaN();
 }
+inline bool is_comparison(int op) { return op >= ORC_LT && op <= ORC_OR; }
 inline double binary_bl(int op, double s, double x, double y, double f)
 {
     (void)x; (void)f;
@@ -157,11 +161,13 @@ struct orc_graph {
     {
         const Node& n = nodes[id];
         switch (n.kind) {
-        case K_VAR: case K_CONST: case K_EQ: case K_GLUE: out[0] = out[1] = 0; break;
-        case K_UNARY: case K_BINARY: case K_POW: case K_DOT: case K_SUM_ITER:
-        case K_PROD_ITER:
+        case K_VAR: case K_CONST: case K_EQ: case K_GLUE: case K_IF_ELSE: out[0] = out[1] = 0; break;
+        case K_BINARY:
+            out[0] = n.size(); out[1] = is_comparison(n.op) ? 0 : n.size(); break;   /* binary.hpp:166-174 */
+        case K_UNARY: case K_POW: case K_DOT: case K_SUM_ITER: case K_PROD_ITER: case K_TRANSPOSE:
+        case K_OPEQ:   /* OpEqNode's cache_ holds the previous lhs value + adjoint, eq.hpp:289-292 */
             out[0] = n.size(); out[1] = n.size(); break;
-        case K_SUM: case K_NORMAL: out[0] = n.size(); out[1] = 0; break; /* sum.hpp:196-199 */
+        case K_SUM: case K_NORMAL: case K_NORM: out[0] = n.size(); out[1] = 0; break; /* sum.hpp:196-199 */
         case K_PROD: out[0] = n.size(); out[1] = nodes[n.ch[0]].size(); break; /* prod.hpp:236-239 */
         }
     }
@@ -172,7 +178,7 @@ struct orc_graph {
         single_size(id, s);
         out[0] = s[0]; out[1] = s[1];
         for (int c : n.ch) {
-            if (n.kind == K_EQ && c == n.ch[0]) continue;  /* the placeholder itself */
+            if ((n.kind == K_EQ || n.kind == K_OPEQ) && c == n.ch[0]) continue;  /* the placeholder itself */
             size_t t[2];
             total_size(c, t);
             out[0] += t[0]; out[1] += t[1];
@@ -201,6 +207,17 @@ struct orc_graph {
             if (e.kind != K_VAR && e.kind != K_CONST) { e.val = w.val; if (r[1]) e.adj = w.adj; }
             return;
         }
+        case K_IF_ELSE:                              /* if_else.hpp:80-85: no storage of its own */
+            for (int c : n.ch) bind_node(c, v, a);
+            return;
+        case K_OPEQ: {                               /* eq.hpp:273-279 */
+            Node& w = nodes[n.ch[0]];
+            n.val = w.val; n.adj = w.adj;
+            bind_node(n.ch[1], v, a);
+            n.extra.assign(2 * n.size(), 0.);        /* cache_: previous value | its adjoint */
+            v += n.size(); a += n.size();
+            return;
+        }
         case K_GLUE: {                               /* glue.hpp:94-100 */
             bind_node(n.ch[0], v, a);
             bind_node(n.ch[1], v, a);
@@ -217,7 +234,8 @@ struct orc_graph {
         size_t s[2];
         single_size(id, s);
         n.val = v; v += s[0];
-        if (n.kind == K_SUM || n.kind == K_NORMAL || n.kind == K_PROD) n.adj = nullptr;
+        if (n.kind == K_SUM || n.kind == K_NORMAL || n.kind == K_PROD || n.kind == K_NORM ||
+            (n.kind == K_BINARY && is_comparison(n.op))) n.adj = nullptr;
         else { n.adj = a; a += n.size(); }
     }
 
@@ -364,6 +382,35 @@ struct orc_graph {
             return feval(n.ch[1]);
         }
         case K_NORMAL: return normal_feval(n);
+        case K_NORM: {                                   /* norm.hpp:47-51 */
+            const double* x = feval(n.ch[0]);
+            const size_t M = nodes[n.ch[0]].size();
+            double acc = 0;
+            for (size_t i = 0; i < M; ++i) acc += x[i] * x[i];
+            n.val[0] = acc;
+            return n.val;
+        }
+        case K_TRANSPOSE: {                              /* transpose.hpp:32-35 */
+            const double* x = feval(n.ch[0]);
+            const size_t m = nodes[n.ch[0]].rows, k = nodes[n.ch[0]].cols;
+            for (size_t j = 0; j < k; ++j)
+                for (size_t i = 0; i < m; ++i) n.val[j + i * k] = x[i + j * m];
+            return n.val;
+        }
+        case K_IF_ELSE: {                                /* if_else.hpp:64-68 */
+            const double c = feval(n.ch[0])[0];
+            n.pw = c != 0 ? 1 : 2;
+            n.val = const_cast<double*>(feval(n.ch[n.pw]));
+            return n.val;
+        }
+        case K_OPEQ: {                                   /* eq.hpp:240-247 */
+            Node& w = nodes[n.ch[0]];
+            for (size_t i = 0; i < N; ++i) n.extra[i] = w.val[i];
+            const double* e = feval(n.ch[1]);
+            const bool es = nodes[n.ch[1]].size() == 1 && N > 1;
+            for (size_t i = 0; i < N; ++i) w.val[i] = binary_f(n.op, w.val[i], e[es ? 0 : i]);
+            return w.val;
+        }
         }
         return nullptr;
     }
@@ -432,6 +479,7 @@ struct orc_graph {
             return;
         }
         case K_BINARY: {                                  /* binary.hpp:120-136 */
+            if (is_comparison(n.op)) return;              /* binary.hpp:124 */
             if (seed.p != n.adj) for (size_t i = 0; i < N; ++i) n.adj[i] = seed.at(i);
             Node& L = nodes[n.ch[0]];
             Node& R = nodes[n.ch[1]];
@@ -544,6 +592,50 @@ struct orc_graph {
             beval(n.ch[0], Seed{nullptr, 0.});
             return;
         case K_NORMAL: normal_beval(n, seed.at(0)); return;
+        case K_NORM: {                                    /* norm.hpp:53-57 */
+            Node& e = nodes[n.ch[0]];
+            n.tmp0.resize(e.size());
+            for (size_t i = 0; i < e.size(); ++i) n.tmp0[i] = seed.at(0) * 2. * e.val[i];
+            beval(n.ch[0], Seed{n.tmp0.data(), 0});
+            return;
+        }
+        case K_TRANSPOSE: {                               /* transpose.hpp:37-41 */
+            if (seed.p != n.adj) for (size_t i = 0; i < N; ++i) n.adj[i] = seed.at(i);
+            const size_t m = nodes[n.ch[0]].rows, k = nodes[n.ch[0]].cols;
+            n.tmp0.resize(N);
+            for (size_t j = 0; j < k; ++j)
+                for (size_t i = 0; i < m; ++i) n.tmp0[i + j * m] = n.adj[j + i * k];
+            beval(n.ch[0], Seed{n.tmp0.data(), 0});
+            return;
+        }
+        case K_IF_ELSE:                                   /* if_else.hpp:70-78 */
+            beval(n.ch[n.pw == 1 ? 1 : 2], seed);
+            return;
+        case K_OPEQ: {                                    /* eq.hpp:249-271 */
+            Node& w = nodes[n.ch[0]];
+            Node& e = nodes[n.ch[1]];
+            const bool es = e.size() == 1 && N > 1;
+            for (size_t i = 0; i < N; ++i) w.adj[i] += seed.at(i);          /* var_view_.beval(seed) */
+            for (size_t i = 0; i < N; ++i) w.val[i] = n.extra[i];           /* restore previous lhs */
+            double* cadj = n.extra.data() + N;
+            for (size_t i = 0; i < N; ++i) { cadj[i] = w.adj[i]; w.adj[i] = 0; }
+            n.tmp0.resize(N); n.tmp1.resize(N);
+            for (size_t i = 0; i < N; ++i) {
+                const double s = cadj[i], x = w.val[i], y = e.val[es ? 0 : i];
+                double ls, rs;
+                switch (n.op) {                                             /* eq.hpp:305-413 */
+                case ORC_ADD: ls = s; rs = s; break;
+                case ORC_SUB: ls = s; rs = -s; break;
+                case ORC_MUL: ls = s * y; rs = s * x; break;
+                default: ls = s / y; rs = -s * x / (y * y); break;
+                }
+                n.tmp0[i] = ls; n.tmp1[i] = rs;
+            }
+            if (es) { double acc = 0; for (size_t i = 0; i < N; ++i) acc += n.tmp1[i]; beval(n.ch[1], Seed{nullptr, acc}); }
+            else beval(n.ch[1], Seed{n.tmp1.data(), 0});
+            beval(n.ch[0], Seed{n.tmp0.data(), 0});
+            return;
+        }
         }
     }
 
@@ -795,6 +887,41 @@ int orc_glue(orc_graph* g, int lhs, int rhs)
 {
     const Node& r = g->nodes[rhs];
     Node n; n.kind = K_GLUE; n.shape = r.shape; n.rows = r.rows; n.cols = r.cols; n.ch = {lhs, rhs};
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+int orc_norm(orc_graph* g, int child)
+{
+    const Node& c = g->nodes[child];
+    if (c.kind == K_CONST) {
+        double acc = 0;
+        for (size_t i = 0; i < c.size(); ++i) acc += c.val[i] * c.val[i];
+        int id = make_const(g, ORC_SCL, 1, 1, {acc}); fix_const_ptrs(g); return id;
+    }
+    Node n; n.kind = K_NORM; n.ch = {child};
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+int orc_transpose(orc_graph* g, int child)
+{
+    const Node& c = g->nodes[child];
+    Node n; n.kind = K_TRANSPOSE; n.shape = ORC_MAT; n.rows = c.cols; n.cols = c.rows; n.ch = {child};
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+int orc_if_else(orc_graph* g, int cond, int a, int b)
+{
+    const Node& c = g->nodes[cond];
+    if (c.kind == K_CONST && c.size() == 1) return c.val[0] != 0 ? a : b;     /* if_else.hpp:141-155 */
+    const Node& x = g->nodes[a];
+    Node n; n.kind = K_IF_ELSE; n.shape = x.shape; n.rows = x.rows; n.cols = x.cols; n.ch = {cond, a, b};
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+int orc_opeq(orc_graph* g, int op, int var, int child)
+{
+    const Node& w = g->nodes[var];
+    Node n; n.kind = K_OPEQ; n.op = op; n.shape = w.shape; n.rows = w.rows; n.cols = w.cols; n.ch = {var, child};
     int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
 }
 

@@ -38,6 +38,8 @@ enum {
 };
 /* binary functors, reverse/core/binary.hpp:265-338 */
 enum { ORC_ADD = 0, ORC_SUB, ORC_MUL, ORC_DIV,
+       /* comparison / logical functors, binary.hpp:347-470: value 0/1, beval is a no-op */
+       ORC_LT, ORC_LE, ORC_GT, ORC_GE, ORC_EQ, ORC_NE, ORC_AND, ORC_OR,
        ORC_MOCKB = 100 /* MockBinary f(x,y)=x-2y, base_fixture.hpp:24-46 */ };
 
 orc_graph* orc_new(void);
@@ -61,6 +63,10 @@ int orc_dot(orc_graph*, int lhs, int rhs);
 int orc_normal(orc_graph*, int x, int mu, int sigma);     /* normal_adj_log_pdf */
 int orc_eq(orc_graph*, int var, int child);               /* placeholder w = expr */
 int orc_glue(orc_graph*, int lhs, int rhs);               /* (lhs, rhs) */
+int orc_norm(orc_graph*, int child);                      /* NormNode, norm.hpp:24-108 */
+int orc_transpose(orc_graph*, int child);                 /* TransposeNode, transpose.hpp:17-81 */
+int orc_if_else(orc_graph*, int cond, int a, int b);      /* IfElseNode, if_else.hpp:29-165 */
+int orc_opeq(orc_graph*, int op, int var, int child);     /* OpEqNode, eq.hpp:194-413 */
 
 /* ad::bind: size query + allocate + post-order bind. out2 = {#val, #adj} as SizePack */
 void orc_bind(orc_graph*, int root, size_t out2[2]);

@@ -194,7 +194,85 @@ def black_scholes_vec(n, put=False):
     return build
 
 
+# ---- SURVEY.md 8f "next" rows -------------------------------------------------------------
+def norm_vec(e):   # norm_unittest.cpp:31-49: NormNode over MockUnary(vec), seed 9.2313
+    v = e.var(kats.FIX_VEC)
+    return e.norm(e.unary("mock2x", v)), [v], 9.2313
+
+
+def norm_mat_chain(n):
+    def build(e):   # node_inttest.cpp:402-442 shape: norm of an elementwise expression of a matrix
+        M = e.var(_vec(n * 3).reshape(n, 3))
+        c = e.var(0.7)
+        return e.norm(e.binary("mul", e.unary("sin", M), c)), [M, c], 1.0
+    return build
+
+
+def transpose_quadratic(e):   # README.md:582-607 with the real transpose node
+    x = e.var(np.array([[0.5], [0.6]]))
+    S = e.const(np.array([[2.0, 3.0], [3.0, 6.0]]))
+    return e.dot(e.dot(e.transpose(x), S), x), [x], np.ones((1, 1))
+
+
+def transpose_of_expr(e):
+    M = e.var(np.array([[1.0, 2.0, -1.0], [0.5, -3.0, 2.0]]))
+    w = e.var(np.array([[0.3], [-0.2]]))
+    t = e.transpose(e.unary("exp", M))                # 3x2
+    return e.sum(e.dot(t, w)), [M, w], 1.0
+
+
+def if_else_scalar(taken):
+    def build(e):   # if_else_unittest: scalar condition from a comparison of variables
+        a, b = e.var(1.5 if taken else -0.5), e.var(0.25)
+        x = e.var(np.array([0.5, 1.5, 2.5]))
+        cond = e.binary("lt", b, a)
+        root = e.sum(e.if_else(cond, e.binary("mul", x, a), e.unary("exp", e.binary("mul", x, b))))
+        return root, [a, b, x], 1.0
+    return build
+
+
+def if_else_logical(e):
+    a, b, c = e.var(0.3), e.var(-1.2), e.var(2.0)
+    cond = e.binary("land", e.binary("ge", a, e.const(0.0)), e.binary("lor", e.binary("gt", b, e.const(0.0)), e.binary("ne", c, a)))
+    root = e.if_else(cond, e.binary("mul", a, c), e.binary("sub", b, c))
+    return root, [a, b, c], 1.0
+
+
+def opeq_scl_alias(e):   # eq_unittest.cpp:143-160: w *= w
+    w = e.var(kats.FIX_SCL)
+    return e.opeq("mul", w, w), [w], 3.2
+def opeq_scl_noalias(e):   # eq_unittest.cpp:162-178: w /= MockUnary(w)
+    w = e.var(kats.FIX_SCL)
+    return e.opeq("div", w, e.unary("mock2x", w)), [w], 3.2
+def opeq_vec_scl(e):   # eq_unittest.cpp:180-199: v *= s
+    v, s_ = e.var(kats.FIX_VEC), e.var(kats.FIX_SCL)
+    return e.opeq("mul", v, s_), [v, s_], np.array([2.1, -0.3, 1.0, 0.5, 4.0])
+def opeq_vec_noalias(e):   # eq_unittest.cpp:220-240: v *= MockUnary(v)
+    v = e.var(kats.FIX_VEC)
+    return e.opeq("mul", v, e.unary("mock2x", v)), [v], np.array([2.1, -0.3, 1.0, 0.5, 4.0])
+def opeq_chain(n):
+    def build(e):   # accumulate-style program: w = x ; w += sin(x) ; w -= c*y ; sum(w*w)
+        x, y, c = e.var(_vec(n)), e.var(_vec(n)), e.var(0.4)
+        w = e.var(np.zeros(n))
+        prog = e.glue(e.eq(w, e.unary("exp", x)), e.opeq("add", w, e.unary("sin", x)), e.opeq("sub", w, e.binary("mul", c, y)),
+                      e.opeq("div", w, e.binary("add", y, e.const(1.0))))
+        return e.glue(prog, e.sum(e.binary("mul", w, w))), [x, y, c, w], 1.0
+    return build
+
+
 CASES = {
+    "norm_vec": norm_vec,
+    "norm_mat_chain": norm_mat_chain(500),
+    "transpose_quadratic": transpose_quadratic,
+    "transpose_of_expr": transpose_of_expr,
+    "if_else_taken": if_else_scalar(True),
+    "if_else_not_taken": if_else_scalar(False),
+    "if_else_logical": if_else_logical,
+    "opeq_scl_alias": opeq_scl_alias,
+    "opeq_scl_noalias": opeq_scl_noalias,
+    "opeq_vec_scl": opeq_vec_scl,
+    "opeq_vec_noalias": opeq_vec_noalias,
+    "opeq_chain": opeq_chain(777),
     "scalar_chain": scalar_chain,
     "placeholders": placeholders,
     "sumnode_benchmark": sumnode_benchmark,

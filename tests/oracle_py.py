@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCL, VEC, MAT = 0, 1, 2
 UNARY = dict(neg=0, sin=1, cos=2, tan=3, asin=4, acos=5, atan=6, exp=7, log=8, sqrt=9, erf=10,
              sigmoid=11, sinh=12, cosh=13, tanh=14, mock2x=100)
-BINARY = dict(add=0, sub=1, mul=2, div=3, mockb=100)
+BINARY = dict(add=0, sub=1, mul=2, div=3, lt=4, le=5, gt=6, ge=7, eq=8, ne=9, land=10, lor=11, mockb=100)
 
 _dp = C.POINTER(C.c_double)
 _lib = None
@@ -36,6 +36,8 @@ def lib(fast=False):
         "orc_sum_iter": (i, [vp, i, C.POINTER(i)]), "orc_prod": (i, [vp, i]),
         "orc_prod_iter": (i, [vp, i, C.POINTER(i)]), "orc_dot": (i, [vp, i, i]),
         "orc_normal": (i, [vp, i, i, i]), "orc_eq": (i, [vp, i, i]), "orc_glue": (i, [vp, i, i]),
+        "orc_norm": (i, [vp, i]), "orc_transpose": (i, [vp, i]), "orc_if_else": (i, [vp, i, i, i]),
+        "orc_opeq": (i, [vp, i, i, i]),
         "orc_bind": (None, [vp, i, C.POINTER(sz)]),
         "orc_feval": (_dp, [vp, i]), "orc_beval": (None, [vp, i, d, vp]),
         "orc_size": (sz, [vp, i]), "orc_is_const": (i, [vp, i]),
@@ -139,6 +141,18 @@ class OracleExpr:
         for nxt in ids[1:]:
             out = self.L.orc_glue(self.g, out, nxt)
         return out
+
+    def norm(self, c):
+        return self.L.orc_norm(self.g, c)
+
+    def transpose(self, c):
+        return self.L.orc_transpose(self.g, c)
+
+    def if_else(self, c, a, b):
+        return self.L.orc_if_else(self.g, c, a, b)
+
+    def opeq(self, op, w, c):
+        return self.L.orc_opeq(self.g, BINARY[op], w, c)
 
     # ---- driver ----
     def bind(self, root):

@@ -267,3 +267,69 @@ def test_threaded_workloads_agree_with_single_thread():
     assert abs(s1 - s2) <= 1e-13 * abs(s1)
     np.testing.assert_array_equal(a1, a2)
     assert_double_eq(a1, np.exp(xs), ulps=1)
+
+
+# ------------------------------------------------------------------ SURVEY.md 8f "next" rows
+def test_norm_goldens():
+    # test/reverse/core/norm_unittest.cpp:31-49: squaredNorm of MockUnary(vec), seed 9.2313
+    e = O.OracleExpr()
+    v = e.var(kats.FIX_VEC)
+    e.bind(e.norm(e.unary("mock2x", v)))
+    assert_double_eq(e.feval(), [float(((2 * kats.FIX_VEC) ** 2).sum())])
+    e.beval(9.2313)
+    assert_double_eq(e.adj(v), 2 * (9.2313 * 2 * (2 * kats.FIX_VEC)))
+
+
+def test_opeq_goldens():
+    # test/reverse/core/eq_unittest.cpp:143-240
+    seed, x0 = 3.2, kats.FIX_SCL
+    e = O.OracleExpr(); w = e.var(x0)
+    e.bind(e.opeq("mul", w, w))
+    assert_double_eq(e.feval(), [x0 * x0])
+    e.beval(seed)
+    assert_double_eq(e.adj(w), [seed * 2 * x0])
+    assert_double_eq(e.value(w), [x0])                       # the previous value is restored (eq.hpp:255)
+    e = O.OracleExpr(); w = e.var(x0)
+    e.bind(e.opeq("div", w, e.unary("mock2x", w)))
+    assert_double_eq(e.feval(), [x0 / (2 * x0)])
+    e.beval(seed)
+    assert abs(e.adj(w)[0]) <= 1e-16
+    vseed = np.array([2.1, -0.3, 1.0, 0.5, 4.0])
+    e = O.OracleExpr(); v = e.var(kats.FIX_VEC); s = e.var(x0)
+    e.bind(e.opeq("mul", v, s))
+    assert_double_eq(e.feval(), kats.FIX_VEC * x0)
+    e.beval(vseed)
+    assert_double_eq(e.adj(v), vseed * x0)
+    assert_double_eq(e.adj(s), [float((vseed * kats.FIX_VEC).sum())])
+    e = O.OracleExpr(); v = e.var(kats.FIX_VEC)
+    e.bind(e.opeq("mul", v, e.unary("mock2x", v)))
+    e.feval(); e.beval(vseed)
+    assert_double_eq(e.adj(v), vseed * (2 * kats.FIX_VEC + 2 * kats.FIX_VEC))
+
+
+def test_if_else_and_comparisons():
+    # test/reverse/core/if_else_unittest.cpp: only the taken branch receives the seed;
+    # comparison nodes have no adjoint (binary.hpp:124)
+    for a0, taken in ((1.5, True), (-0.5, False)):
+        e = O.OracleExpr()
+        a, b = e.var(a0), e.var(0.25)
+        x = e.var(np.array([0.5, 1.5, 2.5]))
+        root = e.sum(e.if_else(e.binary("lt", b, a), e.binary("mul", x, a), e.unary("exp", e.binary("mul", x, b))))
+        e.bind(root)
+        xv = np.array([0.5, 1.5, 2.5])
+        want = (xv * a0).sum() if taken else np.exp(xv * 0.25).sum()
+        assert_double_eq(e.autodiff(), [want])
+        if taken:
+            assert_double_eq(e.adj(a), [xv.sum()]); assert_double_eq(e.adj(b), [0.0]); assert_double_eq(e.adj(x), [a0] * 3)
+        else:
+            assert_double_eq(e.adj(a), [0.0]); assert_double_eq(e.adj(x), 0.25 * np.exp(xv * 0.25))
+
+
+def test_transpose_quadratic_form_readme():
+    # README.md:582-607 with ad::transpose: x^T Sigma x = 4.46, adj [5.6, 10.2]
+    e = O.OracleExpr()
+    x = e.var(np.array([[0.5], [0.6]]))
+    S = e.const(np.array([[2.0, 3.0], [3.0, 6.0]]))
+    e.bind(e.dot(e.dot(e.transpose(x), S), x))
+    assert_double_eq(e.autodiff(np.ones((1, 1))), [4.46])
+    assert_double_eq(e.adj(x), [5.6, 10.2])
