@@ -503,12 +503,20 @@ private:
 template <int Code> struct BinaryTag { static constexpr int code = Code; };
 using Add = BinaryTag<FADB_ADD>; using Sub = BinaryTag<FADB_SUB>; using Mul = BinaryTag<FADB_MUL>;
 using Div = BinaryTag<FADB_DIV>; using MockBinary = BinaryTag<FADB_MOCKB>;
+// comparison / logical functors (binary.hpp:347-470): value 0 or 1, no adjoint
+using LessThan = BinaryTag<FADB_LT>; using LessThanEq = BinaryTag<FADB_LE>; using GreaterThan = BinaryTag<FADB_GT>;
+using GreaterThanEq = BinaryTag<FADB_GE>; using Equal = BinaryTag<FADB_EQ>; using NotEqual = BinaryTag<FADB_NE>;
+using LogicalAnd = BinaryTag<FADB_AND>; using LogicalOr = BinaryTag<FADB_OR>;
 
 inline double fold_binary(int code, double x, double y)
 {
     switch (code) {
     case FADB_ADD: return x + y; case FADB_SUB: return x - y; case FADB_MUL: return x * y;
-    case FADB_DIV: return x / y; default: return x - 2 * y;
+    case FADB_DIV: return x / y;
+    case FADB_LT: return x < y; case FADB_LE: return x <= y; case FADB_GT: return x > y; case FADB_GE: return x >= y;
+    case FADB_EQ: return x == y; case FADB_NE: return x != y; case FADB_AND: return x != 0 && y != 0;
+    case FADB_OR: return x != 0 || y != 0;
+    default: return x - 2 * y;
     }
 }
 
@@ -682,6 +690,85 @@ private:
     R r_;
 };
 
+// NormNode (norm.hpp:24-108): squared L2 / Frobenius norm
+template <class ExprType>
+struct NormNode : ExprBase<NormNode<ExprType>> {
+    static_assert(!util::is_scl_v<ExprType>, "norm of a scalar (norm.hpp:34)");
+    using value_t = double;
+    using shape_t = scl;
+    NormNode(const ExprType& e) : expr_(e) {}
+    size_t rows() const { return 1; }
+    size_t cols() const { return 1; }
+    size_t size() const { return 1; }
+    int lower(detail::Lowering& L) const { return detail::checked_id(fadb_expr_norm(L.e, expr_.lower(L))); }
+    const ExprType& child() const { return expr_; }
+private:
+    ExprType expr_;
+};
+
+// TransposeNode (transpose.hpp:17-60)
+template <class ExprType>
+struct TransposeNode : ExprBase<TransposeNode<ExprType>> {
+    static_assert(!util::is_scl_v<ExprType>, "transpose of a scalar (transpose.hpp:25)");
+    using value_t = double;
+    using shape_t = mat;
+    TransposeNode(const ExprType& e) : expr_(e) {}
+    size_t rows() const { return expr_.cols(); }
+    size_t cols() const { return expr_.rows(); }
+    size_t size() const { return expr_.size(); }
+    int lower(detail::Lowering& L) const { return detail::checked_id(fadb_expr_transpose(L.e, expr_.lower(L))); }
+private:
+    ExprType expr_;
+};
+
+// IfElseNode (if_else.hpp:29-114): scalar condition, branches of one shape
+template <class C, class I, class E>
+struct IfElseNode : ExprBase<IfElseNode<C, I, E>> {
+    static_assert(util::is_scl_v<C> && std::is_same_v<typename I::shape_t, typename E::shape_t>,
+                  "if_else: scalar condition, same-shape branches (if_else.hpp:52-55)");
+    using value_t = double;
+    using shape_t = typename I::shape_t;
+    IfElseNode(const C& c, const I& i, const E& e) : c_(c), i_(i), e_(e) { assert(i.rows() == e.rows() && i.cols() == e.cols()); }
+    size_t rows() const { return i_.rows(); }
+    size_t cols() const { return i_.cols(); }
+    size_t size() const { return i_.size(); }
+    int lower(detail::Lowering& L) const
+    {
+        int c = c_.lower(L);
+        int a = i_.lower(L);
+        int b = e_.lower(L);
+        return detail::checked_id(fadb_expr_if_else(L.e, c, a, b));
+    }
+private:
+    C c_;
+    I i_;
+    E e_;
+};
+
+// OpEqNode (eq.hpp:194-303): w += / -= / *= / /= expr
+template <class Op, class VarViewType, class ExprType>
+struct OpEqNode : ExprBase<OpEqNode<Op, VarViewType, ExprType>> {
+    using value_t = double;
+    using shape_t = typename VarViewType::shape_t;
+    OpEqNode(const VarViewType& v, const ExprType& e) : v_(v), e_(e)
+    {
+        if constexpr (!util::is_scl_v<ExprType>) assert(v.rows() == e.rows() && v.cols() == e.cols());
+    }
+    size_t rows() const { return v_.rows(); }
+    size_t cols() const { return v_.cols(); }
+    size_t size() const { return v_.size(); }
+    int lower(detail::Lowering& L) const
+    {
+        int w = v_.lower(L);
+        int c = e_.lower(L);
+        return detail::checked_id(fadb_expr_opeq(L.e, Op::code, w, c));
+    }
+private:
+    VarViewType v_;
+    ExprType e_;
+};
+using AddEq = BinaryTag<FADB_ADD>; using SubEq = BinaryTag<FADB_SUB>; using MulEq = BinaryTag<FADB_MUL>; using DivEq = BinaryTag<FADB_DIV>;
+
 // ---- operators live in ad::core for ADL (binary.hpp:472-498, unary.hpp:297, glue.hpp:124-139)
 #define FASTAD_B200_BINARY_OP(name, tag)                                                              \
     template <class A, class B,                                                                      \
@@ -702,6 +789,14 @@ FASTAD_B200_BINARY_OP(operator+, Add)
 FASTAD_B200_BINARY_OP(operator-, Sub)
 FASTAD_B200_BINARY_OP(operator*, Mul)
 FASTAD_B200_BINARY_OP(operator/, Div)
+FASTAD_B200_BINARY_OP(operator<, LessThan)
+FASTAD_B200_BINARY_OP(operator<=, LessThanEq)
+FASTAD_B200_BINARY_OP(operator>, GreaterThan)
+FASTAD_B200_BINARY_OP(operator>=, GreaterThanEq)
+FASTAD_B200_BINARY_OP(operator==, Equal)
+FASTAD_B200_BINARY_OP(operator!=, NotEqual)
+FASTAD_B200_BINARY_OP(operator&&, LogicalAnd)
+FASTAD_B200_BINARY_OP(operator||, LogicalOr)
 #undef FASTAD_B200_BINARY_OP
 
 template <class A, class B, class = std::enable_if_t<is_expr_v<A> && is_expr_v<B>>>
@@ -849,6 +944,80 @@ inline auto normal_adj_log_pdf(const X& x, const M& m, const S& s)
     s_t es = s;
     return core::NormalAdjLogPDFNode<x_t, m_t, s_t>(ex, em, es);
 }
+
+// ---- SURVEY.md 8f "next" rows ---------------------------------------------------------------
+template <class A, class = std::enable_if_t<util::is_convertible_to_ad_v<A> && util::any_ad_v<A>>>
+inline auto norm(const A& a)          // norm.hpp:91-106
+{
+    using ea_t = util::convert_to_ad_t<A>;
+    ea_t ea = a;
+    return core::NormNode<ea_t>(ea);
+}
+template <class A, class = std::enable_if_t<util::is_convertible_to_ad_v<A> && util::any_ad_v<A>>>
+inline auto transpose(const A& a)     // transpose.hpp:64-79
+{
+    using ea_t = util::convert_to_ad_t<A>;
+    ea_t ea = a;
+    return core::TransposeNode<ea_t>(ea);
+}
+template <class C, class I, class E,
+          class = std::enable_if_t<util::is_convertible_to_ad_v<C> && util::is_convertible_to_ad_v<I> &&
+                                   util::is_convertible_to_ad_v<E> && util::any_ad_v<C, I, E>>>
+inline auto if_else(const C& c, const I& i, const E& e)   // if_else.hpp:118-163
+{
+    using c_t = util::convert_to_ad_t<C>;
+    using i_t = util::convert_to_ad_t<I>;
+    using e_t = util::convert_to_ad_t<E>;
+    c_t ec = c;
+    i_t ei = i;
+    e_t ee = e;
+    return core::IfElseNode<c_t, i_t, e_t>(ec, ei, ee);
+}
+// ad::for_each(begin, end, f): evaluate every f(x) in order, value of the last (for_each.hpp:19-131);
+// lowered as a left-to-right chain of glue nodes
+namespace core {
+template <class ExprType>
+struct ForEachIterNode : ExprBase<ForEachIterNode<ExprType>> {
+    using value_t = double;
+    using shape_t = typename ExprType::shape_t;
+    ForEachIterNode(std::vector<ExprType> v) : vec_(std::move(v)) { assert(!vec_.empty()); }
+    size_t rows() const { return vec_.back().rows(); }
+    size_t cols() const { return vec_.back().cols(); }
+    size_t size() const { return vec_.back().size(); }
+    int lower(detail::Lowering& L) const
+    {
+        int acc = vec_[0].lower(L);
+        for (size_t k = 1; k < vec_.size(); ++k) acc = detail::checked_id(fadb_expr_glue(L.e, acc, vec_[k].lower(L)));
+        return acc;
+    }
+private:
+    std::vector<ExprType> vec_;
+};
+}  // namespace core
+template <class Iter, class Lmda>
+inline auto for_each(Iter begin, Iter end, Lmda&& f)
+{
+    using expr_t = util::convert_to_ad_t<std::decay_t<decltype(f(*begin))>>;
+    std::vector<expr_t> exprs;
+    exprs.reserve(std::distance(begin, end));
+    for (auto it = begin; it != end; ++it) exprs.emplace_back(f(*it));
+    return core::ForEachIterNode<expr_t>(std::move(exprs));
+}
+
+// w += expr, w -= expr, w *= expr, w /= expr  (var_view.hpp:199-217)
+#define FASTAD_B200_OPEQ(name, tag)                                                                   \
+    template <class V, class S, class D, class = std::enable_if_t<util::is_convertible_to_ad_v<D>>>   \
+    inline auto name(const VarView<V, S>& var, const D& x)                                            \
+    {                                                                                                 \
+        using expr_t = util::convert_to_ad_t<D>;                                                      \
+        expr_t expr = x;                                                                              \
+        return core::OpEqNode<core::tag, VarView<V, S>, expr_t>(var, expr);                           \
+    }
+FASTAD_B200_OPEQ(operator+=, AddEq)
+FASTAD_B200_OPEQ(operator-=, SubEq)
+FASTAD_B200_OPEQ(operator*=, MulEq)
+FASTAD_B200_OPEQ(operator/=, DivEq)
+#undef FASTAD_B200_OPEQ
 
 // ---------------------------------------------------------------------------------------------
 // bind / evaluate / evaluate_adj / autodiff  (bind.hpp:18-49, eval.hpp:18-153)

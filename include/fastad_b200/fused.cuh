@@ -208,7 +208,8 @@ struct Dev<core::BinaryNode<Tag, L, R>> {
     }
 };
 template <class Tag, class L, class R>
-struct fusable<core::BinaryNode<Tag, L, R>> : std::bool_constant<fusable<L>::value && fusable<R>::value> {};
+struct fusable<core::BinaryNode<Tag, L, R>>
+    : std::bool_constant<fusable<L>::value && fusable<R>::value && (Tag::code <= FADB_DIV || Tag::code == FADB_MOCKB)> {};
 
 template <int64_t N, class E>
 struct Dev<core::PowNode<N, E>> {
@@ -293,6 +294,21 @@ struct Dev<core::SumElemNode<E>> {
     __device__ __forceinline__ void bwd(double s, size_t i, Tape& t, Acc& a) const { e.bwd(s, i, t.c, a); }   // sum.hpp:170-173
 };
 
+// NormNode as a root: sum of squares, child seed 2*seed*x (norm.hpp:47-57)
+template <class E>
+struct Dev<core::NormNode<E>> {
+    Dev<E> e;
+    struct Tape { typename Dev<E>::Tape c; double v; };
+    static Dev make(const core::NormNode<E>& n, Ctx& c) { return Dev{Dev<E>::make(n.child(), c)}; }
+    __device__ __forceinline__ void fwd(size_t i, Tape& t, Acc& a) const
+    {
+        e.fwd(i, t.c, a);
+        t.v = t.c.v * t.c.v;
+        a.ch[0] += t.v;
+    }
+    __device__ __forceinline__ void bwd(double s, size_t i, Tape& t, Acc& a) const { e.bwd(s * 2. * t.c.v, i, t.c, a); }
+};
+
 template <class X, class M, class S>
 struct Dev<core::NormalAdjLogPDFNode<X, M, S>> {
     Dev<X> x;
@@ -356,12 +372,14 @@ struct Dev<core::NormalAdjLogPDFNode<X, M, S>> {
 template <class E> struct terminal { static constexpr int kind = T_STORE; using last_t = E; };
 template <class L, class R> struct terminal<core::GlueNode<L, R>> : terminal<R> {};
 template <class E> struct terminal<core::SumElemNode<E>> { static constexpr int kind = T_SUM; using last_t = core::SumElemNode<E>; };
+template <class E> struct terminal<core::NormNode<E>> { static constexpr int kind = T_SUM; using last_t = core::NormNode<E>; };
 template <class X, class M, class S> struct terminal<core::NormalAdjLogPDFNode<X, M, S>> {
     static constexpr int kind = T_NORMAL; using last_t = core::NormalAdjLogPDFNode<X, M, S>;
 };
 // a root may END in a reduction; reductions anywhere else are not fusable
 template <class E> struct root_fusable : fusable<E> {};
 template <class E> struct root_fusable<core::SumElemNode<E>> : fusable<E> {};
+template <class E> struct root_fusable<core::NormNode<E>> : fusable<E> {};
 template <class X, class M, class S>
 struct root_fusable<core::NormalAdjLogPDFNode<X, M, S>>
     : std::bool_constant<fusable<X>::value && fusable<M>::value && fusable<S>::value> {};
@@ -576,6 +594,7 @@ struct FusedBind {
 private:
     template <class E> static size_t domain_size(const E& e) { return e.size(); }
     template <class E> static size_t domain_size(const core::SumElemNode<E>& e) { return e.child().size(); }
+    template <class E> static size_t domain_size(const core::NormNode<E>& e) { return e.child().size(); }
     template <class X, class M, class S>
     static size_t domain_size(const core::NormalAdjLogPDFNode<X, M, S>& e)
     {

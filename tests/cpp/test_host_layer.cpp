@@ -318,6 +318,79 @@ static void vectors_and_seeds()
     CHECK_DOUBLE_EQ(a.get_adj(), 3.0);
 }
 
+static void next_rows()
+{
+    // ---- ad::norm (norm_unittest.cpp:31-49) and a norm of an expression (node_inttest.cpp:402-442 shape)
+    {
+        Var<double, vec> v(5);
+        v.get() = {3.1, -2.3, 1.3, 0., 5.1};
+        core::UnaryNode<core::MockUnary, VarView<double, vec>> u(v);
+        auto b = ad::bind(ad::norm(u));
+        double ref = 0;
+        for (double x : {3.1, -2.3, 1.3, 0., 5.1}) ref += 4 * x * x;
+        CHECK_DOUBLE_EQ(ad::autodiff(b, 9.2313), ref);
+        CHECK_DOUBLE_EQ(v.get_adj()(0), 2 * (9.2313 * 2 * (2 * 3.1)));
+        CHECK_DOUBLE_EQ(v.get_adj()(3), 0.);
+    }
+    // ---- README.md:582-607 exactly as written there: x^T Sigma x with ad::transpose
+    {
+        Var<double, mat> x(2, 1);
+        x.get() = {0.5, 0.6};
+        auto Sigma = ad::constant({2., 3., 3., 6.}, 2, 2);
+        auto b = ad::bind(ad::dot(ad::dot(ad::transpose(x), Sigma), x));
+        auto f = ad::autodiff(b, std::vector<double>{1.});
+        CHECK_DOUBLE_EQ(f[0], 4.46);
+        CHECK_DOUBLE_EQ(x.get_adj(0, 0), 5.6);
+        CHECK_DOUBLE_EQ(x.get_adj(1, 0), 10.2);
+    }
+    // ---- ad::if_else with comparison / logical nodes (if_else_unittest.cpp, binary.hpp:347-470)
+    for (double a0 : {1.5, -0.5}) {
+        Var<double> a(a0), b(0.25);
+        Var<double, vec> x(3);
+        x.get() = {0.5, 1.5, 2.5};
+        auto e = ad::bind(ad::sum(ad::if_else((b < a) && (a != b), x * a, ad::exp(x * b))));
+        const double v = ad::autodiff(e);
+        if (a0 > 0.25) {
+            CHECK_DOUBLE_EQ(v, 4.5 * a0);
+            CHECK_DOUBLE_EQ(a.get_adj(), 4.5);
+            CHECK_DOUBLE_EQ(b.get_adj(), 0.);
+            CHECK_DOUBLE_EQ(x.get_adj()(1), a0);
+        } else {
+            CHECK_DOUBLE_EQ(v, std::exp(0.125) + std::exp(0.375) + std::exp(0.625));
+            CHECK_DOUBLE_EQ(a.get_adj(), 0.);
+            CHECK_DOUBLE_EQ(x.get_adj()(2), 0.25 * std::exp(0.625));
+        }
+    }
+    // ---- op= nodes (eq_unittest.cpp:143-240)
+    {
+        const double seed = 3.2, x0 = 2.31;
+        Var<double> w(x0);
+        auto e1 = ad::bind((w *= w));
+        CHECK_DOUBLE_EQ(ad::autodiff(e1, seed), x0 * x0);
+        CHECK_DOUBLE_EQ(w.get_adj(), seed * 2 * x0);
+        CHECK_DOUBLE_EQ(w.get(), x0);                       // the previous value is restored (eq.hpp:255)
+        Var<double, vec> v(5);
+        Var<double> s(x0);
+        v.get() = {3.1, -2.3, 1.3, 0., 5.1};
+        auto e2 = ad::bind((v *= s));
+        auto r = ad::autodiff(e2, std::vector<double>{2.1, -0.3, 1.0, 0.5, 4.0});
+        CHECK_DOUBLE_EQ(r[0], 3.1 * x0);
+        CHECK_DOUBLE_EQ(v.get_adj()(4), 4.0 * x0);
+        CHECK_DOUBLE_EQ(s.get_adj(), 2.1 * 3.1 + 0.3 * 2.3 + 1.0 * 1.3 + 0.5 * 0. + 4.0 * 5.1);
+    }
+    // ---- ad::for_each (for_each.hpp:19-131): evaluate all, value of the last, seed to the last only
+    {
+        std::vector<Var<double>> xs, ws(3);
+        for (double x : {0.5, 1.5, 2.5}) xs.emplace_back(x);
+        std::vector<size_t> idx{0, 1, 2};
+        auto e = ad::bind(ad::for_each(idx.begin(), idx.end(), [&](size_t k) { return ws[k] = xs[k] * xs[k]; }));
+        CHECK_DOUBLE_EQ(ad::autodiff(e), 6.25);
+        CHECK_DOUBLE_EQ(ws[0].get(), 0.25);
+        CHECK_DOUBLE_EQ(xs[2].get_adj(), 5.0);
+        CHECK_DOUBLE_EQ(xs[0].get_adj(), 0.);
+    }
+}
+
 int main()
 {
     if (fadb_init(0) != 0) { std::printf("no CUDA device: %s\n", fadb_last_error()); return 2; }
@@ -327,5 +400,6 @@ int main()
     stat_normal();
     readme_examples();
     vectors_and_seeds();
+    next_rows();
     return report("test_host_layer");
 }
