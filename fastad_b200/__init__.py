@@ -77,6 +77,7 @@ SIGNATURES = {
     "fadb_expr_normal": (_i, [_vp, _i, _i, _i]),
     "fadb_expr_eq": (_i, [_vp, _i, _i]),
     "fadb_expr_glue": (_i, [_vp, _i, _i]),
+    "fadb_expr_logpdf": (_i, [_vp, _i, _i, _i, _i]),
     "fadb_expr_norm": (_i, [_vp, _i]),
     "fadb_expr_transpose": (_i, [_vp, _i]),
     "fadb_expr_if_else": (_i, [_vp, _i, _i, _i]),
@@ -317,6 +318,9 @@ class Expr:
         for nxt in ids[1:]:
             out = self._id(self.L.fadb_expr_glue(self.h, out, nxt))
         return out
+
+    def logpdf(self, dist, a, b, c=-1):
+        return self._id(self.L.fadb_expr_logpdf(self.h, dict(cauchy=0, uniform=1, bernoulli=2)[dist], a, b, c))
 
     def norm(self, c):
         return self._id(self.L.fadb_expr_norm(self.h, c))

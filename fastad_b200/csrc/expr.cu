@@ -45,7 +45,7 @@ namespace fadb {
 
 // ======================================================================== device program
 enum : int { I_LEAF = 0, I_CONST, I_UNARY, I_BINARY, I_POW, I_EQ, I_GLUE, I_JZ, I_JMP, I_PHI, I_OPEQ };
-enum : int { T_NONE = 0, T_SUM, T_PROD, T_NORMAL };
+enum : int { T_NONE = 0, T_SUM, T_PROD, T_NORMAL, T_CAUCHY, T_UNIFORM, T_BERNOULLI };
 enum : int { M_F = 1, M_B = 2, M_FB = 3 };
 
 struct Ins {
@@ -141,7 +141,7 @@ stage_kernel(StageArgs a)
         sig_s = a.sig_ptr ? *a.sig_ptr : 1.0;
         if (!(sig_s > 0)) gated = true;                       // normal.hpp:147, 231, 344
     }
-    if (a.term == T_NORMAL && !a.seed_vec && seed_s == 0.0) back = false;   // normal.hpp:160
+    if (a.term >= T_NORMAL && !a.seed_vec && seed_s == 0.0) back = false;   // normal.hpp:160, cauchy.hpp:151
     double pr_pnz = 1.0, pr_zeros = 0.0, pr_val = 0.0;
     if (a.term == T_PROD && back) { pr_pnz = a.red[0]; pr_zeros = a.red[1]; pr_val = a.red[2]; }
 
@@ -228,6 +228,24 @@ stage_kernel(StageArgs a)
             } else {
                 acc[0] += nrm_d * nrm_d;                       // squaredNorm, normal.hpp:244
             }
+        } else if (a.term == T_CAUCHY) {
+            // CauchyAdjLogPDFNode (stat/cauchy.hpp): -log(gamma + d^2/gamma) per element, gamma > 0
+            const double d = V(a.nx) - V(a.nm), gm = V(a.ns);
+            if (!(gm > 0)) { acc[2] += 1.0; if (!a.sig_vec) gated = true; }
+            acc[0] += a.N == 1 ? log(gm + (d * d) / gm)                 // cauchy.hpp:144-146
+                               : log(gm + (1. / gm) * (d * d));         // cauchy.hpp:216-217
+        } else if (a.term == T_UNIFORM) {
+            // UniformAdjLogPDFNode (stat/uniform.hpp): -log(max - min), min < x < max
+            const double x = V(a.nx), lo = V(a.nm), hi = V(a.ns);
+            if (!(lo < x && x < hi)) acc[2] += 1.0;
+            acc[0] += log(hi - lo);
+        } else if (a.term == T_BERNOULLI) {
+            // BernoulliAdjLogPDFNode (stat/bernoulli.hpp:119-141): x in {0,1}, 0 < p < 1
+            const double x = V(a.nx), p = V(a.nm);
+            const bool in_range = 0 < p && p < 1, zero_one = x == 0 || x == 1;
+            if (!in_range || !zero_one) acc[2] += 1.0;
+            if (!in_range) acc[0] += (p <= 0) ? (x == 0 ? 0.0 : -INFINITY) : (x == 1 ? 0.0 : -INFINITY);
+            else acc[0] += x == 0 ? log(1 - p) : x == 1 ? log(p) : -INFINITY;
         } else if (fwd_out && a.out_vec) a.out_vec[i] = V(a.root);
         if (!back) continue;
 
@@ -255,6 +273,27 @@ stage_kernel(StageArgs a)
                     G(a.nm) += a.mu_vec ? c * d : sd * (d * inv_s_sq);                           // :370, 277
                     G(a.ns) += sd * ((d * d) / (s * s) - 1.) * inv_s;                            // :273 per element
                 }
+            } else if (a.term == T_CAUCHY) {
+                const double d = V(a.nx) - V(a.nm), gm = V(a.ns);
+                if (a.N == 1) {                                                                   // cauchy.hpp:149-165
+                    const double inner = gm + (d * d) / gm;
+                    const double x0_adj = 2. * d / (gm * inner);
+                    G(a.ns) += sd * (1. / gm * (x0_adj * d - 1));
+                    G(a.nm) += sd * x0_adj;
+                    G(a.nx) += sd * -x0_adj;
+                } else {   // vector cases exactly as written in cauchy.hpp:220-237 (seed enters dx0, dgamma twice)
+                    const double dx = (-2. * sd) * d / (gm * gm + d * d);
+                    G(a.ns) += (-sd / gm) * (dx * d + 1);
+                    G(a.nm) += (-sd) * dx;
+                    G(a.nx) += dx;
+                }
+            } else if (a.term == T_UNIFORM) {                                                     // uniform.hpp:157-163
+                const double adj = sd / (V(a.ns) - V(a.nm));
+                G(a.ns) += -adj;
+                G(a.nm) += adj;
+            } else if (a.term == T_BERNOULLI) {                                                   // bernoulli.hpp:143-149
+                const double x = V(a.nx), p = V(a.nm);
+                G(a.nm) += x == 0 ? -sd / (1 - p) : sd / p;
             } else if (a.term == T_PROD) {
                 const double e = V(a.root);                                                      // prod.hpp:194-207
                 G(a.root) = (e == 0) ? sd * ((pr_zeros > 1) ? 0.0 : pr_pnz) : sd * (pr_val / e);
@@ -396,13 +435,19 @@ stage_kernel(StageArgs a)
                 else val = -0.5 * (tot[0] / (sig_s * sig_s)) - (double)a.N * log(sig_s);         // normal.hpp:245-246
             }
             a.out_scalar[0] = val;
+        } else if (a.term == T_CAUCHY || a.term == T_UNIFORM) {
+            a.red[1] = tot[2];
+            a.out_scalar[0] = tot[2] != 0.0 ? -INFINITY : -tot[0];
+        } else if (a.term == T_BERNOULLI) {
+            a.red[1] = tot[2];
+            a.out_scalar[0] = tot[0];
         }
     }
     if (a.mode & M_B) {
         for (int k = 0; k < a.nleaves; ++k) {
             const LeafDesc& L = s_leaf[k];
             if (L.channel < 0 || L.adj_mode == 0) continue;
-            const bool skip = gated || !back;
+            const bool skip = gated || !back || (a.term > T_NORMAL && (a.mode & M_F) && tot[2] != 0.0);
             if (L.adj_mode == 2) L.adj[0] = skip ? 0.0 : tot[L.channel];
             else if (!skip) L.adj[0] += tot[L.channel];
         }
@@ -468,7 +513,7 @@ __global__ void fill_kernel(double* p, size_t n, double v)
 
 // ======================================================================== host: builder + planner
 enum NodeKind { N_VAR, N_CONST_S, N_CONST_V, N_UNARY, N_BINARY, N_POW, N_SUM, N_SUM_ITER, N_PROD,
-                N_PROD_ITER, N_DOT, N_NORMAL, N_EQ, N_GLUE, N_TRANSPOSE, N_IF_ELSE, N_OPEQ };
+                N_PROD_ITER, N_DOT, N_NORMAL, N_EQ, N_GLUE, N_TRANSPOSE, N_IF_ELSE, N_OPEQ, N_LOGPDF };
 
 struct ENode {
     NodeKind kind;
@@ -496,6 +541,7 @@ struct Stage {
     std::set<int> assigned;        // placeholder node ids assigned in this stage
     int term = T_NONE, root = -1, nx = -1, nm = -1, ns = -1, mu_vec = 0, sig_vec = 0;
     int sig_leaf = -1;             // leaf index of a scalar sigma (T_NORMAL)
+    bool needs_check = false;      // log-pdf whose validity is a property of ALL elements
     double sig_const = 0; bool sig_is_const = false;
     int nch = 0, term_ch = 0;
     int node = -1;                 // expression node this stage evaluates (its output)
@@ -539,7 +585,7 @@ struct fadb_expr {
     bool is_const_scalar(int id) const { return nodes[id].kind == N_CONST_S; }
 
     // ---------------------------------------------------------------- planning (host only)
-    static bool barrier(NodeKind k) { return k == N_SUM || k == N_PROD || k == N_NORMAL || k == N_DOT || k == N_TRANSPOSE; }
+    static bool barrier(NodeKind k) { return k == N_SUM || k == N_PROD || k == N_NORMAL || k == N_DOT || k == N_TRANSPOSE || k == N_LOGPDF; }
 
     int emit(Stage& st, Ins I)
     {
@@ -679,7 +725,7 @@ struct fadb_expr {
                   std::to_string(MAXL) + " distinct leaves";
             return false;
         }
-        st.term_ch = st.term == T_SUM ? 1 : st.term == T_NORMAL ? 3 : st.term == T_PROD ? 1 : 0;
+        st.term_ch = st.term == T_SUM ? 1 : st.term >= T_NORMAL ? 3 : st.term == T_PROD ? 1 : 0;
         int ch = st.term_ch;
         for (auto& L : st.leaves)
             if (L.scalar && L.adj_mode != 0 && st.N > 1) L.channel = ch++;
@@ -714,6 +760,17 @@ struct fadb_expr {
             st->term = n.kind == N_SUM ? T_SUM : T_PROD;
             st->root = lower(n.ch[0], *st);
             if (st->root < 0) return -1;
+        } else if (n.kind == N_LOGPDF) {
+            size_t N = 1;
+            for (int c : n.ch) N = std::max(N, nodes[c].size());
+            st->N = N;
+            st->term = T_CAUCHY + n.fn;
+            st->nx = lower(n.ch[0], *st); if (st->nx < 0) return -1;
+            st->nm = lower(n.ch[1], *st); if (st->nm < 0) return -1;
+            if (n.ch.size() > 2) { st->ns = lower(n.ch[2], *st); if (st->ns < 0) return -1; }
+            st->sig_vec = n.ch.size() > 2 && nodes[n.ch[2]].size() > 1;
+            // Cauchy with a scalar scale is the only case whose validity every thread can see
+            st->needs_check = !(st->term == T_CAUCHY && !st->sig_vec);
         } else if (n.kind == N_NORMAL) {
             size_t N = 1;
             for (int c : n.ch) N = std::max(N, nodes[c].size());
@@ -865,7 +922,7 @@ struct fadb_expr {
     std::string describe() const
     {
         static const char* opn[] = {"leaf", "const", "unary", "binary", "pow", "eq", "glue", "jz", "jmp", "phi", "opeq"};
-        static const char* tn[] = {"store", "sum", "prod", "normal"};
+        static const char* tn[] = {"store", "sum", "prod", "normal", "cauchy", "uniform", "bernoulli"};
         std::ostringstream o;
         o << "stages=" << plan.size() << " cache={" << cache_vals << "," << cache_adjs << "}\n";
         for (size_t k = 0; k < plan.size(); ++k) {
@@ -1002,7 +1059,7 @@ struct fadb_expr {
         a.out_scalar = st.mval;
         a.seed_vec = seed_vec; a.seed_ptr = seed_ptr; a.seed = seed;
         a.red = st.d_red;
-        a.gate = (st.term == T_NORMAL && st.sig_vec && mode == M_B) ? st.d_red + 1 : nullptr;
+        a.gate = (((st.term == T_NORMAL && st.sig_vec) || (st.term > T_NORMAL && st.needs_check)) && mode == M_B) ? st.d_red + 1 : nullptr;
         a.nch = st.nch; a.term_ch = st.term_ch;
         a.partials = c.partials; a.ticket = c.tickets + 8;
         a.scratch = st.d_scratch;
@@ -1134,7 +1191,8 @@ struct fadb_expr {
         if (fast) return run_fast_root(c, rs, seed);
         // root stage: fused when the seed suffices (no global quantity needed before the sweep)
         const bool fusable = rs.type != 0 || rs.term == T_NONE || rs.term == T_SUM ||
-                             (rs.term == T_NORMAL && (!rs.sig_vec || (flags & FADB_TRUST_SIGMA)));
+                             (rs.term == T_NORMAL && (!rs.sig_vec || (flags & FADB_TRUST_SIGMA))) ||
+                             (rs.term > T_NORMAL && (!rs.needs_check || (flags & FADB_TRUST_SIGMA)));
         int rc = 0;
         if (what == 3 && fusable) {
             rc = rs.type != 0 ? run_dot(c, rs, M_FB, seed_vec, seed) : run_map(c, rs, M_FB, seed, seed_vec, nullptr);
@@ -1372,6 +1430,19 @@ int fadb_expr_glue(fadb_expr* e, int lhs, int rhs)
     EXPR_REQUIRE(e, e && e->ok(lhs) && e->ok(rhs), "fadb_expr_glue: bad arguments");
     const ENode& r = e->nodes[rhs];
     ENode n; n.kind = N_GLUE; n.shape = r.shape; n.rows = r.rows; n.cols = r.cols; n.ch = {lhs, rhs};
+    return e->add(std::move(n));
+}
+
+int fadb_expr_logpdf(fadb_expr* e, int dist, int a, int b, int c)
+{
+    EXPR_REQUIRE(e, e && dist >= FADB_CAUCHY && dist <= FADB_BERNOULLI && e->ok(a) && e->ok(b) &&
+                 (dist == FADB_BERNOULLI || e->ok(c)), "fadb_expr_logpdf: bad arguments");
+    size_t N = std::max(e->nodes[a].size(), e->nodes[b].size());
+    if (dist != FADB_BERNOULLI) N = std::max(N, e->nodes[c].size());
+    for (int id : {a, b, dist == FADB_BERNOULLI ? a : c})
+        EXPR_REQUIRE(e, e->nodes[id].size() == 1 || e->nodes[id].size() == N, "adjusted log-pdf: operand sizes differ");
+    ENode n; n.kind = N_LOGPDF; n.fn = dist; n.ch = {a, b};
+    if (dist != FADB_BERNOULLI) n.ch.push_back(c);
     return e->add(std::move(n));
 }
 

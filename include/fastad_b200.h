@@ -217,6 +217,12 @@ int fadb_expr_glue(fadb_expr*, int lhs, int rhs);
  *   fadb_expr_if_else    ad::if_else(cond, a, b), scalar condition           if_else.hpp:29-165
  *   fadb_expr_opeq       w += / -= / *= / /= expr (op = FADB_ADD..FADB_DIV)   eq.hpp:194-413
  * (ad::for_each is a chain of fadb_expr_glue, for_each.hpp:19-131.) */
+/* the other diagonal adjusted log-pdfs (reverse/stat/{cauchy,uniform,bernoulli}.hpp);
+ * operands are scalars or vectors of one length: cauchy(x, loc, scale), uniform(x, min, max),
+ * bernoulli(x, p) (c ignored).  Out-of-range parameters give -inf (bernoulli: see bernoulli.hpp:127-133)
+ * and no adjoint update. */
+enum { FADB_CAUCHY = 0, FADB_UNIFORM = 1, FADB_BERNOULLI = 2 };
+int fadb_expr_logpdf(fadb_expr*, int dist, int a, int b, int c);
 int fadb_expr_norm(fadb_expr*, int child);
 int fadb_expr_transpose(fadb_expr*, int child);
 int fadb_expr_if_else(fadb_expr*, int cond, int if_node, int else_node);

@@ -21,7 +21,7 @@
 namespace {
 
 enum Kind { K_VAR, K_CONST, K_UNARY, K_BINARY, K_POW, K_SUM, K_SUM_ITER, K_PROD,
-            K_PROD_ITER, K_DOT, K_NORMAL, K_EQ, K_GLUE, K_NORM, K_TRANSPOSE, K_IF_ELSE, K_OPEQ };
+            K_PROD_ITER, K_DOT, K_NORMAL, K_EQ, K_GLUE, K_NORM, K_TRANSPOSE, K_IF_ELSE, K_OPEQ, K_LOGPDF };
 
 /* A seed is either a scalar (broadcast) or an array, as in the reference where the
  * seed type is a template parameter (var_view.hpp:91-94). */
@@ -167,7 +167,7 @@ struct orc_graph {
         case K_UNARY: case K_POW: case K_DOT: case K_SUM_ITER: case K_PROD_ITER: case K_TRANSPOSE:
         case K_OPEQ:   /* OpEqNode's cache_ holds the previous lhs value + adjoint, eq.hpp:289-292 */
             out[0] = n.size(); out[1] = n.size(); break;
-        case K_SUM: case K_NORMAL: case K_NORM: out[0] = n.size(); out[1] = 0; break; /* sum.hpp:196-199 */
+        case K_SUM: case K_NORMAL: case K_NORM: case K_LOGPDF: out[0] = n.size(); out[1] = 0; break; /* sum.hpp:196-199 */
         case K_PROD: out[0] = n.size(); out[1] = nodes[n.ch[0]].size(); break; /* prod.hpp:236-239 */
         }
     }
@@ -234,7 +234,7 @@ struct orc_graph {
         size_t s[2];
         single_size(id, s);
         n.val = v; v += s[0];
-        if (n.kind == K_SUM || n.kind == K_NORMAL || n.kind == K_PROD || n.kind == K_NORM ||
+        if (n.kind == K_SUM || n.kind == K_NORMAL || n.kind == K_PROD || n.kind == K_NORM || n.kind == K_LOGPDF ||
             (n.kind == K_BINARY && is_comparison(n.op))) n.adj = nullptr;
         else { n.adj = a; a += n.size(); }
     }
@@ -382,6 +382,7 @@ struct orc_graph {
             return feval(n.ch[1]);
         }
         case K_NORMAL: return normal_feval(n);
+        case K_LOGPDF: return logpdf_feval(n);
         case K_NORM: {                                   /* norm.hpp:47-51 */
             const double* x = feval(n.ch[0]);
             const size_t M = nodes[n.ch[0]].size();
@@ -592,6 +593,7 @@ struct orc_graph {
             beval(n.ch[0], Seed{nullptr, 0.});
             return;
         case K_NORMAL: normal_beval(n, seed.at(0)); return;
+        case K_LOGPDF: logpdf_beval(n, seed.at(0)); return;
         case K_NORM: {                                    /* norm.hpp:53-57 */
             Node& e = nodes[n.ch[0]];
             n.tmp0.resize(e.size());
@@ -636,6 +638,127 @@ struct orc_graph {
             beval(n.ch[0], Seed{n.tmp0.data(), 0});
             return;
         }
+        }
+    }
+
+    /* ---- cauchy / uniform / bernoulli adjusted log-pdfs (reverse/stat/{cauchy,uniform,bernoulli}.hpp).
+     * Operands are scalars or vectors of one length; `at(p, k, i)` reads operand k at element i. */
+    static double at(const Node& o, size_t i) { return o.val[o.size() == 1 ? 0 : i]; }
+    bool logpdf_valid(const Node& n) const
+    {
+        const Node& A = nodes[n.ch[0]];
+        const Node& B = nodes[n.ch[1]];
+        size_t N = std::max(A.size(), B.size());
+        if (n.op != ORC_BERNOULLI) N = std::max(N, nodes[n.ch[2]].size());
+        for (size_t i = 0; i < N; ++i) {
+            if (n.op == ORC_CAUCHY) { if (!(at(nodes[n.ch[2]], i) > 0)) return false; }          /* cauchy.hpp:168-170, 309-311 */
+            else if (n.op == ORC_UNIFORM) {                                                       /* uniform.hpp:170-173 */
+                if (!(at(B, i) < at(A, i) && at(A, i) < at(nodes[n.ch[2]], i))) return false;
+            } else { if (!(0 < at(B, i) && at(B, i) < 1)) return false; }                         /* bernoulli.hpp:165-168 */
+        }
+        return true;
+    }
+    const double* logpdf_feval(Node& n)
+    {
+        feval(n.ch[0]); feval(n.ch[1]);
+        if (n.op != ORC_BERNOULLI) feval(n.ch[2]);
+        const Node& A = nodes[n.ch[0]];
+        const Node& B = nodes[n.ch[1]];
+        size_t N = std::max(A.size(), B.size());
+        if (n.op != ORC_BERNOULLI) N = std::max(N, nodes[n.ch[2]].size());
+        const double ninf = -std::numeric_limits<double>::infinity();
+        n.pos_def = logpdf_valid(n);
+        if (n.op == ORC_CAUCHY) {
+            const Node& G = nodes[n.ch[2]];
+            if (!n.pos_def) { n.val[0] = ninf; return n.val; }
+            if (N == 1) {                                                                         /* sss, cauchy.hpp:134-147 */
+                const double d = A.val[0] - B.val[0], g = G.val[0];
+                n.z_sq = g + (d * d) / g;
+                n.val[0] = -std::log(n.z_sq);
+            } else {                                                                              /* cauchy.hpp:216-217 etc. */
+                double acc = 0;
+                for (size_t i = 0; i < N; ++i) {
+                    const double d = at(A, i) - at(B, i), g = at(G, i);
+                    acc += std::log(g + (1. / g) * (d * d));
+                }
+                n.val[0] = -acc;
+            }
+        } else if (n.op == ORC_UNIFORM) {
+            const Node& MX = nodes[n.ch[2]];
+            if (!n.pos_def) { n.val[0] = ninf; return n.val; }
+            if (B.size() == 1 && MX.size() == 1) {
+                n.val[0] = -(double)N * std::log(MX.val[0] - B.val[0]);                          /* uniform.hpp:154, 240 */
+                if (N == 1) n.val[0] = -std::log(MX.val[0] - B.val[0]);
+            } else {
+                double acc = 0;
+                for (size_t i = 0; i < N; ++i) acc += std::log(at(MX, i) - at(B, i));             /* uniform.hpp:348, 441, 529 */
+                n.val[0] = -acc;
+            }
+        } else {                                                                                  /* bernoulli.hpp:119-141, 215-241 */
+            bool zero_one = true;
+            double x_sum = 0;
+            for (size_t i = 0; i < A.size(); ++i) { zero_one = zero_one && (A.val[i] == 0 || A.val[i] == 1); x_sum += A.val[i]; }
+            n.x_var = zero_one ? 1 : 0;
+            if (B.size() == 1) {
+                const double p = B.val[0];
+                if (!n.pos_def) {
+                    if (p <= 0) n.val[0] = (x_sum == 0 && zero_one) ? 0 : ninf;
+                    else n.val[0] = (x_sum == (double)A.size() && zero_one) ? 0 : ninf;
+                } else if (!zero_one) n.val[0] = ninf;
+                else n.val[0] = x_sum * std::log(p) + ((double)A.size() - x_sum) * std::log(1 - p);
+            } else {
+                double acc = 0;
+                for (size_t i = 0; i < N; ++i) {
+                    const double x = at(A, i), p = at(B, i);
+                    if (!(0 < p && p < 1)) acc += (p <= 0) ? (x == 0 ? 0 : ninf) : (x == 1 ? 0 : ninf);
+                    else acc += x == 0 ? std::log(1 - p) : x == 1 ? std::log(p) : ninf;
+                }
+                n.val[0] = acc;
+            }
+        }
+        return n.val;
+    }
+    void logpdf_beval(Node& n, double seed)
+    {
+        if (seed == 0 || !n.pos_def) return;
+        Node& A = nodes[n.ch[0]];
+        Node& B = nodes[n.ch[1]];
+        size_t N = std::max(A.size(), B.size());
+        if (n.op != ORC_BERNOULLI) N = std::max(N, nodes[n.ch[2]].size());
+        auto send = [&](int child, std::vector<double>& per_elem) {     /* scalar operands receive the sum */
+            Node& c = nodes[child];
+            if (c.size() == 1 && N > 1) { double a = 0; for (double v : per_elem) a += v; beval(child, Seed{nullptr, a}); }
+            else beval(child, Seed{per_elem.data(), 0});
+        };
+        std::vector<double> ga(N), gb(N), gc(N);
+        if (n.op == ORC_CAUCHY) {
+            Node& G = nodes[n.ch[2]];
+            if (N == 1) {                                                                         /* cauchy.hpp:149-165 */
+                const double d = A.val[0] - B.val[0], g = G.val[0];
+                const double x0_adj = 2. * d / (g * n.z_sq);
+                beval(n.ch[2], Seed{nullptr, seed * (1. / g * (x0_adj * d - 1))});
+                beval(n.ch[1], Seed{nullptr, seed * x0_adj});
+                beval(n.ch[0], Seed{nullptr, seed * -x0_adj});
+                return;
+            }
+            /* vector cases, cauchy.hpp:220-237, 290-306, 359-376, 429-445 (note: the reference
+             * multiplies by `seed` twice in dx0 and dgamma; restated as written) */
+            for (size_t i = 0; i < N; ++i) {
+                const double d = at(A, i) - at(B, i), g = at(G, i);
+                const double dx = (-2. * seed) * d / (g * g + d * d);
+                ga[i] = dx;
+                gb[i] = (-seed) * dx;
+                gc[i] = (-seed / g) * (dx * d + 1);
+            }
+            send(n.ch[2], gc); send(n.ch[1], gb); send(n.ch[0], ga);
+        } else if (n.op == ORC_UNIFORM) {                                                         /* uniform.hpp:157-163, 243-250, 336-344 */
+            Node& MX = nodes[n.ch[2]];
+            for (size_t i = 0; i < N; ++i) { const double a = seed / (at(MX, i) - at(B, i)); gc[i] = -a; gb[i] = a; }
+            send(n.ch[2], gc); send(n.ch[1], gb);
+        } else {                                                                                  /* bernoulli.hpp:143-149, 243-250 */
+            if (n.x_var == 0) return;
+            for (size_t i = 0; i < N; ++i) { const double x = at(A, i), p = at(B, i); gb[i] = x == 0 ? -seed / (1 - p) : seed / p; }
+            send(n.ch[1], gb);
         }
     }
 
@@ -887,6 +1010,14 @@ int orc_glue(orc_graph* g, int lhs, int rhs)
 {
     const Node& r = g->nodes[rhs];
     Node n; n.kind = K_GLUE; n.shape = r.shape; n.rows = r.rows; n.cols = r.cols; n.ch = {lhs, rhs};
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+int orc_logpdf(orc_graph* g, int dist, int a, int b, int c)
+{
+    Node n; n.kind = K_LOGPDF; n.op = dist;
+    n.ch = {a, b};
+    if (dist != ORC_BERNOULLI) n.ch.push_back(c);
     int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
 }
 

@@ -67,6 +67,10 @@ int orc_norm(orc_graph*, int child);                      /* NormNode, norm.hpp:
 int orc_transpose(orc_graph*, int child);                 /* TransposeNode, transpose.hpp:17-81 */
 int orc_if_else(orc_graph*, int cond, int a, int b);      /* IfElseNode, if_else.hpp:29-165 */
 int orc_opeq(orc_graph*, int op, int var, int child);     /* OpEqNode, eq.hpp:194-413 */
+/* other diagonal adjusted log-pdfs (reverse/stat): dist = ORC_CAUCHY (x, loc, scale; cauchy.hpp),
+ * ORC_UNIFORM (x, min, max; uniform.hpp), ORC_BERNOULLI (x, p, unused; bernoulli.hpp) */
+enum { ORC_CAUCHY = 0, ORC_UNIFORM = 1, ORC_BERNOULLI = 2 };
+int orc_logpdf(orc_graph*, int dist, int a, int b, int c);
 
 /* ad::bind: size query + allocate + post-order bind. out2 = {#val, #adj} as SizePack */
 void orc_bind(orc_graph*, int root, size_t out2[2]);

@@ -260,7 +260,68 @@ def opeq_chain(n):
     return build
 
 
+# ---- other diagonal log-pdfs ------------------------------------------------
+C_VX, C_VL, C_VS = np.array([0.5, -1.3, -3.2414999]), np.array([0.4, -2.30000001, -10.32]), np.array([0.51, 0.01, 3.4])
+
+
+def cauchy_case(kind, seed=1.0, n=None):
+    def build(e):   # cauchy_unittest.cpp:59-76 fixture values, or n random elements
+        if n is None:
+            xv, lv, sv = C_VX, C_VL, C_VS
+        else:
+            xv, lv, sv = _vec(n, -3, 3), _vec(n, -3, 3), _vec(n, 0.2, 3)
+        x = e.var(xv if kind[0] == "v" else 0.421)
+        l = e.var(lv if kind[1] == "v" else 0.341)
+        s_ = e.var(sv if kind[2] == "v" else 2.132)
+        return e.logpdf("cauchy", x, l, s_), [x, l, s_], seed
+    return build
+
+
+def uniform_case(kind, n=None, bad=False):
+    def build(e):   # uniform_unittest.cpp:62-76 fixture values
+        if n is None:
+            xv, lo, hi = np.array([0.5, -2.3, -3.2414999]), np.array([0.4, -2.30000001, -10.32]), np.array([0.51, 0.0, 3.4])
+        else:
+            xv = _vec(n, -1, 1); lo = xv - _vec(n, 0.1, 2); hi = xv + _vec(n, 0.1, 2)
+        if kind == "vss":
+            xv = np.array([0.5, -2.3, -3.2414999]) if n is None else _vec(n, -3, 0.5)
+        if bad:
+            xv = xv.copy(); xv[0] = -10000.0
+        x = e.var(xv if kind[0] == "v" else 0.45)
+        a = e.var(lo if kind[1] == "v" else -3.2415)
+        b = e.var(hi if kind[2] == "v" else 0.5231)
+        return e.logpdf("uniform", x, a, b), [x, a, b], 0.7
+    return build
+
+
+def bernoulli_case(kind, xs=(1.0, 0.0, 1.0), ps=(0.3, 0.42, 0.98), p_scalar=0.0001):
+    def build(e):   # bernoulli_unittest.cpp:48-57 fixture values
+        x = e.const(np.array(xs)) if kind[0] == "v" else e.const(np.array([xs[0]]))
+        p = e.var(np.array(ps)) if kind[1] == "v" else e.var(p_scalar)
+        return e.logpdf("bernoulli", x, p), [p], 1.3
+    return build
+
+
+def cauchy_in_model(n):
+    def build(e):   # log-posterior shape with an expression location: cauchy(y | a + b*x, exp(ls))
+        y, x = e.const(_vec(n, -2, 2)), e.const(_vec(n))
+        a, b, ls = e.var(0.1), e.var(0.7), e.var(-0.2)
+        loc = e.binary("add", a, e.binary("mul", b, x))
+        return e.binary("add", e.logpdf("cauchy", y, loc, e.unary("exp", ls)), e.logpdf("uniform", a, e.const(-5.0), e.const(5.0))), [a, b, ls], 1.0
+    return build
+
+
 CASES = {
+    "cauchy_sss": cauchy_case("sss"), "cauchy_vss": cauchy_case("vss"), "cauchy_vsv": cauchy_case("vsv"),
+    "cauchy_vvs": cauchy_case("vvs"), "cauchy_vvv": cauchy_case("vvv"),
+    "cauchy_vvv_big_seed": cauchy_case("vvv", seed=0.6, n=4099), "cauchy_vss_big": cauchy_case("vss", n=3001),
+    "uniform_sss": uniform_case("sss"), "uniform_vss": uniform_case("vss"), "uniform_vsv": uniform_case("vsv"),
+    "uniform_vvs": uniform_case("vvs"), "uniform_vvv": uniform_case("vvv"), "uniform_vvv_big": uniform_case("vvv", n=5003),
+    "uniform_out_of_range": uniform_case("vvv", bad=True),
+    "bernoulli_ss": bernoulli_case("ss"), "bernoulli_vs": bernoulli_case("vs"), "bernoulli_vv": bernoulli_case("vv"),
+    "bernoulli_p_out_of_range": bernoulli_case("vs", p_scalar=1.341), "bernoulli_x_not_binary": bernoulli_case("vv", xs=(2.0, 0.0, 1.0)),
+    "bernoulli_p_zero_all_x_zero": bernoulli_case("vs", xs=(0.0, 0.0, 0.0), p_scalar=0.0),
+    "cauchy_in_model": cauchy_in_model(2500),
     "norm_vec": norm_vec,
     "norm_mat_chain": norm_mat_chain(500),
     "transpose_quadratic": transpose_quadratic,

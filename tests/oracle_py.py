@@ -14,6 +14,7 @@ UNARY = dict(neg=0, sin=1, cos=2, tan=3, asin=4, acos=5, atan=6, exp=7, log=8, s
              sigmoid=11, sinh=12, cosh=13, tanh=14, mock2x=100)
 BINARY = dict(add=0, sub=1, mul=2, div=3, lt=4, le=5, gt=6, ge=7, eq=8, ne=9, land=10, lor=11, mockb=100)
 
+DIST = dict(cauchy=0, uniform=1, bernoulli=2)
 _dp = C.POINTER(C.c_double)
 _lib = None
 
@@ -37,7 +38,7 @@ def lib(fast=False):
         "orc_prod_iter": (i, [vp, i, C.POINTER(i)]), "orc_dot": (i, [vp, i, i]),
         "orc_normal": (i, [vp, i, i, i]), "orc_eq": (i, [vp, i, i]), "orc_glue": (i, [vp, i, i]),
         "orc_norm": (i, [vp, i]), "orc_transpose": (i, [vp, i]), "orc_if_else": (i, [vp, i, i, i]),
-        "orc_opeq": (i, [vp, i, i, i]),
+        "orc_opeq": (i, [vp, i, i, i]), "orc_logpdf": (i, [vp, i, i, i, i]),
         "orc_bind": (None, [vp, i, C.POINTER(sz)]),
         "orc_feval": (_dp, [vp, i]), "orc_beval": (None, [vp, i, d, vp]),
         "orc_size": (sz, [vp, i]), "orc_is_const": (i, [vp, i]),
@@ -153,6 +154,9 @@ class OracleExpr:
 
     def opeq(self, op, w, c):
         return self.L.orc_opeq(self.g, BINARY[op], w, c)
+
+    def logpdf(self, dist, a, b, c=-1):
+        return self.L.orc_logpdf(self.g, DIST[dist], a, b, c)
 
     # ---- driver ----
     def bind(self, root):

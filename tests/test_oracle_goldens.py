@@ -333,3 +333,46 @@ def test_transpose_quadratic_form_readme():
     e.bind(e.dot(e.dot(e.transpose(x), S), x))
     assert_double_eq(e.autodiff(np.ones((1, 1))), [4.46])
     assert_double_eq(e.adj(x), [5.6, 10.2])
+
+
+def test_other_logpdf_goldens():
+    # test/reverse/stat/cauchy_unittest.cpp:80-262 (values generated by ref/cauchy_ref.py there)
+    import exprs
+
+    def run(build):
+        e = O.OracleExpr()
+        root, vs, seed = build(e)
+        e.bind(root)
+        return e.autodiff(seed)[0], [e.adj(v).copy() for v in vs]
+    v, (xa, la, sa) = run(exprs.cauchy_case("sss"))
+    assert_double_eq([v], [-0.7584675254495730]); assert_double_eq(xa, [-0.0351507439654960])
+    assert_double_eq(la, [0.0351507439654960]); assert_double_eq(sa, [-0.4677241747104879])
+    v, (xa, la, sa) = run(exprs.cauchy_case("vss"))
+    assert_double_eq([v], [-4.0831775617990589])
+    assert_double_eq(xa, [-0.0695735121824751, 0.4534210702643782, 0.4122618701395337])
+    assert_double_eq(la, [-0.7961094282214367]); assert_double_eq(sa, [-0.3601996841981470])
+    v, (xa, la, sa) = run(exprs.cauchy_case("vvv"))
+    assert_double_eq([v], [-6.867595467569049816])
+    assert_double_eq(xa, [-0.740466493891151267, -1.999800000003999267, -0.229578571732138997])
+    assert_double_eq(la, -np.array(xa))
+    assert_double_eq(sa, [-1.815594805119381983, 99.980002000199945655, 0.183844689107000858])
+    v, _ = run(exprs.cauchy_case("vvs")); assert_double_eq([v], [-4.959070146586642025])
+    v, _ = run(exprs.cauchy_case("vsv")); assert_double_eq([v], [-6.9858076420069022])
+    # test/reverse/stat/uniform_unittest.cpp:80-230
+    v, (xa, lo, hi) = run(exprs.uniform_case("sss"))
+    assert_double_eq([v], [-1.3256416139079406])
+    assert_double_eq(lo, [0.7 / (0.5231 + 3.2415)]); assert_double_eq(hi, [-0.7 / (0.5231 + 3.2415)]); assert xa[0] == 0
+    for kind, want in (("vss", -3.9769248417238217), ("vsv", -4.3915297872269807), ("vvs", -1.3266062626903801),
+                       ("vvv", -1.2444888363909485)):
+        v, _ = run(exprs.uniform_case(kind))
+        assert_double_eq([v], [want], what="uniform " + kind)
+    v, (xa, lo, hi) = run(exprs.uniform_case("vvv", bad=True))
+    assert v == -np.inf and np.all(lo == 0) and np.all(hi == 0)
+    # test/reverse/stat/bernoulli_unittest.cpp:60-200
+    v, _ = run(exprs.bernoulli_case("vs")); assert_double_eq([v], [-18.42078074895269779176])
+    v, (pa,) = run(exprs.bernoulli_case("vs", p_scalar=1.341)); assert v == -np.inf and pa[0] == 0
+    v, (pa,) = run(exprs.bernoulli_case("vs", xs=(0.0, 0.0, 0.0), p_scalar=0.0)); assert v == 0 and pa[0] == 0
+    v, (pa,) = run(exprs.bernoulli_case("vv", xs=(2.0, 0.0, 1.0))); assert v == -np.inf and np.all(pa == 0)
+    v, (pa,) = run(exprs.bernoulli_case("vv"))
+    assert_double_eq([v], [np.log(0.3) + np.log(1 - 0.42) + np.log(0.98)])
+    assert_double_eq(pa, [1.3 / 0.3, -1.3 / (1 - 0.42), 1.3 / 0.98])
