@@ -646,6 +646,31 @@ private:
     S s_;
 };
 
+// Cauchy / Uniform / Bernoulli adjusted log-pdf nodes (reverse/stat/{cauchy,uniform,bernoulli}.hpp)
+template <int Dist, class A, class B, class C>
+struct LogPDFNode : ExprBase<LogPDFNode<Dist, A, B, C>> {
+    using value_t = double;
+    using shape_t = scl;
+    LogPDFNode(const A& a, const B& b, const C& c) : a_(a), b_(b), c_(c) {}
+    size_t rows() const { return 1; }
+    size_t cols() const { return 1; }
+    size_t size() const { return 1; }
+    int lower(detail::Lowering& L) const
+    {
+        int a = a_.lower(L);
+        int b = b_.lower(L);
+        int c = Dist == FADB_BERNOULLI ? -1 : c_.lower(L);
+        return detail::checked_id(fadb_expr_logpdf(L.e, Dist, a, b, c));
+    }
+    const A& first() const { return a_; }
+    const B& second() const { return b_; }
+    const C& third() const { return c_; }
+private:
+    A a_;
+    B b_;
+    C c_;
+};
+
 template <class VarViewType, class ExprType>
 struct EqNode : ExprBase<EqNode<VarViewType, ExprType>> {
     using value_t = double;
@@ -943,6 +968,35 @@ inline auto normal_adj_log_pdf(const X& x, const M& m, const S& s)
     m_t em = m;
     s_t es = s;
     return core::NormalAdjLogPDFNode<x_t, m_t, s_t>(ex, em, es);
+}
+
+// ---- ad::cauchy_adj_log_pdf / uniform_adj_log_pdf / bernoulli_adj_log_pdf ------
+#define FASTAD_B200_LOGPDF3(name, dist)                                                               \
+    template <class X, class P1, class P2,                                                            \
+              class = std::enable_if_t<util::is_convertible_to_ad_v<X> && util::is_convertible_to_ad_v<P1> && \
+                                       util::is_convertible_to_ad_v<P2> && util::any_ad_v<X, P1, P2>>> \
+    inline auto name(const X& x, const P1& p1, const P2& p2)                                          \
+    {                                                                                                 \
+        using x_t = util::convert_to_ad_t<X>;                                                         \
+        using a_t = util::convert_to_ad_t<P1>;                                                        \
+        using b_t = util::convert_to_ad_t<P2>;                                                        \
+        x_t ex = x;                                                                                   \
+        a_t ea = p1;                                                                                  \
+        b_t eb = p2;                                                                                  \
+        return core::LogPDFNode<dist, x_t, a_t, b_t>(ex, ea, eb);                                     \
+    }
+FASTAD_B200_LOGPDF3(cauchy_adj_log_pdf, FADB_CAUCHY)     // cauchy.hpp: (x, loc, scale)
+FASTAD_B200_LOGPDF3(uniform_adj_log_pdf, FADB_UNIFORM)   // uniform.hpp: (x, min, max)
+#undef FASTAD_B200_LOGPDF3
+template <class X, class P, class = std::enable_if_t<util::is_convertible_to_ad_v<X> && util::is_convertible_to_ad_v<P> &&
+                                                     util::any_ad_v<X, P>>>
+inline auto bernoulli_adj_log_pdf(const X& x, const P& p)   // bernoulli.hpp: (x, p)
+{
+    using x_t = util::convert_to_ad_t<X>;
+    using p_t = util::convert_to_ad_t<P>;
+    x_t ex = x;
+    p_t ep = p;
+    return core::LogPDFNode<FADB_BERNOULLI, x_t, p_t, core::Constant<double, scl>>(ex, ep, core::Constant<double, scl>(0.0));
 }
 
 // ---- SURVEY.md 8f "next" rows ---------------------------------------------------------------

@@ -378,6 +378,29 @@ static void next_rows()
         CHECK_DOUBLE_EQ(v.get_adj()(4), 4.0 * x0);
         CHECK_DOUBLE_EQ(s.get_adj(), 2.1 * 3.1 + 0.3 * 2.3 + 1.0 * 1.3 + 0.5 * 0. + 4.0 * 5.1);
     }
+    // ---- other diagonal log-pdfs (cauchy_unittest.cpp:80-262, uniform_unittest.cpp:80-104, bernoulli_unittest.cpp:148-153)
+    {
+        Var<double, vec> x(3), loc(3), sc(3);
+        x.get() = {0.5, -1.3, -3.2414999};
+        loc.get() = {0.4, -2.30000001, -10.32};
+        sc.get() = {0.51, 0.01, 3.4};
+        auto b = ad::bind(ad::cauchy_adj_log_pdf(x, loc, sc));
+        CHECK_DOUBLE_EQ(ad::autodiff(b), -6.867595467569049816);
+        CHECK_DOUBLE_EQ(x.get_adj()(1), -1.999800000003999267);
+        CHECK_DOUBLE_EQ(loc.get_adj()(0), 0.740466493891151267);
+        CHECK_DOUBLE_EQ(sc.get_adj()(1), 99.980002000199945655);
+        Var<double> ux(0.45), lo(-3.2415), hi(0.5231);
+        auto u = ad::bind(ad::uniform_adj_log_pdf(ux, lo, hi));
+        CHECK_DOUBLE_EQ(ad::autodiff(u), -1.3256416139079406);
+        CHECK_DOUBLE_EQ(lo.get_adj(), 1. / (0.5231 + 3.2415));
+        ux.get() = -100;                                    // out of range: -inf, adjoints untouched
+        CHECK(ad::autodiff(u) == -std::numeric_limits<double>::infinity());
+        CHECK_DOUBLE_EQ(hi.get_adj(), -1. / (0.5231 + 3.2415));
+        Var<double> p(0.0001);
+        auto be = ad::bind(ad::bernoulli_adj_log_pdf(ad::constant(std::vector<double>{1, 0, 1}), p));
+        CHECK_DOUBLE_EQ(ad::autodiff(be), -18.42078074895269779176);
+        CHECK_DOUBLE_EQ(p.get_adj(), (2 - 3 * 0.0001) / (0.0001 * (1 - 0.0001)));
+    }
     // ---- ad::for_each (for_each.hpp:19-131): evaluate all, value of the last, seed to the last only
     {
         std::vector<Var<double>> xs, ws(3);
