@@ -55,6 +55,8 @@ SIGNATURES = {
     "fadb_sigma_check": (_i, [_sz, _vp, _vp]),
     "fadb_normal_lpdf_partial": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp, _vp]),
     "fadb_normal_lpdf_finish": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_logpdf": (_i, [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_logpdf_async": (_i, [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp]),
     "fadb_linreg_partial": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
     "fadb_linreg_finish": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_linreg_nll": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
@@ -198,6 +200,17 @@ def normal_lpdf(x, mu, sigma, x_adj=None, mu_adj=None, sigma_adj=None, seed=1.0,
     v = C.c_double()
     check(lib().fadb_normal_lpdf(shape, n, _ptr(x), _ptr(mu), _ptr(sigma), _ptr(x_adj), _ptr(mu_adj),
                                  _ptr(sigma_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+def logpdf(dist, x, b, c=None, x_adj=None, b_adj=None, c_adj=None, seed=1.0, flags=0):
+    """cauchy(x, loc, scale) / uniform(x, min, max) / bernoulli(x, p); 1-element tensors are scalars."""
+    _chk_f64(x, b, c, x_adj, b_adj, c_adj)
+    n = x.numel()
+    shape = (1 if (b.numel() == n and n > 1) else 0) | (2 if (c is not None and c.numel() == n and n > 1) else 0)
+    v = C.c_double()
+    check(lib().fadb_logpdf(dict(cauchy=0, uniform=1, bernoulli=2)[dist], shape, n, _ptr(x), _ptr(b), _ptr(c),
+                            _ptr(x_adj), _ptr(b_adj), _ptr(c_adj), seed, flags, C.byref(v)))
     return v.value
 
 

@@ -38,6 +38,8 @@ extern "C" int fadb_normal_lpdf_partial(int, size_t, const double*, const double
 extern "C" int fadb_normal_lpdf_finish(int, size_t, const double*, const double*, const double*,
                                        const double*, double*, double*, double*, double, unsigned, double*);
 extern "C" int fadb_linreg_partial(size_t, size_t, const double*, const double*, const double*, double*);
+extern "C" int fadb_logpdf_async(int, int, size_t, const double*, const double*, const double*, double*, double*, double*,
+                                 double, unsigned, double*);
 extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, double*, double*, double,
                                   unsigned, double*);
 
@@ -558,7 +560,7 @@ struct Stage {
     double* d_sig = nullptr;       // device copy of a constant scalar sigma
     bool big = false;              // scalar stage too large for the on-chip interpreter
     double* d_scratch = nullptr;
-    int fast = 0;                  // 0 interpreter, 1 sum_unary, 2 normal leaves, 3 linreg
+    int fast = 0;                  // 0 interpreter, 1 sum_unary, 2 normal leaves, 3 linreg, 4 cauchy/uniform/bernoulli leaves
     // fast-path operands
     int f_op = 0; const double* f_x = nullptr; double* f_xadj = nullptr;
     const double *f_mu = nullptr, *f_sig = nullptr; double *f_muadj = nullptr, *f_sigadj = nullptr;
@@ -888,6 +890,21 @@ struct fadb_expr {
             st.f_x = st.leaves[lf].val; st.f_xadj = st.leaves[lf].adj_mode ? st.leaves[lf].adj : nullptr;
             return;
         }
+        if (st.term > T_NORMAL && plan.size() == 1) {
+            int lx, lb, lc = -1;
+            const bool three = st.term != T_BERNOULLI;
+            if (leaf_only(st, st.nx, &lx) && (!st.leaves[lx].scalar || st.N == 1) && leaf_only(st, st.nm, &lb) &&
+                (!three || leaf_only(st, st.ns, &lc)) && st.prog.size() == (three ? 3u : 2u)) {
+                auto adj = [&](int l) { return (l >= 0 && st.leaves[l].adj_mode) ? st.leaves[l].adj : nullptr; };
+                st.fast = 4;
+                st.f_op = st.term - T_CAUCHY;
+                st.f_shape = ((!st.leaves[lb].scalar && st.N > 1) ? 1 : 0) | ((three && !st.leaves[lc].scalar && st.N > 1) ? 2 : 0);
+                st.f_x = st.leaves[lx].val; st.f_xadj = adj(lx);
+                st.f_mu = st.leaves[lb].val; st.f_muadj = adj(lb);
+                st.f_sig = three ? st.leaves[lc].val : nullptr; st.f_sigadj = three ? adj(lc) : nullptr;
+            }
+            return;
+        }
         if (st.term == T_NORMAL && st.N >= 1) {
             int lx, lm, ls;
             const bool x_leaf = leaf_only(st, st.nx, &lx) && (!st.leaves[lx].scalar || st.N == 1);
@@ -1161,6 +1178,13 @@ struct fadb_expr {
             if (rc) return rc;
             // the finish kernel leaves the value in the context scalar slot 0
             FADB_CUDA(cudaMemcpyAsync(st.mval, c.scalars + 0, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+            return FADB_OK;
+        }
+        if (st.fast == 4) {
+            int rc = fadb_logpdf_async(st.f_op, st.f_shape, st.N, st.f_x, st.f_mu, st.f_sig, st.f_xadj, st.f_muadj,
+                                       st.f_sigadj, seed, flags, st.d_red + 4);
+            if (rc) return rc;
+            FADB_CUDA(cudaMemcpyAsync(st.mval, st.d_red + 4, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
             return FADB_OK;
         }
         if (st.fast == 3) {

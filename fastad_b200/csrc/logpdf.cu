@@ -1,0 +1,251 @@
+// logpdf.cu — fused value + adjoint kernels for the other diagonal adjusted log-pdfs with leaf
+// operands: CauchyAdjLogPDFNode (reverse/stat/cauchy.hpp:102-451),
+// UniformAdjLogPDFNode (uniform.hpp:101-536), BernoulliAdjLogPDFNode (bernoulli.hpp:94-280).
+// Same skeleton as normal.cu: the reference makes one pass per quantity; here one streaming pass
+// produces the value sums and every adjoint (256-bit accesses, deterministic reduction).  When
+// validity is a property of ALL elements (uniform: min < x < max everywhere; bernoulli; a vector
+// cauchy scale) a read-only pre-pass decides it first, so that "out of range => no adjoint update"
+// (e.g. cauchy.hpp:151, uniform.hpp:159, bernoulli.hpp:145) holds exactly; FADB_TRUST_SIGMA skips it.
+#include "common.cuh"
+#include "functors.cuh"
+
+namespace fadb {
+
+struct LpArgs {
+    size_t n;
+    const double* x; const double* b; const double* c;     // c unused for bernoulli
+    double* x_adj; double* b_adj; double* c_adj;
+    double seed;
+    int overwrite;
+    const double* invalid_in;
+};
+
+// per-element forward term, validity and adjoints; formulas in the order the reference writes them
+template <int DIST>
+struct Lp;
+
+template <>
+struct Lp<FADB_CAUCHY> {       // x, loc, scale
+    static constexpr bool has_c = true, x_has_adj = true;
+    __device__ __forceinline__ static bool valid(double, double, double g) { return g > 0; }
+    __device__ __forceinline__ static double term(double x, double x0, double g, bool single)
+    {
+        const double d = x - x0;
+        return single ? -log_guarded(g + (d * d) / g) : -log_guarded(g + (1. / g) * (d * d));   // cauchy.hpp:144-146, 216-217
+    }
+    __device__ __forceinline__ static void adj(double x, double x0, double g, double sd, bool single, double& gx, double& gb, double& gc)
+    {
+        const double d = x - x0;
+        if (single) {                                                   // cauchy.hpp:149-165
+            const double inner = g + (d * d) / g;
+            const double x0_adj = 2. * d / (g * inner);
+            gc = sd * (1. / g * (x0_adj * d - 1));
+            gb = sd * x0_adj;
+            gx = sd * -x0_adj;
+        } else {                                                        // cauchy.hpp:220-237 as written (seed twice)
+            const double dx = (-2. * sd) * d / (g * g + d * d);
+            gx = dx;
+            gb = (-sd) * dx;
+            gc = (-sd / g) * (dx * d + 1);
+        }
+    }
+};
+template <>
+struct Lp<FADB_UNIFORM> {      // x, min, max
+    static constexpr bool has_c = true, x_has_adj = false;
+    __device__ __forceinline__ static bool valid(double x, double lo, double hi) { return lo < x && x < hi; }
+    __device__ __forceinline__ static double term(double, double lo, double hi, bool) { return -log_guarded(hi - lo); }
+    __device__ __forceinline__ static void adj(double, double lo, double hi, double sd, bool, double& gx, double& gb, double& gc)
+    {
+        const double a = sd / (hi - lo);                                // uniform.hpp:157-163
+        gx = 0.0; gb = a; gc = -a;
+    }
+};
+template <>
+struct Lp<FADB_BERNOULLI> {    // x, p
+    static constexpr bool has_c = false, x_has_adj = false;
+    __device__ __forceinline__ static bool valid(double x, double p, double) { return 0 < p && p < 1 && (x == 0 || x == 1); }
+    __device__ __forceinline__ static double term(double x, double p, double, bool)
+    {                                                                   // bernoulli.hpp:119-141
+        if (!(0 < p && p < 1)) return (p <= 0) ? (x == 0 ? 0.0 : -INFINITY) : (x == 1 ? 0.0 : -INFINITY);
+        return x == 0 ? log_guarded(1 - p) : x == 1 ? log_guarded(p) : -INFINITY;
+    }
+    __device__ __forceinline__ static void adj(double x, double p, double, double sd, bool, double& gx, double& gb, double& gc)
+    {
+        gx = 0.0; gc = 0.0;
+        gb = x == 0 ? -sd / (1 - p) : sd / p;                          // bernoulli.hpp:143-149
+    }
+};
+
+// read-only validity pre-pass: #elements that are out of range
+template <int DIST, bool B_VEC, bool C_VEC>
+__global__ void __launch_bounds__(512)
+lp_check_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out_count)
+{
+    __shared__ double smem[32];
+    double acc[1] = {0.0};
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const double bs = B_VEC ? 0.0 : __ldg(a.b), cs = (C_VEC || !Lp<DIST>::has_c) ? 0.0 : __ldg(a.c);
+    for (size_t i = tid; i < a.n; i += nth) {
+        const double x = __ldg(a.x + i), b = B_VEC ? __ldg(a.b + i) : bs, c = C_VEC ? __ldg(a.c + i) : cs;
+        acc[0] += Lp<DIST>::valid(x, b, c) ? 0.0 : 1.0;
+    }
+    block_sum<1>(acc, smem);
+    grid_finish<1>(acc, smem, partials, ticket, [&](double (&tot)[1]) { out_count[0] = tot[0]; });
+}
+
+__device__ __forceinline__ void lp_rmw4(double* p, const double (&g)[4], int overwrite)
+{
+    double4_t v;
+    if (overwrite) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.v[k] = g[k];
+    } else {
+        v = ld256(p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.v[k] += g[k];
+    }
+    st256(p, v);
+}
+
+// channels: 0 value sum, 1 scalar-b adjoint sum, 2 scalar-c adjoint sum, 3 #invalid
+template <int DIST, bool B_VEC, bool C_VEC>
+__global__ void __launch_bounds__(256)
+lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] value, invalid, -, - */)
+{
+    __shared__ double smem[32 * 4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const bool single = a.n == 1;
+    const double bs = B_VEC ? 0.0 : __ldg(a.b), cs = (C_VEC || !Lp<DIST>::has_c) ? 0.0 : __ldg(a.c);
+    bool valid_all = a.invalid_in ? (__ldcg(a.invalid_in) == 0.0) : true;
+    if (DIST == FADB_CAUCHY && !C_VEC) valid_all = cs > 0;    // a scalar scale: every thread sees it (cauchy.hpp:168-170)
+    const bool back = valid_all && a.seed != 0.0;
+    const bool wx = back && Lp<DIST>::x_has_adj && a.x_adj, wb = back && a.b_adj, wc = back && Lp<DIST>::has_c && a.c_adj;
+
+    const bool vec = aligned32(a.x) && (!B_VEC || aligned32(a.b)) && (!C_VEC || aligned32(a.c)) &&
+                     (!a.x_adj || aligned32(a.x_adj)) && (!B_VEC || !a.b_adj || aligned32(a.b_adj)) &&
+                     (!C_VEC || !a.c_adj || aligned32(a.c_adj));
+    const size_t n4 = vec ? a.n / 4 : 0;
+    for (size_t q = tid; q < n4; q += nth) {
+        const size_t i = 4 * q;
+        const double4_t xv = ldg256_stream(a.x + i);
+        double4_t bv, cv;
+        if (B_VEC) bv = ldg256_stream(a.b + i);
+        if (C_VEC) cv = ldg256_stream(a.c + i);
+        double gx[4], gb[4], gc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double b = B_VEC ? bv.v[k] : bs, c = C_VEC ? cv.v[k] : cs;
+            const bool ok = Lp<DIST>::valid(xv.v[k], b, c);
+            if (!ok) acc[3] += 1.0;
+            acc[0] += (ok || DIST == FADB_BERNOULLI) ? Lp<DIST>::term(xv.v[k], b, c, single) : 0.0;
+            Lp<DIST>::adj(xv.v[k], b, c, a.seed, single, gx[k], gb[k], gc[k]);
+            if (!B_VEC) acc[1] += gb[k];
+            if (!C_VEC) acc[2] += gc[k];
+        }
+        if (wx) lp_rmw4(a.x_adj + i, gx, a.overwrite);
+        if (wb && B_VEC) lp_rmw4(a.b_adj + i, gb, a.overwrite);
+        if (wc && C_VEC) lp_rmw4(a.c_adj + i, gc, a.overwrite);
+    }
+    for (size_t i = n4 * 4 + tid; i < a.n; i += nth) {
+        const double x = a.x[i], b = B_VEC ? a.b[i] : bs, c = C_VEC ? a.c[i] : cs;
+        const bool ok = Lp<DIST>::valid(x, b, c);
+        if (!ok) acc[3] += 1.0;
+        acc[0] += (ok || DIST == FADB_BERNOULLI) ? Lp<DIST>::term(x, b, c, single) : 0.0;
+        double gx, gb, gc;
+        Lp<DIST>::adj(x, b, c, a.seed, single, gx, gb, gc);
+        if (!B_VEC) acc[1] += gb;
+        if (!C_VEC) acc[2] += gc;
+        if (wx) a.x_adj[i] = a.overwrite ? gx : a.x_adj[i] + gx;
+        if (wb && B_VEC) a.b_adj[i] = a.overwrite ? gb : a.b_adj[i] + gb;
+        if (wc && C_VEC) a.c_adj[i] = a.overwrite ? gc : a.c_adj[i] + gc;
+    }
+    block_sum<4>(acc, smem);
+    grid_finish<4>(acc, smem, partials, ticket, [&](double (&tot)[4]) {
+        const bool invalid = tot[3] != 0.0 || !valid_all;
+        out[1] = invalid ? 1.0 : 0.0;
+        out[0] = (DIST == FADB_BERNOULLI) ? tot[0] : (invalid ? -INFINITY : tot[0]);
+        // adjoints of scalar operands (summed over the elements), only when everything is in range
+        if (!invalid && a.seed != 0.0) {
+            if (!B_VEC && a.b_adj) a.b_adj[0] = a.overwrite ? tot[1] : a.b_adj[0] + tot[1];
+            if (!C_VEC && Lp<DIST>::has_c && a.c_adj) a.c_adj[0] = a.overwrite ? tot[2] : a.c_adj[0] + tot[2];
+        }
+    });
+}
+
+template <int DIST, bool B_VEC, bool C_VEC>
+static int run_logpdf(Context& c, LpArgs a, unsigned flags, bool any_adj, double* out)
+{
+    // validity visible to every thread only for a cauchy with a scalar scale
+    const bool global_check = !(DIST == FADB_CAUCHY && !C_VEC);
+    double* invalid = out + 2;
+    a.invalid_in = nullptr;
+    if (any_adj && a.seed != 0.0) {
+        if (global_check && !(flags & FADB_TRUST_SIGMA)) {
+            const int threads = 512;
+            const int grid = resident_grid(c, lp_check_kernel<DIST, B_VEC, C_VEC>, threads, 0, a.n, threads);
+            lp_check_kernel<DIST, B_VEC, C_VEC><<<grid, threads, 0, c.stream>>>(a, c.partials, c.tickets + 9, invalid);
+            c.launches++;
+            a.invalid_in = invalid;
+        }
+    }
+    const int threads = 256;
+    const int grid = resident_grid(c, lp_kernel<DIST, B_VEC, C_VEC>, threads, 0, (a.n + 3) / 4, threads);
+    lp_kernel<DIST, B_VEC, C_VEC><<<grid, threads, 0, c.stream>>>(a, c.partials, c.tickets + 10, out);
+    c.launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+}  // namespace fadb
+
+using namespace fadb;
+
+// value left in dev_out[0] (device, 4 doubles of scratch); asynchronous
+extern "C" int fadb_logpdf_async(int dist, int shape_code, size_t n, const double* x, const double* b,
+                                 const double* c, double* x_adj, double* b_adj, double* c_adj, double seed,
+                                 unsigned flags, double* dev_out4)
+{
+    FADB_REQUIRE(dist >= FADB_CAUCHY && dist <= FADB_BERNOULLI, "fadb_logpdf: unknown distribution");
+    FADB_REQUIRE(shape_code >= 0 && shape_code <= 3 && dev_out4, "fadb_logpdf: bad shape_code / null output");
+    FADB_REQUIRE(n == 0 || (x && b && (dist == FADB_BERNOULLI || c)), "fadb_logpdf: null operand");
+    Context* ctx;
+    int rc = current_context(&ctx);
+    if (rc) return rc;
+    LpArgs a{n, x, b, c, x_adj, b_adj, c_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, nullptr};
+    const bool any_adj = x_adj || b_adj || c_adj;
+    const bool bv = shape_code & 1, cv = shape_code & 2;
+#define FADB_LP(D)                                                                              \
+    do {                                                                                        \
+        if (bv && cv) return run_logpdf<D, true, true>(*ctx, a, flags, any_adj, dev_out4);     \
+        if (bv) return run_logpdf<D, true, false>(*ctx, a, flags, any_adj, dev_out4);          \
+        if (cv) return run_logpdf<D, false, true>(*ctx, a, flags, any_adj, dev_out4);          \
+        return run_logpdf<D, false, false>(*ctx, a, flags, any_adj, dev_out4);                 \
+    } while (0)
+    if (dist == FADB_CAUCHY) FADB_LP(FADB_CAUCHY);
+    if (dist == FADB_UNIFORM) FADB_LP(FADB_UNIFORM);
+    if (bv) return run_logpdf<FADB_BERNOULLI, true, false>(*ctx, a, flags, any_adj, dev_out4);
+    return run_logpdf<FADB_BERNOULLI, false, false>(*ctx, a, flags, any_adj, dev_out4);
+#undef FADB_LP
+}
+
+extern "C" int fadb_logpdf(int dist, int shape_code, size_t n, const double* x, const double* b,
+                           const double* c, double* x_adj, double* b_adj, double* c_adj, double seed,
+                           unsigned flags, double* host_value)
+{
+    Context* ctx;
+    int rc = current_context(&ctx);
+    if (rc) return rc;
+    double* out = ctx->scalars + 24;
+    rc = fadb_logpdf_async(dist, shape_code, n, x, b, c, x_adj, b_adj, c_adj, seed, flags, out);
+    if (rc) return rc;
+    if (host_value) {
+        FADB_CUDA(cudaMemcpyAsync(ctx->host_scalars + 4, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        FADB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *host_value = ctx->host_scalars[4];
+    }
+    return FADB_OK;
+}

@@ -145,6 +145,21 @@ int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_pa
                             double* x_adj, double* mu_adj, double* sigma_adj, double seed,
                             unsigned flags, double* host_value);
 
+/* ------------------------------------------------------------------ other diagonal log-pdfs
+ * autodiff of ad::cauchy_adj_log_pdf(x, loc, scale) / ad::uniform_adj_log_pdf(x, min, max) /
+ * ad::bernoulli_adj_log_pdf(x, p) with leaf operands (reverse/stat/cauchy.hpp:102-451,
+ * uniform.hpp:101-536, bernoulli.hpp:94-280).  dist = FADB_CAUCHY | FADB_UNIFORM | FADB_BERNOULLI
+ * (declared with the expression builder below); shape_code bit0: b is a vector, bit1: c is a
+ * vector; an operand is constant iff its *_adj pointer is NULL; out-of-range parameters give
+ * -inf (bernoulli: bernoulli.hpp:127-133) and leave every adjoint untouched.  fadb_logpdf_async
+ * leaves {value, #invalid, scratch, scratch} in 4 device doubles instead of synchronising. */
+int fadb_logpdf(int dist, int shape_code, size_t n, const double* x, const double* b, const double* c,
+                double* x_adj, double* b_adj, double* c_adj, double seed, unsigned flags,
+                double* host_value);
+int fadb_logpdf_async(int dist, int shape_code, size_t n, const double* x, const double* b,
+                      const double* c, double* x_adj, double* b_adj, double* c_adj, double seed,
+                      unsigned flags, double* dev_out4);
+
 /* ------------------------------------------------------------------ K5: regression
  * autodiff of normal_adj_log_pdf(y, dot(X, w), sigma) (dot.hpp:54-129 feeding
  * normal.hpp:304-372): X rows x cols column-major constant, y constant, w variable vector,

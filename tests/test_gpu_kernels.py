@@ -319,6 +319,62 @@ def test_black_scholes_full_size_put_call_parity(fb):
     assert np.max(np.abs(host(out[3]) - host(out[6]))) == 0.0   # vega identical by construction
 
 
+# ------------------------------------------------------------------ other diagonal log-pdfs
+def _lp_case(fb, dist, n, bvec, cvec, bad=False, seed=0.8, flags=0):
+    rng = np.random.default_rng(n + 7 * bvec + 13 * cvec)
+    x = rng.uniform(-1, 1, n)
+    if dist == "cauchy":
+        b = rng.uniform(-1, 1, n if bvec else 1); c = rng.uniform(0.2, 2, n if cvec else 1)
+        if bad: c[len(c) // 2] = -0.5
+    elif dist == "uniform":
+        b = -1.5 - rng.uniform(0, 1, n if bvec else 1); c = 1.5 + rng.uniform(0, 1, n if cvec else 1)
+        if bad: x[n // 3] = 7.0
+    else:
+        x = rng.integers(0, 2, n).astype(float); b = rng.uniform(0.05, 0.95, n if bvec else 1); c = None
+        if bad: x[n // 3] = 2.0
+    e = O.OracleExpr()
+    ex = e.var(x) if dist == "cauchy" else e.const(x)
+    eb = e.var(b if bvec else float(b[0]))
+    ec = None if c is None else e.var(c if cvec else float(c[0]))
+    root = e.logpdf(dist, ex, eb, -1 if ec is None else ec)
+    e.bind(root)
+    ov = e.autodiff(seed)[0]
+    gx, gb = dev(x), dev(b)
+    gc = None if c is None else dev(c)
+    xa = zeros(n) if dist == "cauchy" else None
+    ba = zeros(len(b)); ca = None if c is None else zeros(len(c))
+    v = fb.logpdf(dist, gx, gb, gc, xa, ba, ca, seed=seed, flags=flags)
+    outs = [(host(ba), e.adj(eb))]
+    if ca is not None: outs.append((host(ca), e.adj(ec)))
+    if xa is not None: outs.append((host(xa), e.adj(ex)))
+    return v, ov, outs
+
+
+@pytest.mark.parametrize("dist", ["cauchy", "uniform", "bernoulli"])
+@pytest.mark.parametrize("bvec,cvec", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("n", [3, 4097, (1 << 18) + 1])
+def test_logpdf_kernels_vs_oracle(fb, dist, bvec, cvec, n):
+    if dist == "bernoulli" and cvec:
+        pytest.skip("bernoulli has two operands")
+    v, ov, outs = _lp_case(fb, dist, n, bvec, cvec)
+    assert rel(v, ov) <= REL_REDUCE
+    for g, o in outs:
+        if len(o) == n and n > 1:
+            np.testing.assert_allclose(g, o, rtol=4e-16, atol=0)      # arithmetic only: <= 1 ulp
+        else:
+            np.testing.assert_allclose(g, o, rtol=1e-11, atol=1e-12 * max(1.0, np.abs(o).max()))
+
+
+@pytest.mark.parametrize("dist,bvec,cvec", [("cauchy", 1, 1), ("cauchy", 0, 0), ("uniform", 1, 1), ("uniform", 0, 0),
+                                             ("bernoulli", 1, 0), ("bernoulli", 0, 0)])
+def test_logpdf_kernels_out_of_range(fb, dist, bvec, cvec):
+    # cauchy.hpp:151, uniform.hpp:159, bernoulli.hpp:145: -inf and no adjoint update
+    v, ov, outs = _lp_case(fb, dist, 2049, bvec, cvec, bad=True)
+    assert v == -math.inf and ov == -math.inf
+    for g, o in outs:
+        assert np.all(g == 0) and np.all(o == 0)
+
+
 # ------------------------------------------------------------------ K5 regression
 @pytest.mark.parametrize("rows,cols", [(5, 2), (1000, 64), (4097, 64), (777, 7), (300, 130)])
 def test_linreg_vs_oracle(fb, rows, cols):
