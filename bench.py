@@ -330,6 +330,32 @@ def run_ours(args):
         add("normal_vss_xconst_2^26", 8 * n3, t, steps2, n3, "elements", sharded=True)
         del x, mu, sg, xa, ma, sa
 
+    if "logpdf" in wl:
+        # the other diagonal log-pdfs, all-vector operands, N = 2^25, exact semantics
+        # (validity pre-pass included) and FADB_TRUST_SIGMA (single fused pass)
+        n4 = 1 << 25
+        rng = np.random.default_rng(synth.SEED + 77)
+        x = dev(rng.uniform(-1, 1, n4))
+        loc, sc = dev(rng.uniform(-1, 1, n4)), dev(rng.uniform(0.2, 2, n4))
+        lo, hi = dev(-1.5 - rng.uniform(0, 1, n4)), dev(1.5 + rng.uniform(0, 1, n4))
+        xb, pb = dev(rng.integers(0, 2, n4).astype(np.float64)), dev(rng.uniform(0.05, 0.95, n4))
+        a1, a2, a3, out4 = zeros(n4), zeros(n4), zeros(n4), zeros(4)
+
+        def lp_step(dist, X, B, Cc, XA, BA, CA, flags):
+            def step(i):
+                F.check(L.fadb_logpdf_async(dist, 1 | (2 if Cc is not None else 0), n4, P(X), P(B), P(Cc), P(XA), P(BA), P(CA),
+                                            1.0, flags, P(out4)))
+            return step
+        for nm, dist, ops_, bytes_per, pre in (("cauchy_vvv", 0, (x, loc, sc, a1, a2, a3), 72, 24),
+                                               ("uniform_vvv", 1, (x, lo, hi, None, a2, a3), 56, 24),
+                                               ("bernoulli_vv", 2, (xb, pb, None, None, a2, None), 32, 16)):
+            t = timed_loop(lp_step(dist, *ops_, 0), steps2, 3, world)
+            add(f"{nm}_2^25", bytes_per * n4, t, steps2, n4, "elements",
+                {"note": f"exact semantics: +{pre} B/elem validity pre-pass"})
+            t = timed_loop(lp_step(dist, *ops_, F.TRUST_SIGMA), steps2, 3, world)
+            add(f"{nm}_2^25_trusted", bytes_per * n4, t, steps2, n4, "elements")
+        del x, loc, sc, lo, hi, xb, pb, a1, a2, a3
+
     if "linreg" in wl:
         # C4: regression, X 2^20 x 64 column-major; 520 B/row
         rows, cols = 1 << 20, 64
@@ -486,7 +512,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline only, small CPU sample")
-    ap.add_argument("--workloads", default="sum,normal,linreg,mlp3,expr",
+    ap.add_argument("--workloads", default="sum,normal,logpdf,linreg,mlp3,expr",
                     help="secondary workloads to time besides the headline (comma list)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()

@@ -68,12 +68,13 @@ struct Lp<FADB_BERNOULLI> {    // x, p
     __device__ __forceinline__ static double term(double x, double p, double, bool)
     {                                                                   // bernoulli.hpp:119-141
         if (!(0 < p && p < 1)) return (p <= 0) ? (x == 0 ? 0.0 : -INFINITY) : (x == 1 ? 0.0 : -INFINITY);
-        return x == 0 ? log_guarded(1 - p) : x == 1 ? log_guarded(p) : -INFINITY;
+        if (x != 0 && x != 1) return -INFINITY;
+        return log_guarded(x == 0 ? 1 - p : p);            // one log per element, branch-free select
     }
     __device__ __forceinline__ static void adj(double x, double p, double, double sd, bool, double& gx, double& gb, double& gc)
     {
         gx = 0.0; gc = 0.0;
-        gb = x == 0 ? -sd / (1 - p) : sd / p;                          // bernoulli.hpp:143-149
+        gb = (x == 0 ? -sd : sd) / (x == 0 ? 1 - p : p);               // bernoulli.hpp:143-149, one division
     }
 };
 
