@@ -33,6 +33,20 @@ BS_BYTES = 104            # algorithmic bytes per option: 5 in + 8 out doubles (
 L2_BYTES = 126 * (1 << 20)
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, from the
+    committed `ncu --set full` summary (profiles/); None when no capture is on file."""
+    p = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(p):
+        return None
+    tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    import csv
+    for row in csv.reader(open(p)):
+        if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[2]) * scale.get(row[1], 1.0)
+    return tot or None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -489,7 +503,10 @@ def run_ours(args):
                        "l2": f"rotating {nsets} resident buffer sets ({nsets * BS_BYTES * n >> 20} MiB) > 126 MiB L2",
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak_gbs, "traffic": ncu_traffic("r1_ncu_full_bs.csv"),
+                         "traffic_note": "ncu dram bytes inside the launch; most of the 64 B/option of stores is still in "
+                                         "the 126 MB L2 when the 26 us kernel ends",
+                         "peak_source": peak_src,
                          "kernel": "bs_kernel_fast_pf<false>", "algorithmic_bytes_per_launch": BS_BYTES * n},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "options/s", "h2d_bytes_per_step": 40 * n,

@@ -260,7 +260,10 @@ extern "C" int fadb_black_scholes_host(size_t n, const double* hS, const double*
     if (rc) return rc;
 
     constexpr int NBUF = 3;
-    const size_t chunk = n < (size_t)(1u << 18) ? n : (size_t)(1u << 18);
+    static int chunk_log2 = -1;
+    if (chunk_log2 < 0) { const char* e = getenv("FADB_BS_HOST_CHUNK_LOG2"); chunk_log2 = e ? atoi(e) : 18; }
+    const size_t cmax = (size_t)1 << chunk_log2;
+    const size_t chunk = n < cmax ? n : cmax;
     static thread_local double* dbuf[NBUF] = {nullptr, nullptr, nullptr};
     static thread_local size_t dcap = 0;
     static thread_local cudaStream_t st[NBUF];
