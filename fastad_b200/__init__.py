@@ -55,6 +55,8 @@ SIGNATURES = {
     "fadb_sigma_check": (_i, [_sz, _vp, _vp]),
     "fadb_normal_lpdf_partial": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp, _vp]),
     "fadb_normal_lpdf_finish": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_normal_dense": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_normal_dense_async": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _i, _vp]),
     "fadb_logpdf": (_i, [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_logpdf_async": (_i, [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp]),
     "fadb_linreg_partial": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
@@ -200,6 +202,15 @@ def normal_lpdf(x, mu, sigma, x_adj=None, mu_adj=None, sigma_adj=None, seed=1.0,
     v = C.c_double()
     check(lib().fadb_normal_lpdf(shape, n, _ptr(x), _ptr(mu), _ptr(sigma), _ptr(x_adj), _ptr(mu_adj),
                                  _ptr(sigma_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+def normal_dense(x, mu, Sigma, x_adj=None, mu_adj=None, Sigma_adj=None, seed=1.0, flags=0):
+    """Sigma: (n, n) torch tensor holding the column-major matrix (symmetric: layout-agnostic)."""
+    _chk_f64(x, mu, Sigma, x_adj, mu_adj, Sigma_adj)
+    v = C.c_double()
+    check(lib().fadb_normal_dense(x.numel(), _ptr(x), _ptr(mu), 1 if mu.numel() > 1 else 0, _ptr(Sigma), _ptr(x_adj),
+                                  _ptr(mu_adj), _ptr(Sigma_adj), seed, flags, C.byref(v)))
     return v.value
 
 

@@ -145,6 +145,20 @@ int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_pa
                             double* x_adj, double* mu_adj, double* sigma_adj, double seed,
                             unsigned flags, double* host_value);
 
+/* ------------------------------------------------------------------ K7: dense-covariance normal
+ * autodiff of ad::normal_adj_log_pdf(x, mu, Sigma) with Sigma an n x n matrix (vsm / vvm,
+ * reverse/stat/normal.hpp:581-773): blocked Cholesky of the LOWER triangle of Sigma (Eigen::LLT<Lower>),
+ * log-det, explicit inverse, z = inv (x - mu); Sigma_adj += -0.5 seed (inv - z z^T), mu_adj += seed z
+ * (its sum if mu is a scalar: mu_vec = 0), x_adj += -seed z.  Not positive definite => -inf and no
+ * adjoint update (normal.hpp:627-629, 644).  `factor` = 0 reuses the factorisation of the previous
+ * call on this device (constant Sigma, normal.hpp:605-607). */
+int fadb_normal_dense(size_t n, const double* x, const double* mu, int mu_vec, const double* Sigma,
+                      double* x_adj, double* mu_adj, double* Sigma_adj, double seed, unsigned flags,
+                      double* host_value);
+int fadb_normal_dense_async(size_t n, const double* x, const double* mu, int mu_vec, const double* Sigma,
+                            double* x_adj, double* mu_adj, double* Sigma_adj, double seed, unsigned flags,
+                            int factor, double* dev_value);
+
 /* ------------------------------------------------------------------ other diagonal log-pdfs
  * autodiff of ad::cauchy_adj_log_pdf(x, loc, scale) / ad::uniform_adj_log_pdf(x, min, max) /
  * ad::bernoulli_adj_log_pdf(x, p) with leaf operands (reverse/stat/cauchy.hpp:102-451,

@@ -273,6 +273,7 @@ struct orc_graph {
         const Node& sg = nodes[n.ch[2]];
         const Node& mu = nodes[n.ch[1]];
         bool xc = x.kind == K_CONST, sc = sg.kind == K_CONST;
+        if (is_dense(sg, x)) return;
         if (sc) normal_update_cache(n);
         if (x.shape != ORC_SCL && mu.shape == ORC_SCL && sg.shape == ORC_SCL && xc) {
             size_t N = x.size();
@@ -416,11 +417,97 @@ struct orc_graph {
         return nullptr;
     }
 
+    /* ---- dense covariance: vsm / vvm, normal.hpp:581-773.  Eigen::LLT<Lower> reads the lower
+     * triangle only; log_det_ = log(det L); inv_ = llt.solve(I) (normal.hpp:657-665, 756-763). */
+    static bool is_dense(const Node& sn, const Node& xn) { return sn.shape == ORC_MAT && sn.rows == sn.cols && sn.rows == xn.size() && sn.rows > 1; }
+    void dense_update_cache(Node& n)
+    {
+        const Node& sn = nodes[n.ch[2]];
+        const size_t d = sn.rows;
+        std::vector<double> L(d * d, 0.);
+        n.pos_def = true;
+        for (size_t j = 0; j < d && n.pos_def; ++j) {                 /* column Cholesky */
+            double s = sn.val[j + j * d];
+            for (size_t k = 0; k < j; ++k) s -= L[j + k * d] * L[j + k * d];
+            if (!(s > 0)) { n.pos_def = false; break; }
+            const double ljj = std::sqrt(s);
+            L[j + j * d] = ljj;
+            for (size_t i = j + 1; i < d; ++i) {
+                double t = sn.val[i + j * d];
+                for (size_t k = 0; k < j; ++k) t -= L[i + k * d] * L[j + k * d];
+                L[i + j * d] = t / ljj;
+            }
+        }
+        if (!n.pos_def) return;
+        double det = 1;
+        for (size_t j = 0; j < d; ++j) det *= L[j + j * d];
+        n.log_sigma = std::log(det);
+        /* inv = (L L^T)^{-1}: solve L Y = I, then L^T X = Y, column by column */
+        n.extra.assign(d * d + d, 0.);
+        std::vector<double> y(d);
+        for (size_t c = 0; c < d; ++c) {
+            for (size_t i = 0; i < d; ++i) {
+                double t = (i == c) ? 1. : 0.;
+                for (size_t k = 0; k < i; ++k) t -= L[i + k * d] * y[k];
+                y[i] = t / L[i + i * d];
+            }
+            for (size_t ii = d; ii-- > 0;) {
+                double t = y[ii];
+                for (size_t k = ii + 1; k < d; ++k) t -= L[k + ii * d] * n.extra[k + c * d];
+                n.extra[ii + c * d] = t / L[ii + ii * d];
+            }
+        }
+    }
+    const double* dense_feval(Node& n)
+    {
+        Node& xn = nodes[n.ch[0]];
+        Node& mn = nodes[n.ch[1]];
+        Node& sn = nodes[n.ch[2]];
+        const double* x = feval(n.ch[0]);
+        const double* m = feval(n.ch[1]);
+        feval(n.ch[2]);
+        if (sn.kind != K_CONST || n.extra.empty()) dense_update_cache(n);
+        const size_t d = xn.size();
+        if (!n.pos_def) { n.val[0] = -std::numeric_limits<double>::infinity(); return n.val; }
+        const bool mv = mn.size() > 1;
+        double* z = n.extra.data() + d * d;
+        double sq = 0;
+        for (size_t i = 0; i < d; ++i) {
+            double acc = 0;
+            for (size_t k = 0; k < d; ++k) acc += n.extra[i + k * d] * (x[k] - m[mv ? k : 0]);
+            z[i] = acc;
+        }
+        for (size_t i = 0; i < d; ++i) sq += (x[i] - m[mv ? i : 0]) * z[i];
+        n.val[0] = -0.5 * sq - n.log_sigma;
+        return n.val;
+    }
+    void dense_beval(Node& n, double seed)
+    {
+        if (seed == 0 || !n.pos_def) return;                          /* normal.hpp:644, 742 */
+        Node& xn = nodes[n.ch[0]];
+        Node& mn = nodes[n.ch[1]];
+        Node& sn = nodes[n.ch[2]];
+        const size_t d = xn.size();
+        const double* z = n.extra.data() + d * d;
+        if (sn.kind != K_CONST) {
+            n.tmp1.resize(d * d);
+            for (size_t j = 0; j < d; ++j)
+                for (size_t i = 0; i < d; ++i) n.tmp1[i + j * d] = (-0.5 * seed) * (n.extra[i + j * d] - z[i] * z[j]);
+            beval(n.ch[2], Seed{n.tmp1.data(), 0});
+        }
+        n.tmp0.resize(d);
+        if (mn.size() > 1) { for (size_t i = 0; i < d; ++i) n.tmp0[i] = seed * z[i]; beval(n.ch[1], Seed{n.tmp0.data(), 0}); }
+        else { double acc = 0; for (size_t i = 0; i < d; ++i) acc += z[i]; beval(n.ch[1], Seed{nullptr, seed * acc}); }
+        for (size_t i = 0; i < d; ++i) n.tmp0[i] = (-seed) * z[i];
+        beval(n.ch[0], Seed{n.tmp0.data(), 0});
+    }
+
     const double* normal_feval(Node& n)
     {
         Node& xn = nodes[n.ch[0]];
         Node& mn = nodes[n.ch[1]];
         Node& sn = nodes[n.ch[2]];
+        if (is_dense(sn, xn)) return dense_feval(n);
         const double* x = feval(n.ch[0]);
         const double* m = feval(n.ch[1]);
         const double* s = feval(n.ch[2]);
@@ -767,6 +854,7 @@ struct orc_graph {
         Node& xn = nodes[n.ch[0]];
         Node& mn = nodes[n.ch[1]];
         Node& sn = nodes[n.ch[2]];
+        if (is_dense(sn, xn)) { dense_beval(n, seed); return; }
         const bool xc = xn.kind == K_CONST, sc = sn.kind == K_CONST;
         const size_t N = xn.size();
         const double* x = xn.val;

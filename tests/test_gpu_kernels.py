@@ -319,6 +319,74 @@ def test_black_scholes_full_size_put_call_parity(fb):
     assert np.max(np.abs(host(out[3]) - host(out[6]))) == 0.0   # vega identical by construction
 
 
+# ------------------------------------------------------------------ K7 dense-covariance normal
+def _dense_cov(n, rng):
+    # benchmark/normal_benchmark.cpp:15-33 builds Sigma = L L^T, L lower with diagonal 10 and U(-1,1)
+    # below.  The reference forms log(det L) as the log of a PRODUCT (normal.hpp:661), which overflows
+    # to +inf beyond n ~ 300 with that diagonal (10^n); the kernel sums log L_ii instead.  To compare
+    # against the oracle (which restates the product) large cases use a diagonal of 1.2.
+    diag, scale = (10.0, 1.0) if n <= 200 else (1.2, 1.0 / np.sqrt(n))
+    Lo = np.tril(rng.uniform(-1, 1, (n, n)), -1) * scale + diag * np.eye(n)
+    return Lo @ Lo.T
+
+
+def test_dense_normal_reference_goldens(fb):
+    import torch
+    # normal_unittest.cpp:298-395: only the lower triangle of Sigma is set (and read)
+    Sig = np.array([[1.0, 0.0, 0.0], [0.3, 2.0, 0.0], [0.2, -0.3, 3.0]])
+    gS = torch.from_numpy(np.ascontiguousarray(Sig.T)).cuda()         # column-major image
+    xa, ma, Sa = zeros(3), zeros(1), zeros(9)
+    v = fb.normal_dense(dev(kats.N_VX), dev([kats.N_MU]), gS, xa, ma, Sa)
+    assert_double_eq([v], [-8.8105250497069019])
+    assert_double_eq(host(xa), [-3.7624909485879803, 1.6010137581462704, -0.0890658942795076])
+    assert_double_eq(host(ma), [2.2505430847212176])
+    sa = host(Sa).reshape(3, 3, order="F")
+    np.testing.assert_allclose([sa[0, 0], sa[1, 0], sa[2, 0], sa[1, 1], sa[2, 1], sa[2, 2]],
+                               [6.5432306187049774, -2.9250063314004424, 0.2119067294266190, 1.0137007310866775,
+                                -0.1038829443345370, -0.1689156028253514], rtol=1e-14, atol=1e-15)
+    xa, ma, Sa = zeros(3), zeros(3), zeros(9)
+    v = fb.normal_dense(dev(kats.N_VX), dev(kats.N_VMU), gS, xa, ma, Sa)
+    assert_double_eq([v], [-7.3649692930088602])
+    assert_double_eq(host(xa), [-3.4158218682114407, 0.4279507603186097, -0.5628167994207096])
+    assert_double_eq(host(ma), -host(xa))
+    # not positive definite (normal_unittest.cpp:304-310): -inf, adjoints untouched
+    v = fb.normal_dense(dev(kats.N_VX), dev(kats.N_VMU), zeros(9).reshape(3, 3), xa, ma, Sa)
+    assert v == -math.inf
+    assert_double_eq(host(ma), -host(xa))
+
+
+@pytest.mark.parametrize("n,mu_vec", [(7, 1), (32, 0), (33, 1), (100, 1), (257, 0), (1000, 1)])
+def test_dense_normal_vs_oracle(fb, n, mu_vec):
+    import torch
+    rng = np.random.default_rng(n)
+    Sig = _dense_cov(n, rng)
+    x, mu = rng.uniform(-1, 1, n), (rng.uniform(-1, 1, n) if mu_vec else np.array([0.3]))
+    e = O.OracleExpr()
+    ex, em, eS = e.var(x), e.var(mu if mu_vec else float(mu[0])), e.var(Sig)
+    e.bind(e.normal(ex, em, eS))
+    ov = e.autodiff(0.9)[0]
+    xa, ma, Sa = zeros(n), zeros(len(mu)), zeros(n * n)
+    v = fb.normal_dense(dev(x), dev(mu), torch.from_numpy(np.ascontiguousarray(Sig.T)).cuda(), xa, ma, Sa, seed=0.9)
+    assert rel(v, ov) <= 1e-11
+    np.testing.assert_allclose(host(xa), e.adj(ex), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(host(ma), e.adj(em), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(host(Sa), e.adj(eS), rtol=1e-8, atol=1e-12 * np.abs(e.adj(eS)).max())
+
+
+def test_dense_normal_logdet_does_not_overflow(fb):
+    # the reference's own benchmark covariance at n = 1000: log(det L) = log(10^1000) = +inf there
+    import torch
+    n = 1000
+    rng = np.random.default_rng(1)
+    Lo = np.tril(rng.uniform(-1, 1, (n, n)), -1) + 10 * np.eye(n)
+    Sig = Lo @ Lo.T
+    x, mu = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    v = fb.normal_dense(dev(x), dev(mu), torch.from_numpy(np.ascontiguousarray(Sig.T)).cuda(), zeros(n), zeros(n), zeros(n * n))
+    z = np.linalg.solve(Sig, x - mu)
+    want = -0.5 * (x - mu) @ z - np.log(np.diag(np.linalg.cholesky(Sig))).sum()
+    assert rel(v, want) <= 1e-11
+
+
 # ------------------------------------------------------------------ other diagonal log-pdfs
 def _lp_case(fb, dist, n, bvec, cvec, bad=False, seed=0.8, flags=0):
     rng = np.random.default_rng(n + 7 * bvec + 13 * cvec)

@@ -376,3 +376,33 @@ def test_other_logpdf_goldens():
     v, (pa,) = run(exprs.bernoulli_case("vv"))
     assert_double_eq([v], [np.log(0.3) + np.log(1 - 0.42) + np.log(0.98)])
     assert_double_eq(pa, [1.3 / 0.3, -1.3 / (1 - 0.42), 1.3 / 0.98])
+
+
+def test_dense_covariance_normal_goldens():
+    # test/reverse/stat/normal_unittest.cpp:298-395 (vsm / vvm); only the LOWER triangle of Sigma is
+    # set in the fixture (:94-102) and read by Eigen::LLT<Lower>
+    Sig = np.array([[1.0, 0.0, 0.0], [0.3, 2.0, 0.0], [0.2, -0.3, 3.0]])
+    e = O.OracleExpr()
+    x, mu, S = e.var(kats.N_VX), e.var(kats.N_MU), e.var(Sig)
+    e.bind(e.normal(x, mu, S))
+    assert_double_eq(e.autodiff(), [-8.8105250497069019])
+    assert_double_eq(e.adj(x), [-3.7624909485879803, 1.6010137581462704, -0.0890658942795076])
+    assert_double_eq(e.adj(mu), [2.2505430847212176])
+    sa = e.adj(S).reshape(3, 3, order="F")
+    assert_double_eq([sa[0, 0], sa[1, 0], sa[1, 1], sa[2, 1], sa[2, 2]],
+                     [6.5432306187049774, -2.9250063314004424, 1.0137007310866775, -0.1038829443345370, -0.1689156028253514])
+    assert abs(sa[2, 0] - 0.2119067294266190) <= 1e-15
+    e = O.OracleExpr()
+    x, mu, S = e.var(kats.N_VX), e.var(kats.N_VMU), e.var(Sig)
+    e.bind(e.normal(x, mu, S))
+    assert_double_eq(e.autodiff(), [-7.3649692930088602])
+    assert_double_eq(e.adj(x), [-3.4158218682114407, 0.4279507603186097, -0.5628167994207096])
+    assert_double_eq(e.adj(mu), -e.adj(x))
+    sa = e.adj(S).reshape(3, 3, order="F")
+    assert_double_eq([sa[0, 0], sa[1, 0], sa[2, 0], sa[0, 1], sa[1, 1], sa[2, 1]],
+                     [5.2989810672774862, -0.6440082274123684, 1.0055928845283644, -0.6440082274123684,
+                      -0.1763508691715067, -0.1530140218890801])
+    e = O.OracleExpr()
+    x, mu, S = e.var(kats.N_VX), e.var(kats.N_VMU), e.var(np.zeros((3, 3)))
+    e.bind(e.normal(x, mu, S))
+    assert e.autodiff()[0] == -np.inf and np.all(e.adj(x) == 0)       # normal_unittest.cpp:304-310
