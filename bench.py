@@ -370,6 +370,30 @@ def run_ours(args):
             add(f"{nm}_2^25_trusted", bytes_per * n4, t, steps2, n4, "elements")
         del x, loc, sc, lo, hi, xb, pb, a1, a2, a3
 
+    if "dense" in wl:
+        # SURVEY.md 8f row 3 / BASELINE.md section 1: BM_normal_adj_log_pdf (vvm, dense Sigma), the only shape the
+        # reference publishes timings for (benchmark/ref/normal_benchmark_res.py:4-15, ns per autodiff, unknown CPU)
+        published_ns = {1000: 2720733, 2000: 16687945, 4000: 104822861}
+        for nd in (1000, 2000, 4000):
+            rng = np.random.default_rng(nd)
+            Lo = np.tril(rng.uniform(-1, 1, (nd, nd)), -1) + 10 * np.eye(nd)     # make_cov, normal_benchmark.cpp:15-33
+            Sg = torch.from_numpy(Lo @ Lo.T).cuda()
+            xd, md = dev(rng.uniform(-1, 1, nd)), dev(rng.uniform(-1, 1, nd))
+            xa, ma, Sa, dv = zeros(nd), zeros(nd), zeros(nd * nd), zeros(1)
+
+            def dn_step(i):
+                F.check(L.fadb_normal_dense_async(nd, P(xd), P(md), 1, P(Sg), P(xa), P(ma), P(Sa), 1.0, 0, 1, P(dv)))
+            sd = max(3, min(steps2, 10))
+            t = timed_loop(dn_step, sd, 2, world)
+            flops = nd ** 3 * (1 / 3 + 1 / 3 + 1 / 3)          # potrf + trtri + lauum (lower halves)
+            workloads[f"normal_dense_vvm_n{nd}"] = {
+                "ms_per_step": t / sd, "evals_per_s": world * sd / (t * 1e-3),
+                "fp64_gflops": flops / (t / sd * 1e-3) / 1e9,
+                "reference_published_ns": published_ns[nd],
+                "speedup_vs_published": published_ns[nd] * 1e-6 / (t / sd),
+                "note": "published number: unknown CPU, unstated units (Google-Benchmark default ns), reference README has no hardware"}
+            del Sg, Sa
+
     if "linreg" in wl:
         # C4: regression, X 2^20 x 64 column-major; 520 B/row
         rows, cols = 1 << 20, 64
@@ -529,7 +553,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline only, small CPU sample")
-    ap.add_argument("--workloads", default="sum,normal,logpdf,linreg,mlp3,expr",
+    ap.add_argument("--workloads", default="sum,normal,logpdf,dense,linreg,mlp3,expr",
                     help="secondary workloads to time besides the headline (comma list)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()

@@ -38,6 +38,8 @@ extern "C" int fadb_normal_lpdf_partial(int, size_t, const double*, const double
 extern "C" int fadb_normal_lpdf_finish(int, size_t, const double*, const double*, const double*,
                                        const double*, double*, double*, double*, double, unsigned, double*);
 extern "C" int fadb_linreg_partial(size_t, size_t, const double*, const double*, const double*, double*);
+extern "C" int fadb_normal_dense_async(size_t, const double*, const double*, int, const double*, double*, double*, double*,
+                                       double, unsigned, int, double*);
 extern "C" int fadb_logpdf_async(int, int, size_t, const double*, const double*, const double*, double*, double*, double*,
                                  double, unsigned, double*);
 extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, double*, double*, double,
@@ -533,7 +535,7 @@ struct ENode {
 struct OperandRef { const double* val = nullptr; double* adj = nullptr; int adj_mode = 0; int node = -1; int stage = -1; };
 
 struct Stage {
-    int type = 0;                  // 0 = MAP (interpreter), 1 = DOT, 2 = TRANSPOSE
+    int type = 0;                  // 0 = MAP (interpreter), 1 = DOT, 2 = TRANSPOSE, 3 = dense-covariance normal
     size_t N = 1;
     std::vector<Ins> prog;
     std::vector<LeafDesc> leaves;
@@ -550,7 +552,8 @@ struct Stage {
     size_t out_size = 1;
     // DOT
     int m = 0, k = 0, p = 0;
-    OperandRef L, R;
+    OperandRef L, R, S3;           // S3: Sigma of a dense-covariance normal (L = x, R = mu)
+    bool sigma_const = false, factored = false;
     // device state
     double* mval = nullptr;        // materialised output value [out_size]
     double* madj = nullptr;        // materialised output adjoint [out_size] (inner stages)
@@ -773,6 +776,17 @@ struct fadb_expr {
             st->sig_vec = n.ch.size() > 2 && nodes[n.ch[2]].size() > 1;
             // Cauchy with a scalar scale is the only case whose validity every thread can see
             st->needs_check = !(st->term == T_CAUCHY && !st->sig_vec);
+        } else if (n.kind == N_NORMAL && nodes[n.ch[2]].shape == FADB_MAT && nodes[n.ch[2]].rows == nodes[n.ch[2]].cols &&
+                   nodes[n.ch[2]].rows == nodes[n.ch[0]].size() && nodes[n.ch[2]].rows > 1) {
+            // vsm / vvm (normal.hpp:581-773): x, mu, Sigma are handed to K7 as whole operands
+            st->type = 3;
+            st->m = (int)nodes[n.ch[0]].size();
+            st->k = nodes[n.ch[1]].size() > 1 ? 1 : 0;          // mu is a vector
+            st->out_size = 1;
+            st->L = operand(n.ch[0]); if (!err.empty()) return -1;
+            st->R = operand(n.ch[1]); if (!err.empty()) return -1;
+            st->S3 = operand(n.ch[2]); if (!err.empty()) return -1;
+            st->sigma_const = nodes[n.ch[2]].kind == N_CONST_V;
         } else if (n.kind == N_NORMAL) {
             size_t N = 1;
             for (int c : n.ch) N = std::max(N, nodes[c].size());
@@ -944,6 +958,7 @@ struct fadb_expr {
         o << "stages=" << plan.size() << " cache={" << cache_vals << "," << cache_adjs << "}\n";
         for (size_t k = 0; k < plan.size(); ++k) {
             const Stage& st = *plan[k];
+            if (st.type == 3) { o << "stage " << k << ": dense normal n=" << st.m << (st.k ? " (vvm)" : " (vsm)") << "\n"; continue; }
             if (st.type == 2) { o << "stage " << k << ": transpose " << st.m << "x" << st.k << "\n"; continue; }
             if (st.type == 1) { o << "stage " << k << ": dot " << st.m << "x" << st.k << " * " << st.k << "x" << st.p << "\n"; continue; }
             o << "stage " << k << ": map N=" << st.N << " term=" << tn[st.term] << " ins=" << st.prog.size()
@@ -993,7 +1008,8 @@ struct fadb_expr {
             Stage& st = *sp;
             if (st.type != 0) {
                 if (st.L.stage >= 0) { st.L.val = plan[st.L.stage]->mval; st.L.adj = plan[st.L.stage]->madj; }
-                if (st.type == 1 && st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
+                if ((st.type == 1 || st.type == 3) && st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
+                if (st.type == 3 && st.S3.stage >= 0) { st.S3.val = plan[st.S3.stage]->mval; st.S3.adj = plan[st.S3.stage]->madj; }
                 continue;
             }
             for (size_t l = 0; l < st.leaves.size(); ++l)
@@ -1048,7 +1064,8 @@ struct fadb_expr {
             Stage& st = *sp;
             if (st.type != 0) {
                 if (st.L.stage < 0) { st.L.val = nodes[st.L.node].val; st.L.adj = nodes[st.L.node].adj; }
-                if (st.type == 1 && st.R.stage < 0) { st.R.val = nodes[st.R.node].val; st.R.adj = nodes[st.R.node].adj; }
+                if ((st.type == 1 || st.type == 3) && st.R.stage < 0) { st.R.val = nodes[st.R.node].val; st.R.adj = nodes[st.R.node].adj; }
+                if (st.type == 3 && st.S3.stage < 0) { st.S3.val = nodes[st.S3.node].val; st.S3.adj = nodes[st.S3.node].adj; st.factored = false; }
                 continue;
             }
             for (size_t l = 0; l < st.leaves.size(); ++l)
@@ -1116,6 +1133,22 @@ struct fadb_expr {
     int run_dot(Context& c, Stage& st, int mode, const double* seed_vec, double seed)
     {
         const int threads = 128;
+        if (st.type == 3) {
+            // forward-only evaluations zero the seed (no adjoint is touched, normal.hpp:644); an inner
+            // stage reads its scalar seed back from its boundary buffer
+            double sd = (mode & M_B) ? seed : 0.0;
+            if (mode == M_B && !seed_vec) {
+                FADB_CUDA(cudaMemcpyAsync(&sd, st.madj, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+                FADB_CUDA(cudaStreamSynchronize(c.stream));
+            }
+            const bool refactor = !(st.sigma_const && st.factored) && !(mode == M_B);
+            auto adjp = [](const OperandRef& r) { return r.adj_mode ? r.adj : nullptr; };
+            int rc = fadb_normal_dense_async(st.m, st.L.val, st.R.val, st.k, st.S3.val, adjp(st.L), adjp(st.R), adjp(st.S3), sd,
+                                             0, refactor ? 1 : 0, st.mval);
+            if (rc) return rc;
+            st.factored = true;
+            return FADB_OK;
+        }
         if (st.type == 2) {
             const int n = st.m * st.k, blocks = (n + threads - 1) / threads;
             if (n == 0) return FADB_OK;
@@ -1435,7 +1468,8 @@ int fadb_expr_normal(fadb_expr* e, int x, int mu, int sigma)
 {
     EXPR_REQUIRE(e, e && e->ok(x) && e->ok(mu) && e->ok(sigma), "fadb_expr_normal: bad arguments");
     const size_t nx = e->nodes[x].size(), nm = e->nodes[mu].size(), ns = e->nodes[sigma].size();
-    EXPR_REQUIRE(e, (nm == 1 || nm == nx) && (ns == 1 || ns == nx), "normal_adj_log_pdf: operand sizes differ");
+    const bool dense = e->nodes[sigma].shape == FADB_MAT && e->nodes[sigma].rows == nx && e->nodes[sigma].cols == nx && nx > 1;
+    EXPR_REQUIRE(e, (nm == 1 || nm == nx) && (ns == 1 || ns == nx || dense), "normal_adj_log_pdf: operand sizes differ");
     ENode n; n.kind = N_NORMAL; n.ch = {x, mu, sigma};
     return e->add(std::move(n));
 }

@@ -401,6 +401,21 @@ static void next_rows()
         CHECK_DOUBLE_EQ(ad::autodiff(be), -18.42078074895269779176);
         CHECK_DOUBLE_EQ(p.get_adj(), (2 - 3 * 0.0001) / (0.0001 * (1 - 0.0001)));
     }
+    // ---- dense-covariance normal, vvm (normal_unittest.cpp:340-395); Sigma's lower triangle only
+    {
+        Var<double, vec> x(3), mu(3);
+        Var<double, mat> Sig(3, 3);
+        x.get() = {3.1, -2.3, 1.3};
+        mu.get() = {-0.3, -2.3, -1.2};
+        Sig.get() = {1.0, 0.3, 0.2, 0.0, 2.0, -0.3, 0.0, 0.0, 3.0};      // column-major, upper left at zero
+        auto b = ad::bind(ad::normal_adj_log_pdf(x, mu, Sig));
+        CHECK_DOUBLE_EQ(ad::autodiff(b), -7.3649692930088602);
+        CHECK_DOUBLE_EQ(x.get_adj()(0), -3.4158218682114407);
+        CHECK_DOUBLE_EQ(mu.get_adj()(1), -0.4279507603186097);
+        CHECK_DOUBLE_EQ(Sig.get_adj(0, 0), 5.2989810672774862);
+        CHECK_DOUBLE_EQ(Sig.get_adj(2, 1), -0.1530140218890801);
+        CHECK_DOUBLE_EQ(Sig.get_adj(1, 2), -0.1530140218890801);
+    }
     // ---- ad::for_each (for_each.hpp:19-131): evaluate all, value of the last, seed to the last only
     {
         std::vector<Var<double>> xs, ws(3);

@@ -311,7 +311,39 @@ def cauchy_in_model(n):
     return build
 
 
+# ---- dense-covariance normal -------------------------------------------------
+SIG3 = np.array([[1.0, 0.0, 0.0], [0.3, 2.0, 0.0], [0.2, -0.3, 3.0]])    # normal_unittest.cpp:94-102 (lower only)
+
+
+def dense_normal(mu_vec, n=None, const_sigma=False):
+    def build(e):
+        if n is None:
+            xv, mv, Sig = kats.N_VX, (kats.N_VMU if mu_vec else kats.N_MU), SIG3
+        else:
+            Lo = np.tril(_vec(n * n, -1, 1).reshape(n, n), -1) / np.sqrt(n) + 1.2 * np.eye(n)
+            Sig = Lo @ Lo.T
+            xv, mv = _vec(n, -1, 1), (_vec(n, -1, 1) if mu_vec else 0.3)
+        x, mu = e.var(xv), e.var(mv)
+        S = e.const(Sig) if const_sigma else e.var(Sig)
+        return e.normal(x, mu, S), [x, mu] + ([] if const_sigma else [S]), 1.0
+    return build
+
+
+def dense_normal_in_model(n):
+    def build(e):   # multivariate normal with an expression mean plus a prior: N(y | a + b*t, Sigma) + N(a | 0, 10)
+        Lo = np.tril(_vec(n * n, -1, 1).reshape(n, n), -1) / np.sqrt(n) + 1.5 * np.eye(n)
+        y, t = e.const(_vec(n, -1, 1)), e.const(_vec(n))
+        a, b = e.var(0.2), e.var(-0.4)
+        S = e.var(Lo @ Lo.T)
+        mean = e.binary("add", a, e.binary("mul", b, t))
+        return e.binary("add", e.normal(y, mean, S), e.normal(a, e.const(0.0), e.const(10.0))), [a, b, S], 1.0
+    return build
+
+
 CASES = {
+    "dense_normal_vsm": dense_normal(False), "dense_normal_vvm": dense_normal(True),
+    "dense_normal_vvm_100": dense_normal(True, n=100), "dense_normal_vsm_65_const_sigma": dense_normal(False, n=65, const_sigma=True),
+    "dense_normal_in_model": dense_normal_in_model(48),
     "cauchy_sss": cauchy_case("sss"), "cauchy_vss": cauchy_case("vss"), "cauchy_vsv": cauchy_case("vsv"),
     "cauchy_vvs": cauchy_case("vvs"), "cauchy_vvv": cauchy_case("vvv"),
     "cauchy_vvv_big_seed": cauchy_case("vvv", seed=0.6, n=4099), "cauchy_vss_big": cauchy_case("vss", n=3001),
