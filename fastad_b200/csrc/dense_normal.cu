@@ -7,9 +7,10 @@
 // All FP64, hand-written, deterministic (no atomics):
 //   1. blocked right-looking Cholesky, block 32: one CTA factors the diagonal tile (and inverts
 //      it), a panel kernel applies L_kk^{-T}, a tiled SYRK updates the trailing lower triangle;
-//   2. Y = L^{-1} and X = L^{-T} Y by block-column-parallel substitution: one CTA owns a 32-wide
-//      column of the right-hand side and walks the block rows with 32x32x32 register-tiled
-//      products (4x4 outputs per thread);
+//   2. Y = L^{-1} by recursive halving ([A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1]) on a tiled FP64
+//      GEMM that skips the zero tiles of triangular operands, X = Y^T Y on the lower tiles only
+//      (a first version with one CTA per block column walking 32x32 products was 20x slower:
+//      its critical path is nb^2/2 dependent tile products);
 //   3. GEMV z = inv d, the value reduction and the adjoint scatter.
 // The FP64 tensor path (DMMA m8n8k4) is not used: on B200 its peak equals the vector FP64 peak
 // and the dependent 32-wide substitution chains, not the multiply throughput, bound this shape.
@@ -40,36 +41,41 @@ __global__ void dn_copy_lower(int n, const double* __restrict__ S, double* L)
     L[idx] = i >= j ? S[idx] : 0.0;          // LLT<Lower> reads the lower triangle only
 }
 
-// diagonal tile: unblocked Cholesky + inverse of the 32x32 lower factor.  1 CTA, 32x32 threads.
-__global__ void __launch_bounds__(1024)
+// diagonal tile: unblocked Cholesky + inverse of the 32x32 lower factor.  ONE warp, lane r owns
+// row r of the tile in shared memory (a 32x32-thread version with block barriers took 31 us per
+// tile; this one is a few us).
+__global__ void __launch_bounds__(32)
 dn_potf2(int n, double* L, int k0, double* Dinv_k, double* flag)
 {
     __shared__ double T[DB][DB + 1], Inv[DB][DB + 1];
-    const int r = threadIdx.y, c = threadIdx.x;
-    T[r][c] = (r >= c) ? ld_pad(L, n, k0 + r, k0 + c) : 0.0;
-    __syncthreads();
+    const int r = threadIdx.x;
+    for (int c = 0; c < DB; ++c) T[r][c] = (r >= c) ? ld_pad(L, n, k0 + r, k0 + c) : 0.0;
+    __syncwarp();
     for (int j = 0; j < DB; ++j) {
-        if (r == j && c == j) {
+        if (r == j) {
             double p = T[j][j];
             if (!(p > 0)) { flag[0] = 1.0; p = NAN; }      // llt.info() != Success, normal.hpp:660
             T[j][j] = sqrt(p);
         }
-        __syncthreads();
-        if (c == j && r > j) T[r][j] /= T[j][j];
-        __syncthreads();
-        if (r > j && c > j && r >= c) T[r][c] -= T[r][j] * T[c][j];
-        __syncthreads();
+        __syncwarp();
+        if (r > j) T[r][j] /= T[j][j];
+        __syncwarp();
+        if (r > j)
+            for (int c = j + 1; c <= r; ++c) T[r][c] -= T[r][j] * T[c][j];
+        __syncwarp();
     }
-    if (k0 + r < n && k0 + c < n && r >= c) L[(k0 + r) + (size_t)(k0 + c) * n] = T[r][c];
-    if (r == 0) {                                  // thread c solves column c of T^{-1}
+    for (int c = 0; c <= r; ++c)
+        if (k0 + r < n && k0 + c < n) L[(k0 + r) + (size_t)(k0 + c) * n] = T[r][c];
+    {                                              // lane c solves column c of T^{-1}
+        const int c = r;
         for (int i = 0; i < DB; ++i) {
             double t = (i == c) ? 1.0 : 0.0;
             for (int k = c; k < i; ++k) t -= T[i][k] * Inv[k][c];
             Inv[i][c] = (i < c) ? 0.0 : t / T[i][i];
         }
     }
-    __syncthreads();
-    Dinv_k[r + c * DB] = Inv[r][c];
+    __syncwarp();
+    for (int c = 0; c < DB; ++c) Dinv_k[r + c * DB] = Inv[r][c];
 }
 
 // panel: P <- P * L_kk^{-T}, P = L[k0+32 : n, k0 : k0+32].  64 rows per CTA, 256 threads.
@@ -93,147 +99,84 @@ dn_trsm_panel(int n, double* L, int k0, const double* __restrict__ Dinv_k)
     }
 }
 
-// trailing update: C[i][j] -= sum_q P[i][q] P[j][q] on 64x64 tiles with bi >= bj.  16x16 threads, 4x4 each.
+// ---- general FP64 GEMM: C = alpha * op(A) * op(B) + beta * C, column-major, 64x64x16 tiles,
+// 16x16 threads, 4x4 outputs per thread (rows along threadIdx.x so that stores coalesce).
+// Triangular structure is exploited at tile granularity through `kmode`:
+//   0 full K;  1 op(B) is lower triangular (K starts at the tile's first column);
+//   2 op(A) is lower triangular (K ends at the tile's last row);
+//   3 op(A) = M^T, op(B) = M with M lower triangular (K starts at max(tile row, tile col)).
+// lower_only = 1 computes the tiles on or below the diagonal and masks the strict upper part.
+template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
-dn_syrk(int n, double* L, int k0)
+dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+        double beta, double* C, int ldc, int kmode, int lower_only)
 {
-    if (blockIdx.x > blockIdx.y) return;           // x = tile column, y = tile row: lower tiles only
-    __shared__ double Pi[DB][64 + 4], Pj[DB][64 + 4];
-    const int base = k0 + DB;
-    const int i0 = base + blockIdx.y * 64, j0 = base + blockIdx.x * 64;
-    const int t = threadIdx.y * 16 + threadIdx.x;
-    for (int e = t; e < 64 * DB; e += 256) {
-        const int rr = e % 64, q = e / 64;
-        Pi[q][rr] = (i0 + rr < n) ? L[(i0 + rr) + (size_t)(k0 + q) * n] : 0.0;
-        Pj[q][rr] = (j0 + rr < n) ? L[(j0 + rr) + (size_t)(k0 + q) * n] : 0.0;
-    }
-    __syncthreads();
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (lower_only && bj > bi) return;
+    __shared__ double As[16][64 + 4], Bs[16][64 + 4];
+    const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 16 + tx;
+    const int i0 = bi * 64, j0 = bj * 64;
+    int kb = 0, ke = k;
+    if (kmode == 1) kb = j0;
+    else if (kmode == 2) ke = min(k, i0 + 64);
+    else if (kmode == 3) kb = max(i0, j0);
+    kb &= ~15;
     double acc[4][4] = {};
-#pragma unroll 8
-    for (int q = 0; q < DB; ++q) {
-        double a[4], b[4];
+    for (int k0 = kb; k0 < ke; k0 += 16) {
+        for (int e = t; e < 64 * 16; e += 256) {
+            int ii, kk;
+            if (TA) { kk = e % 16; ii = e / 16; } else { ii = e % 64; kk = e / 64; }
+            const int gi = i0 + ii, gk = k0 + kk;
+            double v = 0.0;
+            if (gi < m && gk < ke) v = TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda];
+            As[kk][ii] = v;
+        }
+        for (int e = t; e < 64 * 16; e += 256) {
+            int jj, kk;
+            if (TB) { jj = e % 64; kk = e / 64; } else { kk = e % 16; jj = e / 16; }
+            const int gj = j0 + jj, gk = k0 + kk;
+            double v = 0.0;
+            if (gj < n && gk < ke) v = TB ? B[gj + (size_t)gk * ldb] : B[gk + (size_t)gj * ldb];
+            Bs[kk][jj] = v;
+        }
+        __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a[u] = Pi[q][threadIdx.y * 4 + u]; b[u] = Pj[q][threadIdx.x * 4 + u]; }
+        for (int q = 0; q < 16; ++q) {
+            double a[4], b[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u) { a[u] = As[q][tx * 4 + u]; b[u] = Bs[q][ty * 4 + u]; }
 #pragma unroll
-            for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+        }
+        __syncthreads();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int i = i0 + threadIdx.y * 4 + u, j = j0 + threadIdx.x * 4 + v;
-            if (i < n && j < n && i >= j) L[i + (size_t)j * n] -= acc[u][v];
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + tx * 4 + u, j = j0 + ty * 4 + v;
+            if (i < m && j < n && (!lower_only || i >= j)) {
+                double* c = C + i + (size_t)j * ldc;
+                *c = (beta == 0.0) ? alpha * acc[u][v] : alpha * acc[u][v] + beta * *c;
+            }
         }
 }
 
-// ---- 32x32x32 products on a CTA of 64 threads (8x8), 4x4 outputs per thread -----------------
-// As is stored [q][row] (A^T) and Bs [q][col] so that both operand fetches are 4 consecutive doubles.
-struct Tile { double v[4][4]; };
-__device__ __forceinline__ void tile_mac(Tile& acc, const double (*As)[DB + 4], const double (*Bs)[DB + 4], int ty, int tx)
+// copy the 32x32 inverse tiles of the diagonal blocks into W (start of the recursive inversion)
+__global__ void dn_place_dinv(int n, int nb, const double* __restrict__ Dinv, double* W)
 {
-#pragma unroll 8
-    for (int q = 0; q < DB; ++q) {
-        double a[4], b[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { a[u] = As[q][ty * 4 + u]; b[u] = Bs[q][tx * 4 + u]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc.v[u][v] += a[u] * b[v];
+    const int b = blockIdx.x, r = threadIdx.x % DB, c = threadIdx.x / DB;
+    for (int cc = c; cc < DB; cc += blockDim.x / DB) {
+        const int gi = b * DB + r, gj = b * DB + cc;
+        if (gi < n && gj < n) W[gi + (size_t)gj * n] = Dinv[(size_t)b * DB * DB + r + cc * DB];
     }
 }
-__device__ __forceinline__ void tile_zero(Tile& t)
+__global__ void dn_zero(size_t count, double* p)
 {
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) t.v[u][v] = 0.0;
-}
-
-// Y = L^{-1} (lower), one CTA per 32-wide block column j:  Y_jj = Dinv_j,
-// Y_ij = -Dinv_i * sum_{k=j}^{i-1} L_ik Y_kj   (forward substitution on the identity)
-__global__ void __launch_bounds__(64)
-dn_trtri_cols(int n, int nb, const double* __restrict__ L, const double* __restrict__ Dinv, double* Y)
-{
-    __shared__ double As[DB][DB + 4], Bs[DB][DB + 4];
-    const int j = blockIdx.x, t = threadIdx.x, ty = t / 8, tx = t % 8;
-    for (int i = j; i < nb; ++i) {
-        Tile acc;
-        tile_zero(acc);
-        for (int k = j; k < i; ++k) {
-            for (int e = t; e < DB * DB; e += 64) {
-                const int rr = e % DB, cc = e / DB;
-                As[cc][rr] = (i * DB + rr < n && k * DB + cc < n) ? L[(i * DB + rr) + (size_t)(k * DB + cc) * n] : 0.0;
-                Bs[rr][cc] = (k * DB + rr < n && j * DB + cc < n) ? Y[(k * DB + rr) + (size_t)(j * DB + cc) * n] : 0.0;
-            }
-            __syncthreads();
-            tile_mac(acc, As, Bs, ty, tx);
-            __syncthreads();
-        }
-        // S = (i == j) ? I : -acc, then Y_ij = Dinv_i * S
-        for (int u = 0; u < 4; ++u)
-            for (int v = 0; v < 4; ++v) {
-                const int rr = ty * 4 + u, cc = tx * 4 + v;
-                Bs[rr][cc] = (i == j) ? (rr == cc ? 1.0 : 0.0) : -acc.v[u][v];
-            }
-        for (int e = t; e < DB * DB; e += 64) { const int rr = e % DB, cc = e / DB; As[cc][rr] = Dinv[(size_t)i * DB * DB + rr + cc * DB]; }
-        __syncthreads();
-        Tile out;
-        tile_zero(out);
-        tile_mac(out, As, Bs, ty, tx);
-        for (int u = 0; u < 4; ++u)
-            for (int v = 0; v < 4; ++v) {
-                const int r = i * DB + ty * 4 + u, c = j * DB + tx * 4 + v;
-                if (r < n && c < n) Y[r + (size_t)c * n] = out.v[u][v];
-            }
-        __syncthreads();       // Y_ij is read back from global memory by this CTA in later steps
-    }
-}
-
-// X = L^{-T} Y, lower block rows i >= j only (X = Sigma^{-1} is symmetric):
-// X_ij = Dinv_i^T (Y_ij - sum_{k>i} L_ki^T X_kj), walking i from the last block row up to j
-__global__ void __launch_bounds__(64)
-dn_lauum_cols(int n, int nb, const double* __restrict__ L, const double* __restrict__ Dinv, const double* __restrict__ Y,
-              double* X)
-{
-    __shared__ double As[DB][DB + 4], Bs[DB][DB + 4];
-    const int j = blockIdx.x, t = threadIdx.x, ty = t / 8, tx = t % 8;
-    for (int i = nb - 1; i >= j; --i) {
-        Tile acc;
-        tile_zero(acc);
-        for (int k = i + 1; k < nb; ++k) {
-            for (int e = t; e < DB * DB; e += 64) {
-                const int rr = e % DB, cc = e / DB;
-                // As[q][row] = (L_ki^T)[row][q] = L_ki[q][row]
-                As[rr][cc] = (k * DB + rr < n && i * DB + cc < n) ? L[(k * DB + rr) + (size_t)(i * DB + cc) * n] : 0.0;
-                Bs[rr][cc] = (k * DB + rr < n && j * DB + cc < n) ? X[(k * DB + rr) + (size_t)(j * DB + cc) * n] : 0.0;
-            }
-            __syncthreads();
-            tile_mac(acc, As, Bs, ty, tx);
-            __syncthreads();
-        }
-        for (int u = 0; u < 4; ++u)
-            for (int v = 0; v < 4; ++v) {
-                const int rr = ty * 4 + u, cc = tx * 4 + v;
-                const int r = i * DB + rr, c = j * DB + cc;
-                const double y = (r < n && c < n) ? Y[r + (size_t)c * n] : 0.0;
-                Bs[rr][cc] = y - acc.v[u][v];
-            }
-        // As[q][row] = (Dinv_i^T)[row][q] = Dinv_i[q][row]
-        for (int e = t; e < DB * DB; e += 64) { const int rr = e % DB, cc = e / DB; As[rr][cc] = Dinv[(size_t)i * DB * DB + rr + cc * DB]; }
-        __syncthreads();
-        Tile out;
-        tile_zero(out);
-        tile_mac(out, As, Bs, ty, tx);
-        for (int u = 0; u < 4; ++u)
-            for (int v = 0; v < 4; ++v) {
-                const int r = i * DB + ty * 4 + u, c = j * DB + tx * 4 + v;
-                if (r < n && c < n) X[r + (size_t)c * n] = out.v[u][v];
-            }
-        __syncthreads();
-    }
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx < count) p[idx] = 0.0;
 }
 
 __global__ void dn_symmetrize(int n, double* X)
@@ -296,6 +239,31 @@ __global__ void dn_sigma_adj(int n, const double* __restrict__ X, const double* 
     S_adj[idx] = overwrite ? g : S_adj[idx] + g;
 }
 
+template <bool TA, bool TB>
+static void gemm(Context& c, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+                 double beta, double* C, int ldc, int kmode, int lower_only)
+{
+    if (m <= 0 || n <= 0) return;
+    dim3 grid((m + 63) / 64, (n + 63) / 64);
+    dn_gemm<TA, TB><<<grid, dim3(16, 16), 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+    c.launches++;
+}
+
+// W[off:off+len, off:off+len] holds L there on entry (strictly-lower blocks) with the 32x32 diagonal
+// tiles already inverted; on exit it holds (L[off.., off..])^{-1}.  [A 0; B C]^{-1} = [A^-1 0; -C^-1 B A^-1, C^-1]
+static void trtri_rec(Context& c, int n, double* W, double* T, int off, int len)
+{
+    if (len <= DB) return;
+    const int n1 = std::max(DB, ((len / DB) / 2) * DB), n2 = len - n1;   // split on a tile boundary
+    trtri_rec(c, n, W, T, off, n1);
+    trtri_rec(c, n, W, T, off + n1, n2);
+    double* Ainv = W + off + (size_t)off * n;
+    double* Bm = W + (off + n1) + (size_t)off * n;
+    double* Cinv = W + (off + n1) + (size_t)(off + n1) * n;
+    gemm<false, false>(c, n2, n1, n1, 1.0, Bm, n, Ainv, n, 0.0, T, n2, 1, 0);        // T = B A^-1   (A^-1 lower)
+    gemm<false, false>(c, n2, n1, n2, -1.0, Cinv, n, T, n2, 0.0, Bm, n, 2, 0);       // B <- -C^-1 T (C^-1 lower)
+}
+
 static int ensure_dws(Context& c, size_t n, DenseWs** out)
 {
     DenseWs& w = g_dws[c.device];
@@ -345,22 +313,25 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
         c->launches++;
         for (int k = 0; k < nb; ++k) {
             const int k0 = k * DB;
-            dn_potf2<<<1, dim3(DB, DB), 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB, w->scal);
+            dn_potf2<<<1, 32, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB, w->scal);
             c->launches++;
             const int m = N - k0 - DB;
             if (m > 0) {
                 dn_trsm_panel<<<(m + 63) / 64, 256, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB);
-                const int tiles = (m + 63) / 64;
-                dn_syrk<<<dim3(tiles, tiles), dim3(16, 16), 0, st>>>(N, w->L, k0);
-                c->launches += 2;
+                c->launches++;
+                const double* P = w->L + (k0 + DB) + (size_t)k0 * N;
+                double* Ct = w->L + (k0 + DB) + (size_t)(k0 + DB) * N;
+                gemm<false, true>(*c, m, m, DB, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);     // trailing -= P P^T (lower)
             }
         }
-        {                              // z is formed from the explicit inverse, as the reference does (normal.hpp:632)
-            dn_trtri_cols<<<nb, 64, 0, st>>>(N, nb, w->L, w->Dinv, w->Y);
-            dn_lauum_cols<<<nb, 64, 0, st>>>(N, nb, w->L, w->Dinv, w->Y, w->X);
-            dn_symmetrize<<<eb, 256, 0, st>>>(N, w->X);
-            c->launches += 3;
-        }
+        // inverse: Y <- L^{-1} by recursive halving on GEMMs, X <- Y^T Y (lower tiles, K from the diagonal)
+        FADB_CUDA(cudaMemcpyAsync(w->Y, w->L, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        dn_place_dinv<<<nb, 256, 0, st>>>(N, nb, w->Dinv, w->Y);
+        c->launches++;
+        trtri_rec(*c, N, w->Y, w->X, 0, N);
+        gemm<true, false>(*c, N, N, N, 1.0, w->Y, N, w->Y, N, 0.0, w->X, N, 3, 1);
+        dn_symmetrize<<<eb, 256, 0, st>>>(N, w->X);
+        c->launches++;
     }
     dn_gemv<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, w->X, x, mu, mu_vec, w->d, w->z);
     dn_finish<<<1, 1024, 0, st>>>(N, w->L, w->d, w->z, w->scal, seed, ovw, x_adj, mu_adj, mu_vec, dev_value);
