@@ -5,16 +5,19 @@
 // Sigma_adj += (-0.5 seed)(inv - z z^T), mu_adj += seed z (or its sum), x_adj += -seed z.
 //
 // All FP64, hand-written, deterministic (no atomics):
-//   1. blocked right-looking Cholesky, block 32: one CTA factors the diagonal tile (and inverts
-//      it), a panel kernel applies L_kk^{-T}, a tiled SYRK updates the trailing lower triangle;
-//   2. Y = L^{-1} by recursive halving ([A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1]) on a tiled FP64
-//      GEMM that skips the zero tiles of triangular operands, X = Y^T Y on the lower tiles only
+//   1. two-level right-looking Cholesky (128-wide outer panels, 32-wide inner steps): one warp
+//      factors the diagonal tile in registers (and inverts it), a panel kernel applies L_kk^{-T},
+//      a tiled SYRK updates the rest of the outer panel (rank 32) and the trailing matrix (rank 128);
+//   2. Y = L^{-1} by recursive halving ([A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1]), one batched launch
+//      pair per tree level, on a tiled FP64 GEMM that skips the zero tiles of triangular operands;
+//      X = Y^T Y on the lower tiles only
 //      (a first version with one CTA per block column walking 32x32 products was 20x slower:
 //      its critical path is nb^2/2 dependent tile products);
 //   3. GEMV z = inv d, the value reduction and the adjoint scatter.
 // The FP64 tensor path (DMMA m8n8k4) is not used: on B200 its peak equals the vector FP64 peak
 // and the dependent 32-wide substitution chains, not the multiply throughput, bound this shape.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -41,41 +44,59 @@ __global__ void dn_copy_lower(int n, const double* __restrict__ S, double* L)
     L[idx] = i >= j ? S[idx] : 0.0;          // LLT<Lower> reads the lower triangle only
 }
 
-// diagonal tile: unblocked Cholesky + inverse of the 32x32 lower factor.  ONE warp, lane r owns
-// row r of the tile in shared memory (a 32x32-thread version with block barriers took 31 us per
-// tile; this one is a few us).
+// diagonal tile: unblocked Cholesky + inverse of the 32x32 lower factor.  ONE warp, lane r keeps
+// row r of the tile in registers; pivots and multipliers travel by shuffle, so there is no barrier
+// and no shared memory on the 32-step dependent chain (a 32x32-thread version with block barriers
+// took 31 us per tile, a shared-memory single-warp one 57 us; this one takes a few us).
+// 1/sqrt(pivot) comes from the MUFU seed + Newton steps; the column is divided with one residual
+// correction (within 1 ulp of the IEEE quotient).
 __global__ void __launch_bounds__(32)
 dn_potf2(int n, double* L, int k0, double* Dinv_k, double* flag)
 {
-    __shared__ double T[DB][DB + 1], Inv[DB][DB + 1];
     const int r = threadIdx.x;
-    for (int c = 0; c < DB; ++c) T[r][c] = (r >= c) ? ld_pad(L, n, k0 + r, k0 + c) : 0.0;
-    __syncwarp();
+    double row[DB], rinv[DB];
+#pragma unroll
+    for (int c = 0; c < DB; ++c) row[c] = (r >= c) ? ld_pad(L, n, k0 + r, k0 + c) : 0.0;
+    bool bad = false;
+#pragma unroll
     for (int j = 0; j < DB; ++j) {
-        if (r == j) {
-            double p = T[j][j];
-            if (!(p > 0)) { flag[0] = 1.0; p = NAN; }      // llt.info() != Success, normal.hpp:660
-            T[j][j] = sqrt(p);
-        }
-        __syncwarp();
-        if (r > j) T[r][j] /= T[j][j];
-        __syncwarp();
-        if (r > j)
-            for (int c = j + 1; c <= r; ++c) T[r][c] -= T[r][j] * T[c][j];
-        __syncwarp();
-    }
-    for (int c = 0; c <= r; ++c)
-        if (k0 + r < n && k0 + c < n) L[(k0 + r) + (size_t)(k0 + c) * n] = T[r][c];
-    {                                              // lane c solves column c of T^{-1}
-        const int c = r;
-        for (int i = 0; i < DB; ++i) {
-            double t = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) t -= T[i][k] * Inv[k][c];
-            Inv[i][c] = (i < c) ? 0.0 : t / T[i][i];
+        const double p = __shfl_sync(0xffffffffu, row[j], j);
+        bad |= !(p > 0);                                    // llt.info() != Success, normal.hpp:660
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+        const double h = 0.5 * p;
+        y = y * fma(-h * y, y, 1.5);
+        y = y * fma(-h * y, y, 1.5);
+        double sq = p * y;
+        sq = fma(fma(-sq, sq, p), 0.5 * y, sq);             // sqrt(p)
+        y = fma(y, fma(-sq, y, 1.0), y);                    // 1 / sqrt(p)
+        rinv[j] = y;
+        double q = row[j] * y;
+        q = fma(fma(-sq, q, row[j]), y, q);                 // row[j] / sqrt(p)
+        row[j] = (r == j) ? sq : q;
+#pragma unroll
+        for (int c = j + 1; c < DB; ++c) {
+            const double lcj = __shfl_sync(0xffffffffu, row[j], c);
+            if (r >= c) row[c] = fma(-row[j], lcj, row[c]);
         }
     }
-    __syncwarp();
-    for (int c = 0; c < DB; ++c) Dinv_k[r + c * DB] = Inv[r][c];
+    if (bad && r == 0) flag[0] = 1.0;
+#pragma unroll
+    for (int c = 0; c < DB; ++c)
+        if (c <= r && k0 + r < n && k0 + c < n) L[(k0 + r) + (size_t)(k0 + c) * n] = bad ? NAN : row[c];
+    double inv[DB];                                         // lane r solves column r of T^{-1}
+#pragma unroll
+    for (int i = 0; i < DB; ++i) {
+        double t0 = (i == r) ? 1.0 : 0.0, t1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double tik = __shfl_sync(0xffffffffu, row[k], i);
+            if (k & 1) t1 = fma(-tik, inv[k], t1); else t0 = fma(-tik, inv[k], t0);
+        }
+        inv[i] = (i < r) ? 0.0 : (t0 + t1) * rinv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DB; ++i) Dinv_k[i + r * DB] = bad ? NAN : inv[i];
 }
 
 // panel: P <- P * L_kk^{-T}, P = L[k0+32 : n, k0 : k0+32].  64 rows per CTA, 256 threads.
@@ -107,15 +128,15 @@ dn_trsm_panel(int n, double* L, int k0, const double* __restrict__ Dinv_k)
 //   3 op(A) = M^T, op(B) = M with M lower triangular (K starts at max(tile row, tile col)).
 // lower_only = 1 computes the tiles on or below the diagonal and masks the strict upper part.
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
-dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-        double beta, double* C, int ldc, int kmode, int lower_only)
+__device__ __forceinline__ void gemm_tile(int bi, int bj, int m, int n, int k, double alpha, const double* __restrict__ A,
+                                          int lda, const double* __restrict__ B, int ldb, double beta, double* C, int ldc,
+                                          int kmode, int lower_only)
 {
-    const int bi = blockIdx.x, bj = blockIdx.y;
     if (lower_only && bj > bi) return;
     __shared__ double As[16][64 + 4], Bs[16][64 + 4];
     const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 16 + tx;
     const int i0 = bi * 64, j0 = bj * 64;
+    if (i0 >= m || j0 >= n) return;
     int kb = 0, ke = k;
     if (kmode == 1) kb = j0;
     else if (kmode == 2) ke = min(k, i0 + 64);
@@ -148,7 +169,7 @@ dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
         }
         __syncthreads();
     }
@@ -159,9 +180,36 @@ dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda
             const int i = i0 + tx * 4 + u, j = j0 + ty * 4 + v;
             if (i < m && j < n && (!lower_only || i >= j)) {
                 double* c = C + i + (size_t)j * ldc;
-                *c = (beta == 0.0) ? alpha * acc[u][v] : alpha * acc[u][v] + beta * *c;
+                *c = (beta == 0.0) ? alpha * acc[u][v] : fma(alpha, acc[u][v], beta * *c);
             }
         }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+        double beta, double* C, int ldc, int kmode, int lower_only)
+{
+    gemm_tile<TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+}
+
+// ---- batched triangular inversion.  Node z of the recursion tree owns W[off : off+n1+n2]^2 =
+// [A 0; B C] with A^-1 (n1 x n1) and C^-1 (n2 x n2) already in place; all nodes of equal height are
+// independent, so one launch handles a whole level:  phase 0: T_z = B A^-1,  phase 1: B <- -C^-1 T_z.
+struct TrNode { int off, n1, n2, pad; long long toff; };
+
+__global__ void __launch_bounds__(256)
+dn_trtri_level(int n, double* W, double* T, const TrNode* __restrict__ nodes, int phase)
+{
+    const TrNode nd = nodes[blockIdx.z];
+    double* Ainv = W + nd.off + (size_t)nd.off * n;
+    double* Bm = W + (nd.off + nd.n1) + (size_t)nd.off * n;
+    double* Cinv = W + (nd.off + nd.n1) + (size_t)(nd.off + nd.n1) * n;
+    double* Tz = T + nd.toff;
+    if (phase == 0)
+        gemm_tile<false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n1, 1.0, Bm, n, Ainv, n, 0.0, Tz, nd.n2, 1, 0);
+    else
+        gemm_tile<false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n2, -1.0, Cinv, n, Tz, nd.n2, 0.0, Bm, n, 2, 0);
 }
 
 // copy the 32x32 inverse tiles of the diagonal blocks into W (start of the recursive inversion)
@@ -249,19 +297,55 @@ static void gemm(Context& c, int m, int n, int k, double alpha, const double* A,
     c.launches++;
 }
 
-// W[off:off+len, off:off+len] holds L there on entry (strictly-lower blocks) with the 32x32 diagonal
-// tiles already inverted; on exit it holds (L[off.., off..])^{-1}.  [A 0; B C]^{-1} = [A^-1 0; -C^-1 B A^-1, C^-1]
-static void trtri_rec(Context& c, int n, double* W, double* T, int off, int len)
+// recursion tree of the triangular inversion, grouped by height (leaves = single 32-wide tiles)
+struct TrLevel { int first, count, max_n1, max_n2; };
+struct TrPlan {
+    size_t n = 0;
+    std::vector<TrLevel> levels;
+    TrNode* dev = nullptr;
+};
+static int tr_build(int off, int len, std::vector<std::vector<TrNode>>& by_height)
 {
-    if (len <= DB) return;
+    if (len <= DB) return 0;
     const int n1 = std::max(DB, ((len / DB) / 2) * DB), n2 = len - n1;   // split on a tile boundary
-    trtri_rec(c, n, W, T, off, n1);
-    trtri_rec(c, n, W, T, off + n1, n2);
-    double* Ainv = W + off + (size_t)off * n;
-    double* Bm = W + (off + n1) + (size_t)off * n;
-    double* Cinv = W + (off + n1) + (size_t)(off + n1) * n;
-    gemm<false, false>(c, n2, n1, n1, 1.0, Bm, n, Ainv, n, 0.0, T, n2, 1, 0);        // T = B A^-1   (A^-1 lower)
-    gemm<false, false>(c, n2, n1, n2, -1.0, Cinv, n, T, n2, 0.0, Bm, n, 2, 0);       // B <- -C^-1 T (C^-1 lower)
+    const int h = 1 + std::max(tr_build(off, n1, by_height), tr_build(off + n1, n2, by_height));
+    if ((int)by_height.size() < h) by_height.resize(h);
+    by_height[h - 1].push_back(TrNode{off, n1, n2, 0, 0});
+    return h;
+}
+static TrPlan g_trplan[kMaxDevices];
+
+static int ensure_trplan(Context& c, size_t n, TrPlan** out)
+{
+    TrPlan& p = g_trplan[c.device];
+    if (p.n != n) {
+        std::vector<std::vector<TrNode>> by_height;
+        tr_build(0, (int)n, by_height);
+        std::vector<TrNode> flat;
+        p.levels.clear();
+        for (auto& lv : by_height) {
+            TrLevel L{(int)flat.size(), (int)lv.size(), 0, 0};
+            long long toff = 0;                      // the T buffers of one level are packed into X
+            for (auto& nd : lv) {
+                nd.toff = toff;
+                toff += (long long)nd.n1 * nd.n2;
+                L.max_n1 = std::max(L.max_n1, nd.n1);
+                L.max_n2 = std::max(L.max_n2, nd.n2);
+                flat.push_back(nd);
+            }
+            p.levels.push_back(L);
+        }
+        FADB_CUDA(cudaStreamSynchronize(c.stream));
+        if (p.dev) FADB_CUDA(cudaFree(p.dev));
+        p.dev = nullptr;
+        if (!flat.empty()) {
+            FADB_CUDA(cudaMalloc(&p.dev, flat.size() * sizeof(TrNode)));
+            FADB_CUDA(cudaMemcpy(p.dev, flat.data(), flat.size() * sizeof(TrNode), cudaMemcpyHostToDevice));
+        }
+        p.n = n;
+    }
+    *out = &p;
+    return FADB_OK;
 }
 
 static int ensure_dws(Context& c, size_t n, DenseWs** out)
@@ -302,6 +386,9 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
     DenseWs* w;
     rc = ensure_dws(*c, n, &w);
     if (rc) return rc;
+    TrPlan* tp;
+    rc = ensure_trplan(*c, n, &tp);
+    if (rc) return rc;
     const int N = (int)n, nb = (N + DB - 1) / DB;
     const int ovw = (flags & FADB_OVERWRITE_ADJ) ? 1 : 0;
     const size_t nn = n * n;
@@ -311,24 +398,44 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
         FADB_CUDA(cudaMemsetAsync(w->scal, 0, 8 * sizeof(double), st));
         dn_copy_lower<<<eb, 256, 0, st>>>(N, Sigma, w->L);
         c->launches++;
-        for (int k = 0; k < nb; ++k) {
-            const int k0 = k * DB;
-            dn_potf2<<<1, 32, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB, w->scal);
-            c->launches++;
-            const int m = N - k0 - DB;
-            if (m > 0) {
+        // two-level right-looking Cholesky: 128-wide outer panels, 32-wide inner steps.  The inner
+        // rank-32 update touches the rest of the outer panel only; the trailing matrix gets one
+        // rank-128 update per outer panel.
+        constexpr int OB = 128;
+        for (int K0 = 0; K0 < N; K0 += OB) {
+            const int W = std::min(OB, N - K0), Kend = K0 + W;
+            for (int k0 = K0; k0 < Kend; k0 += DB) {
+                const int k = k0 / DB;
+                dn_potf2<<<1, 32, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB, w->scal);
+                c->launches++;
+                const int m = N - k0 - DB;
+                if (m <= 0) continue;
                 dn_trsm_panel<<<(m + 63) / 64, 256, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB);
                 c->launches++;
-                const double* P = w->L + (k0 + DB) + (size_t)k0 * N;
-                double* Ct = w->L + (k0 + DB) + (size_t)(k0 + DB) * N;
-                gemm<false, true>(*c, m, m, DB, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);     // trailing -= P P^T (lower)
+                const int pc = Kend - (k0 + DB);             // columns of the outer panel still to update
+                if (pc > 0) {
+                    const double* P = w->L + (k0 + DB) + (size_t)k0 * N;
+                    double* Ct = w->L + (k0 + DB) + (size_t)(k0 + DB) * N;
+                    gemm<false, true>(*c, m, pc, DB, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);
+                }
+            }
+            const int m = N - Kend;
+            if (m > 0) {
+                const double* P = w->L + Kend + (size_t)K0 * N;
+                double* Ct = w->L + Kend + (size_t)Kend * N;
+                gemm<false, true>(*c, m, m, W, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);      // trailing -= P P^T (lower)
             }
         }
-        // inverse: Y <- L^{-1} by recursive halving on GEMMs, X <- Y^T Y (lower tiles, K from the diagonal)
+        // inverse: Y <- L^{-1} level by level up the halving tree, X <- Y^T Y (lower tiles, K from the diagonal)
         FADB_CUDA(cudaMemcpyAsync(w->Y, w->L, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
         dn_place_dinv<<<nb, 256, 0, st>>>(N, nb, w->Dinv, w->Y);
         c->launches++;
-        trtri_rec(*c, N, w->Y, w->X, 0, N);
+        for (const TrLevel& lv : tp->levels) {
+            dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
+            dn_trtri_level<<<grid, dim3(16, 16), 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+            dn_trtri_level<<<grid, dim3(16, 16), 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            c->launches += 2;
+        }
         gemm<true, false>(*c, N, N, N, 1.0, w->Y, N, w->Y, N, 0.0, w->X, N, 3, 1);
         dn_symmetrize<<<eb, 256, 0, st>>>(N, w->X);
         c->launches++;
