@@ -5,10 +5,11 @@
 // Sigma_adj += (-0.5 seed)(inv - z z^T), mu_adj += seed z (or its sum), x_adj += -seed z.
 //
 // All FP64, hand-written, deterministic (no atomics):
-//   1. two-level right-looking Cholesky (128-wide outer panels, 32-wide inner steps): one warp
-//      factors the diagonal tile in registers (and inverts it), a panel kernel applies L_kk^{-T},
-//      a tiled SYRK updates the rest of the outer panel (rank 32) and the trailing matrix (rank 128);
-//   2. Y = L^{-1} by recursive halving ([A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1]), one batched launch
+//   1. two-level right-looking Cholesky (128-wide outer panels, 32-wide inner steps): ONE launch per
+//      inner step factors the diagonal tile in registers, solves the panel against it and updates
+//      the rest of the outer panel (rank 32); a tiled SYRK then updates the trailing matrix
+//      (rank 128) once per outer panel;
+//   2. the 32x32 diagonal tiles are inverted in one batched launch, then Y = L^{-1} by recursive halving ([A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1]), one batched launch
 //      pair per tree level, on a tiled FP64 GEMM that skips the zero tiles of triangular operands;
 //      X = Y^T Y on the lower tiles only
 //      (a first version with one CTA per block column walking 32x32 products was 20x slower:
@@ -26,7 +27,7 @@ namespace fadb {
 constexpr int DB = 32;
 
 struct DenseWs {
-    double *L = nullptr, *Y = nullptr, *X = nullptr, *Dinv = nullptr, *d = nullptr, *z = nullptr, *scal = nullptr;
+    double *L = nullptr, *Y = nullptr, *X = nullptr, *d = nullptr, *z = nullptr, *scal = nullptr, *diag = nullptr;
     size_t cap = 0;
 };
 static DenseWs g_dws[kMaxDevices];
@@ -44,140 +45,234 @@ __global__ void dn_copy_lower(int n, const double* __restrict__ S, double* L)
     L[idx] = i >= j ? S[idx] : 0.0;          // LLT<Lower> reads the lower triangle only
 }
 
-// diagonal tile: unblocked Cholesky + inverse of the 32x32 lower factor.  ONE warp, lane r keeps
-// row r of the tile in registers; pivots and multipliers travel by shuffle, so there is no barrier
-// and no shared memory on the 32-step dependent chain (a 32x32-thread version with block barriers
-// took 31 us per tile, a shared-memory single-warp one 57 us; this one takes a few us).
-// 1/sqrt(pivot) comes from the MUFU seed + Newton steps; the column is divided with one residual
-// correction (within 1 ulp of the IEEE quotient).
-__global__ void __launch_bounds__(32)
-dn_potf2(int n, double* L, int k0, double* Dinv_k, double* flag)
-{
-    const int r = threadIdx.x;
-    double row[DB], rinv[DB];
-#pragma unroll
-    for (int c = 0; c < DB; ++c) row[c] = (r >= c) ? ld_pad(L, n, k0 + r, k0 + c) : 0.0;
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < DB; ++j) {
-        const double p = __shfl_sync(0xffffffffu, row[j], j);
-        bad |= !(p > 0);                                    // llt.info() != Success, normal.hpp:660
-        double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-        const double h = 0.5 * p;
-        y = y * fma(-h * y, y, 1.5);
-        y = y * fma(-h * y, y, 1.5);
-        double sq = p * y;
-        sq = fma(fma(-sq, sq, p), 0.5 * y, sq);             // sqrt(p)
-        y = fma(y, fma(-sq, y, 1.0), y);                    // 1 / sqrt(p)
-        rinv[j] = y;
-        double q = row[j] * y;
-        q = fma(fma(-sq, q, row[j]), y, q);                 // row[j] / sqrt(p)
-        row[j] = (r == j) ? sq : q;
-#pragma unroll
-        for (int c = j + 1; c < DB; ++c) {
-            const double lcj = __shfl_sync(0xffffffffu, row[j], c);
-            if (r >= c) row[c] = fma(-row[j], lcj, row[c]);
-        }
-    }
-    if (bad && r == 0) flag[0] = 1.0;
-#pragma unroll
-    for (int c = 0; c < DB; ++c)
-        if (c <= r && k0 + r < n && k0 + c < n) L[(k0 + r) + (size_t)(k0 + c) * n] = bad ? NAN : row[c];
-    double inv[DB];                                         // lane r solves column r of T^{-1}
-#pragma unroll
-    for (int i = 0; i < DB; ++i) {
-        double t0 = (i == r) ? 1.0 : 0.0, t1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) {
-            const double tik = __shfl_sync(0xffffffffu, row[k], i);
-            if (k & 1) t1 = fma(-tik, inv[k], t1); else t0 = fma(-tik, inv[k], t0);
-        }
-        inv[i] = (i < r) ? 0.0 : (t0 + t1) * rinv[i];
-    }
-#pragma unroll
-    for (int i = 0; i < DB; ++i) Dinv_k[i + r * DB] = bad ? NAN : inv[i];
-}
+// ---- one inner step of the blocked Cholesky, ONE launch:  diagonal tile -> panel -> rank-32 update
+// of the rest of the 128-wide outer panel.  CTA b owns rows [k0+32+64b, +64) below the tile.
+//  A. warp 0 of EVERY CTA factors the 32x32 diagonal tile redundantly - it is a dependent 32-step
+//     chain nobody can help with, and repeating it saves two launches and a round trip through
+//     global memory; the other warps meanwhile stage the raw panel rows.
+//     Lane r keeps row r of the trailing tile in registers; each step updates and ROTATES the row
+//     by one column (row[c-1] = row[c] - l_rj * l_(j+c)j), so the step body has static register
+//     indices inside a run-time loop and the code stays small (a fully unrolled version ran at
+//     instruction-fetch speed, 30 us per tile; a shared-memory one at 57 us; a 32x32-thread one
+//     with block barriers at 31 us).  1/sqrt(pivot): MUFU seed + two Newton steps.
+//  B. P <- P L_kk^{-T} by forward substitution, one thread per row (same rotate trick, the row
+//     lives in registers), for the CTA's own 64 rows and (again redundantly) for the `pc` rows at
+//     the top of the panel, whose columns the update needs.
+//  C. C[own rows][top pc columns] -= P_own P_top^T, lower part only; the C values are fetched
+//     before phase B so that their latency hides behind it.
+// The step READS the working matrix L (diagonal tile, raw panel) and WRITES the finished factor
+// columns to F: CTAs of one launch read each other's raw rows, so the panel is never updated in place.
+constexpr int CS_ROWS = 64, CS_TOP = 96;
+struct CholSmem {
+    double Tc[DB][2 * DB];                 // Tc[j][i] = l_ij (column j contiguous), zero for i >= 32
+    double colbuf[2 * DB], rinv_s[DB];
+    double P[CS_ROWS + CS_TOP + 8][DB + 1];// own rows first, then the top rows of the panel (+8 rows of slack)
+};
 
-// panel: P <- P * L_kk^{-T}, P = L[k0+32 : n, k0 : k0+32].  64 rows per CTA, 256 threads.
 __global__ void __launch_bounds__(256)
-dn_trsm_panel(int n, double* L, int k0, const double* __restrict__ Dinv_k)
+dn_chol_step(int n, double* L, double* F, double* diag, int k0, int pc, double* flag)
 {
-    __shared__ double P[64][DB + 1], D[DB][DB + 1];
-    const int t = threadIdx.x;
-    const int r0 = k0 + DB + blockIdx.x * 64;
-    for (int e = t; e < DB * DB; e += 256) D[e % DB][e / DB] = Dinv_k[e];
-    for (int e = t; e < 64 * DB; e += 256) {
-        const int rr = e % 64, cc = e / 64;
-        P[rr][cc] = (r0 + rr < n && k0 + cc < n) ? L[(r0 + rr) + (size_t)(k0 + cc) * n] : 0.0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CholSmem& S = *reinterpret_cast<CholSmem*>(smem_raw);
+    const int t = threadIdx.x, r = t & 31;
+    const int top0 = k0 + DB, own0 = top0 + blockIdx.x * CS_ROWS, R = CS_ROWS + pc;
+    if (t < 32) {
+        double row[DB];
+#pragma unroll
+        for (int c = 0; c < DB; ++c) {
+            row[c] = (r >= c) ? ld_pad(L, n, k0 + r, k0 + c) : 0.0;
+            S.Tc[c][DB + r] = 0.0;
+        }
+        S.colbuf[DB + r] = 0.0;
+        bool bad = false;
+        const bool writer = blockIdx.x == 0;
+        for (int j = 0; j < DB; ++j) {
+            const double p = __shfl_sync(0xffffffffu, row[0], j);
+            bad |= !(p > 0);                                // llt.info() != Success, normal.hpp:660
+            double y;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+            const double h = 0.5 * p;
+            y = y * fma(-h * y, y, 1.5);
+            y = y * fma(-h * y, y, 1.5);
+            const double lrj = (r >= j) ? row[0] * y : 0.0; // l_rj; the pivot lane gets p / sqrt(p)
+            S.colbuf[r] = lrj;
+            S.Tc[j][r] = lrj;
+            if (r == j) S.rinv_s[j] = y;
+            if (writer && r >= j && k0 + r < n && k0 + j < n) F[(k0 + r) + (size_t)(k0 + j) * n] = lrj;
+            if (writer && r == j && k0 + j < n) diag[k0 + j] = lrj;
+            __syncwarp();
+#pragma unroll
+            for (int c = 1; c < DB; ++c) row[c - 1] = fma(-lrj, S.colbuf[j + c], row[c]);
+            row[DB - 1] = 0.0;
+            __syncwarp();
+        }
+        if (bad && writer && r == 0) flag[0] = 1.0;
+    } else {
+        for (int e = t - 32; e < R * DB; e += 224) {
+            const int rr = e % R, cc = e / R;
+            const int g = rr < CS_ROWS ? own0 + rr : top0 + (rr - CS_ROWS);
+            S.P[rr][cc] = (g < n && k0 + cc < n) ? L[g + (size_t)(k0 + cc) * n] : 0.0;
+        }
+    }
+    // C values of this thread (row i, columns jg*8 + 32*b + v), in flight during phase B
+    const int i = t & 63, jg = t >> 6, gi = own0 + i;
+    double cv[3][8];
+#pragma unroll
+    for (int bq = 0; bq < 3; ++bq)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int j = jg * 8 + bq * 32 + v, gj = top0 + j;
+            cv[bq][v] = (j < pc && gi < n && gi >= gj) ? L[gi + (size_t)gj * n] : 0.0;
+        }
+    __syncthreads();
+    if (own0 >= n && blockIdx.x > 0) return;
+    // B: forward substitution x L_kk^T = p, one row per thread, row in registers
+    if (t < R) {
+        double pr[DB];
+#pragma unroll
+        for (int q = 0; q < DB; ++q) pr[q] = S.P[t][q];
+        const bool own = t < CS_ROWS && own0 + t < n;
+        for (int c = 0; c < DB; ++c) {
+            const double x = pr[0] * S.rinv_s[c];
+            S.P[t][c] = x;
+            if (own && k0 + c < n) F[(own0 + t) + (size_t)(k0 + c) * n] = x;
+#pragma unroll
+            for (int u = 1; u < DB; ++u) pr[u - 1] = fma(-x, S.Tc[c][c + u], pr[u]);
+            pr[DB - 1] = 0.0;
+        }
     }
     __syncthreads();
-    for (int e = t; e < 64 * DB; e += 256) {
-        const int rr = e % 64, cc = e / 64;
-        double acc = 0.0;
-        for (int q = 0; q <= cc; ++q) acc += P[rr][q] * D[cc][q];      // (Dinv^T)[q][cc] = Dinv[cc][q]
-        if (r0 + rr < n && k0 + cc < n) L[(r0 + rr) + (size_t)(k0 + cc) * n] = acc;
+    // C: rank-32 update of the rest of the outer panel, 8 columns (independent chains) at a time
+    if (pc <= 0) return;
+    double pr[DB];
+#pragma unroll
+    for (int q = 0; q < DB; ++q) pr[q] = S.P[i][q];
+#pragma unroll
+    for (int bq = 0; bq < 3; ++bq) {
+        const int jb = jg * 8 + bq * 32;
+        if (jb >= pc) break;
+        double acc[8] = {};
+#pragma unroll
+        for (int q = 0; q < DB; ++q)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc[v] = fma(pr[q], S.P[CS_ROWS + jb + v][q], acc[v]);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int gj = top0 + jb + v;
+            if (jb + v < pc && gi < n && gi >= gj) L[gi + (size_t)gj * n] = cv[bq][v] - acc[v];
+        }
     }
 }
 
-// ---- general FP64 GEMM: C = alpha * op(A) * op(B) + beta * C, column-major, 64x64x16 tiles,
-// 16x16 threads, 4x4 outputs per thread (rows along threadIdx.x so that stores coalesce).
+// inverses of all 32x32 diagonal tiles of the factor, in place in Y (the leaves of the recursive
+// inversion), one warp per tile: column-oriented forward substitution, lane r solving column r.
+__global__ void __launch_bounds__(32)
+dn_tile_inverse(int n, double* Y)
+{
+    __shared__ double Tc[DB][2 * DB];
+    const int r = threadIdx.x, k0 = blockIdx.x * DB;
+#pragma unroll
+    for (int c = 0; c < DB; ++c) {
+        Tc[c][r] = (r >= c) ? ld_pad(Y, n, k0 + r, k0 + c) : 0.0;
+        Tc[c][DB + r] = 0.0;
+    }
+    __syncwarp();
+    double tt[DB];
+#pragma unroll
+    for (int u = 0; u < DB; ++u) tt[u] = (u == r) ? 1.0 : 0.0;
+    for (int i = 0; i < DB; ++i) {
+        const double v = tt[0] / Tc[i][i];                  // (L_kk^-1)[i][r]
+        if (k0 + i < n && k0 + r < n) Y[(k0 + i) + (size_t)(k0 + r) * n] = v;
+#pragma unroll
+        for (int u = 1; u < DB; ++u) tt[u - 1] = fma(-Tc[i][i + u], v, tt[u]);
+        tt[DB - 1] = 0.0;
+    }
+}
+
+// ---- general FP64 GEMM: C = alpha * op(A) * op(B) + beta * C, column-major.  256 threads own a
+// BT x BT tile (BT = 64: 4x4 outputs per thread, K step 16; BT = 128: 8x8 outputs, K step 8).
+//  * the next K slab is fetched from global memory into registers while the current one is
+//    multiplied out of shared memory (two shared buffers, one barrier per slab);
+//  * a warp covers 8 x 4 threads and every thread reads its fragments as 16-byte pairs at
+//    (chunk * 32 + 2 * thread) so that the LDS.128s of a warp are conflict-free and 8 lanes
+//    broadcast; rows run along the fast thread index so stores to C coalesce.
 // Triangular structure is exploited at tile granularity through `kmode`:
 //   0 full K;  1 op(B) is lower triangular (K starts at the tile's first column);
 //   2 op(A) is lower triangular (K ends at the tile's last row);
 //   3 op(A) = M^T, op(B) = M with M lower triangular (K starts at max(tile row, tile col)).
 // lower_only = 1 computes the tiles on or below the diagonal and masks the strict upper part.
-template <bool TA, bool TB>
+template <int BT, bool TA, bool TB>
 __device__ __forceinline__ void gemm_tile(int bi, int bj, int m, int n, int k, double alpha, const double* __restrict__ A,
                                           int lda, const double* __restrict__ B, int ldb, double beta, double* C, int ldc,
                                           int kmode, int lower_only)
 {
+    constexpr int BK = BT == 128 ? 8 : 16, TM = BT / 16, SS = BT + 2, NL = BT * BK / 256;
+    __shared__ __align__(16) double As[2][BK][SS], Bs[2][BK][SS];
     if (lower_only && bj > bi) return;
-    __shared__ double As[16][64 + 4], Bs[16][64 + 4];
-    const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 16 + tx;
-    const int i0 = bi * 64, j0 = bj * 64;
+    const int i0 = bi * BT, j0 = bj * BT;
     if (i0 >= m || j0 >= n) return;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int tx = (w & 1) * 8 + (lane & 7), ty = (w >> 1) * 4 + (lane >> 3);
     int kb = 0, ke = k;
     if (kmode == 1) kb = j0;
-    else if (kmode == 2) ke = min(k, i0 + 64);
+    else if (kmode == 2) ke = min(k, i0 + BT);
     else if (kmode == 3) kb = max(i0, j0);
-    kb &= ~15;
-    double acc[4][4] = {};
-    for (int k0 = kb; k0 < ke; k0 += 16) {
-        for (int e = t; e < 64 * 16; e += 256) {
-            int ii, kk;
-            if (TA) { kk = e % 16; ii = e / 16; } else { ii = e % 64; kk = e / 64; }
+    kb &= ~(BK - 1);
+    double acc[TM][TM] = {};
+    double ra[NL], rb[NL];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const int e = t + u * 256;
+            const int ii = TA ? e / BK : e % BT, kk = TA ? e % BK : e / BT;
             const int gi = i0 + ii, gk = k0 + kk;
-            double v = 0.0;
-            if (gi < m && gk < ke) v = TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda];
-            As[kk][ii] = v;
+            ra[u] = (gi < m && gk < ke) ? (TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda]) : 0.0;
+            const int jj = TB ? e % BT : e / BK, kq = TB ? e / BT : e % BK;
+            const int gj = j0 + jj, gq = k0 + kq;
+            rb[u] = (gj < n && gq < ke) ? (TB ? B[gj + (size_t)gq * ldb] : B[gq + (size_t)gj * ldb]) : 0.0;
         }
-        for (int e = t; e < 64 * 16; e += 256) {
-            int jj, kk;
-            if (TB) { jj = e % 64; kk = e / 64; } else { kk = e % 16; jj = e / 16; }
-            const int gj = j0 + jj, gk = k0 + kk;
-            double v = 0.0;
-            if (gj < n && gk < ke) v = TB ? B[gj + (size_t)gk * ldb] : B[gk + (size_t)gj * ldb];
-            Bs[kk][jj] = v;
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const int e = t + u * 256;
+            As[buf][TA ? e % BK : e / BT][TA ? e / BK : e % BT] = ra[u];
+            Bs[buf][TB ? e / BT : e % BK][TB ? e % BT : e / BK] = rb[u];
         }
-        __syncthreads();
+    };
+    gload(kb);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kb; k0 < ke; k0 += BK) {
+        const bool more = k0 + BK < ke;
+        if (more) gload(k0 + BK);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            double a[4], b[4];
+        for (int q = 0; q < BK; ++q) {
+            double a[TM], b[TM];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { a[u] = As[q][tx * 4 + u]; b[u] = Bs[q][ty * 4 + u]; }
+            for (int c = 0; c < TM / 2; ++c) {
+                const double2 va = *reinterpret_cast<const double2*>(&As[buf][q][c * 32 + tx * 2]);
+                const double2 vb = *reinterpret_cast<const double2*>(&Bs[buf][q][c * 32 + ty * 2]);
+                a[2 * c] = va.x; a[2 * c + 1] = va.y;
+                b[2 * c] = vb.x; b[2 * c + 1] = vb.y;
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < TM; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+                for (int v = 0; v < TM; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
         }
-        __syncthreads();
+        if (more) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
+    for (int v = 0; v < TM; ++v)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + tx * 4 + u, j = j0 + ty * 4 + v;
+        for (int u = 0; u < TM; ++u) {
+            const int i = i0 + (u / 2) * 32 + tx * 2 + (u & 1), j = j0 + (v / 2) * 32 + ty * 2 + (v & 1);
             if (i < m && j < n && (!lower_only || i >= j)) {
                 double* c = C + i + (size_t)j * ldc;
                 *c = (beta == 0.0) ? alpha * acc[u][v] : fma(alpha, acc[u][v], beta * *c);
@@ -185,12 +280,12 @@ __device__ __forceinline__ void gemm_tile(int bi, int bj, int m, int n, int k, d
         }
 }
 
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
+template <int BT, bool TA, bool TB>
+__global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
 dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
         double beta, double* C, int ldc, int kmode, int lower_only)
 {
-    gemm_tile<TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+    gemm_tile<BT, TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
 }
 
 // ---- batched triangular inversion.  Node z of the recursion tree owns W[off : off+n1+n2]^2 =
@@ -198,7 +293,8 @@ dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda
 // independent, so one launch handles a whole level:  phase 0: T_z = B A^-1,  phase 1: B <- -C^-1 T_z.
 struct TrNode { int off, n1, n2, pad; long long toff; };
 
-__global__ void __launch_bounds__(256)
+template <int BT>
+__global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
 dn_trtri_level(int n, double* W, double* T, const TrNode* __restrict__ nodes, int phase)
 {
     const TrNode nd = nodes[blockIdx.z];
@@ -207,24 +303,9 @@ dn_trtri_level(int n, double* W, double* T, const TrNode* __restrict__ nodes, in
     double* Cinv = W + (nd.off + nd.n1) + (size_t)(nd.off + nd.n1) * n;
     double* Tz = T + nd.toff;
     if (phase == 0)
-        gemm_tile<false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n1, 1.0, Bm, n, Ainv, n, 0.0, Tz, nd.n2, 1, 0);
+        gemm_tile<BT, false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n1, 1.0, Bm, n, Ainv, n, 0.0, Tz, nd.n2, 1, 0);
     else
-        gemm_tile<false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n2, -1.0, Cinv, n, Tz, nd.n2, 0.0, Bm, n, 2, 0);
-}
-
-// copy the 32x32 inverse tiles of the diagonal blocks into W (start of the recursive inversion)
-__global__ void dn_place_dinv(int n, int nb, const double* __restrict__ Dinv, double* W)
-{
-    const int b = blockIdx.x, r = threadIdx.x % DB, c = threadIdx.x / DB;
-    for (int cc = c; cc < DB; cc += blockDim.x / DB) {
-        const int gi = b * DB + r, gj = b * DB + cc;
-        if (gi < n && gj < n) W[gi + (size_t)gj * n] = Dinv[(size_t)b * DB * DB + r + cc * DB];
-    }
-}
-__global__ void dn_zero(size_t count, double* p)
-{
-    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (idx < count) p[idx] = 0.0;
+        gemm_tile<BT, false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n2, -1.0, Cinv, n, Tz, nd.n2, 0.0, Bm, n, 2, 0);
 }
 
 __global__ void dn_symmetrize(int n, double* X)
@@ -251,14 +332,14 @@ dn_gemv(int n, const double* __restrict__ X, const double* __restrict__ x, const
 
 // value, scalar-mu adjoint and x / vector-mu adjoints.  1 CTA.
 __global__ void __launch_bounds__(1024)
-dn_finish(int n, const double* __restrict__ L, const double* __restrict__ d, const double* __restrict__ z,
+dn_finish(int n, const double* __restrict__ diag, const double* __restrict__ d, const double* __restrict__ z,
           const double* flag, double seed, int overwrite, double* x_adj, double* mu_adj, int mu_vec, double* out_value)
 {
     __shared__ double sm[32 * 3];
     double acc[3] = {0.0, 0.0, 0.0};             // d^T z, sum log L_ii, sum z
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         acc[0] += d[i] * z[i];
-        acc[1] += log(L[i + (size_t)i * n]);
+        acc[1] += log(diag[i]);
         acc[2] += z[i];
     }
     block_sum<3>(acc, sm);
@@ -287,13 +368,22 @@ __global__ void dn_sigma_adj(int n, const double* __restrict__ X, const double* 
     S_adj[idx] = overwrite ? g : S_adj[idx] + g;
 }
 
+// 128-wide tiles (8x8 outputs per thread) once they fill the GPU, 64-wide ones below that
+static inline bool big_tiles(const Context& c, long long tiles128) { return tiles128 >= (long long)c.sms; }
+
 template <bool TA, bool TB>
 static void gemm(Context& c, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
                  double beta, double* C, int ldc, int kmode, int lower_only)
 {
     if (m <= 0 || n <= 0) return;
-    dim3 grid((m + 63) / 64, (n + 63) / 64);
-    dn_gemm<TA, TB><<<grid, dim3(16, 16), 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+    const long long t128 = (long long)((m + 127) / 128) * ((n + 127) / 128) / (lower_only ? 2 : 1);
+    if (big_tiles(c, t128)) {
+        dim3 grid((m + 127) / 128, (n + 127) / 128);
+        dn_gemm<128, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+    } else {
+        dim3 grid((m + 63) / 64, (n + 63) / 64);
+        dn_gemm<64, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+    }
     c.launches++;
 }
 
@@ -353,15 +443,15 @@ static int ensure_dws(Context& c, size_t n, DenseWs** out)
     DenseWs& w = g_dws[c.device];
     if (w.cap < n) {
         FADB_CUDA(cudaStreamSynchronize(c.stream));
-        for (double* p : {w.L, w.Y, w.X, w.Dinv, w.d, w.z, w.scal}) if (p) FADB_CUDA(cudaFree(p));
-        const size_t nb = (n + DB - 1) / DB;
+        for (double* p : {w.L, w.Y, w.X, w.d, w.z, w.scal, w.diag}) if (p) FADB_CUDA(cudaFree(p));
         FADB_CUDA(cudaMalloc(&w.L, n * n * sizeof(double)));
         FADB_CUDA(cudaMalloc(&w.Y, n * n * sizeof(double)));
         FADB_CUDA(cudaMalloc(&w.X, n * n * sizeof(double)));
-        FADB_CUDA(cudaMalloc(&w.Dinv, nb * DB * DB * sizeof(double)));
         FADB_CUDA(cudaMalloc(&w.d, n * sizeof(double)));
         FADB_CUDA(cudaMalloc(&w.z, n * sizeof(double)));
+        FADB_CUDA(cudaMalloc(&w.diag, n * sizeof(double)));
         FADB_CUDA(cudaMalloc(&w.scal, 8 * sizeof(double)));
+        FADB_CUDA(cudaFuncSetAttribute(dn_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
         w.cap = n;
     }
     *out = &w;
@@ -398,6 +488,7 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
         FADB_CUDA(cudaMemsetAsync(w->scal, 0, 8 * sizeof(double), st));
         dn_copy_lower<<<eb, 256, 0, st>>>(N, Sigma, w->L);
         c->launches++;
+        FADB_CUDA(cudaMemsetAsync(w->Y, 0, nn * sizeof(double), st));      // the factor is written into Y, lower part only
         // two-level right-looking Cholesky: 128-wide outer panels, 32-wide inner steps.  The inner
         // rank-32 update touches the rest of the outer panel only; the trailing matrix gets one
         // rank-128 update per outer panel.
@@ -405,35 +496,32 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
         for (int K0 = 0; K0 < N; K0 += OB) {
             const int W = std::min(OB, N - K0), Kend = K0 + W;
             for (int k0 = K0; k0 < Kend; k0 += DB) {
-                const int k = k0 / DB;
-                dn_potf2<<<1, 32, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB, w->scal);
+                const int m = N - k0 - DB, pc = Kend - (k0 + DB);
+                const int grid = m > 0 ? (m + CS_ROWS - 1) / CS_ROWS : 1;
+                dn_chol_step<<<grid, 256, sizeof(CholSmem), st>>>(N, w->L, w->Y, w->diag, k0, m > 0 ? pc : 0, w->scal);
                 c->launches++;
-                const int m = N - k0 - DB;
-                if (m <= 0) continue;
-                dn_trsm_panel<<<(m + 63) / 64, 256, 0, st>>>(N, w->L, k0, w->Dinv + (size_t)k * DB * DB);
-                c->launches++;
-                const int pc = Kend - (k0 + DB);             // columns of the outer panel still to update
-                if (pc > 0) {
-                    const double* P = w->L + (k0 + DB) + (size_t)k0 * N;
-                    double* Ct = w->L + (k0 + DB) + (size_t)(k0 + DB) * N;
-                    gemm<false, true>(*c, m, pc, DB, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);
-                }
             }
             const int m = N - Kend;
             if (m > 0) {
-                const double* P = w->L + Kend + (size_t)K0 * N;
+                const double* P = w->Y + Kend + (size_t)K0 * N;
                 double* Ct = w->L + Kend + (size_t)Kend * N;
                 gemm<false, true>(*c, m, m, W, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);      // trailing -= P P^T (lower)
             }
         }
-        // inverse: Y <- L^{-1} level by level up the halving tree, X <- Y^T Y (lower tiles, K from the diagonal)
-        FADB_CUDA(cudaMemcpyAsync(w->Y, w->L, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        dn_place_dinv<<<nb, 256, 0, st>>>(N, nb, w->Dinv, w->Y);
+        // inverse, in place: Y <- Y^{-1} level by level up the halving tree, X <- Y^T Y (lower tiles, K from the diagonal)
+        dn_tile_inverse<<<nb, 32, 0, st>>>(N, w->Y);
         c->launches++;
         for (const TrLevel& lv : tp->levels) {
-            dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
-            dn_trtri_level<<<grid, dim3(16, 16), 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-            dn_trtri_level<<<grid, dim3(16, 16), 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            const long long t128 = (long long)((lv.max_n2 + 127) / 128) * ((lv.max_n1 + 127) / 128) * lv.count;
+            if (big_tiles(*c, t128)) {
+                dim3 grid((lv.max_n2 + 127) / 128, (lv.max_n1 + 127) / 128, lv.count);
+                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            } else {
+                dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
+                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            }
             c->launches += 2;
         }
         gemm<true, false>(*c, N, N, N, 1.0, w->Y, N, w->Y, N, 0.0, w->X, N, 3, 1);
@@ -441,7 +529,7 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
         c->launches++;
     }
     dn_gemv<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, w->X, x, mu, mu_vec, w->d, w->z);
-    dn_finish<<<1, 1024, 0, st>>>(N, w->L, w->d, w->z, w->scal, seed, ovw, x_adj, mu_adj, mu_vec, dev_value);
+    dn_finish<<<1, 1024, 0, st>>>(N, w->diag, w->d, w->z, w->scal, seed, ovw, x_adj, mu_adj, mu_vec, dev_value);
     c->launches += 2;
     if (Sigma_adj && seed != 0.0) {
         dn_sigma_adj<<<eb, 256, 0, st>>>(N, w->X, w->z, w->scal, seed, ovw, Sigma_adj);
