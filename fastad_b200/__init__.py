@@ -57,6 +57,10 @@ SIGNATURES = {
     "fadb_normal_lpdf_finish": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_normal_dense": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_normal_dense_async": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _i, _vp]),
+    "fadb_det": (_i, [_sz, _vp, _vp, _d, _u, _i, _i, _dp]),
+    "fadb_det_async": (_i, [_sz, _vp, _vp, _d, _u, _i, _i, _i, _vp]),
+    "fadb_wishart": (_i, [_sz, _vp, _vp, _d, _vp, _vp, _d, _u, _dp]),
+    "fadb_wishart_async": (_i, [_sz, _vp, _vp, _d, _vp, _vp, _d, _u, _i, _vp]),
     "fadb_logpdf": (_i, [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_logpdf_async": (_i, [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp]),
     "fadb_linreg_partial": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
@@ -211,6 +215,27 @@ def normal_dense(x, mu, Sigma, x_adj=None, mu_adj=None, Sigma_adj=None, seed=1.0
     v = C.c_double()
     check(lib().fadb_normal_dense(x.numel(), _ptr(x), _ptr(mu), 1 if mu.numel() > 1 else 0, _ptr(Sigma), _ptr(x_adj),
                                   _ptr(mu_adj), _ptr(Sigma_adj), seed, flags, C.byref(v)))
+    return v.value
+
+
+DET_POLICY = dict(fullpivlu=0, ldlt=1, llt=2)
+
+
+def det(A, A_adj=None, seed=1.0, policy="fullpivlu", log=False, flags=0):
+    """det / log_det of the (n, n) column-major matrix A; A_adj += seed * [det] * A^-T."""
+    _chk_f64(A, A_adj)
+    n = int(round(A.numel() ** 0.5))
+    v = C.c_double()
+    check(lib().fadb_det(n, _ptr(A), _ptr(A_adj), seed, flags, DET_POLICY[policy], 1 if log else 0, C.byref(v)))
+    return v.value
+
+
+def wishart(X, V, df, X_adj=None, V_adj=None, seed=1.0, flags=0):
+    """wishart_adj_log_pdf(X, V, df) for (p, p) column-major X, V."""
+    _chk_f64(X, V, X_adj, V_adj)
+    p = int(round(X.numel() ** 0.5))
+    v = C.c_double()
+    check(lib().fadb_wishart(p, _ptr(X), _ptr(V), float(df), _ptr(X_adj), _ptr(V_adj), seed, flags, C.byref(v)))
     return v.value
 
 

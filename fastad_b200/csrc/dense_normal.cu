@@ -458,6 +458,308 @@ static int ensure_dws(Context& c, size_t n, DenseWs** out)
     return FADB_OK;
 }
 
+// Cholesky of the LOWER triangle of Sigma, then its explicit inverse: on return w->diag = L_ii,
+// w->X = Sigma^{-1} (full, symmetric), w->scal[0] != 0 if Sigma is not positive definite.
+static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const double* Sigma)
+{
+    const int nb = (N + DB - 1) / DB;
+    const size_t nn = (size_t)N * N;
+    const int eb = (int)((nn + 255) / 256);
+    cudaStream_t st = c->stream;
+    FADB_CUDA(cudaMemsetAsync(w->scal, 0, 8 * sizeof(double), st));
+    dn_copy_lower<<<eb, 256, 0, st>>>(N, Sigma, w->L);
+    c->launches++;
+    FADB_CUDA(cudaMemsetAsync(w->Y, 0, nn * sizeof(double), st));      // the factor is written into Y, lower part only
+    // two-level right-looking Cholesky: 128-wide outer panels, 32-wide inner steps.  The inner
+    // rank-32 update touches the rest of the outer panel only; the trailing matrix gets one
+    // rank-128 update per outer panel.
+    constexpr int OB = 128;
+    for (int K0 = 0; K0 < N; K0 += OB) {
+        const int W = std::min(OB, N - K0), Kend = K0 + W;
+        for (int k0 = K0; k0 < Kend; k0 += DB) {
+            const int m = N - k0 - DB, pc = Kend - (k0 + DB);
+            const int grid = m > 0 ? (m + CS_ROWS - 1) / CS_ROWS : 1;
+            dn_chol_step<<<grid, 256, sizeof(CholSmem), st>>>(N, w->L, w->Y, w->diag, k0, m > 0 ? pc : 0, w->scal);
+            c->launches++;
+        }
+        const int m = N - Kend;
+        if (m > 0) {
+            const double* P = w->Y + Kend + (size_t)K0 * N;
+            double* Ct = w->L + Kend + (size_t)Kend * N;
+            gemm<false, true>(*c, m, m, W, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);      // trailing -= P P^T (lower)
+        }
+    }
+    // inverse, in place: Y <- Y^{-1} level by level up the halving tree, X <- Y^T Y (lower tiles, K from the diagonal)
+    dn_tile_inverse<<<nb, 32, 0, st>>>(N, w->Y);
+    c->launches++;
+    for (const TrLevel& lv : tp->levels) {
+        const long long t128 = (long long)((lv.max_n2 + 127) / 128) * ((lv.max_n1 + 127) / 128) * lv.count;
+        if (big_tiles(*c, t128)) {
+            dim3 grid((lv.max_n2 + 127) / 128, (lv.max_n1 + 127) / 128, lv.count);
+            dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+            dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+        } else {
+            dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
+            dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+            dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+        }
+        c->launches += 2;
+    }
+    gemm<true, false>(*c, N, N, N, 1.0, w->Y, N, w->Y, N, 0.0, w->X, N, 3, 1);
+    dn_symmetrize<<<eb, 256, 0, st>>>(N, w->X);
+    c->launches++;
+    return FADB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// det / log_det (reverse/core/det.hpp:25-92, log_det.hpp) and wishart_adj_log_pdf
+// (reverse/stat/wishart.hpp:92-231) on the same machinery.
+//  * DetLLT / LogDetLLT (det.hpp:170-202): the Cholesky pipeline above; det = (prod L_ii)^2,
+//    log_det = 2 sum log L_ii (the reference's log(prod) overflows for large n), inverse = X.
+//  * DetFullPivLU (the default) and DetLDLT (det.hpp:97-166): a general matrix.  Determinant and
+//    inverse come from an in-place Gauss-Jordan elimination with PARTIAL pivoting, two launches
+//    per column (pivot search + row swap + scaling by one CTA, then a rank-1 update across the
+//    GPU).  Complete pivoting / symmetric pivoting would serialise a full-matrix search per step;
+//    the value and inverse agree with Eigen's to rounding, and the validity rules of the policies
+//    (FullPivLU::isInvertible's epsilon * n * max-pivot threshold; LDLT: det != 0) are applied to
+//    these pivots.  This path is simple rather than fast (2n launches).
+// stats[0] invalid flag, [1] prod of pivots (signed), [2] sum log|pivot|, [3] min|pivot|, [4] max|pivot|
+__global__ void __launch_bounds__(1024)
+gj_pivot_kernel(int n, double* W, int k, double* rowbuf, double* colbuf, int* perm, double* stats)
+{
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    __shared__ int s_p;
+    __shared__ double s_piv;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + t; i < n; i += blockDim.x) {
+        const double a = fabs(W[i + (size_t)k * n]);
+        if (a > best) { best = a; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sval[wid] = best; sidx[wid] = bi; }
+    __syncthreads();
+    if (t == 0) {
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2)
+            if (sval[w2] > best || (sval[w2] == best && sidx[w2] < bi)) { best = sval[w2]; bi = sidx[w2]; }
+        if (!(best >= 0)) bi = k;                        // NaN column: keep the row, the flag is raised below
+        const double piv = W[bi + (size_t)k * n];
+        s_p = bi; s_piv = piv;
+        perm[k] = bi;
+        const double ap = fabs(piv);
+        if (k == 0) { stats[1] = 1.0; stats[2] = 0.0; stats[3] = ap; stats[4] = ap; }
+        stats[1] *= (bi != k) ? -piv : piv;
+        stats[2] += log(ap);
+        stats[3] = fmin(stats[3], ap);
+        stats[4] = fmax(stats[4], ap);
+        if (!(ap > 0)) stats[0] = 1.0;
+    }
+    __syncthreads();
+    const int p = s_p;
+    const double rinv = 1.0 / s_piv;
+    for (int j = t; j < n; j += blockDim.x) {            // swap rows k and p, scale the pivot row
+        const double a = W[p + (size_t)j * n], b = W[k + (size_t)j * n];
+        if (p != k) W[p + (size_t)j * n] = b;
+        const double r = (j == k) ? rinv : a * rinv;
+        W[k + (size_t)j * n] = r;
+        rowbuf[j] = r;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) {            // multipliers; column k of the inverse-in-progress
+        if (i == k) { colbuf[i] = 0.0; continue; }
+        const double f = W[i + (size_t)k * n];
+        colbuf[i] = f;
+        W[i + (size_t)k * n] = -f * rinv;
+    }
+}
+
+__global__ void gj_update_kernel(int n, double* W, int k, const double* __restrict__ rowbuf, const double* __restrict__ colbuf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double f = colbuf[i];
+    const int j0 = blockIdx.y * 16;
+#pragma unroll 4
+    for (int j = j0; j < min(n, j0 + 16); ++j)
+        if (j != k) W[i + (size_t)j * n] = fma(-f, rowbuf[j], W[i + (size_t)j * n]);
+}
+
+// the row swaps computed (P A)^-1 = A^-1 P^-1: undo them on the columns, last swap first
+__global__ void __launch_bounds__(1024)
+gj_colmap_kernel(int n, const int* __restrict__ perm, int* idx)
+{
+    extern __shared__ int sidx_dyn[];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sidx_dyn[j] = j;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int k = n - 1; k >= 0; --k) {
+            const int p = perm[k];
+            const int a = sidx_dyn[k]; sidx_dyn[k] = sidx_dyn[p]; sidx_dyn[p] = a;
+        }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) idx[j] = sidx_dyn[j];
+}
+__global__ void gj_gather_kernel(int n, const double* __restrict__ W, const int* __restrict__ idx, double* Out)
+{
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    const int i = (int)(e % n), j = (int)(e / n);
+    Out[e] = W[i + (size_t)idx[j] * n];
+}
+
+// value of det / log_det.  policy 2 (LLT): from the Cholesky diagonal; else from the elimination stats.
+// out[0] = value, out[1] = 1 if the decomposition is valid (det.hpp:58 `decomp_.valid()`)
+__global__ void __launch_bounds__(1024)
+det_value_kernel(int n, int policy, int take_log, const double* __restrict__ diag, const double* __restrict__ stats, double* out)
+{
+    __shared__ double sm[32 * 2];
+    if (policy == 2) {
+        double acc[2] = {0.0, 0.0};                      // sum log L_ii ; (product handled below)
+        double prod = 1.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { acc[0] += log(diag[i]); prod *= diag[i]; }
+        for (int o = 16; o > 0; o >>= 1) prod *= __shfl_down_sync(0xffffffffu, prod, o);
+        __shared__ double sp[32];
+        if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = prod;
+        block_sum<2>(acc, sm);
+        if (threadIdx.x == 0) {
+            double pr = 1.0;
+            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) pr *= sp[w2];
+            const bool ok = stats[0] == 0.0;
+            out[0] = !ok ? NAN : (take_log ? 2.0 * acc[0] : pr * pr);
+            out[1] = ok ? 1.0 : 0.0;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const double det = stats[1], la = stats[2];
+        const double v = take_log ? la : det;
+        bool ok = stats[0] == 0.0;
+        if (policy == 0) ok = ok && stats[3] > 2.220446049250313e-16 * (double)n * stats[4];   // FullPivLU::isInvertible
+        else ok = ok && (take_log ? isfinite(la) : det != 0.0);                               // det.hpp:143, log_det.hpp:143
+        out[0] = (stats[0] != 0.0 && !take_log) ? 0.0 : (stats[0] != 0.0 ? -INFINITY : v);
+        out[1] = ok ? 1.0 : 0.0;
+    }
+}
+
+// A_adj += f * inv^T, f = seed (log_det) or seed * det (det.hpp:61-62, log_det.hpp:61-62)
+__global__ void det_adj_kernel(int n, const double* __restrict__ inv, const double* __restrict__ val, int take_log, double seed,
+                               int overwrite, double* A_adj)
+{
+    if (val[1] == 0.0) return;
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    const int i = (int)(e % n), j = (int)(e / n);
+    const double f = take_log ? seed : seed * val[0];
+    const double g = f * inv[j + (size_t)i * n];
+    A_adj[e] = overwrite ? g : A_adj[e] + g;
+}
+
+// wishart: s[0] = log det L_v, s[1] = log det L_x, s[2] = invalid flag
+__global__ void __launch_bounds__(1024)
+ws_logdet_kernel(int n, const double* __restrict__ diag, const double* __restrict__ flag, double* s, int slot)
+{
+    __shared__ double sm[32];
+    double acc[1] = {0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc[0] += log(diag[i]);
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) {
+        s[slot] = acc[0];
+        if (slot == 0) s[2] = 0.0;
+        if (flag[0] != 0.0) s[2] = 1.0;
+    }
+}
+__global__ void __launch_bounds__(1024)
+ws_value_kernel(int p, double df, const double* __restrict__ G1, double* s, double* out)
+{
+    __shared__ double sm[32];
+    double acc[1] = {0.0};
+    for (int i = threadIdx.x; i < p; i += blockDim.x) acc[0] += G1[i + (size_t)i * p];
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) {
+        const bool ok = s[2] == 0.0 && (df + 1.0 > (double)p);                      // wishart.hpp:203-207
+        if (!ok) s[2] = 1.0;
+        out[0] = ok ? (df - (double)p - 1.0) * s[1] - 0.5 * acc[0] - df * s[0] : -INFINITY;   // wishart.hpp:157-165
+    }
+}
+__global__ void ws_adj_kernel(int p, double df, double seed, int overwrite, const double* __restrict__ s,
+                              const double* __restrict__ Xinv, const double* __restrict__ Vinv, const double* __restrict__ G2,
+                              double* X_adj, double* V_adj)
+{
+    if (s[2] != 0.0) return;                                                        // wishart.hpp:170
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= (size_t)p * p) return;
+    const double pd = (double)p;
+    if (V_adj) {
+        const double g = (0.5 * seed) * (G2[e] - df * Vinv[e]);
+        V_adj[e] = overwrite ? g : V_adj[e] + g;
+    }
+    if (X_adj) {
+        const double g = (0.5 * seed) * ((df - pd - 1.0) * Xinv[e] - Vinv[e]);
+        X_adj[e] = overwrite ? g : X_adj[e] + g;
+    }
+}
+
+struct WishartWs { double *Vinv = nullptr, *Xinv = nullptr, *G1 = nullptr, *G2 = nullptr, *s = nullptr; size_t cap = 0; };
+static WishartWs g_wws[kMaxDevices];
+struct GjWs { int *perm = nullptr, *idx = nullptr; double* val = nullptr; size_t cap = 0; };
+static GjWs g_gj[kMaxDevices];
+
+static int ensure_gj(Context& c, size_t n, GjWs** out)
+{
+    GjWs& g = g_gj[c.device];
+    if (g.cap < n) {
+        FADB_CUDA(cudaStreamSynchronize(c.stream));
+        if (g.perm) FADB_CUDA(cudaFree(g.perm));
+        if (g.idx) FADB_CUDA(cudaFree(g.idx));
+        FADB_CUDA(cudaMalloc(&g.perm, n * sizeof(int)));
+        FADB_CUDA(cudaMalloc(&g.idx, n * sizeof(int)));
+        if (!g.val) FADB_CUDA(cudaMalloc(&g.val, 2 * sizeof(double)));
+        FADB_CUDA(cudaFuncSetAttribute(gj_colmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        g.cap = n;
+    }
+    *out = &g;
+    return FADB_OK;
+}
+static int ensure_wws(Context& c, size_t p, WishartWs** out)
+{
+    WishartWs& w = g_wws[c.device];
+    if (w.cap < p) {
+        FADB_CUDA(cudaStreamSynchronize(c.stream));
+        for (double* q : {w.Vinv, w.Xinv, w.G1, w.G2}) if (q) FADB_CUDA(cudaFree(q));
+        for (double** q : {&w.Vinv, &w.Xinv, &w.G1, &w.G2}) FADB_CUDA(cudaMalloc(q, p * p * sizeof(double)));
+        if (!w.s) FADB_CUDA(cudaMalloc(&w.s, 4 * sizeof(double)));
+        w.cap = p;
+    }
+    *out = &w;
+    return FADB_OK;
+}
+
+// general inverse + pivot statistics by Gauss-Jordan: w->X = A^-1, w->scal = stats
+static int gj_inverse(Context* c, DenseWs* w, GjWs* g, int N, const double* A)
+{
+    const size_t nn = (size_t)N * N;
+    cudaStream_t st = c->stream;
+    FADB_CUDA(cudaMemsetAsync(w->scal, 0, 8 * sizeof(double), st));
+    FADB_CUDA(cudaMemcpyAsync(w->L, A, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    dim3 ugrid((N + 127) / 128, (N + 15) / 16);
+    for (int k = 0; k < N; ++k) {
+        gj_pivot_kernel<<<1, 1024, 0, st>>>(N, w->L, k, w->d, w->z, g->perm, w->scal);
+        gj_update_kernel<<<ugrid, 128, 0, st>>>(N, w->L, k, w->d, w->z);
+        c->launches += 2;
+    }
+    gj_colmap_kernel<<<1, 1024, (size_t)N * sizeof(int), st>>>(N, g->perm, g->idx);
+    gj_gather_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(N, w->L, g->idx, w->X);
+    c->launches += 2;
+    return FADB_OK;
+}
+
 }  // namespace fadb
 
 using namespace fadb;
@@ -485,48 +787,8 @@ extern "C" int fadb_normal_dense_async(size_t n, const double* x, const double* 
     const int eb = (int)((nn + 255) / 256);
     cudaStream_t st = c->stream;
     if (factor) {
-        FADB_CUDA(cudaMemsetAsync(w->scal, 0, 8 * sizeof(double), st));
-        dn_copy_lower<<<eb, 256, 0, st>>>(N, Sigma, w->L);
-        c->launches++;
-        FADB_CUDA(cudaMemsetAsync(w->Y, 0, nn * sizeof(double), st));      // the factor is written into Y, lower part only
-        // two-level right-looking Cholesky: 128-wide outer panels, 32-wide inner steps.  The inner
-        // rank-32 update touches the rest of the outer panel only; the trailing matrix gets one
-        // rank-128 update per outer panel.
-        constexpr int OB = 128;
-        for (int K0 = 0; K0 < N; K0 += OB) {
-            const int W = std::min(OB, N - K0), Kend = K0 + W;
-            for (int k0 = K0; k0 < Kend; k0 += DB) {
-                const int m = N - k0 - DB, pc = Kend - (k0 + DB);
-                const int grid = m > 0 ? (m + CS_ROWS - 1) / CS_ROWS : 1;
-                dn_chol_step<<<grid, 256, sizeof(CholSmem), st>>>(N, w->L, w->Y, w->diag, k0, m > 0 ? pc : 0, w->scal);
-                c->launches++;
-            }
-            const int m = N - Kend;
-            if (m > 0) {
-                const double* P = w->Y + Kend + (size_t)K0 * N;
-                double* Ct = w->L + Kend + (size_t)Kend * N;
-                gemm<false, true>(*c, m, m, W, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);      // trailing -= P P^T (lower)
-            }
-        }
-        // inverse, in place: Y <- Y^{-1} level by level up the halving tree, X <- Y^T Y (lower tiles, K from the diagonal)
-        dn_tile_inverse<<<nb, 32, 0, st>>>(N, w->Y);
-        c->launches++;
-        for (const TrLevel& lv : tp->levels) {
-            const long long t128 = (long long)((lv.max_n2 + 127) / 128) * ((lv.max_n1 + 127) / 128) * lv.count;
-            if (big_tiles(*c, t128)) {
-                dim3 grid((lv.max_n2 + 127) / 128, (lv.max_n1 + 127) / 128, lv.count);
-                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
-            } else {
-                dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
-                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
-            }
-            c->launches += 2;
-        }
-        gemm<true, false>(*c, N, N, N, 1.0, w->Y, N, w->Y, N, 0.0, w->X, N, 3, 1);
-        dn_symmetrize<<<eb, 256, 0, st>>>(N, w->X);
-        c->launches++;
+        rc = spd_factor_inverse(c, w, tp, N, Sigma);
+        if (rc) return rc;
     }
     dn_gemv<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, w->X, x, mu, mu_vec, w->d, w->z);
     dn_finish<<<1, 1024, 0, st>>>(N, w->diag, w->d, w->z, w->scal, seed, ovw, x_adj, mu_adj, mu_vec, dev_value);
@@ -553,6 +815,123 @@ extern "C" int fadb_normal_dense(size_t n, const double* x, const double* mu, in
         FADB_CUDA(cudaMemcpyAsync(c->host_scalars + 5, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         FADB_CUDA(cudaStreamSynchronize(c->stream));
         *host_value = c->host_scalars[5];
+    }
+    return FADB_OK;
+}
+
+// det / log_det of a square matrix and its adjoint A_adj += seed * [det] * A^{-T}.  policy:
+// FADB_DET_FULLPIVLU | FADB_DET_LDLT | FADB_DET_LLT.  factor = 0 reuses the decomposition of the
+// previous call on this device (backward pass after a forward-only evaluation).
+extern "C" int fadb_det_async(size_t n, const double* A, double* A_adj, double seed, unsigned flags, int policy, int take_log,
+                              int factor, double* dev_value)
+{
+    FADB_REQUIRE(n >= 1 && n <= 46340, "fadb_det: n out of range");
+    FADB_REQUIRE(A && dev_value, "fadb_det: null pointer");
+    FADB_REQUIRE(policy >= 0 && policy <= 2, "fadb_det: unknown decomposition policy");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    DenseWs* w;
+    if ((rc = ensure_dws(*c, n, &w))) return rc;
+    GjWs* g;
+    if ((rc = ensure_gj(*c, n, &g))) return rc;
+    const int N = (int)n;
+    cudaStream_t st = c->stream;
+    if (factor) {
+        if (policy == 2) {
+            TrPlan* tp;
+            if ((rc = ensure_trplan(*c, n, &tp))) return rc;
+            if ((rc = spd_factor_inverse(c, w, tp, N, A))) return rc;
+        } else {
+            if ((rc = gj_inverse(c, w, g, N, A))) return rc;
+        }
+        det_value_kernel<<<1, 1024, 0, st>>>(N, policy, take_log, w->diag, w->scal, g->val);
+        c->launches++;
+    }
+    FADB_CUDA(cudaMemcpyAsync(dev_value, g->val, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (A_adj && seed != 0.0) {
+        const size_t nn = n * n;
+        det_adj_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(N, w->X, g->val, take_log, seed,
+                                                                      (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, A_adj);
+        c->launches++;
+    }
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+extern "C" int fadb_det(size_t n, const double* A, double* A_adj, double seed, unsigned flags, int policy, int take_log,
+                        double* host_value)
+{
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    double* dval = c->scalars + 33;
+    rc = fadb_det_async(n, A, A_adj, seed, flags, policy, take_log, 1, dval);
+    if (rc) return rc;
+    if (host_value) {
+        FADB_CUDA(cudaMemcpyAsync(c->host_scalars + 6, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FADB_CUDA(cudaStreamSynchronize(c->stream));
+        *host_value = c->host_scalars[6];
+    }
+    return FADB_OK;
+}
+
+// wishart_adj_log_pdf(X, V, df) (reverse/stat/wishart.hpp:140-214): Cholesky + inverse of V and X (lower
+// triangles), value (df-p-1) log det L_x - 0.5 tr(X V^-1) - df log det L_v, adjoints
+// X_adj += 0.5 seed ((df-p-1) X^-1 - V^-1), V_adj += 0.5 seed (V^-1 X V^-1 - df V^-1); -inf and no adjoints
+// when either matrix is not positive definite or df + 1 <= p.  X V^-1 uses the FULL matrix X, as the reference.
+extern "C" int fadb_wishart_async(size_t p, const double* X, const double* V, double df, double* X_adj, double* V_adj,
+                                  double seed, unsigned flags, int factor, double* dev_value)
+{
+    FADB_REQUIRE(p >= 1 && p <= 46340, "fadb_wishart: p out of range");
+    FADB_REQUIRE(X && V && dev_value, "fadb_wishart: null pointer");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    DenseWs* w;
+    if ((rc = ensure_dws(*c, p, &w))) return rc;
+    WishartWs* ww;
+    if ((rc = ensure_wws(*c, p, &ww))) return rc;
+    TrPlan* tp;
+    if ((rc = ensure_trplan(*c, p, &tp))) return rc;
+    const int P = (int)p;
+    const size_t pp = p * p;
+    cudaStream_t st = c->stream;
+    if (factor) {
+        if ((rc = spd_factor_inverse(c, w, tp, P, V))) return rc;
+        ws_logdet_kernel<<<1, 1024, 0, st>>>(P, w->diag, w->scal, ww->s, 0);
+        FADB_CUDA(cudaMemcpyAsync(ww->Vinv, w->X, pp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if ((rc = spd_factor_inverse(c, w, tp, P, X))) return rc;
+        ws_logdet_kernel<<<1, 1024, 0, st>>>(P, w->diag, w->scal, ww->s, 1);
+        FADB_CUDA(cudaMemcpyAsync(ww->Xinv, w->X, pp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        gemm<false, false>(*c, P, P, P, 1.0, X, P, ww->Vinv, P, 0.0, ww->G1, P, 0, 0);          // xv_inv_, wishart.hpp:197
+        ws_value_kernel<<<1, 1024, 0, st>>>(P, df, ww->G1, ww->s, ww->s + 3);
+        c->launches += 3;
+    }
+    FADB_CUDA(cudaMemcpyAsync(dev_value, ww->s + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((X_adj || V_adj) && seed != 0.0) {
+        if (V_adj) gemm<false, false>(*c, P, P, P, 1.0, ww->Vinv, P, ww->G1, P, 0.0, ww->G2, P, 0, 0);
+        ws_adj_kernel<<<(unsigned)((pp + 255) / 256), 256, 0, st>>>(P, df, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, ww->s,
+                                                                     ww->Xinv, ww->Vinv, ww->G2, X_adj, V_adj);
+        c->launches++;
+    }
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+extern "C" int fadb_wishart(size_t p, const double* X, const double* V, double df, double* X_adj, double* V_adj, double seed,
+                            unsigned flags, double* host_value)
+{
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    double* dval = c->scalars + 34;
+    rc = fadb_wishart_async(p, X, V, df, X_adj, V_adj, seed, flags, 1, dval);
+    if (rc) return rc;
+    if (host_value) {
+        FADB_CUDA(cudaMemcpyAsync(c->host_scalars + 7, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FADB_CUDA(cudaStreamSynchronize(c->stream));
+        *host_value = c->host_scalars[7];
     }
     return FADB_OK;
 }

@@ -159,6 +159,23 @@ int fadb_normal_dense_async(size_t n, const double* x, const double* mu, int mu_
                             double* x_adj, double* mu_adj, double* Sigma_adj, double seed, unsigned flags,
                             int factor, double* dev_value);
 
+/* ------------------------------------------------------------------ det / log_det / wishart
+ * autodiff of ad::det<Policy>(A) / ad::log_det<Policy>(A) (reverse/core/det.hpp:25-92, 211-231;
+ * log_det.hpp): value det A (resp. log|det A|), A_adj += seed * det * A^{-T} (resp. seed * A^{-T});
+ * an invalid decomposition (singular / not positive definite) leaves the adjoint untouched
+ * (det.hpp:58-60).  policy selects the reference's decomposition functor (det.hpp:97-202). */
+enum { FADB_DET_FULLPIVLU = 0, FADB_DET_LDLT = 1, FADB_DET_LLT = 2 };
+int fadb_det(size_t n, const double* A, double* A_adj, double seed, unsigned flags, int policy,
+             int take_log, double* host_value);
+int fadb_det_async(size_t n, const double* A, double* A_adj, double seed, unsigned flags, int policy,
+                   int take_log, int factor, double* dev_value);
+/* autodiff of ad::wishart_adj_log_pdf(X, V, n) (reverse/stat/wishart.hpp:92-231, builder :242-257):
+ * X, V p x p column-major (lower triangles factored, X V^-1 formed from the full X), df constant */
+int fadb_wishart(size_t p, const double* X, const double* V, double df, double* X_adj, double* V_adj,
+                 double seed, unsigned flags, double* host_value);
+int fadb_wishart_async(size_t p, const double* X, const double* V, double df, double* X_adj,
+                       double* V_adj, double seed, unsigned flags, int factor, double* dev_value);
+
 /* ------------------------------------------------------------------ other diagonal log-pdfs
  * autodiff of ad::cauchy_adj_log_pdf(x, loc, scale) / ad::uniform_adj_log_pdf(x, min, max) /
  * ad::bernoulli_adj_log_pdf(x, p) with leaf operands (reverse/stat/cauchy.hpp:102-451,

@@ -21,7 +21,7 @@
 namespace {
 
 enum Kind { K_VAR, K_CONST, K_UNARY, K_BINARY, K_POW, K_SUM, K_SUM_ITER, K_PROD,
-            K_PROD_ITER, K_DOT, K_NORMAL, K_EQ, K_GLUE, K_NORM, K_TRANSPOSE, K_IF_ELSE, K_OPEQ, K_LOGPDF };
+            K_PROD_ITER, K_DOT, K_NORMAL, K_EQ, K_GLUE, K_NORM, K_TRANSPOSE, K_IF_ELSE, K_OPEQ, K_LOGPDF, K_DET, K_WISHART };
 
 /* A seed is either a scalar (broadcast) or an array, as in the reference where the
  * seed type is a template parameter (var_view.hpp:91-94). */
@@ -167,7 +167,8 @@ struct orc_graph {
         case K_UNARY: case K_POW: case K_DOT: case K_SUM_ITER: case K_PROD_ITER: case K_TRANSPOSE:
         case K_OPEQ:   /* OpEqNode's cache_ holds the previous lhs value + adjoint, eq.hpp:289-292 */
             out[0] = n.size(); out[1] = n.size(); break;
-        case K_SUM: case K_NORMAL: case K_NORM: case K_LOGPDF: out[0] = n.size(); out[1] = 0; break; /* sum.hpp:196-199 */
+        case K_SUM: case K_NORMAL: case K_NORM: case K_LOGPDF: case K_DET: case K_WISHART:
+            out[0] = n.size(); out[1] = 0; break; /* sum.hpp:196-199, det.hpp:81-84, wishart.hpp single_bind_cache_size */
         case K_PROD: out[0] = n.size(); out[1] = nodes[n.ch[0]].size(); break; /* prod.hpp:236-239 */
         }
     }
@@ -235,6 +236,7 @@ struct orc_graph {
         single_size(id, s);
         n.val = v; v += s[0];
         if (n.kind == K_SUM || n.kind == K_NORMAL || n.kind == K_PROD || n.kind == K_NORM || n.kind == K_LOGPDF ||
+            n.kind == K_DET || n.kind == K_WISHART ||
             (n.kind == K_BINARY && is_comparison(n.op))) n.adj = nullptr;
         else { n.adj = a; a += n.size(); }
     }
@@ -384,6 +386,8 @@ struct orc_graph {
         }
         case K_NORMAL: return normal_feval(n);
         case K_LOGPDF: return logpdf_feval(n);
+        case K_DET: return det_feval(n);
+        case K_WISHART: return wishart_feval(n);
         case K_NORM: {                                   /* norm.hpp:47-51 */
             const double* x = feval(n.ch[0]);
             const size_t M = nodes[n.ch[0]].size();
@@ -415,6 +419,231 @@ struct orc_graph {
         }
         }
         return nullptr;
+    }
+
+
+    /* ---- decompositions behind det / log_det / wishart.  Eigen 3.3.7 (absent here) supplies
+     * FullPivLU, LDLT and LLT; these are plain-loop restatements of the same factorizations
+     * (same pivoting rules), not of Eigen's blocking, so results agree to rounding. ---- */
+    /* Eigen::LLT<Lower>: reads the lower triangle; returns false when a pivot is not positive.
+     * prodL = det(matrixL()); inv = llt.solve(I). */
+    static bool llt_decomp(size_t d, const double* A, double& prodL, std::vector<double>& inv)
+    {
+        std::vector<double> L(d * d, 0.);
+        for (size_t j = 0; j < d; ++j) {
+            double s = A[j + j * d];
+            for (size_t k = 0; k < j; ++k) s -= L[j + k * d] * L[j + k * d];
+            if (!(s > 0)) return false;
+            const double ljj = std::sqrt(s);
+            L[j + j * d] = ljj;
+            for (size_t i = j + 1; i < d; ++i) {
+                double t = A[i + j * d];
+                for (size_t k = 0; k < j; ++k) t -= L[i + k * d] * L[j + k * d];
+                L[i + j * d] = t / ljj;
+            }
+        }
+        prodL = 1;
+        for (size_t j = 0; j < d; ++j) prodL *= L[j + j * d];
+        inv.assign(d * d, 0.);
+        std::vector<double> y(d);
+        for (size_t c = 0; c < d; ++c) {
+            for (size_t i = 0; i < d; ++i) {
+                double t = (i == c) ? 1. : 0.;
+                for (size_t k = 0; k < i; ++k) t -= L[i + k * d] * y[k];
+                y[i] = t / L[i + i * d];
+            }
+            for (size_t ii = d; ii-- > 0;) {
+                double t = y[ii];
+                for (size_t k = ii + 1; k < d; ++k) t -= L[k + ii * d] * inv[k + c * d];
+                inv[ii + c * d] = t / L[ii + ii * d];
+            }
+        }
+        return true;
+    }
+    /* Eigen::FullPivLU: complete pivoting (largest |a_ij| of the trailing block, first hit in
+     * column-major order), determinant = sign * prod(diag U), isInvertible() = every pivot larger
+     * than epsilon * n * |max pivot|, inverse() = solve(I). */
+    static void fullpivlu_decomp(size_t d, const double* A, double& det, bool& invertible, std::vector<double>& inv)
+    {
+        std::vector<double> M(A, A + d * d);
+        std::vector<size_t> rp(d), cp(d);
+        for (size_t i = 0; i < d; ++i) rp[i] = cp[i] = i;
+        int sign = 1;
+        double maxpivot = 0;
+        size_t nonzero = d;
+        for (size_t k = 0; k < d; ++k) {
+            size_t br = k, bc = k;
+            double big = -1;
+            for (size_t j = k; j < d; ++j)
+                for (size_t i = k; i < d; ++i)
+                    if (std::fabs(M[i + j * d]) > big) { big = std::fabs(M[i + j * d]); br = i; bc = j; }
+            if (big == 0) { nonzero = k; break; }
+            if (big > maxpivot) maxpivot = big;
+            if (br != k) { for (size_t j = 0; j < d; ++j) std::swap(M[k + j * d], M[br + j * d]); std::swap(rp[k], rp[br]); sign = -sign; }
+            if (bc != k) { for (size_t i = 0; i < d; ++i) std::swap(M[i + k * d], M[i + bc * d]); std::swap(cp[k], cp[bc]); sign = -sign; }
+            for (size_t i = k + 1; i < d; ++i) M[i + k * d] /= M[k + k * d];
+            for (size_t j = k + 1; j < d; ++j)
+                for (size_t i = k + 1; i < d; ++i) M[i + j * d] -= M[i + k * d] * M[k + j * d];
+        }
+        det = sign;
+        for (size_t k = 0; k < d; ++k) det *= M[k + k * d];
+        const double thr = std::numeric_limits<double>::epsilon() * (double)d * maxpivot;
+        size_t rank = 0;
+        for (size_t k = 0; k < nonzero; ++k) rank += std::fabs(M[k + k * d]) > thr;
+        invertible = rank == d;
+        inv.assign(d * d, 0.);
+        if (!invertible) return;
+        std::vector<double> y(d);
+        for (size_t c = 0; c < d; ++c) {               /* P A Q = L U  =>  A^-1 e_c = Q U^-1 L^-1 P e_c */
+            for (size_t i = 0; i < d; ++i) y[i] = rp[i] == c ? 1. : 0.;
+            for (size_t i = 0; i < d; ++i)
+                for (size_t k = 0; k < i; ++k) y[i] -= M[i + k * d] * y[k];
+            for (size_t ii = d; ii-- > 0;) {
+                for (size_t k = ii + 1; k < d; ++k) y[ii] -= M[ii + k * d] * y[k];
+                y[ii] /= M[ii + ii * d];
+            }
+            for (size_t i = 0; i < d; ++i) inv[cp[i] + c * d] = y[i];
+        }
+    }
+    /* Eigen::LDLT<Lower>: reads the lower triangle, pivots on the largest |diagonal| entry;
+     * vectorD().prod() is the determinant; solve(I) = P^T L^-T D^-1 L^-1 P. */
+    static void ldlt_decomp(size_t d, const double* A, double& det, bool& success, std::vector<double>& inv)
+    {
+        std::vector<double> M(d * d);
+        for (size_t j = 0; j < d; ++j)
+            for (size_t i = 0; i < d; ++i) M[i + j * d] = i >= j ? A[i + j * d] : A[j + i * d];
+        std::vector<size_t> perm(d);
+        for (size_t i = 0; i < d; ++i) perm[i] = i;
+        success = true;
+        for (size_t k = 0; k < d; ++k) {
+            size_t p = k;
+            double big = -1;
+            for (size_t i = k; i < d; ++i)
+                if (std::fabs(M[i + i * d]) > big) { big = std::fabs(M[i + i * d]); p = i; }
+            if (p != k) {
+                for (size_t j = 0; j < d; ++j) std::swap(M[k + j * d], M[p + j * d]);
+                for (size_t i = 0; i < d; ++i) std::swap(M[i + k * d], M[i + p * d]);
+                std::swap(perm[k], perm[p]);
+            }
+            const double dk = M[k + k * d];
+            if (dk == 0) {
+                for (size_t i = k + 1; i < d; ++i) if (M[i + k * d] != 0) success = false;
+                continue;
+            }
+            for (size_t i = k + 1; i < d; ++i) M[i + k * d] /= dk;
+            for (size_t j = k + 1; j < d; ++j)
+                for (size_t i = j; i < d; ++i) M[i + j * d] -= M[i + k * d] * dk * M[j + k * d];
+            for (size_t j = k + 1; j < d; ++j)
+                for (size_t i = k + 1; i < j; ++i) M[i + j * d] = M[j + i * d];
+        }
+        det = 1;
+        for (size_t k = 0; k < d; ++k) det *= M[k + k * d];
+        inv.assign(d * d, 0.);
+        std::vector<double> y(d);
+        for (size_t c = 0; c < d; ++c) {
+            for (size_t i = 0; i < d; ++i) y[i] = perm[i] == c ? 1. : 0.;
+            for (size_t i = 0; i < d; ++i)
+                for (size_t k = 0; k < i; ++k) y[i] -= M[i + k * d] * y[k];
+            for (size_t i = 0; i < d; ++i) y[i] = M[i + i * d] != 0 ? y[i] / M[i + i * d] : 0.;
+            for (size_t ii = d; ii-- > 0;)
+                for (size_t k = ii + 1; k < d; ++k) y[ii] -= M[k + ii * d] * y[k];
+            for (size_t i = 0; i < d; ++i) inv[perm[i] + c * d] = y[i];
+        }
+    }
+
+    /* DetNode / LogDetNode, det.hpp:52-64, log_det.hpp:52-64; policies det.hpp:97-202.
+     * n.op = policy (0 FullPivLU, 1 LDLT, 2 LLT), n.pw = 1 for log_det; n.extra = inverse */
+    const double* det_feval(Node& n)
+    {
+        const Node& e = nodes[n.ch[0]];
+        const double* A = feval(n.ch[0]);
+        const size_t d = e.rows;
+        double det = 0;
+        if (n.op == 2) {
+            double prodL = 0;
+            n.pos_def = llt_decomp(d, A, prodL, n.extra);
+            if (!n.pos_def) prodL = std::numeric_limits<double>::quiet_NaN();     /* Eigen leaves garbage; flagged invalid */
+            n.val[0] = n.pw ? 2. * std::log(std::fabs(prodL)) : prodL * prodL;
+        } else if (n.op == 1) {
+            bool ok;
+            ldlt_decomp(d, A, det, ok, n.extra);
+            n.val[0] = n.pw ? std::log(std::fabs(det)) : det;
+            n.pos_def = ok && (n.pw ? std::isfinite(n.val[0]) : det != 0);
+        } else {
+            bool inv_ok;
+            fullpivlu_decomp(d, A, det, inv_ok, n.extra);
+            n.val[0] = n.pw ? std::log(std::fabs(det)) : det;
+            n.pos_def = inv_ok;
+        }
+        return n.val;
+    }
+    void det_beval(Node& n, double seed)
+    {
+        if (seed == 0 || !n.pos_def) return;
+        const size_t d = nodes[n.ch[0]].rows;
+        const double f = n.pw ? seed : seed * n.val[0];
+        n.tmp0.resize(d * d);
+        for (size_t j = 0; j < d; ++j)
+            for (size_t i = 0; i < d; ++i) n.tmp0[i + j * d] = f * n.extra[j + i * d];     /* inverse().transpose() */
+        beval(n.ch[0], Seed{n.tmp0.data(), 0});
+    }
+
+    /* WishartAdjLogPDFNode, wishart.hpp:140-214.  n.z_sq holds the (constant) degrees of freedom;
+     * n.extra = [x_inv | v_inv | xv_inv], log_sigma = log det L_x, x_mean = log det L_v. */
+    const double* wishart_feval(Node& n)
+    {
+        Node& xn = nodes[n.ch[0]];
+        Node& vn = nodes[n.ch[1]];
+        const double* X = feval(n.ch[0]);
+        const double* V = feval(n.ch[1]);
+        const size_t p = vn.rows, pp = p * p;
+        n.extra.resize(3 * pp);
+        std::vector<double> xi, vi;
+        double pl = 0;
+        bool v_ok = llt_decomp(p, V, pl, vi), x_ok = false;
+        if (v_ok) {
+            n.x_mean = std::log(pl);
+            std::copy(vi.begin(), vi.end(), n.extra.begin() + pp);
+            x_ok = llt_decomp(p, X, pl, xi);
+            if (x_ok) {
+                n.log_sigma = std::log(pl);
+                std::copy(xi.begin(), xi.end(), n.extra.begin());
+                for (size_t j = 0; j < p; ++j)
+                    for (size_t i = 0; i < p; ++i) {
+                        double acc = 0;
+                        for (size_t k = 0; k < p; ++k) acc += X[i + k * p] * vi[k + j * p];
+                        n.extra[2 * pp + i + j * p] = acc;
+                    }
+            }
+        }
+        (void)xn;
+        const double df = n.z_sq;
+        n.pos_def = v_ok && x_ok && (df + 1 > (double)p);
+        if (!n.pos_def) { n.val[0] = -std::numeric_limits<double>::infinity(); return n.val; }
+        double tr = 0;
+        for (size_t i = 0; i < p; ++i) tr += n.extra[2 * pp + i + i * p];
+        n.val[0] = (df - (double)p - 1.) * n.log_sigma - 0.5 * tr - df * n.x_mean;
+        return n.val;
+    }
+    void wishart_beval(Node& n, double seed)
+    {
+        if (seed == 0 || !n.pos_def) return;
+        const size_t p = nodes[n.ch[1]].rows, pp = p * p;
+        const double df = n.z_sq, pd = (double)p;
+        const double* xi = n.extra.data();
+        const double* vi = xi + pp;
+        const double* xv = vi + pp;
+        n.tmp0.resize(pp);
+        n.tmp1.resize(pp);
+        for (size_t j = 0; j < p; ++j)
+            for (size_t i = 0; i < p; ++i) {
+                double acc = 0;
+                for (size_t k = 0; k < p; ++k) acc += vi[i + k * p] * xv[k + j * p];
+                n.tmp1[i + j * p] = (0.5 * seed) * (acc - df * vi[i + j * p]);
+                n.tmp0[i + j * p] = (0.5 * seed) * ((df - pd - 1) * xi[i + j * p] - vi[i + j * p]);
+            }
+        beval(n.ch[1], Seed{n.tmp1.data(), 0});
+        beval(n.ch[0], Seed{n.tmp0.data(), 0});
     }
 
     /* ---- dense covariance: vsm / vvm, normal.hpp:581-773.  Eigen::LLT<Lower> reads the lower
@@ -681,6 +910,8 @@ struct orc_graph {
             return;
         case K_NORMAL: normal_beval(n, seed.at(0)); return;
         case K_LOGPDF: logpdf_beval(n, seed.at(0)); return;
+        case K_DET: det_beval(n, seed.at(0)); return;
+        case K_WISHART: wishart_beval(n, seed.at(0)); return;
         case K_NORM: {                                    /* norm.hpp:53-57 */
             Node& e = nodes[n.ch[0]];
             n.tmp0.resize(e.size());
@@ -1106,6 +1337,25 @@ int orc_logpdf(orc_graph* g, int dist, int a, int b, int c)
     Node n; n.kind = K_LOGPDF; n.op = dist;
     n.ch = {a, b};
     if (dist != ORC_BERNOULLI) n.ch.push_back(c);
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+
+int orc_det(orc_graph* g, int policy, int take_log, int child)
+{
+    const Node& c = g->nodes[child];
+    if (c.kind == K_CONST) {     /* det.hpp:222-227: constants fold through FullPivLU's determinant */
+        double det; bool ok; std::vector<double> inv;
+        orc_graph::fullpivlu_decomp(c.rows, c.val, det, ok, inv);
+        int id = make_const(g, ORC_SCL, 1, 1, {take_log ? std::log(std::fabs(det)) : det}); fix_const_ptrs(g); return id;
+    }
+    Node n; n.kind = K_DET; n.op = policy; n.pw = take_log; n.ch = {child};
+    int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
+}
+
+int orc_wishart(orc_graph* g, int x, int v, double df)
+{
+    Node n; n.kind = K_WISHART; n.z_sq = df; n.ch = {x, v};
     int id = g->add(std::move(n)); fix_const_ptrs(g); return id;
 }
 

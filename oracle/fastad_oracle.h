@@ -72,6 +72,12 @@ int orc_opeq(orc_graph*, int op, int var, int child);     /* OpEqNode, eq.hpp:19
 enum { ORC_CAUCHY = 0, ORC_UNIFORM = 1, ORC_BERNOULLI = 2 };
 int orc_logpdf(orc_graph*, int dist, int a, int b, int c);
 
+/* DetNode / LogDetNode (reverse/core/det.hpp:25-92, log_det.hpp): policy 0 FullPivLU (default),
+ * 1 LDLT, 2 LLT (det.hpp:97-202); take_log = 1 for log_det */
+int orc_det(orc_graph*, int policy, int take_log, int child);
+/* WishartAdjLogPDFNode (reverse/stat/wishart.hpp:92-231): x, v square mat, df a constant */
+int orc_wishart(orc_graph*, int x, int v, double df);
+
 /* ad::bind: size query + allocate + post-order bind. out2 = {#val, #adj} as SizePack */
 void orc_bind(orc_graph*, int root, size_t out2[2]);
 /* ad::evaluate / evaluate_adj / autodiff (eval.hpp:18-153). Return pointer to root value. */

@@ -81,3 +81,13 @@ def assert_double_eq(a, b, ulps=4, what=""):
     same = (a == b) | (np.isnan(a) & np.isnan(b))
     d = np.where(same, 0.0, ulp_diff(a, b))
     assert np.all(d <= ulps), f"{what}: max ulp diff {d.max()} at {int(d.argmax())}: {a[d.argmax()]!r} vs {b[d.argmax()]!r}"
+
+# ---- det / log_det fixtures, test/reverse/core/det_unittest.cpp:34-54 (log_det_unittest.cpp same), seed :15
+DET_SEED = 9.2313
+DET_FPLU = np.array([[2., 3, 1, 5], [3, 5, -1, 3], [-2, 3, 1, 0], [-1, -1, 2, 7]])
+DET_LLT = np.array([[8., 3, 1, 5], [3, 5, 1, 3], [1, 1, 1, 0], [5, 3, 0, 7]])
+# ---- wishart fixture, test/reverse/stat/wishart_unittest.cpp:37-55 (lower triangle set, then mirrored), n = 4
+WISHART_X = np.array([[10., 2, 3], [2, 10, 1], [3, 1, 10]])
+WISHART_V = np.array([[5., 1, 0], [1, 5, 1], [0, 1, 5]])
+WISHART_N = 4
+WISHART_VALUE = -12.55942947411780252764      # wishart_unittest.cpp:66 (ref/wishart_ref.py)

@@ -15,6 +15,7 @@ UNARY = dict(neg=0, sin=1, cos=2, tan=3, asin=4, acos=5, atan=6, exp=7, log=8, s
 BINARY = dict(add=0, sub=1, mul=2, div=3, lt=4, le=5, gt=6, ge=7, eq=8, ne=9, land=10, lor=11, mockb=100)
 
 DIST = dict(cauchy=0, uniform=1, bernoulli=2)
+DET_POLICY = dict(fullpivlu=0, ldlt=1, llt=2)
 _dp = C.POINTER(C.c_double)
 _lib = None
 
@@ -39,6 +40,7 @@ def lib(fast=False):
         "orc_normal": (i, [vp, i, i, i]), "orc_eq": (i, [vp, i, i]), "orc_glue": (i, [vp, i, i]),
         "orc_norm": (i, [vp, i]), "orc_transpose": (i, [vp, i]), "orc_if_else": (i, [vp, i, i, i]),
         "orc_opeq": (i, [vp, i, i, i]), "orc_logpdf": (i, [vp, i, i, i, i]),
+        "orc_det": (i, [vp, i, i, i]), "orc_wishart": (i, [vp, i, i, d]),
         "orc_bind": (None, [vp, i, C.POINTER(sz)]),
         "orc_feval": (_dp, [vp, i]), "orc_beval": (None, [vp, i, d, vp]),
         "orc_size": (sz, [vp, i]), "orc_is_const": (i, [vp, i]),
@@ -157,6 +159,12 @@ class OracleExpr:
 
     def logpdf(self, dist, a, b, c=-1):
         return self.L.orc_logpdf(self.g, DIST[dist], a, b, c)
+
+    def det(self, c, policy="fullpivlu", log=False):
+        return self.L.orc_det(self.g, DET_POLICY[policy], 1 if log else 0, c)
+
+    def wishart(self, x, v, df):
+        return self.L.orc_wishart(self.g, x, v, float(df))
 
     # ---- driver ----
     def bind(self, root):

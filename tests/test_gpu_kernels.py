@@ -387,6 +387,94 @@ def test_dense_normal_logdet_does_not_overflow(fb):
     assert rel(v, want) <= 1e-11
 
 
+# ------------------------------------------------------------------ det / log_det / wishart (8f row 3)
+def _colmajor(M):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(M.T)).cuda()
+
+
+@pytest.mark.parametrize("log", [False, True])
+@pytest.mark.parametrize("policy", ["fullpivlu", "ldlt", "llt"])
+def test_det_reference_goldens(fb, policy, log):
+    # det_unittest.cpp:57-155 / log_det_unittest.cpp:57-152 (exact determinants 153 and 65)
+    A = kats.DET_FPLU if policy == "fullpivlu" else kats.DET_LLT
+    exact = 153.0 if policy == "fullpivlu" else 65.0
+    Aa = zeros(16)
+    v = fb.det(_colmajor(A), Aa, seed=kats.DET_SEED, policy=policy, log=log)
+    assert_double_eq([v], [math.log(exact) if log else exact])
+    want = kats.DET_SEED * (1.0 if log else exact) * np.linalg.inv(A).T
+    assert np.abs(host(Aa).reshape(4, 4, order="F") - want).max() <= 3e-13
+    # adjoints accumulate
+    fb.det(_colmajor(A), Aa, seed=kats.DET_SEED, policy=policy, log=log)
+    assert np.abs(host(Aa).reshape(4, 4, order="F") - 2 * want).max() <= 6e-13
+
+
+@pytest.mark.parametrize("policy,n", [("fullpivlu", 1), ("fullpivlu", 5), ("fullpivlu", 67), ("fullpivlu", 300),
+                                      ("ldlt", 33), ("ldlt", 150), ("llt", 31), ("llt", 130), ("llt", 500)])
+def test_det_vs_oracle(fb, policy, n):
+    rng = np.random.default_rng(n)
+    if policy == "fullpivlu":
+        A = rng.uniform(-1, 1, (n, n)) + 0.5 * np.eye(n)
+    else:
+        Lo = np.tril(rng.uniform(-1, 1, (n, n)), -1) / np.sqrt(n) + 1.1 * np.eye(n)
+        A = Lo @ Lo.T
+    for log in (False, True):
+        e = O.OracleExpr()
+        a = e.var(A)
+        e.bind(e.det(a, policy, log))
+        ov = e.autodiff(0.7)[0]
+        Aa = zeros(n * n)
+        v = fb.det(_colmajor(A), Aa, seed=0.7, policy=policy, log=log)
+        assert rel(v, ov) <= 1e-10, (policy, n, log)
+        oa = e.adj(a)
+        np.testing.assert_allclose(host(Aa), oa, rtol=1e-7, atol=1e-10 * np.abs(oa).max())
+
+
+def test_det_invalid_leaves_adjoint_untouched(fb):
+    for policy, A in (("fullpivlu", np.array([[1., 2], [2, 4]])), ("llt", np.array([[1., 2], [2, 1]])),
+                      ("ldlt", np.zeros((2, 2)))):
+        Aa = zeros(4)
+        v = fb.det(_colmajor(A), Aa, seed=1.0, policy=policy)
+        assert np.all(host(Aa) == 0), policy
+        if policy != "llt":
+            assert v == 0.0
+
+
+def test_wishart_reference_goldens(fb):
+    # wishart_unittest.cpp:62-106
+    Xa, Va = zeros(9), zeros(9)
+    v = fb.wishart(_colmajor(kats.WISHART_X), _colmajor(kats.WISHART_V), kats.WISHART_N, Xa, Va)
+    assert_double_eq([v], [kats.WISHART_VALUE])
+    n, p = kats.WISHART_N, 3
+    vi = np.linalg.inv(kats.WISHART_V)
+    dX = 0.5 * ((n - p - 1) * np.linalg.inv(kats.WISHART_X) - vi)
+    dV = 0.5 * (vi @ kats.WISHART_X @ vi - n * vi)
+    assert np.abs(host(Xa).reshape(3, 3, order="F") - dX).max() <= 1e-15
+    assert np.abs(host(Va).reshape(3, 3, order="F") - dV).max() <= 1e-15
+    v = fb.wishart(_colmajor(kats.WISHART_X), zeros(9), kats.WISHART_N, Xa, Va)     # feval_invalid
+    assert v == -math.inf
+    assert np.abs(host(Xa).reshape(3, 3, order="F") - dX).max() <= 1e-15
+    assert fb.wishart(_colmajor(kats.WISHART_X), _colmajor(kats.WISHART_V), 2, Xa, Va) == -math.inf
+
+
+@pytest.mark.parametrize("p", [2, 40, 129, 400])
+def test_wishart_vs_oracle(fb, p):
+    rng = np.random.default_rng(p)
+    def spd():
+        Lo = np.tril(rng.uniform(-1, 1, (p, p)), -1) / np.sqrt(p) + 1.2 * np.eye(p)
+        return Lo @ Lo.T
+    X, V, df = spd(), spd(), p + 3
+    e = O.OracleExpr()
+    x, vv = e.var(X), e.var(V)
+    e.bind(e.wishart(x, vv, df))
+    ov = e.autodiff(1.3)[0]
+    Xa, Va = zeros(p * p), zeros(p * p)
+    v = fb.wishart(_colmajor(X), _colmajor(V), df, Xa, Va, seed=1.3)
+    assert rel(v, ov) <= 1e-11
+    np.testing.assert_allclose(host(Xa), e.adj(x), rtol=1e-8, atol=1e-11 * np.abs(e.adj(x)).max())
+    np.testing.assert_allclose(host(Va), e.adj(vv), rtol=1e-8, atol=1e-11 * np.abs(e.adj(vv)).max())
+
+
 # ------------------------------------------------------------------ other diagonal log-pdfs
 def _lp_case(fb, dist, n, bvec, cvec, bad=False, seed=0.8, flags=0):
     rng = np.random.default_rng(n + 7 * bvec + 13 * cvec)

@@ -406,3 +406,62 @@ def test_dense_covariance_normal_goldens():
     x, mu, S = e.var(kats.N_VX), e.var(kats.N_VMU), e.var(np.zeros((3, 3)))
     e.bind(e.normal(x, mu, S))
     assert e.autodiff()[0] == -np.inf and np.all(e.adj(x) == 0)       # normal_unittest.cpp:304-310
+
+
+@pytest.mark.parametrize("log", [False, True])
+@pytest.mark.parametrize("policy", ["fullpivlu", "ldlt", "llt"])
+def test_det_log_det_goldens(policy, log):
+    # test/reverse/core/det_unittest.cpp:57-155 and log_det_unittest.cpp:57-152: value == determinant()
+    # (EXPECT_DOUBLE_EQ; the fixtures are integer matrices, exact determinants 153 and 65), adjoint ==
+    # seed * det * inverse().transpose() (resp. seed * inverse().transpose()) within 3e-13
+    A = kats.DET_FPLU if policy == "fullpivlu" else kats.DET_LLT
+    exact = 153.0 if policy == "fullpivlu" else 65.0
+    e = O.OracleExpr()
+    a = e.var(A)
+    sizes = e.bind(e.det(a, policy, log))
+    assert sizes == (1, 0)                                           # det.hpp:75-85
+    v = e.autodiff(kats.DET_SEED)[0]
+    assert_double_eq([v], [math.log(exact) if log else exact])
+    want = kats.DET_SEED * (1.0 if log else exact) * np.linalg.inv(A).T
+    assert np.abs(e.adj(a).reshape(4, 4, order="F") - want).max() <= 3e-13
+    # constant operand folds to a constant (det.hpp:222-227)
+    e = O.OracleExpr()
+    c = e.det(e.const(A), policy, log)
+    assert e.L.orc_is_const(e.g, c)
+    e.bind(c)
+    assert_double_eq(e.feval(), [math.log(exact) if log else exact])
+
+
+def test_det_invalid_matrix_skips_adjoint():
+    # det.hpp:58-60: beval returns early when the decomposition is not valid (singular / not PD)
+    for policy, A in (("fullpivlu", np.array([[1., 2], [2, 4]])), ("llt", np.array([[1., 2], [2, 1]])),
+                      ("ldlt", np.zeros((2, 2)))):
+        e = O.OracleExpr()
+        a = e.var(A)
+        e.bind(e.det(a, policy))
+        e.autodiff(1.0)
+        assert np.all(e.adj(a) == 0), policy
+
+
+def test_wishart_goldens():
+    # test/reverse/stat/wishart_unittest.cpp:62-106
+    e = O.OracleExpr()
+    x, v = e.var(kats.WISHART_X), e.var(kats.WISHART_V)
+    assert e.bind(e.wishart(x, v, kats.WISHART_N)) == (1, 0)
+    assert_double_eq(e.autodiff(1.0), [kats.WISHART_VALUE])
+    n, p = kats.WISHART_N, 3
+    vi = np.linalg.inv(kats.WISHART_V)
+    dX = 0.5 * ((n - p - 1) * np.linalg.inv(kats.WISHART_X) - vi)
+    dV = 0.5 * (vi @ kats.WISHART_X @ vi - n * vi)
+    assert np.abs(e.adj(x).reshape(3, 3, order="F") - dX).max() <= 1e-15
+    assert np.abs(e.adj(v).reshape(3, 3, order="F") - dV).max() <= 1e-15
+    # feval_invalid (:69-75): V = 0 is not positive definite
+    e = O.OracleExpr()
+    x, v = e.var(kats.WISHART_X), e.var(np.zeros((3, 3)))
+    e.bind(e.wishart(x, v, kats.WISHART_N))
+    assert e.autodiff(1.0)[0] == -np.inf and np.all(e.adj(x) == 0) and np.all(e.adj(v) == 0)
+    # n + 1 > p is required (wishart.hpp:203-207)
+    e = O.OracleExpr()
+    x, v = e.var(kats.WISHART_X), e.var(kats.WISHART_V)
+    e.bind(e.wishart(x, v, 2))
+    assert e.autodiff(1.0)[0] == -np.inf
