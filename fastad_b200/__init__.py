@@ -87,6 +87,8 @@ SIGNATURES = {
     "fadb_expr_glue": (_i, [_vp, _i, _i]),
     "fadb_expr_logpdf": (_i, [_vp, _i, _i, _i, _i]),
     "fadb_expr_norm": (_i, [_vp, _i]),
+    "fadb_expr_det": (_i, [_vp, _i, _i, _i]),
+    "fadb_expr_wishart": (_i, [_vp, _i, _i, _d]),
     "fadb_expr_transpose": (_i, [_vp, _i]),
     "fadb_expr_if_else": (_i, [_vp, _i, _i, _i]),
     "fadb_expr_opeq": (_i, [_vp, _i, _i, _i]),
@@ -373,6 +375,12 @@ class Expr:
 
     def norm(self, c):
         return self._id(self.L.fadb_expr_norm(self.h, c))
+
+    def det(self, c, policy="fullpivlu", log=False):
+        return self._id(self.L.fadb_expr_det(self.h, DET_POLICY[policy], 1 if log else 0, c))
+
+    def wishart(self, x, v, df):
+        return self._id(self.L.fadb_expr_wishart(self.h, x, v, float(df)))
 
     def transpose(self, c):
         return self._id(self.L.fadb_expr_transpose(self.h, c))

@@ -40,6 +40,8 @@ extern "C" int fadb_normal_lpdf_finish(int, size_t, const double*, const double*
 extern "C" int fadb_linreg_partial(size_t, size_t, const double*, const double*, const double*, double*);
 extern "C" int fadb_normal_dense_async(size_t, const double*, const double*, int, const double*, double*, double*, double*,
                                        double, unsigned, int, double*);
+extern "C" int fadb_det_async(size_t, const double*, double*, double, unsigned, int, int, int, double*);
+extern "C" int fadb_wishart_async(size_t, const double*, const double*, double, double*, double*, double, unsigned, int, double*);
 extern "C" int fadb_logpdf_async(int, int, size_t, const double*, const double*, const double*, double*, double*, double*,
                                  double, unsigned, double*);
 extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, double*, double*, double,
@@ -517,7 +519,7 @@ __global__ void fill_kernel(double* p, size_t n, double v)
 
 // ======================================================================== host: builder + planner
 enum NodeKind { N_VAR, N_CONST_S, N_CONST_V, N_UNARY, N_BINARY, N_POW, N_SUM, N_SUM_ITER, N_PROD,
-                N_PROD_ITER, N_DOT, N_NORMAL, N_EQ, N_GLUE, N_TRANSPOSE, N_IF_ELSE, N_OPEQ, N_LOGPDF };
+                N_PROD_ITER, N_DOT, N_NORMAL, N_EQ, N_GLUE, N_TRANSPOSE, N_IF_ELSE, N_OPEQ, N_LOGPDF, N_DET, N_WISHART };
 
 struct ENode {
     NodeKind kind;
@@ -535,7 +537,8 @@ struct ENode {
 struct OperandRef { const double* val = nullptr; double* adj = nullptr; int adj_mode = 0; int node = -1; int stage = -1; };
 
 struct Stage {
-    int type = 0;                  // 0 = MAP (interpreter), 1 = DOT, 2 = TRANSPOSE, 3 = dense-covariance normal
+    int type = 0;                  // 0 = MAP (interpreter), 1 = DOT, 2 = TRANSPOSE, 3 = dense-covariance normal,
+                                   // 4 = det / log_det (k = take_log, p = policy), 5 = wishart (sig_const = df)
     size_t N = 1;
     std::vector<Ins> prog;
     std::vector<LeafDesc> leaves;
@@ -590,7 +593,8 @@ struct fadb_expr {
     bool is_const_scalar(int id) const { return nodes[id].kind == N_CONST_S; }
 
     // ---------------------------------------------------------------- planning (host only)
-    static bool barrier(NodeKind k) { return k == N_SUM || k == N_PROD || k == N_NORMAL || k == N_DOT || k == N_TRANSPOSE || k == N_LOGPDF; }
+    static bool barrier(NodeKind k) { return k == N_SUM || k == N_PROD || k == N_NORMAL || k == N_DOT || k == N_TRANSPOSE || k == N_LOGPDF ||
+                                                 k == N_DET || k == N_WISHART; }
 
     int emit(Stage& st, Ins I)
     {
@@ -760,6 +764,19 @@ struct fadb_expr {
             st->m = (int)x.rows; st->k = (int)x.cols; st->p = 0;
             st->out_size = n.size();
             st->L = operand(n.ch[0]); if (!err.empty()) return -1;
+        } else if (n.kind == N_DET) {
+            // DetNode / LogDetNode (det.hpp:25-92): the matrix is handed to the dense kernels as a whole operand
+            st->type = 4;
+            st->m = (int)nodes[n.ch[0]].rows; st->k = (int)n.pw; st->p = n.fn;
+            st->out_size = 1;
+            st->L = operand(n.ch[0]); if (!err.empty()) return -1;
+        } else if (n.kind == N_WISHART) {
+            st->type = 5;
+            st->m = (int)nodes[n.ch[0]].rows;
+            st->sig_const = n.cval;
+            st->out_size = 1;
+            st->L = operand(n.ch[0]); if (!err.empty()) return -1;
+            st->R = operand(n.ch[1]); if (!err.empty()) return -1;
         } else if (n.kind == N_SUM || n.kind == N_PROD) {
             st->N = nodes[n.ch[0]].size();
             st->term = n.kind == N_SUM ? T_SUM : T_PROD;
@@ -958,6 +975,8 @@ struct fadb_expr {
         o << "stages=" << plan.size() << " cache={" << cache_vals << "," << cache_adjs << "}\n";
         for (size_t k = 0; k < plan.size(); ++k) {
             const Stage& st = *plan[k];
+            if (st.type == 5) { o << "stage " << k << ": wishart p=" << st.m << " df=" << st.sig_const << "\n"; continue; }
+            if (st.type == 4) { o << "stage " << k << ": " << (st.k ? "log_det" : "det") << " n=" << st.m << " policy=" << st.p << "\n"; continue; }
             if (st.type == 3) { o << "stage " << k << ": dense normal n=" << st.m << (st.k ? " (vvm)" : " (vsm)") << "\n"; continue; }
             if (st.type == 2) { o << "stage " << k << ": transpose " << st.m << "x" << st.k << "\n"; continue; }
             if (st.type == 1) { o << "stage " << k << ": dot " << st.m << "x" << st.k << " * " << st.k << "x" << st.p << "\n"; continue; }
@@ -1008,7 +1027,7 @@ struct fadb_expr {
             Stage& st = *sp;
             if (st.type != 0) {
                 if (st.L.stage >= 0) { st.L.val = plan[st.L.stage]->mval; st.L.adj = plan[st.L.stage]->madj; }
-                if ((st.type == 1 || st.type == 3) && st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
+                if ((st.type == 1 || st.type == 3 || st.type == 5) && st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
                 if (st.type == 3 && st.S3.stage >= 0) { st.S3.val = plan[st.S3.stage]->mval; st.S3.adj = plan[st.S3.stage]->madj; }
                 continue;
             }
@@ -1064,7 +1083,7 @@ struct fadb_expr {
             Stage& st = *sp;
             if (st.type != 0) {
                 if (st.L.stage < 0) { st.L.val = nodes[st.L.node].val; st.L.adj = nodes[st.L.node].adj; }
-                if ((st.type == 1 || st.type == 3) && st.R.stage < 0) { st.R.val = nodes[st.R.node].val; st.R.adj = nodes[st.R.node].adj; }
+                if ((st.type == 1 || st.type == 3 || st.type == 5) && st.R.stage < 0) { st.R.val = nodes[st.R.node].val; st.R.adj = nodes[st.R.node].adj; }
                 if (st.type == 3 && st.S3.stage < 0) { st.S3.val = nodes[st.S3.node].val; st.S3.adj = nodes[st.S3.node].adj; st.factored = false; }
                 continue;
             }
@@ -1133,20 +1152,32 @@ struct fadb_expr {
     int run_dot(Context& c, Stage& st, int mode, const double* seed_vec, double seed)
     {
         const int threads = 128;
-        if (st.type == 3) {
+        if (st.type >= 3) {
             // forward-only evaluations zero the seed (no adjoint is touched, normal.hpp:644); an inner
-            // stage reads its scalar seed back from its boundary buffer
+            // stage reads its scalar seed back from its boundary buffer.  The dense workspace is shared by
+            // all dense stages of a device: a backward-only call re-factors unless this stage used it last.
+            static const Stage* owner[kMaxDevices] = {};
             double sd = (mode & M_B) ? seed : 0.0;
             if (mode == M_B && !seed_vec) {
                 FADB_CUDA(cudaMemcpyAsync(&sd, st.madj, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
                 FADB_CUDA(cudaStreamSynchronize(c.stream));
             }
-            const bool refactor = !(st.sigma_const && st.factored) && !(mode == M_B);
+            const bool mine = owner[c.device] == &st;
             auto adjp = [](const OperandRef& r) { return r.adj_mode ? r.adj : nullptr; };
-            int rc = fadb_normal_dense_async(st.m, st.L.val, st.R.val, st.k, st.S3.val, adjp(st.L), adjp(st.R), adjp(st.S3), sd,
+            int rc;
+            if (st.type == 3) {
+                const bool refactor = !(mine && ((st.sigma_const && st.factored) || mode == M_B));
+                rc = fadb_normal_dense_async(st.m, st.L.val, st.R.val, st.k, st.S3.val, adjp(st.L), adjp(st.R), adjp(st.S3), sd,
                                              0, refactor ? 1 : 0, st.mval);
+                st.factored = true;
+            } else if (st.type == 4) {
+                rc = fadb_det_async(st.m, st.L.val, adjp(st.L), sd, 0, st.p, st.k, (mine && mode == M_B) ? 0 : 1, st.mval);
+            } else {
+                rc = fadb_wishart_async(st.m, st.L.val, st.R.val, st.sig_const, adjp(st.L), adjp(st.R), sd, 0,
+                                        (mine && mode == M_B) ? 0 : 1, st.mval);
+            }
             if (rc) return rc;
-            st.factored = true;
+            owner[c.device] = &st;
             return FADB_OK;
         }
         if (st.type == 2) {
@@ -1501,6 +1532,26 @@ int fadb_expr_logpdf(fadb_expr* e, int dist, int a, int b, int c)
         EXPR_REQUIRE(e, e->nodes[id].size() == 1 || e->nodes[id].size() == N, "adjusted log-pdf: operand sizes differ");
     ENode n; n.kind = N_LOGPDF; n.fn = dist; n.ch = {a, b};
     if (dist != FADB_BERNOULLI) n.ch.push_back(c);
+    return e->add(std::move(n));
+}
+
+int fadb_expr_det(fadb_expr* e, int policy, int take_log, int child)
+{
+    EXPR_REQUIRE(e, e && e->ok(child) && policy >= FADB_DET_FULLPIVLU && policy <= FADB_DET_LLT, "fadb_expr_det: bad arguments");
+    const ENode& c = e->nodes[child];
+    EXPR_REQUIRE(e, c.shape != FADB_SCL && c.rows == c.cols, "det: the operand must be a square matrix (det.hpp:33, 50)");
+    ENode n; n.kind = N_DET; n.fn = policy; n.pw = take_log ? 1 : 0; n.ch = {child};
+    return e->add(std::move(n));
+}
+
+int fadb_expr_wishart(fadb_expr* e, int x, int v, double df)
+{
+    EXPR_REQUIRE(e, e && e->ok(x) && e->ok(v), "fadb_expr_wishart: bad arguments");
+    const ENode& a = e->nodes[x];
+    const ENode& b = e->nodes[v];
+    EXPR_REQUIRE(e, a.shape == FADB_MAT && b.shape == FADB_MAT && a.rows == a.cols && b.rows == b.cols && a.rows == b.rows,
+                 "wishart_adj_log_pdf: X and V must be square matrices of one size (wishart.hpp:25-27)");
+    ENode n; n.kind = N_WISHART; n.cval = df; n.ch = {x, v};
     return e->add(std::move(n));
 }
 

@@ -269,6 +269,9 @@ int fadb_expr_glue(fadb_expr*, int lhs, int rhs);
  * and no adjoint update. */
 enum { FADB_CAUCHY = 0, FADB_UNIFORM = 1, FADB_BERNOULLI = 2 };
 int fadb_expr_logpdf(fadb_expr*, int dist, int a, int b, int c);
+/* DetNode / LogDetNode (det.hpp:25-92, log_det.hpp:25-92) and WishartAdjLogPDFNode (wishart.hpp:92-231) */
+int fadb_expr_det(fadb_expr*, int policy, int take_log, int child);
+int fadb_expr_wishart(fadb_expr*, int x, int v, double df);
 int fadb_expr_norm(fadb_expr*, int child);
 int fadb_expr_transpose(fadb_expr*, int child);
 int fadb_expr_if_else(fadb_expr*, int cond, int if_node, int else_node);

@@ -715,6 +715,28 @@ private:
     R r_;
 };
 
+// DetNode / LogDetNode (det.hpp:25-92, log_det.hpp:25-92): determinant resp. log|determinant| of a
+// square matrix expression; DecompType carries the reference's decomposition policy as a code
+template <class DecompType, class ExprType, bool TakeLog>
+struct DetNodeBase : ExprBase<DetNodeBase<DecompType, ExprType, TakeLog>> {
+    static_assert(!util::is_scl_v<ExprType>, "det of a scalar (det.hpp:36)");
+    using value_t = double;
+    using shape_t = scl;
+    DetNodeBase(const ExprType& e) : expr_(e) { assert(e.rows() == e.cols()); }
+    size_t rows() const { return 1; }
+    size_t cols() const { return 1; }
+    size_t size() const { return 1; }
+    int lower(detail::Lowering& L) const
+    {
+        return detail::checked_id(fadb_expr_det(L.e, DecompType::code, TakeLog ? 1 : 0, expr_.lower(L)));
+    }
+    const ExprType& child() const { return expr_; }
+private:
+    ExprType expr_;
+};
+template <class DecompType, class ExprType> using DetNode = DetNodeBase<DecompType, ExprType, false>;
+template <class DecompType, class ExprType> using LogDetNode = DetNodeBase<DecompType, ExprType, true>;
+
 // NormNode (norm.hpp:24-108): squared L2 / Frobenius norm
 template <class ExprType>
 struct NormNode : ExprBase<NormNode<ExprType>> {
@@ -997,6 +1019,73 @@ inline auto bernoulli_adj_log_pdf(const X& x, const P& p)   // bernoulli.hpp: (x
     x_t ex = x;
     p_t ep = p;
     return core::LogPDFNode<FADB_BERNOULLI, x_t, p_t, core::Constant<double, scl>>(ex, ep, core::Constant<double, scl>(0.0));
+}
+
+// ---- ad::det / ad::log_det / ad::wishart_adj_log_pdf ------------------------------
+// decomposition policies (det.hpp:97-202, log_det.hpp:97-202); here they only select the device path
+template <class ValueType> struct DetFullPivLU { using value_t = ValueType; static constexpr int code = FADB_DET_FULLPIVLU; };
+template <class ValueType> struct DetLDLT { using value_t = ValueType; static constexpr int code = FADB_DET_LDLT; };
+template <class ValueType> struct DetLLT { using value_t = ValueType; static constexpr int code = FADB_DET_LLT; };
+template <class ValueType> struct LogDetFullPivLU { using value_t = ValueType; static constexpr int code = FADB_DET_FULLPIVLU; };
+template <class ValueType> struct LogDetLDLT { using value_t = ValueType; static constexpr int code = FADB_DET_LDLT; };
+template <class ValueType> struct LogDetLLT { using value_t = ValueType; static constexpr int code = FADB_DET_LLT; };
+
+// det.hpp:211-231.  A constant matrix operand is NOT folded at build time here (the reference
+// returns a Constant): its data lives in HBM, so the node is evaluated like any other.
+template <template <class> class DecompType = DetFullPivLU, class T,
+          class = std::enable_if_t<util::is_convertible_to_ad_v<T> && util::any_ad_v<T>>>
+inline auto det(const T& x)
+{
+    using expr_t = util::convert_to_ad_t<T>;
+    expr_t expr = x;
+    return core::DetNode<DecompType<double>, expr_t>(expr);
+}
+template <template <class> class DecompType = LogDetFullPivLU, class T,
+          class = std::enable_if_t<util::is_convertible_to_ad_v<T> && util::any_ad_v<T>>>
+inline auto log_det(const T& x)       // log_det.hpp:211-231
+{
+    using expr_t = util::convert_to_ad_t<T>;
+    expr_t expr = x;
+    return core::LogDetNode<DecompType<double>, expr_t>(expr);
+}
+
+namespace stat {
+// WishartAdjLogPDFNode (wishart.hpp:92-231): x, v square matrices, n a scalar constant
+template <class X, class V, class N>
+struct WishartAdjLogPDFNode : core::ExprBase<WishartAdjLogPDFNode<X, V, N>> {
+    static_assert(util::is_mat_v<X> && util::is_mat_v<V> && util::is_scl_v<N>, "wishart: mat, mat, scl (wishart.hpp:25-27)");
+    static_assert(core::is_scl_constant_v<N>, "wishart: n must be a constant (wishart.hpp:28)");
+    using value_t = double;
+    using shape_t = scl;
+    WishartAdjLogPDFNode(const X& x, const V& v, const N& n) : x_(x), v_(v), n_(n) {}
+    size_t rows() const { return 1; }
+    size_t cols() const { return 1; }
+    size_t size() const { return 1; }
+    int lower(detail::Lowering& L) const
+    {
+        int a = x_.lower(L);
+        int b = v_.lower(L);
+        return detail::checked_id(fadb_expr_wishart(L.e, a, b, (double)n_.feval()));
+    }
+private:
+    X x_;
+    V v_;
+    N n_;
+};
+}  // namespace stat
+
+template <class XType, class VType, class NType,
+          class = std::enable_if_t<util::is_convertible_to_ad_v<XType> && util::is_convertible_to_ad_v<VType> &&
+                                   util::is_convertible_to_ad_v<NType> && util::any_ad_v<XType, VType, NType>>>
+inline auto wishart_adj_log_pdf(const XType& x, const VType& v, const NType& n)      // wishart.hpp:242-257
+{
+    using x_t = util::convert_to_ad_t<XType>;
+    using v_t = util::convert_to_ad_t<VType>;
+    using n_t = util::convert_to_ad_t<NType>;
+    x_t ex = x;
+    v_t ev = v;
+    n_t en = n;
+    return stat::WishartAdjLogPDFNode<x_t, v_t, n_t>(ex, ev, en);
 }
 
 // ---- SURVEY.md 8f "next" rows ---------------------------------------------------------------

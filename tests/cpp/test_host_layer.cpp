@@ -416,6 +416,42 @@ static void next_rows()
         CHECK_DOUBLE_EQ(Sig.get_adj(2, 1), -0.1530140218890801);
         CHECK_DOUBLE_EQ(Sig.get_adj(1, 2), -0.1530140218890801);
     }
+    // ---- ad::det / ad::log_det (det_unittest.cpp:57-155, log_det_unittest.cpp:57-152)
+    {
+        const double seed = 9.2313;
+        Var<double, mat> A(4, 4), B(4, 4);
+        A.get() = {2, 3, -2, -1, 3, 5, 3, -1, 1, -1, 1, 2, 5, 3, 0, 7};          // init_fplu, column-major
+        B.get() = {8, 3, 1, 5, 3, 5, 1, 3, 1, 1, 1, 0, 5, 3, 0, 7};              // init_llt (symmetric)
+        auto d0 = ad::bind(ad::det(A));
+        CHECK_DOUBLE_EQ(ad::autodiff(d0, seed), 153.);
+        // adj = seed * det * inverse().transpose(): cofactor(0,0) = det [[5,-1,3],[3,1,0],[-1,2,7]] = 77
+        CHECK_NEAR(A.get_adj(0, 0), seed * 77., 3e-13 * 1000);
+        auto d1 = ad::bind(ad::det<ad::DetLLT>(B));
+        CHECK_DOUBLE_EQ(ad::autodiff(d1, seed), 65.);
+        auto d2 = ad::bind(ad::det<ad::DetLDLT>(B));
+        CHECK_DOUBLE_EQ(ad::autodiff(d2, seed), 65.);
+        B.reset_adj();
+        auto l1 = ad::bind(ad::log_det<ad::LogDetLLT>(B));
+        CHECK_DOUBLE_EQ(ad::autodiff(l1, seed), std::log(65.));
+        // adj = seed * inverse().transpose(); inv(B)(2,2) = cofactor / det, cofactor(2,2) = det [[8,3,5],[3,5,3],[5,3,7]] = 110
+        CHECK_NEAR(B.get_adj(2, 2), seed * 110. / 65., 3e-13);
+        auto l0 = ad::bind(ad::log_det(A));
+        CHECK_DOUBLE_EQ(ad::autodiff(l0, 0.), std::log(153.));
+        static_assert(std::is_same_v<decltype(ad::det(A))::shape_t, ad::scl>);
+    }
+    // ---- ad::wishart_adj_log_pdf (wishart_unittest.cpp:62-106)
+    {
+        Var<double, mat> X(3, 3), V(3, 3);
+        X.get() = {10, 2, 3, 2, 10, 1, 3, 1, 10};
+        V.get() = {5, 1, 0, 1, 5, 1, 0, 1, 5};
+        size_t n = 4;
+        auto w = ad::bind(ad::wishart_adj_log_pdf(X, V, n));
+        CHECK_DOUBLE_EQ(ad::autodiff(w), -12.55942947411780252764);
+        // dX = 0.5 ((n-p-1) X^-1 - V^-1) = -0.5 V^-1 for n = 4, p = 3; V^-1(0,0) = 24/115
+        CHECK_NEAR(X.get_adj(0, 0), -0.5 * 24. / 115., 1e-15);
+        V.get() = {0, 0, 0, 0, 0, 0, 0, 0, 0};                                  // feval_invalid
+        CHECK(ad::autodiff(w) == -std::numeric_limits<double>::infinity());
+    }
     // ---- ad::for_each (for_each.hpp:19-131): evaluate all, value of the last, seed to the last only
     {
         std::vector<Var<double>> xs, ws(3);

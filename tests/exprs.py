@@ -340,7 +340,56 @@ def dense_normal_in_model(n):
     return build
 
 
+# ---- det / log_det / wishart ----------------------------------------------------
+def _spd(n, diag=1.2):
+    Lo = np.tril(_vec(n * n, -1, 1).reshape(n, n), -1) / np.sqrt(n) + diag * np.eye(n)
+    return Lo @ Lo.T
+
+
+def det_case(policy, log, n=None):
+    def build(e):
+        if n is None:
+            A = kats.DET_FPLU if policy == "fullpivlu" else kats.DET_LLT
+        else:
+            A = (_vec(n * n, -1, 1).reshape(n, n) + 0.5 * np.eye(n)) if policy == "fullpivlu" else _spd(n)
+        a = e.var(A)
+        return e.det(a, policy, log), [a], kats.DET_SEED
+    return build
+
+
+def log_det_of_expression(n):
+    def build(e):   # log det of a computed matrix, inside a larger scalar expression: 0.5*log_det(s*A + B) - sum(A*A)
+        A, B, s = e.var(_spd(n)), e.const(_spd(n, 0.8)), e.var(1.3)
+        M = e.binary("add", e.binary("mul", s, A), B)
+        root = e.binary("sub", e.binary("mul", e.const(0.5), e.det(M, "llt", True)), e.sum(e.binary("mul", A, A)))
+        return root, [A, s], 0.9
+    return build
+
+
+def wishart_case(p=None, const_v=False):
+    def build(e):
+        X, V, df = (kats.WISHART_X, kats.WISHART_V, kats.WISHART_N) if p is None else (_spd(p), _spd(p), p + 2.5)
+        x = e.var(X)
+        v = e.const(V) if const_v else e.var(V)
+        return e.wishart(x, v, df), [x] + ([] if const_v else [v]), 1.0
+    return build
+
+
+def wishart_plus_det(p):
+    def build(e):   # two dense stages sharing the device workspace, combined by a scalar stage
+        x, v = e.var(_spd(p)), e.var(_spd(p))
+        root = e.binary("add", e.wishart(x, v, p + 4), e.binary("mul", e.const(0.25), e.det(v, "fullpivlu", True)))
+        return root, [x, v], 1.1
+    return build
+
+
 CASES = {
+    "det_fplu": det_case("fullpivlu", False), "det_ldlt": det_case("ldlt", False), "det_llt": det_case("llt", False),
+    "log_det_fplu": det_case("fullpivlu", True), "log_det_ldlt": det_case("ldlt", True), "log_det_llt": det_case("llt", True),
+    "det_fplu_37": det_case("fullpivlu", False, 37), "log_det_llt_70": det_case("llt", True, 70),
+    "log_det_of_expression": log_det_of_expression(45),
+    "wishart": wishart_case(), "wishart_40": wishart_case(40), "wishart_const_v_33": wishart_case(33, True),
+    "wishart_plus_det": wishart_plus_det(36),
     "dense_normal_vsm": dense_normal(False), "dense_normal_vvm": dense_normal(True),
     "dense_normal_vvm_100": dense_normal(True, n=100), "dense_normal_vsm_65_const_sigma": dense_normal(False, n=65, const_sigma=True),
     "dense_normal_in_model": dense_normal_in_model(48),

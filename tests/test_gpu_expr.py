@@ -42,13 +42,14 @@ def test_expr_matches_oracle(fb, name):
     build = exprs.CASES[name]
     ov, oadj, oval, _ = _run(build, O.OracleExpr)
     gv, gadj, gval, ge = _run(build, fb.Expr)
-    rtol = 1e-11 if name.startswith(("black_scholes", "dense_normal")) else 1e-12
+    dense = name.startswith(("dense_normal", "det_", "log_det", "wishart"))
+    rtol = 1e-11 if name.startswith("black_scholes") or dense else 1e-12
     _close(gv, ov, rtol, name + " value")
     # Black-Scholes: the adjoints that flow through the placeholders are differences of nearly
     # equal terms of size ~S*phi(d1) (the residual S*phi(d1) - PV*phi(d2) is ~1e-14): the floor is
     # relative to those terms, not to the residual.
     floor = 100.0 if name.startswith("black_scholes") else 1e-300
-    if name.startswith("dense_normal"):      # factorisation + inverse: conditioning-limited, not ulp-limited
+    if dense:                                # factorisation + inverse: conditioning-limited, not ulp-limited
         for k, (g, o) in enumerate(zip(gadj, oadj)):
             _close(g, o, 1e-8, f"{name} adj[{k}]")
         return
