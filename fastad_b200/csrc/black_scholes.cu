@@ -174,6 +174,7 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
                   const double* __restrict__ sigma, const double* __restrict__ tau,
                   const double* __restrict__ r, BSOut out)
 {
+    pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     size_t i = tid;
@@ -206,7 +207,8 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     const int threads = 256;
     // Measured on B200, 2^20 options per launch (us per launch): libdevice math 29.2 (variant 5);
     // fastmath 27.7 (variant 6); fastmath + software-pipelined loads, 128 registers, 2 CTAs/SM
-    // 25.8 (default).  Two options per thread, tighter launch bounds (spills) and atomic
+    // 25.5 (variant 20); the same kernel launched with programmatic dependent launch 23.5 (default).
+    // Two options per thread, tighter launch bounds (spills) and atomic
     // work-stealing were measured slower and removed.
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 21; }
@@ -219,7 +221,18 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     } while (0)
     if (variant == 5) FADB_BS_LAUNCH(bs_kernel_libdevice);
     else if (variant == 6) FADB_BS_LAUNCH(bs_kernel_fast);
-    else FADB_BS_LAUNCH(bs_kernel_fast_pf);
+    else if (variant == 20) FADB_BS_LAUNCH(bs_kernel_fast_pf);
+    else {
+        // default: same kernel, launched with programmatic stream serialization so that back-to-back
+        // batches overlap launch latency and the tail of the previous grid (the kernel waits on
+        // cudaGridDependencySynchronize before its first memory access)
+        if (ovw)
+            FADB_CUDA(launch_pdl(bs_kernel_fast_pf<false>, resident_grid(c, bs_kernel_fast_pf<false>, threads, 0, n, threads),
+                                 threads, 0, st, n, S, K, sigma, tau, r, o));
+        else
+            FADB_CUDA(launch_pdl(bs_kernel_fast_pf<true>, resident_grid(c, bs_kernel_fast_pf<true>, threads, 0, n, threads),
+                                 threads, 0, st, n, S, K, sigma, tau, r, o));
+    }
 #undef FADB_BS_LAUNCH
     c.launches++;
     FADB_CUDA(cudaGetLastError());

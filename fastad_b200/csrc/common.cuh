@@ -1,6 +1,7 @@
 // common.cuh — shared device/host helpers for the fastad_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include <cmath>
 #include <cstddef>
@@ -176,6 +177,39 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NCH], double* smem, do
         *ticket = 0u;   // self-reset for the next launch on this stream
         fin(tot);
     }
+}
+
+// ---- programmatic dependent launch (PDL).  Back-to-back launches of the full-GPU, single-wave
+// kernels otherwise pay the launch latency and the idle tail of the previous grid every time.
+// launch_pdl() marks the launch as allowed to become resident while the previous kernel on the
+// stream is still running; the kernel calls pdl_prologue() before its FIRST global-memory access,
+// which (a) lets the launch after it do the same and (b) blocks until the previous grid has
+// completed and flushed.  Ordering of memory effects is therefore unchanged.  FADB_NO_PDL=1 disables.
+__device__ __forceinline__ void pdl_prologue()
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+}
+inline bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("FADB_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace fadb

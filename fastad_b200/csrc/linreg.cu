@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(LT_THREADS)
 linreg_tma_kernel(LinregArgs a, const __grid_constant__ CUtensorMap xmap, int box_cols, double* cta_partials,
                   unsigned int* ticket, double* out /* cols+1 */)
 {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char lt_smem[];
     unsigned char* stages = lt_smem;                                       // [LT_STAGES][LT_STAGE_BYTES]
     double* w_s = reinterpret_cast<double*>(lt_smem + LT_STAGES * LT_STAGE_BYTES);   // [64]
@@ -427,7 +428,7 @@ extern "C" int fadb_linreg_partial(size_t rows, size_t cols, const double* X, co
         CUtensorMap xmap;
         rc = encode_xmap(&xmap, X, rows, cols);
         if (rc) return rc;
-        linreg_tma_kernel<<<g2, LT_THREADS, smem, c->stream>>>(a, xmap, (int)cols, ws, c->tickets + 4, dev_partial);
+        FADB_CUDA(launch_pdl(linreg_tma_kernel, g2, LT_THREADS, smem, c->stream, a, xmap, (int)cols, ws, c->tickets + 4, dev_partial));
         c->launches++;
         FADB_CUDA(cudaGetLastError());
         return FADB_OK;

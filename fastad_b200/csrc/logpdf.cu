@@ -83,6 +83,7 @@ template <int DIST, bool B_VEC, bool C_VEC>
 __global__ void __launch_bounds__(512)
 lp_check_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out_count)
 {
+    pdl_prologue();
     __shared__ double smem[32];
     double acc[1] = {0.0};
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -115,6 +116,7 @@ template <int DIST, bool B_VEC, bool C_VEC>
 __global__ void __launch_bounds__(256)
 lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] value, invalid, -, - */)
 {
+    pdl_prologue();
     __shared__ double smem[32 * 4];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -188,14 +190,14 @@ static int run_logpdf(Context& c, LpArgs a, unsigned flags, bool any_adj, double
         if (global_check && !(flags & FADB_TRUST_SIGMA)) {
             const int threads = 512;
             const int grid = resident_grid(c, lp_check_kernel<DIST, B_VEC, C_VEC>, threads, 0, a.n, threads);
-            lp_check_kernel<DIST, B_VEC, C_VEC><<<grid, threads, 0, c.stream>>>(a, c.partials, c.tickets + 9, invalid);
+            FADB_CUDA(launch_pdl(lp_check_kernel<DIST, B_VEC, C_VEC>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 9, invalid));
             c.launches++;
             a.invalid_in = invalid;
         }
     }
     const int threads = 256;
     const int grid = resident_grid(c, lp_kernel<DIST, B_VEC, C_VEC>, threads, 0, (a.n + 3) / 4, threads);
-    lp_kernel<DIST, B_VEC, C_VEC><<<grid, threads, 0, c.stream>>>(a, c.partials, c.tickets + 10, out);
+    FADB_CUDA(launch_pdl(lp_kernel<DIST, B_VEC, C_VEC>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 10, out));
     c.launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256)
 sum_map_kernel(size_t n, const double* __restrict__ x, double* x_adj, double seed, int overwrite,
                F fun, double* partials, unsigned int* ticket, double* out_value)
 {
+    pdl_prologue();
     __shared__ double smem[32];
     double acc[1] = {0.0};
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -76,8 +77,8 @@ static int launch_sum_map(Context& c, size_t n, const double* x, double* x_adj, 
 {
     const int threads = 256;
     const int grid = resident_grid(c, sum_map_kernel<F>, threads, 0, (n + 3) / 4, threads);
-    sum_map_kernel<F><<<grid, threads, 0, c.stream>>>(n, x, x_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
-                                                      fun, c.partials, c.tickets + 2, dval);
+    FADB_CUDA(launch_pdl(sum_map_kernel<F>, grid, threads, 0, c.stream, n, x, x_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
+                         fun, c.partials, c.tickets + 2, dval));
     c.launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;

@@ -27,6 +27,7 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
             const double* __restrict__ parm, double* cta_partials, unsigned int* ticket,
             double* grad, int overwrite, double* out_loss)
 {
+    pdl_prologue();
     __shared__ double p[NP];
     __shared__ double red[8][NOUT];
     __shared__ bool is_last;
@@ -144,8 +145,8 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     if (!g_mlp_ws[c->device]) FADB_CUDA(cudaMalloc(&g_mlp_ws[c->device], sizeof(double) * kMaxGrid * NOUT));
     const int threads = 256;
     const int grid = resident_grid(*c, mlp3_kernel, threads, 0, batch, threads);
-    mlp3_kernel<<<grid, threads, 0, c->stream>>>(batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad,
-                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss);
+    FADB_CUDA(launch_pdl(mlp3_kernel, grid, threads, 0, c->stream, batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad,
+                         (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss));
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;

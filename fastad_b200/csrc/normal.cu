@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(512)
 sigma_check_kernel(size_t n, const double* __restrict__ sigma, double* partials,
                    unsigned int* ticket, double* out_count)
 {
+    pdl_prologue();
     __shared__ double smem[32];
     double acc[1] = {0.0};
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -98,6 +99,7 @@ template <bool MU_VEC, bool SIG_VEC>
 __global__ void __launch_bounds__(256)
 normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_partial)
 {
+    pdl_prologue();
     __shared__ double smem[32 * NCH];
     double acc[NCH] = {0.0, 0.0, 0.0, 0.0};
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -213,8 +215,8 @@ static int launch_partial(Context& c, int shape_code, const NormalArgs& a, doubl
     double* part = c.partials;
     unsigned int* ticket = c.tickets + 1;
 #define FADB_LAUNCH_NORMAL(MV, SV)                                                               \
-    normal_kernel<MV, SV><<<resident_grid(c, normal_kernel<MV, SV>, threads, 0, work, threads),  \
-                            threads, 0, c.stream>>>(a, part, ticket, out_partial)
+    FADB_CUDA(launch_pdl(normal_kernel<MV, SV>, resident_grid(c, normal_kernel<MV, SV>, threads, 0, work, threads), \
+                         threads, 0, c.stream, a, part, ticket, out_partial))
     switch (shape_code & 3) {
     case 0: FADB_LAUNCH_NORMAL(false, false); break;
     case 1: FADB_LAUNCH_NORMAL(true, false); break;
@@ -247,7 +249,7 @@ extern "C" int fadb_sigma_check(size_t n, const double* sigma, double* dev_count
     if (rc) return rc;
     const int threads = 512;
     const int grid = resident_grid(*c, sigma_check_kernel, threads, 0, (n + 3) / 4, threads);
-    sigma_check_kernel<<<grid, threads, 0, c->stream>>>(n, sigma, c->partials, c->tickets + 0, dev_count);
+    FADB_CUDA(launch_pdl(sigma_check_kernel, grid, threads, 0, c->stream, n, sigma, c->partials, c->tickets + 0, dev_count));
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;
