@@ -36,6 +36,17 @@ def test_cpp_fastmath_accuracy_against_glibc(built):
     assert "test_fastmath:" in out
 
 
+def test_cpp_forward_mode_reference_tests(built):
+    out = _run(built, "test_forward")
+    assert "test_forward:" in out
+
+
+@pytest.mark.gpu
+def test_cpp_forward_mode_batched_on_device(built):
+    out = _run(built, "test_forward_batch")
+    assert "test_forward_batch:" in out
+
+
 @pytest.mark.gpu
 def test_cpp_host_layer_reference_tests(built):
     out = _run(built, "test_host_layer")
