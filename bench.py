@@ -451,9 +451,19 @@ def run_ours(args):
 
         def chain_step(i):
             F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+        # default engine: the stage kernel specialised at bind time by NVRTC (csrc/jit.cu), then the
+        # same stage on the tape interpreter (fadb_jit_enable(0))
+        j0 = F.jit_stats()
         t = timed_loop(chain_step, steps2, 3, world)
+        j1 = F.jit_stats()
+        add("expr_sum_chain_2^24_specialised", 32 * n2, t, steps2, n2, "elements",
+            {"note": "g++-side C-ABI path; x read + c read + x_adj RMW = 32 B/elem; 2 scalar adjoints by reduction channels",
+             "specialised_kernel_launches": j1["launched"] - j0["launched"]})
+        prev_jit = F.jit_enable(False)
+        t = timed_loop(chain_step, steps2, 3, world)
+        F.jit_enable(prev_jit)
         add("expr_sum_chain_2^24_interpreter", 32 * n2, t, steps2, n2, "elements",
-            {"note": "x read + c read + x_adj RMW = 32 B/elem; 2 scalar adjoints by reduction channels"})
+            {"note": "same expression, specialisation off"})
         del e
         nb = BS_N
         exprs.RNG = np.random.default_rng(1)
@@ -464,11 +474,19 @@ def run_ours(args):
 
         def bs_expr_step(i):
             F.check(L.fadb_expr_autodiff(e.h, 0.0, P(ones), None))
+        j0 = F.jit_stats()
         t = timed_loop(bs_expr_step, steps2, 3, world)
+        j1 = F.jit_stats()
         # S,K,sigma,tau,sqrt_tau,r reads (48) + seed read (8) + price store (8) + 3 adj RMW (48)
         # + 3 placeholders: value store + adjoint RMW (72) = 184 B/option
+        add("expr_black_scholes_call_2^20_specialised", 184 * nb, t, steps2, nb, "options",
+            {"note": "one autodiff of the CALL expression only, reference placeholder semantics kept",
+             "specialised_kernel_launches": j1["launched"] - j0["launched"]})
+        prev_jit = F.jit_enable(False)
+        t = timed_loop(bs_expr_step, steps2, 3, world)
+        F.jit_enable(prev_jit)
         add("expr_black_scholes_call_2^20_interpreter", 184 * nb, t, steps2, nb, "options",
-            {"note": "one autodiff of the CALL expression only, reference placeholder semantics kept"})
+            {"note": "same expression, specialisation off"})
         del e
 
         # the same two expressions through the TYPE-FUSED path (include/fastad_b200/fused.cuh): the
@@ -535,7 +553,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "options/s", "h2d_bytes_per_step": 40 * n,
                     "d2h_bytes_per_step": 64 * n, "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "fadb_black_scholes_host (pinned host buffers)"},
+                    "api": "fadb_black_scholes_host (page-locked host buffers: one launch reading and writing them over PCIe)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "workloads": workloads,

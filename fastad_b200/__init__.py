@@ -101,6 +101,11 @@ SIGNATURES = {
     "fadb_expr_beval": (_i, [_vp, _d, _vp]),
     "fadb_expr_autodiff": (_i, [_vp, _d, _vp, _dp]),
     "fadb_expr_value_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "fadb_jit_enable": (_i, [_i]),
+    "fadb_jit_stats": (_i, [C.POINTER(C.c_ulonglong)]),
+    "fadb_jit_diagnostics": (C.c_char_p, []),
+    "fadb_expr_jit_program": (_i, [_vp, _i, _i, C.c_char_p, _sz]),
+    "fadb_jit_compile_only": (_i, [C.c_char_p, C.POINTER(_sz), C.c_char_p, _sz]),
 }
 
 _lib = None
@@ -129,6 +134,25 @@ def lib():
 def check(rc):
     if rc != 0:
         raise FadbError(f"fastad_b200 error {rc}: {lib().fadb_last_error().decode()}")
+
+
+def jit_enable(on):
+    """Specialised (NVRTC) stage kernels on/off; returns the previous setting."""
+    return bool(lib().fadb_jit_enable(1 if on else 0))
+
+
+def jit_stats():
+    out = (C.c_ulonglong * 4)()
+    check(lib().fadb_jit_stats(out))
+    return {"compiled": out[0], "hits": out[1], "failed": out[2], "launched": out[3]}
+
+
+def jit_compile_only(program):
+    """NVRTC-compiles a stage program text to an sm_100a cubin (no device needed); returns (bytes, log)."""
+    n = _sz(0)
+    log = C.create_string_buffer(1 << 16)
+    check(lib().fadb_jit_compile_only(program.encode(), C.byref(n), log, len(log)))
+    return n.value, log.value.decode()
 
 
 def _ptr(t):
@@ -396,6 +420,12 @@ class Expr:
         check(self.L.fadb_expr_plan(self.h, root, out))
         self.root = root
         return int(out[0]), int(out[1])
+
+    def jit_program(self, stage, mode):
+        """Constants that specialise planned stage `stage` for mode 1 (forward), 2 (backward), 3 (fused)."""
+        buf = C.create_string_buffer(1 << 16)
+        check(self.L.fadb_expr_jit_program(self.h, stage, mode, buf, len(buf)))
+        return buf.value.decode()
 
     def describe(self):
         buf = C.create_string_buffer(1 << 16)

@@ -109,43 +109,9 @@ __device__ __forceinline__ void st256(double* p, const double4_t& r)
 
 __host__ __device__ inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
-// ---------------------------------------------------------------------------------------
-// Deterministic block reduction of NCH channels: warp shuffle tree, then shared memory,
-// result valid in thread 0.  Fixed tree => run-to-run identical bits.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_prod(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v *= __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-
-template <int NCH>
-__device__ __forceinline__ void block_sum(double (&acc)[NCH], double* smem /* [32*NCH] */)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) acc[c] = warp_sum(acc[c]);
-    if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) smem[warp * NCH + c] = acc[c];
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            double v = lane < nwarp ? smem[lane * NCH + c] : 0.0;
-            acc[c] = warp_sum(v);
-        }
-    }
-    __syncthreads();
-}
+}  // namespace fadb
+#include "device_reduce.cuh"   // warp_sum, warp_prod, block_sum
+namespace fadb {
 
 // Grid-level finish: every CTA stores its NCH partials; the last CTA to arrive (ticket)
 // sums all partials in CTA order with one warp-strided pass + fixed tree, then calls `fin`

@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "functors.cuh"
+#include "jit.h"
 
 extern "C" int fadb_sum_unary_async(int, size_t, const double*, double*, double, unsigned, double*);
 extern "C" int fadb_sigma_check(size_t, const double*, double*);
@@ -47,422 +48,10 @@ extern "C" int fadb_logpdf_async(int, int, size_t, const double*, const double*,
 extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, double*, double*, double,
                                   unsigned, double*);
 
+#include "stage_kernel.cuh"
+
 namespace fadb {
 
-// ======================================================================== device program
-enum : int { I_LEAF = 0, I_CONST, I_UNARY, I_BINARY, I_POW, I_EQ, I_GLUE, I_JZ, I_JMP, I_PHI, I_OPEQ };
-enum : int { T_NONE = 0, T_SUM, T_PROD, T_NORMAL, T_CAUCHY, T_UNIFORM, T_BERNOULLI };
-enum : int { M_F = 1, M_B = 2, M_FB = 3 };
-
-struct Ins {
-    int op, fn, a, b, leaf, pad;
-    double imm;
-};
-// device encoding: 16 bytes (one LDS.128), a single flat opcode so that the interpreter has ONE
-// dense switch (a jump table) per direction instead of nested compare chains
-enum : short { F_LEAF_V = 0, F_LEAF_S, F_CONST, F_EQ, F_GLUE, F_POW, F_POW2, F_UNARY = 8 /* +fn, mock2x = +16 */,
-               F_BINARY = 26 /* +fn, mockb = +12 */, F_JZ = 40, F_JMP = 41, F_PHI = 42, F_OPEQ = 44 /* +op */ };
-struct DIns {
-    short code, a, b, leaf;   // POW: exponent in `leaf`
-    double imm;
-};
-struct LeafDesc {
-    const double* val;
-    double* adj;
-    int scalar;      // 1: one value broadcast over the stage's elements
-    int adj_mode;    // 0 none (constant), 1 accumulate (+=, var_view.hpp:93), 2 assign (stage boundary)
-    int channel;     // reduction channel of a broadcast scalar's adjoint, or -1
-    int assigned;    // 1: an I_EQ in this program owns the adjoint write-back
-};
-
-constexpr int MAXS = 64;    // SSA slots per stage program
-constexpr int MAXL = 24;    // distinct leaves per stage
-constexpr int MAXCH = 8;    // reduction channels per stage
-
-struct StageArgs {
-    const DIns* prog;
-    const LeafDesc* leaves;
-    int nins, nleaves;
-    unsigned long long N;
-    int mode, term, root;
-    int nx, nm, ns;            // T_NORMAL operand slots
-    int mu_vec, sig_vec;       // operand is per-element (1) or one broadcast scalar (0)
-    const double* sig_ptr;     // scalar sigma value (device) when !sig_vec
-    double* out_vec;           // per-element value store of the stage root (may be null)
-    double* out_scalar;        // reduced value of the stage (T_SUM / T_PROD / T_NORMAL)
-    const double* seed_vec;    // per-element seed (vector-valued stage), or null
-    const double* seed_ptr;    // device scalar seed (inner stage), or null
-    double seed;               // host scalar seed (root stage)
-    double* red;               // [8] stage scratch: T_PROD {pnz, zeros, val}; T_NORMAL [1] = #invalid
-    const double* gate;        // if non-null and *gate != 0: adjoint sweep is a no-op (normal.hpp:457)
-    int nch, term_ch;
-    double* partials;
-    unsigned int* ticket;
-    double* scratch;           // BIG programs (scalar stages only): v | g | lacc in global memory
-};
-
-__device__ __forceinline__ double block_prod_all(double p, double* sm)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    p = warp_prod(p);
-    if (lane == 0) sm[warp] = p;
-    __syncthreads();
-    double r = 1.0;
-    if (warp == 0) r = warp_prod(lane < nwarp ? sm[lane] : 1.0);
-    __syncthreads();
-    return r;   // valid in thread 0
-}
-
-// BIG = false: program and leaf table staged in shared memory, node values in thread-local
-// storage.  BIG = true (scalar stages with more than MAXS nodes, e.g. ad::sum over a thousand
-// scalar Vars, test/integration/ad_inttest.cpp:143-156): one thread, everything in global memory.
-// STORE selects where a thread keeps its node values / adjoints / leaf accumulators:
-//   0 = thread-local arrays (fallback), 1 = dynamic shared memory, laid out [slot][thread] so
-//   that a warp access is conflict-free (default: local arrays of this size spill through L1 into
-//   L2/DRAM -- ncu showed 3.6x the algorithmic DRAM writes), 2 = global scratch (BIG programs).
-template <int STORE>
-__global__ void __launch_bounds__(128)
-stage_kernel(StageArgs a)
-{
-    constexpr bool BIG = STORE == 2;
-    extern __shared__ double s_dyn[];
-    __shared__ DIns s_prog_sm[BIG ? 1 : MAXS];
-    __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
-    __shared__ double s_red[32 * MAXCH];
-    __shared__ bool s_last;
-    const DIns* s_prog = BIG ? a.prog : s_prog_sm;
-    const LeafDesc* s_leaf = BIG ? a.leaves : s_leaf_sm;
-    if (!BIG) {
-        for (int k = threadIdx.x; k < a.nins; k += blockDim.x) s_prog_sm[k] = a.prog[k];
-        for (int k = threadIdx.x; k < a.nleaves; k += blockDim.x) s_leaf_sm[k] = a.leaves[k];
-        __syncthreads();
-    }
-
-    const bool fwd_out = a.mode & M_F;     // forward results are stored in this launch
-    bool back = a.mode & M_B;
-    double seed_s = a.seed_ptr ? *a.seed_ptr : a.seed;
-    bool gated = a.gate && *a.gate != 0.0;
-    double sig_s = 1.0;
-    if (a.term == T_NORMAL && !a.sig_vec) {
-        sig_s = a.sig_ptr ? *a.sig_ptr : 1.0;
-        if (!(sig_s > 0)) gated = true;                       // normal.hpp:147, 231, 344
-    }
-    if (a.term >= T_NORMAL && !a.seed_vec && seed_s == 0.0) back = false;   // normal.hpp:160, cauchy.hpp:151
-    double pr_pnz = 1.0, pr_zeros = 0.0, pr_val = 0.0;
-    if (a.term == T_PROD && back) { pr_pnz = a.red[0]; pr_zeros = a.red[1]; pr_val = a.red[2]; }
-
-    double acc[MAXCH];
-#pragma unroll
-    for (int c = 0; c < MAXCH; ++c) acc[c] = 0.0;
-    double p_nz = 1.0, p_zeros = 0.0;
-
-    double v_loc[STORE == 0 ? MAXS : 1], g_loc[STORE == 0 ? MAXS : 1], l_loc[STORE == 0 ? MAXL : 1];
-    const int vs = STORE == 1 ? (int)blockDim.x : 1;             // slot stride
-    double* vb = STORE == 0 ? v_loc : STORE == 1 ? s_dyn + threadIdx.x : a.scratch;
-    double* gb = STORE == 0 ? g_loc : vb + (size_t)a.nins * vs;
-    double* lb = STORE == 0 ? l_loc : gb + (size_t)a.nins * vs;
-#define V(k) vb[(k) * vs]
-#define G(k) gb[(k) * vs]
-#define LA(k) lb[(k) * vs]
-    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = tid; i < a.N; i += nth) {
-        // ------------------------------------------------ forward (feval)
-        for (int k = 0; k < a.nins; ++k) {
-            const DIns I = s_prog[k];
-            double r;
-            switch (I.code) {
-            case F_LEAF_V: r = s_leaf[I.leaf].val[i]; break;              // var_view.hpp:69
-            case F_LEAF_S: r = s_leaf[I.leaf].val[0]; break;
-            case F_CONST: r = I.imm; break;
-            case F_EQ: {                                                   // eq.hpp:89-92
-                r = V(I.a);
-                if (fwd_out) { const LeafDesc& L = s_leaf[I.leaf]; const_cast<double*>(L.val)[L.scalar ? 0 : i] = r; }
-                break;
-            }
-            case F_GLUE: r = V(I.b); break;                               // glue.hpp:67-71
-            case F_POW: r = pow_int((long)I.leaf, V(I.a)); break;
-            case F_POW2: { const double x = V(I.a); r = x * x; break; }
-#define U(FN) case F_UNARY + FN: r = Unary<FN>::f(V(I.a)); break;
-            U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
-            U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
-            U(FADB_SQUARE)
-#undef U
-            case F_UNARY + 16: r = 2 * V(I.a); break;                     // MockUnary
-            case F_BINARY + FADB_ADD: r = V(I.a) + V(I.b); break;         // binary.hpp:265-338
-            case F_BINARY + FADB_SUB: r = V(I.a) - V(I.b); break;
-            case F_BINARY + FADB_MUL: r = V(I.a) * V(I.b); break;
-            case F_BINARY + FADB_DIV: r = div_guarded(V(I.a), V(I.b)); break;
-            case F_BINARY + FADB_LT: r = V(I.a) < V(I.b) ? 1.0 : 0.0; break;     // binary.hpp:347-470
-            case F_BINARY + FADB_LE: r = V(I.a) <= V(I.b) ? 1.0 : 0.0; break;
-            case F_BINARY + FADB_GT: r = V(I.a) > V(I.b) ? 1.0 : 0.0; break;
-            case F_BINARY + FADB_GE: r = V(I.a) >= V(I.b) ? 1.0 : 0.0; break;
-            case F_BINARY + FADB_EQ: r = V(I.a) == V(I.b) ? 1.0 : 0.0; break;
-            case F_BINARY + FADB_NE: r = V(I.a) != V(I.b) ? 1.0 : 0.0; break;
-            case F_BINARY + FADB_AND: r = (V(I.a) != 0 && V(I.b) != 0) ? 1.0 : 0.0; break;
-            case F_BINARY + FADB_OR: r = (V(I.a) != 0 || V(I.b) != 0) ? 1.0 : 0.0; break;
-            case F_BINARY + 12: r = V(I.a) - 2 * V(I.b); break;           // MockBinary
-            // IfElseNode (if_else.hpp:64-68): the condition is a scalar, so the jump is uniform
-            case F_JZ: r = 0.0; if (V(I.a) == 0.0) k = I.b - 1; break;
-            case F_JMP: r = 0.0; k = I.b - 1; break;
-            case F_PHI: r = V(I.leaf) != 0.0 ? V(I.a) : V(I.b); break;
-            default: {                                                     // OpEqNode::feval, eq.hpp:240-247
-                const double old = V(I.b), e = V(I.a);
-                const int op = I.code - F_OPEQ;
-                r = op == FADB_ADD ? old + e : op == FADB_SUB ? old - e : op == FADB_MUL ? old * e : old / e;
-                if (fwd_out) { const LeafDesc& L = s_leaf[I.leaf]; const_cast<double*>(L.val)[i] = r; }
-                break;
-            }
-            }
-            V(k) = r;
-        }
-        // ------------------------------------------------ terminal, forward part
-        double nrm_d = 0, nrm_s = 1, nrm_z = 0;
-        if (a.term == T_SUM) acc[0] += V(a.root);
-        else if (a.term == T_PROD) { if (V(a.root) == 0) p_zeros += 1.0; else p_nz *= V(a.root); }
-        else if (a.term == T_NORMAL) {
-            nrm_d = V(a.nx) - V(a.nm);
-            nrm_s = V(a.ns);
-            if (a.sig_vec) {
-                if (!(nrm_s > 0)) acc[2] += 1.0;
-                nrm_z = nrm_d / nrm_s;
-                acc[0] += nrm_z * nrm_z;                       // normal.hpp:449, 546
-                acc[1] += log(nrm_s);
-            } else if (a.N == 1) {
-                nrm_z = nrm_d / nrm_s;                         // sss, normal.hpp:153-155
-                acc[0] += nrm_z * nrm_z;
-            } else {
-                acc[0] += nrm_d * nrm_d;                       // squaredNorm, normal.hpp:244
-            }
-        } else if (a.term == T_CAUCHY) {
-            // CauchyAdjLogPDFNode (stat/cauchy.hpp): -log(gamma + d^2/gamma) per element, gamma > 0
-            const double d = V(a.nx) - V(a.nm), gm = V(a.ns);
-            if (!(gm > 0)) { acc[2] += 1.0; if (!a.sig_vec) gated = true; }
-            acc[0] += a.N == 1 ? log(gm + (d * d) / gm)                 // cauchy.hpp:144-146
-                               : log(gm + (1. / gm) * (d * d));         // cauchy.hpp:216-217
-        } else if (a.term == T_UNIFORM) {
-            // UniformAdjLogPDFNode (stat/uniform.hpp): -log(max - min), min < x < max
-            const double x = V(a.nx), lo = V(a.nm), hi = V(a.ns);
-            if (!(lo < x && x < hi)) acc[2] += 1.0;
-            acc[0] += log(hi - lo);
-        } else if (a.term == T_BERNOULLI) {
-            // BernoulliAdjLogPDFNode (stat/bernoulli.hpp:119-141): x in {0,1}, 0 < p < 1
-            const double x = V(a.nx), p = V(a.nm);
-            const bool in_range = 0 < p && p < 1, zero_one = x == 0 || x == 1;
-            if (!in_range || !zero_one) acc[2] += 1.0;
-            if (!in_range) acc[0] += (p <= 0) ? (x == 0 ? 0.0 : -INFINITY) : (x == 1 ? 0.0 : -INFINITY);
-            else acc[0] += x == 0 ? log(1 - p) : x == 1 ? log(p) : -INFINITY;
-        } else if (fwd_out && a.out_vec) a.out_vec[i] = V(a.root);
-        if (!back) continue;
-
-        // ------------------------------------------------ adjoint sweep (beval)
-        for (int k = 0; k < a.nins; ++k) G(k) = 0.0;
-        for (int k = 0; k < a.nleaves; ++k) LA(k) = 0.0;
-        const double sd = a.seed_vec ? a.seed_vec[i] : seed_s;
-        if (!gated) {
-            if (a.term == T_NORMAL) {
-                const double x = V(a.nx), m = V(a.nm), s = nrm_s, d = nrm_d;
-                if (a.sig_vec) {
-                    const double s2 = s * s;
-                    if (a.mu_vec) { G(a.nx) += sd * (m - x) / s2; G(a.nm) += sd * d / s2; }      // :563-564
-                    else { G(a.nx) += (sd / s2) * (m - x); G(a.nm) += sd * (d / s2); }           // :471-474
-                    G(a.ns) += (sd / s) * (nrm_z * nrm_z - 1.);                                  // :468, 560
-                } else if (a.N == 1) {
-                    const double inv_s = 1. / s, z = d * inv_s;                                  // :158-171
-                    G(a.ns) += sd * (z * z - 1) * inv_s;
-                    const double adj = sd * z * inv_s;
-                    G(a.nm) += adj;
-                    G(a.nx) += -adj;
-                } else {
-                    const double inv_s = 1. / s, inv_s_sq = inv_s * inv_s, c = sd * inv_s_sq;
-                    G(a.nx) += c * (m - x);                                                      // :282, 371
-                    G(a.nm) += a.mu_vec ? c * d : sd * (d * inv_s_sq);                           // :370, 277
-                    G(a.ns) += sd * ((d * d) / (s * s) - 1.) * inv_s;                            // :273 per element
-                }
-            } else if (a.term == T_CAUCHY) {
-                const double d = V(a.nx) - V(a.nm), gm = V(a.ns);
-                if (a.N == 1) {                                                                   // cauchy.hpp:149-165
-                    const double inner = gm + (d * d) / gm;
-                    const double x0_adj = 2. * d / (gm * inner);
-                    G(a.ns) += sd * (1. / gm * (x0_adj * d - 1));
-                    G(a.nm) += sd * x0_adj;
-                    G(a.nx) += sd * -x0_adj;
-                } else {   // vector cases exactly as written in cauchy.hpp:220-237 (seed enters dx0, dgamma twice)
-                    const double dx = (-2. * sd) * d / (gm * gm + d * d);
-                    G(a.ns) += (-sd / gm) * (dx * d + 1);
-                    G(a.nm) += (-sd) * dx;
-                    G(a.nx) += dx;
-                }
-            } else if (a.term == T_UNIFORM) {                                                     // uniform.hpp:157-163
-                const double adj = sd / (V(a.ns) - V(a.nm));
-                G(a.ns) += -adj;
-                G(a.nm) += adj;
-            } else if (a.term == T_BERNOULLI) {                                                   // bernoulli.hpp:143-149
-                const double x = V(a.nx), p = V(a.nm);
-                G(a.nm) += x == 0 ? -sd / (1 - p) : sd / p;
-            } else if (a.term == T_PROD) {
-                const double e = V(a.root);                                                      // prod.hpp:194-207
-                G(a.root) = (e == 0) ? sd * ((pr_zeros > 1) ? 0.0 : pr_pnz) : sd * (pr_val / e);
-            } else {
-                G(a.root) = sd;
-            }
-            for (int k = a.nins - 1; k >= 0; --k) {
-                const DIns I = s_prog[k];
-                const double s = G(k);
-                switch (I.code) {
-                case F_LEAF_V: case F_LEAF_S: LA(I.leaf) += s; break;
-                case F_CONST: break;
-                case F_EQ: {                                                                      // eq.hpp:101-107
-                    const LeafDesc& L = s_leaf[I.leaf];
-                    if (L.scalar && a.N > 1) { G(I.a) += s + LA(I.leaf); break; }                // not produced by the planner
-                    const double tot = (L.adj[i] + LA(I.leaf)) + s;
-                    L.adj[i] = tot;
-                    LA(I.leaf) = 0.0;
-                    G(I.a) += tot;
-                    break;
-                }
-                case F_GLUE: G(I.b) += s; break;                                                  // lhs gets 0, glue.hpp:81-86
-                case F_POW: G(I.a) += pow_bmap((long)I.leaf, s, V(I.a), V(k)); break;            // pow.hpp:101-162
-                case F_POW2: { const double x = V(I.a); G(I.a) += 2. * s * (x == 0 ? 0 : V(k) / x); break; }
-#define U(FN) case F_UNARY + FN: G(I.a) += Unary<FN>::b(s, V(I.a), V(k)); break;                 /* unary.hpp:81-89 */
-                U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
-                U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
-                U(FADB_SQUARE)
-#undef U
-                case F_UNARY + 16: G(I.a) += s * 2; break;
-                // binary.hpp:120-136: rhs seed first, then lhs
-                case F_BINARY + FADB_ADD: G(I.b) += s; G(I.a) += s; break;
-                case F_BINARY + FADB_SUB: G(I.b) += -s; G(I.a) += s; break;
-                case F_BINARY + FADB_MUL: { const double x = V(I.a), y = V(I.b); G(I.b) += s * x; G(I.a) += s * y; break; }
-                case F_BINARY + FADB_DIV: { const double y = V(I.b); G(I.b) += div_guarded(-s * V(k), y); G(I.a) += div_guarded(s, y); break; }
-                case F_BINARY + 12: G(I.b) += -2. * s; G(I.a) += s; break;                        // MockBinary
-                // comparisons: no adjoint (binary.hpp:124)
-                case F_BINARY + FADB_LT: case F_BINARY + FADB_LE: case F_BINARY + FADB_GT: case F_BINARY + FADB_GE:
-                case F_BINARY + FADB_EQ: case F_BINARY + FADB_NE: case F_BINARY + FADB_AND: case F_BINARY + FADB_OR: break;
-                // IfElseNode::beval (if_else.hpp:70-78): only the taken branch is swept
-                case F_PHI:
-                    if (V(I.leaf) != 0.0) { G(I.a) += s; k = (int)I.imm + 1; }    // skip the else branch
-                    else G(I.b) += s;
-                    break;
-                case F_JMP: if (V(I.a) == 0.0) k = I.leaf + 1; break;             // else was taken: skip the if branch
-                case F_JZ: break;
-                default: {                                                         // OpEqNode::beval, eq.hpp:249-271
-                    const LeafDesc& L = s_leaf[I.leaf];
-                    const double tot = (L.adj[i] + LA(I.leaf)) + s;
-                    LA(I.leaf) = 0.0;
-                    const double old = V(I.b), e = V(I.a);
-                    const int op = I.code - F_OPEQ;
-                    double ls, rs;
-                    if (op == FADB_ADD) { ls = tot; rs = tot; }
-                    else if (op == FADB_SUB) { ls = tot; rs = -tot; }
-                    else if (op == FADB_MUL) { ls = tot * e; rs = tot * old; }
-                    else { ls = tot / e; rs = -tot * old / (e * e); }
-                    G(I.a) += rs;
-                    L.adj[i] = ls;                                                 // reset_adj(); beval(lseed)
-                    const_cast<double*>(L.val)[i] = old;                           // the previous value is restored
-                    break;
-                }
-                }
-            }
-        }
-        // ------------------------------------------------ leaf write-back: adj += seed (var_view.hpp:91-94)
-        for (int k = 0; k < a.nleaves; ++k) {
-            const LeafDesc& L = s_leaf[k];
-            if (L.adj_mode == 0) continue;
-            if (L.assigned) {          // reads that precede the assignment in program order
-                if (LA(k) != 0.0) L.adj[i] += LA(k);
-                continue;
-            }
-            if (L.scalar && a.N > 1) { acc[L.channel] += LA(k); continue; }
-            if (L.adj_mode == 2) L.adj[i] = LA(k);
-            else if (!gated) L.adj[i] += LA(k);
-        }
-    }
-
-    // ---------------------------------------------------- grid reduction + scalar epilogue
-    if (a.nch == 0 && a.term != T_PROD) return;
-    if (a.term == T_PROD && (a.mode & M_F)) {
-        const double bp = block_prod_all(p_nz, s_red);
-        acc[0] = p_zeros;
-        block_sum<MAXCH>(acc, s_red);
-        if (threadIdx.x == 0) {
-            a.partials[(size_t)blockIdx.x * (MAXCH + 1) + MAXCH] = bp;
-            for (int c = 0; c < MAXCH; ++c) a.partials[(size_t)blockIdx.x * (MAXCH + 1) + c] = acc[c];
-            __threadfence();
-            s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        double p = 1.0, z = 0.0;
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            p *= __ldcg(&a.partials[(size_t)b * (MAXCH + 1) + MAXCH]);
-            z += __ldcg(&a.partials[(size_t)b * (MAXCH + 1)]);
-        }
-        p = block_prod_all(p, s_red);
-        double zz[1] = {z};
-        block_sum<1>(zz, s_red);
-        if (threadIdx.x == 0) {
-            a.red[0] = p; a.red[1] = zz[0]; a.red[2] = (zz[0] > 0) ? 0.0 : p;                    // prod.hpp:178
-            a.out_scalar[0] = a.red[2];
-            *a.ticket = 0u;
-        }
-        return;
-    }
-    block_sum<MAXCH>(acc, s_red);
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < MAXCH; ++c) a.partials[(size_t)blockIdx.x * (MAXCH + 1) + c] = acc[c];
-        __threadfence();
-        s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double tot[MAXCH];
-#pragma unroll
-    for (int c = 0; c < MAXCH; ++c) tot[c] = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-#pragma unroll
-        for (int c = 0; c < MAXCH; ++c) tot[c] += __ldcg(&a.partials[(size_t)b * (MAXCH + 1) + c]);
-    block_sum<MAXCH>(tot, s_red);
-    if (threadIdx.x != 0) return;
-    *a.ticket = 0u;
-    if (a.mode & M_F) {
-        if (a.term == T_SUM) a.out_scalar[0] = tot[0];
-        else if (a.term == T_NORMAL) {
-            double val;
-            if (a.sig_vec) {
-                a.red[1] = tot[2];
-                val = (tot[2] != 0.0) ? -INFINITY : -0.5 * tot[0] - tot[1];                      // normal.hpp:451, 548
-            } else {
-                a.red[1] = (sig_s > 0) ? 0.0 : 1.0;
-                if (!(sig_s > 0)) val = -INFINITY;
-                else if (a.N == 1) val = -0.5 * tot[0] - log(sig_s);
-                else val = -0.5 * (tot[0] / (sig_s * sig_s)) - (double)a.N * log(sig_s);         // normal.hpp:245-246
-            }
-            a.out_scalar[0] = val;
-        } else if (a.term == T_CAUCHY || a.term == T_UNIFORM) {
-            a.red[1] = tot[2];
-            a.out_scalar[0] = tot[2] != 0.0 ? -INFINITY : -tot[0];
-        } else if (a.term == T_BERNOULLI) {
-            a.red[1] = tot[2];
-            a.out_scalar[0] = tot[0];
-        }
-    }
-    if (a.mode & M_B) {
-        for (int k = 0; k < a.nleaves; ++k) {
-            const LeafDesc& L = s_leaf[k];
-            if (L.channel < 0 || L.adj_mode == 0) continue;
-            const bool skip = gated || !back || (a.term > T_NORMAL && (a.mode & M_F) && tot[2] != 0.0);
-            if (L.adj_mode == 2) L.adj[0] = skip ? 0.0 : tot[L.channel];
-            else if (!skip) L.adj[0] += tot[L.channel];
-        }
-    }
-}
-
-#undef V
-#undef G
-#undef LA
 
 // ------------------------------------------------------------------------ DotNode kernels
 // dot.hpp:89-104: V = L R; R_adj (+)= L^T A; L_adj (+)= A R^T.  Column-major, naive (one thread
@@ -561,6 +150,9 @@ struct Stage {
     double* mval = nullptr;        // materialised output value [out_size]
     double* madj = nullptr;        // materialised output adjoint [out_size] (inner stages)
     DIns* d_prog = nullptr;
+    std::vector<DIns> enc;         // device encoding of `prog` (also the text of the specialised kernel)
+    JitKernel jit[4];              // specialised kernels by mode (M_F, M_B, M_FB), compiled on first use
+    int jit_state[4] = {0, 0, 0, 0};   // 0 untried, 1 ready, -1 not specialisable / compile failed
     LeafDesc* d_leaves = nullptr;
     double* d_red = nullptr;       // [8]
     double* d_sig = nullptr;       // device copy of a constant scalar sigma
@@ -1004,6 +596,31 @@ struct fadb_expr {
         return o.str();
     }
 
+    // device encoding of a stage program (host only; needs the planner's leaf table)
+    static void encode_stage(Stage& st)
+    {
+        std::vector<DIns>& enc = st.enc;
+        enc.assign(st.prog.size(), DIns{});
+        for (size_t k = 0; k < st.prog.size(); ++k) {
+            const Ins& I = st.prog[k];
+            DIns D{0, (short)I.a, (short)I.b, (short)I.leaf, I.imm};
+            switch (I.op) {
+            case I_LEAF: D.code = st.leaves[I.leaf].scalar ? F_LEAF_S : F_LEAF_V; break;
+            case I_CONST: D.code = F_CONST; break;
+            case I_EQ: D.code = F_EQ; break;
+            case I_GLUE: D.code = F_GLUE; break;
+            case I_POW: D.code = I.fn == 2 ? F_POW2 : F_POW; D.leaf = (short)I.fn; break;
+            case I_UNARY: D.code = (short)(F_UNARY + (I.fn == FADB_MOCK2X ? 16 : I.fn)); break;
+            case I_BINARY: D.code = (short)(F_BINARY + (I.fn == FADB_MOCKB ? 12 : I.fn)); break;
+            case I_JZ: D.code = F_JZ; break;
+            case I_JMP: D.code = F_JMP; break;
+            case I_PHI: D.code = F_PHI; break;
+            default: D.code = (short)(F_OPEQ + I.fn); break;
+            }
+            enc[k] = D;
+        }
+    }
+
     // ---------------------------------------------------------------- device state
     int dev_alloc(size_t bytes, void** out)
     {
@@ -1039,27 +656,9 @@ struct fadb_expr {
             int rc;
             if ((rc = dev_alloc(std::max<size_t>(1, st.prog.size()) * sizeof(DIns), (void**)&st.d_prog))) return rc;
             if ((rc = dev_alloc(std::max<size_t>(1, st.leaves.size()) * sizeof(LeafDesc), (void**)&st.d_leaves))) return rc;
-            std::vector<DIns> enc(st.prog.size());
-            for (size_t k = 0; k < st.prog.size(); ++k) {
-                const Ins& I = st.prog[k];
-                DIns D{0, (short)I.a, (short)I.b, (short)I.leaf, I.imm};
-                switch (I.op) {
-                case I_LEAF: D.code = st.leaves[I.leaf].scalar ? F_LEAF_S : F_LEAF_V; break;
-                case I_CONST: D.code = F_CONST; break;
-                case I_EQ: D.code = F_EQ; break;
-                case I_GLUE: D.code = F_GLUE; break;
-                case I_POW: D.code = I.fn == 2 ? F_POW2 : F_POW; D.leaf = (short)I.fn; break;
-                case I_UNARY: D.code = (short)(F_UNARY + (I.fn == FADB_MOCK2X ? 16 : I.fn)); break;
-                case I_BINARY: D.code = (short)(F_BINARY + (I.fn == FADB_MOCKB ? 12 : I.fn)); break;
-                case I_JZ: D.code = F_JZ; break;
-                case I_JMP: D.code = F_JMP; break;
-                case I_PHI: D.code = F_PHI; break;
-                default: D.code = (short)(F_OPEQ + I.fn); break;
-                }
-                enc[k] = D;
-            }
+            encode_stage(st);
+            std::vector<DIns>& enc = st.enc;
             FADB_CUDA(cudaMemcpyAsync(st.d_prog, enc.data(), enc.size() * sizeof(DIns), cudaMemcpyHostToDevice, c.stream));
-            FADB_CUDA(cudaStreamSynchronize(c.stream));     // `enc` is a temporary
             FADB_CUDA(cudaMemcpyAsync(st.d_leaves, st.leaves.data(), st.leaves.size() * sizeof(LeafDesc), cudaMemcpyHostToDevice, c.stream));
             if (st.term == T_NORMAL && st.sig_is_const) {
                 if ((rc = dev_alloc(sizeof(double), (void**)&st.d_sig))) return rc;
@@ -1099,6 +698,34 @@ struct fadb_expr {
         return FADB_OK;
     }
 
+    // ---------------------------------------------------------------- specialisation (jit.cu)
+    // The compile-time half of a stage: program, leaf attributes, terminal configuration, mode.
+    // Pointers, N and seeds are NOT part of it.  false: this stage stays on the interpreter.
+    static bool jit_program_text(const Stage& st, int mode, std::string& out)
+    {
+        if (st.big || st.enc.empty() || st.enc.size() > (size_t)MAXS || st.leaves.size() > (size_t)MAXL) return false;
+        std::ostringstream o;
+        char buf[64];
+        o << "\n#define JIT_NINS " << st.enc.size() << "\n#define JIT_NLEAVES " << st.leaves.size()
+          << "\n#define JIT_MODE " << mode << "\n#define JIT_TERM " << st.term << "\n#define JIT_ROOT " << st.root
+          << "\n#define JIT_NX " << st.nx << "\n#define JIT_NM " << st.nm << "\n#define JIT_NS " << st.ns
+          << "\n#define JIT_MU_VEC " << st.mu_vec << "\n#define JIT_SIG_VEC " << st.sig_vec << "\n#define JIT_NCH " << st.nch
+          << "\n__device__ constexpr DIns JIT_PROG[JIT_NINS] = {\n";
+        for (const DIns& d : st.enc) {
+            if (d.code == F_JZ || d.code == F_JMP || d.code == F_PHI) return false;      // control flow: loops cannot unroll
+            if (!std::isfinite(d.imm)) return false;
+            snprintf(buf, sizeof buf, "%a", d.imm);                                      // hex float: exact
+            o << "  {" << d.code << ", " << d.a << ", " << d.b << ", " << d.leaf << ", " << buf << "},\n";
+        }
+        o << "};\n__device__ constexpr JitLeaf JIT_LEAF[JIT_NLEAVES > 0 ? JIT_NLEAVES : 1] = {\n";
+        for (const LeafDesc& l : st.leaves)
+            o << "  {" << l.scalar << ", " << l.adj_mode << ", " << l.channel << ", " << l.assigned << "},\n";
+        if (st.leaves.empty()) o << "  {0, 0, -1, 0}\n";
+        o << "};\n";
+        out = o.str();
+        return true;
+    }
+
     // ---------------------------------------------------------------- execution
     int run_map(Context& c, Stage& st, int mode, double seed, const double* seed_vec, const double* seed_ptr)
     {
@@ -1121,6 +748,21 @@ struct fadb_expr {
             c.launches++;
             FADB_CUDA(cudaGetLastError());
             return FADB_OK;
+        }
+        if (jit_enabled() && st.jit_state[mode] >= 0) {
+            // specialised kernel of this stage program (jit.cu): compiled once per (program, mode, device)
+            if (st.jit_state[mode] == 0) {
+                std::string text;
+                st.jit_state[mode] = (jit_program_text(st, mode, text) && jit_get(c, text, &st.jit[mode]) == FADB_OK) ? 1 : -1;
+            }
+            if (st.jit_state[mode] == 1) {
+                int grid = grid_for(c, st.N, st.jit[mode].per_sm, 128);
+                if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
+                int rc = jit_launch(st.jit[mode], (unsigned)grid, 128, c.stream, &a);
+                if (rc) return rc;
+                c.launches++;
+                return FADB_OK;
+            }
         }
         const int threads = st.N >= 4096 ? 128 : 32;
         const size_t smem = (2 * st.prog.size() + st.leaves.size()) * threads * sizeof(double);
@@ -1617,6 +1259,24 @@ int fadb_expr_plan(fadb_expr* e, int root, size_t out_cache_size[2])
     int rc = e->do_plan(root);
     if (rc) { set_error("fastad_b200: cannot plan expression: " + e->err); return rc; }
     if (out_cache_size) { out_cache_size[0] = e->cache_vals; out_cache_size[1] = e->cache_adjs; }
+    return FADB_OK;
+}
+
+// Text of the compile-time constants that specialise stage `stage` of the plan for `mode`
+// (1 forward, 2 backward, 3 fused); host only.  FADB_ERR_UNSUPPORTED: the stage is not a
+// specialisable elementwise program (control flow, non-finite immediates, a dot / dense stage).
+int fadb_expr_jit_program(fadb_expr* e, int stage, int mode, char* buf, size_t cap)
+{
+    EXPR_REQUIRE(e, e && buf && cap > 0, "fadb_expr_jit_program: null argument");
+    EXPR_REQUIRE(e, e->planned, "fadb_expr_jit_program: plan first");
+    EXPR_REQUIRE(e, stage >= 0 && stage < (int)e->plan.size() && mode >= 1 && mode <= 3, "fadb_expr_jit_program: bad stage or mode");
+    Stage& st = *e->plan[stage];
+    std::string text;
+    if (st.type != 0) { set_error("fastad_b200: not an elementwise stage"); return FADB_ERR_UNSUPPORTED; }
+    if (st.enc.empty()) fadb_expr::encode_stage(st);
+    if (!fadb_expr::jit_program_text(st, mode, text)) { set_error("fastad_b200: stage is not specialisable"); return FADB_ERR_UNSUPPORTED; }
+    if (text.size() + 1 > cap) { set_error("fastad_b200: buffer too small"); return FADB_ERR_ARG; }
+    memcpy(buf, text.c_str(), text.size() + 1);
     return FADB_OK;
 }
 

@@ -1,0 +1,227 @@
+// jit.cu — bind-time specialisation of stage kernels with NVRTC.
+//
+// The reference gets a fused evaluator for every expression from the C++ compiler (expression
+// templates).  A g++-built host program has no device compiler, so the generic path
+// of expr.cu would be left with the tape interpreter (~8 % of the HBM roofline).  Here the planner's
+// stage program is turned into compile-time constants and the SAME kernel source (stage_kernel.cuh,
+// embedded in this library at build time) is compiled for sm_100a by NVRTC on first use: loops unroll,
+// switches fold, node values sit in registers.  Kernels are cached per device by program text; leaf
+// pointers, sizes and seeds are launch arguments, so rebinding never recompiles.
+//
+// libnvrtc and the driver entry points are resolved at run time (dlopen / cudaGetDriverEntryPoint):
+// the library itself links only against cudart and still loads on a machine without a driver.  If
+// NVRTC is missing the stage runs on the interpreter — same CUDA path, same results, slower.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "jit.h"
+#include "jit_sources.inc"
+
+namespace fadb {
+
+namespace {
+
+struct Nvrtc {
+    void* h = nullptr;
+    decltype(&nvrtcCreateProgram) create = nullptr;
+    decltype(&nvrtcCompileProgram) compile = nullptr;
+    decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+    decltype(&nvrtcGetCUBIN) cubin = nullptr;
+    decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+    decltype(&nvrtcGetProgramLog) log = nullptr;
+    decltype(&nvrtcDestroyProgram) destroy = nullptr;
+    decltype(&nvrtcGetErrorString) err = nullptr;
+    bool ok = false;
+};
+struct Driver {
+    CUresult (*module_load)(CUmodule*, const void*) = nullptr;
+    CUresult (*module_unload)(CUmodule) = nullptr;
+    CUresult (*module_func)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*launch)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*occupancy)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*func_attr)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    bool ok = false;
+};
+struct Entry { CUmodule mod = nullptr; CUfunction fn = nullptr; int per_sm = 1; int regs = 0, local_bytes = 0; bool failed = false; };
+
+std::mutex g_mu;
+Nvrtc g_rtc;
+Driver g_drv;
+int g_state = 0;            // 0 untried, 1 ready, -1 unavailable
+int g_enabled = -1;         // -1: from FADB_NO_JIT on first use
+std::string g_why, g_log;
+std::unordered_map<std::string, Entry> g_cache;
+unsigned long long g_compiled = 0, g_hits = 0, g_failed = 0, g_launched = 0;
+
+template <class F> bool sym(void* h, const char* name, F& out) { out = reinterpret_cast<F>(dlsym(h, name)); return out != nullptr; }
+template <class F> bool drv(const char* name, F& out)
+{
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !p) {
+        cudaGetLastError();
+        return false;
+    }
+    out = reinterpret_cast<F>(p);
+    return true;
+}
+
+bool init_locked()
+{
+    if (g_state != 0) return g_state > 0;
+    g_state = -1;
+    const char* env = getenv("FADB_NVRTC_PATH");
+    const char* names[] = {env, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* n : names) {
+        if (!n) continue;
+        g_rtc.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_rtc.h) break;
+    }
+    if (!g_rtc.h) { g_why = "libnvrtc not found (set FADB_NVRTC_PATH)"; return false; }
+    Nvrtc& r = g_rtc;
+    if (!(sym(r.h, "nvrtcCreateProgram", r.create) && sym(r.h, "nvrtcCompileProgram", r.compile) &&
+          sym(r.h, "nvrtcGetCUBINSize", r.cubin_size) && sym(r.h, "nvrtcGetCUBIN", r.cubin) &&
+          sym(r.h, "nvrtcGetProgramLogSize", r.log_size) && sym(r.h, "nvrtcGetProgramLog", r.log) &&
+          sym(r.h, "nvrtcDestroyProgram", r.destroy) && sym(r.h, "nvrtcGetErrorString", r.err))) {
+        g_why = "libnvrtc lacks a required entry point";
+        return false;
+    }
+    Driver& d = g_drv;
+    if (!(drv("cuModuleLoadData", d.module_load) && drv("cuModuleUnload", d.module_unload) &&
+          drv("cuModuleGetFunction", d.module_func) && drv("cuLaunchKernel", d.launch) &&
+          drv("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.occupancy) && drv("cuFuncGetAttribute", d.func_attr))) {
+        g_why = "driver entry points unavailable";
+        return false;
+    }
+    g_state = 1;
+    return true;
+}
+
+}  // namespace
+
+bool jit_enabled()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_enabled < 0) { const char* e = getenv("FADB_NO_JIT"); g_enabled = (e && e[0] == '1') ? 0 : 1; }
+    return g_enabled == 1;
+}
+
+std::string jit_source(const std::string& program) { return std::string(kJitPrelude) + program + kJitKernel; }
+
+// Returns 0 and a launchable kernel, or a negative code (caller falls back to the interpreter).
+int jit_get(const Context& c, const std::string& program, JitKernel* out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!init_locked()) return FADB_ERR_STATE;
+    const std::string key = std::to_string(c.device) + "|" + program;
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) {
+        if (it->second.failed) return FADB_ERR_STATE;
+        ++g_hits;
+        out->fn = it->second.fn; out->per_sm = it->second.per_sm; out->regs = it->second.regs; out->local_bytes = it->second.local_bytes;
+        return FADB_OK;
+    }
+    Entry e;
+    e.failed = true;
+    const std::string src = jit_source(program);
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr);
+    if (r == NVRTC_SUCCESS) {
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177"};
+        r = g_rtc.compile(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+        size_t ls = 0;
+        if (g_rtc.log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1) { g_log.resize(ls); g_rtc.log(prog, &g_log[0]); }
+        if (r == NVRTC_SUCCESS) {
+            size_t n = 0;
+            std::vector<char> bin;
+            if (g_rtc.cubin_size(prog, &n) == NVRTC_SUCCESS && n > 0) {
+                bin.resize(n);
+                if (g_rtc.cubin(prog, bin.data()) == NVRTC_SUCCESS && g_drv.module_load(&e.mod, bin.data()) == CUDA_SUCCESS &&
+                    g_drv.module_func(&e.fn, e.mod, "fadb_stage_jit") == CUDA_SUCCESS) {
+                    if (g_drv.occupancy(&e.per_sm, e.fn, 128, 0) != CUDA_SUCCESS || e.per_sm < 1) e.per_sm = 1;
+                    g_drv.func_attr(&e.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, e.fn);
+                    g_drv.func_attr(&e.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, e.fn);
+                    e.failed = false;
+                }
+            }
+        } else {
+            g_why = std::string("NVRTC: ") + g_rtc.err(r);
+        }
+        g_rtc.destroy(&prog);
+    }
+    g_cache.emplace(key, e);
+    if (e.failed) { ++g_failed; return FADB_ERR_STATE; }
+    ++g_compiled;
+    out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes;
+    return FADB_OK;
+}
+
+int jit_launch(const JitKernel& k, unsigned grid, unsigned block, cudaStream_t st, void* args_struct)
+{
+    void* params[1] = {args_struct};
+    const CUresult r = g_drv.launch(reinterpret_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, 0, reinterpret_cast<CUstream>(st), params, nullptr);
+    if (r != CUDA_SUCCESS) { set_error("fastad_b200: launch of a specialised stage kernel failed (CUresult " + std::to_string((int)r) + ")"); return FADB_ERR_CUDA; }
+    ++g_launched;
+    return FADB_OK;
+}
+
+}  // namespace fadb
+
+using namespace fadb;
+
+extern "C" int fadb_jit_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_enabled < 0) { const char* e = getenv("FADB_NO_JIT"); g_enabled = (e && e[0] == '1') ? 0 : 1; }
+    const int prev = g_enabled;
+    g_enabled = on ? 1 : 0;
+    return prev;
+}
+extern "C" int fadb_jit_stats(unsigned long long out[4])
+{
+    if (!out) return FADB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_mu);
+    out[0] = g_compiled; out[1] = g_hits; out[2] = g_failed; out[3] = g_launched;
+    return FADB_OK;
+}
+extern "C" const char* fadb_jit_diagnostics(void)
+{
+    static thread_local std::string s;
+    std::lock_guard<std::mutex> lk(g_mu);
+    s = (g_state < 0 ? "unavailable: " : "") + g_why + (g_log.empty() ? "" : "\n" + g_log);
+    return s.c_str();
+}
+// Compiles `program` (the text expr.cu generates for one stage and mode) to a cubin WITHOUT a device
+// or a driver: the CPU-side build check of the specialisation path (tests, __graft_entry__.build()).
+extern "C" int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, char* log, size_t log_cap)
+{
+    if (!program) return FADB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_state == 0) init_locked();
+    if (!g_rtc.create || !g_rtc.compile) { set_error("fastad_b200: libnvrtc not available"); return FADB_ERR_STATE; }
+    const std::string src = jit_source(program);
+    nvrtcProgram prog = nullptr;
+    if (g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return FADB_ERR_STATE;
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", "--ptxas-options=-v"};
+    const nvrtcResult r = g_rtc.compile(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    size_t ls = 0;
+    if (g_rtc.log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1 && log && log_cap) {
+        std::string l(ls, '\0');
+        g_rtc.log(prog, &l[0]);
+        snprintf(log, log_cap, "%s", l.c_str());
+    } else if (log && log_cap) log[0] = 0;
+    size_t n = 0;
+    if (r == NVRTC_SUCCESS) g_rtc.cubin_size(prog, &n);
+    if (cubin_bytes) *cubin_bytes = n;
+    g_rtc.destroy(&prog);
+    if (r != NVRTC_SUCCESS) { set_error(std::string("fastad_b200: NVRTC: ") + g_rtc.err(r)); return FADB_ERR_STATE; }
+    return FADB_OK;
+}

@@ -23,8 +23,10 @@
  */
 #ifndef FASTAD_B200_H
 #define FASTAD_B200_H
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -57,6 +59,7 @@ enum { FADB_ADD = 0, FADB_SUB, FADB_MUL, FADB_DIV,
        FADB_LT, FADB_LE, FADB_GT, FADB_GE, FADB_EQ, FADB_NE, FADB_AND, FADB_OR, FADB_BINARY_COUNT,
        FADB_MOCKB = 100 /* test functor f(x,y)=x-2y (base_fixture.hpp:24-46) */ };
 
+#ifndef __CUDACC_RTC__   /* device code (NVRTC, csrc/jit.cu) needs only the constants above */
 /* ------------------------------------------------------------------ lifecycle / runtime */
 /* Binds the library to the current CUDA device (cudaSetDevice(device)), creates its stream
  * and workspace.  Idempotent. */
@@ -285,6 +288,28 @@ int fadb_expr_feval(fadb_expr*, double* host_value);
 int fadb_expr_beval(fadb_expr*, double seed, const double* seed_dev);
 int fadb_expr_autodiff(fadb_expr*, double seed, const double* seed_dev, double* host_value);
 int fadb_expr_value_ptr(fadb_expr*, const double** dev_value, size_t* size);
+
+/* ---- bind-time kernel specialisation (csrc/jit.cu) ------------------------------------------
+ * The reference's expression templates hand every expression its own fused evaluator at compile
+ * time (bind.hpp / eval.hpp instantiate feval/beval per expression type).  For host code built
+ * without nvcc the library does the same at bind time: the stage program the planner produced is
+ * spliced, as compile-time constants, into the stage-kernel source embedded in this library and
+ * compiled for sm_100a with NVRTC on first use (cached per device and program).  Stages NVRTC
+ * cannot take (if_else control flow, programs over 64 nodes) and machines without libnvrtc run
+ * the same source as a tape interpreter.  On by default; FADB_NO_JIT=1 or fadb_jit_enable(0)
+ * select the interpreter.
+ *   fadb_jit_enable         switch at run time, returns the previous setting
+ *   fadb_jit_stats          out = {kernels compiled, cache hits, compile failures, launches}
+ *   fadb_jit_diagnostics    why the layer is unavailable / the last NVRTC log
+ *   fadb_expr_jit_program   the generated constants of one planned stage (host only)
+ *   fadb_jit_compile_only   NVRTC-compile such a text to a cubin; needs no device (build check) */
+int fadb_jit_enable(int on);
+int fadb_jit_stats(unsigned long long out[4]);
+const char* fadb_jit_diagnostics(void);
+int fadb_expr_jit_program(fadb_expr*, int stage, int mode, char* buf, size_t cap);
+int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, char* log, size_t log_cap);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

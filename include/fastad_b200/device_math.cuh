@@ -5,12 +5,21 @@
 // order of the reference so that per-instance results agree to the last few ulp (CUDA's
 // libdevice exp/log/erf differ from glibc's by <= 1-2 ulp).
 #pragma once
+#ifndef __CUDACC_RTC__   // NVRTC (specialised stage kernels, csrc/jit.cu) gets these files pre-concatenated
 #include <cuda_runtime.h>
 
 #include <cmath>
 
 #include "../fastad_b200.h"
 #include "fastmath.cuh"
+#else
+#ifndef INFINITY
+#define INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#endif
+#ifndef NAN
+#define NAN __longlong_as_double(0x7ff8000000000000LL)
+#endif
+#endif
 
 namespace fadb {
 

@@ -1,5 +1,6 @@
-"""GPU parity of the generic expression path (builder -> planner -> interpreter kernels, and
-the fast-path dispatch) against the CPU oracle, on the same seeded inputs."""
+"""GPU parity of the generic expression path (builder -> planner -> stage kernels, and the fast-path
+dispatch) against the CPU oracle, on the same seeded inputs.  Every case runs twice: on the
+bind-time specialised kernels (NVRTC, csrc/jit.cu -- the default) and on the tape interpreter."""
 import numpy as np
 import pytest
 
@@ -37,11 +38,23 @@ def _close(a, b, rtol, what, floor=1e-300):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * max(scale, floor), err_msg=what)
 
 
+@pytest.fixture(params=["specialised", "interpreter"])
+def engine(fb, request):
+    prev = fb.jit_enable(request.param == "specialised")
+    yield request.param
+    fb.jit_enable(prev)
+
+
 @pytest.mark.parametrize("name", sorted(exprs.CASES))
-def test_expr_matches_oracle(fb, name):
+def test_expr_matches_oracle(fb, engine, name):
     build = exprs.CASES[name]
     ov, oadj, oval, _ = _run(build, O.OracleExpr)
+    before = fb.jit_stats()
     gv, gadj, gval, ge = _run(build, fb.Expr)
+    after = fb.jit_stats()
+    assert after["failed"] == before["failed"], fb.lib().fadb_jit_diagnostics().decode()
+    if engine == "interpreter":
+        assert after["launched"] == before["launched"]
     dense = name.startswith(("dense_normal", "det_", "log_det", "wishart"))
     rtol = 1e-11 if name.startswith("black_scholes") or dense else 1e-12
     _close(gv, ov, rtol, name + " value")
@@ -84,6 +97,37 @@ def test_expr_feval_then_beval_equals_autodiff(fb, name):
     np.testing.assert_array_equal(v1, v2)
     for x, y in zip(a1, a2):
         np.testing.assert_allclose(x, y, rtol=1e-14, atol=0)
+
+
+def test_expr_specialised_kernels_are_the_default_and_bit_identical_to_interpreter(fb):
+    # same source, same flags (-fmad=false): the specialised kernel and the interpreter must agree to the bit
+    res = {}
+    for on in (True, False):
+        prev = fb.jit_enable(on)
+        try:
+            s0 = fb.jit_stats()
+            _, adj, val, e = _run(exprs.CASES["vec_sum_chain_100k"], fb.Expr)
+            v = e.autodiff(0.0)                      # second sweep with seed 0: cache hit, adjoints unchanged
+            s1 = fb.jit_stats()
+            res[on] = (v, adj, val, s1["launched"] - s0["launched"], s1["compiled"] + s1["hits"] - s0["compiled"] - s0["hits"])
+        finally:
+            fb.jit_enable(prev)
+    assert res[True][3] == 2 and res[True][4] >= 1, (res[True][3:], fb.lib().fadb_jit_diagnostics().decode())
+    assert res[False][3] == 0
+    np.testing.assert_array_equal(res[True][0], res[False][0])
+    for a, b in zip(res[True][1], res[False][1]):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_expr_if_else_stays_on_the_interpreter(fb):
+    # control flow cannot be unrolled: the stage is not specialised, results still match the oracle
+    name = next(n for n in sorted(exprs.CASES) if "if_else" in n)
+    s0 = fb.jit_stats()
+    gv, _, _, _ = _run(exprs.CASES[name], fb.Expr)
+    ov, _, _, _ = _run(exprs.CASES[name], O.OracleExpr)
+    s1 = fb.jit_stats()
+    assert s1["failed"] == s0["failed"]
+    _close(gv, ov, 1e-12, name)
 
 
 def test_expr_normal_invalid_sigma_generic_path(fb):

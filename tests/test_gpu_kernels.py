@@ -306,6 +306,29 @@ def test_black_scholes_accumulate_and_host_entry(fb):
         np.testing.assert_array_equal(h, host(g))
 
 
+def test_black_scholes_host_entry_page_locked_direct_path(fb):
+    # all 13 arrays page-locked: the resident kernel runs on their device aliases (one launch, no copies);
+    # mixed page-locked / pageable arrays: staged path.  Both must return the resident call's bits.
+    import torch
+    n = (1 << 18) + 77                                      # more than one staged chunk is not needed here
+    inp = synth.black_scholes_inputs(n)
+    keys = ("S", "K", "sigma", "tau", "r")
+    out1 = fb.black_scholes(*(dev(inp[k]) for k in keys))
+    pin_in = [torch.from_numpy(inp[k]).pin_memory() for k in keys]
+    pin_out = [torch.full((n,), -7.0, dtype=torch.float64).pin_memory() for _ in range(8)]
+    l0 = fb.lib().fadb_launch_count()
+    fb.black_scholes_host(*[t.numpy() for t in pin_in], [t.numpy() for t in pin_out])
+    assert fb.lib().fadb_launch_count() - l0 == 1          # one kernel launch, nothing staged
+    for h, g in zip(pin_out, out1):
+        np.testing.assert_array_equal(h.numpy(), host(g))
+    mixed_out = [t.numpy() if k % 2 else np.zeros(n) for k, t in enumerate(pin_out)]
+    for t in pin_out:
+        t.fill_(-7.0)
+    fb.black_scholes_host(*[t.numpy() for t in pin_in], mixed_out)
+    for h, g in zip(mixed_out, out1):
+        np.testing.assert_array_equal(h, host(g))
+
+
 def test_black_scholes_full_size_put_call_parity(fb):
     # BASELINE config 1 size: 2^20 options; size-independent property C - P = S - PV
     n = 1 << 20

@@ -111,3 +111,45 @@ def test_builder_rejects_bad_shapes(F):
         e.dot(M, v)
     with pytest.raises(F.FadbError):
         e.unary("exp", 12345)
+
+
+# ---------------------------------------------------------------- bind-time specialisation (csrc/jit.cu)
+@pytest.mark.parametrize("name", ["vec_sum_chain_100k", "black_scholes_call", "placeholders", "normal_vec_sigma_expr"])
+def test_stage_program_specialises_to_register_code(F, name):
+    """NVRTC needs no device: the generated constants + the embedded stage-kernel source must compile
+    for sm_100a with every node value in a register (no stack frame, no spills)."""
+    exprs.RNG = np.random.default_rng(1)
+    e = F.Expr(device=False)
+    root, _, _ = exprs.CASES[name](e)
+    e.plan(root)
+    nstages = int(e.describe().split()[0].split("=")[1])
+    compiled = 0
+    for st in range(nstages):
+        for mode in (1, 2, 3):
+            try:
+                text = e.jit_program(st, mode)
+            except F.FadbError:
+                continue                       # a dot / dense stage
+            assert "JIT_PROG" in text and "#define JIT_MODE %d" % mode in text
+            nbytes, log = F.jit_compile_only(text)
+            assert nbytes > 0
+            assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in log, log[-800:]
+            compiled += 1
+    assert compiled >= 3
+
+
+def test_control_flow_stage_is_not_specialisable(F):
+    name = next(n for n in sorted(exprs.CASES) if "if_else" in n)
+    exprs.RNG = np.random.default_rng(1)
+    e = F.Expr(device=False)
+    root, _, _ = exprs.CASES[name](e)
+    e.plan(root)
+    d = e.describe()
+    nstages = int(d.split()[0].split("=")[1])
+    refused = 0
+    for st in range(nstages):
+        try:
+            e.jit_program(st, 3)
+        except F.FadbError as ex:
+            refused += 1
+    assert refused >= 1
