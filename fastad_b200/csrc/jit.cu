@@ -135,7 +135,8 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     nvrtcProgram prog = nullptr;
     nvrtcResult r = g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr);
     if (r == NVRTC_SUCCESS) {
-        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177"};
+        static std::string pf = std::string("-DFADB_JIT_PF_DIST=") + (getenv("FADB_JIT_PF_DIST") ? getenv("FADB_JIT_PF_DIST") : "1");
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", pf.c_str()};
         r = g_rtc.compile(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
         size_t ls = 0;
         if (g_rtc.log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1) { g_log.resize(ls); g_rtc.log(prog, &g_log[0]); }

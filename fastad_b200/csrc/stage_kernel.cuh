@@ -71,6 +71,9 @@ struct StageArgs {
 };
 
 #ifdef FADB_JIT
+#ifndef FADB_JIT_PF_DIST
+#define FADB_JIT_PF_DIST 1   // trips ahead the operand prefetch runs
+#endif
 struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-time part of a LeafDesc
 #endif
 //@@FADB_JIT_PROGRAM@@  (jit.cu splices the generated program constants in here)
@@ -185,6 +188,31 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = tid; i < a.N; i += nth) {
+#ifdef FADB_JIT
+        {   // One element per trip leaves a thread with too few bytes in flight (ncu on the 10-node chain:
+            // long-scoreboard 13.3 of 20 stall cycles per issue, DRAM 37 %).  Start fetching the NEXT
+            // trip's operand and adjoint lines now; prefetches hold no registers and merge with the loads.
+            const unsigned long long j = i + FADB_JIT_PF_DIST * nth;
+            K_UNROLL
+            for (int k = 0; k < K_NLEAVES; ++k) {
+                if (K_LEAF_SCALAR(k)) continue;
+                const LeafDesc& L = s_leaf[k];
+                if (i == tid) {
+                    if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(L.adj + i));
+#pragma unroll
+                    for (int d = 1; d < FADB_JIT_PF_DIST; ++d)
+                        if (i + d * nth < a.N) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(L.val + i + d * nth));
+                            if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(L.adj + i + d * nth));
+                        }
+                }
+                if (j < a.N) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(L.val + j));
+                    if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(L.adj + j));
+                }
+            }
+        }
+#endif
         // ------------------------------------------------ forward (feval)
         K_UNROLL
         for (int k = 0; k < K_NINS; ++k) {
