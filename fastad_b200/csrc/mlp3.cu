@@ -22,7 +22,71 @@ constexpr int NOUT = NP + 1;      // + loss
 __device__ __forceinline__ double inv1p(double e) { return e > 1e300 ? 0.0 : fm::rcp_(1 + e); }
 __device__ __forceinline__ double exp_s(double x) { return (fabs(x) <= 700.0) ? fm::exp_(x) : exp(x); }
 
-__global__ void __launch_bounds__(256)
+// one row: forward + adjoint sweep in registers, the 26 sums accumulated into acc
+__device__ __forceinline__ void mlp3_row(const double* __restrict__ p, double xa, double xb, double yy, double (&acc)[NOUT])
+{
+    const double* A1 = p;        // A1(i,j) = A1[i + 3j]
+    const double* b1 = p + 6;
+    const double* A2 = p + 9;    // A2(i,j) = A2[i + 3j]
+    const double* b2 = p + 18;
+    const double* A3 = p + 21;   // A3(0,j) = A3[j]
+    const double b3 = p[24];
+    // ---- forward ----
+    double x1[3], e1[3], y1[3], h[3], e2[3], s2[3], y2[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        x1[i] = (A1[i] * xa + A1[i + 3] * xb) + b1[i];          // dot(A1, xi) + b1
+        e1[i] = exp_s(-x1[i]);
+        y1[i] = inv1p(e1[i]);                            // sigmoid = 1/(1+exp(-x)), unary.hpp:273-275
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        h[i] = ((A2[i] * y1[0] + A2[i + 3] * y1[1]) + A2[i + 6] * y1[2]) + b2[i];
+        e2[i] = exp_s(-h[i]);
+        s2[i] = inv1p(e2[i]);
+        y2[i] = s2[i] + x1[i];                                  // sigmoid(...) + x1
+    }
+    const double y3 = ((A3[0] * y2[0] + A3[1] * y2[1]) + A3[2] * y2[2]) + b3;
+    const double d = yy - y3;
+    const double loss = d * d;                                  // pow<2>
+    acc[NP] += loss;
+    // ---- backward, seed 1 ----
+    const double g_d = 2. * (d == 0 ? 0 : loss / d);            // pow.hpp:125-140
+    const double g_y3 = -g_d;                                   // Sub::brmap
+    double g_y2[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        acc[21 + j] += g_y3 * y2[j];                            // A3_adj = adj * y2^T
+        g_y2[j] = A3[j] * g_y3;                                 // A3^T * adj
+    }
+    acc[24] += g_y3;                                            // b3
+    double g_h[3], g_y1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g_h[i] = g_y2[i] * e2[i] * (s2[i] * s2[i]);             // Sigmoid::bmap seed*e/((e+1)(e+1)), unary.hpp:276-278
+        acc[18 + i] += g_h[i];                                  // b2
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[9 + i + 3 * j] += g_h[i] * y1[j];               // A2_adj = adj * y1^T
+            g_y1[j] += A2[i + 3 * j] * g_h[i];                  // A2^T * adj
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // x1 enters twice (README form has the sub-tree twice): through y1 and the jump
+        const double g_x1 = g_y1[i] * e1[i] * (y1[i] * y1[i]) + g_y2[i];
+        acc[i] += g_x1 * xa;                                    // A1_adj = adj * xi^T
+        acc[i + 3] += g_x1 * xb;
+        acc[6 + i] += g_x1;                                     // b1
+    }
+}
+
+// ROWS rows per thread and trip (independent dependency chains for the FP64 pipe), MINB resident CTAs
+template <int ROWS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict__ y,
             const double* __restrict__ parm, double* cta_partials, unsigned int* ticket,
             double* grad, int overwrite, double* out_loss)
@@ -33,12 +97,6 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
     __shared__ bool is_last;
     if (threadIdx.x < NP) p[threadIdx.x] = parm[threadIdx.x];
     __syncthreads();
-    const double* A1 = p;        // A1(i,j) = A1[i + 3j]
-    const double* b1 = p + 6;
-    const double* A2 = p + 9;    // A2(i,j) = A2[i + 3j]
-    const double* b2 = p + 18;
-    const double* A3 = p + 21;   // A3(0,j) = A3[j]
-    const double b3 = p[24];
 
     double acc[NOUT];
 #pragma unroll
@@ -46,59 +104,19 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
 
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
-    for (size_t row = tid; row < batch; row += nth) {
-        const double xa = __ldg(X + row), xb = __ldg(X + batch + row), yy = __ldg(y + row);
-        // ---- forward ----
-        double x1[3], e1[3], y1[3], h[3], e2[3], s2[3], y2[3];
+    for (size_t row0 = tid; row0 < batch; row0 += ROWS * nth) {
+        double xa[ROWS], xb[ROWS], yy[ROWS];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            x1[i] = (A1[i] * xa + A1[i + 3] * xb) + b1[i];          // dot(A1, xi) + b1
-            e1[i] = exp_s(-x1[i]);
-            y1[i] = inv1p(e1[i]);                            // sigmoid = 1/(1+exp(-x)), unary.hpp:273-275
+        for (int r = 0; r < ROWS; ++r) {
+            const size_t row = row0 + r * nth;
+            const bool in = row < batch;
+            xa[r] = in ? __ldg(X + row) : 0.0;
+            xb[r] = in ? __ldg(X + batch + row) : 0.0;
+            yy[r] = in ? __ldg(y + row) : 0.0;
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            h[i] = ((A2[i] * y1[0] + A2[i + 3] * y1[1]) + A2[i + 6] * y1[2]) + b2[i];
-            e2[i] = exp_s(-h[i]);
-            s2[i] = inv1p(e2[i]);
-            y2[i] = s2[i] + x1[i];                                  // sigmoid(...) + x1
-        }
-        const double y3 = ((A3[0] * y2[0] + A3[1] * y2[1]) + A3[2] * y2[2]) + b3;
-        const double d = yy - y3;
-        const double loss = d * d;                                  // pow<2>
-        acc[NP] += loss;
-        // ---- backward, seed 1 ----
-        const double g_d = 2. * (d == 0 ? 0 : loss / d);            // pow.hpp:125-140
-        const double g_y3 = -g_d;                                   // Sub::brmap
-        double g_y2[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            acc[21 + j] += g_y3 * y2[j];                            // A3_adj = adj * y2^T
-            g_y2[j] = A3[j] * g_y3;                                 // A3^T * adj
-        }
-        acc[24] += g_y3;                                            // b3
-        double g_h[3], g_y1[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            g_h[i] = g_y2[i] * e2[i] * (s2[i] * s2[i]);             // Sigmoid::bmap seed*e/((e+1)(e+1)), unary.hpp:276-278
-            acc[18 + i] += g_h[i];                                  // b2
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                acc[9 + i + 3 * j] += g_h[i] * y1[j];               // A2_adj = adj * y1^T
-                g_y1[j] += A2[i + 3 * j] * g_h[i];                  // A2^T * adj
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            // x1 enters twice (README form has the sub-tree twice): through y1 and the jump
-            const double g_x1 = g_y1[i] * e1[i] * (y1[i] * y1[i]) + g_y2[i];
-            acc[i] += g_x1 * xa;                                    // A1_adj = adj * xi^T
-            acc[i + 3] += g_x1 * xb;
-            acc[6 + i] += g_x1;                                     // b1
-        }
+        for (int r = 0; r < ROWS; ++r)
+            if (row0 + r * nth < batch) mlp3_row(p, xa[r], xb[r], yy[r], acc);
     }
     // ---- CTA reduce of the 26 channels ----
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,6 +137,9 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // last CTA: warp w sums CTAs w, w+8, ... (lane = channel), then the 8 warp sums in a fixed order
+    // (a wider final pass -- 8 warps x 26 lanes over the CTA partials, then a shared-memory step -- measured
+    // 1.7-2.8 us SLOWER than these 26 independent load streams at 148-296 CTAs)
     if (threadIdx.x < NOUT) {
         double v = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&cta_partials[(size_t)b * NOUT + threadIdx.x]);
@@ -144,9 +165,23 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     if (rc) return rc;
     if (!g_mlp_ws[c->device]) FADB_CUDA(cudaMalloc(&g_mlp_ws[c->device], sizeof(double) * kMaxGrid * NOUT));
     const int threads = 256;
-    const int grid = resident_grid(*c, mlp3_kernel, threads, 0, batch, threads);
-    FADB_CUDA(launch_pdl(mlp3_kernel, grid, threads, 0, c->stream, batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad,
-                         (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss));
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("FADB_MLP_VARIANT"); variant = e ? atoi(e) : -2; }
+#define FADB_MLP_LAUNCH(K)                                                                                     \
+    FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm, \
+                         g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss))
+    // measured on B200, batch 2^22: <1,1> 166 us (153 registers, 8 warps/SM: FP64 pipe 37 % active, stalls are
+    // dependent-issue waits), <2,1> 155, <3,1> 159, <2,2> 121, <1,2> 115 (128 registers, 16 warps/SM): default
+    if (variant == 1) FADB_MLP_LAUNCH((mlp3_kernel<2, 1>));
+    else if (variant == 3) FADB_MLP_LAUNCH((mlp3_kernel<2, 2>));
+    else if (variant == 4) FADB_MLP_LAUNCH((mlp3_kernel<3, 1>));
+    else if (variant == 0) FADB_MLP_LAUNCH((mlp3_kernel<1, 1>));
+    else if (variant == 2) FADB_MLP_LAUNCH((mlp3_kernel<1, 2>));
+    // default: occupancy wins once every CTA slot has work; below that the grid-wide reduction (one partial
+    // row + one ticket per CTA) dominates and fewer CTAs are faster (2^16 rows: 11.1 us vs 13.9 us)
+    else if (batch > (size_t)4 * c->sms * threads) FADB_MLP_LAUNCH((mlp3_kernel<1, 2>));
+    else FADB_MLP_LAUNCH((mlp3_kernel<1, 1>));
+#undef FADB_MLP_LAUNCH
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;
