@@ -105,6 +105,18 @@ bool init_locked()
     return true;
 }
 
+// cubin -> module -> kernel handle + its occupancy at 128 threads
+bool finish_load(Entry& e, const std::vector<char>& bin)
+{
+    if (g_drv.module_load(&e.mod, bin.data()) != CUDA_SUCCESS) return false;
+    if (g_drv.module_func(&e.fn, e.mod, "fadb_stage_jit") != CUDA_SUCCESS) return false;
+    if (g_drv.occupancy(&e.per_sm, e.fn, 128, 0) != CUDA_SUCCESS || e.per_sm < 1) e.per_sm = 1;
+    g_drv.func_attr(&e.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, e.fn);
+    g_drv.func_attr(&e.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, e.fn);
+    e.failed = false;
+    return true;
+}
+
 }  // namespace
 
 bool jit_enabled()
@@ -132,10 +144,32 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     Entry e;
     e.failed = true;
     const std::string src = jit_source(program);
+    static const std::string pf = std::string("-DFADB_JIT_PF_DIST=") + (getenv("FADB_JIT_PF_DIST") ? getenv("FADB_JIT_PF_DIST") : "1");
+    // optional on-disk cubin cache (FADB_JIT_CACHE_DIR): keyed by a hash of the full source text
+    std::string cache_file;
+    if (const char* dir = getenv("FADB_JIT_CACHE_DIR")) {
+        unsigned long long h = 1469598103934665603ull;                 // FNV-1a 64
+        for (unsigned char ch : src + pf) { h ^= ch; h *= 1099511628211ull; }
+        char name[64];
+        snprintf(name, sizeof name, "/fadb_sm100a_%016llx.cubin", h);
+        cache_file = std::string(dir) + name;
+        if (FILE* f = fopen(cache_file.c_str(), "rb")) {
+            std::vector<char> bin;
+            char buf[65536];
+            size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) bin.insert(bin.end(), buf, buf + n);
+            fclose(f);
+            if (!bin.empty() && finish_load(e, bin)) {
+                g_cache.emplace(key, e);
+                ++g_hits;
+                out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes;
+                return FADB_OK;
+            }
+        }
+    }
     nvrtcProgram prog = nullptr;
     nvrtcResult r = g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr);
     if (r == NVRTC_SUCCESS) {
-        static std::string pf = std::string("-DFADB_JIT_PF_DIST=") + (getenv("FADB_JIT_PF_DIST") ? getenv("FADB_JIT_PF_DIST") : "1");
         const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", pf.c_str()};
         r = g_rtc.compile(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
         size_t ls = 0;
@@ -145,12 +179,12 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
             std::vector<char> bin;
             if (g_rtc.cubin_size(prog, &n) == NVRTC_SUCCESS && n > 0) {
                 bin.resize(n);
-                if (g_rtc.cubin(prog, bin.data()) == NVRTC_SUCCESS && g_drv.module_load(&e.mod, bin.data()) == CUDA_SUCCESS &&
-                    g_drv.module_func(&e.fn, e.mod, "fadb_stage_jit") == CUDA_SUCCESS) {
-                    if (g_drv.occupancy(&e.per_sm, e.fn, 128, 0) != CUDA_SUCCESS || e.per_sm < 1) e.per_sm = 1;
-                    g_drv.func_attr(&e.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, e.fn);
-                    g_drv.func_attr(&e.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, e.fn);
-                    e.failed = false;
+                if (g_rtc.cubin(prog, bin.data()) == NVRTC_SUCCESS && finish_load(e, bin) && !cache_file.empty()) {
+                    if (FILE* f = fopen((cache_file + ".tmp").c_str(), "wb")) {
+                        const bool okw = fwrite(bin.data(), 1, bin.size(), f) == bin.size();
+                        fclose(f);
+                        if (okw) rename((cache_file + ".tmp").c_str(), cache_file.c_str());
+                    }
                 }
             }
         } else {

@@ -119,6 +119,25 @@ def test_expr_specialised_kernels_are_the_default_and_bit_identical_to_interpret
         np.testing.assert_array_equal(a, b)
 
 
+def test_expr_specialised_kernel_disk_cache(tmp_path):
+    # FADB_JIT_CACHE_DIR: the first process compiles and stores the cubin, the second loads it (no NVRTC run)
+    import os, subprocess, sys, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r); import fastad_b200 as F\n"
+        "F.load(); F.check(F.lib().fadb_init(0))\n"
+        "e = F.Expr(); x = e.var(np.linspace(0.5, 2, 777))\n"
+        "e.bind(e.sum(e.binary('mul', e.unary('tanh', x), e.unary('atan', x))))\n"
+        "v = e.autodiff(1.0); print(json.dumps([float(v[0]), F.jit_stats()]))\n" % root)
+    env = dict(os.environ, FADB_JIT_CACHE_DIR=str(tmp_path))
+    outs = [json.loads(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+            for _ in range(2)]
+    assert outs[0][1]["compiled"] == 1 and outs[0][1]["launched"] == 1
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
+    assert outs[1][1]["compiled"] == 0 and outs[1][1]["hits"] == 1 and outs[1][1]["launched"] == 1
+    assert outs[0][0] == outs[1][0]
+
+
 def test_expr_if_else_stays_on_the_interpreter(fb):
     # control flow cannot be unrolled: the stage is not specialised, results still match the oracle
     name = next(n for n in sorted(exprs.CASES) if "if_else" in n)
