@@ -81,32 +81,7 @@ inline int resident_grid(const Context& c, Kernel kernel, int threads, size_t dy
     return grid_for(c, work_items, per_sm, items_per_cta);
 }
 
-// ---------------------------------------------------------------------------------------
-// 256-bit global memory access (LDG.E.256 / STG.E.256 on sm_100a).
-// Streaming data is read once: bypass L1 allocation; adjoint RMW uses plain ld/st.
-// ---------------------------------------------------------------------------------------
-struct __align__(32) double4_t { double v[4]; };
-
-__device__ __forceinline__ double4_t ldg256_stream(const double* p)
-{
-    double4_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ double4_t ld256(const double* p)
-{
-    double4_t r;
-    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ void st256(double* p, const double4_t& r)
-{
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
-}
-
+// 256-bit global memory access helpers (double4_t, ldg256_stream, ld256, st256): device_reduce.cuh
 __host__ __device__ inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 }  // namespace fadb

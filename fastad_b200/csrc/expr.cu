@@ -701,12 +701,27 @@ struct fadb_expr {
     // ---------------------------------------------------------------- specialisation (jit.cu)
     // The compile-time half of a stage: program, leaf attributes, terminal configuration, mode.
     // Pointers, N and seeds are NOT part of it.  false: this stage stays on the interpreter.
+    // 4 elements per thread with 256-bit accesses: per-element operands only through F_LEAF_V (no
+    // placeholder or op= stores, whose order inside the program matters), and enough elements
+    static int jit_vec_width(const Stage& st)
+    {
+        static const bool off = getenv("FADB_JIT_NO_VEC") != nullptr;
+        if (off || st.N < 4096) return 1;
+        bool any_vec = false;
+        for (const LeafDesc& l : st.leaves) {
+            if (l.assigned) return 1;
+            any_vec = any_vec || !l.scalar;
+        }
+        for (const DIns& d : st.enc)
+            if (d.code == F_EQ || d.code >= F_OPEQ) return 1;
+        return any_vec ? 4 : 1;
+    }
     static bool jit_program_text(const Stage& st, int mode, std::string& out)
     {
         if (st.big || st.enc.empty() || st.enc.size() > (size_t)MAXS || st.leaves.size() > (size_t)MAXL) return false;
         std::ostringstream o;
         char buf[64];
-        o << "\n#define JIT_NINS " << st.enc.size() << "\n#define JIT_NLEAVES " << st.leaves.size()
+        o << "\n#define JIT_VEC " << jit_vec_width(st) << "\n#define JIT_NINS " << st.enc.size() << "\n#define JIT_NLEAVES " << st.leaves.size()
           << "\n#define JIT_MODE " << mode << "\n#define JIT_TERM " << st.term << "\n#define JIT_ROOT " << st.root
           << "\n#define JIT_NX " << st.nx << "\n#define JIT_NM " << st.nm << "\n#define JIT_NS " << st.ns
           << "\n#define JIT_MU_VEC " << st.mu_vec << "\n#define JIT_SIG_VEC " << st.sig_vec << "\n#define JIT_NCH " << st.nch
@@ -743,6 +758,8 @@ struct fadb_expr {
         a.nch = st.nch; a.term_ch = st.term_ch;
         a.partials = c.partials; a.ticket = c.tickets + 8;
         a.scratch = st.d_scratch;
+        a.vec_ok = 0;
+        for (size_t l = 0; l < st.leaves.size() && l < (size_t)MAXL; ++l) { a.lp_val[l] = st.leaves[l].val; a.lp_adj[l] = st.leaves[l].adj; }
         if (st.big) {
             stage_kernel<2><<<1, 32, 0, c.stream>>>(a);
             c.launches++;
@@ -756,7 +773,12 @@ struct fadb_expr {
                 st.jit_state[mode] = (jit_program_text(st, mode, text) && jit_get(c, text, &st.jit[mode]) == FADB_OK) ? 1 : -1;
             }
             if (st.jit_state[mode] == 1) {
-                int grid = grid_for(c, st.N, st.jit[mode].per_sm, 128);
+                const int vw = jit_vec_width(st);
+                a.vec_ok = 1;
+                if (vw > 1)
+                    for (const LeafDesc& l : st.leaves)
+                        if (!l.scalar && (!aligned32(l.val) || (l.adj_mode && !aligned32(l.adj)))) a.vec_ok = 0;
+                int grid = grid_for(c, (st.N + vw - 1) / vw, st.jit[mode].per_sm, 128);
                 if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
                 int rc = jit_launch(st.jit[mode], (unsigned)grid, 128, c.stream, &a);
                 if (rc) return rc;

@@ -38,6 +38,8 @@ struct Nvrtc {
     decltype(&nvrtcGetProgramLog) log = nullptr;
     decltype(&nvrtcDestroyProgram) destroy = nullptr;
     decltype(&nvrtcGetErrorString) err = nullptr;
+    decltype(&nvrtcVersion) version = nullptr;
+    int major = 0, minor = 0;
     bool ok = false;
 };
 struct Driver {
@@ -78,8 +80,10 @@ bool init_locked()
     if (g_state != 0) return g_state > 0;
     g_state = -1;
     const char* env = getenv("FADB_NVRTC_PATH");
-    const char* names[] = {env, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
-                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    // the toolkit's own NVRTC first: a process that imported torch already holds torch's bundled (older)
+    // libnvrtc.so.12 under that name
+    const char* names[] = {env, "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                           "libnvrtc.so"};
     for (const char* n : names) {
         if (!n) continue;
         g_rtc.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
@@ -94,6 +98,7 @@ bool init_locked()
         g_why = "libnvrtc lacks a required entry point";
         return false;
     }
+    if (sym(r.h, "nvrtcVersion", r.version)) r.version(&r.major, &r.minor);
     Driver& d = g_drv;
     if (!(drv("cuModuleLoadData", d.module_load) && drv("cuModuleUnload", d.module_unload) &&
           drv("cuModuleGetFunction", d.module_func) && drv("cuLaunchKernel", d.launch) &&
@@ -145,11 +150,12 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     e.failed = true;
     const std::string src = jit_source(program);
     static const std::string pf = std::string("-DFADB_JIT_PF_DIST=") + (getenv("FADB_JIT_PF_DIST") ? getenv("FADB_JIT_PF_DIST") : "1");
+    static const std::string minb = getenv("FADB_JIT_MINB") ? std::string("-DFADB_JIT_MINB=") + getenv("FADB_JIT_MINB") : std::string();
     // optional on-disk cubin cache (FADB_JIT_CACHE_DIR): keyed by a hash of the full source text
     std::string cache_file;
     if (const char* dir = getenv("FADB_JIT_CACHE_DIR")) {
         unsigned long long h = 1469598103934665603ull;                 // FNV-1a 64
-        for (unsigned char ch : src + pf) { h ^= ch; h *= 1099511628211ull; }
+        for (unsigned char ch : src + pf + minb) { h ^= ch; h *= 1099511628211ull; }
         char name[64];
         snprintf(name, sizeof name, "/fadb_sm100a_%016llx.cubin", h);
         cache_file = std::string(dir) + name;
@@ -170,8 +176,10 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     nvrtcProgram prog = nullptr;
     nvrtcResult r = g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr);
     if (r == NVRTC_SUCCESS) {
-        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", pf.c_str()};
-        r = g_rtc.compile(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+        std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", pf.c_str()};
+        if (g_rtc.major * 100 + g_rtc.minor < 1209) opts.push_back("-DFADB_NO_LD256=1");   // 256-bit ld/st need PTX ISA 8.8
+        if (!minb.empty()) opts.push_back(minb.c_str());
+        r = g_rtc.compile(prog, (int)opts.size(), opts.data());
         size_t ls = 0;
         if (g_rtc.log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1) { g_log.resize(ls); g_rtc.log(prog, &g_log[0]); }
         if (r == NVRTC_SUCCESS) {
@@ -231,7 +239,8 @@ extern "C" const char* fadb_jit_diagnostics(void)
 {
     static thread_local std::string s;
     std::lock_guard<std::mutex> lk(g_mu);
-    s = (g_state < 0 ? "unavailable: " : "") + g_why + (g_log.empty() ? "" : "\n" + g_log);
+    s = (g_state < 0 ? "unavailable: " : "") + g_why + " [NVRTC " + std::to_string(g_rtc.major) + "." + std::to_string(g_rtc.minor) + "]" +
+        (g_log.empty() ? "" : "\n" + g_log);
     return s.c_str();
 }
 // Compiles `program` (the text expr.cu generates for one stage and mode) to a cubin WITHOUT a device
@@ -245,8 +254,9 @@ extern "C" int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, c
     const std::string src = jit_source(program);
     nvrtcProgram prog = nullptr;
     if (g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return FADB_ERR_STATE;
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", "--ptxas-options=-v"};
-    const nvrtcResult r = g_rtc.compile(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", "--ptxas-options=-v"};
+    if (g_rtc.major * 100 + g_rtc.minor < 1209) opts.push_back("-DFADB_NO_LD256=1");
+    const nvrtcResult r = g_rtc.compile(prog, (int)opts.size(), opts.data());
     size_t ls = 0;
     if (g_rtc.log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1 && log && log_cap) {
         std::string l(ls, '\0');

@@ -68,6 +68,11 @@ struct StageArgs {
     double* partials;
     unsigned int* ticket;
     double* scratch;           // BIG programs (scalar stages only): v | g | lacc in global memory
+    int vec_ok;                // specialised vector path: every per-element leaf pointer is 32-byte aligned
+    // leaf pointers again, in PARAMETER space: the specialised kernel indexes them with compile-time
+    // constants, so they are constant-bank operands (no registers, no loads); the interpreter uses `leaves`
+    const double* lp_val[MAXL];
+    double* lp_adj[MAXL];
 };
 
 #ifdef FADB_JIT
@@ -82,6 +87,11 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #define K_NINS JIT_NINS
 #define K_NLEAVES JIT_NLEAVES
 #define K_INS(k) JIT_PROG[k]
+#ifndef JIT_VEC
+#define JIT_VEC 1
+#endif
+#define K_LVAL(k) a.lp_val[k]
+#define K_LADJ(k) a.lp_adj[k]
 #define K_LEAF_SCALAR(k) JIT_LEAF[k].scalar
 #define K_LEAF_ADJ_MODE(k) JIT_LEAF[k].adj_mode
 #define K_LEAF_CHANNEL(k) JIT_LEAF[k].channel
@@ -98,10 +108,17 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #define K_SLOTS JIT_NINS
 #define K_LSLOTS (JIT_NLEAVES > 0 ? JIT_NLEAVES : 1)
 #define K_UNROLL _Pragma("unroll")
+#if JIT_VEC > 1
+#define K_LOADV(k) lv[k][e]
+#else
+#define K_LOADV(k) K_LVAL(k)[i]
+#endif
 #else
 #define K_NINS a.nins
 #define K_NLEAVES a.nleaves
 #define K_INS(k) s_prog[k]
+#define K_LVAL(k) s_leaf[k].val
+#define K_LADJ(k) s_leaf[k].adj
 #define K_LEAF_SCALAR(k) s_leaf[k].scalar
 #define K_LEAF_ADJ_MODE(k) s_leaf[k].adj_mode
 #define K_LEAF_CHANNEL(k) s_leaf[k].channel
@@ -118,6 +135,7 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #define K_SLOTS MAXS
 #define K_LSLOTS MAXL
 #define K_UNROLL
+#define K_LOADV(k) K_LVAL(k)[i]
 #endif
 
 __device__ __forceinline__ double block_prod_all(double p, double* sm)
@@ -144,20 +162,19 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
 {
     constexpr bool BIG = STORE == 2;
     extern __shared__ double s_dyn[];
-    __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
     __shared__ double s_red[32 * MAXCH];
     __shared__ bool s_last;
-    const LeafDesc* s_leaf = BIG ? a.leaves : s_leaf_sm;
 #ifndef FADB_JIT
+    __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
+    const LeafDesc* s_leaf = BIG ? a.leaves : s_leaf_sm;
     __shared__ DIns s_prog_sm[BIG ? 1 : MAXS];
     const DIns* s_prog = BIG ? a.prog : s_prog_sm;
-    if (!BIG)
-        for (int k = threadIdx.x; k < K_NINS; k += blockDim.x) s_prog_sm[k] = a.prog[k];
-#endif
     if (!BIG) {
+        for (int k = threadIdx.x; k < K_NINS; k += blockDim.x) s_prog_sm[k] = a.prog[k];
         for (int k = threadIdx.x; k < K_NLEAVES; k += blockDim.x) s_leaf_sm[k] = a.leaves[k];
         __syncthreads();
     }
+#endif
 
     const bool fwd_out = K_MODE & M_F;     // forward results are stored in this launch
     bool back = K_MODE & M_B;
@@ -187,8 +204,44 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
 #define LA(k) lb[(k) * vs]
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long nth = (unsigned long long)gridDim.x * blockDim.x;
+#if defined(FADB_JIT) && JIT_VEC > 1
+    // JIT_VEC consecutive elements per thread and trip: every per-element leaf is read with ONE 256-bit
+    // load and its adjoint updated with one 256-bit load + store, as in the hand-written kernels
+    // (map_reduce.cu, normal.cu).  The planner only asks for this when the program has no placeholder
+    // stores; a.vec_ok says whether every per-element leaf pointer is 32-byte aligned.  A trip that is
+    // not full (the last elements) or an unaligned operand takes scalar accesses in the same loop.
+    static_assert(JIT_VEC == 4, "the vector path moves 256-bit words");
+    for (unsigned long long base = tid * JIT_VEC; base < a.N; base += nth * JIT_VEC) {
+        const bool full = a.vec_ok && base + JIT_VEC <= a.N;
+        double lv[K_LSLOTS][JIT_VEC], la[K_LSLOTS][JIT_VEC];
+        K_UNROLL
+        for (int k = 0; k < K_NLEAVES; ++k) {
+            if (K_LEAF_SCALAR(k)) continue;
+            if (full) {
+                const double4_t w = K_LEAF_ADJ_MODE(k) == 0 ? ldg256_stream(K_LVAL(k) + base) : ld256(K_LVAL(k) + base);
+#pragma unroll
+                for (int e = 0; e < JIT_VEC; ++e) lv[k][e] = w.v[e];
+                if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(K_LADJ(k) + base));
+            } else {
+#pragma unroll
+                for (int e = 0; e < JIT_VEC; ++e) lv[k][e] = base + e < a.N ? K_LVAL(k)[base + e] : 0.0;
+            }
+            const unsigned long long nb = base + nth * JIT_VEC;       // next trip's lines
+            if (nb < a.N) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(K_LVAL(k) + nb));
+                if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(K_LADJ(k) + nb));
+            }
+#pragma unroll
+            for (int e = 0; e < JIT_VEC; ++e) la[k][e] = 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < JIT_VEC; ++e) {
+        const unsigned long long i = base + e;
+        if (!full && i >= a.N) break;
+#else
     for (unsigned long long i = tid; i < a.N; i += nth) {
-#ifdef FADB_JIT
+#endif
+#if defined(FADB_JIT) && JIT_VEC == 1
         {   // One element per trip leaves a thread with too few bytes in flight (ncu on the 10-node chain:
             // long-scoreboard 13.3 of 20 stall cycles per issue, DRAM 37 %).  Start fetching the NEXT
             // trip's operand and adjoint lines now; prefetches hold no registers and merge with the loads.
@@ -196,19 +249,18 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             K_UNROLL
             for (int k = 0; k < K_NLEAVES; ++k) {
                 if (K_LEAF_SCALAR(k)) continue;
-                const LeafDesc& L = s_leaf[k];
                 if (i == tid) {
-                    if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(L.adj + i));
+                    if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(K_LADJ(k) + i));
 #pragma unroll
                     for (int d = 1; d < FADB_JIT_PF_DIST; ++d)
                         if (i + d * nth < a.N) {
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(L.val + i + d * nth));
-                            if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(L.adj + i + d * nth));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(K_LVAL(k) + i + d * nth));
+                            if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(K_LADJ(k) + i + d * nth));
                         }
                 }
                 if (j < a.N) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(L.val + j));
-                    if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(L.adj + j));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(K_LVAL(k) + j));
+                    if (K_LEAF_ADJ_MODE(k) == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(K_LADJ(k) + j));
                 }
             }
         }
@@ -219,12 +271,12 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             const DIns I = K_INS(k);
             double r;
             switch (I.code) {
-            case F_LEAF_V: r = s_leaf[I.leaf].val[i]; break;              // var_view.hpp:69
-            case F_LEAF_S: r = s_leaf[I.leaf].val[0]; break;
+            case F_LEAF_V: r = K_LOADV(I.leaf); break;              // var_view.hpp:69
+            case F_LEAF_S: r = K_LVAL(I.leaf)[0]; break;
             case F_CONST: r = I.imm; break;
             case F_EQ: {                                                   // eq.hpp:89-92
                 r = V(I.a);
-                if (fwd_out) const_cast<double*>(s_leaf[I.leaf].val)[K_LEAF_SCALAR(I.leaf) ? 0 : i] = r;
+                if (fwd_out) const_cast<double*>(K_LVAL(I.leaf))[K_LEAF_SCALAR(I.leaf) ? 0 : i] = r;
                 break;
             }
             case F_GLUE: r = V(I.b); break;                               // glue.hpp:67-71
@@ -259,7 +311,7 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                 const double old = V(I.b), e = V(I.a);
                 const int op = I.code - F_OPEQ;
                 r = op == FADB_ADD ? old + e : op == FADB_SUB ? old - e : op == FADB_MUL ? old * e : old / e;
-                if (fwd_out) { const LeafDesc& L = s_leaf[I.leaf]; const_cast<double*>(L.val)[i] = r; }
+                if (fwd_out) const_cast<double*>(K_LVAL(I.leaf))[i] = r;
                 break;
             }
             }
@@ -365,17 +417,16 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                 case F_LEAF_V: case F_LEAF_S: LA(I.leaf) += s; break;
                 case F_CONST: break;
                 case F_EQ: {                                                                      // eq.hpp:101-107
-                    const LeafDesc& L = s_leaf[I.leaf];
                     if (K_LEAF_SCALAR(I.leaf) && a.N > 1) { G(I.a) += s + LA(I.leaf); break; }   // not produced by the planner
-                    const double tot = (L.adj[i] + LA(I.leaf)) + s;
-                    L.adj[i] = tot;
+                    const double tot = (K_LADJ(I.leaf)[i] + LA(I.leaf)) + s;
+                    K_LADJ(I.leaf)[i] = tot;
                     LA(I.leaf) = 0.0;
                     G(I.a) += tot;
                     break;
                 }
                 case F_GLUE: G(I.b) += s; break;                                                  // lhs gets 0, glue.hpp:81-86
                 case F_POW: G(I.a) += pow_bmap((long)I.leaf, s, V(I.a), V(k)); break;            // pow.hpp:101-162
-                case F_POW2: { const double x = V(I.a); G(I.a) += 2. * s * (x == 0 ? 0 : V(k) / x); break; }
+                case F_POW2: { const double x = V(I.a); G(I.a) += 2. * s * (x == 0 ? 0 : div_guarded(V(k), x)); break; }
 #define U(FN) case F_UNARY + FN: G(I.a) += Unary<FN>::b(s, V(I.a), V(k)); break;                 /* unary.hpp:81-89 */
                 U(FADB_NEG) U(FADB_SIN) U(FADB_COS) U(FADB_TAN) U(FADB_ASIN) U(FADB_ACOS) U(FADB_ATAN) U(FADB_EXP)
                 U(FADB_LOG) U(FADB_SQRT) U(FADB_ERF) U(FADB_SIGMOID) U(FADB_SINH) U(FADB_COSH) U(FADB_TANH)
@@ -386,7 +437,7 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                 case F_BINARY + FADB_ADD: G(I.b) += s; G(I.a) += s; break;
                 case F_BINARY + FADB_SUB: G(I.b) += -s; G(I.a) += s; break;
                 case F_BINARY + FADB_MUL: { const double x = V(I.a), y = V(I.b); G(I.b) += s * x; G(I.a) += s * y; break; }
-                case F_BINARY + FADB_DIV: { const double y = V(I.b); G(I.b) += div_guarded(-s * V(k), y); G(I.a) += div_guarded(s, y); break; }
+                case F_BINARY + FADB_DIV: { double qr, ql; div2_guarded(-s * V(k), s, V(I.b), qr, ql); G(I.b) += qr; G(I.a) += ql; break; }
                 case F_BINARY + 12: G(I.b) += -2. * s; G(I.a) += s; break;                        // MockBinary
                 // comparisons: no adjoint (binary.hpp:124)
                 case F_BINARY + FADB_LT: case F_BINARY + FADB_LE: case F_BINARY + FADB_GT: case F_BINARY + FADB_GE:
@@ -401,8 +452,7 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                 case F_JZ: break;
 #endif
                 default: {                                                         // OpEqNode::beval, eq.hpp:249-271
-                    const LeafDesc& L = s_leaf[I.leaf];
-                    const double tot = (L.adj[i] + LA(I.leaf)) + s;
+                    const double tot = (K_LADJ(I.leaf)[i] + LA(I.leaf)) + s;
                     LA(I.leaf) = 0.0;
                     const double old = V(I.b), e = V(I.a);
                     const int op = I.code - F_OPEQ;
@@ -412,8 +462,8 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                     else if (op == FADB_MUL) { ls = tot * e; rs = tot * old; }
                     else { ls = tot / e; rs = -tot * old / (e * e); }
                     G(I.a) += rs;
-                    L.adj[i] = ls;                                                 // reset_adj(); beval(lseed)
-                    const_cast<double*>(L.val)[i] = old;                           // the previous value is restored
+                    K_LADJ(I.leaf)[i] = ls;                                                 // reset_adj(); beval(lseed)
+                    const_cast<double*>(K_LVAL(I.leaf))[i] = old;                           // the previous value is restored
                     break;
                 }
                 }
@@ -422,16 +472,48 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         // ------------------------------------------------ leaf write-back: adj += seed (var_view.hpp:91-94)
         K_UNROLL
         for (int k = 0; k < K_NLEAVES; ++k) {
-            const LeafDesc& L = s_leaf[k];
             if (K_LEAF_ADJ_MODE(k) == 0) continue;
             if (K_LEAF_ASSIGNED(k)) {  // reads that precede the assignment in program order
-                if (LA(k) != 0.0) L.adj[i] += LA(k);
+                if (LA(k) != 0.0) K_LADJ(k)[i] += LA(k);
                 continue;
             }
             if (K_LEAF_SCALAR(k) && a.N > 1) { acc[K_LEAF_CHANNEL(k) < 0 ? 0 : K_LEAF_CHANNEL(k)] += LA(k); continue; }
-            if (K_LEAF_ADJ_MODE(k) == 2) L.adj[i] = LA(k);
-            else if (!gated) L.adj[i] += LA(k);
+#if defined(FADB_JIT) && JIT_VEC > 1
+            la[k][e] = LA(k);                              // stored by the vector write-back below
+#else
+            if (K_LEAF_ADJ_MODE(k) == 2) K_LADJ(k)[i] = LA(k);
+            else if (!gated) K_LADJ(k)[i] += LA(k);
+#endif
         }
+#if defined(FADB_JIT) && JIT_VEC > 1
+        }   // e
+        if (back) {
+            K_UNROLL
+            for (int k = 0; k < K_NLEAVES; ++k) {
+                if (K_LEAF_SCALAR(k) || K_LEAF_ADJ_MODE(k) == 0) continue;
+                if (K_LEAF_ADJ_MODE(k) == 1 && gated) continue;
+                if (full) {
+                    double4_t w;
+                    if (K_LEAF_ADJ_MODE(k) == 1) {
+                        w = ld256(K_LADJ(k) + base);
+#pragma unroll
+                        for (int e = 0; e < JIT_VEC; ++e) w.v[e] += la[k][e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < JIT_VEC; ++e) w.v[e] = la[k][e];
+                    }
+                    st256(K_LADJ(k) + base, w);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < JIT_VEC; ++e)
+                        if (base + e < a.N) {
+                            if (K_LEAF_ADJ_MODE(k) == 2) K_LADJ(k)[base + e] = la[k][e];
+                            else K_LADJ(k)[base + e] += la[k][e];
+                        }
+                }
+            }
+        }
+#endif
     }
 
     // ---------------------------------------------------- grid reduction + scalar epilogue
@@ -507,11 +589,10 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
     if (K_MODE & M_B) {
         K_UNROLL
         for (int k = 0; k < K_NLEAVES; ++k) {
-            const LeafDesc& L = s_leaf[k];
             if (K_LEAF_CHANNEL(k) < 0 || K_LEAF_ADJ_MODE(k) == 0) continue;
             const bool skip = gated || !back || (K_TERM > T_NORMAL && (K_MODE & M_F) && tot[2] != 0.0);
-            if (K_LEAF_ADJ_MODE(k) == 2) L.adj[0] = skip ? 0.0 : tot[K_LEAF_CHANNEL(k)];
-            else if (!skip) L.adj[0] += tot[K_LEAF_CHANNEL(k)];
+            if (K_LEAF_ADJ_MODE(k) == 2) K_LADJ(k)[0] = skip ? 0.0 : tot[K_LEAF_CHANNEL(k)];
+            else if (!skip) K_LADJ(k)[0] += tot[K_LEAF_CHANNEL(k)];
         }
     }
 }
@@ -521,7 +602,10 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
 #undef LA
 
 #ifdef FADB_JIT
-extern "C" __global__ void __launch_bounds__(128) fadb_stage_jit(StageArgs a) { stage_body<0>(a); }
+#ifndef FADB_JIT_MINB
+#define FADB_JIT_MINB 8   // <= 64 registers: measured best on B200 (chain 0.127 -> 0.113 ms, Black-Scholes stage 0.070 -> 0.061 ms vs no cap)
+#endif
+extern "C" __global__ void __launch_bounds__(128, FADB_JIT_MINB) fadb_stage_jit(StageArgs a) { stage_body<0>(a); }
 #else
 template <int STORE>
 __global__ void __launch_bounds__(128) stage_kernel(StageArgs a) { stage_body<STORE>(a); }

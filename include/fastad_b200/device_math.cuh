@@ -53,13 +53,32 @@ __device__ __forceinline__ double log_guarded(double x)
     return (ux - 0x0010000000000000ull < 0x7fe0000000000000ull) ? fm::log_(x) : log(x);
 }
 FADB_UNARY(FADB_EXP, exp_guarded(x), seed * f)
-// Log::bmap seed / x (unary.hpp:250-255): Newton reciprocal + residual correction (<= 1 ulp) when
-// both operands are ordinary, IEEE division otherwise
+// Division by Newton reciprocal + residual correction (fm::div_, <= 1 ulp) when both operands are
+// "ordinary", IEEE division otherwise.  Ordinary = biased exponent in [512, 1534], i.e. 2^-511 <= |v| <
+// 2^512 (or a == 0): the quotient then lies in [2^-1023, 2^1023) and neither it nor the residual can
+// overflow or go subnormal.  The window test is two integer instructions on the high word (the
+// earlier form, four FP64 compares against 1e+-290, cost 5 DSETP + 8 UMOV per division and let
+// |a/d| > DBL_MAX through to the Newton path, which returns NaN instead of inf there).
+__device__ __forceinline__ bool ordinary_(double v)
+{
+    return ((((unsigned)__double2hiint(v)) >> 20) & 0x7ffu) - 512u < 1023u;
+}
 __device__ __forceinline__ double div_guarded(double a, double d)
 {
-    const double ad = fabs(d), aa = fabs(a);
-    if (ad > 1e-290 && ad < 1e290 && aa < 1e290 && (aa > 1e-290 || aa == 0.0)) return fm::div_(a, d);
+    if (ordinary_(d) && (ordinary_(a) || a == 0.0)) return fm::div_(a, d);
     return a / d;
+}
+// a1 / d and a2 / d with one reciprocal (Div::blmap / brmap share the denominator, binary.hpp:320-338)
+__device__ __forceinline__ void div2_guarded(double a1, double a2, double d, double& q1, double& q2)
+{
+    if (ordinary_(d) && (ordinary_(a1) || a1 == 0.0) && (ordinary_(a2) || a2 == 0.0)) {
+        const double y = fm::rcp_(d);
+        q1 = fm::div_(a1, d, y);
+        q2 = fm::div_(a2, d, y);
+    } else {
+        q1 = a1 / d;
+        q2 = a2 / d;
+    }
 }
 FADB_UNARY(FADB_LOG, log_guarded(x), div_guarded(seed, x))
 FADB_UNARY(FADB_SQRT, sqrt(x), 0.5 * seed / f)

@@ -133,10 +133,12 @@ def test_stage_program_specialises_to_register_code(F, name):
             assert "JIT_PROG" in text and "#define JIT_MODE %d" % mode in text
             nbytes, log = F.jit_compile_only(text)
             assert nbytes > 0
-            # node values in local memory would need >= 8 bytes x nodes of stack
+            # node values in local memory would need >= 8 bytes x nodes of stack (80-400 bytes for these
+            # programs); the 64-register cap (8 CTAs/SM) may cost a register or two of spills
             import re
             m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", log)
-            assert m and int(m.group(1)) <= 16 and m.group(2) == "0" and m.group(3) == "0", log[-800:]
+            assert m and int(m.group(1)) <= 48, log[-800:]
+            assert re.search(r"Used (\d+) registers", log) and int(re.search(r"Used (\d+) registers", log).group(1)) <= 64
             compiled += 1
     assert compiled >= 3
 

@@ -31,3 +31,5 @@ e0.record()
 for _ in range(reps): step()
 e1.record(); torch.cuda.synchronize()
 print(which, "ms/step", e0.elapsed_time(e1) / reps, F.jit_stats())
+if F.jit_stats()["failed"]:
+    print("JIT diagnostics:", L.fadb_jit_diagnostics().decode()[:3000])
