@@ -79,7 +79,10 @@ __device__ __forceinline__ BSRes bs_eval(double S, double K, double sigma, doubl
 
 // Same forward pass and adjoint sweep with the constant-bank / Newton math of fastmath.cuh:
 // one shared reciprocal per division, exp(-u^2) shared between Phi(d) and its derivative.
-__device__ __forceinline__ BSRes bs_eval_fast(double S, double K, double sigma, double tau, double r)
+// PW: Phi through the 32-interval degree-7 table (fm::phi_pair_pw, `tab` = its shared-memory copy)
+// instead of the single degree-27 polynomial: 40 fewer FP64 instructions per option
+template <bool PW = false>
+__device__ __forceinline__ BSRes bs_eval_fast(double S, double K, double sigma, double tau, double r, const double* tab = nullptr)
 {
     constexpr double inv_sqrt2 = 0.70710678118654752440;
     constexpr double dphi_c = 0.5 * 1.1283791670955126 * inv_sqrt2;
@@ -95,8 +98,13 @@ __device__ __forceinline__ BSRes bs_eval_fast(double S, double K, double sigma, 
     const double c1 = fm::div_(c0 + drift, sst, inv_sst);      // cache[1]
     const double c2 = c1 - sst;                                // cache[2]
     double Phi1, Phi1n, E1, Phi2, Phi2n, E2;
-    fm::phi_pair(c1, Phi1, Phi1n, E1);
-    fm::phi_pair(c2, Phi2, Phi2n, E2);
+    if (PW) {
+        fm::phi_pair_pw(c1, tab, Phi1, Phi1n, E1);
+        fm::phi_pair_pw(c2, tab, Phi2, Phi2n, E2);
+    } else {
+        fm::phi_pair(c1, Phi1, Phi1n, E1);
+        fm::phi_pair(c2, Phi2, Phi2n, E2);
+    }
     const double PV = K * fm::exp_(-r * tau);
 
     BSRes o;
@@ -168,12 +176,17 @@ bs_kernel_fast(size_t n, const double* __restrict__ S, const double* __restrict_
 
 // software-pipelined variant: the next option's inputs are loaded before the current one is
 // evaluated, so the ~800-cycle load latency overlaps the ~2000-cycle evaluation of the same thread
-template <bool ACC>
-__global__ void __launch_bounds__(256, 2)
+template <bool ACC, bool PW = false, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
 bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restrict__ K,
                   const double* __restrict__ sigma, const double* __restrict__ tau,
                   const double* __restrict__ r, BSOut out)
 {
+    __shared__ double s_tab[PW ? 256 : 1];
+    if (PW) {            // constant memory: written before any launch, safe to read ahead of the dependency sync
+        s_tab[threadIdx.x] = fm::kErfcx32_d[threadIdx.x];
+        __syncthreads();
+    }
     pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
@@ -185,16 +198,19 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
         const bool more = j < n;
         double s2 = 0, k2 = 1, g2 = 1, t2 = 1, r2 = 0;
         if (more) { s2 = __ldg(S + j); k2 = __ldg(K + j); g2 = __ldg(sigma + j); t2 = __ldg(tau + j); r2 = __ldg(r + j); }
-        const BSRes o = bs_eval_fast(s, k, g, t, rr);
+        const BSRes o = bs_eval_fast<PW>(s, k, g, t, rr, s_tab);
         bs_store1<ACC>(out, i, o);
         if (!more) break;
         i = j; s = s2; k = k2; g = g2; t = t2; rr = r2;
     }
 }
 
+// host_mapped: the arrays are page-locked HOST memory (fadb_black_scholes_host): the PCIe link, not the
+// FP64 pipe, is the limit there and FEWER resident CTAs are faster -- measured per 2^20 options:
+// 444 CTAs 1.62 ms, 296 1.57, 148 1.54, 74 1.52, 24-48 1.506, 16 1.53, 8 1.56 (FADB_BS_HOST_GRID)
 int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S, const double* K,
                          const double* sigma, const double* tau, const double* r,
-                         double* const out[8], unsigned flags)
+                         double* const out[8], unsigned flags, bool host_mapped = false)
 {
     BSOut o;
     bool vec_ok = (((uintptr_t)S | (uintptr_t)K | (uintptr_t)sigma | (uintptr_t)tau |
@@ -207,11 +223,16 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     const int threads = 256;
     // Measured on B200, 2^20 options per launch (us per launch): libdevice math 29.2 (variant 5);
     // fastmath 27.7 (variant 6); fastmath + software-pipelined loads, 128 registers, 2 CTAs/SM
-    // 25.5 (variant 20); the same kernel launched with programmatic dependent launch 23.5 (default).
+    // 25.5 (variant 20); the same kernel launched with programmatic dependent launch 23.5 (variant 22);
+    // Phi from the 32-interval degree-7 erfcx table in shared memory (40 fewer FP64 instructions per
+    // option, 110 registers) 22.6 (variant 21); the same at 3 CTAs/SM (78 registers, no spills) 21.4
+    // (default); 4 CTAs/SM (64 registers, spills) 22.7 (variant 24).
     // Two options per thread, tighter launch bounds (spills) and atomic
     // work-stealing were measured slower and removed.
     static int variant = -1;
-    if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 21; }
+    if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 23; }
+    static int host_grid = -1;
+    if (host_grid < 0) { const char* e = getenv("FADB_BS_HOST_GRID"); host_grid = e ? atoi(e) : 32; }
     (void)vec_ok;
     const bool ovw = flags & FADB_OVERWRITE_ADJ;
 #define FADB_BS_LAUNCH(KERNEL)                                                                          \
@@ -226,12 +247,26 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
         // default: same kernel, launched with programmatic stream serialization so that back-to-back
         // batches overlap launch latency and the tail of the previous grid (the kernel waits on
         // cudaGridDependencySynchronize before its first memory access)
-        if (ovw)
-            FADB_CUDA(launch_pdl(bs_kernel_fast_pf<false>, resident_grid(c, bs_kernel_fast_pf<false>, threads, 0, n, threads),
-                                 threads, 0, st, n, S, K, sigma, tau, r, o));
-        else
-            FADB_CUDA(launch_pdl(bs_kernel_fast_pf<true>, resident_grid(c, bs_kernel_fast_pf<true>, threads, 0, n, threads),
-                                 threads, 0, st, n, S, K, sigma, tau, r, o));
+        if (variant == 22) {      // single degree-27 erfcx polynomial (23.5 us)
+            if (ovw)
+                FADB_CUDA(launch_pdl(bs_kernel_fast_pf<false>, resident_grid(c, bs_kernel_fast_pf<false>, threads, 0, n, threads),
+                                     threads, 0, st, n, S, K, sigma, tau, r, o));
+            else
+                FADB_CUDA(launch_pdl(bs_kernel_fast_pf<true>, resident_grid(c, bs_kernel_fast_pf<true>, threads, 0, n, threads),
+                                     threads, 0, st, n, S, K, sigma, tau, r, o));
+#define FADB_BS_PW(MINB)                                                                                                 \
+    do {                                                                                                                 \
+        int grid_ = resident_grid(c, bs_kernel_fast_pf<false, true, MINB>, threads, 0, n, threads);                      \
+        if (host_mapped && grid_ > host_grid) grid_ = host_grid;                                                         \
+        if (ovw)                                                                                                         \
+            FADB_CUDA(launch_pdl(bs_kernel_fast_pf<false, true, MINB>, grid_, threads, 0, st, n, S, K, sigma, tau, r, o)); \
+        else                                                                                                             \
+            FADB_CUDA(launch_pdl(bs_kernel_fast_pf<true, true, MINB>, grid_, threads, 0, st, n, S, K, sigma, tau, r, o)); \
+    } while (0)
+        } else if (variant == 21) { FADB_BS_PW(2);
+        } else if (variant == 24) { FADB_BS_PW(4);
+        } else { FADB_BS_PW(3);
+        }
     }
 #undef FADB_BS_LAUNCH
     c.launches++;
@@ -296,7 +331,7 @@ extern "C" int fadb_black_scholes_host(size_t n, const double* hS, const double*
     // gives) the resident kernel runs directly on their UVA device aliases instead: ONE launch reads
     // the inputs and writes the results over PCIe, both directions busy at once, no staging buffers and
     // no copy calls.  Measured on B200, 2^20 options (104 MB over PCIe): staged 1.78 ms at the best
-    // chunk size (4 chunks; more chunks cost ~35 us each in copy calls), direct 1.56 ms; plain
+    // chunk size (4 chunks; more chunks cost ~35 us each in copy calls), direct 1.51 ms (32 CTAs); plain
     // cudaMemcpy of the 64 MB of results alone takes 1.18 ms.  A mix (kernel reads host memory, DMA
     // write-back) measured slower than both (2.04 ms).  FADB_BS_HOST_MODE=0 forces the staged path.
     const double* hin[5] = {hS, hK, hsigma, htau, hr};
@@ -314,7 +349,7 @@ extern "C" int fadb_black_scholes_host(size_t n, const double* hS, const double*
         else dout_zc[k - 5] = static_cast<double*>(at.devicePointer);
     }
     if (locked) {
-        rc = launch_black_scholes(*c, c->stream, n, din[0], din[1], din[2], din[3], din[4], dout_zc, FADB_OVERWRITE_ADJ);
+        rc = launch_black_scholes(*c, c->stream, n, din[0], din[1], din[2], din[3], din[4], dout_zc, FADB_OVERWRITE_ADJ, true);
         if (rc) return rc;
         FADB_CUDA(cudaStreamSynchronize(c->stream));
         return FADB_OK;

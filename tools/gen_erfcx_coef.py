@@ -48,3 +48,38 @@ print("// erfcx(w) * (w+2)/2 as a degree-27 polynomial in x = 2t-1, t = 2/(w+2);
 print("// computed with mpmath at 40 digits (generator: tools/gen_erfcx_coef.py)")
 for k,m in enumerate(mono):
     print("    %s,%s" % (mp.nstr(m, 20), "" if k%1 else ""))
+
+# ---- piecewise table (fm::kErfcx32): g(t) = erfcx(2(1-t)/t)/t on 32 equal sub-intervals of (0,1], degree 7
+# in the local variable x = 64 t - (2 j + 1); printed coefficient-major: entry k*32 + j.
+def g_t(t):
+    if t < mp.mpf('1e-30'): return 1/(cpar*mp.sqrt(mp.pi))
+    return erfcx(cpar*(1-t)/t)/t
+def cheb_fit_ab(f, deg, a, b):
+    N = deg+1
+    xs = [mp.cos(mp.pi*(k+mp.mpf(1)/2)/N) for k in range(N)]
+    fs = [f((a+b)/2 + (b-a)/2*x) for x in xs]
+    c = [2*sum(fs[k]*mp.cos(mp.pi*j*(k+mp.mpf(1)/2)/N) for k in range(N))/N for j in range(N)]
+    c[0] /= 2
+    return c
+K8, D8 = 32, 7
+Tm = [[mp.mpf(0)]*(D8+1) for _ in range(D8+1)]
+Tm[0][0] = mp.mpf(1); Tm[1][1] = mp.mpf(1)
+for n in range(2, D8+1):
+    for k in range(D8+1):
+        Tm[n][k] = (2*Tm[n-1][k-1] if k>0 else 0) - Tm[n-2][k]
+table = []
+for j in range(K8):
+    cj = cheb_fit_ab(g_t, D8, mp.mpf(j)/K8, mp.mpf(j+1)/K8)
+    table.append([sum(cj[n]*Tm[n][k] for n in range(D8+1)) for k in range(D8+1)])
+print("// kErfcx32: 32 intervals x 8 coefficients, entry k*32 + j")
+for k in range(D8+1):
+    print("    " + ", ".join(mp.nstr(table[j][k], 20) for j in range(K8)) + ", \\")
+# max relative error of the monomial form evaluated in 40-digit arithmetic
+worst = 0
+for j in range(K8):
+    for s in range(201):
+        x = mp.mpf(-1) + mp.mpf(2)*s/200
+        t = (x + 2*j + 1)/(2*K8)
+        p = sum(table[j][k]*x**k for k in range(D8+1))
+        worst = max(worst, abs(p/g_t(t) - 1))
+print("// max relative truncation error:", mp.nstr(worst, 3))
