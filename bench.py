@@ -489,6 +489,26 @@ def run_ours(args):
             {"note": "same expression, specialisation off"})
         del e
 
+        # least squares sum(pow<2>(y - dot(X, w))), the batched form of the reference's README regression
+        # example (README.md:640-662): recognised at bind time, one pass over X; then the same expression
+        # with an extra map between dot and pow (not recognised): tall GEMV kernels, two passes over X
+        rows, cols = 1 << 20, 64
+        Xh, yh, wt = synth.linreg_inputs(rows, cols)
+        for tag, inner in (("one_pass", False), ("generic_dot", True)):
+            e = F.Expr()
+            Xc, yc, w = e.const(Xh), e.const(yh), e.var((wt + 0.05).reshape(cols, 1))
+            r = e.binary("sub", yc, e.dot(Xc, w))
+            if inner:
+                r = e.binary("mul", r, e.const(1.0 + 0 * yh))
+            e.bind(e.sum(e.pow(2, r)))
+
+            def ls_step(i):
+                F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+            t = timed_loop(ls_step, steps2, 3, world)
+            add(f"expr_least_squares_2^20x64_{tag}", 8 * rows * (cols + 1), t, steps2, rows, "rows",
+                {"note": "algorithmic bytes = one pass over X + y" + ("; this form needs two passes + a 24 B/row map stage" if inner else "")})
+            del e
+
         # the same two expressions through the TYPE-FUSED path (include/fastad_b200/fused.cuh): the
         # expression type instantiates the kernel in an nvcc-compiled TU (tests/cpp/fused_bench.cu)
         fb_path = os.path.join(ROOT, "tests", "_build", "libfused_bench.so")

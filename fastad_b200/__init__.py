@@ -66,6 +66,8 @@ SIGNATURES = {
     "fadb_linreg_partial": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
     "fadb_linreg_finish": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_linreg_nll": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_lsq": (_i, [_sz, _sz, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_lsq_finish": (_i, [_sz, _vp, _vp, _d, _u, _vp]),
     "fadb_mlp3": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _dp]),
     "fadb_mlp3_async": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _vp]),
     "fadb_expr_create": (_i, [C.POINTER(_vp)]),

@@ -47,6 +47,7 @@ extern "C" int fadb_logpdf_async(int, int, size_t, const double*, const double*,
                                  double, unsigned, double*);
 extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, double*, double*, double,
                                   unsigned, double*);
+extern "C" int fadb_lsq_finish(size_t, const double*, double*, double, unsigned, double*);
 
 #include "stage_kernel.cuh"
 
@@ -85,6 +86,94 @@ __global__ void dot_bwd_kernel(int m, int k, int p, const double* __restrict__ L
     }
 }
 // TransposeNode (transpose.hpp:32-41): V = X^T; X_adj (+)= A^T.  X is m x k column-major.
+// ---- tall operands: L is m x k with m large and R a k-vector (p == 1), the dot(X, w) of a statistical
+// model.  HBM-bound: L crosses memory once per direction (8 m k bytes), coalesced down the columns.
+constexpr int GV_THREADS = 256;
+constexpr int GV_KT = 16;          // columns per register tile of the transposed product
+
+// V = L R: one row per thread and trip, R in shared memory, the k loads of a row are independent
+__global__ void __launch_bounds__(GV_THREADS)
+gemv_n_kernel(size_t m, int k, const double* __restrict__ L, const double* __restrict__ R, double* __restrict__ V)
+{
+    extern __shared__ double s_r[];
+    for (int q = threadIdx.x; q < k; q += blockDim.x) s_r[q] = R[q];
+    __syncthreads();
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += nth) {
+        double acc = 0.0;
+        const double* row = L + i;
+#pragma unroll 8
+        for (int q = 0; q < k; ++q) acc += __ldg(row + (size_t)q * m) * s_r[q];     // dot.hpp:93, same order over q
+        V[i] = acc;
+    }
+}
+
+// Radj (+)= L^T A: every CTA owns a contiguous block of rows; GV_KT column sums at a time live in
+// registers, A is re-read per column tile (8 bytes per row against 8 GV_KT of L).  Deterministic: warp
+// tree -> shared memory -> per-CTA partial row; the last CTA to arrive adds the rows in CTA order.
+__global__ void __launch_bounds__(GV_THREADS)
+gemv_t_kernel(size_t m, int k, const double* __restrict__ L, const double* __restrict__ A, double* partials /* [grid][k] */,
+              unsigned int* ticket, double* Radj, int rmode)
+{
+    __shared__ double s_red[GV_THREADS / 32][GV_KT];
+    __shared__ bool s_last;
+    const size_t per = (m + gridDim.x - 1) / gridDim.x;
+    const size_t r0 = (size_t)blockIdx.x * per, r1 = r0 + per < m ? r0 + per : m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q0 = 0; q0 < k; q0 += GV_KT) {
+        double acc[GV_KT];
+#pragma unroll
+        for (int t = 0; t < GV_KT; ++t) acc[t] = 0.0;
+        if (q0 + GV_KT <= k) {
+            for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+                const double a = __ldg(A + i);
+#pragma unroll
+                for (int t = 0; t < GV_KT; ++t) acc[t] += __ldg(L + i + (size_t)(q0 + t) * m) * a;
+            }
+        } else {
+            for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+                const double a = __ldg(A + i);
+#pragma unroll
+                for (int t = 0; t < GV_KT; ++t)
+                    if (q0 + t < k) acc[t] += __ldg(L + i + (size_t)(q0 + t) * m) * a;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < GV_KT; ++t) {
+            const double v = warp_sum(acc[t]);
+            if (lane == 0) s_red[warp][t] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < GV_KT && q0 + (int)threadIdx.x < k) {
+            double v = 0.0;
+            for (int w = 0; w < GV_THREADS / 32; ++w) v += s_red[w][threadIdx.x];
+            partials[(size_t)blockIdx.x * k + q0 + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int q = threadIdx.x; q < k; q += blockDim.x) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&partials[(size_t)b * k + q]);
+        Radj[q] = (rmode == 2) ? v : Radj[q] + v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// Ladj (+)= A R^T for p == 1: an outer product, one element per thread (only when L is a variable)
+__global__ void outer_kernel(size_t m, int k, const double* __restrict__ A, const double* __restrict__ R, double* Ladj, int lmode)
+{
+    const size_t n = m * (size_t)k, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += nth) {
+        const double v = A[idx % m] * R[idx / m];
+        Ladj[idx] = (lmode == 2) ? v : Ladj[idx] + v;
+    }
+}
+
 __global__ void transpose_fwd_kernel(int m, int k, const double* __restrict__ X, double* V)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,6 +253,7 @@ struct Stage {
     const double *f_mu = nullptr, *f_sig = nullptr; double *f_muadj = nullptr, *f_sigadj = nullptr;
     int f_shape = 0; const double* f_X = nullptr; const double* f_w = nullptr; double* f_wadj = nullptr;
     size_t f_rows = 0, f_cols = 0; double* f_part = nullptr;
+    double* gv_part = nullptr; int gv_grid = 0;    // tall dot stage: per-CTA partial rows of L^T A
 };
 
 }  // namespace fadb
@@ -505,7 +595,24 @@ struct fadb_expr {
         st.fast = 0;
         if (st.type != 0 || plan.size() > 2) return;
         int lf;
-        if (plan.size() == 2 && st.term != T_NORMAL) return;
+        if (plan.size() == 2 && st.term != T_NORMAL && st.term != T_SUM) return;
+        // sum(pow<2>(y - dot(X, w))) or sum(pow<2>(dot(X, w) - y)), X and y constant: least squares, one pass over X
+        if (plan.size() == 2 && st.term == T_SUM) {
+            if (st.prog.size() != 4 || st.root != 3) return;
+            const Ins &Ip = st.prog[3], &Is = st.prog[2];
+            if (Ip.op != I_POW || Ip.fn != 2 || Ip.a != 2 || Is.op != I_BINARY || Is.fn != FADB_SUB) return;
+            if (st.prog[Is.a].op != I_LEAF || st.prog[Is.b].op != I_LEAF) return;
+            int ld = st.prog[Is.a].leaf, ly = st.prog[Is.b].leaf;
+            if (st.leaf_stage[ld] < 0) std::swap(ld, ly);
+            if (st.leaf_stage[ld] < 0 || st.leaf_stage[ly] >= 0 || st.leaves[ly].scalar || st.leaves[ly].adj_mode != 0) return;
+            Stage& ds = *plan[st.leaf_stage[ld]];
+            if (ds.type != 1 || ds.p != 1 || ds.L.stage >= 0 || ds.R.stage >= 0 || ds.L.adj_mode != 0 || ds.k > 4096) return;
+            st.fast = 5;
+            st.f_X = ds.L.val; st.f_w = ds.R.val; st.f_wadj = ds.R.adj_mode ? ds.R.adj : nullptr;
+            st.f_rows = ds.m; st.f_cols = ds.k;
+            st.f_x = st.leaves[ly].val;
+            return;
+        }
         if (plan.size() == 1 && st.term == T_SUM && st.prog.size() == 2 && st.root == 1 && leaf_only(st, 0, &lf) &&
             !st.leaves[lf].scalar && (st.prog[1].op == I_UNARY || st.prog[1].op == I_POW) && st.prog[1].a == 0) {
             st.fast = 1;
@@ -643,6 +750,11 @@ struct fadb_expr {
         for (auto& sp : plan) {
             Stage& st = *sp;
             if (st.type != 0) {
+                if (st.type == 1 && st.p == 1 && st.m >= 4096 && st.k <= 4096) {
+                    st.gv_grid = std::min(2 * c.sms, (st.m + 255) / 256);
+                    int rc = dev_alloc((size_t)st.gv_grid * st.k * sizeof(double), (void**)&st.gv_part);
+                    if (rc) return rc;
+                }
                 if (st.L.stage >= 0) { st.L.val = plan[st.L.stage]->mval; st.L.adj = plan[st.L.stage]->madj; }
                 if ((st.type == 1 || st.type == 3 || st.type == 5) && st.R.stage >= 0) { st.R.val = plan[st.R.stage]->mval; st.R.adj = plan[st.R.stage]->madj; }
                 if (st.type == 3 && st.S3.stage >= 0) { st.S3.val = plan[st.S3.stage]->mval; st.S3.adj = plan[st.S3.stage]->madj; }
@@ -664,7 +776,7 @@ struct fadb_expr {
                 if ((rc = dev_alloc(sizeof(double), (void**)&st.d_sig))) return rc;
                 FADB_CUDA(cudaMemcpyAsync(st.d_sig, &st.sig_const, sizeof(double), cudaMemcpyHostToDevice, c.stream));
             }
-            if (st.fast == 3) {
+            if (st.fast == 3 || st.fast == 5) {
                 if ((rc = dev_alloc((st.f_cols + 1) * sizeof(double), (void**)&st.f_part))) return rc;
             }
             if (st.big) {
@@ -863,6 +975,32 @@ struct fadb_expr {
             FADB_CUDA(cudaGetLastError());
             return FADB_OK;
         }
+        if (st.gv_part) {       // tall L, vector R: the HBM-bound kernels
+            if (mode & M_F) {
+                const int grid = grid_for(c, st.m, 8, GV_THREADS);
+                gemv_n_kernel<<<grid, GV_THREADS, st.k * sizeof(double), c.stream>>>((size_t)st.m, st.k, st.L.val, st.R.val, st.mval);
+                c.launches++;
+            }
+            if (mode & M_B) {
+                const double* A = seed_vec ? seed_vec : st.madj;
+                if (!seed_vec && mode == M_FB) {
+                    fill_kernel<<<(st.m + threads - 1) / threads, threads, 0, c.stream>>>(st.madj, st.m, seed);
+                    c.launches++;
+                }
+                if (st.R.adj_mode) {
+                    gemv_t_kernel<<<st.gv_grid, GV_THREADS, 0, c.stream>>>((size_t)st.m, st.k, st.L.val, A, st.gv_part, c.tickets + 12,
+                                                                            st.R.adj, st.R.adj_mode);
+                    c.launches++;
+                }
+                if (st.L.adj_mode) {
+                    outer_kernel<<<grid_for(c, (size_t)st.m * st.k, 8, 256), 256, 0, c.stream>>>((size_t)st.m, st.k, A, st.R.val, st.L.adj,
+                                                                                                  st.L.adj_mode);
+                    c.launches++;
+                }
+            }
+            FADB_CUDA(cudaGetLastError());
+            return FADB_OK;
+        }
         if (mode & M_F) {
             int n = st.m * st.p;
             dot_fwd_kernel<<<(n + threads - 1) / threads, threads, 0, c.stream>>>(st.m, st.k, st.p, st.L.val, st.R.val, st.mval);
@@ -923,6 +1061,11 @@ struct fadb_expr {
             FADB_CUDA(cudaMemcpyAsync(st.mval, c.scalars + 2, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
             return FADB_OK;
         }
+        if (st.fast == 5) {
+            int rc = fadb_linreg_partial(st.f_rows, st.f_cols, st.f_X, st.f_x, st.f_w, st.f_part);
+            if (rc) return rc;
+            return fadb_lsq_finish(st.f_cols, st.f_part, st.f_wadj, seed, 0, st.mval);
+        }
         return FADB_ERR_STATE;
     }
 
@@ -932,7 +1075,7 @@ struct fadb_expr {
         const int last = (int)plan.size() - 1;
         Stage& rs = *plan[last];
         const bool fast = rs.fast != 0 && what == 3 && !seed_vec;
-        const size_t first = (fast && rs.fast == 3) ? plan.size() : 0;   // linreg subsumes its dot stage
+        const size_t first = (fast && (rs.fast == 3 || rs.fast == 5)) ? plan.size() : 0;   // linreg / least squares subsume their dot stage
         if (what & 1) {
             for (size_t k = first; k + 1 < plan.size(); ++k) {
                 Stage& st = *plan[k];

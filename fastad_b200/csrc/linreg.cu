@@ -345,6 +345,20 @@ __global__ void linreg_finish_kernel(double n_total, size_t cols, const double* 
     }
 }
 
+// least squares on the same partials: value = sum r^2, w_adj (+)= seed * (-2) * X^T r  with r = y - X w
+// (pow.hpp:125-140 through Sub::brmap, binary.hpp:296-303, into dot.hpp:96-104)
+__global__ void lsq_finish_kernel(size_t cols, const double* partial, double* w_adj, double seed, int overwrite,
+                                  double* out_value)
+{
+    if (threadIdx.x == 0) out_value[0] = partial[0];
+    if (!w_adj) return;
+    const double c = -2. * seed;
+    for (size_t j = threadIdx.x; j < cols; j += blockDim.x) {
+        const double g = c * partial[1 + j];
+        w_adj[j] = overwrite ? g : w_adj[j] + g;
+    }
+}
+
 // rank-2 tensor map over the column-major X: dim0 = rows (contiguous), dim1 = cols
 static int encode_xmap(CUtensorMap* map, const double* X, size_t rows, size_t cols)
 {
@@ -460,6 +474,47 @@ extern "C" int fadb_linreg_finish(size_t rows_total, size_t cols, const double* 
         FADB_CUDA(cudaMemcpyAsync(c->host_scalars + 2, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         FADB_CUDA(cudaStreamSynchronize(c->stream));
         *host_value = c->host_scalars[2];
+    }
+    return FADB_OK;
+}
+
+// Least squares sum((y - X w)^2), value + gradient from ONE pass over X: the batched form of the
+// reference's README regression example (README.md:606-662).  dev_value: device double.
+extern "C" int fadb_lsq_finish(size_t cols, const double* dev_partial, double* w_adj, double seed, unsigned flags,
+                               double* dev_value)
+{
+    FADB_REQUIRE(dev_partial && dev_value, "fadb_lsq_finish: null argument");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    lsq_finish_kernel<<<1, 128, 0, c->stream>>>(cols, dev_partial, w_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_value);
+    c->launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
+extern "C" int fadb_lsq(size_t rows, size_t cols, const double* X, const double* y, const double* w, double* w_adj,
+                        double seed, unsigned flags, double* host_value)
+{
+    FADB_REQUIRE(cols >= 1 && cols <= 4096, "fadb_lsq: cols must be in 1..4096");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    const size_t ntiles = (rows + LR_ROWS - 1) / LR_ROWS;
+    const size_t grid = std::min<size_t>(std::max<size_t>(ntiles, 1), (size_t)c->sms * 4);
+    double* ws;
+    rc = ensure_ws(*c, grid * (cols + 1) + cols + 1, &ws);
+    if (rc) return rc;
+    double* partial = ws + grid * (cols + 1);
+    rc = fadb_linreg_partial(rows, cols, X, y, w, partial);
+    if (rc) return rc;
+    double* dval = c->scalars + 40;
+    rc = fadb_lsq_finish(cols, partial, w_adj, seed, flags, dval);
+    if (rc) return rc;
+    if (host_value) {
+        FADB_CUDA(cudaMemcpyAsync(c->host_scalars + 40, dval, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FADB_CUDA(cudaStreamSynchronize(c->stream));
+        *host_value = c->host_scalars[40];
     }
     return FADB_OK;
 }

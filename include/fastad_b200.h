@@ -208,6 +208,13 @@ int fadb_linreg_finish(size_t rows_total, size_t cols, const double* dev_partial
 int fadb_linreg_nll(size_t rows, size_t cols, const double* X, const double* y,
                     const double* w, double* w_adj, const double* sigma, double* sigma_adj,
                     double seed, unsigned flags, double* host_value);
+/* Least squares sum((y - X w)^2): value + w_adj += seed * (-2) X^T (y - X w) from one pass over X -- the
+ * batched form of the reference's regression example, bind(pow<2>(yi - dot(xi, theta))) looped over rows
+ * (README.md:640-662).  ad::bind recognises sum(pow<2>(y - dot(X, w))) and routes it here. */
+int fadb_lsq(size_t rows, size_t cols, const double* X, const double* y, const double* w, double* w_adj,
+             double seed, unsigned flags, double* host_value);
+int fadb_lsq_finish(size_t cols, const double* dev_partial, double* w_adj, double seed, unsigned flags,
+                    double* dev_value);
 
 /* ------------------------------------------------------------------ K6: 3-layer network
  * The expression of README.md:676-726 / example/ceres_3layer_neural_net/src.cpp:38-40

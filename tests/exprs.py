@@ -169,6 +169,21 @@ def linreg_expr(rows, cols):
     return build
 
 
+def least_squares(rows, cols, flipped=False, x_var=False, inner=False):
+    def build(e):   # README.md:640-662 batched: sum(pow<2>(y - dot(X, w))); X constant (or a variable: outer-product adjoint)
+        import synth
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=9)
+        Xn = e.var(X) if x_var else e.const(X)
+        yc = e.const(y)
+        w = e.var(w_true + 0.05)
+        d = e.dot(Xn, w)
+        r = e.binary("sub", d, yc) if flipped else e.binary("sub", yc, d)
+        if inner:          # not the recognised shape: the residual goes through another map first
+            r = e.binary("mul", r, e.unary("exp", e.binary("mul", e.const(-0.01), r)))
+        return e.sum(e.pow(2, r)), ([Xn, w] if x_var else [w]), 0.75
+    return build
+
+
 def black_scholes_vec(n, put=False):
     def build(e):   # example/black_scholes.cpp:16-39 over vec leaves
         import synth
@@ -436,6 +451,11 @@ CASES = {
     "mlp3_row": mlp3_row,
     "linreg_expr": linreg_expr(2000, 64),
     "linreg_expr_small": linreg_expr(130, 5),
+    "least_squares": least_squares(5000, 64),
+    "least_squares_flipped_odd": least_squares(4099, 7, flipped=True),
+    "least_squares_small": least_squares(100, 3),
+    "least_squares_tall_generic": least_squares(6001, 19, inner=True),
+    "least_squares_x_variable": least_squares(4500, 5, x_var=True),
     "black_scholes_call": black_scholes_vec(2001),
     "black_scholes_put": black_scholes_vec(2001, put=True),
 }

@@ -342,6 +342,24 @@ def test_black_scholes_full_size_put_call_parity(fb):
     assert np.max(np.abs(host(out[3]) - host(out[6]))) == 0.0   # vega identical by construction
 
 
+def test_least_squares_one_pass_kernel(fb):
+    # fadb_lsq: sum((y - X w)^2) and -2 X^T (y - X w) from one pass over X; odd sizes, accumulate / overwrite
+    import ctypes as C
+    for rows, cols in ((1 << 14, 64), (5003, 7), (129, 1), (70000, 33)):
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=rows)
+        w = w_true + 0.1
+        Xd, yd, wd = dev(X.reshape(-1, order="F")), dev(y), dev(w)
+        wadj = dev(np.full(cols, 0.5))
+        val = C.c_double()
+        fb.check(fb.lib().fadb_lsq(rows, cols, fb._ptr(Xd), fb._ptr(yd), fb._ptr(wd), fb._ptr(wadj), 0.75, 0, C.byref(val)))
+        r = y - X @ w
+        np.testing.assert_allclose(val.value, r @ r, rtol=1e-12)
+        ref = 0.5 + 0.75 * (-2.0) * (X.T @ r)
+        np.testing.assert_allclose(host(wadj), ref, rtol=1e-11, atol=1e-11 * np.max(np.abs(ref)))
+        fb.check(fb.lib().fadb_lsq(rows, cols, fb._ptr(Xd), fb._ptr(yd), fb._ptr(wd), fb._ptr(wadj), 1.0, fb.OVERWRITE_ADJ, C.byref(val)))
+        np.testing.assert_allclose(host(wadj), -2.0 * (X.T @ r), rtol=1e-11, atol=1e-11 * np.max(np.abs(ref)))
+
+
 # ------------------------------------------------------------------ K7 dense-covariance normal
 def _dense_cov(n, rng):
     # benchmark/normal_benchmark.cpp:15-33 builds Sigma = L L^T, L lower with diagonal 10 and U(-1,1)

@@ -84,6 +84,14 @@ def test_planner_fast_paths(F):
     assert "fast=1" in e.describe()
     d, _ = _plan(F, exprs.CASES["linreg_expr"])
     assert "fast=3" in d and "dot 2000x64" in d
+    d, _ = _plan(F, exprs.CASES["least_squares"])
+    assert "fast=5" in d and "dot 5000x64" in d
+    d, _ = _plan(F, exprs.CASES["least_squares_flipped_odd"])
+    assert "fast=5" in d
+    d, _ = _plan(F, exprs.CASES["least_squares_tall_generic"])
+    assert "fast=0" in d
+    d, _ = _plan(F, exprs.CASES["least_squares_x_variable"])
+    assert "fast=0" in d
     d, _ = _plan(F, exprs.CASES["normal_expr_mean"])
     assert "fast=0" in d and "term=normal" in d
 

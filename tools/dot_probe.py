@@ -1,0 +1,30 @@
+"""Least squares through the generic path: sum(pow<2>(y - dot(X, w))), X rows x cols constant (README.md:606-662
+batched).  Prints ms per autodiff and the describe() of the plan."""
+import os, sys
+import numpy as np, torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+import fastad_b200 as F, synth
+F.load(); L = F.lib(); F.check(L.fadb_init(0)); F.use_torch_stream()
+rows = 1 << int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+cols = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+reps = 20
+Xh, yh, _ = synth.linreg_inputs(rows, cols)
+e = F.Expr()
+X = e.const(Xh); y = e.const(yh); w = e.var(0.01 * np.arange(cols, dtype=np.float64).reshape(cols, 1))
+root = e.sum(e.pow(2, e.binary("sub", y, e.dot(X, w))))
+e.bind(root)
+print(e.describe().split("\n")[0], [l for l in e.describe().split("\n") if l.startswith("stage")])
+step = lambda: F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+for _ in range(3): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps): step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print("rows", rows, "cols", cols, "ms/step %.4f" % ms, "X passes at roofline (6550 GB/s): %.2f" % (ms * 1e-3 * 6550e9 / (rows * cols * 8)))
+v = e.autodiff(1.0)
+wh = 0.01 * np.arange(cols)
+r = yh - Xh @ wh
+print("value rel err", abs(v[0] - r @ r) / (r @ r), "adj rel err", np.max(np.abs(e.adj(w).ravel() / (reps + 4) - (-2 * Xh.T @ r))) / np.max(np.abs(2 * Xh.T @ r)))
