@@ -48,6 +48,7 @@ extern "C" int fadb_logpdf_async(int, int, size_t, const double*, const double*,
 extern "C" int fadb_linreg_finish(size_t, size_t, const double*, const double*, double*, double*, double,
                                   unsigned, double*);
 extern "C" int fadb_lsq_finish(size_t, const double*, double*, double, unsigned, double*);
+extern "C" const char* fadb_jit_diagnostics(void);
 
 #include "stage_kernel.cuh"
 
@@ -246,6 +247,7 @@ struct Stage {
     double* d_red = nullptr;       // [8]
     double* d_sig = nullptr;       // device copy of a constant scalar sigma
     bool big = false;              // scalar stage too large for the on-chip interpreter
+    bool jit_only = false;         // vector stage beyond the interpreter's limits: specialised kernel only
     double* d_scratch = nullptr;
     int fast = 0;                  // 0 interpreter, 1 sum_unary, 2 normal leaves, 3 linreg, 4 cauchy/uniform/bernoulli leaves
     // fast-path operands
@@ -412,15 +414,27 @@ struct fadb_expr {
     {
         st.big = (int)st.prog.size() > MAXS || (int)st.leaves.size() > MAXL;
         if (st.big && st.N > 1) {
-            err = "a fused vector stage is limited to " + std::to_string(MAXS) + " nodes and " +
-                  std::to_string(MAXL) + " distinct leaves";
-            return false;
+            // too large for the interpreter's fixed arrays: fine for a specialised kernel (no control flow)
+            bool cf = false;
+            for (const Ins& I : st.prog) cf = cf || I.op == I_JZ || I.op == I_JMP || I.op == I_PHI;
+            if (cf || (int)st.prog.size() > MAXS_JIT || (int)st.leaves.size() > MAXL_JIT) {
+                err = "a fused vector stage is limited to " + std::to_string(cf ? MAXS : MAXS_JIT) + " nodes and " +
+                      std::to_string(cf ? MAXL : MAXL_JIT) + " distinct leaves" + (cf ? " when it contains if_else" : "");
+                return false;
+            }
+            st.big = false;
+            st.jit_only = true;
         }
         st.term_ch = st.term == T_SUM ? 1 : st.term >= T_NORMAL ? 3 : st.term == T_PROD ? 1 : 0;
         int ch = st.term_ch;
         for (auto& L : st.leaves)
             if (L.scalar && L.adj_mode != 0 && st.N > 1) L.channel = ch++;
-        if (ch > MAXCH) { err = "expression stage needs more than " + std::to_string(MAXCH) + " reduction channels"; return false; }
+        if (ch > MAXCH_JIT) { err = "expression stage needs more than " + std::to_string(MAXCH_JIT) + " reduction channels"; return false; }
+        if (ch > MAXCH) {
+            for (const Ins& I : st.prog)
+                if (I.op == I_JZ || I.op == I_JMP || I.op == I_PHI) { err = "an if_else stage is limited to " + std::to_string(MAXCH) + " reduction channels"; return false; }
+            st.jit_only = true;
+        }
         st.nch = ch;
         return true;
     }
@@ -681,7 +695,7 @@ struct fadb_expr {
             if (st.type == 1) { o << "stage " << k << ": dot " << st.m << "x" << st.k << " * " << st.k << "x" << st.p << "\n"; continue; }
             o << "stage " << k << ": map N=" << st.N << " term=" << tn[st.term] << " ins=" << st.prog.size()
               << " leaves=" << st.leaves.size() << " channels=" << st.nch << " fast=" << st.fast
-              << (st.big ? " big" : "") << "\n";
+              << (st.big ? " big" : "") << (st.jit_only ? " specialised-only" : "") << "\n";
             for (size_t i = 0; i < st.prog.size() && i < 256; ++i) {
                 const Ins& I = st.prog[i];
                 o << "  %" << i << " = " << opn[I.op];
@@ -830,9 +844,11 @@ struct fadb_expr {
     }
     static bool jit_program_text(const Stage& st, int mode, std::string& out)
     {
-        if (st.big || st.enc.empty() || st.enc.size() > (size_t)MAXS || st.leaves.size() > (size_t)MAXL) return false;
+        if (st.big || st.enc.empty() || st.enc.size() > (size_t)MAXS_JIT || st.leaves.size() > (size_t)MAXL_JIT) return false;
         std::ostringstream o;
         char buf[64];
+        // registers: 8 CTAs/SM (64 registers) is the measured optimum for small programs; larger ones spill there
+        if (st.enc.size() > 64) o << "\n#ifndef FADB_JIT_MINB\n#define FADB_JIT_MINB " << (st.enc.size() > 128 ? 2 : 4) << "\n#endif";
         o << "\n#define JIT_VEC " << jit_vec_width(st) << "\n#define JIT_NINS " << st.enc.size() << "\n#define JIT_NLEAVES " << st.leaves.size()
           << "\n#define JIT_MODE " << mode << "\n#define JIT_TERM " << st.term << "\n#define JIT_ROOT " << st.root
           << "\n#define JIT_NX " << st.nx << "\n#define JIT_NM " << st.nm << "\n#define JIT_NS " << st.ns
@@ -871,7 +887,7 @@ struct fadb_expr {
         a.partials = c.partials; a.ticket = c.tickets + 8;
         a.scratch = st.d_scratch;
         a.vec_ok = 0;
-        for (size_t l = 0; l < st.leaves.size() && l < (size_t)MAXL; ++l) { a.lp_val[l] = st.leaves[l].val; a.lp_adj[l] = st.leaves[l].adj; }
+        for (size_t l = 0; l < st.leaves.size() && l < (size_t)MAXL_JIT; ++l) { a.lp_val[l] = st.leaves[l].val; a.lp_adj[l] = st.leaves[l].adj; }
         if (st.big) {
             stage_kernel<2><<<1, 32, 0, c.stream>>>(a);
             c.launches++;
@@ -891,12 +907,19 @@ struct fadb_expr {
                     for (const LeafDesc& l : st.leaves)
                         if (!l.scalar && (!aligned32(l.val) || (l.adj_mode && !aligned32(l.adj)))) a.vec_ok = 0;
                 int grid = grid_for(c, (st.N + vw - 1) / vw, st.jit[mode].per_sm, 128);
-                if ((size_t)grid * (MAXCH + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (MAXCH + 1);
+                const int kacc = std::max(st.nch, 3);      // K_ACC of the specialised kernel
+                if ((size_t)grid * (kacc + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (kacc + 1);
                 int rc = jit_launch(st.jit[mode], (unsigned)grid, 128, c.stream, &a);
                 if (rc) return rc;
                 c.launches++;
                 return FADB_OK;
             }
+        }
+        if (st.jit_only) {
+            set_error("fastad_b200: this expression stage (" + std::to_string(st.prog.size()) + " nodes, " + std::to_string(st.leaves.size()) +
+                      " leaves, " + std::to_string(st.nch) + " reduction channels) exceeds the interpreter's limits and needs the "
+                      "NVRTC-specialised kernel: " + fadb_jit_diagnostics());
+            return FADB_ERR_UNSUPPORTED;
         }
         const int threads = st.N >= 4096 ? 128 : 32;
         const size_t smem = (2 * st.prog.size() + st.leaves.size()) * threads * sizeof(double);

@@ -47,6 +47,10 @@ struct LeafDesc {
 constexpr int MAXS = 64;    // SSA slots per stage program
 constexpr int MAXL = 24;    // distinct leaves per stage
 constexpr int MAXCH = 8;    // reduction channels per stage
+// The three limits above are the interpreter's (fixed-size local and shared arrays).  A specialised
+// kernel sizes everything from its own program, so stages up to the limits below are accepted and
+// simply have no interpreter form (they need libnvrtc at run time):
+constexpr int MAXS_JIT = 512, MAXL_JIT = 64, MAXCH_JIT = 32;
 
 struct StageArgs {
     const DIns* prog;
@@ -71,8 +75,8 @@ struct StageArgs {
     int vec_ok;                // specialised vector path: every per-element leaf pointer is 32-byte aligned
     // leaf pointers again, in PARAMETER space: the specialised kernel indexes them with compile-time
     // constants, so they are constant-bank operands (no registers, no loads); the interpreter uses `leaves`
-    const double* lp_val[MAXL];
-    double* lp_adj[MAXL];
+    const double* lp_val[MAXL_JIT];
+    double* lp_adj[MAXL_JIT];
 };
 
 #ifdef FADB_JIT
@@ -106,6 +110,7 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #define K_SIG_VEC JIT_SIG_VEC
 #define K_NCH JIT_NCH
 #define K_SLOTS JIT_NINS
+#define K_ACC (JIT_NCH > 3 ? JIT_NCH : 3)      // accumulators: the terminal's own channels are 0..2
 #define K_LSLOTS (JIT_NLEAVES > 0 ? JIT_NLEAVES : 1)
 #define K_UNROLL _Pragma("unroll")
 #if JIT_VEC > 1
@@ -133,6 +138,7 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #define K_SIG_VEC a.sig_vec
 #define K_NCH a.nch
 #define K_SLOTS MAXS
+#define K_ACC MAXCH
 #define K_LSLOTS MAXL
 #define K_UNROLL
 #define K_LOADV(k) K_LVAL(k)[i]
@@ -162,7 +168,7 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
 {
     constexpr bool BIG = STORE == 2;
     extern __shared__ double s_dyn[];
-    __shared__ double s_red[32 * MAXCH];
+    __shared__ double s_red[32 * K_ACC];
     __shared__ bool s_last;
 #ifndef FADB_JIT
     __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
@@ -189,9 +195,9 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
     double pr_pnz = 1.0, pr_zeros = 0.0, pr_val = 0.0;
     if (K_TERM == T_PROD && back) { pr_pnz = a.red[0]; pr_zeros = a.red[1]; pr_val = a.red[2]; }
 
-    double acc[MAXCH];
+    double acc[K_ACC];
 #pragma unroll
-    for (int c = 0; c < MAXCH; ++c) acc[c] = 0.0;
+    for (int c = 0; c < K_ACC; ++c) acc[c] = 0.0;
     double p_nz = 1.0, p_zeros = 0.0;
 
     double v_loc[STORE == 0 ? K_SLOTS : 1], g_loc[STORE == 0 ? K_SLOTS : 1], l_loc[STORE == 0 ? K_LSLOTS : 1];
@@ -521,10 +527,10 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
     if (K_TERM == T_PROD && (K_MODE & M_F)) {
         const double bp = block_prod_all(p_nz, s_red);
         acc[0] = p_zeros;
-        block_sum<MAXCH>(acc, s_red);
+        block_sum<K_ACC>(acc, s_red);
         if (threadIdx.x == 0) {
-            a.partials[(size_t)blockIdx.x * (MAXCH + 1) + MAXCH] = bp;
-            for (int c = 0; c < MAXCH; ++c) a.partials[(size_t)blockIdx.x * (MAXCH + 1) + c] = acc[c];
+            a.partials[(size_t)blockIdx.x * (K_ACC + 1) + K_ACC] = bp;
+            for (int c = 0; c < K_ACC; ++c) a.partials[(size_t)blockIdx.x * (K_ACC + 1) + c] = acc[c];
             __threadfence();
             s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
         }
@@ -533,8 +539,8 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         __threadfence();
         double p = 1.0, z = 0.0;
         for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            p *= __ldcg(&a.partials[(size_t)b * (MAXCH + 1) + MAXCH]);
-            z += __ldcg(&a.partials[(size_t)b * (MAXCH + 1)]);
+            p *= __ldcg(&a.partials[(size_t)b * (K_ACC + 1) + K_ACC]);
+            z += __ldcg(&a.partials[(size_t)b * (K_ACC + 1)]);
         }
         p = block_prod_all(p, s_red);
         double zz[1] = {z};
@@ -546,22 +552,22 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         }
         return;
     }
-    block_sum<MAXCH>(acc, s_red);
+    block_sum<K_ACC>(acc, s_red);
     if (threadIdx.x == 0) {
-        for (int c = 0; c < MAXCH; ++c) a.partials[(size_t)blockIdx.x * (MAXCH + 1) + c] = acc[c];
+        for (int c = 0; c < K_ACC; ++c) a.partials[(size_t)blockIdx.x * (K_ACC + 1) + c] = acc[c];
         __threadfence();
         s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    double tot[MAXCH];
+    double tot[K_ACC];
 #pragma unroll
-    for (int c = 0; c < MAXCH; ++c) tot[c] = 0.0;
+    for (int c = 0; c < K_ACC; ++c) tot[c] = 0.0;
     for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
 #pragma unroll
-        for (int c = 0; c < MAXCH; ++c) tot[c] += __ldcg(&a.partials[(size_t)b * (MAXCH + 1) + c]);
-    block_sum<MAXCH>(tot, s_red);
+        for (int c = 0; c < K_ACC; ++c) tot[c] += __ldcg(&a.partials[(size_t)b * (K_ACC + 1) + c]);
+    block_sum<K_ACC>(tot, s_red);
     if (threadIdx.x != 0) return;
     *a.ticket = 0u;
     if (K_MODE & M_F) {

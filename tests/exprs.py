@@ -184,6 +184,41 @@ def least_squares(rows, cols, flipped=False, x_var=False, inner=False):
     return build
 
 
+def many_scalar_params(n, nparams):
+    def build(e):   # a vector model with more scalar parameters than the interpreter has reduction channels
+        x = e.var(RNG.uniform(0.2, 1.5, n))
+        ps = [e.var(float(v)) for v in RNG.uniform(0.5, 1.5, nparams)]
+        acc = e.binary("mul", ps[0], x)
+        for k, p in enumerate(ps[1:], 1):
+            t = e.binary("mul", p, e.unary(("sin", "cos", "exp", "tanh")[k % 4], e.binary("mul", e.const(0.3 * k), x)))
+            acc = e.binary("add", acc, t)
+        return e.sum(acc), [x] + ps, 0.5
+    return build
+
+
+def long_chain(n, depth):
+    def build(e):   # more nodes than the interpreter's 64 slots, one stage
+        x = e.var(RNG.uniform(0.5, 1.5, n)); c = e.const(RNG.uniform(0.5, 1.5, n))
+        v = x
+        for k in range(depth):
+            v = e.binary("add", e.binary("mul", e.unary(("sin", "cos", "atan")[k % 3], v), c), e.binary("div", x, e.const(1.0 + k)))
+        return e.sum(v), [x], 1.0
+    return build
+
+
+def many_vector_leaves(n, nl):
+    def build(e):   # more distinct per-element operands than the interpreter's leaf table holds
+        xs = [e.var(RNG.uniform(0.5, 1.5, n)) for _ in range(nl)]
+        acc = xs[0]
+        for k, x in enumerate(xs[1:], 1):
+            acc = e.binary("add", acc, e.binary("mul", e.const(1.0 / k), e.pow(2, x)))
+        return e.sum(acc), xs, 2.0
+    return build
+
+
+JIT_ONLY = ("many_scalar_params", "long_chain_200_nodes", "many_vector_leaves")
+
+
 def black_scholes_vec(n, put=False):
     def build(e):   # example/black_scholes.cpp:16-39 over vec leaves
         import synth
@@ -451,6 +486,9 @@ CASES = {
     "mlp3_row": mlp3_row,
     "linreg_expr": linreg_expr(2000, 64),
     "linreg_expr_small": linreg_expr(130, 5),
+    "many_scalar_params": many_scalar_params(5003, 14),
+    "long_chain_200_nodes": long_chain(4100, 40),
+    "many_vector_leaves": many_vector_leaves(4097, 30),
     "least_squares": least_squares(5000, 64),
     "least_squares_flipped_odd": least_squares(4099, 7, flipped=True),
     "least_squares_small": least_squares(100, 3),

@@ -166,3 +166,15 @@ def test_control_flow_stage_is_not_specialisable(F):
         except F.FadbError as ex:
             refused += 1
     assert refused >= 1
+
+
+@pytest.mark.parametrize("name", exprs.JIT_ONLY)
+def test_stages_beyond_interpreter_limits_plan_and_compile(F, name):
+    exprs.RNG = np.random.default_rng(1)
+    e = F.Expr(device=False)
+    root, _, _ = exprs.CASES[name](e)
+    e.plan(root)
+    d = e.describe()
+    assert d.startswith("stages=1") and "specialised-only" in d, d[:300]
+    nbytes, log = F.jit_compile_only(e.jit_program(0, 3))
+    assert nbytes > 0
