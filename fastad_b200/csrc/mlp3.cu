@@ -171,7 +171,8 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm, \
                          g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss))
     // measured on B200, batch 2^22: <1,1> 166 us (153 registers, 8 warps/SM: FP64 pipe 37 % active, stalls are
-    // dependent-issue waits), <2,1> 155, <3,1> 159, <2,2> 121, <1,2> 115 (128 registers, 16 warps/SM): default
+    // dependent-issue waits), <2,1> 155, <3,1> 159, <2,2> 121, <1,2> 115 (128 registers, 16 warps/SM): default;
+    // <1,3> 152 and <1,4> 199 (80 / 64 registers: 430-530 bytes of spills per row)
     if (variant == 1) FADB_MLP_LAUNCH((mlp3_kernel<2, 1>));
     else if (variant == 3) FADB_MLP_LAUNCH((mlp3_kernel<2, 2>));
     else if (variant == 4) FADB_MLP_LAUNCH((mlp3_kernel<3, 1>));
