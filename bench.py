@@ -47,6 +47,17 @@ def ncu_traffic(name):
     return tot or None
 
 
+def ncu_metric(name, metric):
+    p = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(p):
+        return None
+    import csv
+    for row in csv.reader(open(p)):
+        if row and row[0] == metric:
+            return float(row[2])
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -297,7 +308,13 @@ def run_ours(args):
             t = timed_loop(step, steps2, 3, world)
             nm = op if isinstance(op, str) else f"pow{op[1]}"
             add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements")
-        del xs, adjs
+        # prod_benchmark.cpp shape: ad::prod over a vector (prod.hpp:172-212): reduce pass (8 B/elem) + adjoint pass (24 B/elem)
+        def prod_step(i):
+            F.check(L.fadb_prod(n2, C.c_void_p(xp.data_ptr()), C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0, None))
+        xp = dev(np.exp(np.random.default_rng(3).uniform(-1e-3, 1e-3, n2)))       # product stays O(1)
+        t = timed_loop(prod_step, steps2, 3, world)
+        add("prod_2^24", 32 * n2, t, steps2, n2, "elements", {"note": "two passes: (prod of non-zeros, #zeros), then adj_i += seed * prod / x_i"})
+        del xs, adjs, xp
 
     if "normal" in wl:
         # C3: normal log-pdf, N = 2^26 per rank.  vvv 72 B/elem; vss (x var) 24; vss (x const) 8
@@ -569,7 +586,13 @@ def run_ours(args):
                          "traffic_note": "ncu dram bytes inside the launch; most of the 64 B/option of stores is still in "
                                          "the 126 MB L2 when the 26 us kernel ends",
                          "peak_source": peak_src,
-                         "kernel": "bs_kernel_fast_pf<false>", "algorithmic_bytes_per_launch": BS_BYTES * n},
+                         "kernel": "bs_kernel_fast_pf<false, true, 3>", "algorithmic_bytes_per_launch": BS_BYTES * n,
+                         # the second bound of this kernel: FP64-pipe issue.  148 SMs x 64 lanes x
+                         # 1.965 GHz = 18.6e12 FP64 instructions/s; the kernel executes ~190 per option (ncu:
+                         # sm__inst_executed_pipe_fp64 of the committed capture), the reference formulation ~280
+                         "fp64": {"pipe_active_pct_ncu": ncu_metric("r1_ncu_full_bs.csv", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                                  "ceiling_options_per_s_at_280_inst": 18.6e12 / 280,
+                                  "frac_of_that_ceiling": value / world / (18.6e12 / 280)}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "options/s", "h2d_bytes_per_step": 40 * n,
                     "d2h_bytes_per_step": 64 * n, "ms_per_step": ms_e2e / e2e_steps,
