@@ -465,6 +465,64 @@ static void next_rows()
     }
 }
 
+// The README regression in its batched form and a vector model with many scalar parameters: both are
+// bound from plain g++ code and must run on the one-pass least-squares kernel / a specialised stage kernel.
+static void batched_models()
+{
+    // ---- README.md:623-662 with the 5 rows replicated 2000 times: one autodiff instead of a row loop
+    {
+        const size_t reps = 2000, rows = 5 * reps;
+        const double Xr[5][2] = {{1, 10}, {2, 20}, {3, 30}, {4, 40}, {5, 50}};
+        const double yr[5] = {32, 64, 96, 128, 160};
+        Var<double, mat> X(rows, 2);
+        Var<double, vec> y(rows);
+        for (size_t i = 0; i < rows; ++i) {
+            X.get()(i, 0) = Xr[i % 5][0]; X.get()(i, 1) = Xr[i % 5][1];
+            y.get()(i) = yr[i % 5];
+        }
+        X.upload(); y.upload();
+        Var<double, vec> theta(2);
+        theta.get() = {1., 2.};
+        auto expr = ad::bind(ad::sum(ad::pow<2>(ad::constant_view(y.data(), rows) - ad::dot(ad::constant_view(X.data(), rows, 2), theta))));
+        unsigned long long j0[4], j1[4];
+        fadb_jit_stats(j0);
+        const unsigned long long l0 = fadb_launch_count();
+        CHECK_REL(ad::autodiff(expr), 6655. * reps, 1e-13);
+        CHECK(fadb_launch_count() - l0 == 2);                 // fadb_lsq: one pass over X + the scalar epilogue
+        CHECK_REL(theta.get_adj()(0), -1210. * reps, 1e-13);
+        CHECK_REL(theta.get_adj()(1), -12100. * reps, 1e-13);
+        fadb_jit_stats(j1);
+        CHECK(j1[3] == j0[3]);                                // no stage kernel involved
+    }
+    // ---- 12 scalar parameters broadcast into one vector stage (more reduction channels than the interpreter has)
+    {
+        const size_t n = 4321;
+        Var<double, vec> x(n);
+        for (size_t i = 0; i < n; ++i) x.get()(i) = 0.2 + 1.3 * double(i) / n;
+        std::vector<Var<double>> p;
+        for (int k = 0; k < 12; ++k) p.emplace_back(0.5 + 0.1 * k);
+        auto term = [&](int k) { return p[k] * ad::sin((0.3 * (k + 1)) * x); };
+        auto model = ad::sum(term(0) + term(1) + term(2) + term(3) + term(4) + term(5) + term(6) + term(7) + term(8) + term(9) +
+                             term(10) + term(11));
+        auto expr = ad::bind(model);
+        unsigned long long j0[4], j1[4];
+        fadb_jit_stats(j0);
+        const double v = ad::autodiff(expr);
+        fadb_jit_stats(j1);
+        CHECK(j1[3] == j0[3] + 1 && j1[2] == j0[2]);          // ran on a specialised kernel
+        double ref = 0, dp3 = 0, dx7 = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const double xi = 0.2 + 1.3 * double(i) / n;
+            for (int k = 0; k < 12; ++k) ref += (0.5 + 0.1 * k) * std::sin(0.3 * (k + 1) * xi);
+            dp3 += std::sin(0.3 * 4 * xi);
+            if (i == 7) for (int k = 0; k < 12; ++k) dx7 += (0.5 + 0.1 * k) * 0.3 * (k + 1) * std::cos(0.3 * (k + 1) * xi);
+        }
+        CHECK_REL(v, ref, 1e-12);
+        CHECK_REL(p[3].get_adj(), dp3, 1e-12);
+        CHECK_REL(x.get_adj()(7), dx7, 1e-13);
+    }
+}
+
 int main()
 {
     if (fadb_init(0) != 0) { std::printf("no CUDA device: %s\n", fadb_last_error()); return 2; }
@@ -475,5 +533,6 @@ int main()
     readme_examples();
     vectors_and_seeds();
     next_rows();
+    batched_models();
     return report("test_host_layer");
 }
