@@ -175,6 +175,99 @@ __global__ void outer_kernel(size_t m, int k, const double* __restrict__ A, cons
     }
 }
 
+// Ladj (+)= A R^T when the SHARED dimension p is the large one (a small weight matrix times a batch:
+// dot(W, X) with X k x p, p = batch): the m x k result is tiny, the sum runs over p columns.  Every CTA
+// takes a contiguous range of columns, thread e owns output entry e (m k <= GV_THREADS * WR_PER), per-CTA
+// partial results, last CTA adds them in CTA order (deterministic).  A and R are read exactly once.
+constexpr int WR_PER = 4;
+__global__ void __launch_bounds__(GV_THREADS)
+wide_outer_kernel(int m, int k, size_t p, const double* __restrict__ A, const double* __restrict__ R, double* partials /* [grid][m k] */,
+                  unsigned int* ticket, double* Ladj, int lmode)
+{
+    __shared__ bool s_last;
+    const int n = m * k;
+    const size_t per = (p + gridDim.x - 1) / gridDim.x;
+    const size_t j0 = (size_t)blockIdx.x * per, j1 = j0 + per < p ? j0 + per : p;
+    double acc[WR_PER];
+    int ei[WR_PER], eq[WR_PER];
+#pragma unroll
+    for (int t = 0; t < WR_PER; ++t) {
+        const int e = threadIdx.x + t * GV_THREADS;
+        acc[t] = 0.0; ei[t] = e < n ? e % m : 0; eq[t] = e < n ? e / m : 0;
+    }
+    for (size_t j = j0; j < j1; ++j) {
+        const double* a = A + j * (size_t)m;
+        const double* r = R + j * (size_t)k;
+#pragma unroll
+        for (int t = 0; t < WR_PER; ++t) acc[t] += __ldg(a + ei[t]) * __ldg(r + eq[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < WR_PER; ++t) {
+        const int e = threadIdx.x + t * GV_THREADS;
+        if (e < n) partials[(size_t)blockIdx.x * n + e] = acc[t];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&partials[(size_t)b * n + e]);
+        Ladj[e] = (lmode == 2) ? v : Ladj[e] + v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// The same sum for a SMALL result (m k <= WS_MAXN, e.g. a 3 x 2 weight matrix): a thread per output entry
+// would leave almost every thread idle, so the columns are spread over the lanes instead: a warp takes 32
+// consecutive columns (coalesced), each product is summed across the warp and lane 0 adds it to the warp's
+// row of shared-memory accumulators; warps, CTAs and the final pass combine in a fixed order.
+constexpr int WS_MAXN = 256;
+__global__ void __launch_bounds__(GV_THREADS)
+wide_outer_small_kernel(int m, int k, size_t p, const double* __restrict__ A, const double* __restrict__ R, double* partials,
+                        unsigned int* ticket, double* Ladj, int lmode)
+{
+    __shared__ double s_acc[GV_THREADS / 32][WS_MAXN];
+    __shared__ bool s_last;
+    const int n = m * k, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = GV_THREADS / 32;
+    for (int e = lane; e < n; e += 32) s_acc[warp][e] = 0.0;
+    __syncwarp();
+    const size_t per = (p + gridDim.x - 1) / gridDim.x;
+    const size_t j0 = (size_t)blockIdx.x * per, j1 = j0 + per < p ? j0 + per : p;
+    for (size_t jb = j0 + (size_t)warp * 32; jb < j1; jb += (size_t)nw * 32) {
+        const size_t j = jb + lane;
+        const bool in = j < j1;
+        for (int q = 0; q < k; ++q) {
+            const double rq = in ? __ldg(R + j * (size_t)k + q) : 0.0;
+            for (int i = 0; i < m; ++i) {
+                double v = in ? __ldg(A + j * (size_t)m + i) * rq : 0.0;
+                v = warp_sum(v);
+                if (lane == 0) s_acc[warp][i + q * m] += v;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += s_acc[w][e];
+        partials[(size_t)blockIdx.x * n + e] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&partials[(size_t)b * n + e]);
+        Ladj[e] = (lmode == 2) ? v : Ladj[e] + v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 __global__ void transpose_fwd_kernel(int m, int k, const double* __restrict__ X, double* V)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,6 +349,7 @@ struct Stage {
     int f_shape = 0; const double* f_X = nullptr; const double* f_w = nullptr; double* f_wadj = nullptr;
     size_t f_rows = 0, f_cols = 0; double* f_part = nullptr;
     double* gv_part = nullptr; int gv_grid = 0;    // tall dot stage: per-CTA partial rows of L^T A
+    double* wr_part = nullptr; int wr_grid = 0;    // wide dot stage (large p, small m x k): per-CTA partials of A R^T
 };
 
 }  // namespace fadb
@@ -764,9 +858,13 @@ struct fadb_expr {
         for (auto& sp : plan) {
             Stage& st = *sp;
             if (st.type != 0) {
-                if (st.type == 1 && st.p == 1 && st.m >= 4096 && st.k <= 4096) {
+                if (st.type == 1 && st.p <= 16 && st.m >= 4096 && st.k <= 4096) {
                     st.gv_grid = std::min(2 * c.sms, (st.m + 255) / 256);
                     int rc = dev_alloc((size_t)st.gv_grid * st.k * sizeof(double), (void**)&st.gv_part);
+                    if (rc) return rc;
+                } else if (st.type == 1 && st.p >= 4096 && st.m * st.k <= GV_THREADS * WR_PER && st.L.adj_mode) {
+                    st.wr_grid = (int)std::min<size_t>(2 * c.sms, ((size_t)st.p + 1023) / 1024);
+                    int rc = dev_alloc((size_t)st.wr_grid * st.m * st.k * sizeof(double), (void**)&st.wr_part);
                     if (rc) return rc;
                 }
                 if (st.L.stage >= 0) { st.L.val = plan[st.L.stage]->mval; st.L.adj = plan[st.L.stage]->madj; }
@@ -998,26 +1096,37 @@ struct fadb_expr {
             FADB_CUDA(cudaGetLastError());
             return FADB_OK;
         }
-        if (st.gv_part) {       // tall L, vector R: the HBM-bound kernels
+        if (st.gv_part) {       // tall L, R a vector or a few columns: the HBM-bound kernels, one launch per column of R
+            const size_t mp = (size_t)st.m * st.p;
             if (mode & M_F) {
                 const int grid = grid_for(c, st.m, 8, GV_THREADS);
-                gemv_n_kernel<<<grid, GV_THREADS, st.k * sizeof(double), c.stream>>>((size_t)st.m, st.k, st.L.val, st.R.val, st.mval);
-                c.launches++;
+                for (int j = 0; j < st.p; ++j) {
+                    gemv_n_kernel<<<grid, GV_THREADS, st.k * sizeof(double), c.stream>>>((size_t)st.m, st.k, st.L.val, st.R.val + (size_t)j * st.k,
+                                                                                           st.mval + (size_t)j * st.m);
+                    c.launches++;
+                }
             }
             if (mode & M_B) {
                 const double* A = seed_vec ? seed_vec : st.madj;
                 if (!seed_vec && mode == M_FB) {
-                    fill_kernel<<<(st.m + threads - 1) / threads, threads, 0, c.stream>>>(st.madj, st.m, seed);
+                    fill_kernel<<<(unsigned)((mp + threads - 1) / threads), threads, 0, c.stream>>>(st.madj, mp, seed);
                     c.launches++;
                 }
-                if (st.R.adj_mode) {
-                    gemv_t_kernel<<<st.gv_grid, GV_THREADS, 0, c.stream>>>((size_t)st.m, st.k, st.L.val, A, st.gv_part, c.tickets + 12,
-                                                                            st.R.adj, st.R.adj_mode);
-                    c.launches++;
-                }
+                if (st.R.adj_mode)
+                    for (int j = 0; j < st.p; ++j) {
+                        gemv_t_kernel<<<st.gv_grid, GV_THREADS, 0, c.stream>>>((size_t)st.m, st.k, st.L.val, A + (size_t)j * st.m, st.gv_part,
+                                                                                c.tickets + 12, st.R.adj + (size_t)j * st.k, st.R.adj_mode);
+                        c.launches++;
+                    }
                 if (st.L.adj_mode) {
-                    outer_kernel<<<grid_for(c, (size_t)st.m * st.k, 8, 256), 256, 0, c.stream>>>((size_t)st.m, st.k, A, st.R.val, st.L.adj,
-                                                                                                  st.L.adj_mode);
+                    if (st.p == 1)
+                        outer_kernel<<<grid_for(c, (size_t)st.m * st.k, 8, 256), 256, 0, c.stream>>>((size_t)st.m, st.k, A, st.R.val, st.L.adj,
+                                                                                                      st.L.adj_mode);
+                    else {
+                        const int n = st.m * st.k;
+                        dot_bwd_kernel<<<(n + threads - 1) / threads, threads, 0, c.stream>>>(st.m, st.k, st.p, st.L.val, st.R.val, A, st.L.adj,
+                                                                                                st.L.adj_mode, nullptr, 0);
+                    }
                     c.launches++;
                 }
             }
@@ -1036,11 +1145,24 @@ struct fadb_expr {
                 fill_kernel<<<(n + threads - 1) / threads, threads, 0, c.stream>>>(st.madj, n, seed);
                 c.launches++;
             }
-            int n = std::max(st.m * st.k, st.k * st.p);
-            dot_bwd_kernel<<<(n + threads - 1) / threads, threads, 0, c.stream>>>(
-                st.m, st.k, st.p, st.L.val, st.R.val, A, st.L.adj_mode ? st.L.adj : nullptr, st.L.adj_mode,
-                st.R.adj_mode ? st.R.adj : nullptr, st.R.adj_mode);
-            c.launches++;
+            const bool wide = st.wr_part != nullptr;    // A R^T summed over a large p: partial sums per CTA
+            if (wide) {
+                if (st.m * st.k <= WS_MAXN)
+                    wide_outer_small_kernel<<<st.wr_grid, GV_THREADS, 0, c.stream>>>(st.m, st.k, (size_t)st.p, A, st.R.val, st.wr_part,
+                                                                                      c.tickets + 13, st.L.adj, st.L.adj_mode);
+                else
+                    wide_outer_kernel<<<st.wr_grid, GV_THREADS, 0, c.stream>>>(st.m, st.k, (size_t)st.p, A, st.R.val, st.wr_part, c.tickets + 13,
+                                                                                st.L.adj, st.L.adj_mode);
+                c.launches++;
+            }
+            const bool want_l = st.L.adj_mode && !wide;
+            if (want_l || st.R.adj_mode) {
+                int n = std::max(want_l ? st.m * st.k : 0, st.R.adj_mode ? st.k * st.p : 0);
+                dot_bwd_kernel<<<(n + threads - 1) / threads, threads, 0, c.stream>>>(
+                    st.m, st.k, st.p, st.L.val, st.R.val, A, want_l ? st.L.adj : nullptr, st.L.adj_mode,
+                    st.R.adj_mode ? st.R.adj : nullptr, st.R.adj_mode);
+                c.launches++;
+            }
         }
         FADB_CUDA(cudaGetLastError());
         return FADB_OK;

@@ -219,6 +219,26 @@ def many_vector_leaves(n, nl):
 JIT_ONLY = ("many_scalar_params", "long_chain_200_nodes", "many_vector_leaves")
 
 
+def dot_tall_multi_rhs(rows, cols, outs, x_var=False):
+    def build(e):   # multi-output regression: X (rows x cols) times W (cols x outs); sum of squared residuals
+        X = RNG.normal(size=(rows, cols)); W = RNG.normal(size=(cols, outs)); Y = X @ W + 0.1 * RNG.normal(size=(rows, outs))
+        Xn = e.var(X) if x_var else e.const(X)
+        Wn = e.var(W + 0.05)
+        r = e.binary("sub", e.const(Y), e.dot(Xn, Wn))
+        return e.sum(e.pow(2, r)), ([Xn, Wn] if x_var else [Wn]), 0.5
+    return build
+
+
+def dot_wide_batch(hidden, inputs, batch):
+    def build(e):   # a small weight matrix times a batch of columns: dot(W, X), X inputs x batch (the batched layer of a network)
+        W = e.var(RNG.normal(size=(hidden, inputs))); b = e.var(RNG.normal(size=(hidden, 1)))
+        X = e.const(RNG.uniform(-1, 1, size=(inputs, batch)))
+        T = e.const(RNG.uniform(0, 1, size=(hidden, batch)))
+        h = e.unary("sigmoid", e.dot(W, X))
+        return e.sum(e.pow(2, e.binary("sub", h, T))), [W], 1.0
+    return build
+
+
 def black_scholes_vec(n, put=False):
     def build(e):   # example/black_scholes.cpp:16-39 over vec leaves
         import synth
@@ -489,6 +509,10 @@ CASES = {
     "many_scalar_params": many_scalar_params(5003, 14),
     "long_chain_200_nodes": long_chain(4100, 40),
     "many_vector_leaves": many_vector_leaves(4097, 30),
+    "dot_tall_3_rhs": dot_tall_multi_rhs(4500, 6, 3),
+    "dot_tall_2_rhs_x_variable": dot_tall_multi_rhs(4100, 3, 2, x_var=True),
+    "dot_wide_batch": dot_wide_batch(3, 2, 6000),
+    "dot_wide_batch_16x8": dot_wide_batch(16, 8, 4099),
     "least_squares": least_squares(5000, 64),
     "least_squares_flipped_odd": least_squares(4099, 7, flipped=True),
     "least_squares_small": least_squares(100, 3),

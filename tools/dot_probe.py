@@ -28,3 +28,17 @@ v = e.autodiff(1.0)
 wh = 0.01 * np.arange(cols)
 r = yh - Xh @ wh
 print("value rel err", abs(v[0] - r @ r) / (r @ r), "adj rel err", np.max(np.abs(e.adj(w).ravel() / (reps + 4) - (-2 * Xh.T @ r))) / np.max(np.abs(2 * Xh.T @ r)))
+
+# ---- wide case: a 3x2 weight matrix times a 2 x 2^20 batch (the batched layer of the README network)
+B = 1 << 20
+rng = np.random.default_rng(5)
+e = F.Expr()
+W = e.var(rng.normal(size=(3, 2))); Xb = e.const(rng.uniform(-1, 1, size=(2, B))); T = e.const(rng.uniform(0, 1, size=(3, B)))
+e.bind(e.sum(e.pow(2, e.binary("sub", e.unary("sigmoid", e.dot(W, Xb)), T))))
+print([l for l in e.describe().split("\n") if l.startswith("stage")])
+for _ in range(3): step2 = F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+torch.cuda.synchronize()
+e0.record()
+for _ in range(reps): F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+e1.record(); torch.cuda.synchronize()
+print("wide 3x2 * 2x2^20: ms/step %.4f" % (e0.elapsed_time(e1) / reps))
