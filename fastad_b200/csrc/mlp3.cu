@@ -9,6 +9,8 @@
 // One thread owns one row: forward and adjoint sweep in registers; the 25 gradients + loss are
 // reduced across the CTA with warp shuffles and across CTAs by the last-arriving CTA.
 // The matrices are 3x2, 3x3 and 1x3: far below a DMMA tile, so the FP64 tensor path is not used.
+#include <algorithm>
+
 #include "common.cuh"
 #include "../../include/fastad_b200/fastmath.cuh"
 
@@ -85,15 +87,15 @@ __device__ __forceinline__ void mlp3_row(const double* __restrict__ p, double xa
 }
 
 // ROWS rows per thread and trip (independent dependency chains for the FP64 pipe), MINB resident CTAs
-template <int ROWS, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int ROWS, int MINB, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB)
 mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict__ y,
             const double* __restrict__ parm, double* cta_partials, unsigned int* ticket,
             double* grad, int overwrite, double* out_loss)
 {
     pdl_prologue();
     __shared__ double p[NP];
-    __shared__ double red[8][NOUT];
+    __shared__ double red[THREADS / 32][NOUT];
     __shared__ bool is_last;
     if (threadIdx.x < NP) p[threadIdx.x] = parm[threadIdx.x];
     __syncthreads();
@@ -181,6 +183,11 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     // default: occupancy wins once every CTA slot has work; below that the grid-wide reduction (one partial
     // row + one ticket per CTA) dominates and fewer CTAs are faster (2^16 rows: 11.1 us vs 13.9 us)
     else if (batch > (size_t)4 * c->sms * threads) FADB_MLP_LAUNCH((mlp3_kernel<1, 2>));
+    else if (variant == 7 || (variant == -2 && batch > (size_t)c->sms * 256 && batch <= (size_t)c->sms * 512)) {
+        // one row per thread in ONE trip with no more CTAs (= partial rows and tickets) than SMs: 512-thread CTAs
+        FADB_CUDA(launch_pdl(mlp3_kernel<1, 1, 512>, (int)std::min<size_t>((batch + 511) / 512, (size_t)c->sms), 512, 0, c->stream, batch, X, y,
+                             parm, g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss));
+    }
     else FADB_MLP_LAUNCH((mlp3_kernel<1, 1>));
 #undef FADB_MLP_LAUNCH
     c->launches++;
