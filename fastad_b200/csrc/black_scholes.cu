@@ -105,7 +105,7 @@ __device__ __forceinline__ BSRes bs_eval_fast(double S, double K, double sigma, 
         fm::phi_pair(c1, Phi1, Phi1n, E1);
         fm::phi_pair(c2, Phi2, Phi2n, E2);
     }
-    const double PV = K * fm::exp_(-r * tau);
+    const double PV = K * (PW ? fm::exp_t(-r * tau, tab + 256) : fm::exp_(-r * tau));
 
     BSRes o;
     o.call = Phi1 * S - Phi2 * PV;
@@ -182,9 +182,10 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
                   const double* __restrict__ sigma, const double* __restrict__ tau,
                   const double* __restrict__ r, BSOut out)
 {
-    __shared__ double s_tab[PW ? 256 : 1];
+    __shared__ double s_tab[PW ? 288 : 1];      // erfcx pieces [0, 256) + 2^(j/32) [256, 288)
     if (PW) {            // constant memory: written before any launch, safe to read ahead of the dependency sync
         s_tab[threadIdx.x] = fm::kErfcx32_d[threadIdx.x];
+        if (threadIdx.x < 32) s_tab[256 + threadIdx.x] = fm::kExp2_32_d[threadIdx.x];
         __syncthreads();
     }
     pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
@@ -225,8 +226,9 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     // fastmath 27.7 (variant 6); fastmath + software-pipelined loads, 128 registers, 2 CTAs/SM
     // 25.5 (variant 20); the same kernel launched with programmatic dependent launch 23.5 (variant 22);
     // Phi from the 32-interval degree-7 erfcx table in shared memory (40 fewer FP64 instructions per
-    // option, 110 registers) 22.6 (variant 21); the same at 3 CTAs/SM (78 registers, no spills) 21.4
-    // (default); 4 CTAs/SM (64 registers, spills) 22.7 (variant 24).
+    // option, 110 registers) 22.6 (variant 21); the same at 3 CTAs/SM (78 registers, no spills) 21.4;
+    // 4 CTAs/SM (64 registers, spills) 22.7 (variant 24); exp through a 32-entry 2^(j/32) table in shared
+    // memory (11 instead of 20 FP64 instructions, three per option) 20.7 (default).
     // Two options per thread, tighter launch bounds (spills) and atomic
     // work-stealing were measured slower and removed.
     static int variant = -1;

@@ -9,11 +9,12 @@ int main()
 {
     std::mt19937_64 gen(12345);
     std::uniform_real_distribution<double> U(0., 1.);
-    double e_exp = 0, e_log = 0, e_div = 0, e_sqrt = 0, e_phi_abs = 0, e_phi_tail = 0, e_E = 0, e_pw_abs = 0, e_pw_tail = 0, e_pw_vs = 0;
+    double e_expt = 0, e_exp = 0, e_log = 0, e_div = 0, e_sqrt = 0, e_phi_abs = 0, e_phi_tail = 0, e_E = 0, e_pw_abs = 0, e_pw_tail = 0, e_pw_vs = 0;
     for (int i = 0; i < 2000000; ++i) {
         const double a = U(gen), b = U(gen);
         const double x = -60.0 * a * a + 2.0 * (b - 0.5);                 // exp arguments, mostly negative
         e_exp = std::max(e_exp, ulp_diff(fm::exp_(x), std::exp(x)));
+        e_expt = std::max(e_expt, ulp_diff(fm::exp_t(x, fm::bs_table_host() + 256), std::exp(x)));
         const double y = std::exp(8.0 * (a - 0.5));                       // log arguments 0.018 .. 55
         e_log = std::max(e_log, ulp_diff(fm::log_(y), std::log(y)));
         const double p = 0.01 + 300 * a, q = 0.01 + 300 * b;
@@ -30,18 +31,22 @@ int main()
         e_E = std::max(e_E, ulp_diff(E, std::exp(-(u * u))));
         // piecewise-table variant (what the Black-Scholes kernel uses)
         double Phi2, PhiN2, E2;
-        fm::phi_pair_pw(d, fm::kErfcx32_h, Phi2, PhiN2, E2);
+        fm::phi_pair_pw(d, fm::bs_table_host(), Phi2, PhiN2, E2);
         e_pw_abs = std::max(e_pw_abs, std::max(std::fabs(Phi2 - ref), std::fabs(PhiN2 - refn)));
         e_pw_tail = std::max(e_pw_tail, d < 0 ? ulp_diff(Phi2, ref) : ulp_diff(PhiN2, refn));
         e_pw_vs = std::max(e_pw_vs, std::max(std::fabs(Phi2 - Phi), std::fabs(PhiN2 - PhiN)));
-        CHECK(E2 == E);
+        e_E = std::max(e_E, ulp_diff(E2, std::exp(-(u * u))));   // the table exp: same 1-ulp bound
     }
     std::printf("piecewise Phi: abs %.3g, tail ulp %.2f, vs single polynomial abs %.3g\n", e_pw_abs, e_pw_tail, e_pw_vs);
     CHECK(e_pw_abs <= 4e-16);
     CHECK(e_pw_tail <= 8.0);
     std::printf("max ulp: exp %.2f log %.2f div %.2f sqrt %.2f gauss %.2f | Phi abs %.3g, tail ulp %.2f\n",
                 e_exp, e_log, e_div, e_sqrt, e_E, e_phi_abs, e_phi_tail);
+    std::printf("table exp: max ulp %.2f\n", e_expt);
     CHECK(e_exp <= 1.0);
+    CHECK(e_expt <= 1.0);
+    CHECK(fm::exp_t(-800.0, fm::bs_table_host() + 256) == 0.0 && fm::exp_t(0.0, fm::bs_table_host() + 256) == 1.0);
+    for (double xx : {-708.0, -707.9, -1e-300, 1e-17, 0.0108, 709.0, 700.5}) CHECK(ulp_diff(fm::exp_t(xx, fm::bs_table_host() + 256), std::exp(xx)) <= 1.0);
     CHECK(e_log <= 1.0);
     CHECK(e_div <= 1.0);
     CHECK(e_sqrt <= 1.0);
@@ -57,11 +62,11 @@ int main()
     CHECK(std::fabs(P - 0.5) <= 1.2e-16 && std::fabs(N - 0.5) <= 1.2e-16 && E == 1.0);
     fm::phi_pair(40.0, P, N, E);
     CHECK(P == 1.0 && N == 0.0 && E == 0.0);
-    fm::phi_pair_pw(0.0, fm::kErfcx32_h, P, N, E);
+    fm::phi_pair_pw(0.0, fm::bs_table_host(), P, N, E);
     CHECK(std::fabs(P - 0.5) <= 1.2e-16 && std::fabs(N - 0.5) <= 1.2e-16 && E == 1.0);
-    fm::phi_pair_pw(40.0, fm::kErfcx32_h, P, N, E);
+    fm::phi_pair_pw(40.0, fm::bs_table_host(), P, N, E);
     CHECK(P == 1.0 && N == 0.0 && E == 0.0);
-    fm::phi_pair_pw(-1e-300, fm::kErfcx32_h, P, N, E);
+    fm::phi_pair_pw(-1e-300, fm::bs_table_host(), P, N, E);
     CHECK(std::fabs(P - 0.5) <= 1.2e-16);
     return report("test_fastmath");
 }
