@@ -91,7 +91,7 @@ __device__ __forceinline__ BSRes bs_eval_fast(double S, double K, double sigma, 
     const double sqrt_tau = fm::sqrt_(tau);
     const double inv_K = fm::rcp_(K);
     const double x = fm::div_(S, K, inv_K);                    // S / K
-    const double c0 = fm::log_(x);                             // cache[0]
+    const double c0 = PW ? fm::log_t(x, tab + 288) : fm::log_(x);   // cache[0]
     const double sst = sigma * sqrt_tau;
     const double drift = (r + sigma * sigma * 0.5) * tau;
     const double inv_sst = fm::rcp_(sst);
@@ -182,10 +182,11 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
                   const double* __restrict__ sigma, const double* __restrict__ tau,
                   const double* __restrict__ r, BSOut out)
 {
-    __shared__ double s_tab[PW ? 288 : 1];      // erfcx pieces [0, 256) + 2^(j/32) [256, 288)
+    __shared__ double s_tab[PW ? 675 : 1];      // erfcx pieces [0, 256) + 2^(j/32) [256, 288) + log table [288, 675)
     if (PW) {            // constant memory: written before any launch, safe to read ahead of the dependency sync
         s_tab[threadIdx.x] = fm::kErfcx32_d[threadIdx.x];
         if (threadIdx.x < 32) s_tab[256 + threadIdx.x] = fm::kExp2_32_d[threadIdx.x];
+        for (int i = threadIdx.x; i < 387; i += 256) s_tab[288 + i] = fm::kLogT_d[i];
         __syncthreads();
     }
     pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
@@ -228,7 +229,8 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     // Phi from the 32-interval degree-7 erfcx table in shared memory (40 fewer FP64 instructions per
     // option, 110 registers) 22.6 (variant 21); the same at 3 CTAs/SM (78 registers, no spills) 21.4;
     // 4 CTAs/SM (64 registers, spills) 22.7 (variant 24); exp through a 32-entry 2^(j/32) table in shared
-    // memory (11 instead of 20 FP64 instructions, three per option) 20.7 (default).
+    // memory (11 instead of 20 FP64 instructions, three per option) 20.7; log through a 129-entry
+    // {1/c, log c} table (no division, 15 instead of 27) 20.5 (default).
     // Two options per thread, tighter launch bounds (spills) and atomic
     // work-stealing were measured slower and removed.
     static int variant = -1;

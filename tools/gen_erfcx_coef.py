@@ -83,3 +83,22 @@ for j in range(K8):
         p = sum(table[j][k]*x**k for k in range(D8+1))
         worst = max(worst, abs(p/g_t(t) - 1))
 print("// max relative truncation error:", mp.nstr(worst, 3))
+
+# ---- log table (fm::kLogT): z in [0.75, 1.5) = 2^-k x; i = ((bits(x) - bits(0.75) + 2^44) >> 45) & 255 picks one of
+# 129 centres c_i (c_64 = 1 exactly; spacing 2^-8 below 1, 2^-7 above); entry i = {invc, logc_hi, logc_lo} with
+# invc = double(1 / c_i) and logc = -log(invc) for THAT double, split so that logc_hi has 32 trailing zero bits
+# (k ln2_hi + logc_hi is then exact).  |r| = |z invc - 1| <= 2^-8 (+ rounding of invc).
+import struct
+def dbits(x): return struct.unpack("<Q", struct.pack("<d", x))[0]
+def fbits(u): return struct.unpack("<d", struct.pack("<Q", u))[0]
+rows = []
+for i in range(129):
+    c = mp.mpf(1) - (64 - i) * mp.mpf(2) ** -8 if i <= 64 else mp.mpf(1) + (i - 64) * mp.mpf(2) ** -7
+    invc = float(1 / c)
+    logc = -mp.log(mp.mpf(invc))
+    hi = fbits(dbits(float(logc)) & ~((1 << 26) - 1)) if logc != 0 else 0.0       # 27 significant bits kept... exactness margin
+    lo = float(logc - mp.mpf(hi))
+    rows.append((invc, hi, lo))
+print("// kLogT: 129 x {invc, logc_hi, logc_lo}")
+for i, (a, b, c) in enumerate(rows):
+    print("    %.17g, %.17g, %.17g, \\" % (a, b, c))
