@@ -46,6 +46,8 @@ SIGNATURES = {
     "fadb_memset_zero": (_i, [_vp, _sz]),
     "fadb_host_alloc_pinned": (_i, [_sz, C.POINTER(_vp)]),
     "fadb_host_free_pinned": (_i, [_vp]),
+    "fadb_host_register": (_i, [_vp, _sz]),
+    "fadb_host_unregister": (_i, [_vp]),
     "fadb_black_scholes": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _u]),
     "fadb_black_scholes_host": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "fadb_sum_unary": (_i, [_i, _sz, _vp, _vp, _d, _u, _dp]),

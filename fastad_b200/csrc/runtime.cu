@@ -228,4 +228,24 @@ int fadb_host_free_pinned(void* host)
     return FADB_OK;
 }
 
+// Page-lock and map an EXISTING host array (a std::vector, an Eigen matrix): the host entry points then take
+// their one-launch path over PCIe instead of staging through bounce buffers.  The caller keeps ownership
+// and must call fadb_host_unregister before freeing the memory.
+int fadb_host_register(void* host, size_t nbytes)
+{
+    FADB_REQUIRE(host != nullptr && nbytes > 0, "fadb_host_register: null pointer or empty range");
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    FADB_CUDA(cudaHostRegister(host, nbytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return FADB_OK;
+}
+
+int fadb_host_unregister(void* host)
+{
+    if (!host) return FADB_OK;
+    FADB_CUDA(cudaHostUnregister(host));
+    return FADB_OK;
+}
+
 }  // extern "C"

@@ -88,6 +88,10 @@ int fadb_d2h(void* host_dst, const void* dev_src, size_t nbytes);
 int fadb_memset_zero(void* dev, size_t nbytes);           /* reset_adj(), value_adj_view.hpp:57 */
 int fadb_host_alloc_pinned(size_t nbytes, void** out_host);
 int fadb_host_free_pinned(void* host);
+/* page-lock + map an existing host array (caller keeps ownership; unregister before freeing it): the *_host
+ * entry points then run ONE launch over PCIe on it instead of staging copies */
+int fadb_host_register(void* host, size_t nbytes);
+int fadb_host_unregister(void* host);
 
 /* ------------------------------------------------------------------ K1: Black-Scholes
  * The expression of example/black_scholes.cpp:16-39 (call and put, each bound and

@@ -329,6 +329,34 @@ def test_black_scholes_host_entry_page_locked_direct_path(fb):
         np.testing.assert_array_equal(h, host(g))
 
 
+def test_black_scholes_host_entry_registered_user_arrays(fb):
+    # plain numpy arrays (what a user of the reference holds), page-locked in place with fadb_host_register:
+    # the host entry takes the one-launch path; after unregistering it stages again.  Same bits every time.
+    import ctypes as C
+    n = 50000
+    inp = synth.black_scholes_inputs(n)
+    keys = ("S", "K", "sigma", "tau", "r")
+    out1 = fb.black_scholes(*(dev(inp[k]) for k in keys))
+    ins = [np.ascontiguousarray(inp[k]) for k in keys]
+    outs = [np.zeros(n) for _ in range(8)]
+    for a in ins + outs:
+        fb.check(fb.lib().fadb_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+    try:
+        l0 = fb.lib().fadb_launch_count()
+        fb.black_scholes_host(*ins, outs)
+        assert fb.lib().fadb_launch_count() - l0 == 1
+        for h, g in zip(outs, out1):
+            np.testing.assert_array_equal(h, host(g))
+    finally:
+        for a in ins + outs:
+            fb.check(fb.lib().fadb_host_unregister(C.c_void_p(a.ctypes.data)))
+    for o in outs:
+        o[:] = 0
+    fb.black_scholes_host(*ins, outs)                        # pageable again: staged copies
+    for h, g in zip(outs, out1):
+        np.testing.assert_array_equal(h, host(g))
+
+
 def test_black_scholes_full_size_put_call_parity(fb):
     # BASELINE config 1 size: 2^20 options; size-independent property C - P = S - PV
     n = 1 << 20
