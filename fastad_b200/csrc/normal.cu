@@ -38,7 +38,17 @@ sigma_check_kernel(size_t n, const double* __restrict__ sigma, double* partials,
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const bool vec = aligned32(sigma);
     const size_t n4 = vec ? n / 4 : 0;
-    for (size_t q = tid; q < n4; q += nth) {
+    size_t q = tid;
+    for (; q + 3 * nth < n4; q += 4 * nth) {          // read-only stream: four 256-bit loads in flight per thread
+        double4_t s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] = ldg256_stream(sigma + 4 * (q + u * nth));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[0] += (s[u].v[k] > 0) ? 0.0 : 1.0;
+    }
+    for (; q < n4; q += nth) {
         const double4_t s = ldg256_stream(sigma + 4 * q);
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[0] += (s.v[k] > 0) ? 0.0 : 1.0;
@@ -127,7 +137,25 @@ normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_
                (!a.x_adj || aligned32(a.x_adj)) && (!MU_VEC || !a.mu_adj || aligned32(a.mu_adj)) &&
                (!SIG_VEC || !a.sigma_adj || aligned32(a.sigma_adj));
     const size_t n4 = vec ? a.n / 4 : 0;
-    for (size_t q = tid; q < n4; q += nth) {
+    size_t q0 = tid;
+    if (!MU_VEC && !SIG_VEC && !wx) {
+        // constant x, scalar mu and sigma: a pure reduction (8 B/elem).  Four independent 256-bit loads per
+        // thread and trip keep the read stream deep; same per-thread accumulation order as the loop below.
+        for (; q0 + 3 * nth < n4; q0 += 4 * nth) {
+            double4_t xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = ldg256_stream(a.x + 4 * (q0 + u * nth));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double d = xv[u].v[k] - m_scl;
+                    acc[0] += d * d;
+                    acc[2] += d;
+                }
+        }
+    }
+    for (size_t q = q0; q < n4; q += nth) {
         const size_t i = 4 * q;
         const double4_t xv = ldg256_stream(a.x + i);
         double4_t mv, sv;
