@@ -588,7 +588,7 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "kernel": "bs_kernel_fast_pf<false, true, 3>", "algorithmic_bytes_per_launch": BS_BYTES * n,
                          # the second bound of this kernel: FP64-pipe issue.  148 SMs x 64 lanes x
-                         # 1.965 GHz = 18.6e12 FP64 instructions/s; the kernel executes ~190 per option (ncu:
+                         # 1.965 GHz = 18.6e12 FP64 instructions/s; the kernel executes ~155 per option (ncu:
                          # sm__inst_executed_pipe_fp64 of the committed capture), the reference formulation ~280
                          "fp64": {"pipe_active_pct_ncu": ncu_metric("r1_ncu_full_bs.csv", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                                   "ceiling_options_per_s_at_280_inst": 18.6e12 / 280,
