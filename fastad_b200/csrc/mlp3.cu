@@ -22,10 +22,16 @@ constexpr int NOUT = NP + 1;      // + loss
 // exp on the ordinary range through fastmath.cuh (<= 1 ulp), libdevice otherwise
 // 1 / (1 + e) by Newton reciprocal; e = +inf (x < -709) gives 0 like the IEEE division would
 __device__ __forceinline__ double inv1p(double e) { return e > 1e300 ? 0.0 : fm::rcp_(1 + e); }
-__device__ __forceinline__ double exp_s(double x) { return (fabs(x) <= 700.0) ? fm::exp_(x) : exp(x); }
+// t32 != nullptr: the 32-entry-table exp of fastmath.cuh (11 instead of 20 FP64 instructions, <= 1 ulp)
+__device__ __forceinline__ double exp_s(double x, const double* t32)
+{
+    return (fabs(x) <= 700.0) ? (t32 ? fm::exp_t(x, t32) : fm::exp_(x)) : exp(x);
+}
 
 // one row: forward + adjoint sweep in registers, the 26 sums accumulated into acc
-__device__ __forceinline__ void mlp3_row(const double* __restrict__ p, double xa, double xb, double yy, double (&acc)[NOUT])
+template <bool TAB>
+__device__ __forceinline__ void mlp3_row(const double* __restrict__ p, const double* __restrict__ t32s, double xa, double xb, double yy,
+                                         double (&acc)[NOUT])
 {
     const double* A1 = p;        // A1(i,j) = A1[i + 3j]
     const double* b1 = p + 6;
@@ -33,18 +39,19 @@ __device__ __forceinline__ void mlp3_row(const double* __restrict__ p, double xa
     const double* b2 = p + 18;
     const double* A3 = p + 21;   // A3(0,j) = A3[j]
     const double b3 = p[24];
+    const double* t32 = TAB ? t32s : nullptr;
     // ---- forward ----
     double x1[3], e1[3], y1[3], h[3], e2[3], s2[3], y2[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         x1[i] = (A1[i] * xa + A1[i + 3] * xb) + b1[i];          // dot(A1, xi) + b1
-        e1[i] = exp_s(-x1[i]);
+        e1[i] = exp_s(-x1[i], t32);
         y1[i] = inv1p(e1[i]);                            // sigmoid = 1/(1+exp(-x)), unary.hpp:273-275
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         h[i] = ((A2[i] * y1[0] + A2[i + 3] * y1[1]) + A2[i + 6] * y1[2]) + b2[i];
-        e2[i] = exp_s(-h[i]);
+        e2[i] = exp_s(-h[i], t32);
         s2[i] = inv1p(e2[i]);
         y2[i] = s2[i] + x1[i];                                  // sigmoid(...) + x1
     }
@@ -94,10 +101,13 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
             double* grad, int overwrite, double* out_loss)
 {
     pdl_prologue();
+    constexpr bool TAB = MINB >= 2;          // large-batch variant: table exp (the copy costs the small-batch one more than it saves)
     __shared__ double p[NP];
+    __shared__ double t32[TAB ? 32 : 1];
     __shared__ double red[THREADS / 32][NOUT];
     __shared__ bool is_last;
     if (threadIdx.x < NP) p[threadIdx.x] = parm[threadIdx.x];
+    if (TAB && threadIdx.x >= 32 && threadIdx.x < 64) t32[threadIdx.x - 32] = fm::kExp2_32_d[threadIdx.x - 32];
     __syncthreads();
 
     double acc[NOUT];
@@ -117,7 +127,7 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
                 const bool more = nxt < batch;
                 double xa2 = 0.0, xb2 = 0.0, yy2 = 0.0;
                 if (more) { xa2 = __ldg(X + nxt); xb2 = __ldg(X + batch + nxt); yy2 = __ldg(y + nxt); }
-                mlp3_row(p, xa, xb, yy, acc);
+                mlp3_row<TAB>(p, t32, xa, xb, yy, acc);
                 if (!more) break;
                 row = nxt; xa = xa2; xb = xb2; yy = yy2;
             }
@@ -135,7 +145,7 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
             }
 #pragma unroll
             for (int r = 0; r < ROWS; ++r)
-                if (row0 + r * nth < batch) mlp3_row(p, xa[r], xb[r], yy[r], acc);
+                if (row0 + r * nth < batch) mlp3_row<TAB>(p, t32, xa[r], xb[r], yy[r], acc);
         }
     }
     // ---- CTA reduce of the 26 channels ----
