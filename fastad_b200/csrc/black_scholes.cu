@@ -176,17 +176,17 @@ bs_kernel_fast(size_t n, const double* __restrict__ S, const double* __restrict_
 
 // software-pipelined variant: the next option's inputs are loaded before the current one is
 // evaluated, so the ~800-cycle load latency overlaps the ~2000-cycle evaluation of the same thread
-template <bool ACC, bool PW = false, int MINB = 2>
-__global__ void __launch_bounds__(256, MINB)
+template <bool ACC, bool PW = false, int MINB = 2, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB)
 bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restrict__ K,
                   const double* __restrict__ sigma, const double* __restrict__ tau,
                   const double* __restrict__ r, BSOut out)
 {
     __shared__ double s_tab[PW ? 675 : 1];      // erfcx pieces [0, 256) + 2^(j/32) [256, 288) + log table [288, 675)
     if (PW) {            // constant memory: written before any launch, safe to read ahead of the dependency sync
-        s_tab[threadIdx.x] = fm::kErfcx32_d[threadIdx.x];
+        for (int i = threadIdx.x; i < 256; i += THREADS) s_tab[i] = fm::kErfcx32_d[i];
         if (threadIdx.x < 32) s_tab[256 + threadIdx.x] = fm::kExp2_32_d[threadIdx.x];
-        for (int i = threadIdx.x; i < 387; i += 256) s_tab[288 + i] = fm::kLogT_d[i];
+        for (int i = threadIdx.x; i < 387; i += THREADS) s_tab[288 + i] = fm::kLogT_d[i];
         __syncthreads();
     }
     pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
@@ -230,7 +230,8 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     // option, 110 registers) 22.6 (variant 21); the same at 3 CTAs/SM (78 registers, no spills) 21.4;
     // 4 CTAs/SM (64 registers, spills) 22.7 (variant 24); exp through a 32-entry 2^(j/32) table in shared
     // memory (11 instead of 20 FP64 instructions, three per option) 20.7; log through a 129-entry
-    // {1/c, log c} table (no division, 15 instead of 27) 20.5 (default).
+    // {1/c, log c} table (no division, 15 instead of 27) 20.5 (default).  4 CTAs of 224 threads at 72 registers
+    // (7.9 instead of 9.2 trips per thread at 2^20 options) measured 21.4: removed.
     // Two options per thread, tighter launch bounds (spills) and atomic
     // work-stealing were measured slower and removed.
     static int variant = -1;
