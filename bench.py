@@ -302,12 +302,16 @@ def run_ours(args):
             dval = zeros(1)
 
             def step(i, code=code):
+                # N > 1: every rank owns 2^24 elements of ONE sum; the seed is known up front, so the
+                # adjoints are shard-local and the exchange is the 1-double value (sharding.sharded_sum_autodiff)
                 F.check(L.fadb_sum_unary_async(code, n2, C.c_void_p(xs[i % 2].data_ptr()),
                                                C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0,
                                                C.c_void_p(dval.data_ptr())))
+                if world > 1:
+                    torch.distributed.all_reduce(dval)
             t = timed_loop(step, steps2, 3, world)
             nm = op if isinstance(op, str) else f"pow{op[1]}"
-            add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements")
+            add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements", sharded=world > 1)
         # prod_benchmark.cpp shape: ad::prod over a vector (prod.hpp:172-212): reduce pass (8 B/elem) + adjoint pass (24 B/elem)
         def prod_step(i):
             F.check(L.fadb_prod(n2, C.c_void_p(xp.data_ptr()), C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0, None))
@@ -445,13 +449,20 @@ def run_ours(args):
             Xn, yn = synth.mlp3_inputs(b)
             Xd, yd = torch.from_numpy(np.ascontiguousarray(Xn.T)).cuda(), dev(yn)
             import kats
-            parm, grad, dl = dev(kats.NN_PARM), zeros(25), zeros(1)
+            parm = dev(kats.NN_PARM)
+            gl = zeros(26)                      # {grad[25], loss}: one buffer so that N > 1 exchanges it in one piece
+            p_grad, p_loss = C.c_void_p(gl.data_ptr()), C.c_void_p(gl.data_ptr() + 25 * 8)
+            mflags = F.OVERWRITE_ADJ if world > 1 else 0
 
             def mlp_step(i):
-                F.check(L.fadb_mlp3_async(b, P(Xd), P(yd), P(parm), P(grad), 0, P(dl)))
+                # N > 1: rows are sharded over the ranks, the 25 gradients + the loss are sums over rows: ONE
+                # 26-double all-reduce per evaluation (sharding.sharded_mlp3_autodiff)
+                F.check(L.fadb_mlp3_async(b, P(Xd), P(yd), P(parm), p_grad, mflags, p_loss))
+                if world > 1:
+                    torch.distributed.all_reduce(gl)
             t = timed_loop(mlp_step, steps2, 3, world)
             add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples",
-                {"bound": "fp64 pipe / launch latency, not HBM"})
+                {"bound": "fp64 pipe / launch latency, not HBM"}, sharded=world > 1)
 
     if "expr" in wl:
         # the GENERIC path (ad::bind -> planner -> interpreter kernel), same C-ABI calls the C++

@@ -37,3 +37,36 @@ def sharded_linreg_autodiff(ops, all_reduce, rows_total, seed):
     part = ops.partial()
     all_reduce(part)
     return ops.finish(part, rows_total, seed)
+
+
+def sharded_sum_autodiff(ops, all_reduce):
+    """sum(f(x)) over element-range shards: the root seed is known up front, so every rank's fused pass
+    already wrote its adjoints; the only exchange is the 1-double value.
+    ops.run() -> 1-slot value buffer (adjoints of the shard updated as a side effect)."""
+    val = ops.run()
+    all_reduce(val)
+    return val
+
+
+def sharded_prod_autodiff(ops, all_gather, world):
+    """prod(x) over element-range shards (prod.hpp:172-212 semantics incl. exact zeros): every rank reduces
+    {product of its non-zeros, its number of zeros}; the pairs are all-gathered and multiplied / added in
+    rank order, then each rank scatters adj_i from the GLOBAL pair.
+    ops.reduce() -> 2-slot buffer; ops.scatter(p_nz_global, zeros_global) -> None."""
+    mine = ops.reduce()
+    pairs = all_gather(mine)            # list of `world` 2-slot buffers
+    p_nz, zeros = 1.0, 0.0
+    for r in range(world):
+        p_nz *= float(pairs[r][0])
+        zeros += float(pairs[r][1])
+    ops.scatter(p_nz, zeros)
+    return 0.0 if zeros > 0 else p_nz
+
+
+def sharded_mlp3_autodiff(ops, all_reduce):
+    """The network of example/ceres_3layer_neural_net over batch shards: rows are independent, the 25
+    parameter gradients and the loss are sums over rows: one 26-double all-reduce.
+    ops.run() -> 26-slot buffer {grad[25], loss} of the local rows."""
+    part = ops.run()
+    all_reduce(part)
+    return part

@@ -92,6 +92,51 @@ def _worker(rank, world, port, q):
         ops = LR()
         out["lr"] = sharding.sharded_linreg_autodiff(ops, ar, rows, 1.0)
         out["lr_adj"] = (ops.w_adj, ops.sigma_adj)
+        # ---- sum(exp(x)): 1-double exchange, adjoints shard-local
+        xs = synth.sum_inputs(n)
+
+        class SUM:
+            def run(self):
+                self.adj = seed * np.exp(xs[b:e])
+                return torch.tensor([np.sum(np.exp(xs[b:e]))], dtype=torch.float64)
+        ops = SUM()
+        out["sum"] = sharding.sharded_sum_autodiff(ops, ar).item()
+        out["sum_adj"] = ops.adj
+
+        # ---- prod(x) with one exact zero living in rank 1's shard: {prod of non-zeros, #zeros} all-gathered
+        xp = np.exp(np.linspace(-1e-3, 1e-3, n)); xp[n - 5] = 0.0
+
+        class PROD:
+            def reduce(self):
+                sh = xp[b:e]
+                return torch.tensor([np.prod(sh[sh != 0]), float((sh == 0).sum())], dtype=torch.float64)
+
+            def scatter(self, p_nz, zeros):
+                sh = xp[b:e]
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    self.adj = np.where(sh == 0, seed * (0.0 if zeros > 1 else p_nz), seed * ((0.0 if zeros > 0 else p_nz) / sh))
+
+        def all_gather(t):
+            outl = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(outl, t)
+            return outl
+        ops = PROD()
+        out["prod"] = sharding.sharded_prod_autodiff(ops, all_gather, world)
+        out["prod_adj"] = ops.adj
+
+        # ---- network: batch shards, one 26-double all-reduce
+        import oracle_py as O
+        import kats
+        B = 2001
+        Xn, yn = synth.mlp3_inputs(B)
+        bb, be = sharding.shard_range(B, rank, world)
+
+        class NN:
+            def run(self):
+                g = np.zeros(25)
+                loss = O.mlp3(np.asfortranarray(Xn[bb:be]), np.ascontiguousarray(yn[bb:be]), kats.NN_PARM, g) if be > bb else 0.0
+                return torch.tensor(np.concatenate([g, [loss]]), dtype=torch.float64)
+        out["nn"] = sharding.sharded_mlp3_autodiff(NN(), ar).numpy()
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -139,6 +184,32 @@ def test_sharded_reductions_two_ranks_gloo():
         assert abs(res[r]["lr"] - ov) <= 1e-12 * abs(ov)
         np.testing.assert_allclose(res[r]["lr_adj"][0], wa, rtol=1e-11, atol=1e-9 * np.abs(wa).max())
         assert abs(res[r]["lr_adj"][1] - sa1[0]) <= 1e-11 * abs(sa1[0])
+
+
+    # sum / prod / network
+    xs = synth.sum_inputs(n)
+    oa = np.zeros(n)
+    ov = O.sum_unary("exp", xs, oa, seed=0.75)
+    xp = np.exp(np.linspace(-1e-3, 1e-3, n)); xp[n - 5] = 0.0
+    # prod.hpp:172-212 through the oracle's expression interface
+    eo = O.OracleExpr()
+    xv = eo.var(xp)
+    eo.bind(eo.prod(xv))
+    pv = eo.autodiff(0.75)[0]
+    pa = eo.adj(xv)
+    import kats
+    B = 2001
+    Xn, yn = synth.mlp3_inputs(B)
+    g = np.zeros(25)
+    lv = O.mlp3(Xn, yn, kats.NN_PARM, g)
+    for r in range(2):
+        b, e, _ = res[r]["vvv_xa"]
+        assert abs(res[r]["sum"] - ov) <= 1e-12 * abs(ov)
+        np.testing.assert_allclose(res[r]["sum_adj"], oa[b:e], rtol=1e-15)
+        assert res[r]["prod"] == pv == 0.0
+        np.testing.assert_allclose(res[r]["prod_adj"], pa[b:e], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(res[r]["nn"][:25], g, rtol=1e-11, atol=1e-9 * np.abs(g).max())
+        assert abs(res[r]["nn"][25] - lv) <= 1e-12 * abs(lv)
 
 
 def test_shard_ranges_tile_and_stay_aligned():
