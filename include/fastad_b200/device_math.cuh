@@ -82,7 +82,7 @@ __device__ __forceinline__ void div2_guarded(double a1, double a2, double d, dou
 }
 FADB_UNARY(FADB_LOG, log_guarded(x), div_guarded(seed, x))
 FADB_UNARY(FADB_SQRT, sqrt(x), 0.5 * seed / f)
-FADB_UNARY(FADB_ERF, erf(x), 1.1283791670955126 * seed * exp(-x * x))
+FADB_UNARY(FADB_ERF, erf(x), 1.1283791670955126 * seed * exp_guarded(-x * x))
 FADB_UNARY(FADB_SINH, sinh(x), seed * cosh(x))
 FADB_UNARY(FADB_COSH, cosh(x), seed * sinh(x))
 FADB_UNARY(FADB_TANH, tanh(x), seed * (1 - f * f))
@@ -93,11 +93,11 @@ FADB_UNARY(FADB_SQUARE, x * x, seed * 2. * x)      // NormNode, norm.hpp:47-57
 // Sigmoid: the reference evaluates exp(-x) three times in bmap (unary.hpp:273-278); the value
 // is the same each time, so it is computed once.
 template <> struct Unary<FADB_SIGMOID> {
-    __device__ __forceinline__ static double f(double x) { return 1 / (1 + exp(-x)); }
+    __device__ __forceinline__ static double f(double x) { return div_guarded(1., 1 + exp_guarded(-x)); }
     __device__ __forceinline__ static double b(double seed, double x, double)
     {
-        const double e = exp(-x);
-        return seed * e / ((e + 1) * (e + 1));
+        const double e = exp_guarded(-x);
+        return div_guarded(seed * e, (e + 1) * (e + 1));
     }
 };
 
