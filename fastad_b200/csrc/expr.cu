@@ -92,28 +92,49 @@ __global__ void dot_bwd_kernel(int m, int k, int p, const double* __restrict__ L
 constexpr int GV_THREADS = 256;
 constexpr int GV_KT = 16;          // columns per register tile of the transposed product
 
-// V = L R: one row per thread and trip, R in shared memory, the k loads of a row are independent
+// V = L R: KS threads share a row (thread (r, g) takes columns g, g + KS, ...; for a fixed column the rows
+// of a CTA are contiguous, so every load is coalesced), partial dots meet in shared memory.  KS = 1 for very
+// tall operands (one row per thread and trip), KS = 4 when there are too few rows to fill the GPU.
+template <int KS>
 __global__ void __launch_bounds__(GV_THREADS)
 gemv_n_kernel(size_t m, int k, const double* __restrict__ L, const double* __restrict__ R, double* __restrict__ V)
 {
-    extern __shared__ double s_r[];
+    extern __shared__ double s_r[];                          // [k] (+ [KS][GV_THREADS / KS] partials when KS > 1)
     for (int q = threadIdx.x; q < k; q += blockDim.x) s_r[q] = R[q];
     __syncthreads();
-    const size_t nth = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += nth) {
+    constexpr int RPB = GV_THREADS / KS;                     // rows per CTA and trip
+    const int rl = threadIdx.x % RPB, g = threadIdx.x / RPB;
+    double* s_p = s_r + k;
+    for (size_t r0 = (size_t)blockIdx.x * RPB; r0 < m; r0 += (size_t)gridDim.x * RPB) {
+        const size_t i = r0 + rl;
         double acc = 0.0;
-        const double* row = L + i;
+        if (i < m) {
+            const double* row = L + i;
 #pragma unroll 8
-        for (int q = 0; q < k; ++q) acc += __ldg(row + (size_t)q * m) * s_r[q];     // dot.hpp:93, same order over q
-        V[i] = acc;
+            for (int q = g; q < k; q += KS) acc += __ldg(row + (size_t)q * m) * s_r[q];
+        }
+        if (KS == 1) {
+            if (i < m) V[i] = acc;                           // dot.hpp:93, same order over q
+        } else {
+            s_p[g * RPB + rl] = acc;
+            __syncthreads();
+            if (g == 0 && i < m) {
+                double v = s_p[rl];
+#pragma unroll
+                for (int t = 1; t < KS; ++t) v += s_p[t * RPB + rl];
+                V[i] = v;
+            }
+            __syncthreads();
+        }
     }
 }
 
-// Radj (+)= L^T A: every CTA owns a contiguous block of rows; GV_KT column sums at a time live in
-// registers, A is re-read per column tile (8 bytes per row against 8 GV_KT of L).  Deterministic: warp
-// tree -> shared memory -> per-CTA partial row; the last CTA to arrive adds the rows in CTA order.
+// Radj (+)= L^T A.  2D grid: blockIdx.x = block of rows, blockIdx.y = tile of GV_KT columns; a thread
+// accumulates its rows' contribution to the GV_KT column sums in registers and the CTA reduces them ONCE
+// (warp tree -> shared memory) into its partial row.  Deterministic: the last CTA to arrive adds the
+// partial rows in row-block order.  L is read exactly once, A once per column tile (L2).
 __global__ void __launch_bounds__(GV_THREADS)
-gemv_t_kernel(size_t m, int k, const double* __restrict__ L, const double* __restrict__ A, double* partials /* [grid][k] */,
+gemv_t_kernel(size_t m, int k, const double* __restrict__ L, const double* __restrict__ A, double* partials /* [gridDim.x][k] */,
               unsigned int* ticket, double* Radj, int rmode)
 {
     __shared__ double s_red[GV_THREADS / 32][GV_KT];
@@ -121,39 +142,38 @@ gemv_t_kernel(size_t m, int k, const double* __restrict__ L, const double* __res
     const size_t per = (m + gridDim.x - 1) / gridDim.x;
     const size_t r0 = (size_t)blockIdx.x * per, r1 = r0 + per < m ? r0 + per : m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q0 = 0; q0 < k; q0 += GV_KT) {
-        double acc[GV_KT];
+    const int q0 = blockIdx.y * GV_KT;
+    double acc[GV_KT];
 #pragma unroll
-        for (int t = 0; t < GV_KT; ++t) acc[t] = 0.0;
-        if (q0 + GV_KT <= k) {
-            for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
-                const double a = __ldg(A + i);
+    for (int t = 0; t < GV_KT; ++t) acc[t] = 0.0;
+    if (q0 + GV_KT <= k) {
+        for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+            const double a = __ldg(A + i);
 #pragma unroll
-                for (int t = 0; t < GV_KT; ++t) acc[t] += __ldg(L + i + (size_t)(q0 + t) * m) * a;
-            }
-        } else {
-            for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
-                const double a = __ldg(A + i);
-#pragma unroll
-                for (int t = 0; t < GV_KT; ++t)
-                    if (q0 + t < k) acc[t] += __ldg(L + i + (size_t)(q0 + t) * m) * a;
-            }
+            for (int t = 0; t < GV_KT; ++t) acc[t] += __ldg(L + i + (size_t)(q0 + t) * m) * a;
         }
+    } else {
+        for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+            const double a = __ldg(A + i);
 #pragma unroll
-        for (int t = 0; t < GV_KT; ++t) {
-            const double v = warp_sum(acc[t]);
-            if (lane == 0) s_red[warp][t] = v;
+            for (int t = 0; t < GV_KT; ++t)
+                if (q0 + t < k) acc[t] += __ldg(L + i + (size_t)(q0 + t) * m) * a;
         }
-        __syncthreads();
-        if (threadIdx.x < GV_KT && q0 + (int)threadIdx.x < k) {
-            double v = 0.0;
-            for (int w = 0; w < GV_THREADS / 32; ++w) v += s_red[w][threadIdx.x];
-            partials[(size_t)blockIdx.x * k + q0 + threadIdx.x] = v;
-        }
-        __syncthreads();
+    }
+#pragma unroll
+    for (int t = 0; t < GV_KT; ++t) {
+        const double v = warp_sum(acc[t]);
+        if (lane == 0) s_red[warp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < GV_KT && q0 + (int)threadIdx.x < k) {
+        double v = 0.0;
+        for (int w = 0; w < GV_THREADS / 32; ++w) v += s_red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * k + q0 + threadIdx.x] = v;
     }
     __threadfence();
-    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -714,7 +734,7 @@ struct fadb_expr {
             if (st.leaf_stage[ld] < 0) std::swap(ld, ly);
             if (st.leaf_stage[ld] < 0 || st.leaf_stage[ly] >= 0 || st.leaves[ly].scalar || st.leaves[ly].adj_mode != 0) return;
             Stage& ds = *plan[st.leaf_stage[ld]];
-            if (ds.type != 1 || ds.p != 1 || ds.L.stage >= 0 || ds.R.stage >= 0 || ds.L.adj_mode != 0 || ds.k > 4096) return;
+            if (ds.type != 1 || ds.p != 1 || ds.L.stage >= 0 || ds.R.stage >= 0 || ds.L.adj_mode != 0 || ds.k > 64) return;   // beyond one 64-column block the two-pass GEMV kernels are faster (measured)
             st.fast = 5;
             st.f_X = ds.L.val; st.f_w = ds.R.val; st.f_wadj = ds.R.adj_mode ? ds.R.adj : nullptr;
             st.f_rows = ds.m; st.f_cols = ds.k;
@@ -763,7 +783,7 @@ struct fadb_expr {
                 st.leaf_stage[Im.leaf] >= 0 && st.prog.size() == 3) {
                 Stage& ds = *plan[st.leaf_stage[Im.leaf]];
                 if (ds.type == 1 && ds.p == 1 && ds.L.stage < 0 && ds.R.stage < 0 && ds.L.adj_mode == 0 &&
-                    ds.k <= 4096 && plan.size() == 2) {
+                    ds.k <= 64 && plan.size() == 2) {
                     st.fast = 3;
                     st.f_X = ds.L.val; st.f_w = ds.R.val; st.f_wadj = ds.R.adj_mode ? ds.R.adj : nullptr;
                     st.f_rows = ds.m; st.f_cols = ds.k;
@@ -859,7 +879,12 @@ struct fadb_expr {
             Stage& st = *sp;
             if (st.type != 0) {
                 if (st.type == 1 && st.p <= 16 && st.m >= 4096 && st.k <= 4096) {
-                    st.gv_grid = std::min(2 * c.sms, (st.m + 255) / 256);
+                    // row blocks of >= 1024 rows (4 per thread), as many as keep ~4 CTAs per SM busy with the column tiles
+                    {
+                        const int ctiles = (st.k + GV_KT - 1) / GV_KT;
+                        const int want = std::max(1, 4 * c.sms / ctiles);
+                        st.gv_grid = std::max(1, std::min(want, (st.m + 1023) / 1024));
+                    }
                     int rc = dev_alloc((size_t)st.gv_grid * st.k * sizeof(double), (void**)&st.gv_part);
                     if (rc) return rc;
                 } else if (st.type == 1 && st.p >= 4096 && st.m * st.k <= GV_THREADS * WR_PER && st.L.adj_mode) {
@@ -1099,10 +1124,14 @@ struct fadb_expr {
         if (st.gv_part) {       // tall L, R a vector or a few columns: the HBM-bound kernels, one launch per column of R
             const size_t mp = (size_t)st.m * st.p;
             if (mode & M_F) {
-                const int grid = grid_for(c, st.m, 8, GV_THREADS);
+                const bool split = (size_t)st.m < (size_t)c.sms * 8 * GV_THREADS;      // too few rows for one thread each
                 for (int j = 0; j < st.p; ++j) {
-                    gemv_n_kernel<<<grid, GV_THREADS, st.k * sizeof(double), c.stream>>>((size_t)st.m, st.k, st.L.val, st.R.val + (size_t)j * st.k,
-                                                                                           st.mval + (size_t)j * st.m);
+                    if (split)
+                        gemv_n_kernel<4><<<grid_for(c, st.m, 8, GV_THREADS / 4), GV_THREADS, (st.k + GV_THREADS) * sizeof(double), c.stream>>>(
+                            (size_t)st.m, st.k, st.L.val, st.R.val + (size_t)j * st.k, st.mval + (size_t)j * st.m);
+                    else
+                        gemv_n_kernel<1><<<grid_for(c, st.m, 8, GV_THREADS), GV_THREADS, st.k * sizeof(double), c.stream>>>(
+                            (size_t)st.m, st.k, st.L.val, st.R.val + (size_t)j * st.k, st.mval + (size_t)j * st.m);
                     c.launches++;
                 }
             }
@@ -1114,7 +1143,7 @@ struct fadb_expr {
                 }
                 if (st.R.adj_mode)
                     for (int j = 0; j < st.p; ++j) {
-                        gemv_t_kernel<<<st.gv_grid, GV_THREADS, 0, c.stream>>>((size_t)st.m, st.k, st.L.val, A + (size_t)j * st.m, st.gv_part,
+                        gemv_t_kernel<<<dim3(st.gv_grid, (st.k + GV_KT - 1) / GV_KT), GV_THREADS, 0, c.stream>>>((size_t)st.m, st.k, st.L.val, A + (size_t)j * st.m, st.gv_part,
                                                                                 c.tickets + 12, st.R.adj + (size_t)j * st.k, st.R.adj_mode);
                         c.launches++;
                     }

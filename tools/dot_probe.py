@@ -12,7 +12,11 @@ reps = 20
 Xh, yh, _ = synth.linreg_inputs(rows, cols)
 e = F.Expr()
 X = e.const(Xh); y = e.const(yh); w = e.var(0.01 * np.arange(cols, dtype=np.float64).reshape(cols, 1))
-root = e.sum(e.pow(2, e.binary("sub", y, e.dot(X, w))))
+inner = len(sys.argv) > 3
+res = e.binary("sub", y, e.dot(X, w))
+if inner:
+    res = e.binary("mul", res, e.const(1.0 + 0 * yh))      # defeats the least-squares pattern: generic GEMV kernels
+root = e.sum(e.pow(2, res))
 e.bind(root)
 print(e.describe().split("\n")[0], [l for l in e.describe().split("\n") if l.startswith("stage")])
 step = lambda: F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
