@@ -387,6 +387,16 @@ static void gemm(Context& c, int m, int n, int k, double alpha, const double* A,
     c.launches++;
 }
 
+// C = alpha * op(A) * op(B) + beta * C for other translation units (DotNode with large matrix operands, expr.cu)
+void gemm_f64(Context& c, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+              double beta, double* C, int ldc)
+{
+    if (!ta && !tb) gemm<false, false>(c, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 0);
+    else if (ta && !tb) gemm<true, false>(c, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 0);
+    else if (!ta && tb) gemm<false, true>(c, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 0);
+    else gemm<true, true>(c, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 0);
+}
+
 // recursion tree of the triangular inversion, grouped by height (leaves = single 32-wide tiles)
 struct TrLevel { int first, count, max_n1, max_n2; };
 struct TrPlan {

@@ -54,6 +54,9 @@ extern "C" const char* fadb_jit_diagnostics(void);
 
 namespace fadb {
 
+// tiled FP64 GEMM of dense_normal.cu: C = alpha op(A) op(B) + beta C, column-major
+void gemm_f64(Context& c, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+              double beta, double* C, int ldc);
 
 // ------------------------------------------------------------------------ DotNode kernels
 // dot.hpp:89-104: V = L R; R_adj (+)= L^T A; L_adj (+)= A R^T.  Column-major, naive (one thread
@@ -1158,6 +1161,25 @@ struct fadb_expr {
                     }
                     c.launches++;
                 }
+            }
+            FADB_CUDA(cudaGetLastError());
+            return FADB_OK;
+        }
+        // matrix x matrix with every dimension large enough for 64-wide tiles: the double-buffered FP64 GEMM
+        const bool tiled = st.m >= 64 && st.p >= 64 && st.k >= 32;
+        if (tiled) {
+            if (mode & M_F) gemm_f64(c, false, false, st.m, st.p, st.k, 1.0, st.L.val, st.m, st.R.val, st.k, 0.0, st.mval, st.m);   // V = L R
+            if (mode & M_B) {
+                const double* A = seed_vec ? seed_vec : st.madj;
+                if (!seed_vec && mode == M_FB) {
+                    const size_t n = (size_t)st.m * st.p;
+                    fill_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, c.stream>>>(st.madj, n, seed);
+                    c.launches++;
+                }
+                if (st.R.adj_mode)      // R_adj (+)= L^T A   (dot.hpp:100)
+                    gemm_f64(c, true, false, st.k, st.p, st.m, 1.0, st.L.val, st.m, A, st.m, st.R.adj_mode == 2 ? 0.0 : 1.0, st.R.adj, st.k);
+                if (st.L.adj_mode)      // L_adj (+)= A R^T   (dot.hpp:101)
+                    gemm_f64(c, false, true, st.m, st.k, st.p, 1.0, A, st.m, st.R.val, st.k, st.L.adj_mode == 2 ? 0.0 : 1.0, st.L.adj, st.m);
             }
             FADB_CUDA(cudaGetLastError());
             return FADB_OK;

@@ -239,6 +239,14 @@ def dot_wide_batch(hidden, inputs, batch):
     return build
 
 
+def dot_matrix_product(m, k, p):
+    def build(e):   # matrix x matrix with both operands variable, through a map on each side (dot_unittest.cpp:128-153 shape, large)
+        A = e.var(RNG.normal(size=(m, k))); B = e.var(RNG.normal(size=(k, p)))
+        prod = e.dot(e.unary("tanh", A), B)
+        return e.sum(e.pow(2, prod)), [A, B], 0.5
+    return build
+
+
 def black_scholes_vec(n, put=False):
     def build(e):   # example/black_scholes.cpp:16-39 over vec leaves
         import synth
@@ -509,6 +517,8 @@ CASES = {
     "many_scalar_params": many_scalar_params(5003, 14),
     "long_chain_200_nodes": long_chain(4100, 40),
     "many_vector_leaves": many_vector_leaves(4097, 30),
+    "dot_matrix_product_tiled": dot_matrix_product(150, 70, 97),
+    "dot_matrix_product_small": dot_matrix_product(40, 70, 97),
     "dot_tall_3_rhs": dot_tall_multi_rhs(4500, 6, 3),
     "dot_tall_2_rhs_x_variable": dot_tall_multi_rhs(4100, 3, 2, x_var=True),
     "dot_wide_batch": dot_wide_batch(3, 2, 6000),

@@ -46,3 +46,16 @@ e0.record()
 for _ in range(reps): F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
 e1.record(); torch.cuda.synchronize()
 print("wide 3x2 * 2x2^20: ms/step %.4f" % (e0.elapsed_time(e1) / reps))
+
+# ---- matrix x matrix: 1024 x 1024 x 1024, both variable
+rng = np.random.default_rng(6)
+e = F.Expr()
+A = e.var(rng.normal(size=(1024, 1024))); Bm = e.var(rng.normal(size=(1024, 1024)))
+e.bind(e.sum(e.pow(2, e.dot(A, Bm))))
+for _ in range(3): F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+torch.cuda.synchronize()
+e0.record()
+for _ in range(reps): F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print("matmul 1024^3 fwd+bwd: ms/step %.4f  (%.1f TFLOP/s FP64 on 3 x 2 n^3 flop)" % (ms, 6 * 1024**3 / (ms * 1e-3) / 1e12))
