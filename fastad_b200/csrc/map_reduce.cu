@@ -123,7 +123,31 @@ prod_reduce_kernel(size_t n, const double* __restrict__ x, double* partials, uns
     double p = 1.0, z = 0.0;
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = tid; i < n; i += nth) {
+    // read-only stream: 256-bit loads, four in flight per thread (two independent product chains)
+    const size_t n4 = aligned32(x) ? n / 4 : 0;
+    double p2 = 1.0;
+    size_t q = tid;
+    for (; q + 3 * nth < n4; q += 4 * nth) {
+        double4_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg256_stream(x + 4 * (q + u * nth));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double w = v[u].v[k];
+                if (w == 0) z += 1.0;
+                else if (u & 1) p2 *= w;
+                else p *= w;
+            }
+    }
+    for (; q < n4; q += nth) {
+        const double4_t v = ldg256_stream(x + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (v.v[k] == 0) z += 1.0; else p *= v.v[k]; }
+    }
+    p *= p2;
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) {
         const double v = __ldg(x + i);
         if (v == 0) z += 1.0; else p *= v;
     }
@@ -169,12 +193,23 @@ prod_scatter_kernel(size_t n, const double* __restrict__ x, double* x_adj, doubl
     const double pnz = red[0], zeros = red[1], val = red[2];
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = tid; i < n; i += nth) {
-        const double v = __ldg(x + i);
-        double g;
-        // prod.hpp:194-207: zero element -> product of all the others; else seed * (prod / x_i)
-        if (v == 0) g = seed * ((zeros > 1) ? 0.0 : pnz);
-        else g = seed * (val / v);
+    // prod.hpp:194-207: zero element -> product of all the others; else seed * (prod / x_i)
+    auto adj = [&](double v) { return (v == 0) ? seed * ((zeros > 1) ? 0.0 : pnz) : seed * div_guarded(val, v); };
+    const size_t n4 = (aligned32(x) && aligned32(x_adj)) ? n / 4 : 0;
+    for (size_t q = tid; q < n4; q += nth) {
+        const double4_t v = ldg256_stream(x + 4 * q);
+        double4_t g;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g.v[k] = adj(v.v[k]);
+        if (!overwrite) {
+            const double4_t old = ld256(x_adj + 4 * q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) g.v[k] += old.v[k];
+        }
+        st256(x_adj + 4 * q, g);
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) {
+        const double g = adj(__ldg(x + i));
         x_adj[i] = overwrite ? g : x_adj[i] + g;
     }
 }
