@@ -207,6 +207,16 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     return FADB_OK;
 }
 
+// fadb_shutdown: unload every specialised module of the current process
+void jit_shutdown()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_state == 1)
+        for (auto& kv : g_cache)
+            if (kv.second.mod) g_drv.module_unload(kv.second.mod);
+    g_cache.clear();
+}
+
 int jit_launch(const JitKernel& k, unsigned grid, unsigned block, cudaStream_t st, void* args_struct)
 {
     void* params[1] = {args_struct};

@@ -3,6 +3,7 @@
 // (reverse/core/var.hpp:23-220), ExprBind's caches (bind.hpp:38-40), PtrPack
 // (util/ptr_pack.hpp:13-25).  There is deliberately no CPU fallback anywhere.
 #include "common.cuh"
+#include "jit.h"
 
 namespace fadb {
 
@@ -81,6 +82,7 @@ int fadb_init(int device)
 
 void fadb_shutdown(void)
 {
+    jit_shutdown();           // specialised stage kernels (jit.cu)
     for (int d = 0; d < kMaxDevices; ++d) {
         Context& c = g_ctx[d];
         if (!c.ready) continue;

@@ -504,6 +504,9 @@ CASES = {
     "vec_prod": vec_prod(300),
     "vec_prod_one_zero": vec_prod(300, zeros=(17,)),
     "vec_prod_two_zeros": vec_prod(300, zeros=(17, 200)),
+    "vec_prod_4099": vec_prod(4099),                               # 4 elements per thread in the specialised kernel
+    "vec_prod_4099_one_zero": vec_prod(4099, zeros=(4097,)),
+    "vec_root_vector_seed_4100": vec_root_with_vector_seed(4100),
     "vec_root_vector_seed": vec_root_with_vector_seed(2049),
     "vec_placeholder_chain": vec_placeholder_chain(1025),
     "normal_expr_mean": normal_with_expr_mean(5001),
