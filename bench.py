@@ -288,6 +288,20 @@ def run_ours(args):
         if extra:
             workloads[name].update(extra)
 
+    # The one exchange of a sharded evaluation (1-66 doubles): the peer-memory mailbox all-reduce of
+    # csrc/p2p.cu (one tiny kernel per rank over NVLink, measured 8-10 us against NCCL's 18-35 us at N=2);
+    # NCCL if the mailboxes cannot be set up (no CUDA IPC) or --collective nccl.
+    collective = "none (1 GPU)"
+    small_all_reduce = lambda t: None
+    if world > 1:
+        small_all_reduce, collective = (lambda t: torch.distributed.all_reduce(t)), "NCCL all-reduce"
+        if args.collective == "p2p":
+            try:
+                from fastad_b200 import sharding as _sh
+                _pa = _sh.PeerAllReduce(world, rank)
+                small_all_reduce, collective = _pa, "peer-memory mailbox all-reduce over NVLink (csrc/p2p.cu)"
+            except Exception as ex:        # every rank fails or succeeds together (same node, same driver)
+                collective = "NCCL all-reduce (peer-memory setup failed: %s)" % str(ex)[:80]
     wl = set() if args.quick else set(args.workloads.split(","))
     steps2 = max(5, min(args.steps, 50))
     import ctypes as C
@@ -308,7 +322,7 @@ def run_ours(args):
                                                C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0,
                                                C.c_void_p(dval.data_ptr())))
                 if world > 1:
-                    torch.distributed.all_reduce(dval)
+                    small_all_reduce(dval)
             t = timed_loop(step, steps2, 3, world)
             nm = op if isinstance(op, str) else f"pow{op[1]}"
             add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements", sharded=world > 1)
@@ -328,7 +342,7 @@ def run_ours(args):
         part = zeros(4); inval = zeros(1)
 
         from fastad_b200 import sharding
-        all_reduce = (lambda t: torch.distributed.all_reduce(t)) if world > 1 else (lambda t: None)
+        all_reduce = small_all_reduce
 
         def normal_step(shape, x_adj, mu_t, sg_t, mu_adj, sg_adj, flags=0):
             # rank-local shard of n3 elements; N > 1: one 4-double NCCL all-reduce per evaluation
@@ -426,7 +440,7 @@ def run_ours(args):
         lpart = zeros(cols + 1)
 
         from fastad_b200 import sharding
-        all_reduce = (lambda t: torch.distributed.all_reduce(t)) if world > 1 else (lambda t: None)
+        all_reduce = small_all_reduce
 
         def lin_step(i):
             Xd, yd = Xs[i % 2]
@@ -459,7 +473,7 @@ def run_ours(args):
                 # 26-double all-reduce per evaluation (sharding.sharded_mlp3_autodiff)
                 F.check(L.fadb_mlp3_async(b, P(Xd), P(yd), P(parm), p_grad, mflags, p_loss))
                 if world > 1:
-                    torch.distributed.all_reduce(gl)
+                    small_all_reduce(gl)
             t = timed_loop(mlp_step, steps2, 3, world)
             add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples",
                 {"bound": "fp64 pipe / launch latency, not HBM"}, sharded=world > 1)
@@ -591,7 +605,8 @@ def run_ours(args):
             "config": {"workload": f"black_scholes call+put price + delta/vega/rho (example/black_scholes.cpp), "
                                    f"batch 2^20 options per GPU per step",
                        "l2": f"rotating {nsets} resident buffer sets ({nsets * BS_BYTES * n >> 20} MiB) > 126 MiB L2",
-                       "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+                       "collective_of_the_sharded_workloads": collective},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": ncu_traffic("r1_ncu_full_bs.csv"),
                          "traffic_note": "ncu dram bytes inside the launch; most of the 64 B/option of stores is still in "
@@ -627,6 +642,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="headline only, small CPU sample")
     ap.add_argument("--workloads", default="sum,normal,logpdf,dense,linreg,mlp3,expr",
                     help="secondary workloads to time besides the headline (comma list)")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: exchange of the sharded reductions (peer-memory mailboxes or NCCL)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:

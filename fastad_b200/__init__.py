@@ -105,6 +105,11 @@ SIGNATURES = {
     "fadb_expr_beval": (_i, [_vp, _d, _vp]),
     "fadb_expr_autodiff": (_i, [_vp, _d, _vp, _dp]),
     "fadb_expr_value_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "fadb_p2p_create": (_i, [_i, _i, _vp]),
+    "fadb_p2p_connect": (_i, [_vp]),
+    "fadb_p2p_allreduce": (_i, [_vp, _i]),
+    "fadb_p2p_status": (_i, [C.POINTER(C.c_ulonglong)]),
+    "fadb_p2p_destroy": (_i, []),
     "fadb_jit_enable": (_i, [_i]),
     "fadb_jit_stats": (_i, [C.POINTER(C.c_ulonglong)]),
     "fadb_jit_diagnostics": (C.c_char_p, []),

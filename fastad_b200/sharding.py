@@ -70,3 +70,39 @@ def sharded_mlp3_autodiff(ops, all_reduce):
     part = ops.run()
     all_reduce(part)
     return part
+
+
+class PeerAllReduce:
+    """The small all-reduce over NVLink peer memory (csrc/p2p.cu) for the ranks of one node: mailboxes are
+    exchanged once through torch.distributed, after that `pa(t)` sums the float64 CUDA tensor `t` (<= 128
+    elements) over the ranks in place with one tiny kernel per rank on the library stream."""
+
+    def __init__(self, world, rank):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import fastad_b200 as F
+        self.F, self.L = F, F.lib()
+        h = C.create_string_buffer(64)
+        F.check(self.L.fadb_p2p_create(world, rank, h))
+        mine = torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).cuda()
+        allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        F.check(self.L.fadb_p2p_connect(C.c_char_p(blob)))
+        dist.barrier()
+
+    def __call__(self, t):
+        import ctypes as C
+        assert t.is_cuda and t.dtype.is_floating_point and t.element_size() == 8 and t.is_contiguous() and t.numel() <= 128
+        self.F.check(self.L.fadb_p2p_allreduce(C.c_void_p(t.data_ptr()), t.numel()))
+        return t
+
+    def healthy(self):
+        import ctypes as C
+        e = C.c_ulonglong(0)
+        self.F.check(self.L.fadb_p2p_status(C.byref(e)))
+        return e.value == 0
+
+    def close(self):
+        self.F.check(self.L.fadb_p2p_destroy())

@@ -300,6 +300,19 @@ int fadb_expr_beval(fadb_expr*, double seed, const double* seed_dev);
 int fadb_expr_autodiff(fadb_expr*, double seed, const double* seed_dev, double* host_value);
 int fadb_expr_value_ptr(fadb_expr*, const double** dev_value, size_t* size);
 
+/* ---- the one exchange of a sharded reduction, over NVLink peer memory (csrc/p2p.cu) ------------
+ * element-range shards exchange 1-66 partial sums per evaluation.  Every rank (one process
+ * per GPU of one node) owns a mailbox in its HBM; fadb_p2p_create returns its CUDA IPC handle, the caller
+ * all-gathers the handles with whatever it has (torch.distributed, MPI) and passes them to
+ * fadb_p2p_connect.  fadb_p2p_allreduce then sums dev_buf[0..n), n <= 128, over the ranks in place with ONE
+ * small kernel per rank: peer stores + system-scope fence + flags, a bounded wait, a rank-ordered sum (all
+ * ranks get identical bits).  Asynchronous on the library stream; no NCCL, no host synchronisation. */
+int fadb_p2p_create(int world, int rank, void* out_handle64);
+int fadb_p2p_connect(const void* all_handles /* world x 64 bytes, rank order */);
+int fadb_p2p_allreduce(double* dev_buf, int n);
+int fadb_p2p_status(unsigned long long* out_error_seq);
+int fadb_p2p_destroy(void);
+
 /* ---- bind-time kernel specialisation (csrc/jit.cu) ------------------------------------------
  * The reference's expression templates hand every expression its own fused evaluator at compile
  * time (bind.hpp / eval.hpp instantiate feval/beval per expression type).  For host code built

@@ -370,6 +370,27 @@ def test_black_scholes_full_size_put_call_parity(fb):
     assert np.max(np.abs(host(out[3]) - host(out[6]))) == 0.0   # vega identical by construction
 
 
+def test_peer_memory_allreduce_single_rank(fb):
+    # csrc/p2p.cu with a world of one (the multi-rank exchange is exercised by tools/p2p_probe.py under torchrun:
+    # bit-identical to the rank-ordered sum on 2 and 8 GPUs): mailbox, IPC handle, push / flag / wait / reduce
+    import ctypes as C
+    L = fb.lib()
+    h = C.create_string_buffer(64)
+    fb.check(L.fadb_p2p_create(1, 0, h))
+    fb.check(L.fadb_p2p_connect(C.c_char_p(h.raw)))
+    for n in (1, 26, 128):
+        x = np.random.default_rng(n).normal(size=n)
+        t = dev(x)
+        for _ in range(3):                       # sequence numbers advance, both payload buffers get used
+            fb.check(L.fadb_p2p_allreduce(fb._ptr(t), n))
+        np.testing.assert_array_equal(host(t), x)
+    err = C.c_ulonglong(7)
+    fb.check(L.fadb_p2p_status(C.byref(err)))
+    assert err.value == 0
+    assert L.fadb_p2p_allreduce(fb._ptr(t), 129) != 0          # payload limit is enforced
+    fb.check(L.fadb_p2p_destroy())
+
+
 def test_least_squares_one_pass_kernel(fb):
     # fadb_lsq: sum((y - X w)^2) and -2 X^T (y - X w) from one pass over X; odd sizes, accumulate / overwrite
     import ctypes as C
