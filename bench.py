@@ -452,9 +452,18 @@ def run_ours(args):
 
                 def finish(self, prt, rows_total, seed):
                     F.check(L.fadb_linreg_finish(rows_total, cols, P(prt), P(sg1), P(wa), P(sga1), seed, 0, None))
-            sharding.sharded_linreg_autodiff(Ops(), all_reduce, rows * world, 1.0)
+            if fused_exchange:
+                # exchange fused into the two kernels: the last CTA of the pass pushes {sum r^2, X^T r} into every
+                # rank's mailbox over NVLink, the finish kernel waits, reduces in rank order and finishes
+                F.check(L.fadb_linreg_partial_push(rows, cols, P(Xd), P(yd), P(w), P(lpart)))
+                F.check(L.fadb_linreg_finish_pull(rows * world, cols, P(sg1), P(wa), P(sga1), 1.0, 0, None))
+            else:
+                sharding.sharded_linreg_autodiff(Ops(), all_reduce, rows * world, 1.0)
+        fused_exchange = world > 1 and collective.startswith("peer-memory")
         t = timed_loop(lin_step, steps2, 3, world)
-        add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows", sharded=True)
+        add("linreg_2^20x64", 520 * rows, t, steps2, rows, "rows",
+            {"exchange": "fused into the pass and the finish kernel (fadb_linreg_partial_push / _finish_pull)"} if fused_exchange else None,
+            sharded=True)
         del Xs
 
     if "mlp3" in wl:

@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "p2p_device.cuh"
 
 namespace fadb {
 
@@ -29,7 +30,7 @@ struct LinregArgs {
 
 // partial layout per CTA: [0] = sum r^2, [1 .. cols] = (X^T r)_j
 __global__ void __launch_bounds__(LR_THREADS)
-linreg_kernel(LinregArgs a, double* cta_partials, unsigned int* ticket, double* out /* cols+1 */)
+linreg_kernel(LinregArgs a, double* cta_partials, unsigned int* ticket, double* out /* cols+1 */, P2PLink link)
 {
     extern __shared__ double sm[];
     double* w_s = sm;                                  // [cols_pad]
@@ -136,12 +137,16 @@ linreg_kernel(LinregArgs a, double* cta_partials, unsigned int* ticket, double* 
     if (!is_last) return;
     __threadfence();
     // ---- last CTA: fixed-order sum over CTAs, one thread per output slot ----
+    double mine_acc = 0.0;
     for (size_t j = threadIdx.x; j < a.cols + 1; j += LR_THREADS) {
         double acc = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(&cta_partials[(size_t)b * (a.cols + 1) + j]);
         out[j] = acc;
+        mine_acc = acc;                 // cols + 1 <= LR_THREADS whenever the exchange is fused: one slot per thread
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    // fused exchange: the reduced partials go straight to every rank's mailbox over NVLink (p2p_device.cuh)
+    if (link.world) p2p_push(link, (int)threadIdx.x, (int)a.cols + 1, mine_acc, [] { __syncthreads(); });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -201,7 +206,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 
 __global__ void __launch_bounds__(LT_THREADS)
 linreg_tma_kernel(LinregArgs a, const __grid_constant__ CUtensorMap xmap, int box_cols, double* cta_partials,
-                  unsigned int* ticket, double* out /* cols+1 */)
+                  unsigned int* ticket, double* out /* cols+1 */, P2PLink link)
 {
     pdl_prologue();
     extern __shared__ __align__(128) unsigned char lt_smem[];
@@ -310,19 +315,30 @@ linreg_tma_kernel(LinregArgs a, const __grid_constant__ CUtensorMap xmap, int bo
     consumer_bar();
     if (!is_last) return;
     __threadfence();
+    double mine_acc = 0.0;
     if ((int)threadIdx.x < cols + 1) {
         double acc = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(&cta_partials[(size_t)b * (a.cols + 1) + threadIdx.x]);
         out[threadIdx.x] = acc;
+        mine_acc = acc;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    // fused exchange: the reduced partials go straight to every rank's mailbox over NVLink (p2p_device.cuh)
+    if (link.world) p2p_push(link, (int)threadIdx.x, cols + 1, mine_acc, [] { consumer_bar(); });
 }
 
 // scalar epilogue: value + w_adj + sigma_adj from {sum r^2, X^T r} (normal.hpp:350-371, dot.hpp:96-104)
 __global__ void linreg_finish_kernel(double n_total, size_t cols, const double* partial,
                                      const double* sigma, double* w_adj, double* sigma_adj,
-                                     double seed, int overwrite, double* out_value)
+                                     double seed, int overwrite, double* out_value, P2PLink link)
 {
+    __shared__ double s_part[P2P_MAXN];
+    if (link.world) {       // fused exchange: wait for every rank's push, reduce in rank order (cols + 1 <= 128)
+        const double v = p2p_pull(link, (int)threadIdx.x, (int)cols + 1);
+        if (threadIdx.x < cols + 1) s_part[threadIdx.x] = v;
+        __syncthreads();
+        partial = s_part;
+    }
     const double s = sigma[0];
     if (!(s > 0)) {
         if (threadIdx.x == 0) out_value[0] = -INFINITY;       // normal.hpp:344
@@ -410,14 +426,20 @@ using namespace fadb;
 
 // dev_partial: cols+1 device doubles = {sum r^2, (X^T r)_0..}; all-reduce them across row
 // shards, then call fadb_linreg_finish with the global row count.
-extern "C" int fadb_linreg_partial(size_t rows, size_t cols, const double* X, const double* y,
-                                   const double* w, double* dev_partial)
+static int linreg_partial_impl(size_t rows, size_t cols, const double* X, const double* y, const double* w, double* dev_partial,
+                               bool push)
 {
     FADB_REQUIRE(cols >= 1 && cols <= 4096, "fadb_linreg: cols must be in 1..4096");
     FADB_REQUIRE(X && y && w && dev_partial, "fadb_linreg: null pointer");
     Context* c;
     int rc = current_context(&c);
     if (rc) return rc;
+    P2PLink link;
+    link.world = 0;
+    if (push) {
+        FADB_REQUIRE(cols + 1 <= (size_t)P2P_MAXN, "fadb_linreg_partial_push: the fused exchange carries at most 128 doubles (cols <= 127)");
+        if ((rc = p2p_next_link(*c, &link))) return rc;
+    }
     const size_t ntiles = (rows + LR_ROWS - 1) / LR_ROWS;
     int grid = (int)std::min<size_t>(std::max<size_t>(ntiles, 1), (size_t)c->sms * 4);
     double* ws;
@@ -442,7 +464,7 @@ extern "C" int fadb_linreg_partial(size_t rows, size_t cols, const double* X, co
         CUtensorMap xmap;
         rc = encode_xmap(&xmap, X, rows, cols);
         if (rc) return rc;
-        FADB_CUDA(launch_pdl(linreg_tma_kernel, g2, LT_THREADS, smem, c->stream, a, xmap, (int)cols, ws, c->tickets + 4, dev_partial));
+        FADB_CUDA(launch_pdl(linreg_tma_kernel, g2, LT_THREADS, smem, c->stream, a, xmap, (int)cols, ws, c->tickets + 4, dev_partial, link));
         c->launches++;
         FADB_CUDA(cudaGetLastError());
         return FADB_OK;
@@ -452,22 +474,39 @@ extern "C" int fadb_linreg_partial(size_t rows, size_t cols, const double* X, co
     if (smem > 48 * 1024)
         FADB_CUDA(cudaFuncSetAttribute(linreg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LinregArgs a{rows, cols, X, y, w};
-    linreg_kernel<<<grid, LR_THREADS, smem, c->stream>>>(a, ws, c->tickets + 4, dev_partial);
+    linreg_kernel<<<grid, LR_THREADS, smem, c->stream>>>(a, ws, c->tickets + 4, dev_partial, link);
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;
 }
 
-extern "C" int fadb_linreg_finish(size_t rows_total, size_t cols, const double* dev_partial,
-                                  const double* sigma, double* w_adj, double* sigma_adj, double seed,
-                                  unsigned flags, double* host_value)
+extern "C" int fadb_linreg_partial(size_t rows, size_t cols, const double* X, const double* y,
+                                   const double* w, double* dev_partial)
+{
+    return linreg_partial_impl(rows, cols, X, y, w, dev_partial, false);
+}
+
+// The same pass with the exchange FUSED into it: the CTA that forms {sum r^2, X^T r} stores them straight into
+// every rank's mailbox over NVLink (csrc/p2p.cu; cols <= 127).  Pair with fadb_linreg_finish_pull: no
+// collective call and no extra launch between the two kernels.
+extern "C" int fadb_linreg_partial_push(size_t rows, size_t cols, const double* X, const double* y,
+                                        const double* w, double* dev_partial)
+{
+    return linreg_partial_impl(rows, cols, X, y, w, dev_partial, true);
+}
+
+static int linreg_finish_impl(size_t rows_total, size_t cols, const double* dev_partial, const double* sigma, double* w_adj,
+                              double* sigma_adj, double seed, unsigned flags, double* host_value, bool pull)
 {
     Context* c;
     int rc = current_context(&c);
     if (rc) return rc;
+    P2PLink link;
+    link.world = 0;
+    if (pull && (rc = p2p_current_link(*c, &link))) return rc;
     double* dval = c->scalars + 2;
     linreg_finish_kernel<<<1, 128, 0, c->stream>>>((double)rows_total, cols, dev_partial, sigma, w_adj,
-                                                   sigma_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval);
+                                                   sigma_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval, link);
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     if (host_value) {
@@ -476,6 +515,22 @@ extern "C" int fadb_linreg_finish(size_t rows_total, size_t cols, const double* 
         *host_value = c->host_scalars[2];
     }
     return FADB_OK;
+}
+
+extern "C" int fadb_linreg_finish(size_t rows_total, size_t cols, const double* dev_partial,
+                                  const double* sigma, double* w_adj, double* sigma_adj, double seed,
+                                  unsigned flags, double* host_value)
+{
+    return linreg_finish_impl(rows_total, cols, dev_partial, sigma, w_adj, sigma_adj, seed, flags, host_value, false);
+}
+
+// Consumer of fadb_linreg_partial_push: waits for every rank's push, sums the mailbox slots in rank order and
+// forms the value and the adjoints, all in the one finish kernel.
+extern "C" int fadb_linreg_finish_pull(size_t rows_total, size_t cols, const double* sigma, double* w_adj, double* sigma_adj,
+                                       double seed, unsigned flags, double* host_value)
+{
+    FADB_REQUIRE(cols + 1 <= (size_t)P2P_MAXN, "fadb_linreg_finish_pull: cols <= 127");
+    return linreg_finish_impl(rows_total, cols, nullptr, sigma, w_adj, sigma_adj, seed, flags, host_value, true);
 }
 
 // Least squares sum((y - X w)^2), value + gradient from ONE pass over X: the batched form of the

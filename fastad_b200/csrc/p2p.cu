@@ -14,17 +14,9 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "p2p_device.cuh"
 
 namespace fadb {
-
-constexpr int P2P_MAXN = 128;        // doubles per exchange
-constexpr int P2P_MAXW = 16;         // ranks per node
-
-struct Mailbox {                     // lives in device memory, one per rank
-    double slot[2][P2P_MAXW][P2P_MAXN];
-    unsigned long long flag[P2P_MAXW];
-    unsigned long long error;        // set by a rank whose wait timed out
-};
 
 struct P2PState {
     int world = 0, rank = -1;
@@ -63,6 +55,27 @@ p2p_allreduce_kernel(P2PArgs a)
         for (int r = 0; r < a.world; ++r) s += *reinterpret_cast<volatile double*>(&a.local->slot[b][r][t]);
         a.buf[t] = s;
     }
+}
+
+static void fill_link(const P2PState& s, P2PLink* out)
+{
+    for (int r = 0; r < P2P_MAXW; ++r) out->peer[r] = s.peer[r];
+    out->local = s.local; out->world = s.world; out->rank = s.rank; out->seq = s.seq;
+}
+int p2p_next_link(Context& c, P2PLink* out)
+{
+    P2PState& s = g_p2p[c.device];
+    if (!s.local || !s.peer[s.world - 1]) { set_error("fastad_b200: peer-memory exchange is not connected (fadb_p2p_create / fadb_p2p_connect)"); return FADB_ERR_STATE; }
+    ++s.seq;
+    fill_link(s, out);
+    return FADB_OK;
+}
+int p2p_current_link(Context& c, P2PLink* out)
+{
+    P2PState& s = g_p2p[c.device];
+    if (!s.local || !s.peer[s.world - 1] || s.seq == 0) { set_error("fastad_b200: no pushed exchange to pull"); return FADB_ERR_STATE; }
+    fill_link(s, out);
+    return FADB_OK;
 }
 
 }  // namespace fadb

@@ -388,6 +388,27 @@ def test_peer_memory_allreduce_single_rank(fb):
     fb.check(L.fadb_p2p_status(C.byref(err)))
     assert err.value == 0
     assert L.fadb_p2p_allreduce(fb._ptr(t), 129) != 0          # payload limit is enforced
+    # the regression pass with the exchange fused in (push from the last CTA, pull in the finish kernel) must
+    # give the bits of partial + finish; TMA shape (64 columns) and the register-tile shape (7 columns)
+    for rows, cols in ((1 << 14, 64), (5002, 7)):
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=3)
+        Xd, yd, wd, sg = dev(X.reshape(-1, order="F")), dev(y), dev(w_true + 0.01), dev([1.3])
+        out = []
+        for fused in (False, True):
+            wa, sa, part = zeros(cols), zeros(1), zeros(cols + 1)
+            val = C.c_double()
+            if fused:
+                fb.check(L.fadb_linreg_partial_push(rows, cols, fb._ptr(Xd), fb._ptr(yd), fb._ptr(wd), fb._ptr(part)))
+                fb.check(L.fadb_linreg_finish_pull(rows, cols, fb._ptr(sg), fb._ptr(wa), fb._ptr(sa), 0.75, 0, C.byref(val)))
+            else:
+                fb.check(L.fadb_linreg_partial(rows, cols, fb._ptr(Xd), fb._ptr(yd), fb._ptr(wd), fb._ptr(part)))
+                fb.check(L.fadb_linreg_finish(rows, cols, fb._ptr(part), fb._ptr(sg), fb._ptr(wa), fb._ptr(sa), 0.75, 0, C.byref(val)))
+            out.append((val.value, host(wa), host(sa)))
+        assert out[0][0] == out[1][0]
+        np.testing.assert_array_equal(out[0][1], out[1][1])
+        np.testing.assert_array_equal(out[0][2], out[1][2])
+    fb.check(L.fadb_p2p_status(C.byref(err)))
+    assert err.value == 0
     fb.check(L.fadb_p2p_destroy())
 
 
