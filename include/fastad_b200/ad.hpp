@@ -216,6 +216,14 @@ template <class Derived>
 struct ExprBase : ExprTag {
     Derived& self() { return static_cast<Derived&>(*this); }
     const Derived& self() const { return static_cast<const Derived&>(*this); }
+    // The reference's manual binding protocol (e.g. unary.hpp:95-116, README.md:284-306; example/main.cpp):
+    //   auto sz = expr.bind_cache_size();  std::vector<double> v(sz(0)), a(sz(1));
+    //   expr.bind_cache({v.data(), a.data()});  autodiff(expr);
+    // Temporaries live in registers and stage boundaries in HBM buffers the library allocates itself, so the
+    // sizes are what the planner reports and the caller's host buffers are accepted but not used; the
+    // returned pack is advanced past them like the reference's.
+    util::SizePack bind_cache_size() const;
+    util::PtrPack<double> bind_cache(util::PtrPack<double> begin) const;
 };
 
 // Var<T,S> derives from ExprBase<VarView<T,S>>: anything below an ExprBase is an expression
@@ -1353,6 +1361,15 @@ inline util::SizePack bind_cache_size(const core::ExprBase<Derived>& expr)
     size_t cs[2] = {0, 0};
     detail::check(fadb_expr_plan(h, root, cs));
     return {{cs[0], cs[1]}};
+}
+
+template <class Derived>
+inline util::SizePack core::ExprBase<Derived>::bind_cache_size() const { return ad::bind_cache_size(*this); }
+template <class Derived>
+inline util::PtrPack<double> core::ExprBase<Derived>::bind_cache(util::PtrPack<double> begin) const
+{
+    const util::SizePack sz = ad::bind_cache_size(*this);
+    return {begin.val ? begin.val + sz(0) : nullptr, begin.adj ? begin.adj + sz(1) : nullptr};
 }
 
 }  // namespace ad

@@ -60,6 +60,12 @@ def test_cpp_reference_black_scholes_example_unchanged(built):
 
 
 @pytest.mark.gpu
+def test_cpp_reference_main_example_patterns(built):
+    out = _run(built, "example_main")
+    assert "example_main:" in out
+
+
+@pytest.mark.gpu
 def test_cpp_type_fused_kernels_match_c_abi_path(built):
     out = _run(built, "test_fused")
     assert "test_fused:" in out
