@@ -361,9 +361,23 @@ def run_ours(args):
                                                       P(mu_adj), P(sg_adj), seed, flags, None))
             ops = Ops()
 
+            fused = world > 1 and collective.startswith("peer-memory")
+
             def step(i):
-                sharding.sharded_normal_autodiff(ops, all_reduce, shape, n3 * world, 1.0,
-                                                 not (flags & F.TRUST_SIGMA))
+                if fused:
+                    # exchange fused into the two kernels (fadb_normal_lpdf_partial_push / _finish_pull); the sigma
+                    # validity count of the exact semantics keeps its own 1-double mailbox exchange
+                    cnt = None
+                    if (shape & 2) and not (flags & F.TRUST_SIGMA):
+                        cnt = ops.sigma_check()
+                        all_reduce(cnt)
+                    F.check(L.fadb_normal_lpdf_partial_push(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj),
+                                                            P(sg_adj), 1.0, flags, P(cnt), P(part)))
+                    F.check(L.fadb_normal_lpdf_finish_pull(shape, n3 * world, P(x), P(mu_t), P(sg_t), None,
+                                                           P(mu_adj), P(sg_adj), 1.0, flags, None))
+                else:
+                    sharding.sharded_normal_autodiff(ops, all_reduce, shape, n3 * world, 1.0,
+                                                     not (flags & F.TRUST_SIGMA))
             return step
 
         mu1, sg1, mua1, sga1 = dev([0.1]), dev([1.3]), zeros(1), zeros(1)

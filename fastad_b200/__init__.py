@@ -110,6 +110,8 @@ SIGNATURES = {
     "fadb_p2p_allreduce": (_i, [_vp, _i]),
     "fadb_p2p_status": (_i, [C.POINTER(C.c_ulonglong)]),
     "fadb_p2p_destroy": (_i, []),
+    "fadb_normal_lpdf_partial_push": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp, _vp]),
+    "fadb_normal_lpdf_finish_pull": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_linreg_partial_push": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
     "fadb_linreg_finish_pull": (_i, [_sz, _sz, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_jit_enable": (_i, [_i]),

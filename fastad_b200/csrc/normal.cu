@@ -12,6 +12,7 @@
 // written (normal.hpp:440-442,457: sigma<=0 => value -inf and NO adjoint update), which costs
 // one extra streaming read of sigma (8 B/element) unless the caller passes FADB_TRUST_SIGMA.
 #include "common.cuh"
+#include "p2p_device.cuh"
 
 namespace fadb {
 
@@ -107,7 +108,7 @@ __device__ __forceinline__ void rmw4(double* p, const double (&g)[4], int overwr
 
 template <bool MU_VEC, bool SIG_VEC>
 __global__ void __launch_bounds__(256)
-normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_partial)
+normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_partial, P2PLink link)
 {
     pdl_prologue();
     __shared__ double smem[32 * NCH];
@@ -187,6 +188,8 @@ normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_
     grid_finish<NCH>(acc, smem, partials, ticket, [&](double (&tot)[NCH]) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) out_partial[c] = tot[c];
+        // fused exchange: the partial sums go straight into every rank's mailbox over NVLink (p2p_device.cuh)
+        if (link.world) p2p_push1(link, tot, NCH);
     });
 }
 
@@ -196,8 +199,13 @@ normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_
 __global__ void normal_finish_kernel(int shape_code, double n_total, const double* partial,
                                      const double* x, const double* mu, const double* sigma,
                                      double* x_adj, double* mu_adj, double* sigma_adj, double seed,
-                                     int overwrite, double* out_value)
+                                     int overwrite, double* out_value, P2PLink link)
 {
+    double pulled[NCH];
+    if (link.world) {       // fused exchange: wait for every rank's push, reduce in rank order
+        p2p_pull1(link, pulled, NCH);
+        partial = pulled;
+    }
     const bool mu_vec = shape_code & 1, sig_vec = shape_code & 2;
     if (partial[3] != 0.0) { out_value[0] = -INFINITY; return; }   // normal.hpp:147, 440-442
     if (n_total == 1.0 && shape_code == 0) {
@@ -236,15 +244,18 @@ __global__ void normal_finish_kernel(int shape_code, double n_total, const doubl
     }
 }
 
-static int launch_partial(Context& c, int shape_code, const NormalArgs& a, double* out_partial)
+static int launch_partial(Context& c, int shape_code, const NormalArgs& a, double* out_partial, const P2PLink* lk = nullptr)
 {
+    P2PLink link;
+    link.world = 0;
+    if (lk) link = *lk;
     const int threads = 256;
     const size_t work = (a.n + 3) / 4;
     double* part = c.partials;
     unsigned int* ticket = c.tickets + 1;
 #define FADB_LAUNCH_NORMAL(MV, SV)                                                               \
     FADB_CUDA(launch_pdl(normal_kernel<MV, SV>, resident_grid(c, normal_kernel<MV, SV>, threads, 0, work, threads), \
-                         threads, 0, c.stream, a, part, ticket, out_partial))
+                         threads, 0, c.stream, a, part, ticket, out_partial, link))
     switch (shape_code & 3) {
     case 0: FADB_LAUNCH_NORMAL(false, false); break;
     case 1: FADB_LAUNCH_NORMAL(true, false); break;
@@ -300,18 +311,39 @@ extern "C" int fadb_normal_lpdf_partial(int shape_code, size_t n, const double* 
     return launch_partial(*c, shape_code, a, dev_partial4);
 }
 
-extern "C" int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_partial4,
-                                       const double* x, const double* mu, const double* sigma,
-                                       double* x_adj, double* mu_adj, double* sigma_adj,
-                                       double seed, unsigned flags, double* host_value)
+// The same fused pass with the exchange fused in: the CTA that forms the four partial sums stores them straight
+// into every rank's mailbox over NVLink (csrc/p2p.cu).  Pair with fadb_normal_lpdf_finish_pull.
+extern "C" int fadb_normal_lpdf_partial_push(int shape_code, size_t n, const double* x, const double* mu, const double* sigma,
+                                             double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                                             const double* dev_invalid_in, double* dev_partial4)
+{
+    int rc = check_normal_args(shape_code, n, x, mu, sigma);
+    if (rc) return rc;
+    FADB_REQUIRE(dev_partial4 != nullptr, "normal_lpdf_partial_push: null partial buffer");
+    Context* c;
+    rc = current_context(&c);
+    if (rc) return rc;
+    P2PLink link;
+    if ((rc = p2p_next_link(*c, &link))) return rc;
+    NormalArgs a{n, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
+                 dev_invalid_in};
+    return launch_partial(*c, shape_code, a, dev_partial4, &link);
+}
+
+static int normal_finish_impl(int shape_code, size_t n_total, const double* dev_partial4, const double* x, const double* mu,
+                              const double* sigma, double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                              double* host_value, bool pull)
 {
     Context* c;
     int rc = current_context(&c);
     if (rc) return rc;
+    P2PLink link;
+    link.world = 0;
+    if (pull && (rc = p2p_current_link(*c, &link))) return rc;
     double* dval = c->scalars + 0;
     normal_finish_kernel<<<1, 1, 0, c->stream>>>(shape_code, (double)n_total, dev_partial4, x, mu, sigma,
                                                  x_adj, mu_adj, sigma_adj, seed,
-                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval);
+                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval, link);
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     if (host_value) {
@@ -320,6 +352,23 @@ extern "C" int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const dou
         *host_value = c->host_scalars[0];
     }
     return FADB_OK;
+}
+
+extern "C" int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_partial4,
+                                       const double* x, const double* mu, const double* sigma,
+                                       double* x_adj, double* mu_adj, double* sigma_adj,
+                                       double seed, unsigned flags, double* host_value)
+{
+    return normal_finish_impl(shape_code, n_total, dev_partial4, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, flags, host_value, false);
+}
+
+// Consumer of fadb_normal_lpdf_partial_push: waits for every rank's push, sums the mailbox slots in rank order
+// and forms the value and the scalar adjoints in the one finish kernel.
+extern "C" int fadb_normal_lpdf_finish_pull(int shape_code, size_t n_total, const double* x, const double* mu, const double* sigma,
+                                            double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                                            double* host_value)
+{
+    return normal_finish_impl(shape_code, n_total, nullptr, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, flags, host_value, true);
 }
 
 extern "C" int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const double* mu,

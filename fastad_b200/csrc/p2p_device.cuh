@@ -54,6 +54,33 @@ __device__ __forceinline__ double p2p_pull(const P2PLink& l, int j, int n)
     return s;
 }
 
+// Single-thread forms for kernels whose reduced values end up in ONE thread (grid_finish epilogues, <<<1,1>>>
+// finish kernels): push n <= P2P_MAXN values / wait for all ranks and return the rank-ordered sums.
+__device__ __forceinline__ void p2p_push1(const P2PLink& l, const double* v, int n)
+{
+    const int b = (int)(l.seq & 1);
+    for (int r = 0; r < l.world; ++r)
+        for (int c = 0; c < n; ++c) l.peer[r]->slot[b][l.rank][c] = v[c];
+    __threadfence_system();
+    for (int r = 0; r < l.world; ++r) *reinterpret_cast<volatile unsigned long long*>(&l.peer[r]->flag[l.rank]) = l.seq;
+}
+__device__ __forceinline__ void p2p_pull1(const P2PLink& l, double* out, int n)
+{
+    for (int r = 0; r < l.world; ++r) {
+        volatile unsigned long long* f = &l.local->flag[r];
+        const long long t0 = clock64();
+        while (*f < l.seq)
+            if (clock64() - t0 > (1ll << 33)) { l.local->error = l.seq; break; }
+    }
+    __threadfence_system();
+    const int b = (int)(l.seq & 1);
+    for (int c = 0; c < n; ++c) {
+        double s = 0.0;
+        for (int r = 0; r < l.world; ++r) s += *reinterpret_cast<volatile double*>(&l.local->slot[b][r][c]);
+        out[c] = s;
+    }
+}
+
 // host side (p2p.cu): the link of the NEXT exchange (advances the sequence) / of the exchange just pushed
 struct Context;
 int p2p_next_link(Context& c, P2PLink* out);

@@ -312,8 +312,14 @@ int fadb_p2p_connect(const void* all_handles /* world x 64 bytes, rank order */)
 int fadb_p2p_allreduce(double* dev_buf, int n);
 int fadb_p2p_status(unsigned long long* out_error_seq);
 int fadb_p2p_destroy(void);
-/* the regression pass with the exchange fused in: the producing kernel's last CTA pushes {sum r^2, X^T r} into every
+/* the normal log-pdf and regression passes with the exchange fused in: the producing kernel's last CTA pushes {sum r^2, X^T r} into every
  * rank's mailbox, the finish kernel waits, reduces in rank order and forms value + adjoints (cols <= 127) */
+int fadb_normal_lpdf_partial_push(int shape_code, size_t n, const double* x, const double* mu, const double* sigma,
+                                  double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                                  const double* dev_invalid_in, double* dev_partial4);
+int fadb_normal_lpdf_finish_pull(int shape_code, size_t n_total, const double* x, const double* mu, const double* sigma,
+                                 double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                                 double* host_value);
 int fadb_linreg_partial_push(size_t rows, size_t cols, const double* X, const double* y, const double* w, double* dev_partial);
 int fadb_linreg_finish_pull(size_t rows_total, size_t cols, const double* sigma, double* w_adj, double* sigma_adj, double seed,
                             unsigned flags, double* host_value);

@@ -407,6 +407,28 @@ def test_peer_memory_allreduce_single_rank(fb):
         assert out[0][0] == out[1][0]
         np.testing.assert_array_equal(out[0][1], out[1][1])
         np.testing.assert_array_equal(out[0][2], out[1][2])
+    # the same for the normal log-pdf: vvv (vector adjoints in the pass) and vss (scalar adjoints in the finish kernel)
+    n = 5003
+    x, mu, sg = synth.normal_inputs(n)
+    for shape, m, s_ in ((3, mu, sg), (0, np.array([0.1]), np.array([1.3]))):
+        out = []
+        for fused in (False, True):
+            xd, md, sd = dev(x), dev(m), dev(s_)
+            xa, ma, sa, part = zeros(n), zeros(len(m)), zeros(len(s_)), zeros(4)
+            val = C.c_double()
+            args = (shape, n, fb._ptr(xd), fb._ptr(md), fb._ptr(sd), fb._ptr(xa), fb._ptr(ma), fb._ptr(sa), 0.75, fb.TRUST_SIGMA, None, fb._ptr(part))
+            if fused:
+                fb.check(L.fadb_normal_lpdf_partial_push(*args))
+                fb.check(L.fadb_normal_lpdf_finish_pull(shape, n, fb._ptr(xd), fb._ptr(md), fb._ptr(sd), None, fb._ptr(ma), fb._ptr(sa), 0.75,
+                                                        fb.TRUST_SIGMA, C.byref(val)))
+            else:
+                fb.check(L.fadb_normal_lpdf_partial(*args))
+                fb.check(L.fadb_normal_lpdf_finish(shape, n, fb._ptr(part), fb._ptr(xd), fb._ptr(md), fb._ptr(sd), None, fb._ptr(ma), fb._ptr(sa),
+                                                   0.75, fb.TRUST_SIGMA, C.byref(val)))
+            out.append((val.value, host(xa), host(ma), host(sa)))
+        assert out[0][0] == out[1][0]
+        for a, b in zip(out[0][1:], out[1][1:]):
+            np.testing.assert_array_equal(a, b)
     fb.check(L.fadb_p2p_status(C.byref(err)))
     assert err.value == 0
     fb.check(L.fadb_p2p_destroy())
