@@ -567,13 +567,25 @@ struct fadb_expr {
             ENode& r = nodes[n.ch[1]];
             if (l.cols != r.rows) { err = "dot: inner dimensions differ"; return -1; }
             st->type = 1;
+            // rows of a tall L are indexed with size_t; every other extent and every small-operand product is an int
+            constexpr size_t IMAX = 0x7fffffffu;
+            if (l.rows > IMAX || l.cols > IMAX || r.cols > IMAX || l.cols * r.cols > IMAX) {
+                err = "dot: an extent (or the right operand) exceeds 2^31 - 1";
+                return -1;
+            }
             st->m = (int)l.rows; st->k = (int)l.cols; st->p = (int)r.cols;
             st->out_size = n.size();
             st->L = operand(n.ch[0]); if (!err.empty()) return -1;
             st->R = operand(n.ch[1]); if (!err.empty()) return -1;
+            const bool tall = r.cols <= 16 && l.rows >= 4096 && l.cols <= 4096;      // the size_t-indexed GEMV kernels
+            if ((l.rows * l.cols > IMAX || l.rows * r.cols > IMAX) && !(tall && (r.cols == 1 || !st->L.adj_mode))) {
+                err = "dot: operand exceeds 2^31 - 1 elements and is not a tall matrix times a vector";
+                return -1;
+            }
         } else if (n.kind == N_TRANSPOSE) {
             ENode& x = nodes[n.ch[0]];
             st->type = 2;
+            if (x.rows * x.cols > 0x7fffffffu) { err = "transpose: operand exceeds 2^31 - 1 elements"; return -1; }
             st->m = (int)x.rows; st->k = (int)x.cols; st->p = 0;
             st->out_size = n.size();
             st->L = operand(n.ch[0]); if (!err.empty()) return -1;

@@ -121,6 +121,30 @@ def test_builder_rejects_bad_shapes(F):
         e.unary("exp", 12345)
 
 
+def test_planner_rejects_int_indexed_operands_beyond_2_31(F):
+    """The matrix x matrix and transpose kernels index with int; only a tall matrix times a vector (size_t rows)
+    may exceed 2^31 - 1 elements.  Planning is host-only: the pointers are never dereferenced here."""
+    import ctypes as C
+    fake = C.c_void_p(0x1000)
+
+    def mat(e, shape, rows, cols, variable=True):
+        if variable:
+            return e._id(e.L.fadb_expr_var(e.h, shape, rows, cols, fake, fake))
+        return e._id(e.L.fadb_expr_const_view(e.h, shape, rows, cols, fake))
+
+    e = F.Expr(device=False)                    # 2^26 x 64 (32 GiB) constant X times a vector: allowed
+    X, w = mat(e, F.MAT, 1 << 26, 64, variable=False), mat(e, F.VEC, 64, 1)
+    e.plan(e.sum(e.dot(X, w)))
+    e = F.Expr(device=False)                    # the same X as a VARIABLE times 2 columns: int-indexed adjoint
+    X, W = mat(e, F.MAT, 1 << 26, 64), mat(e, F.MAT, 64, 2)
+    with pytest.raises(F.FadbError, match="2\\^31"):
+        e.plan(e.sum(e.dot(X, W)))
+    e = F.Expr(device=False)
+    X = mat(e, F.MAT, 1 << 26, 64)
+    with pytest.raises(F.FadbError, match="2\\^31"):
+        e.plan(e.sum(e.transpose(X)))
+
+
 # ---------------------------------------------------------------- bind-time specialisation (csrc/jit.cu)
 @pytest.mark.parametrize("name", ["vec_sum_chain_100k", "black_scholes_call", "placeholders", "normal_vec_sigma_expr"])
 def test_stage_program_specialises_to_register_code(F, name):
