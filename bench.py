@@ -315,17 +315,22 @@ def run_ours(args):
             code = F._op_code(op)
             dval = zeros(1)
 
+            fused_sum = world > 1 and collective.startswith("peer-memory")
+
             def step(i, code=code):
                 # N > 1: every rank owns 2^24 elements of ONE sum; the seed is known up front, so the
-                # adjoints are shard-local and the exchange is the 1-double value (sharding.sharded_sum_autodiff)
-                F.check(L.fadb_sum_unary_async(code, n2, C.c_void_p(xs[i % 2].data_ptr()),
-                                               C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0,
-                                               C.c_void_p(dval.data_ptr())))
-                if world > 1:
+                # adjoints are shard-local and the exchange is the 1-double value (sharding.sharded_sum_autodiff);
+                # with the mailboxes connected the all-reduce is fused into the pass (the last CTA pushes, waits, sums)
+                call = L.fadb_sum_unary_allreduce_async if fused_sum else L.fadb_sum_unary_async
+                F.check(call(code, n2, C.c_void_p(xs[i % 2].data_ptr()), C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0,
+                             C.c_void_p(dval.data_ptr())))
+                if world > 1 and not fused_sum:
                     small_all_reduce(dval)
             t = timed_loop(step, steps2, 3, world)
             nm = op if isinstance(op, str) else f"pow{op[1]}"
-            add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements", sharded=world > 1)
+            add(f"sum_{nm}_2^24", 24 * n2, t, steps2, n2, "elements",
+                {"exchange": "all-reduce fused into the pass (fadb_sum_unary_allreduce_async)"} if fused_sum else None,
+                sharded=world > 1)
         # prod_benchmark.cpp shape: ad::prod over a vector (prod.hpp:172-212): reduce pass (8 B/elem) + adjoint pass (24 B/elem)
         def prod_step(i):
             F.check(L.fadb_prod(n2, C.c_void_p(xp.data_ptr()), C.c_void_p(adjs[i % 2].data_ptr()), 1.0, 0, None))
@@ -491,15 +496,21 @@ def run_ours(args):
             p_grad, p_loss = C.c_void_p(gl.data_ptr()), C.c_void_p(gl.data_ptr() + 25 * 8)
             mflags = F.OVERWRITE_ADJ if world > 1 else 0
 
+            fused_mlp = world > 1 and collective.startswith("peer-memory")
+
             def mlp_step(i):
                 # N > 1: rows are sharded over the ranks, the 25 gradients + the loss are sums over rows: ONE
-                # 26-double all-reduce per evaluation (sharding.sharded_mlp3_autodiff)
-                F.check(L.fadb_mlp3_async(b, P(Xd), P(yd), P(parm), p_grad, mflags, p_loss))
-                if world > 1:
+                # 26-double all-reduce per evaluation (sharding.sharded_mlp3_autodiff), fused into the kernel's
+                # last CTA when the mailboxes are connected (fadb_mlp3_allreduce_async: one launch per evaluation)
+                call = L.fadb_mlp3_allreduce_async if fused_mlp else L.fadb_mlp3_async
+                F.check(call(b, P(Xd), P(yd), P(parm), p_grad, mflags, p_loss))
+                if world > 1 and not fused_mlp:
                     small_all_reduce(gl)
             t = timed_loop(mlp_step, steps2, 3, world)
-            add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples",
-                {"bound": "fp64 pipe / launch latency, not HBM"}, sharded=world > 1)
+            extra = {"bound": "fp64 pipe / launch latency, not HBM"}
+            if fused_mlp:
+                extra["exchange"] = "all-reduce fused into the kernel (fadb_mlp3_allreduce_async)"
+            add(f"mlp3_batch_{b}", 24 * b, t, steps2, b, "samples", extra, sharded=world > 1)
 
     if "expr" in wl:
         # the GENERIC path (ad::bind -> planner -> interpreter kernel), same C-ABI calls the C++

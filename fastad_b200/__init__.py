@@ -114,6 +114,8 @@ SIGNATURES = {
     "fadb_normal_lpdf_finish_pull": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_linreg_partial_push": (_i, [_sz, _sz, _vp, _vp, _vp, _vp]),
     "fadb_linreg_finish_pull": (_i, [_sz, _sz, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_sum_unary_allreduce_async": (_i, [_i, _sz, _vp, _vp, _d, _u, _vp]),
+    "fadb_mlp3_allreduce_async": (_i, [_sz, _vp, _vp, _vp, _vp, _u, _vp]),
     "fadb_jit_enable": (_i, [_i]),
     "fadb_jit_stats": (_i, [C.POINTER(C.c_ulonglong)]),
     "fadb_jit_diagnostics": (C.c_char_p, []),

@@ -18,6 +18,10 @@ namespace fadb {
 // No C++ exception crosses the ABI.
 // ---------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
+// Modules that keep lazily allocated per-device workspaces register a release function; fadb_shutdown calls each
+// with every initialised device (current device already set, library stream already synchronised).
+void on_shutdown(void (*release)(int device));
+struct ShutdownHook { explicit ShutdownHook(void (*release)(int device)) { on_shutdown(release); } };
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define FADB_CUDA(expr)                                                             \

@@ -721,6 +721,20 @@ static WishartWs g_wws[kMaxDevices];
 struct GjWs { int *perm = nullptr, *idx = nullptr; double* val = nullptr; size_t cap = 0; };
 static GjWs g_gj[kMaxDevices];
 
+static ShutdownHook g_dense_release([](int d) {
+    DenseWs& w = g_dws[d];
+    for (double* p : {w.L, w.Y, w.X, w.d, w.z, w.scal, w.diag}) cudaFree(p);
+    w = DenseWs();
+    cudaFree(g_trplan[d].dev);
+    g_trplan[d] = TrPlan();
+    WishartWs& ws = g_wws[d];
+    for (double* p : {ws.Vinv, ws.Xinv, ws.G1, ws.G2, ws.s}) cudaFree(p);
+    ws = WishartWs();
+    GjWs& g = g_gj[d];
+    cudaFree(g.perm); cudaFree(g.idx); cudaFree(g.val);
+    g = GjWs();
+});
+
 static int ensure_gj(Context& c, size_t n, GjWs** out)
 {
     GjWs& g = g_gj[c.device];

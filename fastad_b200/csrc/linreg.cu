@@ -408,6 +408,7 @@ static int encode_xmap(CUtensorMap* map, const double* X, size_t rows, size_t co
 
 static double* g_ws[kMaxDevices] = {nullptr};
 static size_t g_ws_cap[kMaxDevices] = {0};
+static ShutdownHook g_ws_release([](int d) { cudaFree(g_ws[d]); g_ws[d] = nullptr; g_ws_cap[d] = 0; });
 
 static int ensure_ws(Context& c, size_t doubles, double** out)
 {

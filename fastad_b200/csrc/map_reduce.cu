@@ -8,15 +8,21 @@
 // K3 replaces autodiff of ad::prod(x): ProdElemNode::feval/beval (prod.hpp:172-212).  The
 // reference recomputes an O(N) product for every exact zero; here pass 1 reduces
 // (product of non-zeros, #zeros) and pass 2 scatters adj_i from those two numbers.
+#include <type_traits>
+
 #include "common.cuh"
 #include "functors.cuh"
+#include "p2p_device.cuh"
 
 namespace fadb {
 
-template <class F>
+// Link = P2PLink: element-range shard of ONE sum over the ranks of a node.  The adjoints are shard-local
+// (the seed is known up front); the last CTA pushes its 1-double partial value into every rank's mailbox over NVLink,
+// waits for the other ranks and writes the rank-ordered total: pass + all-reduce in one launch.
+template <class F, class Link = NoLink>
 __global__ void __launch_bounds__(256)
 sum_map_kernel(size_t n, const double* __restrict__ x, double* x_adj, double seed, int overwrite,
-               F fun, double* partials, unsigned int* ticket, double* out_value)
+               F fun, double* partials, unsigned int* ticket, double* out_value, Link link)
 {
     // functors that look values up per thread (the table log) get the table staged in shared memory
     __shared__ double s_tab[F::kTableDoubles ? F::kTableDoubles : 1];
@@ -60,7 +66,13 @@ sum_map_kernel(size_t n, const double* __restrict__ x, double* x_adj, double see
         }
     }
     block_sum<1>(acc, smem);
-    grid_finish<1>(acc, smem, partials, ticket, [&](double (&tot)[1]) { out_value[0] = tot[0]; });
+    grid_finish<1>(acc, smem, partials, ticket, [&](double (&tot)[1]) {
+        if constexpr (std::is_same<Link, P2PLink>::value) {
+            p2p_push1(link, tot, 1);
+            p2p_pull1(link, tot, 1);
+        }
+        out_value[0] = tot[0];
+    });
 }
 
 template <int OP>
@@ -102,12 +114,21 @@ struct Pow2Fun {   // pow<2>: f = x*x, adj = 2*seed*(x==0 ? 0 : f/x)   (pow.hpp:
 
 template <class F>
 static int launch_sum_map(Context& c, size_t n, const double* x, double* x_adj, double seed,
-                          unsigned flags, F fun, double* dval)
+                          unsigned flags, F fun, double* dval, bool exchange = false)
 {
     const int threads = 256;
-    const int grid = resident_grid(c, sum_map_kernel<F>, threads, 0, (n + 3) / 4, threads);
-    FADB_CUDA(launch_pdl(sum_map_kernel<F>, grid, threads, 0, c.stream, n, x, x_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
-                         fun, c.partials, c.tickets + 2, dval));
+    if (exchange) {
+        P2PLink link;
+        int rc = p2p_next_link(c, &link);
+        if (rc) return rc;
+        const int grid = resident_grid(c, sum_map_kernel<F, P2PLink>, threads, 0, (n + 3) / 4, threads);
+        FADB_CUDA(launch_pdl(sum_map_kernel<F, P2PLink>, grid, threads, 0, c.stream, n, x, x_adj, seed,
+                             (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, fun, c.partials, c.tickets + 2, dval, link));
+    } else {
+        const int grid = resident_grid(c, sum_map_kernel<F, NoLink>, threads, 0, (n + 3) / 4, threads);
+        FADB_CUDA(launch_pdl(sum_map_kernel<F, NoLink>, grid, threads, 0, c.stream, n, x, x_adj, seed,
+                             (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, fun, c.partials, c.tickets + 2, dval, NoLink{}));
+    }
     c.launches++;
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;
@@ -227,8 +248,8 @@ static int read_back(Context& c, const double* dval, double* host_value)
     return FADB_OK;
 }
 
-extern "C" int fadb_sum_unary_async(int op, size_t n, const double* x, double* x_adj, double seed,
-                                    unsigned flags, double* dev_value)
+static int sum_unary_launch(int op, size_t n, const double* x, double* x_adj, double seed, unsigned flags, double* dev_value,
+                            bool exchange)
 {
     FADB_REQUIRE(n == 0 || x, "fadb_sum_unary: null x");
     FADB_REQUIRE(dev_value != nullptr, "fadb_sum_unary: null value slot");
@@ -237,12 +258,12 @@ extern "C" int fadb_sum_unary_async(int op, size_t n, const double* x, double* x
     if (rc) return rc;
     if (op >= 1000 - 64 && op <= 1000 + 64) {
         const long pw = op - 1000;
-        if (pw == 2) return launch_sum_map(*c, n, x, x_adj, seed, flags, Pow2Fun{}, dev_value);
-        return launch_sum_map(*c, n, x, x_adj, seed, flags, PowFun{nullptr, pw}, dev_value);
+        if (pw == 2) return launch_sum_map(*c, n, x, x_adj, seed, flags, Pow2Fun{}, dev_value, exchange);
+        return launch_sum_map(*c, n, x, x_adj, seed, flags, PowFun{nullptr, pw}, dev_value, exchange);
     }
-    if (op == FADB_LOG) return launch_sum_map(*c, n, x, x_adj, seed, flags, LogTFun{}, dev_value);
+    if (op == FADB_LOG) return launch_sum_map(*c, n, x, x_adj, seed, flags, LogTFun{}, dev_value, exchange);
     switch (op) {
-#define C(OP) case OP: return launch_sum_map(*c, n, x, x_adj, seed, flags, UnaryFun<OP>{}, dev_value);
+#define C(OP) case OP: return launch_sum_map(*c, n, x, x_adj, seed, flags, UnaryFun<OP>{}, dev_value, exchange);
         C(FADB_NEG) C(FADB_SIN) C(FADB_COS) C(FADB_TAN) C(FADB_ASIN) C(FADB_ACOS) C(FADB_ATAN)
         C(FADB_EXP) C(FADB_LOG) C(FADB_SQRT) C(FADB_ERF) C(FADB_SIGMOID) C(FADB_SINH) C(FADB_COSH)
         C(FADB_TANH) C(FADB_MOCK2X) C(FADB_SQUARE)
@@ -250,6 +271,20 @@ extern "C" int fadb_sum_unary_async(int op, size_t n, const double* x, double* x
     }
     set_error("fadb_sum_unary: unknown op code " + std::to_string(op));
     return FADB_ERR_ARG;
+}
+
+extern "C" int fadb_sum_unary_async(int op, size_t n, const double* x, double* x_adj, double seed,
+                                    unsigned flags, double* dev_value)
+{
+    return sum_unary_launch(op, n, x, x_adj, seed, flags, dev_value, false);
+}
+
+// The shard's pass with the all-reduce of the value fused in (csrc/p2p.cu must be connected): dev_value receives
+// the sum over ALL ranks' elements, identical bits on every rank; one launch, no collective call.
+extern "C" int fadb_sum_unary_allreduce_async(int op, size_t n, const double* x, double* x_adj, double seed,
+                                              unsigned flags, double* dev_value)
+{
+    return sum_unary_launch(op, n, x, x_adj, seed, flags, dev_value, true);
 }
 
 extern "C" int fadb_sum_unary(int op, size_t n, const double* x, double* x_adj, double seed,

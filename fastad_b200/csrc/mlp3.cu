@@ -10,8 +10,10 @@
 // reduced across the CTA with warp shuffles and across CTAs by the last-arriving CTA.
 // The matrices are 3x2, 3x3 and 1x3: far below a DMMA tile, so the FP64 tensor path is not used.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
+#include "p2p_device.cuh"
 #include "../../include/fastad_b200/fastmath.cuh"
 
 namespace fadb {
@@ -94,11 +96,13 @@ __device__ __forceinline__ void mlp3_row(const double* __restrict__ p, const dou
 }
 
 // ROWS rows per thread and trip (independent dependency chains for the FP64 pipe), MINB resident CTAs
-template <int ROWS, int MINB, int THREADS = 256>
+// Link = P2PLink: batch shard of ONE evaluation over the ranks of a node; the last CTA pushes its 26 sums into every
+// rank's mailbox over NVLink, waits for the other ranks and writes the rank-ordered totals (pass + all-reduce in one launch).
+template <int ROWS, int MINB, int THREADS = 256, class Link = NoLink>
 __global__ void __launch_bounds__(THREADS, MINB)
 mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict__ y,
             const double* __restrict__ parm, double* cta_partials, unsigned int* ticket,
-            double* grad, int overwrite, double* out_loss)
+            double* grad, int overwrite, double* out_loss, Link link)
 {
     pdl_prologue();
     constexpr bool TAB = MINB >= 2;          // large-batch variant: table exp (the copy costs the small-batch one more than it saves)
@@ -170,9 +174,14 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
     // last CTA: warp w sums CTAs w, w+8, ... (lane = channel), then the 8 warp sums in a fixed order
     // (a wider final pass -- 8 warps x 26 lanes over the CTA partials, then a shared-memory step -- measured
     // 1.7-2.8 us SLOWER than these 26 independent load streams at 148-296 CTAs)
-    if (threadIdx.x < NOUT) {
-        double v = 0.0;
+    double v = 0.0;
+    if (threadIdx.x < NOUT)
         for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&cta_partials[(size_t)b * NOUT + threadIdx.x]);
+    if constexpr (std::is_same<Link, P2PLink>::value) {
+        p2p_push(link, (int)threadIdx.x, NOUT, v, [] { __syncthreads(); });
+        v = p2p_pull(link, (int)threadIdx.x, NOUT);
+    }
+    if (threadIdx.x < NOUT) {
         if (threadIdx.x == NP) out_loss[0] = v;
         else if (grad) grad[threadIdx.x] = overwrite ? v : grad[threadIdx.x] + v;
     }
@@ -180,13 +189,31 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
 }
 
 static double* g_mlp_ws[kMaxDevices] = {nullptr};
+static ShutdownHook g_mlp_ws_release([](int d) { cudaFree(g_mlp_ws[d]); g_mlp_ws[d] = nullptr; });
 
 }  // namespace fadb
 
 using namespace fadb;
 
+static int mlp3_launch(size_t batch, const double* X, const double* y, const double* parm, double* grad, unsigned flags,
+                       double* dev_loss, bool exchange);
+
 extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, const double* parm,
                                double* grad, unsigned flags, double* dev_loss)
+{
+    return mlp3_launch(batch, X, y, parm, grad, flags, dev_loss, false);
+}
+
+// This rank's rows with the 26-double all-reduce fused in (csrc/p2p.cu must be connected): grad / dev_loss receive the
+// sums over ALL ranks' rows, identical bits on every rank; one launch, no collective call.
+extern "C" int fadb_mlp3_allreduce_async(size_t batch, const double* X, const double* y, const double* parm,
+                                         double* grad, unsigned flags, double* dev_loss)
+{
+    return mlp3_launch(batch, X, y, parm, grad, flags, dev_loss, true);
+}
+
+static int mlp3_launch(size_t batch, const double* X, const double* y, const double* parm, double* grad, unsigned flags,
+                       double* dev_loss, bool exchange)
 {
     FADB_REQUIRE(batch == 0 || (X && y), "fadb_mlp3: null data");
     FADB_REQUIRE(parm && dev_loss, "fadb_mlp3: null parameter / loss pointer");
@@ -195,11 +222,32 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     if (rc) return rc;
     if (!g_mlp_ws[c->device]) FADB_CUDA(cudaMalloc(&g_mlp_ws[c->device], sizeof(double) * kMaxGrid * NOUT));
     const int threads = 256;
+    if (exchange) {
+        // same variant choice as below, by batch size
+        P2PLink link;
+        if ((rc = p2p_next_link(*c, &link))) return rc;
+        const int ow = (flags & FADB_OVERWRITE_ADJ) ? 1 : 0;
+        if (batch > (size_t)4 * c->sms * threads) {
+            auto K = mlp3_kernel<1, 2, 256, P2PLink>;
+            FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm,
+                                 g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link));
+        } else if (batch > (size_t)c->sms * 256 && batch <= (size_t)c->sms * 512) {
+            FADB_CUDA(launch_pdl(mlp3_kernel<1, 1, 512, P2PLink>, (int)std::min<size_t>((batch + 511) / 512, (size_t)c->sms), 512, 0,
+                                 c->stream, batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link));
+        } else {
+            auto K = mlp3_kernel<1, 1, 256, P2PLink>;
+            FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm,
+                                 g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link));
+        }
+        c->launches++;
+        FADB_CUDA(cudaGetLastError());
+        return FADB_OK;
+    }
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("FADB_MLP_VARIANT"); variant = e ? atoi(e) : -2; }
 #define FADB_MLP_LAUNCH(K)                                                                                     \
     FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm, \
-                         g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss))
+                         g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}))
     // measured on B200, batch 2^22: <1,1> 166 us (153 registers, 8 warps/SM: FP64 pipe 37 % active, stalls are
     // dependent-issue waits), <2,1> 155, <3,1> 159, <2,2> 121, <1,2> 115 (128 registers, 16 warps/SM): default;
     // <1,3> 152 and <1,4> 199 (80 / 64 registers: 430-530 bytes of spills per row)
@@ -214,7 +262,7 @@ extern "C" int fadb_mlp3_async(size_t batch, const double* X, const double* y, c
     else if (variant == 7 || (variant == -2 && batch > (size_t)c->sms * 256 && batch <= (size_t)c->sms * 512)) {
         // one row per thread in ONE trip with no more CTAs (= partial rows and tickets) than SMs: 512-thread CTAs
         FADB_CUDA(launch_pdl(mlp3_kernel<1, 1, 512>, (int)std::min<size_t>((batch + 511) / 512, (size_t)c->sms), 512, 0, c->stream, batch, X, y,
-                             parm, g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss));
+                             parm, g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}));
     }
     else FADB_MLP_LAUNCH((mlp3_kernel<1, 1>));
 #undef FADB_MLP_LAUNCH

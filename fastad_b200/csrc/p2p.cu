@@ -26,6 +26,14 @@ struct P2PState {
     cudaIpcMemHandle_t handle;
 };
 static P2PState g_p2p[kMaxDevices];
+static ShutdownHook g_p2p_release([](int d) {
+    P2PState& s = g_p2p[d];
+    if (!s.local) return;
+    for (int r = 0; r < s.world; ++r)
+        if (r != s.rank && s.peer[r]) cudaIpcCloseMemHandle(s.peer[r]);
+    cudaFree(s.local);
+    s = P2PState();
+});
 
 struct P2PArgs { Mailbox* peer[P2P_MAXW]; Mailbox* local; int world, rank, n; unsigned long long seq; double* buf; };
 
@@ -41,6 +49,7 @@ p2p_allreduce_kernel(P2PArgs a)
     __threadfence_system();
     __syncthreads();
     if (t < a.world) {
+        __threadfence_system();      // release by the flag's writer (cumulative over the stores ordered before the barrier)
         *reinterpret_cast<volatile unsigned long long*>(&a.peer[t]->flag[a.rank]) = a.seq;
         volatile unsigned long long* f = &a.local->flag[t];
         const long long t0 = clock64();

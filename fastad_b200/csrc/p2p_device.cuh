@@ -13,6 +13,9 @@ struct Mailbox {                     // lives in device memory, one per rank
     unsigned long long error;        // set by a rank whose wait timed out
 };
 
+// stands in for P2PLink in the single-GPU instantiation of a kernel template (no parameter bytes, no code)
+struct NoLink {};
+
 // by-value kernel argument; world == 0: no exchange
 struct P2PLink {
     Mailbox* peer[P2P_MAXW];
@@ -31,7 +34,10 @@ __device__ __forceinline__ void p2p_push(const P2PLink& l, int j, int n, double 
         for (int r = 0; r < l.world; ++r) l.peer[r]->slot[b][l.rank][j] = v;
     __threadfence_system();
     bar();
-    if (j < l.world) *reinterpret_cast<volatile unsigned long long*>(&l.peer[j]->flag[l.rank]) = l.seq;
+    if (j < l.world) {
+        __threadfence_system();      // release by the flag's writer: cumulative over the payload stores ordered before bar()
+        *reinterpret_cast<volatile unsigned long long*>(&l.peer[j]->flag[l.rank]) = l.seq;
+    }
 }
 
 // Called by all threads of a CTA (blockDim >= world): waits for every rank's flag, then thread j < n returns

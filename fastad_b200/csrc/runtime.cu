@@ -10,6 +10,14 @@ namespace fadb {
 static thread_local std::string g_last_error;
 static Context g_ctx[kMaxDevices];
 
+typedef void (*ReleaseFn)(int);
+static ReleaseFn* shutdown_hooks() { static ReleaseFn hooks[16]; return hooks; }
+static int& shutdown_hook_count() { static int n = 0; return n; }
+void on_shutdown(void (*release)(int device))
+{
+    if (shutdown_hook_count() < 16) shutdown_hooks()[shutdown_hook_count()++] = release;
+}
+
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
@@ -88,6 +96,7 @@ void fadb_shutdown(void)
         if (!c.ready) continue;
         cudaSetDevice(d);
         cudaStreamSynchronize(c.stream);
+        for (int h = 0; h < shutdown_hook_count(); ++h) shutdown_hooks()[h](d);     // the kernels' own workspaces
         if (c.own_stream) cudaStreamDestroy(c.stream);
         cudaFree(c.partials);
         cudaFree(c.tickets);

@@ -323,6 +323,13 @@ int fadb_normal_lpdf_finish_pull(int shape_code, size_t n_total, const double* x
 int fadb_linreg_partial_push(size_t rows, size_t cols, const double* X, const double* y, const double* w, double* dev_partial);
 int fadb_linreg_finish_pull(size_t rows_total, size_t cols, const double* sigma, double* w_adj, double* sigma_adj, double seed,
                             unsigned flags, double* host_value);
+/* sum(f(x)) (sum.hpp:156-173) and the network (example/ceres_3layer_neural_net/src.cpp:48-55) over a shard with the WHOLE all-reduce
+ * fused into the one launch: the last CTA pushes its 1 / 26 sums into every rank's mailbox, waits for the other ranks and writes the
+ * rank-ordered totals (dev_value; grad[25] and dev_loss) - same arguments as fadb_sum_unary_async / fadb_mlp3_async, identical bits on
+ * every rank, and with one rank the bits of the plain calls.  Vector adjoints stay shard-local (the seed is known up front). */
+int fadb_sum_unary_allreduce_async(int op, size_t n, const double* x, double* x_adj, double seed, unsigned flags, double* dev_value);
+int fadb_mlp3_allreduce_async(size_t batch, const double* X, const double* y, const double* parm, double* grad, unsigned flags,
+                              double* dev_loss);
 
 /* ---- bind-time kernel specialisation (csrc/jit.cu) ------------------------------------------
  * The reference's expression templates hand every expression its own fused evaluator at compile

@@ -429,9 +429,36 @@ def test_peer_memory_allreduce_single_rank(fb):
         assert out[0][0] == out[1][0]
         for a, b in zip(out[0][1:], out[1][1:]):
             np.testing.assert_array_equal(a, b)
+    # sum(f(x)) and the network with the WHOLE all-reduce fused into the one launch (last CTA pushes, waits, sums):
+    # one rank must give the bits of the plain calls; odd sizes, table-log functor, all three network variants
+    import torch
+    for op, n in (("exp", 5003), ("log", 1 << 16), (("pow", 2), 70001), (("pow", 3), 129)):
+        xs = synth.sum_inputs(n)
+        out = []
+        for call in (L.fadb_sum_unary_async, L.fadb_sum_unary_allreduce_async):
+            xd, xa, dv = dev(xs), dev(np.full(n, 0.25)), zeros(1)
+            for _ in range(2):                   # accumulating adjoints, both payload buffers
+                fb.check(call(fb._op_code(op), n, fb._ptr(xd), fb._ptr(xa), 0.75, 0, fb._ptr(dv)))
+            out.append((host(dv), host(xa)))
+        np.testing.assert_array_equal(out[0][0], out[1][0])
+        np.testing.assert_array_equal(out[0][1], out[1][1])
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for batch in (257, sms * 256 + 77, sms * 1024 + 5):      # <1,1,256>, <1,1,512> and <1,2,256> variants
+        Xn, yn = synth.mlp3_inputs(batch)
+        gX, gy, gp = torch.from_numpy(np.ascontiguousarray(Xn.T)).cuda(), dev(yn), dev(kats.NN_PARM)
+        out = []
+        for call in (L.fadb_mlp3_async, L.fadb_mlp3_allreduce_async):
+            gl = dev(np.full(26, 0.5))
+            for flags in (0, fb.OVERWRITE_ADJ, 0):
+                fb.check(call(batch, fb._ptr(gX), fb._ptr(gy), fb._ptr(gp), fb._ptr(gl), flags, C.c_void_p(gl.data_ptr() + 25 * 8)))
+            out.append(host(gl))
+        np.testing.assert_array_equal(out[0], out[1])
     fb.check(L.fadb_p2p_status(C.byref(err)))
     assert err.value == 0
     fb.check(L.fadb_p2p_destroy())
+    # without connected mailboxes the fused calls fail loudly instead of skipping the exchange
+    assert L.fadb_sum_unary_allreduce_async(fb._op_code("exp"), 4, fb._ptr(t), fb._ptr(t), 1.0, 0, fb._ptr(t)) != 0
+    assert L.fadb_mlp3_allreduce_async(1, fb._ptr(t), fb._ptr(t), fb._ptr(t), None, 0, fb._ptr(t)) != 0
 
 
 def test_least_squares_one_pass_kernel(fb):
@@ -717,6 +744,33 @@ def test_mlp3_vs_oracle(fb, batch):
     ol = O.mlp3(X, y, kats.NN_PARM.copy(), og, nthreads=4)
     assert rel(loss, ol) <= REL_REDUCE
     np.testing.assert_allclose(host(grad), og, rtol=1e-10, atol=1e-12 * np.abs(og).max())
+
+
+def test_shutdown_releases_workspaces_and_reinit_reproduces(fb):
+    # fadb_shutdown frees the kernels' lazily allocated per-device workspaces (regression partial rows, network
+    # partial rows, dense-normal factors, mailboxes); after fadb_init every path must allocate afresh and give
+    # the same bits
+    import torch
+    L = fb.lib()
+
+    def run():
+        rows, cols = 5002, 7
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=3)
+        wa, sa = zeros(cols), zeros(1)
+        v1 = fb.linreg_nll(torch.from_numpy(np.ascontiguousarray(X.T)).cuda(), dev(y), dev(w_true + 0.01), wa, dev([1.3]), sa)
+        Xn, yn = synth.mlp3_inputs(300)
+        grad = zeros(25)
+        v2 = fb.mlp3(torch.from_numpy(np.ascontiguousarray(Xn.T)).cuda(), dev(yn), dev(kats.NN_PARM), grad)
+        return v1, host(wa), host(sa), v2, host(grad)
+    a = run()
+    torch.cuda.synchronize()
+    L.fadb_shutdown()
+    fb.check(L.fadb_init(0))
+    fb.use_torch_stream()
+    b = run()
+    assert a[0] == b[0] and a[3] == b[3]
+    for i in (1, 2, 4):
+        np.testing.assert_array_equal(a[i], b[i])
 
 
 # ------------------------------------------------------------------ ABI behaviour
