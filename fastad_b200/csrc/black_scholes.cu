@@ -232,8 +232,8 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     // memory (11 instead of 20 FP64 instructions, three per option) 20.7; log through a 129-entry
     // {1/c, log c} table (no division, 15 instead of 27) 20.5 (default).  4 CTAs of 224 threads at 72 registers
     // (7.9 instead of 9.2 trips per thread at 2^20 options) measured 21.4: removed.
-    // Two options per thread, tighter launch bounds (spills) and atomic
-    // work-stealing were measured slower and removed.
+    // Two options per thread, tighter launch bounds (spills), atomic work-stealing and streaming (st.global.cs)
+    // result stores (20.68 against 20.48 us, A/B twice) were measured slower and removed.
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 23; }
     static int host_grid = -1;
@@ -338,7 +338,10 @@ extern "C" int fadb_black_scholes_host(size_t n, const double* hS, const double*
     // no copy calls.  Measured on B200, 2^20 options (104 MB over PCIe): staged 1.78 ms at the best
     // chunk size (4 chunks; more chunks cost ~35 us each in copy calls), direct 1.51 ms (32 CTAs); plain
     // cudaMemcpy of the 64 MB of results alone takes 1.18 ms.  A mix (kernel reads host memory, DMA
-    // write-back) measured slower than both (2.04 ms).  FADB_BS_HOST_MODE=0 forces the staged path.
+    // write-back) measured slower than both (2.04 ms), and so did the opposite mix (copy engine brings the inputs in
+    // chunk by chunk, the kernel stores straight to the host arrays): 1.72 / 1.87 / 2.17 ms at 4 / 8 / 16 chunks,
+    // i.e. ~37 us per chunk for its five small serial copies, whatever the CTA count.  FADB_BS_HOST_MODE=0 forces
+    // the staged path.
     const double* hin[5] = {hS, hK, hsigma, htau, hr};
     static int direct_ok = -1;
     if (direct_ok < 0) { const char* e = getenv("FADB_BS_HOST_MODE"); direct_ok = (e && atoi(e) == 0) ? 0 : 1; }
