@@ -129,7 +129,7 @@ _lib = None
 def load(path=None):
     """dlopen the shared library and attach signatures.  Raises if it is not built."""
     global _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("FASTAD_B200_LIB") or LIB_PATH      # the override serves A/B runs of two builds
     if not os.path.exists(path):
         raise FadbError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -233,7 +233,10 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     // {1/c, log c} table (no division, 15 instead of 27) 20.5 (default).  4 CTAs of 224 threads at 72 registers
     // (7.9 instead of 9.2 trips per thread at 2^20 options) measured 21.4: removed.
     // Two options per thread, tighter launch bounds (spills), atomic work-stealing and streaming (st.global.cs)
-    // result stores (20.68 against 20.48 us, A/B twice) were measured slower and removed.
+    // result stores (20.68 against 20.48 us, A/B twice) were measured slower and removed.  So was a branch-free loop body
+    // (exp_t without its early return + an unconditional prefetch: 347 instead of 405 instructions per option, one
+    // straight-line block, 21.3 us) and exp_t / log_t literals from the constant bank (326 instructions, 22.0 us; without
+    // the branch-free part 20.9-23.4 us): the kernel is bound by dependent-issue latency, not by issue slots.
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 23; }
     static int host_grid = -1;

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <type_traits>
 
+#define FM_CONST_LITERALS      // fastmath.cuh: exp_t's literals from the constant bank (measured: 100.8 -> 97.5 us at 2^22 rows)
 #include "common.cuh"
 #include "p2p_device.cuh"
 #include "../../include/fastad_b200/fastmath.cuh"
