@@ -349,8 +349,8 @@ def run_ours(args):
         from fastad_b200 import sharding
         all_reduce = small_all_reduce
 
-        def normal_step(shape, x_adj, mu_t, sg_t, mu_adj, sg_adj, flags=0):
-            # rank-local shard of n3 elements; N > 1: one 4-double NCCL all-reduce per evaluation
+        def normal_step(shape, x_adj, mu_t, sg_t, mu_adj, sg_adj, flags=0, n3=n3, x=x):
+            # rank-local shard of n3 elements; N > 1: one 4-double all-reduce per evaluation
             class Ops:
                 def sigma_check(self):
                     F.check(L.fadb_sigma_check(n3, P(sg_t), P(inval)))
@@ -397,6 +397,23 @@ def run_ours(args):
         t = timed_loop(normal_step(0, None, mu1, sg1, mua1, sga1), steps2, 3, world)
         add("normal_vss_xconst_2^26", 8 * n3, t, steps2, n3, "elements", sharded=True)
         del x, mu, sg, xa, ma, sa
+        # the upper size of BASELINE config 3: 2^28 elements per GPU, vvv (6 x 2 GiB of operands and adjoints); inputs
+        # drawn on the device (same distributions; parity at this size is tests/test_gpu_kernels.py's job)
+        n5 = 1 << 28
+        gen = torch.Generator(device="cuda").manual_seed(synth.SEED + rank)
+        xL = torch.randn(n5, dtype=torch.float64, device="cuda", generator=gen)
+        muL = torch.randn(n5, dtype=torch.float64, device="cuda", generator=gen)
+        sgL = torch.rand(n5, dtype=torch.float64, device="cuda", generator=gen) * 1.5 + 0.5
+        xaL, maL, saL = zeros(n5), zeros(n5), zeros(n5)
+        steps5 = max(5, min(steps2, 20))
+        t = timed_loop(normal_step(3, xaL, muL, sgL, maL, saL, 0, n5, xL), steps5, 3, world)
+        add("normal_vvv_2^28", 72 * n5, t, steps5, n5, "elements",
+            {"note": "exact semantics: +8 B/elem sigma validity pre-pass (80 B/elem traffic); per-GPU shard"},
+            sharded=True)
+        t = timed_loop(normal_step(3, xaL, muL, sgL, maL, saL, F.TRUST_SIGMA, n5, xL), steps5, 3, world)
+        add("normal_vvv_2^28_trust_sigma", 72 * n5, t, steps5, n5, "elements", sharded=True)
+        del xL, muL, sgL, xaL, maL, saL
+        torch.cuda.empty_cache()
 
     if "logpdf" in wl:
         # the other diagonal log-pdfs, all-vector operands, N = 2^25, exact semantics
