@@ -163,6 +163,41 @@ def test_normal_unaligned_and_empty(fb):
     assert fb.normal_lpdf(e, one, one, None, zeros(1), zeros(1)) == 0.0
 
 
+@pytest.mark.parametrize("log2n", [26, 28])
+def test_normal_full_size_properties(fb, log2n):
+    # BASELINE config 3 sizes (2^26 and 2^28 elements, vvv).  The oracle does not finish in seconds here, so the inputs
+    # are built to make every per-element quantity exactly representable: z = (x - mu) / sigma cycles through dyadic
+    # values with sum z^2 = 15 per 8 elements, sigma cycles through powers of two whose logs cancel per 8 elements.
+    # Then value = -0.5 * 15 * n / 8 and all three adjoint vectors are exact dyadic numbers: compared bit for bit.
+    import torch
+    n = 1 << log2n
+    f64 = dict(dtype=torch.float64, device="cuda")
+    i = torch.arange(n, device="cuda")
+    z = torch.tensor([0.5, -1.0, 1.5, -2.0, 2.0, -1.5, 1.0, -0.5], **f64)[i & 7]
+    sigma = torch.tensor([1.0, 2.0, 0.5, 4.0, 0.25, 2.0, 0.5, 1.0], **f64)[i & 7]
+    mu = (i & 1023).to(torch.float64) / 1024.0
+    del i
+    x = mu + sigma * z                                   # exact
+    seed = 0.75
+    want_x = 0.5 - seed * z / sigma                      # adjoints accumulate onto 0.5
+    want_m = 0.5 + seed * z / sigma
+    want_s = 0.5 + seed * (z * z - 1.0) / sigma
+    del z
+    for flags in (0, fb.TRUST_SIGMA):
+        xa, ma, sa = (torch.full((n,), 0.5, **f64) for _ in range(3))
+        v = fb.normal_lpdf(x, mu, sigma, xa, ma, sa, seed=seed, flags=flags)
+        assert rel(v, -0.5 * 15.0 * n / 8.0) <= REL_REDUCE
+        assert torch.equal(xa, want_x) and torch.equal(ma, want_m) and torch.equal(sa, want_s)
+        del xa, ma, sa
+    # one invalid sigma anywhere in 2^28 elements: -inf and no adjoint touched (normal.hpp:440-457)
+    sigma[n - 3] = -1.0
+    xa = torch.zeros(n, **f64)
+    assert fb.normal_lpdf(x, mu, sigma, xa, None, None) == -math.inf
+    assert not bool(xa.any())
+    del x, mu, sigma, xa, want_x, want_m, want_s
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------ K2 sum of unary maps
 @pytest.mark.parametrize("op", ["exp", "log", "sqrt", "sin", "cos", "tan", "atan", "erf", "sigmoid",
                                 "sinh", "cosh", "tanh", "neg", ("pow", 2), ("pow", 3), ("pow", 5), ("pow", -2)])
