@@ -727,6 +727,28 @@ def test_logpdf_kernels_out_of_range(fb, dist, bvec, cvec):
 
 
 # ------------------------------------------------------------------ K5 regression
+def test_linreg_full_size_properties(fb):
+    # BASELINE config 4 size: X 2^20 x 64 (512 MiB), the TMA kernel.  Integer-valued X and w, dyadic residuals and
+    # sigma = 2 make X w, X^T r and every adjoint exactly representable whatever the summation order: w_adj and
+    # sigma_adj are compared bit for bit with the same quantities formed by torch, the value to 1e-12.
+    import torch
+    rows, cols = 1 << 20, 64
+    f64 = dict(dtype=torch.float64, device="cuda")
+    i = torch.arange(rows, device="cuda")
+    j = torch.arange(cols, device="cuda")
+    X = (((i[None, :] * 7 + j[:, None] * 3) % 5) - 2).to(torch.float64)         # (cols, rows) == rows x cols column-major
+    w = ((j % 3) - 1).to(torch.float64)
+    r = torch.tensor([0.5, -1.0, 1.5, -2.0, 2.0, -1.5, 1.0, -0.5], **f64)[i & 7]
+    y = w @ X + r
+    sigma, seed = torch.tensor([2.0], **f64), 0.75
+    sum_r2 = 15.0 * rows / 8.0
+    w_adj, s_adj = torch.full((cols,), 0.5, **f64), torch.full((1,), 0.5, **f64)
+    v = fb.linreg_nll(X, y, w, w_adj, sigma, s_adj, seed=seed)
+    assert rel(v, -0.5 * sum_r2 / 4.0 - rows * math.log(2.0)) <= REL_REDUCE
+    assert torch.equal(w_adj, 0.5 + seed * 0.25 * (X @ r))
+    assert float(s_adj[0]) == 0.5 + seed * (sum_r2 / 4.0 - rows) / 2.0
+
+
 @pytest.mark.parametrize("rows,cols", [(5, 2), (1000, 64), (4097, 64), (777, 7), (300, 130)])
 def test_linreg_vs_oracle(fb, rows, cols):
     import torch
