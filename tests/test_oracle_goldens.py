@@ -307,6 +307,19 @@ def test_opeq_goldens():
     assert_double_eq(e.adj(v), vseed * (2 * kats.FIX_VEC + 2 * kats.FIX_VEC))
 
 
+def test_for_each_goldens():
+    # test/reverse/core/for_each_unittest.cpp:33-46: for_each over {x += 1, x += 1} (ForEachIterNode, for_each.hpp:19-111,
+    # is the glue of its sub-expressions): value x + 2, stored back into x; beval(seed) leaves x_adj = seed
+    seed, x0 = 3.14, kats.FIX_SCL
+    e = O.OracleExpr(); x = e.var(x0)
+    e.bind(e.glue(e.opeq("add", x, e.const(1.0)), e.opeq("add", x, e.const(1.0))))
+    res = e.feval()
+    assert_double_eq(res, [x0 + 2.0])
+    assert_double_eq(e.value(x), res)
+    e.beval(seed)
+    assert_double_eq(e.adj(x), [seed])
+
+
 def test_if_else_and_comparisons():
     # test/reverse/core/if_else_unittest.cpp: only the taken branch receives the seed;
     # comparison nodes have no adjoint (binary.hpp:124)
