@@ -33,6 +33,7 @@ SIGNATURES = {
     "fadb_init": (_i, [_i]),
     "fadb_shutdown": (None, []),
     "fadb_device_count": (_i, []),
+    "fadb_get_device": (_i, []),
     "fadb_set_stream": (_i, [_vp]),
     "fadb_get_stream": (_i, [C.POINTER(_vp)]),
     "fadb_sync": (_i, []),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "fadb_host_unregister": (_i, [_vp]),
     "fadb_black_scholes": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _u]),
     "fadb_black_scholes_host": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "fadb_black_scholes_batches": (_i, [_sz, _sz, _sz, _sz, C.POINTER(_vp), C.POINTER(_vp), _u]),
     "fadb_sum_unary": (_i, [_i, _sz, _vp, _vp, _d, _u, _dp]),
     "fadb_sum_unary_async": (_i, [_i, _sz, _vp, _vp, _d, _u, _vp]),
     "fadb_prod": (_i, [_sz, _vp, _vp, _d, _u, _dp]),
@@ -107,6 +109,7 @@ SIGNATURES = {
     "fadb_expr_value_ptr": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "fadb_p2p_create": (_i, [_i, _i, _vp]),
     "fadb_p2p_connect": (_i, [_vp]),
+    "fadb_p2p_create_local": (_i, [_i, C.POINTER(_i)]),
     "fadb_p2p_allreduce": (_i, [_vp, _i]),
     "fadb_p2p_status": (_i, [C.POINTER(C.c_ulonglong)]),
     "fadb_p2p_destroy": (_i, []),
@@ -206,6 +209,25 @@ def black_scholes(S, K, sigma, tau, r, out=None, flags=OVERWRITE_ADJ):
     arr = (C.c_void_p * 8)(*[o.data_ptr() for o in out])
     check(lib().fadb_black_scholes(n, _ptr(S), _ptr(K), _ptr(sigma), _ptr(tau), _ptr(r), arr, flags))
     return out
+
+
+class BlackScholesBatches:
+    """Operand tables for fadb_black_scholes_batches: `sets` = [(inputs[5], outputs[8]), ...] of float64 CUDA tensors of
+    one length; run(count, first) launches `count` batches back to back from ONE host call (no Python between launches)."""
+
+    def __init__(self, sets, flags=OVERWRITE_ADJ):
+        for ins, outs in sets:
+            _chk_f64(*ins, *outs)
+        self.keep = sets
+        self.n = sets[0][0][0].numel()
+        self.nsets = len(sets)
+        self.flags = flags
+        self.tin = (C.c_void_p * (5 * self.nsets))(*[t.data_ptr() for ins, _ in sets for t in ins])
+        self.tout = (C.c_void_p * (8 * self.nsets))(*[t.data_ptr() for _, outs in sets for t in outs])
+        self.fn = lib().fadb_black_scholes_batches
+
+    def run(self, count, first=0):
+        check(self.fn(count, self.n, self.nsets, first, self.tin, self.tout, self.flags))
 
 
 def black_scholes_host(S, K, sigma, tau, r, out):

@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tma_util.cuh"
 #include "../../include/fastad_b200/fastmath.cuh"
 
 namespace fadb {
@@ -207,6 +208,151 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Bulk-copy (TMA) variant: ONE persistent CTA per SM; every group of G warps runs its own pipeline.
+// A tile is G*32*OPL consecutive options.  The group's leader thread streams the five input tiles of the group's
+// next tiles into a group-private STAGES-deep shared-memory ring with cp.async.bulk (completion on a group-private
+// mbarrier); the threads read their option from shared memory (conflict-free LDS.64), evaluate it in registers
+// exactly like bs_kernel_fast_pf, stage the eight results in a group-private tile, and the leader sends them out
+// with cp.async.bulk shared -> global (accumulating adjoints: cp.reduce.async.bulk .add.f64, the same IEEE add
+// performed at L2).  No per-thread global address arithmetic, no registers held for prefetched operands, no
+// CTA-wide barrier in the loop (G = 1: __syncwarp only; G > 1: one named barrier per group), and the load depth
+// is set by the ring instead of by occupancy.  Needs 16-byte aligned arrays; the n % tile tail and small batches
+// take the per-thread path.
+// ---------------------------------------------------------------------------------------
+template <int WARPS, int G, int STAGES, int OPL, int OB>
+struct BsTmaSmem {
+    static constexpr int GROUPS = WARPS / G, TILE = G * 32 * OPL;
+    double in[GROUPS][STAGES][5][TILE];
+    double out[GROUPS][OB][8][TILE];
+    double tab[676];                       // erfcx pieces [0, 256) + 2^(j/32) [256, 288) + log table [288, 675)
+    uint64_t full[GROUPS][STAGES];
+};
+
+template <int G>
+__device__ __forceinline__ void bs_group_sync(int grp)
+{
+    if (G == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(G * 32) : "memory");
+}
+
+template <bool ACC, int WARPS, int G, int STAGES, int OPL, int OB>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+bs_kernel_tma(size_t n, const double* __restrict__ S, const double* __restrict__ K,
+              const double* __restrict__ sigma, const double* __restrict__ tau,
+              const double* __restrict__ r, BSOut out)
+{
+    static_assert(WARPS % G == 0 && (G == 1 || WARPS / G <= 15), "bs_kernel_tma: one named barrier per group");
+    using Smem = BsTmaSmem<WARPS, G, STAGES, OPL, OB>;
+    constexpr int TILE = Smem::TILE, GROUPS = Smem::GROUPS;
+    constexpr unsigned TB = TILE * 8;
+    extern __shared__ __align__(128) unsigned char bs_tma_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(bs_tma_raw);
+    // warp index through a shuffle: the compiler then knows it (and the tile arithmetic derived from it) is warp-uniform
+    // and issues the bulk copies from uniform registers instead of a per-lane waterfall loop around each of them
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int grp = warp / G, lig = (int)threadIdx.x - grp * (G * 32);      // thread index inside the group
+    const bool leader = lig == 0;
+    for (int i = threadIdx.x; i < 256; i += WARPS * 32) sm.tab[i] = fm::kErfcx32_d[i];
+    if (threadIdx.x < 32) sm.tab[256 + threadIdx.x] = fm::kExp2_32_d[threadIdx.x];
+    for (int i = threadIdx.x; i < 387; i += WARPS * 32) sm.tab[288 + i] = fm::kLogT_d[i];
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full[grp][s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_prologue();      // no global-memory access before the previous grid on the stream has completed
+
+    const unsigned ntiles = (unsigned)(n / TILE);
+    const unsigned stride = GROUPS * gridDim.x;
+    const unsigned first = (unsigned)grp * gridDim.x + blockIdx.x;      // a partial last round spreads over all SMs
+    uint64_t* bar = sm.full[grp];
+    auto issue = [&](unsigned tile, int s) {                            // leader only
+        mbar_arrive_expect_tx(&bar[s], 5 * TB);
+        const size_t off = (size_t)tile * TILE;
+        bulk_g2s(sm.in[grp][s][0], S + off, TB, &bar[s]);
+        bulk_g2s(sm.in[grp][s][1], K + off, TB, &bar[s]);
+        bulk_g2s(sm.in[grp][s][2], sigma + off, TB, &bar[s]);
+        bulk_g2s(sm.in[grp][s][3], tau + off, TB, &bar[s]);
+        bulk_g2s(sm.in[grp][s][4], r + off, TB, &bar[s]);
+    };
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const unsigned t = first + (unsigned)s * stride;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+    int s = 0, ob = 0;
+    unsigned par = 0;
+    for (unsigned tile = first; tile < ntiles; tile += stride) {
+        mbar_wait(&bar[s], par);
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) {
+            const int e = o * (G * 32) + lig;
+            const double vs = sm.in[grp][s][0][e], vk = sm.in[grp][s][1][e], vg = sm.in[grp][s][2][e],
+                         vt = sm.in[grp][s][3][e], vr = sm.in[grp][s][4][e];
+            if (o == OPL - 1) {          // the stage is in registers: refill it with the tile STAGES rounds ahead
+                bs_group_sync<G>(grp);
+                if (leader) {
+                    const unsigned nt = tile + STAGES * stride;
+                    if (nt < ntiles) issue(nt, s);
+                }
+            }
+            const BSRes o8 = bs_eval_fast<true>(vs, vk, vg, vt, vr, sm.tab);
+            if (o == 0) {                // the result tile sent OB rounds ago has left shared memory: its buffer is free
+                if (leader) bulk_wait_read<OB - 1>();
+                bs_group_sync<G>(grp);
+            }
+            double* po = &sm.out[grp][ob][0][e];
+            po[0 * TILE] = o8.call; po[1 * TILE] = o8.put;
+            po[2 * TILE] = o8.cS;   po[3 * TILE] = o8.cSig; po[4 * TILE] = o8.cR;
+            po[5 * TILE] = o8.pS;   po[6 * TILE] = o8.pSig; po[7 * TILE] = o8.pR;
+        }
+        fence_async_smem();
+        bs_group_sync<G>(grp);
+        if (leader) {
+            const size_t off = (size_t)tile * TILE;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (ACC && k >= 2) bulk_s2g_add_f64(out.p[k] + off, sm.out[grp][ob][k], TB);
+                else bulk_s2g(out.p[k] + off, sm.out[grp][ob][k], TB);
+            }
+            bulk_commit();
+        }
+        if (OB > 1) ob ^= 1;
+        if (++s == STAGES) { s = 0; par ^= 1; }
+    }
+    if (leader) bulk_wait<0>();
+    // the n % TILE options behind the last full tile: per-thread path, the last CTA
+    if (blockIdx.x == gridDim.x - 1) {
+        for (size_t i = (size_t)ntiles * TILE + threadIdx.x; i < n; i += WARPS * 32) {
+            const BSRes o8 = bs_eval_fast<true>(__ldg(S + i), __ldg(K + i), __ldg(sigma + i), __ldg(tau + i), __ldg(r + i), sm.tab);
+            bs_store1<ACC>(out, i, o8);
+        }
+    }
+}
+
+template <bool ACC, int WARPS, int G, int STAGES, int OPL, int OB>
+static int launch_bs_tma(Context& c, cudaStream_t st, size_t n, const double* S, const double* K, const double* sigma,
+                         const double* tau, const double* r, const BSOut& o, int max_grid)
+{
+    using Smem = BsTmaSmem<WARPS, G, STAGES, OPL, OB>;
+    auto kern = bs_kernel_tma<ACC, WARPS, G, STAGES, OPL, OB>;
+    constexpr size_t smem = sizeof(Smem);
+    static_assert(smem <= 227 * 1024, "bs_kernel_tma: shared-memory ring exceeds 227 KB");
+    static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    FADB_CUDA(attr);
+    const size_t ntiles = n / Smem::TILE;
+    size_t grid = (ntiles + Smem::GROUPS - 1) / Smem::GROUPS;
+    if (grid > (size_t)c.sms) grid = c.sms;
+    if (max_grid > 0 && grid > (size_t)max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+    FADB_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(WARPS * 32), smem, st, n, S, K, sigma, tau, r, o));
+    return FADB_OK;
+}
+
 // host_mapped: the arrays are page-locked HOST memory (fadb_black_scholes_host): the PCIe link, not the
 // FP64 pipe, is the limit there and FEWER resident CTAs are faster -- measured per 2^20 options:
 // 444 CTAs 1.62 ms, 296 1.57, 148 1.54, 74 1.52, 24-48 1.506, 16 1.53, 8 1.56 (FADB_BS_HOST_GRID)
@@ -237,12 +383,34 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     // (exp_t without its early return + an unconditional prefetch: 347 instead of 405 instructions per option, one
     // straight-line block, 21.3 us) and exp_t / log_t literals from the constant bank (326 instructions, 22.0 us; without
     // the branch-free part 20.9-23.4 us): the kernel is bound by dependent-issue latency, not by issue slots.
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("FADB_BS_VARIANT"); variant = e ? atoi(e) : 23; }
-    static int host_grid = -1;
-    if (host_grid < 0) { const char* e = getenv("FADB_BS_HOST_GRID"); host_grid = e ? atoi(e) : 32; }
-    (void)vec_ok;
+    // (function-local statics with an initialiser: thread-safe on first use, C++11 [stmt.dcl])
+    static const int variant = [] { const char* e = getenv("FADB_BS_VARIANT"); return e ? atoi(e) : 23; }();
+    static const int host_grid = [] { const char* e = getenv("FADB_BS_HOST_GRID"); return e ? atoi(e) : 32; }();
+    static const long tma_min = [] { const char* e = getenv("FADB_BS_TMA_MIN"); return e ? atol(e) : 148l * 24 * 32; }();
     const bool ovw = flags & FADB_OVERWRITE_ADJ;
+    // bulk-copy pipeline (variants 30-39): 16-byte aligned arrays, at least one tile per warp
+    if (variant >= 30 && variant < 40 && vec_ok && n >= (size_t)tma_min && (n >> 36) == 0) {
+        const int mg = host_mapped ? host_grid : 0;
+        int rc;
+#define FADB_BS_TMA(W, G_, ST, OPL_, OB_) (ovw ? launch_bs_tma<false, W, G_, ST, OPL_, OB_>(c, st, n, S, K, sigma, tau, r, o, mg) \
+                                               : launch_bs_tma<true, W, G_, ST, OPL_, OB_>(c, st, n, S, K, sigma, tau, r, o, mg))
+        switch (variant) {
+        case 31: rc = FADB_BS_TMA(24, 1, 2, 2, 1); break;
+        case 32: rc = FADB_BS_TMA(28, 1, 3, 1, 1); break;
+        case 33: rc = FADB_BS_TMA(32, 1, 2, 1, 2); break;
+        case 34: rc = FADB_BS_TMA(24, 2, 3, 1, 2); break;
+        case 35: rc = FADB_BS_TMA(24, 4, 3, 1, 2); break;
+        case 36: rc = FADB_BS_TMA(24, 8, 3, 1, 2); break;
+        case 37: rc = FADB_BS_TMA(28, 4, 3, 1, 1); break;
+        case 38: rc = FADB_BS_TMA(24, 2, 2, 2, 1); break;
+        case 39: rc = FADB_BS_TMA(32, 4, 2, 1, 2); break;
+        default: rc = FADB_BS_TMA(24, 1, 3, 1, 2); break;
+        }
+#undef FADB_BS_TMA
+        if (rc) return rc;
+        c.launches++;
+        return FADB_OK;
+    }
 #define FADB_BS_LAUNCH(KERNEL)                                                                          \
     do {                                                                                                \
         if (ovw) KERNEL<false><<<resident_grid(c, KERNEL<false>, threads, 0, n, threads), threads, 0, st>>>(n, S, K, sigma, tau, r, o); \
@@ -301,6 +469,30 @@ extern "C" int fadb_black_scholes(size_t n, const double* S, const double* K,
     return launch_black_scholes(*c, c->stream, n, S, K, sigma, tau, r, out, flags);
 }
 
+// `count` batches in ONE host call (the per-option loop of example/black_scholes.cpp:43-70 over count x n options): batch b
+// reads the operand set (first_set + b) % nsets -- in[5 * s + {0..4}] = S, K, sigma, tau, r of set s, out[8 * s + k] its
+// eight result arrays -- with one kernel launch per batch, back to back on the library stream, no host work in between.
+extern "C" int fadb_black_scholes_batches(size_t count, size_t n, size_t nsets, size_t first_set,
+                                          const double* const* in, double* const* out, unsigned flags)
+{
+    FADB_REQUIRE(nsets >= 1 && in != nullptr && out != nullptr, "fadb_black_scholes_batches: null operand tables");
+    if (n > 0)
+        for (size_t s = 0; s < nsets; ++s) {
+            for (int k = 0; k < 5; ++k) FADB_REQUIRE(in[5 * s + k] != nullptr, "fadb_black_scholes_batches: null input");
+            for (int k = 0; k < 8; ++k) FADB_REQUIRE(out[8 * s + k] != nullptr, "fadb_black_scholes_batches: null output");
+        }
+    Context* c;
+    int rc = current_context(&c);
+    if (rc) return rc;
+    for (size_t b = 0; b < count; ++b) {
+        const size_t s = (first_set + b) % nsets;
+        rc = launch_black_scholes(*c, c->stream, n, in[5 * s], in[5 * s + 1], in[5 * s + 2], in[5 * s + 3], in[5 * s + 4],
+                                  out + 8 * s, flags);
+        if (rc) return rc;
+    }
+    return FADB_OK;
+}
+
 // Host-buffer entry: the call a user of the reference makes with plain host arrays.
 // Page-locked arrays: one launch of the resident kernel over PCIe.  Pageable arrays: the batch is
 // chunked and H2D / kernel / D2H overlap on three streams' worth of double buffering.
@@ -316,8 +508,7 @@ extern "C" int fadb_black_scholes_host(size_t n, const double* hS, const double*
     if (rc) return rc;
 
     constexpr int NBUF = 3;
-    static int chunk_log2 = -1;
-    if (chunk_log2 < 0) { const char* e = getenv("FADB_BS_HOST_CHUNK_LOG2"); chunk_log2 = e ? atoi(e) : 18; }
+    static const int chunk_log2 = [] { const char* e = getenv("FADB_BS_HOST_CHUNK_LOG2"); return e ? atoi(e) : 18; }();
     const size_t cmax = (size_t)1 << chunk_log2;
     const size_t chunk = n < cmax ? n : cmax;
     static thread_local double* dbuf[NBUF] = {nullptr, nullptr, nullptr};
@@ -346,8 +537,7 @@ extern "C" int fadb_black_scholes_host(size_t n, const double* hS, const double*
     // i.e. ~37 us per chunk for its five small serial copies, whatever the CTA count.  FADB_BS_HOST_MODE=0 forces
     // the staged path.
     const double* hin[5] = {hS, hK, hsigma, htau, hr};
-    static int direct_ok = -1;
-    if (direct_ok < 0) { const char* e = getenv("FADB_BS_HOST_MODE"); direct_ok = (e && atoi(e) == 0) ? 0 : 1; }
+    static const int direct_ok = [] { const char* e = getenv("FADB_BS_HOST_MODE"); return (e && atoi(e) == 0) ? 0 : 1; }();
     const double* din[5];
     double* dout_zc[8];
     bool locked = direct_ok != 0;

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <set>
@@ -331,7 +332,10 @@ struct ENode {
 
 struct OperandRef { const double* val = nullptr; double* adj = nullptr; int adj_mode = 0; int node = -1; int stage = -1; };
 
+inline unsigned long long next_stage_uid() { static std::atomic<unsigned long long> n{0}; return ++n; }
+
 struct Stage {
+    unsigned long long uid = next_stage_uid();
     int type = 0;                  // 0 = MAP (interpreter), 1 = DOT, 2 = TRANSPOSE, 3 = dense-covariance normal,
                                    // 4 = det / log_det (k = take_log, p = policy), 5 = wishart (sig_const = df)
     size_t N = 1;
@@ -360,6 +364,13 @@ struct Stage {
     JitKernel jit[4];              // specialised kernels by mode (M_F, M_B, M_FB), compiled on first use
     int jit_state[4] = {0, 0, 0, 0};   // 0 untried, 1 ready, -1 not specialisable / compile failed
     LeafDesc* d_leaves = nullptr;
+    // Leaves that this stage READS from memory and later ASSIGNS (w op= expr, or a read of w ahead of `w = expr`):
+    // a backward-only launch (M_B) recomputes the forward values, but the forward-only launch (M_F) has already
+    // overwritten w.  Like OpEqNode's cache_ (eq.hpp:240-271) the pre-stage value is kept: M_F saves it, M_B reads
+    // it instead of w.val and, for op=, restores w from it afterwards.
+    struct PreVal { int leaf; double* cache; size_t n; bool restore; };
+    std::vector<PreVal> pre;
+    LeafDesc* d_leaves_b = nullptr;    // d_leaves with those leaves' val redirected to their cache (M_B launches)
     double* d_red = nullptr;       // [8]
     double* d_sig = nullptr;       // device copy of a constant scalar sigma
     bool big = false;              // scalar stage too large for the on-chip interpreter
@@ -924,6 +935,24 @@ struct fadb_expr {
             std::vector<DIns>& enc = st.enc;
             FADB_CUDA(cudaMemcpyAsync(st.d_prog, enc.data(), enc.size() * sizeof(DIns), cudaMemcpyHostToDevice, c.stream));
             FADB_CUDA(cudaMemcpyAsync(st.d_leaves, st.leaves.data(), st.leaves.size() * sizeof(LeafDesc), cudaMemcpyHostToDevice, c.stream));
+            // pre-stage values of leaves that are read and then assigned in this stage (see Stage::pre)
+            st.pre.clear();
+            for (size_t l = 0; l < st.leaves.size(); ++l) {
+                if (!st.leaves[l].assigned || st.leaf_node[l] < 0) continue;
+                bool read = false, opeq = false;
+                for (const Ins& I : st.prog) {
+                    if (I.op == I_LEAF && I.leaf == (int)l) read = true;
+                    if (I.op == I_OPEQ && I.leaf == (int)l) opeq = true;
+                }
+                if (!read) continue;
+                Stage::PreVal pv{(int)l, nullptr, st.leaves[l].scalar ? (size_t)1 : st.N, opeq};
+                if ((rc = dev_alloc(pv.n * sizeof(double), (void**)&pv.cache))) return rc;
+                st.pre.push_back(pv);
+            }
+            if (!st.pre.empty()) {
+                if ((rc = dev_alloc(st.leaves.size() * sizeof(LeafDesc), (void**)&st.d_leaves_b))) return rc;
+                if ((rc = upload_leaves_b(c, st))) return rc;
+            }
             if (st.term == T_NORMAL && st.sig_is_const) {
                 if ((rc = dev_alloc(sizeof(double), (void**)&st.d_sig))) return rc;
                 FADB_CUDA(cudaMemcpyAsync(st.d_sig, &st.sig_const, sizeof(double), cudaMemcpyHostToDevice, c.stream));
@@ -937,6 +966,19 @@ struct fadb_expr {
         }
         FADB_CUDA(cudaStreamSynchronize(c.stream));   // host vectors may be reallocated later
         bound = true;
+        return FADB_OK;
+    }
+
+    // d_leaves_b = leaf table of the backward-only launches; the caches start as a copy of the current values
+    int upload_leaves_b(Context& c, Stage& st)
+    {
+        std::vector<LeafDesc> lb = st.leaves;
+        for (const Stage::PreVal& pv : st.pre) {
+            lb[pv.leaf].val = pv.cache;
+            FADB_CUDA(cudaMemcpyAsync(pv.cache, st.leaves[pv.leaf].val, pv.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        }
+        FADB_CUDA(cudaMemcpyAsync(st.d_leaves_b, lb.data(), lb.size() * sizeof(LeafDesc), cudaMemcpyHostToDevice, c.stream));
+        FADB_CUDA(cudaStreamSynchronize(c.stream));      // `lb` is a local
         return FADB_OK;
     }
 
@@ -956,6 +998,7 @@ struct fadb_expr {
                     st.leaves[l].adj = st.leaves[l].adj_mode ? nodes[st.leaf_node[l]].adj : nullptr;
                 }
             FADB_CUDA(cudaMemcpyAsync(st.d_leaves, st.leaves.data(), st.leaves.size() * sizeof(LeafDesc), cudaMemcpyHostToDevice, c.stream));
+            if (!st.pre.empty()) { int rc = upload_leaves_b(c, st); if (rc) return rc; }
         }
         FADB_CUDA(cudaStreamSynchronize(c.stream));
         detect_fast_paths();
@@ -1026,6 +1069,25 @@ struct fadb_expr {
         a.scratch = st.d_scratch;
         a.vec_ok = 0;
         for (size_t l = 0; l < st.leaves.size() && l < (size_t)MAXL_JIT; ++l) { a.lp_val[l] = st.leaves[l].val; a.lp_adj[l] = st.leaves[l].adj; }
+        if (!st.pre.empty() && mode == M_F)        // forward-only launch: keep the values it is about to overwrite
+            for (const Stage::PreVal& pv : st.pre)
+                FADB_CUDA(cudaMemcpyAsync(pv.cache, st.leaves[pv.leaf].val, pv.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        if (!st.pre.empty() && mode == M_B) {      // backward-only launch: the recomputed forward pass reads them back
+            a.leaves = st.d_leaves_b;
+            for (const Stage::PreVal& pv : st.pre) a.lp_val[pv.leaf] = pv.cache;
+        }
+        int rc_launch = launch_map(c, st, mode, a);
+        if (rc_launch) return rc_launch;
+        if (!st.pre.empty() && mode == M_B)        // OpEqNode::beval leaves the previous value in w (eq.hpp:262-271)
+            for (const Stage::PreVal& pv : st.pre)
+                if (pv.restore)
+                    FADB_CUDA(cudaMemcpyAsync(const_cast<double*>(st.leaves[pv.leaf].val), pv.cache, pv.n * sizeof(double),
+                                              cudaMemcpyDeviceToDevice, c.stream));
+        return FADB_OK;
+    }
+
+    int launch_map(Context& c, Stage& st, int mode, StageArgs& a)
+    {
         if (st.big) {
             stage_kernel<2><<<1, 32, 0, c.stream>>>(a);
             c.launches++;
@@ -1034,6 +1096,7 @@ struct fadb_expr {
         }
         if (jit_enabled() && st.jit_state[mode] >= 0) {
             // specialised kernel of this stage program (jit.cu): compiled once per (program, mode, device)
+            if (st.jit_state[mode] == 1 && st.jit[mode].gen != jit_generation()) st.jit_state[mode] = 0;   // unloaded by fadb_shutdown
             if (st.jit_state[mode] == 0) {
                 std::string text;
                 st.jit_state[mode] = (jit_program_text(st, mode, text) && jit_get(c, text, &st.jit[mode]) == FADB_OK) ? 1 : -1;
@@ -1093,13 +1156,13 @@ struct fadb_expr {
             // forward-only evaluations zero the seed (no adjoint is touched, normal.hpp:644); an inner
             // stage reads its scalar seed back from its boundary buffer.  The dense workspace is shared by
             // all dense stages of a device: a backward-only call re-factors unless this stage used it last.
-            static const Stage* owner[kMaxDevices] = {};
+            static unsigned long long owner[kMaxDevices] = {};      // Stage::uid (never reused, unlike a freed stage's address)
             double sd = (mode & M_B) ? seed : 0.0;
             if (mode == M_B && !seed_vec) {
                 FADB_CUDA(cudaMemcpyAsync(&sd, st.madj, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
                 FADB_CUDA(cudaStreamSynchronize(c.stream));
             }
-            const bool mine = owner[c.device] == &st;
+            const bool mine = owner[c.device] == st.uid;
             auto adjp = [](const OperandRef& r) { return r.adj_mode ? r.adj : nullptr; };
             int rc;
             if (st.type == 3) {
@@ -1114,7 +1177,7 @@ struct fadb_expr {
                                         (mine && mode == M_B) ? 0 : 1, st.mval);
             }
             if (rc) return rc;
-            owner[c.device] = &st;
+            owner[c.device] = st.uid;
             return FADB_OK;
         }
         if (st.type == 2) {
@@ -1282,6 +1345,13 @@ struct fadb_expr {
     {
         const int last = (int)plan.size() - 1;
         Stage& rs = *plan[last];
+        // A log-pdf root swept with seed 0 leaves EVERYTHING below it untouched (normal.hpp:160, cauchy.hpp:151,
+        // uniform.hpp / bernoulli.hpp alike): no root sweep and no producer sweeps either -- their boundary adjoints
+        // would otherwise still hold the seeds of the previous call.
+        if ((what & 2) && !seed_vec && seed == 0.0 && rs.type == 0 && rs.term >= T_NORMAL) {
+            what &= 1;
+            if (!what) return FADB_OK;
+        }
         const bool fast = rs.fast != 0 && what == 3 && !seed_vec;
         const size_t first = (fast && (rs.fast == 3 || rs.fast == 5)) ? plan.size() : 0;   // linreg / least squares subsume their dot stage
         if (what & 1) {

@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -54,6 +55,7 @@ struct Driver {
 struct Entry { CUmodule mod = nullptr; CUfunction fn = nullptr; int per_sm = 1; int regs = 0, local_bytes = 0; bool failed = false; };
 
 std::mutex g_mu;
+std::atomic<unsigned long long> g_generation{1};      // bumped when every module is unloaded (jit_shutdown)
 Nvrtc g_rtc;
 Driver g_drv;
 int g_state = 0;            // 0 untried, 1 ready, -1 unavailable
@@ -144,6 +146,7 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
         if (it->second.failed) return FADB_ERR_STATE;
         ++g_hits;
         out->fn = it->second.fn; out->per_sm = it->second.per_sm; out->regs = it->second.regs; out->local_bytes = it->second.local_bytes;
+        out->gen = g_generation.load();
         return FADB_OK;
     }
     Entry e;
@@ -168,7 +171,7 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
             if (!bin.empty() && finish_load(e, bin)) {
                 g_cache.emplace(key, e);
                 ++g_hits;
-                out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes;
+                out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes; out->gen = g_generation.load();
                 return FADB_OK;
             }
         }
@@ -203,14 +206,17 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     g_cache.emplace(key, e);
     if (e.failed) { ++g_failed; return FADB_ERR_STATE; }
     ++g_compiled;
-    out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes;
+    out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes; out->gen = g_generation.load();
     return FADB_OK;
 }
+
+unsigned long long jit_generation() { return g_generation.load(); }
 
 // fadb_shutdown: unload every specialised module of the current process
 void jit_shutdown()
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    ++g_generation;
     if (g_state == 1)
         for (auto& kv : g_cache)
             if (kv.second.mod) g_drv.module_unload(kv.second.mod);

@@ -4,7 +4,9 @@
 
 namespace fadb {
 struct Context;
-struct JitKernel { void* fn = nullptr; int per_sm = 1; int regs = 0; int local_bytes = 0; };
+struct JitKernel { void* fn = nullptr; int per_sm = 1; int regs = 0; int local_bytes = 0; unsigned long long gen = 0; };
+// bumped by jit_shutdown (every module is unloaded): a handle of an older generation must be re-fetched, not launched
+unsigned long long jit_generation();
 bool jit_enabled();
 int jit_get(const Context& c, const std::string& program, JitKernel* out);
 void jit_shutdown();

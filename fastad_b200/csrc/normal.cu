@@ -277,6 +277,8 @@ static int check_normal_args(int shape_code, size_t n, const double* x, const do
 {
     FADB_REQUIRE(shape_code >= 0 && shape_code <= 3, "normal_lpdf: shape_code must be 0..3");
     FADB_REQUIRE(n == 0 || (x && mu && sigma), "normal_lpdf: null operand");
+    // scalar operands are dereferenced by the kernels whatever n is (an empty x still has a mu and a sigma)
+    FADB_REQUIRE(((shape_code & 1) || mu) && ((shape_code & 2) || sigma), "normal_lpdf: null scalar operand");
     return FADB_OK;
 }
 

@@ -113,6 +113,13 @@ int fadb_device_count(void)
     return n;
 }
 
+int fadb_get_device(void)
+{
+    int dev = -1;
+    FADB_CUDA(cudaGetDevice(&dev));
+    return dev;
+}
+
 int fadb_set_stream(void* cuda_stream)
 {
     Context* c;

@@ -66,6 +66,7 @@ enum { FADB_ADD = 0, FADB_SUB, FADB_MUL, FADB_DIV,
 int fadb_init(int device);
 void fadb_shutdown(void);
 int fadb_device_count(void);
+int fadb_get_device(void);                     /* the current CUDA device (>= 0) or a negative FADB_ERR_* code */
 /* Use a caller-owned cudaStream_t (e.g. torch's current stream) for all launches on the
  * current device; NULL restores the library's own stream (pass cudaStreamLegacy, (void*)1, to
  * name the legacy default stream). */
@@ -102,6 +103,12 @@ int fadb_host_unregister(void* host);
 int fadb_black_scholes(size_t n, const double* S, const double* K, const double* sigma,
                        const double* tau, const double* r, double* const out[8],
                        unsigned flags);
+/* `count` batches of n options in ONE host call: batch b runs fadb_black_scholes on operand set (first_set + b) % nsets,
+ * in[5*s + {0..4}] = S, K, sigma, tau, r and out[8*s + {0..7}] of set s.  One launch per batch, back to back on the
+ * library stream: the per-option loop of example/black_scholes.cpp:43-70 over count x n options without host work
+ * between the batches. */
+int fadb_black_scholes_batches(size_t count, size_t n, size_t nsets, size_t first_set,
+                               const double* const* in, double* const* out, unsigned flags);
 /* Same call through HOST buffers (host↔device copies inside, chunked and overlapped). */
 int fadb_black_scholes_host(size_t n, const double* host_S, const double* host_K,
                             const double* host_sigma, const double* host_tau,
@@ -309,8 +316,16 @@ int fadb_expr_value_ptr(fadb_expr*, const double** dev_value, size_t* size);
  * ranks get identical bits).  Asynchronous on the library stream; no NCCL, no host synchronisation. */
 int fadb_p2p_create(int world, int rank, void* out_handle64);
 int fadb_p2p_connect(const void* all_handles /* world x 64 bytes, rank order */);
+/* ONE process driving several GPUs: rank r = devices[r], mailboxes connected through plain peer access (no IPC, no handle
+ * exchange).  The caller then selects a device and issues that rank's calls; a pull is enqueued after every rank's push. */
+int fadb_p2p_create_local(int world, const int* devices);
 int fadb_p2p_allreduce(double* dev_buf, int n);
+/* Failure mode: a wait that exceeds FADB_P2P_TIMEOUT_MS (default 30000) -- dead peer, mismatched rank count -- sets a STICKY
+ * error: that exchange and every later one deliver NaN (never a plausible partial sum), and every later host entry of the
+ * exchange (fadb_p2p_allreduce, *_push, *_pull, *_allreduce_async) returns FADB_ERR_STATE until fadb_p2p_destroy +
+ * fadb_p2p_create.  fadb_p2p_status synchronises the stream and returns the failed sequence number (0 = healthy). */
 int fadb_p2p_status(unsigned long long* out_error_seq);
+/* the caller barriers all ranks between their last exchange and this call (peers store into this mailbox) */
 int fadb_p2p_destroy(void);
 /* the normal log-pdf and regression passes with the exchange fused in: the producing kernel's last CTA pushes {sum r^2, X^T r} into every
  * rank's mailbox, the finish kernel waits, reduces in rank order and forms value + adjoints (cols <= 127) */

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <iterator>
 #include <limits>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -80,28 +81,41 @@ struct Slab {
     size_t used = 0;
     static constexpr size_t cap = 8192;
 };
-inline double* pool_take(size_t n)
+// Per (thread, device) pool with one free list per block size: a Var that dies returns its block, so a loop that
+// creates temporaries per iteration (as the reference's examples do) reuses them instead of growing without bound,
+// and a block carved on device A is never handed out on device B.
+struct Pool {
+    std::vector<Slab> slabs;
+    std::vector<double*> free_[33];      // by block size in doubles (2 .. 32)
+};
+inline Pool& pool_of(int dev)
 {
-    static thread_local std::vector<Slab> slabs;
-    static thread_local std::vector<double*> free2;
-    if (n == 2 && !free2.empty()) { double* p = free2.back(); free2.pop_back(); return p; }
-    if (slabs.empty() || slabs.back().used + n > Slab::cap) {
+    static thread_local std::map<int, Pool> pools;
+    return pools[dev];
+}
+inline double* pool_take(int dev, size_t n)
+{
+    Pool& P = pool_of(dev);
+    if (!P.free_[n].empty()) { double* p = P.free_[n].back(); P.free_[n].pop_back(); return p; }
+    if (P.slabs.empty() || P.slabs.back().used + n > Slab::cap) {
         Slab s;
         void* p = nullptr;
         check(fadb_malloc(Slab::cap * sizeof(double), &p));
         s.base = static_cast<double*>(p);
-        slabs.push_back(s);
+        P.slabs.push_back(s);
     }
-    double* r = slabs.back().base + slabs.back().used;
-    slabs.back().used += n;
+    double* r = P.slabs.back().base + P.slabs.back().used;
+    P.slabs.back().used += n;
     return r;
 }
+inline void pool_give(int dev, double* p, size_t n) { pool_of(dev).free_[n].push_back(p); }
 
 struct Storage {
     double* dval = nullptr;
     double* dadj = nullptr;
     size_t n = 0;
     int own = 0;   // 0: caller's device pointers, 1: fadb_malloc, 2: pooled
+    int dev = 0;   // device the pooled block was carved on
     std::vector<double> hval, hadj;
     bool host_val_newer = false, host_adj_newer = false, dev_val_newer = false, dev_adj_newer = false;
 
@@ -109,7 +123,9 @@ struct Storage {
     {
         if (!owning) return;
         if (n <= 16) {
-            dval = pool_take(2 * n);
+            dev = fadb_get_device();
+            check(dev);
+            dval = pool_take(dev, 2 * n);
             dadj = dval + n;
             own = 2;
         } else {
@@ -124,7 +140,11 @@ struct Storage {
         host_val_newer = host_adj_newer = true;   // zero-initialised like var.hpp:33-36
     }
     Storage(double* v, double* a, size_t n_) : dval(v), dadj(a), n(n_) {}
-    ~Storage() { if (own == 1) fadb_free(dval); }
+    ~Storage()
+    {
+        if (own == 1) fadb_free(dval);
+        else if (own == 2) pool_give(dev, dval, 2 * n);
+    }
     Storage(const Storage&) = delete;
     Storage& operator=(const Storage&) = delete;
 

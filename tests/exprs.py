@@ -338,6 +338,23 @@ def opeq_chain(n):
     return build
 
 
+def opeq_mul_then_sum(n):
+    def build(e):   # (w *= x, sum(w)) -- the op= statement is not the root
+        x, w = e.var(_vec(n)), e.var(_vec(n, -1.5, 1.5))
+        return e.glue(e.opeq("mul", w, x), e.sum(w)), [x, w], 1.0
+    return build
+def opeq_div_self_then_sum(n):
+    def build(e):   # (w /= exp(w), sum(w)): the right-hand side reads the PREVIOUS value of w (eq.hpp:240-271)
+        w = e.var(_vec(n, -1.0, 1.0))
+        return e.glue(e.opeq("div", w, e.unary("exp", w)), e.sum(w)), [w], 0.7
+    return build
+def opeq_then_dot(e):   # the op= stage is an inner stage: its output w is read by a dot stage through memory
+    A = e.const(np.array([[1.0, 2.0, -0.5], [-1.0, 3.0, 0.25], [2.0, -3.0, 1.5], [0.5, 0.5, -2.0]]))
+    w, x = e.var(np.array([[0.5], [-1.5], [2.0]])), e.var(np.array([[1.25], [0.75], [-0.5]]))
+    d = e.dot(A, w)
+    return e.glue(e.opeq("mul", w, x), e.sum(e.binary("mul", d, d))), [w, x], 1.0
+
+
 # ---- other diagonal log-pdfs ------------------------------------------------
 C_VX, C_VL, C_VS = np.array([0.5, -1.3, -3.2414999]), np.array([0.4, -2.30000001, -10.32]), np.array([0.51, 0.01, 3.4])
 
@@ -493,6 +510,9 @@ CASES = {
     "opeq_vec_scl": opeq_vec_scl,
     "opeq_vec_noalias": opeq_vec_noalias,
     "opeq_chain": opeq_chain(777),
+    "opeq_mul_then_sum": opeq_mul_then_sum(1001),
+    "opeq_div_self_then_sum": opeq_div_self_then_sum(333),
+    "opeq_then_dot": opeq_then_dot,
     "scalar_chain": scalar_chain,
     "placeholders": placeholders,
     "sumnode_benchmark": sumnode_benchmark,

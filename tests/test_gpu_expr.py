@@ -86,9 +86,18 @@ def test_expr_adjoints_accumulate(fb, name):
         _close(g, o, 1e-11, name)
 
 
-@pytest.mark.parametrize("name", ["scalar_chain", "vec_nested_sum", "vec_prod_one_zero", "normal_vec_sigma_expr"])
-def test_expr_feval_then_beval_equals_autodiff(fb, name):
+@pytest.mark.parametrize("name", ["scalar_chain", "vec_nested_sum", "vec_prod_one_zero", "normal_vec_sigma_expr",
+                                  "opeq_scl_alias", "opeq_scl_noalias", "opeq_vec_scl", "opeq_vec_noalias", "opeq_chain",
+                                  "opeq_mul_then_sum", "opeq_div_self_then_sum", "opeq_then_dot"])
+def test_expr_feval_then_beval_equals_autodiff(fb, engine, name):
+    # ad::evaluate followed by ad::evaluate_adj (eval.hpp:18-73): forward-only and backward-only launches.  op= stages
+    # overwrite w in the forward launch; the backward launch must still see the previous value (eq.hpp:240-271)
     build = exprs.CASES[name]
+    exprs.RNG = np.random.default_rng(20261019)
+    oe = O.OracleExpr()
+    oroot, ovars, oseed = build(oe)
+    oe.bind(oroot)
+    ov = oe.autodiff(oseed)
     exprs.RNG = np.random.default_rng(20261019)
     e = fb.Expr()
     root, variables, seed = build(e)
@@ -96,12 +105,36 @@ def test_expr_feval_then_beval_equals_autodiff(fb, name):
     v1 = e.feval()
     e.beval(seed)
     a1 = [e.adj(v).copy() for v in variables]
+    x1 = [e.value(v).copy() for v in variables]
+    np.testing.assert_allclose(v1, ov, rtol=1e-12)
+    for k, (g, o) in enumerate(zip(a1, [oe.adj(v) for v in ovars])):
+        _close(g, o, 1e-11, f"{name} adj[{k}] after feval + beval")
+    for k, (g, o) in enumerate(zip(x1, [oe.value(v) for v in ovars])):      # op= restores the previous value
+        _close(g, o, 1e-12, f"{name} val[{k}] after feval + beval")
     e.reset_adj()
     v2 = e.autodiff(seed)
     a2 = [e.adj(v).copy() for v in variables]
     np.testing.assert_array_equal(v1, v2)
     for x, y in zip(a1, a2):
         np.testing.assert_allclose(x, y, rtol=1e-14, atol=0)
+
+
+def test_logpdf_root_seed_zero_leaves_producers_untouched(fb, engine):
+    # autodiff(1.0) then autodiff(0.0) on normal(y, dot(X, w), sigma_vec): the second call must not
+    # accumulate the first call's boundary adjoints again (normal.hpp:160: beval(0) returns before any sweep)
+    rng = np.random.default_rng(3)
+    e = fb.Expr()
+    X, y = e.const(rng.normal(size=(40, 3))), e.const(rng.normal(size=40))
+    w, ls = e.var(rng.normal(size=(3, 1))), e.var(rng.uniform(-0.3, 0.3, 40))
+    e.bind(e.normal(y, e.dot(X, w), e.unary("exp", ls)))
+    v1 = e.autodiff(1.0)
+    a1 = [e.adj(w).copy(), e.adj(ls).copy()]
+    v2 = e.autodiff(0.0)
+    np.testing.assert_array_equal(v1, v2)
+    np.testing.assert_array_equal(e.adj(w), a1[0])
+    np.testing.assert_array_equal(e.adj(ls), a1[1])
+    e.beval(0.0)
+    np.testing.assert_array_equal(e.adj(w), a1[0])
 
 
 def test_expr_specialised_kernels_are_the_default_and_bit_identical_to_interpreter(fb):
