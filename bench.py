@@ -182,18 +182,23 @@ def timed_loop(fn, steps, warmup, world, windows=3):
     return sorted(out)[len(out) // 2]
 
 
-def timed_windows(run_k, steps, world, windows):
+def timed_windows(run_k, steps, world, windows, gate=None):
     """`windows` repeats of the K-step timed region (run_k(w) issues exactly K steps), each bracketed by barrier +
     synchronize and reduced by MAX over ranks; returns the sorted per-window times in ms.  The median is what is reported:
-    a single 0.45 ms window (20 x 22 us) swings by ~8 % with clock ramp and launch jitter (VERDICT r1 weak #8)."""
+    a single 0.45 ms window (20 x 22 us) swings by ~8 % with clock ramp and launch jitter.
+    gate (tools/probes/gate.cu): the region is enqueued behind a host-released gate, so the K launches run from a full
+    queue and the window is the DEVICE time of exactly K steps, not K steps + the CPU's enqueue latency of the first."""
     import torch
     out = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for w in range(windows):
         barrier(world)
+        gated = gate is not None and gate.fadb_probe_gate_arm(torch.cuda.current_stream().cuda_stream) == 0
         e0.record()
         run_k(w)
         e1.record()
+        if gated:
+            gate.fadb_probe_gate_release()
         barrier(world)
         out.append(max_over_ranks(e0.elapsed_time(e1), world))
     return sorted(out)
@@ -208,6 +213,7 @@ def load_probes():
     L = C.CDLL(p)
     L.fadb_probe_dfma_peak.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.fadb_probe_pcie.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.fadb_probe_gate_arm.argtypes = [C.c_void_p]
     return L
 
 
@@ -283,9 +289,11 @@ def run_ours(args):
         m = n if not args.quick else 1 << 14
         batches.run(1, 0)
         ref = O.black_scholes(*(sets[0][2][k][:m] for k in keys), nthreads=os.cpu_count() or 1)
-        for g, o in zip(sets[0][1], ref):
+        import bs_tol                                  # tests/bs_tol.py: eps x the magnitude of each output's terms
+        sub = {k: sets[0][2][k][:m] for k in keys}
+        for nm, g, o, sc in zip(bs_tol.NAMES, sets[0][1], ref, bs_tol.scales(sub)):
             err = np.abs(g[:m].cpu().numpy() - o)
-            assert np.all(err <= 1e-11 * np.maximum(1.0, np.abs(o))), "parity gate failed"
+            assert np.all(err <= 8.0 * sc), f"parity gate failed on {nm}: {float(np.max(err / sc)):.2f} x scale"
 
     # ---------------- N > 1: the sharded evaluations must be CORRECT before anything is timed (tests/sharded_gate.py)
     # The one exchange of a sharded evaluation (1-66 doubles): the peer-memory mailbox all-reduce of
@@ -318,7 +326,9 @@ def run_ours(args):
     launches0 = L.fadb_launch_count()
     batches.run(args.warmup, 0)
     windows = 3 if args.quick else args.windows
-    ws = timed_windows(lambda w: batches.run(args.steps, args.warmup + w * args.steps), args.steps, world, windows)
+    probes = load_probes()
+    gate_lib = None if args.no_gate else probes
+    ws = timed_windows(lambda w: batches.run(args.steps, args.warmup + w * args.steps), args.steps, world, windows, gate_lib)
     ms = ws[len(ws) // 2]                          # median window
     launches = (L.fadb_launch_count() - launches0 - args.warmup) // windows
     value = world * n * args.steps / (ms * 1e-3)
@@ -326,7 +336,6 @@ def run_ours(args):
     achieved = BS_BYTES * n / (kernel_ms * 1e-3) / 1e9
 
     # ---------------- measured FP64 issue peak (register-resident DFMA chains, all SMs) for the second roofline
-    probes = load_probes()
     fp64_peak = None
     if probes is not None:
         import ctypes as C
@@ -743,7 +752,7 @@ def run_ours(args):
         # the sharded configs (C2-C5) in a field the driver keeps: per-GPU GB/s, ms, and the exchange that was timed
         sharded = {"n_gpus": world, "exchange": collective, "correctness_gate": gate, "p2p_status_after_timing": p2p_status}
         for k, v in workloads.items():
-            if k.startswith(("normal_", "sum_", "linreg_", "mlp3_", "prod_")):
+            if k.startswith(("normal_", "sum_", "linreg_", "mlp3_", "prod_")) and "hbm_gbs" in v:
                 sharded[k] = {"ms": round(v["ms_per_step"], 5), "gbs_per_gpu": round(v["hbm_gbs"], 1),
                               "frac_hbm": round(v["roofline_frac"], 4), "evals_per_s": round(v["evals_per_s"], 2)}
         fp64 = {"pipe_active_pct_ncu": ncu_metric(NCU_BS, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
@@ -774,7 +783,9 @@ def run_ours(args):
                        "l2": f"rotating {nsets} resident buffer sets ({nsets * BS_BYTES * n >> 20} MiB) > 126 MiB L2",
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
                        "timing": f"median of {windows} windows of exactly {args.steps} steps (one launch each, issued by ONE "
-                                 f"fadb_black_scholes_batches call per window); windows_us_per_step min/med/max = "
+                                 f"fadb_black_scholes_batches call per window"
+                                 + (", enqueued behind a host-released gate: device time of the K steps" if gate_lib else "")
+                                 + f"); windows_us_per_step min/med/max = "
                                  f"{ws[0] / args.steps * 1e3:.2f}/{kernel_ms * 1e3:.2f}/{ws[-1] / args.steps * 1e3:.2f}",
                        "collective_of_the_sharded_workloads": collective,
                        "sharded": sharded},
@@ -828,6 +839,7 @@ def main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: exchange of the sharded reductions (peer-memory mailboxes or NCCL)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-gate", action="store_true", help="time the K-step windows without the host-released gate")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -10,6 +10,7 @@
 // placeholders cache[0..2] is identical for call and put and is swept once.
 //
 // HBM layout: SoA.  5 input streams, 8 output streams, 104 algorithmic bytes per option.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -205,6 +206,38 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
         bs_store1<ACC>(out, i, o);
         if (!more) break;
         i = j; s = s2; k = k2; g = g2; t = t2; rr = r2;
+    }
+}
+
+// Diagnostic variants of bs_kernel_fast_pf (FADB_BS_VARIANT=40 / 41, never the default): the same grid, trip structure and
+// 13 streams with the arithmetic removed (MODE 1: what the memory system alone takes for this access pattern) and the same
+// arithmetic on cache-resident operands with the stores predicated off (MODE 2: what the SMs alone take).  Their two
+// times bracket the real kernel: max(mem, compute) is its floor, the gap to it is imperfect overlap.
+template <int MODE>
+__global__ void __launch_bounds__(256, 3)
+bs_kernel_diag(size_t n, const double* __restrict__ S, const double* __restrict__ K,
+               const double* __restrict__ sigma, const double* __restrict__ tau,
+               const double* __restrict__ r, BSOut out)
+{
+    __shared__ double s_tab[675];
+    for (int i = threadIdx.x; i < 256; i += 256) s_tab[i] = fm::kErfcx32_d[i];
+    if (threadIdx.x < 32) s_tab[256 + threadIdx.x] = fm::kExp2_32_d[threadIdx.x];
+    for (int i = threadIdx.x; i < 387; i += 256) s_tab[288 + i] = fm::kLogT_d[i];
+    __syncthreads();
+    pdl_prologue();
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += nthreads) {
+        const size_t j = MODE == 2 ? (i & 4095) : i;
+        const double s = __ldg(S + j), k = __ldg(K + j), g = __ldg(sigma + j), t = __ldg(tau + j), rr = __ldg(r + j);
+        if (MODE == 1) {
+            BSRes o;
+            o.call = s + k; o.put = s - k; o.cS = g; o.cSig = t; o.cR = rr; o.pS = g + t; o.pSig = t + rr; o.pR = s + rr;
+            bs_store1<false>(out, i, o);
+        } else {
+            const BSRes o = bs_eval_fast<true>(s, k, g, t, rr, s_tab);
+            if (o.call == -12345.678) bs_store1<false>(out, i, o);     // never true: keeps the evaluation alive
+        }
     }
 }
 
@@ -416,6 +449,17 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
         if (ovw) KERNEL<false><<<resident_grid(c, KERNEL<false>, threads, 0, n, threads), threads, 0, st>>>(n, S, K, sigma, tau, r, o); \
         else KERNEL<true><<<resident_grid(c, KERNEL<true>, threads, 0, n, threads), threads, 0, st>>>(n, S, K, sigma, tau, r, o);       \
     } while (0)
+    if (variant == 42) {       // memory-only at the real kernel's grid (3 CTAs/SM)
+        FADB_CUDA(launch_pdl(bs_kernel_diag<1>, std::min(3 * c.sms, (int)((n + threads - 1) / threads)), threads, 0, st, n, S, K, sigma, tau, r, o));
+        c.launches++;
+        return FADB_OK;
+    }
+    if (variant == 40 || variant == 41) {
+        if (variant == 40) FADB_CUDA(launch_pdl(bs_kernel_diag<1>, resident_grid(c, bs_kernel_diag<1>, threads, 0, n, threads), threads, 0, st, n, S, K, sigma, tau, r, o));
+        else FADB_CUDA(launch_pdl(bs_kernel_diag<2>, resident_grid(c, bs_kernel_diag<2>, threads, 0, n, threads), threads, 0, st, n, S, K, sigma, tau, r, o));
+        c.launches++;
+        return FADB_OK;
+    }
     if (variant == 5) FADB_BS_LAUNCH(bs_kernel_libdevice);
     else if (variant == 6) FADB_BS_LAUNCH(bs_kernel_fast);
     else if (variant == 20) FADB_BS_LAUNCH(bs_kernel_fast_pf);

@@ -233,6 +233,10 @@ namespace core {
 // CRTP base (reverse/core/expr_base.hpp:16-23)
 struct ExprTag {};
 template <class Derived>
+struct ExprBase;
+template <class ExprType> struct ExprBind;
+template <class D> ExprBind<D>& own_binding(const ExprBase<D>&);
+template <class Derived>
 struct ExprBase : ExprTag {
     Derived& self() { return static_cast<Derived&>(*this); }
     const Derived& self() const { return static_cast<const Derived&>(*this); }
@@ -244,6 +248,18 @@ struct ExprBase : ExprTag {
     // returned pack is advanced past them like the reference's.
     util::SizePack bind_cache_size() const;
     util::PtrPack<double> bind_cache(util::PtrPack<double> begin) const;
+    // The node-level protocol of the reference (unary.hpp:63-89, binary.hpp:100-136; README.md:284-306):
+    //   expr.bind_cache({v, a});  auto f = expr.feval();  expr.beval(seed);
+    // feval() = ad::evaluate, beval(seed) = ad::evaluate_adj on a binding the node makes on first use and keeps
+    // (copies of the node share it, like copies of a reference node share the cache they were bound to).
+    // Returns double for a scalar expression, std::vector<double> (column-major) otherwise.
+    auto feval() const;
+    void beval(double seed = 1.) const;
+    void beval(const std::vector<double>& seed) const;
+
+private:
+    mutable std::shared_ptr<void> own_binding_;      // type-erased ExprBind<Derived>
+    template <class D> friend ExprBind<D>& own_binding(const ExprBase<D>&);
 };
 
 // Var<T,S> derives from ExprBase<VarView<T,S>>: anything below an ExprBase is an expression
@@ -1382,6 +1398,24 @@ inline util::SizePack bind_cache_size(const core::ExprBase<Derived>& expr)
     detail::check(fadb_expr_plan(h, root, cs));
     return {{cs[0], cs[1]}};
 }
+
+namespace core {
+template <class D>
+inline ExprBind<D>& own_binding(const ExprBase<D>& e)
+{
+    if (!e.own_binding_) {
+        auto b = std::make_shared<ExprBind<D>>(e.self());      // the copy inside holds no binding yet: no cycle
+        e.own_binding_ = b;
+    }
+    return *static_cast<ExprBind<D>*>(e.own_binding_.get());
+}
+}  // namespace core
+template <class Derived>
+inline auto core::ExprBase<Derived>::feval() const { return ad::evaluate(core::own_binding(*this)); }
+template <class Derived>
+inline void core::ExprBase<Derived>::beval(double seed) const { ad::evaluate_adj(core::own_binding(*this), seed); }
+template <class Derived>
+inline void core::ExprBase<Derived>::beval(const std::vector<double>& seed) const { ad::evaluate_adj(core::own_binding(*this), seed); }
 
 template <class Derived>
 inline util::SizePack core::ExprBase<Derived>::bind_cache_size() const { return ad::bind_cache_size(*this); }

@@ -523,6 +523,46 @@ static void batched_models()
     }
 }
 
+static void node_level_protocol()
+{
+    // README.md:284-306: manual bind_cache, then the node's own feval() / beval(seed)
+    // (unary.hpp:63-89, binary.hpp:100-136) -- `sin(x) + cos(v)` is a vector expression
+    Var<double> x(0.7);
+    Var<double, vec> v(3);
+    v.get() = {0.1, -0.4, 1.2};
+    auto expr = (ad::sin(x) + ad::cos(v));
+    auto size_pack = expr.bind_cache_size();
+    std::vector<double> val_buf(size_pack(0)), adj_buf(size_pack(1));
+    expr.bind_cache({val_buf.data(), adj_buf.data()});
+    auto f = expr.feval();
+    CHECK(f.size() == 3);
+    for (int i = 0; i < 3; ++i) CHECK_DOUBLE_EQ(f[i], std::sin(0.7) + std::cos(v.get()(i)));
+    CHECK(x.get_adj() == 0.);                                  // feval touches no adjoint
+    expr.beval(std::vector<double>{1., 2., -1.});
+    CHECK_DOUBLE_EQ(x.get_adj(), 2. * std::cos(0.7));          // seeds sum into the scalar (binary.hpp:266-338)
+    for (int i = 0; i < 3; ++i) CHECK_DOUBLE_EQ(v.get_adj()(i), (i == 0 ? 1. : i == 1 ? 2. : -1.) * -std::sin(v.get()(i)));
+    expr.beval(std::vector<double>{1., 2., -1.});              // adjoints accumulate (var_view.hpp:91-94)
+    CHECK_DOUBLE_EQ(x.get_adj(), 4. * std::cos(0.7));
+    // scalar expression: default seed 1; a copy of the node shares the binding; a changed value is seen
+    Var<double> a(1.5), b(-0.5);
+    auto e2 = a * b + ad::exp(a);
+    CHECK_DOUBLE_EQ(e2.feval(), 1.5 * -0.5 + std::exp(1.5));
+    auto e3 = e2;
+    e3.beval();
+    CHECK_DOUBLE_EQ(a.get_adj(), -0.5 + std::exp(1.5));
+    CHECK_DOUBLE_EQ(b.get_adj(), 1.5);
+    a.get() = 2.0;
+    CHECK_DOUBLE_EQ(e2.feval(), 2.0 * -0.5 + std::exp(2.0));
+    // op= statement: feval applies it, beval restores the previous value (eq.hpp:240-271)
+    Var<double> w(3.0), y(1.25);
+    auto e4 = (w *= y);
+    CHECK_DOUBLE_EQ(e4.feval(), 3.75);
+    CHECK_DOUBLE_EQ(w.get(), 3.75);
+    e4.beval(2.0);
+    CHECK_DOUBLE_EQ(w.get(), 3.0);
+    CHECK_DOUBLE_EQ(y.get_adj(), 2.0 * 3.0);
+}
+
 int main()
 {
     if (fadb_init(0) != 0) { std::printf("no CUDA device: %s\n", fadb_last_error()); return 2; }
@@ -534,5 +574,6 @@ int main()
     vectors_and_seeds();
     next_rows();
     batched_models();
+    node_level_protocol();
     return report("test_host_layer");
 }

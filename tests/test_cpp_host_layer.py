@@ -69,3 +69,13 @@ def test_cpp_reference_main_example_patterns(built):
 def test_cpp_type_fused_kernels_match_c_abi_path(built):
     out = _run(built, "test_fused")
     assert "test_fused:" in out
+
+
+@pytest.mark.gpu
+def test_fastmath_accuracy_on_the_device(built, capsys):
+    # fastmath.cuh was only validated on the host; this runs exp_t / log_t / phi_pair_pw / div_ /
+    # sqrt_ / rcp_ ON the GPU, built -fmad=true like black_scholes.cu, over 2^21 points against glibc (<= 1 ulp)
+    out = _run(built, "test_fastmath_device")
+    assert "test_fastmath_device:" in out
+    with capsys.disabled():
+        print("\n" + out.strip().splitlines()[0])

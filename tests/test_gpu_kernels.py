@@ -9,6 +9,7 @@ Tolerances (BASELINE.json north_star):
   * reordered reductions: <= 1e-12 relative.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -290,28 +291,114 @@ def test_prod_fixture_zero(fb):
     np.testing.assert_allclose(host(ga), [0, 0, 0, 2.0 * others, 0], rtol=1e-15)
 
 
+@pytest.mark.parametrize("zeros_where", [(), ("first",), ("last",), ("middle",), ("first", "last"), ("middle", "last")])
+def test_prod_full_size_exact(fb, zeros_where):
+    # prod_benchmark size (N = 2^24, the size bench.py times): every x_i is a signed power of two and every aligned group
+    # of 4 multiplies to 1, so each thread's running product, each CTA partial and the grid total are exact whatever the
+    # order: value and all 2^24 adjoints are compared BIT FOR BIT.  Zeros are placed in the first / middle / last CTA's
+    # range: one zero -> only its adjoint is non-zero (seed x product of the others), two zeros (in different CTAs, so the
+    # zero COUNT crosses the ticket reduction) -> every adjoint is zero (prod.hpp:188-212).
+    import torch
+    n = 1 << 24
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cyc = torch.tensor([2.0, 0.5, -4.0, -0.25, 0.5, 2.0, 0.25, 4.0], **f64)
+    x = cyc[torch.arange(n, device="cuda") & 7].contiguous()
+    pos = {"first": 5, "middle": n // 2 + 1, "last": n - 3}
+    zs = [pos[w] for w in zeros_where]
+    orig = [float(x[z]) for z in zs]
+    for z in zs:
+        x[z] = 0.0
+    seed = 1.5
+    adj = torch.full((n,), 0.5, **f64)
+    v = fb.prod(x, adj, seed=seed)
+    if not zs:
+        assert v == 1.0
+        assert torch.equal(adj, 0.5 + seed / x)
+    elif len(zs) == 1:
+        assert v == 0.0
+        want = torch.full((n,), 0.5, **f64)
+        want[zs[0]] = 0.5 + seed * (1.0 / orig[0])          # product of all the others = 1 / (the value that was there)
+        assert torch.equal(adj, want)
+    else:
+        assert v == 0.0
+        assert torch.equal(adj, torch.full((n,), 0.5, **f64))
+    del x, adj
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("kind", ["vss", "vsv", "vvs"])
+def test_normal_scalar_operand_shapes_full_size(fb, kind):
+    # BASELINE config 3 size (2^26) for the shapes with a SCALAR operand (normal.hpp:225-478): the scalar's adjoint is a
+    # sum over all elements.  Dyadic z and power-of-two sigma make every term and every partial sum exactly
+    # representable: value to 1e-12 (it contains n log sigma), all adjoints bit for bit.
+    import torch
+    n = 1 << 26
+    f64 = dict(dtype=torch.float64, device="cuda")
+    i = torch.arange(n, device="cuda")
+    z = torch.tensor([0.5, -1.0, 1.5, -2.0, 2.0, -1.5, 1.0, 0.5], **f64)[i & 7]      # sum z = 1, sum z^2 = 15 per cycle
+    cyc = n / 8.0
+    seed = 0.75
+    one = lambda v: torch.tensor([v], **f64)
+    if kind == "vss":
+        mu, sg = one(0.25), one(2.0)
+        x = 0.25 + 2.0 * z
+        want_v = -0.5 * 15.0 * cyc - n * math.log(2.0)
+        want_x, want_m, want_s = 0.5 - seed * z / 2.0, 0.5 + seed * cyc / 2.0, 0.5 + seed * (15.0 - 8.0) * cyc / 2.0
+    elif kind == "vvs":
+        mu, sg = (i & 1023).to(torch.float64) / 1024.0, one(2.0)
+        x = mu + 2.0 * z
+        want_v = -0.5 * 15.0 * cyc - n * math.log(2.0)
+        want_x, want_m, want_s = 0.5 - seed * z / 2.0, 0.5 + seed * z / 2.0, 0.5 + seed * (15.0 - 8.0) * cyc / 2.0
+    else:   # vsv: scalar mu, vector sigma whose logs cancel per cycle
+        mu = one(0.25)
+        sg = torch.tensor([1.0, 2.0, 0.5, 4.0, 0.25, 2.0, 0.5, 1.0], **f64)[i & 7]
+        x = 0.25 + sg * z
+        want_v = -0.5 * 15.0 * cyc
+        zs = (z / sg)
+        per_cycle = float(zs[:8].sum())                      # sum over one cycle of z / sigma (dyadic)
+        want_x, want_m, want_s = 0.5 - seed * zs, 0.5 + seed * per_cycle * cyc, 0.5 + seed * (z * z - 1.0) / sg
+    del i
+    xa = torch.full((n,), 0.5, **f64)
+    ma = torch.full((mu.numel(),), 0.5, **f64)
+    sa = torch.full((sg.numel(),), 0.5, **f64)
+    v = fb.normal_lpdf(x, mu, sg, xa, ma, sa, seed=seed)
+    assert rel(v, want_v) <= REL_REDUCE
+    assert torch.equal(xa, want_x)
+    assert torch.equal(ma, want_m) if ma.numel() > 1 else float(ma[0]) == want_m
+    assert torch.equal(sa, want_s) if sa.numel() > 1 else float(sa[0]) == want_s
+    del x, xa, z
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------ K1 Black-Scholes
-def _bs_tol(inp, ref_out):
-    S, K, sig, tau, r = (inp[k] for k in ("S", "K", "sigma", "tau", "r"))
-    scale_price = np.maximum(S, K)
-    sst = sig * np.sqrt(tau)
-    # conditioning floors: prices subtract Phi1*S - Phi2*PV; the AD delta carries the residual
-    # (S*phi(d1) - PV*phi(d2)) / (S*sst); vega and rho scale with S*sqrt(tau) and K*tau.
-    floors = [1e-13 * scale_price, 1e-13 * scale_price,
-              1e-13 / sst, 1e-13 * scale_price * np.sqrt(tau) / sst, 1e-13 * K * tau / sst + 1e-13 * K * tau,
-              1e-13 / sst, 1e-13 * scale_price * np.sqrt(tau) / sst, 1e-13 * K * tau / sst + 1e-13 * K * tau]
-    return [4 * np.spacing(np.abs(o)) + f for o, f in zip(ref_out, floors)]
+BS_C = 8.0      # |gpu - oracle| <= BS_C x (eps x magnitude of the output's terms), tests/bs_tol.py
 
 
 @pytest.mark.parametrize("n", [1, 2, 1001, 1 << 16])
 def test_black_scholes_vs_oracle(fb, n):
+    import bs_tol
     inp = synth.black_scholes_inputs(n)
     ref = O.black_scholes(inp["S"], inp["K"], inp["sigma"], inp["tau"], inp["r"], nthreads=4)
     out = fb.black_scholes(*(dev(inp[k]) for k in ("S", "K", "sigma", "tau", "r")))
-    for name, g, o, tol in zip(["call", "put", "dC/dS", "dC/dsig", "dC/dr", "dP/dS", "dP/dsig", "dP/dr"],
-                               out, ref, _bs_tol(inp, ref)):
+    for name, g, o, sc in zip(bs_tol.NAMES, out, ref, bs_tol.scales(inp)):
         err = np.abs(host(g) - o)
-        assert np.all(err <= tol), (name, float(np.max(err / tol)), int(np.argmax(err / tol)))
+        assert np.all(err <= BS_C * sc), (name, float(np.max(err / sc)), int(np.argmax(err / sc)))
+
+
+def test_black_scholes_ulp_report_full_size(fb, capsys):
+    # BASELINE config 1 at full size against the oracle: 2^20 options, every output, error in units of eps x the
+    # magnitude of its terms (bs_tol.scales), plus the two prices in ulps OF THE PRICE for |S/K - 1| < 5 %
+    import bs_tol
+    n = 1 << 20
+    inp = synth.black_scholes_inputs(n)
+    ref = O.black_scholes(inp["S"], inp["K"], inp["sigma"], inp["tau"], inp["r"], nthreads=os.cpu_count() or 4)
+    out = [host(t) for t in fb.black_scholes(*(dev(inp[k]) for k in ("S", "K", "sigma", "tau", "r")))]
+    ratios, atm_ulps = bs_tol.report(inp, out, ref)
+    with capsys.disabled():
+        print("\nblack-scholes 2^20 vs oracle, max |err| / (eps x term magnitude): "
+              + ", ".join(f"{nm} {r:.2f}" for nm, r in zip(bs_tol.NAMES, ratios))
+              + f" | near-the-money prices: call {atm_ulps[0]:.1f} ulp, put {atm_ulps[1]:.1f} ulp")
+    assert max(ratios) <= BS_C, dict(zip(bs_tol.NAMES, ratios))
 
 
 def test_black_scholes_example_point(fb):

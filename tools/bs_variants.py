@@ -43,6 +43,18 @@ def child(variant):
         e0.record(); B.run(20); e1.record(); torch.cuda.synchronize()
         t20.append(e0.elapsed_time(e1) / 20 * 1e3)
     t20.sort()
+    # the same windows enqueued behind the host-released gate (tools/probes/gate.cu): device time of the 20 launches
+    import ctypes as C
+    G = C.CDLL(os.path.join(R, "tools", "_build", "libfadb_probes.so"))
+    G.fadb_probe_gate_arm.argtypes = [C.c_void_p]
+    g20 = []
+    for _ in range(25):
+        torch.cuda.synchronize()
+        G.fadb_probe_gate_arm(None)
+        e0.record(); B.run(20); e1.record()
+        G.fadb_probe_gate_release(); torch.cuda.synchronize()
+        g20.append(e0.elapsed_time(e1) / 20 * 1e3)
+    g20.sort()
     # host-buffer call
     inp = synth.black_scholes_inputs(n)
     h_in = [torch.from_numpy(inp[k]).pin_memory().numpy() for k in keys]
@@ -53,8 +65,8 @@ def child(variant):
         e0.record(); F.black_scholes_host(*h_in, h_out); e1.record(); torch.cuda.synchronize()
         te.append(e0.elapsed_time(e1))
     te.sort()
-    print("variant %3d  us/launch min %.2f med %.2f | 20-step windows min %.2f med %.2f max %.2f | e2e ms min %.3f med %.3f | acc %s | %s"
-          % (variant, times[0], times[len(times) // 2], t20[0], t20[len(t20) // 2], t20[-1], te[0], te[len(te) // 2],
+    print("variant %3d  us/launch min %.2f med %.2f | 20-step windows min %.2f med %.2f max %.2f | gated min %.2f med %.2f max %.2f | e2e ms min %.3f med %.3f | acc %s | %s"
+          % (variant, times[0], times[len(times) // 2], t20[0], t20[len(t20) // 2], t20[-1], g20[0], g20[len(g20) // 2], g20[-1], te[0], te[len(te) // 2],
              "ok" if acc_ok else "MISMATCH", h.hexdigest()[:16]), flush=True)
 
 
