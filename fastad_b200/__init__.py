@@ -51,6 +51,7 @@ SIGNATURES = {
     "fadb_host_unregister": (_i, [_vp]),
     "fadb_black_scholes": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _u]),
     "fadb_black_scholes_host": (_i, [_sz, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "fadb_black_scholes_host_mode": (_i, [_dp]),
     "fadb_black_scholes_batches": (_i, [_sz, _sz, _sz, _sz, C.POINTER(_vp), C.POINTER(_vp), _u]),
     "fadb_sum_unary": (_i, [_i, _sz, _vp, _vp, _d, _u, _dp]),
     "fadb_sum_unary_async": (_i, [_i, _sz, _vp, _vp, _d, _u, _vp]),

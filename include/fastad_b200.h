@@ -113,6 +113,10 @@ int fadb_black_scholes_batches(size_t count, size_t n, size_t nsets, size_t firs
 int fadb_black_scholes_host(size_t n, const double* host_S, const double* host_K,
                             const double* host_sigma, const double* host_tau,
                             const double* host_r, double* const host_out[8]);
+/* the transfer scheme the call above currently uses on this device: 1 = one launch over PCIe on page-locked arrays, 0 = staged
+ * through the copy engines, -1 = still measuring (it times both on its first six calls and keeps the faster;
+ * FADB_BS_HOST_MODE=0/1 pins it); out_ms[2] (may be NULL) = best call time seen for {staged, direct}, -1 if not measured */
+int fadb_black_scholes_host_mode(double out_ms[2]);
 
 /* ------------------------------------------------------------------ K2: sum of a unary map
  * autodiff of ad::sum(f(x)) for a VarView x (sum.hpp:129-203 over unary.hpp:32-120 /

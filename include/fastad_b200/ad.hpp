@@ -1314,21 +1314,21 @@ inline void evaluate_adj(core::ExprBind<E>& b, double seed = 1.)
 {
     b.before();
     detail::check(fadb_expr_beval(b.handle(), seed, nullptr));
-    b.after(false, true);
+    b.after(true, true);      // values too: the sweep of `w op= expr` puts the previous value back into w (eq.hpp:262-271)
 }
 template <class E>
 inline void evaluate_adj(core::ExprBind<E>& b, const std::vector<double>& seed)
 {
     b.before();
     detail::check(fadb_expr_beval(b.handle(), 0., b.stage_seed(seed)));
-    b.after(false, true);
+    b.after(true, true);      // values too: the sweep of `w op= expr` puts the previous value back into w (eq.hpp:262-271)
 }
 template <class E>
 inline void evaluate_adj(core::ExprBind<E>& b, device_seed seed)
 {
     b.before();
     detail::check(fadb_expr_beval(b.handle(), 0., seed.ptr));
-    b.after(false, true);
+    b.after(true, true);      // values too: the sweep of `w op= expr` puts the previous value back into w (eq.hpp:262-271)
 }
 
 template <class E, class = std::enable_if_t<util::is_scl_v<E>>>
