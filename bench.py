@@ -34,6 +34,7 @@ BS_WORKLOAD = ("black_scholes call+put price + delta/vega/rho (example/black_sch
                "batch 2^20 options per GPU per step")
 BS_BYTES = 104            # algorithmic bytes per option: 5 in + 8 out doubles
 L2_BYTES = 126 * (1 << 20)
+NCCL_LOG_DIR = os.environ.get("FADB_NCCL_LOG_DIR", "/tmp/fadb_nccl_logs")
 # committed `ncu --set full` summary of the headline kernel (profiles/): this round's capture, else round 1's
 NCU_BS = next((f for f in ("r2_ncu_full_bs.csv", "r1_ncu_full_bs.csv")
                if os.path.exists(os.path.join(ROOT, "profiles", f))), "r2_ncu_full_bs.csv")
@@ -134,10 +135,12 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        # NCCL's INFO log (rank / nranks lines the driver checks) goes to stderr: stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        # NCCL's INFO log is NOT silenced: it goes to a file per process (stdout stays the one JSON
+        # line); rank 0 copies the communicator lines (rank / nranks) to stderr at the end of the run.
+        os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(NCCL_LOG_DIR, "nccl_%h_%p.log")
+        os.makedirs(NCCL_LOG_DIR, exist_ok=True)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -829,6 +832,20 @@ def run_ours(args):
             peer.close()
         dist.destroy_process_group()
     if stderr_tail:
+        if world > 1:      # the communicator lines of NCCL's INFO log (every rank's "... rank r nranks N ..." init line)
+            import glob
+            seen = 0
+            for f in sorted(glob.glob(os.path.join(NCCL_LOG_DIR, "nccl_*.log")), key=os.path.getmtime)[-world:]:
+                for ln in open(f, errors="replace"):
+                    if "nranks" in ln and "Init COMPLETE" in ln and seen < 16:
+                        print(ln.rstrip()[:300], file=sys.stderr)
+                        seen += 1
+            if not seen:
+                for f in sorted(glob.glob(os.path.join(NCCL_LOG_DIR, "nccl_*.log")), key=os.path.getmtime)[-world:]:
+                    for ln in open(f, errors="replace"):
+                        if "nranks" in ln and seen < 16:
+                            print(ln.rstrip()[:300], file=sys.stderr)
+                            seen += 1
         print(stderr_tail[:1000], file=sys.stderr, flush=True)
 
 

@@ -288,6 +288,113 @@ dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda
     gemm_tile<BT, TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
 }
 
+// ---- the same tile on the FP64 TENSOR cores (BASELINE.json north_star: "FP64 DMMA ... only if ncu shows they pay").
+// mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4): one warp instruction does 8 x 8 x 4 = 256 FMAs against 32 for a DFMA, with
+// A / B fragments of ONE double per thread -- the register-tiled kernel above spends one LDS.128 per 4 FMAs on operand
+// traffic and 2 operand registers per FMA, this one one LDS.64 per 21 FMAs.  Same staging (global -> registers -> shared,
+// double-buffered), same kmode / lower_only tile skipping, same epilogue; only the summation order inside a tile differs.
+// 8 warps as WM x WN, each owning MT x NT fragments of 8 x 8.  Shared rows are padded to SS = BT + 4 doubles: the fragment
+// loads As[k + lane % 4][m + lane / 4] of a half-warp then fall on 16 distinct bank pairs (row stride = 8 banks mod 32).
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int BT, bool TA, bool TB>
+__device__ __forceinline__ void gemm_tile_mma(int bi, int bj, int m, int n, int k, double alpha, const double* __restrict__ A,
+                                              int lda, const double* __restrict__ B, int ldb, double beta, double* C, int ldc,
+                                              int kmode, int lower_only)
+{
+    constexpr int BK = BT == 128 ? 8 : 16, SS = BT + 4, NL = BT * BK / 256;
+    constexpr int WM = BT == 128 ? 4 : 2, WN = 8 / WM, MT = BT / WM / 8, NT = BT / WN / 8;
+    __shared__ __align__(16) double As[2][BK][SS], Bs[2][BK][SS];
+    if (lower_only && bj > bi) return;
+    const int i0 = bi * BT, j0 = bj * BT;
+    if (i0 >= m || j0 >= n) return;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int wm = w % WM, wn = w / WM, g = lane >> 2, q4 = lane & 3;
+    int kb = 0, ke = k;
+    if (kmode == 1) kb = j0;
+    else if (kmode == 2) ke = min(k, i0 + BT);
+    else if (kmode == 3) kb = max(i0, j0);
+    kb &= ~(BK - 1);
+    double acc[MT][NT][2] = {};
+    double ra[NL], rb[NL];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const int e = t + u * 256;
+            const int ii = TA ? e / BK : e % BT, kk = TA ? e % BK : e / BT;
+            const int gi = i0 + ii, gk = k0 + kk;
+            ra[u] = (gi < m && gk < ke) ? (TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda]) : 0.0;
+            const int jj = TB ? e % BT : e / BK, kq = TB ? e / BT : e % BK;
+            const int gj = j0 + jj, gq = k0 + kq;
+            rb[u] = (gj < n && gq < ke) ? (TB ? B[gj + (size_t)gq * ldb] : B[gq + (size_t)gj * ldb]) : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const int e = t + u * 256;
+            As[buf][TA ? e % BK : e / BT][TA ? e / BK : e % BT] = ra[u];
+            Bs[buf][TB ? e / BT : e % BK][TB ? e % BT : e / BK] = rb[u];
+        }
+    };
+    gload(kb);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kb; k0 < ke; k0 += BK) {
+        const bool more = k0 + BK < ke;
+        if (more) gload(k0 + BK);
+#pragma unroll
+        for (int q = 0; q < BK; q += 4) {
+            double a[MT], b[NT];
+#pragma unroll
+            for (int u = 0; u < MT; ++u) a[u] = As[buf][q + q4][wm * (MT * 8) + u * 8 + g];
+#pragma unroll
+            for (int v = 0; v < NT; ++v) b[v] = Bs[buf][q + q4][wn * (NT * 8) + v * 8 + g];
+#pragma unroll
+            for (int u = 0; u < MT; ++u)
+#pragma unroll
+                for (int v = 0; v < NT; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+        }
+        if (more) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NT; ++v)
+#pragma unroll
+        for (int u = 0; u < MT; ++u)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + wm * (MT * 8) + u * 8 + g, j = j0 + wn * (NT * 8) + v * 8 + q4 * 2 + h;
+                if (i < m && j < n && (!lower_only || i >= j)) {
+                    double* c = C + i + (size_t)j * ldc;
+                    *c = (beta == 0.0) ? alpha * acc[u][v][h] : fma(alpha, acc[u][v][h], beta * *c);
+                }
+            }
+}
+
+template <int BT, bool TA, bool TB>
+__global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
+dn_gemm_mma(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+            double beta, double* C, int ldc, int kmode, int lower_only)
+{
+    gemm_tile_mma<BT, TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+}
+
+// FADB_GEMM_DMMA=0 selects the DFMA register-tiled kernels everywhere (A/B runs); default: tensor cores
+static inline bool use_dmma()
+{
+    static const bool on = [] { const char* e = getenv("FADB_GEMM_DMMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // ---- batched triangular inversion.  Node z of the recursion tree owns W[off : off+n1+n2]^2 =
 // [A 0; B C] with A^-1 (n1 x n1) and C^-1 (n2 x n2) already in place; all nodes of equal height are
 // independent, so one launch handles a whole level:  phase 0: T_z = B A^-1,  phase 1: B <- -C^-1 T_z.
@@ -306,6 +413,20 @@ dn_trtri_level(int n, double* W, double* T, const TrNode* __restrict__ nodes, in
         gemm_tile<BT, false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n1, 1.0, Bm, n, Ainv, n, 0.0, Tz, nd.n2, 1, 0);
     else
         gemm_tile<BT, false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n2, -1.0, Cinv, n, Tz, nd.n2, 0.0, Bm, n, 2, 0);
+}
+template <int BT>
+__global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
+dn_trtri_level_mma(int n, double* W, double* T, const TrNode* __restrict__ nodes, int phase)
+{
+    const TrNode nd = nodes[blockIdx.z];
+    double* Ainv = W + nd.off + (size_t)nd.off * n;
+    double* Bm = W + (nd.off + nd.n1) + (size_t)nd.off * n;
+    double* Cinv = W + (nd.off + nd.n1) + (size_t)(nd.off + nd.n1) * n;
+    double* Tz = T + nd.toff;
+    if (phase == 0)
+        gemm_tile_mma<BT, false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n1, 1.0, Bm, n, Ainv, n, 0.0, Tz, nd.n2, 1, 0);
+    else
+        gemm_tile_mma<BT, false, false>(blockIdx.x, blockIdx.y, nd.n2, nd.n1, nd.n2, -1.0, Cinv, n, Tz, nd.n2, 0.0, Bm, n, 2, 0);
 }
 
 __global__ void dn_symmetrize(int n, double* X)
@@ -379,10 +500,12 @@ static void gemm(Context& c, int m, int n, int k, double alpha, const double* A,
     const long long t128 = (long long)((m + 127) / 128) * ((n + 127) / 128) / (lower_only ? 2 : 1);
     if (big_tiles(c, t128)) {
         dim3 grid((m + 127) / 128, (n + 127) / 128);
-        dn_gemm<128, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        if (use_dmma()) dn_gemm_mma<128, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        else dn_gemm<128, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
     } else {
         dim3 grid((m + 63) / 64, (n + 63) / 64);
-        dn_gemm<64, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        if (use_dmma()) dn_gemm_mma<64, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        else dn_gemm<64, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
     }
     c.launches++;
 }
@@ -506,12 +629,22 @@ static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const d
         const long long t128 = (long long)((lv.max_n2 + 127) / 128) * ((lv.max_n1 + 127) / 128) * lv.count;
         if (big_tiles(*c, t128)) {
             dim3 grid((lv.max_n2 + 127) / 128, (lv.max_n1 + 127) / 128, lv.count);
-            dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-            dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            if (use_dmma()) {
+                dn_trtri_level_mma<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+                dn_trtri_level_mma<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            } else {
+                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            }
         } else {
             dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
-            dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-            dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            if (use_dmma()) {
+                dn_trtri_level_mma<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+                dn_trtri_level_mma<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            } else {
+                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
+                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+            }
         }
         c->launches += 2;
     }
