@@ -38,7 +38,8 @@ NCCL_LOG_DIR = os.environ.get("FADB_NCCL_LOG_DIR", "/tmp/fadb_nccl_logs")
 # committed `ncu --set full` summary of the headline kernel (profiles/): this round's capture, else round 1's
 NCU_BS = next((f for f in ("r2_ncu_full_bs.csv", "r1_ncu_full_bs.csv")
                if os.path.exists(os.path.join(ROOT, "profiles", f))), "r2_ncu_full_bs.csv")
-BS_KERNEL = "bs_kernel_fast_pf<false, true, 3>"
+BS_KERNEL = ("bs_kernel_fast_pf<false, true, 3, 256, PDL_EARLY> (batch 0 of each K-step call: the PDL_HEAD instantiation, "
+             "same code with the dependency wait at its start)")
 
 
 def ncu_traffic(name):

@@ -179,7 +179,18 @@ bs_kernel_fast(size_t n, const double* __restrict__ S, const double* __restrict_
 
 // software-pipelined variant: the next option's inputs are loaded before the current one is
 // evaluated, so the ~800-cycle load latency overlaps the ~2000-cycle evaluation of the same thread
-template <bool ACC, bool PW = false, int MINB = 2, int THREADS = 256>
+// EARLY (batches 1.. of fadb_black_scholes_batches, never the first kernel of a call): the previous grid on the stream is
+// this same kernel working on ANOTHER operand set, so nothing this grid reads or writes depends on it.  The grid then
+// skips the dependency wait at its start -- its CTAs begin streaming as soon as the previous grid's CTAs free their
+// slots, instead of idling until the slowest CTA of the previous grid has retired (the ~1.5 us bubble per launch that
+// separates the kernel at 2^20 options from its own steady state at 2^24) -- and executes the wait at its END, so that
+// its completion still implies the completion (and visibility) of every grid before it: what follows on the stream
+// sees exactly the ordinary stream order.
+// The batch AHEAD of such a chain (PDL_HEAD) waits first and only then lets its dependents launch: the early grids behind
+// it can therefore never run before whatever preceded the call on the stream (possibly the producer of the inputs, possibly
+// itself a kernel that triggers early) has completed and is visible.
+enum : int { PDL_PLAIN = 0, PDL_EARLY = 1, PDL_HEAD = 2 };
+template <bool ACC, bool PW = false, int MINB = 2, int THREADS = 256, int PDL = PDL_PLAIN>
 __global__ void __launch_bounds__(THREADS, MINB)
 bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restrict__ K,
                   const double* __restrict__ sigma, const double* __restrict__ tau,
@@ -192,22 +203,26 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
         for (int i = threadIdx.x; i < 387; i += THREADS) s_tab[288 + i] = fm::kLogT_d[i];
         __syncthreads();
     }
-    pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
+    if (PDL == PDL_EARLY) cudaTriggerProgrammaticLaunchCompletion();
+    else if (PDL == PDL_HEAD) { cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion(); }
+    else pdl_prologue();      // common.cuh: no memory access before the previous grid on the stream has completed
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     size_t i = tid;
-    if (i >= n) return;
-    double s = __ldg(S + i), k = __ldg(K + i), g = __ldg(sigma + i), t = __ldg(tau + i), rr = __ldg(r + i);
-    while (true) {
-        const size_t j = i + nthreads;
-        const bool more = j < n;
-        double s2 = 0, k2 = 1, g2 = 1, t2 = 1, r2 = 0;
-        if (more) { s2 = __ldg(S + j); k2 = __ldg(K + j); g2 = __ldg(sigma + j); t2 = __ldg(tau + j); r2 = __ldg(r + j); }
-        const BSRes o = bs_eval_fast<PW>(s, k, g, t, rr, s_tab);
-        bs_store1<ACC>(out, i, o);
-        if (!more) break;
-        i = j; s = s2; k = k2; g = g2; t = t2; rr = r2;
+    if (i < n) {
+        double s = __ldg(S + i), k = __ldg(K + i), g = __ldg(sigma + i), t = __ldg(tau + i), rr = __ldg(r + i);
+        while (true) {
+            const size_t j = i + nthreads;
+            const bool more = j < n;
+            double s2 = 0, k2 = 1, g2 = 1, t2 = 1, r2 = 0;
+            if (more) { s2 = __ldg(S + j); k2 = __ldg(K + j); g2 = __ldg(sigma + j); t2 = __ldg(tau + j); r2 = __ldg(r + j); }
+            const BSRes o = bs_eval_fast<PW>(s, k, g, t, rr, s_tab);
+            bs_store1<ACC>(out, i, o);
+            if (!more) break;
+            i = j; s = s2; k = k2; g = g2; t = t2; rr = r2;
+        }
     }
+    if (PDL == PDL_EARLY && threadIdx.x == 0) cudaGridDependencySynchronize();     // the CTA retires only after the previous grid has
 }
 
 // Diagnostic variants of bs_kernel_fast_pf (FADB_BS_VARIANT=40 / 41, never the default): the same grid, trip structure and
@@ -421,7 +436,7 @@ static int launch_bs_tma(Context& c, cudaStream_t st, size_t n, const double* S,
 // 444 CTAs 1.62 ms, 296 1.57, 148 1.54, 74 1.52, 24-48 1.506, 16 1.53, 8 1.56 (FADB_BS_HOST_GRID)
 int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S, const double* K,
                          const double* sigma, const double* tau, const double* r,
-                         double* const out[8], unsigned flags, bool host_mapped = false)
+                         double* const out[8], unsigned flags, bool host_mapped = false, int pdl_mode = PDL_PLAIN)
 {
     BSOut o;
     bool vec_ok = (((uintptr_t)S | (uintptr_t)K | (uintptr_t)sigma | (uintptr_t)tau |
@@ -521,6 +536,12 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
     } while (0)
         } else if (variant == 21) { FADB_BS_PW(2);
         } else if (variant == 24) { FADB_BS_PW(4);
+        } else if (pdl_mode == PDL_EARLY && ovw && !host_mapped && pdl_enabled()) {
+            auto kern = bs_kernel_fast_pf<false, true, 3, 256, PDL_EARLY>;
+            FADB_CUDA(launch_pdl(kern, resident_grid(c, kern, threads, 0, n, threads), threads, 0, st, n, S, K, sigma, tau, r, o));
+        } else if (pdl_mode == PDL_HEAD && ovw && !host_mapped && pdl_enabled()) {
+            auto kern = bs_kernel_fast_pf<false, true, 3, 256, PDL_HEAD>;
+            FADB_CUDA(launch_pdl(kern, resident_grid(c, kern, threads, 0, n, threads), threads, 0, st, n, S, K, sigma, tau, r, o));
         } else { FADB_BS_PW(3);
         }
     }
@@ -564,10 +585,15 @@ extern "C" int fadb_black_scholes_batches(size_t count, size_t n, size_t nsets, 
     Context* c;
     int rc = current_context(&c);
     if (rc) return rc;
+    // Batches 1.. start without waiting for the previous batch's grid (see bs_kernel_fast_pf<EARLY>): allowed when consecutive
+    // batches work on DIFFERENT operand sets (nsets >= 2: the caller's sets must not alias each other) and results are
+    // stored, not accumulated.  FADB_BS_EARLY=0 keeps every batch on the ordinary wait-first kernel.
+    static const bool early_ok = [] { const char* e = getenv("FADB_BS_EARLY"); return !(e && e[0] == '0'); }();
+    const bool can_early = early_ok && nsets >= 2 && (flags & FADB_OVERWRITE_ADJ);
     for (size_t b = 0; b < count; ++b) {
         const size_t s = (first_set + b) % nsets;
         rc = launch_black_scholes(*c, c->stream, n, in[5 * s], in[5 * s + 1], in[5 * s + 2], in[5 * s + 3], in[5 * s + 4],
-                                  out + 8 * s, flags);
+                                  out + 8 * s, flags, false, !can_early || count < 2 ? PDL_PLAIN : (b > 0 ? PDL_EARLY : PDL_HEAD));
         if (rc) return rc;
     }
     return FADB_OK;

@@ -111,6 +111,12 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
     __shared__ double t32[TAB ? 32 : 1];
     __shared__ double red[THREADS / 32][NOUT];
     __shared__ bool is_last;
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    // the first row's inputs are requested BEFORE the parameter copy and its barrier: one DRAM round trip instead of two
+    // on the critical path of the small-batch launch (one row per thread, latency-bound)
+    double xa0 = 0.0, xb0 = 0.0, yy0 = 0.0;
+    if (ROWS == 1 && tid < batch) { xa0 = __ldg(X + tid); xb0 = __ldg(X + batch + tid); yy0 = __ldg(y + tid); }
     if (threadIdx.x < NP) p[threadIdx.x] = parm[threadIdx.x];
     if (TAB && threadIdx.x >= 32 && threadIdx.x < 64) t32[threadIdx.x - 32] = fm::kExp2_32_d[threadIdx.x - 32];
     __syncthreads();
@@ -119,14 +125,12 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) acc[k] = 0.0;
 
-    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t nth = (size_t)gridDim.x * blockDim.x;
     if (ROWS == 1) {
         // software pipeline: the next row's three inputs are loaded before the current row is evaluated
         // (ncu before: long-scoreboard 2.1 cycles per issue at 4 warps per scheduler)
         size_t row = tid;
         if (row < batch) {
-            double xa = __ldg(X + row), xb = __ldg(X + batch + row), yy = __ldg(y + row);
+            double xa = xa0, xb = xb0, yy = yy0;
             while (true) {
                 const size_t nxt = row + nth;
                 const bool more = nxt < batch;

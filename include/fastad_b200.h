@@ -106,7 +106,11 @@ int fadb_black_scholes(size_t n, const double* S, const double* K, const double*
 /* `count` batches of n options in ONE host call: batch b runs fadb_black_scholes on operand set (first_set + b) % nsets,
  * in[5*s + {0..4}] = S, K, sigma, tau, r and out[8*s + {0..7}] of set s.  One launch per batch, back to back on the
  * library stream: the per-option loop of example/black_scholes.cpp:43-70 over count x n options without host work
- * between the batches. */
+ * between the batches.  The operand sets must not alias each other (no array of one set inside another set): with
+ * FADB_OVERWRITE_ADJ and nsets >= 2 the batches are independent, and batch b+1 starts on the SMs batch b frees
+ * instead of waiting for its slowest CTA.  Towards the rest of the stream the call is ordered like count ordinary
+ * launches: nothing starts before the work enqueued ahead of the call has completed, and work enqueued behind it
+ * sees every batch complete (FADB_BS_EARLY=0 turns the overlap off). */
 int fadb_black_scholes_batches(size_t count, size_t n, size_t nsets, size_t first_set,
                                const double* const* in, double* const* out, unsigned flags);
 /* Same call through HOST buffers (host↔device copies inside, chunked and overlapped). */

@@ -479,6 +479,42 @@ def test_black_scholes_host_entry_registered_user_arrays(fb):
         np.testing.assert_array_equal(h, host(g))
 
 
+@pytest.mark.parametrize("n", [777, (1 << 16) + 5, 1 << 20])
+def test_black_scholes_batches_early_start_chain(fb, n):
+    # fadb_black_scholes_batches: batches 1.. start without waiting for the batch before them (bs_kernel_fast_pf<PDL_EARLY>)
+    # and wait at their END.  (a) every batch returns the single call's bits, at sizes where many grids are co-resident
+    # (777) and at the BASELINE size; (b) the chain stays ordered after the stream work that precedes the call (inputs
+    # produced by a kernel enqueued right before it) and before the work that follows it (a reduction of the results
+    # enqueued right after it), repeated to give a broken ordering the chance to show.
+    import torch
+    keys = ("S", "K", "sigma", "tau", "r")
+    nsets = 4
+    host_in = [synth.black_scholes_inputs(n, seed=synth.SEED + 31 * s) for s in range(nsets)]
+    want = [[t.clone() for t in fb.black_scholes(*(dev(hi[k]) for k in keys))] for hi in host_in]
+    src = [[dev(hi[k]) for k in keys] for hi in host_in]
+    sets = [([torch.empty(n, dtype=torch.float64, device="cuda") for _ in keys],
+             [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(8)]) for _ in range(nsets)]
+    B = fb.BlackScholesBatches(sets)
+    big = torch.empty(1 << 24, dtype=torch.float64, device="cuda")
+    for rep in range(6):
+        for ins, outs in sets:
+            for t in ins:
+                t.fill_(1.0)                 # valid but wrong operands
+            for t in outs:
+                t.fill_(-3.0)
+        big.fill_(float(rep))                # a long kernel, then the producers of the real inputs, then the call
+        for s in range(nsets):
+            for t, a in zip(sets[s][0], src[s]):
+                t.copy_(a)
+        B.run(2 * nsets + 3, rep)
+        sums = [torch.stack([o.sum() for o in outs]) for _, outs in sets]      # consumers right behind the chain
+        torch.cuda.synchronize()
+        for s in range(nsets):
+            for k in range(8):
+                assert torch.equal(sets[s][1][k], want[s][k]), (rep, s, k)
+            assert torch.equal(sums[s], torch.stack([w.sum() for w in want[s]])), (rep, s)
+
+
 def test_black_scholes_full_size_put_call_parity(fb):
     # BASELINE config 1 size: 2^20 options; size-independent property C - P = S - PV
     n = 1 << 20
