@@ -468,31 +468,45 @@ def run_ours(args):
                 def finish(self, prt, n_total, seed):
                     F.check(L.fadb_normal_lpdf_finish(shape, n_total, P(prt), P(x), P(mu_t), P(sg_t), None,
                                                       P(mu_adj), P(sg_adj), seed, flags, None))
+
+                def undo(self, prt, seed):      # returns at once unless the global count prt[3] is non-zero
+                    F.check(L.fadb_normal_lpdf_undo(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj), P(sg_adj), seed, flags,
+                                                    C.c_void_p(prt.data_ptr() + 24)))
             ops = Ops()
 
             fused = world > 1 and collective.startswith("peer-memory")
+            guarded = bool(shape & 2) and not (flags & F.TRUST_SIGMA)
+            strict = bool(flags & F.STRICT_SIGMA)
 
             def step(i):
                 if fused:
-                    # exchange fused into the two kernels (fadb_normal_lpdf_partial_push / _finish_pull); the sigma
-                    # validity count of the exact semantics keeps its own 1-double mailbox exchange
+                    # exchange fused into the two kernels (fadb_normal_lpdf_partial_push / _finish_pull).  The sigma
+                    # validity count travels with it (optimistic pass + undo); only the strict form needs its own
+                    # 1-double mailbox exchange ahead of the pass
                     cnt = None
-                    if (shape & 2) and not (flags & F.TRUST_SIGMA):
+                    if guarded and strict:
                         cnt = ops.sigma_check()
                         all_reduce(cnt)
                     F.check(L.fadb_normal_lpdf_partial_push(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj),
                                                             P(sg_adj), 1.0, flags, P(cnt), P(part)))
                     F.check(L.fadb_normal_lpdf_finish_pull(shape, n3 * world, P(x), P(mu_t), P(sg_t), None,
                                                            P(mu_adj), P(sg_adj), 1.0, flags, None))
+                    if guarded and not strict:
+                        F.check(L.fadb_normal_lpdf_undo(shape, n3, P(x), P(mu_t), P(sg_t), P(x_adj), P(mu_adj), P(sg_adj), 1.0,
+                                                        flags, None))
                 else:
-                    sharding.sharded_normal_autodiff(ops, all_reduce, shape, n3 * world, 1.0,
-                                                     not (flags & F.TRUST_SIGMA))
+                    sharding.sharded_normal_autodiff(ops, all_reduce, shape, n3 * world, 1.0, guarded, strict)
             return step
 
         mu1, sg1, mua1, sga1 = dev([0.1]), dev([1.3]), zeros(1), zeros(1)
         t = timed_loop(normal_step(3, xa, mu, sg, ma, sa), steps2, 3, world)
         add("normal_vvv_2^26", 72 * n3, t, steps2, n3, "elements",
-            {"note": "exact semantics: +8 B/elem sigma validity pre-pass (80 B/elem traffic); per-GPU shard"},
+            {"note": "exact semantics (default): optimistic single pass, the sigma validity count rides on the partial sums, "
+                     "undo launch behind the finish (returns at once when every sigma_i > 0); per-GPU shard"},
+            sharded=True)
+        t = timed_loop(normal_step(3, xa, mu, sg, ma, sa, F.STRICT_SIGMA), steps2, 3, world)
+        add("normal_vvv_2^26_strict_sigma", 72 * n3, t, steps2, n3, "elements",
+            {"note": "FADB_STRICT_SIGMA: +8 B/elem sigma validity pre-pass (80 B/elem traffic); per-GPU shard"},
             sharded=True)
         t = timed_loop(normal_step(3, xa, mu, sg, ma, sa, F.TRUST_SIGMA), steps2, 3, world)
         add("normal_vvv_2^26_trust_sigma", 72 * n3, t, steps2, n3, "elements", sharded=True)
@@ -512,7 +526,7 @@ def run_ours(args):
         steps5 = max(5, min(steps2, 20))
         t = timed_loop(normal_step(3, xaL, muL, sgL, maL, saL, 0, n5, xL), steps5, 3, world)
         add("normal_vvv_2^28", 72 * n5, t, steps5, n5, "elements",
-            {"note": "exact semantics: +8 B/elem sigma validity pre-pass (80 B/elem traffic); per-GPU shard"},
+            {"note": "exact semantics (default): optimistic single pass + undo launch; per-GPU shard"},
             sharded=True)
         t = timed_loop(normal_step(3, xaL, muL, sgL, maL, saL, F.TRUST_SIGMA, n5, xL), steps5, 3, world)
         add("normal_vvv_2^28_trust_sigma", 72 * n5, t, steps5, n5, "elements", sharded=True)
@@ -521,7 +535,7 @@ def run_ours(args):
 
     if "logpdf" in wl:
         # the other diagonal log-pdfs, all-vector operands, N = 2^25, exact semantics
-        # (validity pre-pass included) and FADB_TRUST_SIGMA (single fused pass)
+        # (optimistic pass + undo launch) and FADB_TRUST_SIGMA (the pass alone)
         n4 = 1 << 25
         rng = np.random.default_rng(synth.SEED + 77)
         x = dev(rng.uniform(-1, 1, n4))
@@ -540,7 +554,8 @@ def run_ours(args):
                                                ("bernoulli_vv", 2, (xb, pb, None, None, a2, None), 32, 16)):
             t = timed_loop(lp_step(dist, *ops_, 0), steps2, 3, world)
             add(f"{nm}_2^25", bytes_per * n4, t, steps2, n4, "elements",
-                {"note": f"exact semantics: +{pre} B/elem validity pre-pass"})
+                {"note": "exact semantics (default): optimistic single pass + undo launch (returns at once when every "
+                         f"element is in range); FADB_STRICT_SIGMA would add a {pre} B/elem validity pre-pass"})
             t = timed_loop(lp_step(dist, *ops_, F.TRUST_SIGMA), steps2, 3, world)
             add(f"{nm}_2^25_trusted", bytes_per * n4, t, steps2, n4, "elements")
         del x, loc, sc, lo, hi, xb, pb, a1, a2, a3

@@ -7,7 +7,7 @@ fallback: if the shared library is missing, or there is no CUDA device, calls fa
 import ctypes as C
 import os
 
-__all__ = ["lib", "load", "FadbError", "OVERWRITE_ADJ", "TRUST_SIGMA", "UNARY", "BINARY",
+__all__ = ["lib", "load", "FadbError", "OVERWRITE_ADJ", "TRUST_SIGMA", "STRICT_SIGMA", "UNARY", "BINARY",
            "black_scholes", "sum_unary", "prod", "normal_lpdf", "linreg_nll", "mlp3"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfastad_b200.so")
 
 OVERWRITE_ADJ = 1
 TRUST_SIGMA = 2
+STRICT_SIGMA = 4
 SCL, VEC, MAT = 0, 1, 2
 UNARY = dict(neg=0, sin=1, cos=2, tan=3, asin=4, acos=5, atan=6, exp=7, log=8, sqrt=9, erf=10,
              sigmoid=11, sinh=12, cosh=13, tanh=14, mock2x=100)
@@ -60,6 +61,7 @@ SIGNATURES = {
     "fadb_sigma_check": (_i, [_sz, _vp, _vp]),
     "fadb_normal_lpdf_partial": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp, _vp]),
     "fadb_normal_lpdf_finish": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
+    "fadb_normal_lpdf_undo": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp]),
     "fadb_normal_dense": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_normal_dense_async": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _i, _vp]),
     "fadb_det": (_i, [_sz, _vp, _vp, _d, _u, _i, _i, _dp]),

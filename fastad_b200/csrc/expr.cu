@@ -37,6 +37,8 @@ extern "C" int fadb_sum_unary_async(int, size_t, const double*, double*, double,
 extern "C" int fadb_sigma_check(size_t, const double*, double*);
 extern "C" int fadb_normal_lpdf_partial(int, size_t, const double*, const double*, const double*, double*,
                                         double*, double*, double, unsigned, const double*, double*);
+extern "C" int fadb_normal_lpdf_undo(int, size_t, const double*, const double*, const double*, double*, double*, double*, double,
+                                     unsigned, const double*);
 extern "C" int fadb_normal_lpdf_finish(int, size_t, const double*, const double*, const double*,
                                        const double*, double*, double*, double*, double, unsigned, double*);
 extern "C" int fadb_linreg_partial(size_t, size_t, const double*, const double*, const double*, double*);
@@ -1299,8 +1301,10 @@ struct fadb_expr {
         if (st.fast == 1)
             return fadb_sum_unary_async(st.f_op, st.N, st.f_x, st.f_xadj, seed, 0, st.mval);
         if (st.fast == 2) {
+            // vector sigma: optimistic pass + undo behind the finish (normal.cu), or the pre-pass with FADB_STRICT_SIGMA
+            const bool guarded = st.sig_vec && seed != 0.0 && (st.f_xadj || st.f_muadj || st.f_sigadj) && !(flags & FADB_TRUST_SIGMA);
             const double* inv = nullptr;
-            if (st.sig_vec && seed != 0.0 && (st.f_xadj || st.f_muadj || st.f_sigadj) && !(flags & FADB_TRUST_SIGMA)) {
+            if (guarded && (flags & FADB_STRICT_SIGMA)) {
                 int rc = fadb_sigma_check(st.N, st.f_sig, st.d_red + 1);
                 if (rc) return rc;
                 inv = st.d_red + 1;
@@ -1315,6 +1319,9 @@ struct fadb_expr {
             if (rc) return rc;
             // the finish kernel leaves the value in the context scalar slot 0
             FADB_CUDA(cudaMemcpyAsync(st.mval, c.scalars + 0, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+            if (guarded && !(flags & FADB_STRICT_SIGMA))
+                return fadb_normal_lpdf_undo(st.f_shape, st.N, st.f_x, st.f_mu, st.f_sig, st.f_xadj, st.f_muadj, st.f_sigadj, seed, 0,
+                                             st.d_red + 7);
             return FADB_OK;
         }
         if (st.fast == 4) {

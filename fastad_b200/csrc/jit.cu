@@ -282,6 +282,11 @@ extern "C" int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, c
     size_t n = 0;
     if (r == NVRTC_SUCCESS) g_rtc.cubin_size(prog, &n);
     if (cubin_bytes) *cubin_bytes = n;
+    if (const char* dump = getenv("FADB_JIT_DUMP_CUBIN"); dump && n && g_rtc.cubin) {   // for cuobjdump -sass (instruction mix studies)
+        std::string bin(n, '\0');
+        if (g_rtc.cubin(prog, &bin[0]) == NVRTC_SUCCESS)
+            if (FILE* f = fopen(dump, "wb")) { fwrite(bin.data(), 1, n, f); fclose(f); }
+    }
     g_rtc.destroy(&prog);
     if (r != NVRTC_SUCCESS) { set_error(std::string("fastad_b200: NVRTC: ") + g_rtc.err(r)); return FADB_ERR_STATE; }
     return FADB_OK;

@@ -4,8 +4,11 @@
 // Same skeleton as normal.cu: the reference makes one pass per quantity; here one streaming pass
 // produces the value sums and every adjoint (256-bit accesses, deterministic reduction).  When
 // validity is a property of ALL elements (uniform: min < x < max everywhere; bernoulli; a vector
-// cauchy scale) a read-only pre-pass decides it first, so that "out of range => no adjoint update"
-// (e.g. cauchy.hpp:151, uniform.hpp:159, bernoulli.hpp:145) holds exactly; FADB_TRUST_SIGMA skips it.
+// cauchy scale), "out of range => no adjoint update" (e.g. cauchy.hpp:151, uniform.hpp:159,
+// bernoulli.hpp:145) is reached as in normal.cu: the pass is optimistic (an out-of-range element adds
+// nothing and is counted), and lp_undo_kernel behind it takes the vector adjoints back when the count is
+// non-zero -- it returns on its first load otherwise.  FADB_STRICT_SIGMA decides validity in a read-only
+// pre-pass instead (bit-exact "untouched"), FADB_TRUST_SIGMA drops the guard.
 #include "common.cuh"
 #include "functors.cuh"
 
@@ -146,6 +149,7 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
             if (!ok) acc[3] += 1.0;
             acc[0] += (ok || DIST == FADB_BERNOULLI) ? Lp<DIST>::term(xv.v[k], b, c, single) : 0.0;
             Lp<DIST>::adj(xv.v[k], b, c, a.seed, single, gx[k], gb[k], gc[k]);
+            if (!ok) gx[k] = gb[k] = gc[k] = 0.0;          // optimistic pass: an out-of-range element adds nothing
             if (!B_VEC) acc[1] += gb[k];
             if (!C_VEC) acc[2] += gc[k];
         }
@@ -160,6 +164,7 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
         acc[0] += (ok || DIST == FADB_BERNOULLI) ? Lp<DIST>::term(x, b, c, single) : 0.0;
         double gx, gb, gc;
         Lp<DIST>::adj(x, b, c, a.seed, single, gx, gb, gc);
+        if (!ok) gx = gb = gc = 0.0;
         if (!B_VEC) acc[1] += gb;
         if (!C_VEC) acc[2] += gc;
         if (wx) a.x_adj[i] = a.overwrite ? gx : a.x_adj[i] + gx;
@@ -179,6 +184,30 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
     });
 }
 
+// undo of the optimistic pass: `verdict` = out[1] of lp_kernel (1 = something was out of range).  Zero: every thread
+// leaves after one load.  Otherwise the contributions are recomputed as lp_kernel formed them and taken back.
+template <int DIST, bool B_VEC, bool C_VEC>
+__global__ void __launch_bounds__(256)
+lp_undo_kernel(LpArgs a, const double* verdict)
+{
+    pdl_prologue();
+    if (__ldcg(verdict) == 0.0 || a.seed == 0.0) return;
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const bool single = a.n == 1;
+    const double bs = B_VEC ? 0.0 : __ldg(a.b), cs = (C_VEC || !Lp<DIST>::has_c) ? 0.0 : __ldg(a.c);
+    const bool wx = Lp<DIST>::x_has_adj && a.x_adj, wb = B_VEC && a.b_adj, wc = C_VEC && Lp<DIST>::has_c && a.c_adj;
+    for (size_t i = tid; i < a.n; i += nth) {
+        const double x = a.x[i], b = B_VEC ? a.b[i] : bs, c = C_VEC ? a.c[i] : cs;
+        double gx, gb, gc;
+        Lp<DIST>::adj(x, b, c, a.seed, single, gx, gb, gc);
+        if (!Lp<DIST>::valid(x, b, c)) gx = gb = gc = 0.0;
+        if (wx) a.x_adj[i] = a.overwrite ? 0.0 : a.x_adj[i] - gx;
+        if (wb) a.b_adj[i] = a.overwrite ? 0.0 : a.b_adj[i] - gb;
+        if (wc) a.c_adj[i] = a.overwrite ? 0.0 : a.c_adj[i] - gc;
+    }
+}
+
 template <int DIST, bool B_VEC, bool C_VEC>
 static int run_logpdf(Context& c, LpArgs a, unsigned flags, bool any_adj, double* out)
 {
@@ -186,19 +215,25 @@ static int run_logpdf(Context& c, LpArgs a, unsigned flags, bool any_adj, double
     const bool global_check = !(DIST == FADB_CAUCHY && !C_VEC);
     double* invalid = out + 2;
     a.invalid_in = nullptr;
-    if (any_adj && a.seed != 0.0) {
-        if (global_check && !(flags & FADB_TRUST_SIGMA)) {
-            const int threads = 512;
-            const int grid = resident_grid(c, lp_check_kernel<DIST, B_VEC, C_VEC>, threads, 0, a.n, threads);
-            FADB_CUDA(launch_pdl(lp_check_kernel<DIST, B_VEC, C_VEC>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 9, invalid));
-            c.launches++;
-            a.invalid_in = invalid;
-        }
+    // only VECTOR adjoints are written by the pass itself (scalar ones by its epilogue, which knows the verdict)
+    const bool vec_adj = (Lp<DIST>::x_has_adj && a.x_adj) || (B_VEC && a.b_adj) || (C_VEC && Lp<DIST>::has_c && a.c_adj);
+    const bool guarded = any_adj && vec_adj && a.seed != 0.0 && global_check && !(flags & FADB_TRUST_SIGMA);
+    if (guarded && (flags & FADB_STRICT_SIGMA)) {
+        const int threads = 512;
+        const int grid = resident_grid(c, lp_check_kernel<DIST, B_VEC, C_VEC>, threads, 0, a.n, threads);
+        FADB_CUDA(launch_pdl(lp_check_kernel<DIST, B_VEC, C_VEC>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 9, invalid));
+        c.launches++;
+        a.invalid_in = invalid;
     }
     const int threads = 256;
     const int grid = resident_grid(c, lp_kernel<DIST, B_VEC, C_VEC>, threads, 0, (a.n + 3) / 4, threads);
     FADB_CUDA(launch_pdl(lp_kernel<DIST, B_VEC, C_VEC>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 10, out));
     c.launches++;
+    if (guarded && !(flags & FADB_STRICT_SIGMA)) {
+        const int ugrid = resident_grid(c, lp_undo_kernel<DIST, B_VEC, C_VEC>, threads, 0, a.n, threads);
+        FADB_CUDA(launch_pdl(lp_undo_kernel<DIST, B_VEC, C_VEC>, ugrid, threads, 0, c.stream, a, out + 1));
+        c.launches++;
+    }
     FADB_CUDA(cudaGetLastError());
     return FADB_OK;
 }

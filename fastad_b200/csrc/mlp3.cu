@@ -96,6 +96,41 @@ __device__ __forceinline__ void mlp3_row(const double* __restrict__ p, const dou
     }
 }
 
+// Warp-level reduce-scatter of the 26 channels by recursive halving: at the step with partner lane ^ H a lane keeps one half
+// of its channels (which half: its own bit H) and hands the other half to the partner, so the five steps cost 16 + 8 + 4 + 2 + 1
+// = 31 shuffles of a double instead of the 26 x 5 = 130 of one butterfly per channel (ncu before: the shuffles of the CTA
+// reduction were ~2 us of the 10.6 us small-batch launch).  Afterwards lane l holds the warp's total of channel l (0 for
+// l >= NOUT).  Fixed tree: the bits do not depend on timing.
+__device__ __forceinline__ double warp_reduce_scatter26(const double (&acc)[NOUT], int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    double a16[16], a8[8], a4[4], a2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const double hi = (k + 16 < NOUT) ? acc[k + 16] : 0.0;
+        const double keep = b4 ? hi : acc[k], give = b4 ? acc[k] : hi;
+        a16[k] = keep + __shfl_xor_sync(FULL, give, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double keep = b3 ? a16[k + 8] : a16[k], give = b3 ? a16[k] : a16[k + 8];
+        a8[k] = keep + __shfl_xor_sync(FULL, give, 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double keep = b2 ? a8[k + 4] : a8[k], give = b2 ? a8[k] : a8[k + 4];
+        a4[k] = keep + __shfl_xor_sync(FULL, give, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double keep = b1 ? a4[k + 2] : a4[k], give = b1 ? a4[k] : a4[k + 2];
+        a2[k] = keep + __shfl_xor_sync(FULL, give, 2);
+    }
+    const double keep = b0 ? a2[1] : a2[0], give = b0 ? a2[0] : a2[1];
+    return keep + __shfl_xor_sync(FULL, give, 1);
+}
+
 // ROWS rows per thread and trip (independent dependency chains for the FP64 pipe), MINB resident CTAs
 // Link = P2PLink: batch shard of ONE evaluation over the ranks of a node; the last CTA pushes its 26 sums into every
 // rank's mailbox over NVLink, waits for the other ranks and writes the rank-ordered totals (pass + all-reduce in one launch).
@@ -103,13 +138,13 @@ template <int ROWS, int MINB, int THREADS = 256, class Link = NoLink>
 __global__ void __launch_bounds__(THREADS, MINB)
 mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict__ y,
             const double* __restrict__ parm, double* cta_partials, unsigned int* ticket,
-            double* grad, int overwrite, double* out_loss, Link link)
+            double* grad, int overwrite, double* out_loss, Link link, int red_mode)
 {
     pdl_prologue();
     constexpr bool TAB = MINB >= 2;          // large-batch variant: table exp (the copy costs the small-batch one more than it saves)
     __shared__ double p[NP];
     __shared__ double t32[TAB ? 32 : 1];
-    __shared__ double red[THREADS / 32][NOUT];
+    __shared__ double red[THREADS / 32][32];
     __shared__ bool is_last;
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
@@ -159,29 +194,70 @@ mlp3_kernel(size_t batch, const double* __restrict__ X, const double* __restrict
     }
     // ---- CTA reduce of the 26 channels ----
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NOUT; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) red[warp][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < NOUT) {
-        double v = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
-        cta_partials[(size_t)blockIdx.x * NOUT + threadIdx.x] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last CTA: warp w sums CTAs w, w+8, ... (lane = channel), then the 8 warp sums in a fixed order
-    // (a wider final pass -- 8 warps x 26 lanes over the CTA partials, then a shared-memory step -- measured
-    // 1.7-2.8 us SLOWER than these 26 independent load streams at 148-296 CTAs)
     double v = 0.0;
-    if (threadIdx.x < NOUT)
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&cta_partials[(size_t)b * NOUT + threadIdx.x]);
+    if (red_mode == 0) {
+        // FADB_MLP_REDUCE=0, the round-1 protocol kept for A/B runs: one butterfly per channel, every warp fences twice,
+        // 26 threads of the last CTA walk the partial rows
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+            const double w = warp_sum(acc[k]);
+            if (lane == 0) red[warp][k] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x < NOUT) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
+            cta_partials[(size_t)blockIdx.x * NOUT + threadIdx.x] = t;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        if (threadIdx.x < NOUT)
+            for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&cta_partials[(size_t)b * NOUT + threadIdx.x]);
+    } else {
+        red[warp][lane] = warp_reduce_scatter26(acc, lane);       // lane = channel
+        __syncthreads();
+        if (warp == 0) {
+            // warp 0 alone publishes the CTA's row: its lanes store, the warp converges, ONE thread fences (cumulative over
+            // the stores ordered before it by the warp barrier) and takes the ticket; the other 15 warps never fence
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) t += red[w][lane];
+            if (lane < NOUT) cta_partials[(size_t)blockIdx.x * NOUT + lane] = t;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+                if (is_last) __threadfence();                     // acquire side: the partial rows are read with ld.cg below
+            }
+        }
+        __syncthreads();
+        if (!is_last) return;
+        // last CTA: warp w sums the rows of CTAs w, w + nwarps, ... (lane = channel), all of a lane's loads independent and in
+        // flight together (one L2 round trip for up to 8 rows per warp); then the warp sums in warp order
+        double t = 0.0;
+        if (lane < NOUT) {
+            unsigned b = warp;
+            for (; b + 3 * (THREADS / 32) < gridDim.x; b += 4 * (THREADS / 32)) {
+                const double t0 = __ldcg(&cta_partials[(size_t)b * NOUT + lane]);
+                const double t1 = __ldcg(&cta_partials[(size_t)(b + THREADS / 32) * NOUT + lane]);
+                const double t2 = __ldcg(&cta_partials[(size_t)(b + 2 * (THREADS / 32)) * NOUT + lane]);
+                const double t3 = __ldcg(&cta_partials[(size_t)(b + 3 * (THREADS / 32)) * NOUT + lane]);
+                t += (t0 + t1) + (t2 + t3);
+            }
+            for (; b < gridDim.x; b += THREADS / 32) t += __ldcg(&cta_partials[(size_t)b * NOUT + lane]);
+        }
+        __syncthreads();                                           // red[] is reused
+        red[warp][lane] = t;
+        __syncthreads();
+        if (threadIdx.x < NOUT) {
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) v += red[w][threadIdx.x];
+        }
+    }
     if constexpr (std::is_same<Link, P2PLink>::value) {
         p2p_push(link, (int)threadIdx.x, NOUT, v, [] { __syncthreads(); });
         v = p2p_pull(link, (int)threadIdx.x, NOUT);
@@ -227,6 +303,8 @@ static int mlp3_launch(size_t batch, const double* X, const double* y, const dou
     if (rc) return rc;
     if (!g_mlp_ws[c->device]) FADB_CUDA(cudaMalloc(&g_mlp_ws[c->device], sizeof(double) * kMaxGrid * NOUT));
     const int threads = 256;
+    // FADB_MLP_REDUCE=0: the round-1 reduction protocol (A/B runs); default: reduce-scatter + single-thread fences + wide last pass
+    static const int red = [] { const char* e = getenv("FADB_MLP_REDUCE"); return (e && e[0] == '0') ? 0 : 1; }();
     if (exchange) {
         // same variant choice as below, by batch size
         P2PLink link;
@@ -235,14 +313,14 @@ static int mlp3_launch(size_t batch, const double* X, const double* y, const dou
         if (batch > (size_t)4 * c->sms * threads) {
             auto K = mlp3_kernel<1, 2, 256, P2PLink>;
             FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm,
-                                 g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link));
+                                 g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link, red));
         } else if (batch > (size_t)c->sms * 256 && batch <= (size_t)c->sms * 512) {
             FADB_CUDA(launch_pdl(mlp3_kernel<1, 1, 512, P2PLink>, (int)std::min<size_t>((batch + 511) / 512, (size_t)c->sms), 512, 0,
-                                 c->stream, batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link));
+                                 c->stream, batch, X, y, parm, g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link, red));
         } else {
             auto K = mlp3_kernel<1, 1, 256, P2PLink>;
             FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm,
-                                 g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link));
+                                 g_mlp_ws[c->device], c->tickets + 5, grad, ow, dev_loss, link, red));
         }
         c->launches++;
         FADB_CUDA(cudaGetLastError());
@@ -252,7 +330,7 @@ static int mlp3_launch(size_t batch, const double* X, const double* y, const dou
     if (variant < 0) { const char* e = getenv("FADB_MLP_VARIANT"); variant = e ? atoi(e) : -2; }
 #define FADB_MLP_LAUNCH(K)                                                                                     \
     FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm, \
-                         g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}))
+                         g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}, red))
     // measured on B200, batch 2^22: <1,1> 166 us (153 registers, 8 warps/SM: FP64 pipe 37 % active, stalls are
     // dependent-issue waits), <2,1> 155, <3,1> 159, <2,2> 121, <1,2> 115 (128 registers, 16 warps/SM): default;
     // <1,3> 152 and <1,4> 199 (80 / 64 registers: 430-530 bytes of spills per row)
@@ -267,7 +345,7 @@ static int mlp3_launch(size_t batch, const double* X, const double* y, const dou
     else if (variant == 7 || (variant == -2 && batch > (size_t)c->sms * 256 && batch <= (size_t)c->sms * 512)) {
         // one row per thread in ONE trip with no more CTAs (= partial rows and tickets) than SMs: 512-thread CTAs
         FADB_CUDA(launch_pdl(mlp3_kernel<1, 1, 512>, (int)std::min<size_t>((batch + 511) / 512, (size_t)c->sms), 512, 0, c->stream, batch, X, y,
-                             parm, g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}));
+                             parm, g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}, red));
     }
     else FADB_MLP_LAUNCH((mlp3_kernel<1, 1>));
 #undef FADB_MLP_LAUNCH

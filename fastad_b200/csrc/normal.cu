@@ -8,9 +8,15 @@
 // value and three adjoint passes that each re-read x,mu,sigma (~160 B/element for vvv).
 // Here the root-level seed is known when the call is made, so value and all adjoints are
 // produced by ONE fused pass: 3 streaming reads + 3 read-modify-writes = 72 B/element (vvv).
-// A vector sigma that is a variable needs its validity known before the first adjoint is
-// written (normal.hpp:440-442,457: sigma<=0 => value -inf and NO adjoint update), which costs
-// one extra streaming read of sigma (8 B/element) unless the caller passes FADB_TRUST_SIGMA.
+// A vector sigma must be valid EVERYWHERE for any adjoint to be written (normal.hpp:440-442,457:
+// sigma_i <= 0 => value -inf and NO adjoint update).  The pass is therefore OPTIMISTIC: it writes the
+// adjoints of every element whose own sigma_i is valid and counts the invalid ones in the same sweep; when the
+// (global) count turns out non-zero -- the rare error case -- normal_undo_kernel takes the contributions back
+// (recomputed bit-identically, subtracted).  The common case stays at 72 B/element; the undo launch exits on its
+// first load otherwise.  With zero-initialised or FADB_OVERWRITE_ADJ adjoints the undo is exact (they read 0
+// afterwards); accumulated into non-zero adjoints it restores them to within one rounding of (previous +
+// contribution).  FADB_STRICT_SIGMA buys the bit-exact "untouched" with a read-only pre-pass over sigma
+// (+8 B/element, sigma_check_kernel); FADB_TRUST_SIGMA skips the undo launch altogether.
 #include "common.cuh"
 #include "p2p_device.cuh"
 
@@ -166,9 +172,9 @@ normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const double s = SIG_VEC ? sv.v[k] : s_scl;
-            if (SIG_VEC && !(s > 0)) acc[3] += 1.0;
             Elem<MU_VEC, SIG_VEC>::run(xv.v[k], MU_VEC ? mv.v[k] : m_scl, s, a.seed, inv_s_sq, acc,
                                        gx[k], gm[k], gs[k]);
+            if (SIG_VEC && !(s > 0)) { acc[3] += 1.0; gx[k] = gm[k] = gs[k] = 0.0; }   // optimistic pass: an invalid element adds nothing
         }
         if (wx) rmw4(a.x_adj + i, gx, a.overwrite);
         if (wm) rmw4(a.mu_adj + i, gm, a.overwrite);
@@ -176,9 +182,9 @@ normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_
     }
     for (size_t i = n4 * 4 + tid; i < a.n; i += nth) {
         const double s = SIG_VEC ? a.sigma[i] : s_scl;
-        if (SIG_VEC && !(s > 0)) acc[3] += 1.0;
         double gx, gm, gs;
         Elem<MU_VEC, SIG_VEC>::run(a.x[i], MU_VEC ? a.mu[i] : m_scl, s, a.seed, inv_s_sq, acc, gx, gm, gs);
+        if (SIG_VEC && !(s > 0)) { acc[3] += 1.0; gx = gm = gs = 0.0; }
         if (wx) a.x_adj[i] = a.overwrite ? gx : a.x_adj[i] + gx;
         if (wm) a.mu_adj[i] = a.overwrite ? gm : a.mu_adj[i] + gm;
         if (ws) a.sigma_adj[i] = a.overwrite ? gs : a.sigma_adj[i] + gs;
@@ -193,21 +199,82 @@ normal_kernel(NormalArgs a, double* partials, unsigned int* ticket, double* out_
     });
 }
 
+// ------------------------------------------------------------------ undo of the optimistic pass (vector sigma)
+// Runs behind the finish kernel; `count` = global number of sigma_i <= 0.  Zero (the common case): every thread
+// leaves after one load.  Otherwise the per-element contributions are recomputed exactly as normal_kernel formed
+// them (same Elem::run, same flags) and taken back: stored adjoints are zeroed, accumulated ones get them subtracted.
+__device__ __forceinline__ void undo4(double* p, const double (&g)[4], int overwrite)
+{
+    double4_t v;
+    if (overwrite) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.v[k] = 0.0;
+    } else {
+        v = ld256(p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.v[k] -= g[k];
+    }
+    st256(p, v);
+}
+
+template <bool MU_VEC>
+__global__ void __launch_bounds__(256)
+normal_undo_kernel(NormalArgs a, const double* count)
+{
+    pdl_prologue();
+    if (__ldcg(count) == 0.0 || a.seed == 0.0) return;
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const double m_scl = MU_VEC ? 0.0 : __ldg(a.mu);
+    const bool wx = a.x_adj, wm = MU_VEC && a.mu_adj, ws = a.sigma_adj;
+    const bool vec = aligned32(a.x) && (!MU_VEC || aligned32(a.mu)) && aligned32(a.sigma) &&
+                     (!a.x_adj || aligned32(a.x_adj)) && (!MU_VEC || !a.mu_adj || aligned32(a.mu_adj)) &&
+                     (!a.sigma_adj || aligned32(a.sigma_adj));
+    const size_t n4 = vec ? a.n / 4 : 0;
+    double unused[NCH] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t q = tid; q < n4; q += nth) {
+        const size_t i = 4 * q;
+        const double4_t xv = ldg256_stream(a.x + i), sv = ldg256_stream(a.sigma + i);
+        double4_t mv;
+        if (MU_VEC) mv = ldg256_stream(a.mu + i);
+        double gx[4], gm[4], gs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            Elem<MU_VEC, true>::run(xv.v[k], MU_VEC ? mv.v[k] : m_scl, sv.v[k], a.seed, 1.0, unused, gx[k], gm[k], gs[k]);
+            if (!(sv.v[k] > 0)) gx[k] = gm[k] = gs[k] = 0.0;
+        }
+        if (wx) undo4(a.x_adj + i, gx, a.overwrite);
+        if (wm) undo4(a.mu_adj + i, gm, a.overwrite);
+        if (ws) undo4(a.sigma_adj + i, gs, a.overwrite);
+    }
+    for (size_t i = n4 * 4 + tid; i < a.n; i += nth) {
+        const double s = a.sigma[i];
+        double gx, gm, gs;
+        Elem<MU_VEC, true>::run(a.x[i], MU_VEC ? a.mu[i] : m_scl, s, a.seed, 1.0, unused, gx, gm, gs);
+        if (!(s > 0)) gx = gm = gs = 0.0;
+        if (wx) a.x_adj[i] = a.overwrite ? 0.0 : a.x_adj[i] - gx;
+        if (wm) a.mu_adj[i] = a.overwrite ? 0.0 : a.mu_adj[i] - gm;
+        if (ws) a.sigma_adj[i] = a.overwrite ? 0.0 : a.sigma_adj[i] - gs;
+    }
+}
+
 // ------------------------------------------------------------------ scalar epilogue
 // Turns the (possibly all-reduced) partial sums into the node value and the adjoints of
 // scalar operands.  n_total is the global element count.
 __global__ void normal_finish_kernel(int shape_code, double n_total, const double* partial,
                                      const double* x, const double* mu, const double* sigma,
                                      double* x_adj, double* mu_adj, double* sigma_adj, double seed,
-                                     int overwrite, double* out_value, P2PLink link)
+                                     int overwrite, double* out_value, double* out_invalid, P2PLink link)
 {
     double pulled[NCH];
     if (link.world) {       // fused exchange: wait for every rank's push, reduce in rank order
         p2p_pull1(link, pulled, NCH);
         partial = pulled;
     }
+    out_invalid[0] = partial[3];      // global #sigma<=0: what normal_undo_kernel behind this launch looks at
     const bool mu_vec = shape_code & 1, sig_vec = shape_code & 2;
-    if (partial[3] != 0.0) { out_value[0] = -INFINITY; return; }   // normal.hpp:147, 440-442
+    // normal.hpp:147, 440-442; a NaN count is the poison of a failed exchange (p2p_device.cuh) and stays NaN
+    if (partial[3] != 0.0) { out_value[0] = (partial[3] != partial[3]) ? partial[3] : -INFINITY; return; }
     if (n_total == 1.0 && shape_code == 0) {
         // sss, normal.hpp:141-171
         const double s = sigma[0], inv_s = 1. / s;
@@ -345,7 +412,7 @@ static int normal_finish_impl(int shape_code, size_t n_total, const double* dev_
     double* dval = c->scalars + 0;
     normal_finish_kernel<<<1, 1, 0, c->stream>>>(shape_code, (double)n_total, dev_partial4, x, mu, sigma,
                                                  x_adj, mu_adj, sigma_adj, seed,
-                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval, link);
+                                                 (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dval, c->scalars + 12, link);
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     if (host_value) {
@@ -373,6 +440,34 @@ extern "C" int fadb_normal_lpdf_finish_pull(int shape_code, size_t n_total, cons
     return normal_finish_impl(shape_code, n_total, nullptr, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, flags, host_value, true);
 }
 
+// Takes back what an optimistic pass over a vector sigma wrote when the global count of sigma_i <= 0 is non-zero
+// (dev_invalid_count; NULL = the count the last finish kernel on this device published).  No-op for a scalar sigma.
+extern "C" int fadb_normal_lpdf_undo(int shape_code, size_t n, const double* x, const double* mu, const double* sigma,
+                                     double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                                     const double* dev_invalid_count)
+{
+    int rc = check_normal_args(shape_code, n, x, mu, sigma);
+    if (rc) return rc;
+    if (!(shape_code & 2) || seed == 0.0 || n == 0) return FADB_OK;
+    const bool mu_vec = shape_code & 1;
+    if (!x_adj && !(mu_vec && mu_adj) && !sigma_adj) return FADB_OK;
+    Context* c;
+    rc = current_context(&c);
+    if (rc) return rc;
+    NormalArgs a{n, x, mu, sigma, x_adj, mu_vec ? mu_adj : nullptr, sigma_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, nullptr};
+    const double* cnt = dev_invalid_count ? dev_invalid_count : c->scalars + 12;
+    const int threads = 256;
+    if (mu_vec)
+        FADB_CUDA(launch_pdl(normal_undo_kernel<true>, resident_grid(*c, normal_undo_kernel<true>, threads, 0, (n + 3) / 4, threads),
+                             threads, 0, c->stream, a, cnt));
+    else
+        FADB_CUDA(launch_pdl(normal_undo_kernel<false>, resident_grid(*c, normal_undo_kernel<false>, threads, 0, (n + 3) / 4, threads),
+                             threads, 0, c->stream, a, cnt));
+    c->launches++;
+    FADB_CUDA(cudaGetLastError());
+    return FADB_OK;
+}
+
 extern "C" int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const double* mu,
                                 const double* sigma, double* x_adj, double* mu_adj,
                                 double* sigma_adj, double seed, unsigned flags, double* host_value)
@@ -384,11 +479,11 @@ extern "C" int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const
     if (rc) return rc;
     double* partial = c->scalars + 8;     // 4 doubles
     double* invalid = c->scalars + 12;    // 1 double
-    const bool sig_vec = shape_code & 2;
-    const bool any_adj = x_adj || mu_adj || sigma_adj;
+    const bool sig_vec = shape_code & 2, mu_vec = shape_code & 1;
+    // vector adjoints are written by the pass itself: with a vector sigma they need the all-elements validity verdict
+    const bool guarded = sig_vec && (x_adj || (mu_vec && mu_adj) || sigma_adj) && seed != 0.0 && !(flags & FADB_TRUST_SIGMA);
     const double* invalid_in = nullptr;
-    // A variable OR constant vector sigma must be known valid before adjoints are written.
-    if (sig_vec && any_adj && seed != 0.0 && !(flags & FADB_TRUST_SIGMA)) {
+    if (guarded && (flags & FADB_STRICT_SIGMA)) {          // verdict first (read-only pre-pass), then the pass
         rc = fadb_sigma_check(n, sigma, invalid);
         if (rc) return rc;
         invalid_in = invalid;
@@ -409,6 +504,14 @@ extern "C" int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const
     rc = launch_partial(*c, shape_code, a, partial);
     if (rc) return rc;
     // vector adjoints are done; scalar operands and the value come from the partial sums
-    return fadb_normal_lpdf_finish(shape_code, n, partial, x, mu, sigma, nullptr, mu_adj, sigma_adj,
-                                   seed, flags, host_value);
+    rc = fadb_normal_lpdf_finish(shape_code, n, partial, x, mu, sigma, nullptr, mu_adj, sigma_adj,
+                                 seed, flags, host_value);
+    if (rc || !guarded || (flags & FADB_STRICT_SIGMA)) return rc;
+    // optimistic pass: the undo launch looks at the count the finish kernel published.  A caller that waited for the
+    // value already knows whether there is anything to take back (only a -inf / NaN value can come with a count).
+    if (host_value && *host_value > -INFINITY) return FADB_OK;
+    rc = fadb_normal_lpdf_undo(shape_code, n, x, mu, sigma, x_adj, mu_adj, sigma_adj, seed, flags, invalid);
+    if (rc) return rc;
+    if (host_value) FADB_CUDA(cudaStreamSynchronize(c->stream));
+    return FADB_OK;
 }

@@ -19,17 +19,27 @@ def shard_range(n, rank, world):
     return b, e
 
 
-def sharded_normal_autodiff(ops, all_reduce, shape_code, n_total, seed, check_sigma):
+def sharded_normal_autodiff(ops, all_reduce, shape_code, n_total, seed, check_sigma, strict=False):
     """normal_adj_log_pdf over element-range shards.
-    ops.sigma_check() -> count buffer; ops.partial(count_or_None) -> 4-slot partial buffer;
-    ops.finish(partial, n_total) -> value.  Buffers are whatever `all_reduce` accepts."""
+    ops.partial(count_or_None, seed) -> 4-slot partial buffer {.., .., .., #sigma_i <= 0 of the shard};
+    ops.finish(partial, n_total, seed) -> value; buffers are whatever `all_reduce` accepts.
+    A vector sigma must be valid on ALL shards for any adjoint to be written (normal.hpp:440-457):
+      default: every shard runs the optimistic pass (elements with an invalid sigma_i add nothing and are counted), the
+               count travels with the ONE exchange of the evaluation, and ops.undo(partial, seed) takes the shard's
+               vector adjoints back when the global count is non-zero (it returns at once otherwise);
+      strict:  ops.sigma_check() -> count buffer, all-reduced FIRST (a second exchange), then the pass either writes
+               adjoints or does not (bit-exact "untouched")."""
+    guarded = bool(shape_code & 2) and check_sigma
     cnt = None
-    if (shape_code & 2) and check_sigma:
+    if guarded and strict:
         cnt = ops.sigma_check()
         all_reduce(cnt)                 # 1 double: #sigma_i <= 0 over ALL shards
     part = ops.partial(cnt, seed)
     all_reduce(part)                    # 4 doubles: the one exchange of the evaluation
-    return ops.finish(part, n_total, seed)
+    val = ops.finish(part, n_total, seed)
+    if guarded and not strict:
+        ops.undo(part, seed)
+    return val
 
 
 def sharded_linreg_autodiff(ops, all_reduce, rows_total, seed):

@@ -40,7 +40,9 @@ extern "C" {
 
 /* flags */
 #define FADB_OVERWRITE_ADJ 1u  /* adjoint outputs are stored, not accumulated ("fused reset") */
-#define FADB_TRUST_SIGMA 2u    /* caller guarantees sigma > 0: skip the validity pre-pass     */
+#define FADB_TRUST_SIGMA 2u    /* caller guarantees every element is in range (sigma > 0 ...): no validity guard at all */
+#define FADB_STRICT_SIGMA 4u   /* decide validity in a read-only pre-pass BEFORE any adjoint is written (bit-exact "untouched"
+                                  on invalid input, +8 B/element) instead of the default optimistic pass + undo         */
 
 /* shapes: ad::scl / ad::vec / ad::mat (util/shape_traits.hpp:7-9) */
 enum { FADB_SCL = 0, FADB_VEC = 1, FADB_MAT = 2 };
@@ -145,18 +147,24 @@ int fadb_prod(size_t n, const double* x, double* x_adj, double seed, unsigned fl
  *   an operand is a CONSTANT (no adjoint) iff its *_adj pointer is NULL;
  *   scalar mu/sigma are device scalars; their adjoints are device scalars too.
  * Returns -inf in *host_value and leaves all adjoints untouched when any sigma <= 0
- * (normal.hpp:147,160,440-442,457). */
+ * (normal.hpp:147,160,440-442,457).  For a vector sigma "untouched" is reached by an optimistic single pass plus, in the
+ * invalid case only, an undo pass that takes the contributions back: exact for zero-initialised or FADB_OVERWRITE_ADJ
+ * adjoints (they read 0), to within one rounding of (previous + contribution) for accumulated ones; FADB_STRICT_SIGMA
+ * selects the bit-exact pre-pass form. */
 int fadb_normal_lpdf(int shape_code, size_t n, const double* x, const double* mu,
                      const double* sigma, double* x_adj, double* mu_adj, double* sigma_adj,
                      double seed, unsigned flags, double* host_value);
 /* Multi-GPU building blocks (element-range shards).  Vector adjoints only need
  * the seed, so each shard runs the same fused pass; what must cross GPUs are the partial sums
  * dev_partial4 = {sum d^2 | z^2, sum log sigma_i, sum d | d/sigma_i^2, #sigma<=0}:
- *   [fadb_sigma_check -> all-reduce count]   (vector sigma only, for the no-adjoint-on-invalid rule)
- *   fadb_normal_lpdf_partial                 (fused value sums + vector adjoints of the shard)
+ *   fadb_normal_lpdf_partial                 (fused value sums + vector adjoints of the shard; dev_invalid_in = NULL:
+ *                                             optimistic -- elements with sigma_i <= 0 add nothing and are counted)
  *   all-reduce dev_partial4 (ncclSum)        (the caller's collective)
  *   fadb_normal_lpdf_finish                  (value + adjoints of scalar operands, n_total global)
- * fadb_normal_lpdf is exactly this chain on one device. */
+ *   fadb_normal_lpdf_undo                    (vector sigma without FADB_TRUST_SIGMA: takes the shard's vector adjoints back
+ *                                             when the global count dev_partial4[3] != 0; returns at once otherwise)
+ * fadb_normal_lpdf is exactly this chain on one device.  The strict form instead starts with
+ *   fadb_sigma_check -> all-reduce count -> fadb_normal_lpdf_partial(dev_invalid_in = count) and needs no undo. */
 int fadb_sigma_check(size_t n, const double* sigma, double* dev_count);
 int fadb_normal_lpdf_partial(int shape_code, size_t n, const double* x, const double* mu,
                              const double* sigma, double* x_adj, double* mu_adj,
@@ -166,6 +174,11 @@ int fadb_normal_lpdf_finish(int shape_code, size_t n_total, const double* dev_pa
                             const double* x, const double* mu, const double* sigma,
                             double* x_adj, double* mu_adj, double* sigma_adj, double seed,
                             unsigned flags, double* host_value);
+/* dev_invalid_count: device double holding the GLOBAL number of sigma_i <= 0 (dev_partial4 + 3 after the all-reduce);
+ * NULL = the count published by the last fadb_normal_lpdf_finish / _finish_pull on this device. */
+int fadb_normal_lpdf_undo(int shape_code, size_t n, const double* x, const double* mu, const double* sigma,
+                          double* x_adj, double* mu_adj, double* sigma_adj, double seed, unsigned flags,
+                          const double* dev_invalid_count);
 
 /* ------------------------------------------------------------------ K7: dense-covariance normal
  * autodiff of ad::normal_adj_log_pdf(x, mu, Sigma) with Sigma an n x n matrix (vsm / vvm,

@@ -60,37 +60,55 @@ def run(F, world, rank, small_all_reduce, fused, rows_per_rank_log2=18, n_per_ra
     part, inval = torch.zeros(4, **f64), torch.zeros(1, **f64)
 
     def normal_eval(shape, x, mu, sg, xa, ma, sa, flags):
+        # default: optimistic pass, the count of sigma_i <= 0 rides on the one exchange, undo launch behind the finish;
+        # FADB_STRICT_SIGMA: the count is exchanged first; FADB_TRUST_SIGMA: no guard
         val = C.c_double()
+        guarded = bool(shape & 2) and not (flags & F.TRUST_SIGMA)
+        strict = bool(flags & F.STRICT_SIGMA)
+        cnt = None
+        if guarded and strict:
+            F.check(L.fadb_sigma_check(n, P(sg), P(inval)))
+            small_all_reduce(inval)
+            cnt = inval
         if fused:
-            cnt = None
-            if (shape & 2) and not (flags & F.TRUST_SIGMA):
-                F.check(L.fadb_sigma_check(n, P(sg), P(inval)))
-                small_all_reduce(inval)
-                cnt = inval
             F.check(L.fadb_normal_lpdf_partial_push(shape, n, P(x), P(mu), P(sg), P(xa), P(ma), P(sa), seed, flags, P(cnt), P(part)))
             F.check(L.fadb_normal_lpdf_finish_pull(shape, n_total, P(x), P(mu), P(sg), None, P(ma), P(sa), seed, flags, C.byref(val)))
+            if guarded and not strict:
+                F.check(L.fadb_normal_lpdf_undo(shape, n, P(x), P(mu), P(sg), P(xa), P(ma), P(sa), seed, flags, None))
         else:
-            cnt = None
-            if (shape & 2) and not (flags & F.TRUST_SIGMA):
-                F.check(L.fadb_sigma_check(n, P(sg), P(inval)))
-                small_all_reduce(inval)
-                cnt = inval
             F.check(L.fadb_normal_lpdf_partial(shape, n, P(x), P(mu), P(sg), P(xa), P(ma), P(sa), seed, flags, P(cnt), P(part)))
             small_all_reduce(part)
             F.check(L.fadb_normal_lpdf_finish(shape, n_total, P(part), P(x), P(mu), P(sg), None, P(ma), P(sa), seed, flags, C.byref(val)))
+            if guarded and not strict:
+                F.check(L.fadb_normal_lpdf_undo(shape, n, P(x), P(mu), P(sg), P(xa), P(ma), P(sa), seed, flags,
+                                                C.c_void_p(part.data_ptr() + 24)))
         return val.value
 
     # vvv: sigma cycles through powers of two whose logs cancel per cycle
     sg = torch.tensor([1.0, 2.0, 0.5, 4.0, 0.25, 2.0, 0.5, 1.0], **f64)[i & 7]
     mu = (i & 1023).to(torch.float64) / 1024.0
     x = mu + sg * z
-    for flags in (0, F.TRUST_SIGMA):
+    for flags in (0, F.TRUST_SIGMA, F.STRICT_SIGMA):
         xa, ma, sa = (torch.full((n,), 0.5, **f64) for _ in range(3))
         v = normal_eval(3, x, mu, sg, xa, ma, sa, flags)
         assert _rel(v, -0.5 * 15.0 * n_total / 8.0) <= REL, ("normal vvv value", v, flags)
         assert torch.equal(xa, 0.5 - seed * z / sg) and torch.equal(ma, 0.5 + seed * z / sg) \
             and torch.equal(sa, 0.5 + seed * (z * z - 1.0) / sg), "normal vvv adjoints"
         same_on_all_ranks("normal vvv value", torch.tensor([v], **f64))
+    # ONE sigma_i <= 0, in the last rank's shard: every rank must report -inf and hold untouched adjoints
+    # (normal.hpp:440-457) -- through the undo of the optimistic pass (every contribution here is exactly representable,
+    # so taking it back restores the previous bits) and through the strict pre-pass
+    sg_bad = sg.clone()
+    if rank == world - 1:
+        sg_bad[n - 3] = -1.0
+    for flags in (0, F.STRICT_SIGMA):
+        xa, ma, sa = (torch.full((n,), 0.5, **f64) for _ in range(3))
+        v = normal_eval(3, x, mu, sg_bad, xa, ma, sa, flags)
+        torch.cuda.synchronize()
+        assert v == -math.inf, ("normal vvv with one invalid sigma", v, flags)
+        assert bool((xa == 0.5).all()) and bool((ma == 0.5).all()) and bool((sa == 0.5).all()), \
+            ("normal vvv adjoints after an invalid evaluation", flags)
+    del sg_bad
     done["normal_vvv"] = n_total
     # vss: scalar mu = 0.25, sigma = 2 as variables; their adjoints are sums over ALL shards
     mu1, sg1 = torch.tensor([0.25], **f64), torch.tensor([2.0], **f64)

@@ -40,20 +40,53 @@ def _worker(rank, world, port, q):
 
         # ---- vvv: vector adjoints are shard-local, the value needs the exchange
         class VVV:
+            def __init__(self, sigma):
+                self.sg = sigma
+                self.undone = None
+
             def sigma_check(self):
-                return torch.tensor([float((sg[b:e] <= 0).sum())], dtype=torch.float64)
+                return torch.tensor([float((self.sg[b:e] <= 0).sum())], dtype=torch.float64)
+
+            def contrib(self, seed):
+                ok = self.sg[b:e] > 0
+                with np.errstate(all="ignore"):
+                    g = seed * (mu[b:e] - x[b:e]) / (self.sg[b:e] * self.sg[b:e])
+                return np.where(ok, g, 0.0)
 
             def partial(self, cnt, seed):
-                assert cnt is not None and cnt.item() == 0
-                z = (x[b:e] - mu[b:e]) / sg[b:e]
-                self.xa = seed * (mu[b:e] - x[b:e]) / (sg[b:e] * sg[b:e])
-                return torch.tensor([np.sum(z * z), np.sum(np.log(sg[b:e])), 0.0, 0.0], dtype=torch.float64)
+                s_ = self.sg[b:e]
+                bad = float((s_ <= 0).sum())
+                with np.errstate(all="ignore"):
+                    z = (x[b:e] - mu[b:e]) / s_
+                    sums = [np.sum(z * z), np.sum(np.log(s_))]
+                self.xa = np.zeros(e - b)
+                if cnt is None or cnt.item() == 0:        # strict form: no adjoint when the global count says invalid
+                    self.xa = self.xa + self.contrib(seed)
+                return torch.tensor([sums[0], sums[1], 0.0, bad], dtype=torch.float64)
 
             def finish(self, part, n_total, seed):
-                return -0.5 * part[0].item() - part[1].item()
-        ops = VVV()
+                return -np.inf if part[3].item() != 0 else -0.5 * part[0].item() - part[1].item()
+
+            def undo(self, part, seed):
+                self.undone = part[3].item() != 0
+                if self.undone:
+                    self.xa = self.xa - self.contrib(seed)
+        ops = VVV(sg)
         out["vvv"] = sharding.sharded_normal_autodiff(ops, ar, 3, n, seed, True)
         out["vvv_xa"] = (b, e, ops.xa)
+        assert ops.undone is False
+        ops = VVV(sg)
+        out["vvv_strict"] = sharding.sharded_normal_autodiff(ops, ar, 3, n, seed, True, strict=True)
+        assert out["vvv_strict"] == out["vvv"] and ops.undone is None
+        # one invalid sigma in the LAST rank's shard: every rank must end with -inf and untouched (zero) adjoints,
+        # through the optimistic pass + undo and through the strict pre-pass alike
+        sg_bad = sg.copy()
+        sg_bad[n - 2] = -0.5
+        for strict in (False, True):
+            ops = VVV(sg_bad)
+            v = sharding.sharded_normal_autodiff(ops, ar, 3, n, seed, True, strict=strict)
+            assert v == -np.inf and np.all(ops.xa == 0.0), (rank, strict)
+            assert ops.undone is (None if strict else True)
 
         # ---- vss: scalar mu / sigma adjoints are formed from the all-reduced sums
         class VSS:
