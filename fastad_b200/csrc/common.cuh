@@ -106,10 +106,10 @@ __device__ __forceinline__ void grid_finish(double (&acc)[NCH], double* smem, do
         __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
         is_last = (t == gridDim.x - 1);
+        if (is_last) __threadfence();      // acquire side, once: the barrier below orders the other threads' ld.cg reads after it
     }
     __syncthreads();
     if (!is_last) return;
-    __threadfence();
     double tot[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) tot[c] = 0.0;

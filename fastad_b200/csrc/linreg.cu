@@ -280,18 +280,51 @@ linreg_tma_kernel(LinregArgs a, const __grid_constant__ CUtensorMap xmap, int bo
     double* mine = cta_partials + (size_t)blockIdx.x * (a.cols + 1);
     if (threadIdx.x == 0) mine[0] = rr_s;
     if ((int)threadIdx.x < cols) mine[1 + threadIdx.x] = g_s[threadIdx.x];
-    __threadfence();
     consumer_bar();
-    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    // ONE thread publishes the row: its fence is cumulative over the stores the barrier ordered before it
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (is_last) __threadfence();             // acquire side; the rows are read with ld.cg below
+    }
     consumer_bar();
     if (!is_last) return;
-    __threadfence();
+    // last CTA: warp q sums rows q, q + 4, ... (lane = slot, slot + 32, slot + 64), eight rows' loads in flight per lane,
+    // then the four warp sums in warp order (the 65 single-thread walks over 296 rows this replaces cost ~6 us)
+    const int nslot = cols + 1;
+    double acc3[3] = {0.0, 0.0, 0.0};
+    {
+        const size_t stride = a.cols + 1;
+        unsigned b = warp;
+        for (; b + 28 < gridDim.x; b += 32) {
+            double v[8][3];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int slot = lane + 32 * k;
+                    v[u][k] = slot < nslot ? __ldcg(&cta_partials[(size_t)(b + 4 * u) * stride + slot]) : 0.0;
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc3[k] += v[u][k];
+        }
+        for (; b < gridDim.x; b += 4)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int slot = lane + 32 * k;
+                if (slot < nslot) acc3[k] += __ldcg(&cta_partials[(size_t)b * stride + slot]);
+            }
+    }
+    double* red = pt_s;                           // [4][96] of the 512 doubles (the tile loop is over)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) red[warp * 96 + lane + 32 * k] = acc3[k];
+    consumer_bar();
     double mine_acc = 0.0;
-    if ((int)threadIdx.x < cols + 1) {
-        double acc = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(&cta_partials[(size_t)b * (a.cols + 1) + threadIdx.x]);
-        out[threadIdx.x] = acc;
-        mine_acc = acc;
+    if ((int)threadIdx.x < nslot) {
+        mine_acc = ((red[threadIdx.x] + red[96 + threadIdx.x]) + red[192 + threadIdx.x]) + red[288 + threadIdx.x];
+        out[threadIdx.x] = mine_acc;
     }
     if (threadIdx.x == 0) *ticket = 0u;
     // fused exchange: the reduced partials go straight to every rank's mailbox over NVLink (p2p_device.cuh)

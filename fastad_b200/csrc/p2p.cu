@@ -5,10 +5,11 @@
 // that size a collective is pure latency: NCCL's all-reduce costs 15-25 us per call on this box against
 // 60-800 us of kernel time.  Here every rank owns a mailbox in its HBM, exported to the other ranks of the
 // node with CUDA IPC; the all-reduce is one tiny kernel per rank:
-//   push   my n doubles into slot[my rank] of EVERY rank's mailbox (peer stores through NVLink / NVSwitch),
-//          fence (system scope), then raise flag[my rank] = sequence number in every mailbox;
-//   wait   until all flags of MY mailbox carry this sequence number (bounded spin);
-//   reduce the world's slots in rank order (every rank forms the bit-identical sum) into the caller's buffer.
+//   push   my n doubles into entry [my rank] of EVERY rank's mailbox (peer stores through NVLink / NVSwitch); each double
+//          travels as two 8-byte words {32 data bits | 32 sequence bits}: the flag is IN the payload (p2p_device.cuh),
+//          no fence, no separate flag store;
+//   wait   until the words of MY mailbox carry this sequence number (bounded spin per element);
+//   reduce the world's entries in rank order (every rank forms the bit-identical sum) into the caller's buffer.
 // Two payload buffers alternate by sequence parity: a rank can only start evaluation k + 2 after all ranks
 // raised flag k + 1, i.e. after they finished reading buffer k.  No NCCL, no host synchronisation.
 #include <cstring>
@@ -81,26 +82,14 @@ __global__ void __launch_bounds__(P2P_MAXN)
 p2p_allreduce_kernel(P2PArgs a)
 {
     const P2PLink& l = a.link;
-    const int t = threadIdx.x, b = (int)(l.seq & 1);
-    // peer stores (NVLink; r == rank is local): consecutive threads write consecutive doubles of one mailbox
+    const int t = threadIdx.x;
+    // peer stores (NVLink; r == rank is local): consecutive threads write consecutive 16-byte entries of one mailbox
     for (int idx = t; idx < a.n * l.world; idx += blockDim.x) {
         const int r = idx / a.n, k = idx - r * a.n;
-        l.peer[r]->slot[b][l.rank][k] = a.buf[k];
+        p2p_send(l, r, k, a.buf[k]);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (t < l.world) {
-        __threadfence_system();      // release by the flag's writer (cumulative over the stores ordered before the barrier)
-        *reinterpret_cast<volatile unsigned long long*>(&l.peer[t]->flag[l.rank]) = l.seq;
-        p2p_wait_flag(l, t);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t < a.n) {
-        double s = 0.0;
-        for (int r = 0; r < l.world; ++r) s += *reinterpret_cast<volatile double*>(&l.local->slot[b][r][t]);
-        a.buf[t] = p2p_poison(l, s);
-    }
+    __syncthreads();                 // every thread has read buf[] before any thread overwrites it
+    if (t < a.n) a.buf[t] = p2p_pull(l, t, a.n);
 }
 
 static void fill_link(const P2PState& s, P2PLink* out)

@@ -7,9 +7,13 @@ namespace fadb {
 constexpr int P2P_MAXN = 128;        // doubles per exchange
 constexpr int P2P_MAXW = 16;         // ranks per node
 
+// Flag-in-payload layout (the scheme of NCCL's LL protocol): a double travels as two 8-byte words, each
+// {32 data bits | low 32 bits of the exchange's sequence number << 32}.  An aligned 8-byte store is single-copy atomic, so
+// a word whose flag half matches carries valid data -- the receiver needs no separate flag, the sender no fence between
+// payload and flag.  (The previous protocol: payload stores, fence.sys, CTA barrier, fence.sys, flag store, flag wait:
+// 8-10 us per exchange, most of it the two system-scope fences draining peer stores.)
 struct Mailbox {                     // lives in device memory, one per rank
-    double slot[2][P2P_MAXW][P2P_MAXN];
-    unsigned long long flag[P2P_MAXW];
+    unsigned long long ll[2][P2P_MAXW][P2P_MAXN][2];   // [sequence parity][sender][element][half]
     unsigned long long error;        // STICKY: sequence number of the first exchange whose wait timed out (0 = healthy)
 };
 
@@ -32,55 +36,58 @@ __device__ __forceinline__ unsigned long long p2p_now_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// Wait until rank r's flag carries this exchange's sequence number.  A peer that never arrives (dead process, wrong
-// rank count) must not yield a plausible number: on timeout the sticky error words are set -- the device one poisons
-// this and every later exchange (p2p_poison), the host one makes the next host entry return FADB_ERR_STATE.
-__device__ __forceinline__ void p2p_wait_flag(const P2PLink& l, int r)
-{
-    volatile unsigned long long* f = &l.local->flag[r];
-    if (*f >= l.seq) return;
-    const unsigned long long t0 = p2p_now_ns();
-    while (*f < l.seq) {
-        if (p2p_now_ns() - t0 > l.timeout_ns) {
-            atomicCAS(&l.local->error, 0ull, l.seq);
-            if (l.host_error) { *reinterpret_cast<volatile unsigned long long*>(l.host_error) = l.seq; __threadfence_system(); }
-            break;
-        }
-    }
-}
 // NaN once any wait on this mailbox has timed out (read after the waits of the current exchange are over)
 __device__ __forceinline__ double p2p_poison(const P2PLink& l, double v)
 {
     return *reinterpret_cast<volatile unsigned long long*>(&l.local->error) ? __longlong_as_double(0x7ff8000000000000ll) : v;
 }
 
-// Called by ALL threads of the (last) CTA that holds the reduced values: thread j < n owns value v.
-// Pushes v into slot[rank][j] of every mailbox, fences, raises the flags.  `bar` is the CTA barrier to use.
-template <class Bar>
-__device__ __forceinline__ void p2p_push(const P2PLink& l, int j, int n, double v, Bar&& bar)
+// element k of this rank's contribution -> entry [rank][k] of rank r's mailbox (peer store over NVLink; r == rank is local)
+__device__ __forceinline__ void p2p_send(const P2PLink& l, int r, int k, double v)
 {
-    const int b = (int)(l.seq & 1);
-    if (j < n)
-        for (int r = 0; r < l.world; ++r) l.peer[r]->slot[b][l.rank][j] = v;
-    __threadfence_system();
-    bar();
-    if (j < l.world) {
-        __threadfence_system();      // release by the flag's writer: cumulative over the payload stores ordered before bar()
-        *reinterpret_cast<volatile unsigned long long*>(&l.peer[j]->flag[l.rank]) = l.seq;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v), f = (l.seq & 0xffffffffull) << 32;
+    unsigned long long* dst = l.peer[r]->ll[l.seq & 1][l.rank][k];
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((bits & 0xffffffffull) | f), "l"((bits >> 32) | f) : "memory");
+}
+// element k of rank r's contribution, once both of its words carry this exchange's sequence number.  A peer that never
+// arrives (dead process, wrong rank count) must not yield a plausible number: on timeout the sticky error words are set --
+// the device one poisons this and every later exchange (p2p_poison), the host one makes the next host entry return
+// FADB_ERR_STATE.
+__device__ __forceinline__ double p2p_recv(const P2PLink& l, int r, int k)
+{
+    const unsigned long long* src = l.local->ll[l.seq & 1][r][k];
+    const unsigned long long want = l.seq & 0xffffffffull;
+    unsigned long long w0, w1, t0 = 0;
+    while (true) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+        if ((w0 >> 32) == want && (w1 >> 32) == want) break;
+        if (*reinterpret_cast<volatile unsigned long long*>(&l.local->error)) break;      // already failed: do not wait again
+        const unsigned long long now = p2p_now_ns();
+        if (!t0) t0 = now;
+        else if (now - t0 > l.timeout_ns) {
+            atomicCAS(&l.local->error, 0ull, l.seq);
+            if (l.host_error) { *reinterpret_cast<volatile unsigned long long*>(l.host_error) = l.seq; __threadfence_system(); }
+            break;
+        }
     }
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
 
-// Called by all threads of a CTA (blockDim >= world): waits for every rank's flag, then thread j < n returns
-// the rank-ordered sum of slot[.][j] (NaN after a timeout); other threads return 0.
+// Called by ALL threads of the (last) CTA that holds the reduced values: thread j < n owns value v and sends it to every
+// rank.  (`bar`, the CTA barrier of the fenced protocol, is no longer needed; kept in the signature for the callers.)
+template <class Bar>
+__device__ __forceinline__ void p2p_push(const P2PLink& l, int j, int n, double v, Bar&&)
+{
+    if (j < n)
+        for (int r = 0; r < l.world; ++r) p2p_send(l, (l.rank + r) % l.world, j, v);      // own mailbox first, peers staggered by rank
+}
+
+// Thread j < n returns the rank-ordered sum of element j over all ranks (NaN after a timeout); other threads return 0.
 __device__ __forceinline__ double p2p_pull(const P2PLink& l, int j, int n)
 {
-    if ((int)threadIdx.x < l.world) p2p_wait_flag(l, (int)threadIdx.x);
-    __threadfence_system();
-    __syncthreads();
     double s = 0.0;
     if (j < n) {
-        const int b = (int)(l.seq & 1);
-        for (int r = 0; r < l.world; ++r) s += *reinterpret_cast<volatile double*>(&l.local->slot[b][r][j]);
+        for (int r = 0; r < l.world; ++r) s += p2p_recv(l, r, j);
         s = p2p_poison(l, s);
     }
     return s;
@@ -90,22 +97,17 @@ __device__ __forceinline__ double p2p_pull(const P2PLink& l, int j, int n)
 // finish kernels): push n <= P2P_MAXN values / wait for all ranks and return the rank-ordered sums.
 __device__ __forceinline__ void p2p_push1(const P2PLink& l, const double* v, int n)
 {
-    const int b = (int)(l.seq & 1);
     for (int r = 0; r < l.world; ++r)
-        for (int c = 0; c < n; ++c) l.peer[r]->slot[b][l.rank][c] = v[c];
-    __threadfence_system();
-    for (int r = 0; r < l.world; ++r) *reinterpret_cast<volatile unsigned long long*>(&l.peer[r]->flag[l.rank]) = l.seq;
+        for (int c = 0; c < n; ++c) p2p_send(l, (l.rank + r) % l.world, c, v[c]);
 }
 __device__ __forceinline__ void p2p_pull1(const P2PLink& l, double* out, int n)
 {
-    for (int r = 0; r < l.world; ++r) p2p_wait_flag(l, r);
-    __threadfence_system();
-    const int b = (int)(l.seq & 1);
     for (int c = 0; c < n; ++c) {
         double s = 0.0;
-        for (int r = 0; r < l.world; ++r) s += *reinterpret_cast<volatile double*>(&l.local->slot[b][r][c]);
-        out[c] = p2p_poison(l, s);
+        for (int r = 0; r < l.world; ++r) s += p2p_recv(l, r, c);
+        out[c] = s;
     }
+    for (int c = 0; c < n; ++c) out[c] = p2p_poison(l, out[c]);
 }
 
 // host side (p2p.cu): the link of the NEXT exchange (advances the sequence) / of the exchange just pushed
