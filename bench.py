@@ -706,19 +706,24 @@ def run_ours(args):
         # with an extra map between dot and pow (not recognised): tall GEMV kernels, two passes over X
         rows, cols = 1 << 20, 64
         Xh, yh, wt = synth.linreg_inputs(rows, cols)
-        for tag, inner in (("one_pass", False), ("generic_dot", True)):
+        L.fadb_glm_enable.argtypes, L.fadb_glm_enable.restype = [C.c_int], C.c_int
+        for tag, inner, glm in (("one_pass", False, 1), ("map_one_pass", True, 1), ("generic_dot", True, 0)):
             e = F.Expr()
             Xc, yc, w = e.const(Xh), e.const(yh), e.var((wt + 0.05).reshape(cols, 1))
             r = e.binary("sub", yc, e.dot(Xc, w))
-            if inner:
-                r = e.binary("mul", r, e.const(1.0 + 0 * yh))
+            if inner:          # a map between dot and the reduction: not the fixed least-squares shape
+                r = e.binary("mul", r, e.unary("exp", e.binary("mul", e.const(-0.01), e.binary("mul", r, r))))
             e.bind(e.sum(e.pow(2, r)))
+            prev_glm = L.fadb_glm_enable(glm)
 
             def ls_step(i):
                 F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
             t = timed_loop(ls_step, steps2, 3, world)
+            L.fadb_glm_enable(prev_glm)
             add(f"expr_least_squares_2^20x64_{tag}", 8 * rows * (cols + 1), t, steps2, rows, "rows",
-                {"note": "algorithmic bytes = one pass over X + y" + ("; this form needs two passes + a 24 B/row map stage" if inner else "")})
+                {"note": "algorithmic bytes = one pass over X + y"
+                         + ("; the map (r exp(-0.01 r^2)) runs inside the one-pass tile kernel specialised at bind time (fast=6)" if inner and glm else "")
+                         + ("; same expression with the one-pass route off: gemv -> map stage -> gemv^T, two passes over X" if inner and not glm else "")})
             del e
 
         # the same two expressions through the TYPE-FUSED path (include/fastad_b200/fused.cuh): the

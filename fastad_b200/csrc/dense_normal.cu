@@ -72,6 +72,7 @@ struct CholSmem {
 __global__ void __launch_bounds__(256)
 dn_chol_step(int n, double* L, double* F, double* diag, int k0, int pc, double* flag)
 {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CholSmem& S = *reinterpret_cast<CholSmem*>(smem_raw);
     const int t = threadIdx.x, r = t & 31;
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
 dn_gemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
         double beta, double* C, int ldc, int kmode, int lower_only)
 {
+    pdl_prologue();
     gemm_tile<BT, TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
 }
 
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
 dn_gemm_mma(int m, int n, int k, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
             double beta, double* C, int ldc, int kmode, int lower_only)
 {
+    pdl_prologue();
     gemm_tile_mma<BT, TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
 }
 
@@ -404,6 +407,7 @@ template <int BT>
 __global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
 dn_trtri_level(int n, double* W, double* T, const TrNode* __restrict__ nodes, int phase)
 {
+    pdl_prologue();
     const TrNode nd = nodes[blockIdx.z];
     double* Ainv = W + nd.off + (size_t)nd.off * n;
     double* Bm = W + (nd.off + nd.n1) + (size_t)nd.off * n;
@@ -418,6 +422,7 @@ template <int BT>
 __global__ void __launch_bounds__(256, BT == 128 ? 1 : 3)
 dn_trtri_level_mma(int n, double* W, double* T, const TrNode* __restrict__ nodes, int phase)
 {
+    pdl_prologue();
     const TrNode nd = nodes[blockIdx.z];
     double* Ainv = W + nd.off + (size_t)nd.off * n;
     double* Bm = W + (nd.off + nd.n1) + (size_t)nd.off * n;
@@ -500,12 +505,12 @@ static void gemm(Context& c, int m, int n, int k, double alpha, const double* A,
     const long long t128 = (long long)((m + 127) / 128) * ((n + 127) / 128) / (lower_only ? 2 : 1);
     if (big_tiles(c, t128)) {
         dim3 grid((m + 127) / 128, (n + 127) / 128);
-        if (use_dmma()) dn_gemm_mma<128, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
-        else dn_gemm<128, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        if (use_dmma()) launch_pdl(dn_gemm_mma<128, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        else launch_pdl(dn_gemm<128, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
     } else {
         dim3 grid((m + 63) / 64, (n + 63) / 64);
-        if (use_dmma()) dn_gemm_mma<64, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
-        else dn_gemm<64, TA, TB><<<grid, 256, 0, c.stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        if (use_dmma()) launch_pdl(dn_gemm_mma<64, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+        else launch_pdl(dn_gemm<64, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
     }
     c.launches++;
 }
@@ -612,7 +617,7 @@ static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const d
         for (int k0 = K0; k0 < Kend; k0 += DB) {
             const int m = N - k0 - DB, pc = Kend - (k0 + DB);
             const int grid = m > 0 ? (m + CS_ROWS - 1) / CS_ROWS : 1;
-            dn_chol_step<<<grid, 256, sizeof(CholSmem), st>>>(N, w->L, w->Y, w->diag, k0, m > 0 ? pc : 0, w->scal);
+            launch_pdl(dn_chol_step, dim3(grid), dim3(256), sizeof(CholSmem), st, N, w->L, w->Y, w->diag, k0, m > 0 ? pc : 0, w->scal);
             c->launches++;
         }
         const int m = N - Kend;
@@ -630,20 +635,20 @@ static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const d
         if (big_tiles(*c, t128)) {
             dim3 grid((lv.max_n2 + 127) / 128, (lv.max_n1 + 127) / 128, lv.count);
             if (use_dmma()) {
-                dn_trtri_level_mma<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-                dn_trtri_level_mma<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+                launch_pdl(dn_trtri_level_mma<128>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 0);
+                launch_pdl(dn_trtri_level_mma<128>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 1);
             } else {
-                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-                dn_trtri_level<128><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+                launch_pdl(dn_trtri_level<128>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 0);
+                launch_pdl(dn_trtri_level<128>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 1);
             }
         } else {
             dim3 grid((lv.max_n2 + 63) / 64, (lv.max_n1 + 63) / 64, lv.count);
             if (use_dmma()) {
-                dn_trtri_level_mma<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-                dn_trtri_level_mma<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+                launch_pdl(dn_trtri_level_mma<64>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 0);
+                launch_pdl(dn_trtri_level_mma<64>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 1);
             } else {
-                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 0);
-                dn_trtri_level<64><<<grid, 256, 0, st>>>(N, w->Y, w->X, tp->dev + lv.first, 1);
+                launch_pdl(dn_trtri_level<64>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 0);
+                launch_pdl(dn_trtri_level<64>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 1);
             }
         }
         c->launches += 2;

@@ -309,6 +309,39 @@ __global__ void transpose_bwd_kernel(int m, int k, const double* __restrict__ A,
     const double a = A[j + (size_t)i * k];
     Xadj[idx] = (mode == 2) ? a : Xadj[idx] + a;
 }
+// ---- one-pass dot -> map -> sum (csrc/glm_kernel.cuh, compiled by NVRTC): host mirror of its argument block and the
+// scalar epilogue.  out = {channel totals [nacc], X^T a [cols]} as the kernel's last CTA left them.
+struct GlmArgsHost {
+    unsigned long long rows;
+    int cols, pad;
+    const double* w;
+    double seed;
+    double* cta_partials;
+    unsigned int* ticket;
+    double* out;
+    const double* lp_val[MAXL_JIT];
+};
+struct GlmFinish {
+    int nacc, cols, nscal;
+    double* w_adj; int w_mode;           // 0 none, 1 accumulate, 2 assign
+    double* s_adj[MAXCH_JIT]; int s_ch[MAXCH_JIT]; int s_mode[MAXCH_JIT];
+};
+__global__ void glm_finish_kernel(GlmFinish f, const double* __restrict__ out, double* value)
+{
+    const int t = threadIdx.x;
+    if (t == 0) value[0] = out[0];                                           // SumElemNode::feval (sum.hpp:156-160)
+    if (t < f.nscal) {                                                       // VarView::beval of a scalar variable (var_view.hpp:91-94)
+        const double g = out[f.s_ch[t]];
+        f.s_adj[t][0] = f.s_mode[t] == 2 ? g : f.s_adj[t][0] + g;
+    }
+    if (f.w_adj)
+        for (int j = t; j < f.cols; j += blockDim.x) {                       // DotNode::beval: w_adj += X^T a (dot.hpp:100)
+            const double g = out[f.nacc + j];
+            f.w_adj[j] = f.w_mode == 2 ? g : f.w_adj[j] + g;
+        }
+}
+int linreg_encode_xmap(void* map128, const double* X, size_t rows, size_t cols);   // linreg.cu (CUtensorMap, 128 bytes, 64-aligned)
+
 __global__ void fill_kernel(double* p, size_t n, double v)
 {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -347,6 +380,7 @@ struct Stage {
     std::vector<int> leaf_stage;   // producing stage of a boundary leaf (-1 otherwise)
     std::map<int, int> eq_slot;    // placeholder node id -> slot holding its current value
     std::set<int> assigned;        // placeholder node ids assigned in this stage
+    std::map<int, int> boundary_slot;   // node id of a producer-stage result -> the slot that already reads it in this stage
     int term = T_NONE, root = -1, nx = -1, nm = -1, ns = -1, mu_vec = 0, sig_vec = 0;
     int sig_leaf = -1;             // leaf index of a scalar sigma (T_NORMAL)
     bool needs_check = false;      // log-pdf whose validity is a property of ALL elements
@@ -384,6 +418,9 @@ struct Stage {
     const double *f_mu = nullptr, *f_sig = nullptr; double *f_muadj = nullptr, *f_sigadj = nullptr;
     int f_shape = 0; const double* f_X = nullptr; const double* f_w = nullptr; double* f_wadj = nullptr;
     size_t f_rows = 0, f_cols = 0; double* f_part = nullptr;
+    // fast == 6: the one-pass dot -> map -> sum kernel (glm_kernel.cuh): leaf of the dot result, per-row operand slots
+    int g_dot_leaf = -1, g_nvec = 0; std::vector<int> g_vec_slot; int g_dot_stage = -1;
+    JitKernel g_jit; int g_jit_state = 0; double* g_ws = nullptr; size_t g_ws_cap = 0;
     double* gv_part = nullptr; int gv_grid = 0;    // tall dot stage: per-CTA partial rows of L^T A
     double* wr_part = nullptr; int wr_grid = 0;    // wide dot stage (large p, small m x k): per-CTA partials of A R^T
 };
@@ -391,6 +428,8 @@ struct Stage {
 }  // namespace fadb
 
 using namespace fadb;
+
+static std::atomic<int> g_glm_enabled{1};     // fadb_glm_enable: the one-pass dot -> map -> sum route (A/B runs, tests)
 
 struct fadb_expr {
     std::vector<ENode> nodes;
@@ -452,6 +491,11 @@ struct fadb_expr {
         if (barrier(n.kind) || !same) {
             // produced by another stage: a reduction, a dot, or a sub-expression of another shape
             if (!barrier(n.kind) && !bcast) { err = "shape mismatch between elementwise operands"; return -1; }
+            // The same producer node read twice by this stage (eta = dot(X, w) + b used in two terms): the reference evaluates
+            // its copy of the sub-expression twice with identical results; here it is planned once and its slot reused, the
+            // adjoints of both uses meet in that slot.  Not across an assignment of this stage (the operands may have changed).
+            auto seen = st.boundary_slot.find(nid);
+            if (seen != st.boundary_slot.end()) return seen->second;
             int sidx = plan_stage(nid);
             if (sidx < 0) return -1;
             Stage& ps = *plan[sidx];
@@ -459,7 +503,9 @@ struct fadb_expr {
             if (ps.out_size != st.N && !sc) { err = "shape mismatch at a stage boundary"; return -1; }
             int lf = leaf_index(st, -1, nullptr, nullptr, sc, 2, sidx);
             st.leaves[lf].adj_mode = 2;       // pointers are patched at bind time
-            return emit(st, Ins{I_LEAF, 0, 0, 0, lf, 0, 0.0});
+            const int slot = emit(st, Ins{I_LEAF, 0, 0, 0, lf, 0, 0.0});
+            st.boundary_slot[nid] = slot;
+            return slot;
         }
         switch (n.kind) {
         case N_UNARY: {
@@ -493,6 +539,7 @@ struct fadb_expr {
             int s = emit(st, Ins{I_EQ, 0, a, 0, lf, 0, 0.0});
             st.eq_slot[n.ch[0]] = s;
             st.assigned.insert(n.ch[0]);
+            st.boundary_slot.clear();
             return s;
         }
         case N_GLUE: {
@@ -504,11 +551,14 @@ struct fadb_expr {
             // cond ; JZ else ; <if> ; JMP end ; else: <else> ; end: PHI    (if_else.hpp:64-78)
             int c = lower(n.ch[0], st); if (c < 0) return -1;
             int jz = emit(st, Ins{I_JZ, 0, c, 0, 0, 0, 0.0});
+            const std::map<int, int> outer = st.boundary_slot;   // slots loaded inside a branch exist only when it is taken
             int a = lower(n.ch[1], st); if (a < 0) return -1;
             int jmp = emit(st, Ins{I_JMP, 0, c, 0, jz, 0, 0.0});
             st.prog[jz].b = (int)st.prog.size();
+            st.boundary_slot = outer;
             int b = lower(n.ch[2], st); if (b < 0) return -1;
             st.prog[jmp].b = (int)st.prog.size();
+            st.boundary_slot = outer;
             return emit(st, Ins{I_PHI, 0, a, b, c, 0, (double)jmp});
         }
         case N_OPEQ: {
@@ -520,6 +570,7 @@ struct fadb_expr {
             int s = emit(st, Ins{I_OPEQ, n.fn, a, old, lf, 0, 0.0});
             st.eq_slot[n.ch[0]] = s;
             st.assigned.insert(n.ch[0]);
+            st.boundary_slot.clear();
             return s;
         }
         default: break;
@@ -744,6 +795,124 @@ struct fadb_expr {
         return true;
     }
 
+    bool detect_lsq(Stage& st)
+    {
+        if (st.prog.size() != 4 || st.root != 3) return false;
+        const Ins &Ip = st.prog[3], &Is = st.prog[2];
+        if (Ip.op != I_POW || Ip.fn != 2 || Ip.a != 2 || Is.op != I_BINARY || Is.fn != FADB_SUB) return false;
+        if (st.prog[Is.a].op != I_LEAF || st.prog[Is.b].op != I_LEAF) return false;
+        int ld = st.prog[Is.a].leaf, ly = st.prog[Is.b].leaf;
+        if (st.leaf_stage[ld] < 0) std::swap(ld, ly);
+        if (st.leaf_stage[ld] < 0 || st.leaf_stage[ly] >= 0 || st.leaves[ly].scalar || st.leaves[ly].adj_mode != 0) return false;
+        Stage& ds = *plan[st.leaf_stage[ld]];
+        if (ds.type != 1 || ds.p != 1 || ds.L.stage >= 0 || ds.R.stage >= 0 || ds.L.adj_mode != 0 || ds.k > 64) return false;   // beyond one 64-column block the two-pass GEMV kernels are faster (measured)
+        st.fast = 5;
+        st.f_X = ds.L.val; st.f_w = ds.R.val; st.f_wadj = ds.R.adj_mode ? ds.R.adj : nullptr;
+        st.f_rows = ds.m; st.f_cols = ds.k;
+        st.f_x = st.leaves[ly].val;
+        return true;
+    }
+
+    // sum(f(dot(X, w), per-row constants, scalars)) with X constant and at most 64 columns: the row adjoint of the product
+    // depends on the row alone (root seed known up front), so the map runs inside the one-pass TMA kernel (glm_kernel.cuh)
+    // and X crosses HBM once instead of twice.  Anything the kernel does not cover keeps fast == 0 (gemv -> stage -> gemv^T).
+    void detect_glm(Stage& st)
+    {
+        static const bool off = getenv("FADB_NO_GLM") != nullptr;
+        if (off || st.big || st.prog.size() > 48 || st.nch > 16 || st.N < 64 || st.N % 2 != 0) return;     // the TMA tile path needs an even row count
+        int ld = -1, nvec = 0;
+        std::vector<int> slot(st.leaves.size(), -1);
+        for (size_t l = 0; l < st.leaves.size(); ++l) {
+            const LeafDesc& L = st.leaves[l];
+            if (st.leaf_stage[l] >= 0) { if (ld >= 0 || L.scalar) return; ld = (int)l; continue; }
+            if (L.assigned) return;
+            if (L.scalar) { if (L.adj_mode == 2) return; continue; }
+            if (L.adj_mode != 0 || nvec >= 4) return;         // per-row operands: constants only (y, offsets, weights)
+            slot[l] = nvec++;
+        }
+        if (ld < 0) return;
+        for (const Ins& I : st.prog)
+            if (I.op != I_LEAF && I.op != I_CONST && I.op != I_UNARY && I.op != I_BINARY && I.op != I_POW) return;
+        Stage& ds = *plan[st.leaf_stage[ld]];
+        if (ds.type != 1 || ds.p != 1 || ds.L.stage >= 0 || ds.R.stage >= 0 || ds.L.adj_mode != 0 || ds.k > 64 || ds.k < 1 ||
+            (size_t)ds.m != st.N) return;
+        st.fast = 6;
+        st.g_dot_leaf = ld; st.g_nvec = nvec; st.g_vec_slot = slot; st.g_dot_stage = st.leaf_stage[ld];
+        st.f_rows = ds.m; st.f_cols = ds.k;
+    }
+
+    // program text of the one-pass kernel: the stage's constants (mode M_FB) + which leaf is the product, which are row operands
+    static bool glm_program_text(Stage& st, std::string& out)
+    {
+        if (st.enc.empty()) encode_stage(st);
+        std::string base;
+        if (!jit_program_text(st, M_FB, base)) return false;
+        std::ostringstream o;
+        o << base << "#define GLM_DOT_LEAF " << st.g_dot_leaf << "\n#define GLM_NVEC " << st.g_nvec
+          << "\n__device__ constexpr int GLM_VEC_SLOT[JIT_NLEAVES] = {";
+        for (size_t l = 0; l < st.g_vec_slot.size(); ++l) o << (l ? ", " : "") << st.g_vec_slot[l];
+        o << "};\n";
+        out = o.str();
+        return true;
+    }
+    static size_t glm_smem_bytes(const Stage& st)
+    {
+        const size_t stage_bytes = 64 * 64 * 8 + (size_t)std::max(st.g_nvec, 1) * 64 * 8;
+        return 3 * stage_bytes + (64 + 2 * 4 * 64 + 64 + 32) * sizeof(double) + 2 * 3 * sizeof(unsigned long long);
+    }
+
+    // can this call take the one-pass kernel?  (operands may have been rebound since the plan was made)
+    bool glm_usable(Context& c, Stage& st)
+    {
+        if (!g_glm_enabled.load() || !jit_enabled() || st.g_jit_state < 0) return false;
+        const Stage& ds = *plan[st.g_dot_stage];
+        if (st.f_rows % 2 != 0 || (reinterpret_cast<uintptr_t>(ds.L.val) & 15u)) return false;
+        for (size_t l = 0; l < st.leaves.size(); ++l)
+            if (st.g_vec_slot[l] >= 0 && (reinterpret_cast<uintptr_t>(st.leaves[l].val) & 15u)) return false;
+        if (st.g_jit_state == 1 && st.g_jit.gen != jit_generation()) st.g_jit_state = 0;
+        if (st.g_jit_state == 0) {
+            std::string text;
+            st.g_jit_state = (glm_program_text(st, text) && jit_get(c, text, &st.g_jit, 1, glm_smem_bytes(st)) == FADB_OK) ? 1 : -1;
+        }
+        return st.g_jit_state == 1;
+    }
+
+    int run_glm(Context& c, Stage& st, double seed)
+    {
+        const Stage& ds = *plan[st.g_dot_stage];
+        const int nacc = std::max(st.nch, 1), cols = (int)st.f_cols, nslot = nacc + cols;
+        const size_t ntiles = (st.f_rows + 63) / 64;
+        const int grid = (int)std::min<size_t>(ntiles, (size_t)c.sms * std::min(std::max(st.g_jit.per_sm, 1), 4));
+        const size_t need = (size_t)grid * nslot + nslot;
+        if (st.g_ws_cap < need) {
+            int rc = dev_alloc(need * sizeof(double), (void**)&st.g_ws);
+            if (rc) return rc;
+            st.g_ws_cap = need;
+        }
+        GlmArgsHost a;
+        a.rows = st.f_rows; a.cols = cols; a.pad = 0; a.w = ds.R.val; a.seed = seed;
+        a.cta_partials = st.g_ws; a.ticket = c.tickets + 20; a.out = st.g_ws + (size_t)grid * nslot;
+        for (size_t l = 0; l < (size_t)MAXL_JIT; ++l) a.lp_val[l] = l < st.leaves.size() ? st.leaves[l].val : nullptr;
+        alignas(64) unsigned char xmap[128];
+        int rc = linreg_encode_xmap(xmap, ds.L.val, st.f_rows, st.f_cols);
+        if (rc) return rc;
+        void* params[2] = {&a, xmap};
+        rc = jit_launch_params(st.g_jit, (unsigned)grid, 160, glm_smem_bytes(st), c.stream, params);
+        if (rc) return rc;
+        c.launches++;
+        GlmFinish f;
+        f.nacc = nacc; f.cols = cols; f.nscal = 0;
+        f.w_adj = ds.R.adj_mode ? ds.R.adj : nullptr; f.w_mode = ds.R.adj_mode;
+        for (const LeafDesc& L : st.leaves)
+            if (L.scalar && L.adj_mode != 0 && L.channel > 0 && f.nscal < MAXCH_JIT) {
+                f.s_adj[f.nscal] = L.adj; f.s_ch[f.nscal] = L.channel; f.s_mode[f.nscal] = L.adj_mode; ++f.nscal;
+            }
+        glm_finish_kernel<<<1, 64, 0, c.stream>>>(f, a.out, st.mval);
+        c.launches++;
+        FADB_CUDA(cudaGetLastError());
+        return FADB_OK;
+    }
+
     void detect_fast_paths()
     {
         if (plan.empty()) return;
@@ -754,19 +923,8 @@ struct fadb_expr {
         if (plan.size() == 2 && st.term != T_NORMAL && st.term != T_SUM) return;
         // sum(pow<2>(y - dot(X, w))) or sum(pow<2>(dot(X, w) - y)), X and y constant: least squares, one pass over X
         if (plan.size() == 2 && st.term == T_SUM) {
-            if (st.prog.size() != 4 || st.root != 3) return;
-            const Ins &Ip = st.prog[3], &Is = st.prog[2];
-            if (Ip.op != I_POW || Ip.fn != 2 || Ip.a != 2 || Is.op != I_BINARY || Is.fn != FADB_SUB) return;
-            if (st.prog[Is.a].op != I_LEAF || st.prog[Is.b].op != I_LEAF) return;
-            int ld = st.prog[Is.a].leaf, ly = st.prog[Is.b].leaf;
-            if (st.leaf_stage[ld] < 0) std::swap(ld, ly);
-            if (st.leaf_stage[ld] < 0 || st.leaf_stage[ly] >= 0 || st.leaves[ly].scalar || st.leaves[ly].adj_mode != 0) return;
-            Stage& ds = *plan[st.leaf_stage[ld]];
-            if (ds.type != 1 || ds.p != 1 || ds.L.stage >= 0 || ds.R.stage >= 0 || ds.L.adj_mode != 0 || ds.k > 64) return;   // beyond one 64-column block the two-pass GEMV kernels are faster (measured)
-            st.fast = 5;
-            st.f_X = ds.L.val; st.f_w = ds.R.val; st.f_wadj = ds.R.adj_mode ? ds.R.adj : nullptr;
-            st.f_rows = ds.m; st.f_cols = ds.k;
-            st.f_x = st.leaves[ly].val;
+            if (detect_lsq(st)) return;
+            detect_glm(st);
             return;
         }
         if (plan.size() == 1 && st.term == T_SUM && st.prog.size() == 2 && st.root == 1 && leaf_only(st, 0, &lf) &&
@@ -1344,6 +1502,7 @@ struct fadb_expr {
             if (rc) return rc;
             return fadb_lsq_finish(st.f_cols, st.f_part, st.f_wadj, seed, 0, st.mval);
         }
+        if (st.fast == 6) return run_glm(c, st, seed);
         return FADB_ERR_STATE;
     }
 
@@ -1359,8 +1518,8 @@ struct fadb_expr {
             what &= 1;
             if (!what) return FADB_OK;
         }
-        const bool fast = rs.fast != 0 && what == 3 && !seed_vec;
-        const size_t first = (fast && (rs.fast == 3 || rs.fast == 5)) ? plan.size() : 0;   // linreg / least squares subsume their dot stage
+        const bool fast = rs.fast != 0 && what == 3 && !seed_vec && (rs.fast != 6 || glm_usable(c, rs));
+        const size_t first = (fast && (rs.fast == 3 || rs.fast == 5 || rs.fast == 6)) ? plan.size() : 0;   // linreg / least squares / one-pass map subsume their dot stage
         if (what & 1) {
             for (size_t k = first; k + 1 < plan.size(); ++k) {
                 Stage& st = *plan[k];
@@ -1719,16 +1878,20 @@ int fadb_expr_jit_program(fadb_expr* e, int stage, int mode, char* buf, size_t c
 {
     EXPR_REQUIRE(e, e && buf && cap > 0, "fadb_expr_jit_program: null argument");
     EXPR_REQUIRE(e, e->planned, "fadb_expr_jit_program: plan first");
-    EXPR_REQUIRE(e, stage >= 0 && stage < (int)e->plan.size() && mode >= 1 && mode <= 3, "fadb_expr_jit_program: bad stage or mode");
+    EXPR_REQUIRE(e, stage >= 0 && stage < (int)e->plan.size() && ((mode >= 1 && mode <= 3) || mode == 6), "fadb_expr_jit_program: bad stage or mode");
     Stage& st = *e->plan[stage];
     std::string text;
     if (st.type != 0) { set_error("fastad_b200: not an elementwise stage"); return FADB_ERR_UNSUPPORTED; }
     if (st.enc.empty()) fadb_expr::encode_stage(st);
-    if (!fadb_expr::jit_program_text(st, mode, text)) { set_error("fastad_b200: stage is not specialisable"); return FADB_ERR_UNSUPPORTED; }
+    if (mode == 6) {         // the one-pass dot -> map -> sum kernel of a fast == 6 root stage
+        if (st.fast != 6 || !fadb_expr::glm_program_text(st, text)) { set_error("fastad_b200: not a one-pass (fast=6) stage"); return FADB_ERR_UNSUPPORTED; }
+    } else if (!fadb_expr::jit_program_text(st, mode, text)) { set_error("fastad_b200: stage is not specialisable"); return FADB_ERR_UNSUPPORTED; }
     if (text.size() + 1 > cap) { set_error("fastad_b200: buffer too small"); return FADB_ERR_ARG; }
     memcpy(buf, text.c_str(), text.size() + 1);
     return FADB_OK;
 }
+
+int fadb_glm_enable(int on) { return g_glm_enabled.exchange(on ? 1 : 0); }
 
 int fadb_expr_describe(fadb_expr* e, char* buf, size_t cap)
 {

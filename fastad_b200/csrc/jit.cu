@@ -16,6 +16,7 @@
 #include <nvrtc.h>
 
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -50,6 +51,7 @@ struct Driver {
     CUresult (*launch)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*occupancy)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*func_attr)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*func_set_attr)(CUfunction, CUfunction_attribute, int) = nullptr;
     bool ok = false;
 };
 struct Entry { CUmodule mod = nullptr; CUfunction fn = nullptr; int per_sm = 1; int regs = 0, local_bytes = 0; bool failed = false; };
@@ -104,7 +106,8 @@ bool init_locked()
     Driver& d = g_drv;
     if (!(drv("cuModuleLoadData", d.module_load) && drv("cuModuleUnload", d.module_unload) &&
           drv("cuModuleGetFunction", d.module_func) && drv("cuLaunchKernel", d.launch) &&
-          drv("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.occupancy) && drv("cuFuncGetAttribute", d.func_attr))) {
+          drv("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.occupancy) && drv("cuFuncGetAttribute", d.func_attr) &&
+          drv("cuFuncSetAttribute", d.func_set_attr))) {
         g_why = "driver entry points unavailable";
         return false;
     }
@@ -112,12 +115,14 @@ bool init_locked()
     return true;
 }
 
-// cubin -> module -> kernel handle + its occupancy at 128 threads
-bool finish_load(Entry& e, const std::vector<char>& bin)
+// cubin -> module -> kernel handle + its occupancy at the kernel's block size
+bool finish_load(Entry& e, const std::vector<char>& bin, int kind, size_t dyn_smem)
 {
     if (g_drv.module_load(&e.mod, bin.data()) != CUDA_SUCCESS) return false;
-    if (g_drv.module_func(&e.fn, e.mod, "fadb_stage_jit") != CUDA_SUCCESS) return false;
-    if (g_drv.occupancy(&e.per_sm, e.fn, 128, 0) != CUDA_SUCCESS || e.per_sm < 1) e.per_sm = 1;
+    if (g_drv.module_func(&e.fn, e.mod, kind == 1 ? "fadb_glm_jit" : "fadb_stage_jit") != CUDA_SUCCESS) return false;
+    if (dyn_smem > 48 * 1024 &&
+        g_drv.func_set_attr(e.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem) != CUDA_SUCCESS) return false;
+    if (g_drv.occupancy(&e.per_sm, e.fn, kind == 1 ? 160 : 128, dyn_smem) != CUDA_SUCCESS || e.per_sm < 1) e.per_sm = 1;
     g_drv.func_attr(&e.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, e.fn);
     g_drv.func_attr(&e.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, e.fn);
     e.failed = false;
@@ -133,14 +138,14 @@ bool jit_enabled()
     return g_enabled == 1;
 }
 
-std::string jit_source(const std::string& program) { return std::string(kJitPrelude) + program + kJitKernel; }
+std::string jit_source(const std::string& program, int kind = 0) { return std::string(kJitPrelude) + program + (kind == 1 ? kGlmKernel : kJitKernel); }
 
 // Returns 0 and a launchable kernel, or a negative code (caller falls back to the interpreter).
-int jit_get(const Context& c, const std::string& program, JitKernel* out)
+int jit_get(const Context& c, const std::string& program, JitKernel* out, int kind, size_t dyn_smem)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!init_locked()) return FADB_ERR_STATE;
-    const std::string key = std::to_string(c.device) + "|" + program;
+    const std::string key = std::to_string(c.device) + "|" + std::to_string(kind) + "|" + program;
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
         if (it->second.failed) return FADB_ERR_STATE;
@@ -151,7 +156,7 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
     }
     Entry e;
     e.failed = true;
-    const std::string src = jit_source(program);
+    const std::string src = jit_source(program, kind);
     static const std::string pf = std::string("-DFADB_JIT_PF_DIST=") + (getenv("FADB_JIT_PF_DIST") ? getenv("FADB_JIT_PF_DIST") : "1");
     static const std::string minb = getenv("FADB_JIT_MINB") ? std::string("-DFADB_JIT_MINB=") + getenv("FADB_JIT_MINB") : std::string();
     // optional on-disk cubin cache (FADB_JIT_CACHE_DIR): keyed by a hash of the full source text
@@ -168,7 +173,7 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
             size_t n;
             while ((n = fread(buf, 1, sizeof buf, f)) > 0) bin.insert(bin.end(), buf, buf + n);
             fclose(f);
-            if (!bin.empty() && finish_load(e, bin)) {
+            if (!bin.empty() && finish_load(e, bin, kind, dyn_smem)) {
                 g_cache.emplace(key, e);
                 ++g_hits;
                 out->fn = e.fn; out->per_sm = e.per_sm; out->regs = e.regs; out->local_bytes = e.local_bytes; out->gen = g_generation.load();
@@ -190,7 +195,7 @@ int jit_get(const Context& c, const std::string& program, JitKernel* out)
             std::vector<char> bin;
             if (g_rtc.cubin_size(prog, &n) == NVRTC_SUCCESS && n > 0) {
                 bin.resize(n);
-                if (g_rtc.cubin(prog, bin.data()) == NVRTC_SUCCESS && finish_load(e, bin) && !cache_file.empty()) {
+                if (g_rtc.cubin(prog, bin.data()) == NVRTC_SUCCESS && finish_load(e, bin, kind, dyn_smem) && !cache_file.empty()) {
                     if (FILE* f = fopen((cache_file + ".tmp").c_str(), "wb")) {
                         const bool okw = fwrite(bin.data(), 1, bin.size(), f) == bin.size();
                         fclose(f);
@@ -232,6 +237,14 @@ int jit_launch(const JitKernel& k, unsigned grid, unsigned block, cudaStream_t s
     return FADB_OK;
 }
 
+int jit_launch_params(const JitKernel& k, unsigned grid, unsigned block, size_t dyn_smem, cudaStream_t st, void** params)
+{
+    const CUresult r = g_drv.launch(reinterpret_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, (unsigned)dyn_smem, reinterpret_cast<CUstream>(st), params, nullptr);
+    if (r != CUDA_SUCCESS) { set_error("fastad_b200: launch of a specialised kernel failed (CUresult " + std::to_string((int)r) + ")"); return FADB_ERR_CUDA; }
+    ++g_launched;
+    return FADB_OK;
+}
+
 }  // namespace fadb
 
 using namespace fadb;
@@ -267,7 +280,7 @@ extern "C" int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, c
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_state == 0) init_locked();
     if (!g_rtc.create || !g_rtc.compile) { set_error("fastad_b200: libnvrtc not available"); return FADB_ERR_STATE; }
-    const std::string src = jit_source(program);
+    const std::string src = jit_source(program, strstr(program, "#define GLM_DOT_LEAF") ? 1 : 0);     // the one-pass kernel's programs carry its defines
     nvrtcProgram prog = nullptr;
     if (g_rtc.create(&prog, src.c_str(), "fadb_stage_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return FADB_ERR_STATE;
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DFADB_JIT=1", "-diag-suppress=177", "--ptxas-options=-v"};

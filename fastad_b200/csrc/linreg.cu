@@ -410,6 +410,13 @@ static int encode_xmap(CUtensorMap* map, const double* X, size_t rows, size_t co
     return FADB_OK;
 }
 
+// for expr.cu's one-pass dot -> map -> sum kernel (glm_kernel.cuh): same tile geometry
+int linreg_encode_xmap(void* map128, const double* X, size_t rows, size_t cols)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    return encode_xmap(static_cast<CUtensorMap*>(map128), X, rows, cols);
+}
+
 static double* g_ws[kMaxDevices] = {nullptr};
 static size_t g_ws_cap[kMaxDevices] = {0};
 static ShutdownHook g_ws_release([](int d) { cudaFree(g_ws[d]); g_ws[d] = nullptr; g_ws_cap[d] = 0; });

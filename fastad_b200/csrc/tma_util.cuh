@@ -1,7 +1,9 @@
 // tma_util.cuh — mbarrier / bulk-copy (TMA) PTX wrappers shared by the kernels that stage tiles in shared memory
 // (linreg.cu: 2-D tensor tiles of X; black_scholes.cu: 1-D bulk tiles of the SoA option streams).
 #pragma once
+#ifndef __CUDACC_RTC__   // NVRTC (glm_kernel.cuh): the integer typedefs come from fastmath.cuh
 #include <cstdint>
+#endif
 
 namespace fadb {
 

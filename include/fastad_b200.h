@@ -385,6 +385,10 @@ int fadb_jit_enable(int on);
 int fadb_jit_stats(unsigned long long out[4]);
 const char* fadb_jit_diagnostics(void);
 int fadb_expr_jit_program(fadb_expr*, int stage, int mode, char* buf, size_t cap);
+/* sum(f(dot(X, w), per-row constants, scalars)) with X constant and <= 64 columns is evaluated in ONE pass over X (the map runs
+ * inside the tile kernel, csrc/glm_kernel.cuh; `fast=6` in fadb_expr_describe) instead of gemv -> map -> gemv^T.
+ * fadb_glm_enable(0) turns the route off (returns the previous setting); fadb_expr_jit_program(.., mode 6) is its program. */
+int fadb_glm_enable(int on);
 int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, char* log, size_t log_cap);
 
 #endif /* !__CUDACC_RTC__ */

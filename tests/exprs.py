@@ -184,6 +184,19 @@ def least_squares(rows, cols, flipped=False, x_var=False, inner=False):
     return build
 
 
+def glm_logistic(rows, cols, weights=False):
+    def build(e):   # logistic-regression log-likelihood: sum(w_i (y_i eta_i - log(1 + exp(eta_i)))), eta = dot(X, beta) + b
+        X = np.asfortranarray(RNG.normal(size=(rows, cols)) / np.sqrt(cols))
+        y = RNG.integers(0, 2, rows).astype(np.float64)
+        beta, b = e.var(0.3 * RNG.normal(size=cols)), e.var(0.2)
+        eta = e.binary("add", e.dot(e.const(X), beta), b)
+        ll = e.binary("sub", e.binary("mul", e.const(y), eta), e.unary("log", e.binary("add", e.const(1.0), e.unary("exp", eta))))
+        if weights:
+            ll = e.binary("mul", e.const(RNG.uniform(0.5, 1.5, rows)), ll)
+        return e.sum(ll), [beta, b], 0.75
+    return build
+
+
 def many_scalar_params(n, nparams):
     def build(e):   # a vector model with more scalar parameters than the interpreter has reduction channels
         x = e.var(RNG.uniform(0.2, 1.5, n))
@@ -549,7 +562,11 @@ CASES = {
     "least_squares": least_squares(5000, 64),
     "least_squares_flipped_odd": least_squares(4099, 7, flipped=True),
     "least_squares_small": least_squares(100, 3),
-    "least_squares_tall_generic": least_squares(6001, 19, inner=True),
+    "least_squares_tall_generic": least_squares(6001, 19, inner=True),          # odd row count: gemv -> stage -> gemv^T
+    "glm_least_squares_inner": least_squares(6000, 19, inner=True),            # even: the one-pass kernel (fast=6)
+    "glm_logistic": glm_logistic(4160, 64),
+    "glm_logistic_weighted_ragged": glm_logistic(4290, 5, weights=True),        # last tile holds 2 of 64 rows
+    "glm_logistic_tiny": glm_logistic(66, 3),
     "least_squares_x_variable": least_squares(4500, 5, x_var=True),
     "black_scholes_call": black_scholes_vec(2001),
     "black_scholes_put": black_scholes_vec(2001, put=True),

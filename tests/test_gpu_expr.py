@@ -137,6 +137,62 @@ def test_logpdf_root_seed_zero_leaves_producers_untouched(fb, engine):
     np.testing.assert_array_equal(e.adj(w), a1[0])
 
 
+@pytest.mark.parametrize("name", ["glm_logistic", "glm_logistic_weighted_ragged", "glm_logistic_tiny", "glm_least_squares_inner"])
+def test_one_pass_dot_map_sum_route(fb, name):
+    # sum(f(dot(X, w), row constants, scalars)): ONE specialised launch (glm_kernel.cuh) + the scalar epilogue instead of
+    # gemv -> stage -> gemv^T; value and adjoints against the oracle AND against the three-launch route of the same plan
+    build = exprs.CASES[name]
+    ov, oadj, _, _ = _run(build, O.OracleExpr)
+    res = {}
+    for on in (True, False):
+        prev = fb.lib().fadb_glm_enable(1 if on else 0)
+        try:
+            exprs.RNG = np.random.default_rng(20261019)
+            e = fb.Expr()
+            root, variables, seed = build(e)
+            e.bind(root)
+            assert "fast=6" in e.describe()
+            l0, j0 = fb.lib().fadb_launch_count(), fb.jit_stats()
+            v = e.autodiff(seed)
+            l1, j1 = fb.lib().fadb_launch_count(), fb.jit_stats()
+            v2 = e.autodiff(seed)                    # adjoints accumulate; same kernel again
+            res[on] = (v, [e.adj(x).copy() for x in variables], l1 - l0, j1["launched"] - j0["launched"])
+            np.testing.assert_array_equal(v, v2)
+        finally:
+            fb.lib().fadb_glm_enable(prev)
+    assert res[True][2] == 2 and res[True][3] == 1, res[True][2:]          # the tile kernel + glm_finish_kernel
+    assert res[False][2] >= 3
+    _close(res[True][0], ov, 1e-12, name + " value")
+    _close(res[True][0], res[False][0], 1e-12, name + " value vs three-launch route")
+    for k, (g, o, h) in enumerate(zip(res[True][1], oadj, res[False][1])):
+        _close(g, 2.0 * np.asarray(o), 1e-11, f"{name} adj[{k}] (two sweeps)")
+        _close(g, h, 1e-11, f"{name} adj[{k}] vs three-launch route")
+
+
+def test_one_pass_route_falls_back_on_unaligned_operands(fb):
+    # X offset by one double (a view into a larger buffer): the tile path needs 16-byte alignment, the call must take the
+    # three-launch route and still be right
+    import torch
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    rows, cols = 1024, 6
+    X = rng.normal(size=(rows, cols)); y = rng.normal(size=rows); w0 = rng.normal(size=cols)
+    buf = torch.zeros(rows * cols + 1, dtype=torch.float64, device="cuda")
+    buf[1:] = torch.from_numpy(np.asfortranarray(X).reshape(-1, order="F")).cuda()
+    e = fb.Expr()
+    e.keep += [buf]
+    Xc = e._id(fb.lib().fadb_expr_const_view(e.h, fb.MAT, rows, cols, C.c_void_p(buf.data_ptr() + 8)))
+    w = e.var(w0.reshape(cols, 1))
+    r = e.unary("tanh", e.binary("sub", e.const(y), e.dot(Xc, w)))
+    e.bind(e.sum(e.pow(2, r)))
+    assert "fast=6" in e.describe()
+    j0 = fb.jit_stats()
+    v = e.autodiff(1.0)
+    t = np.tanh(y - X @ w0)
+    np.testing.assert_allclose(v[0], np.sum(t * t), rtol=1e-12)
+    np.testing.assert_allclose(e.adj(w).reshape(-1), -X.T @ (2 * t * (1 - t * t)), rtol=1e-11, atol=1e-12)
+
+
 def test_expr_specialised_kernels_are_the_default_and_bit_identical_to_interpreter(fb):
     # same source, same flags (-fmad=false): the specialised kernel and the interpreter must agree to the bit
     res = {}

@@ -175,6 +175,26 @@ def test_stage_program_specialises_to_register_code(F, name):
     assert compiled >= 3
 
 
+@pytest.mark.parametrize("name", ["glm_logistic", "glm_logistic_weighted_ragged", "glm_least_squares_inner"])
+def test_one_pass_dot_map_sum_kernel_compiles(F, name):
+    """sum(f(dot(X, w), ...)): the planner routes the root stage to the one-pass kernel (fast=6) and its NVRTC source
+    (glm_kernel.cuh + the stage program) compiles for sm_100a within the 2-CTAs-per-SM register budget."""
+    import re
+    exprs.RNG = np.random.default_rng(1)
+    e = F.Expr(device=False)
+    root, _, _ = exprs.CASES[name](e)
+    e.plan(root)
+    d = e.describe()
+    assert d.startswith("stages=2") and "fast=6" in d, d[:400]
+    text = e.jit_program(1, 6)
+    assert "#define GLM_DOT_LEAF" in text and "GLM_VEC_SLOT" in text
+    nbytes, log = F.jit_compile_only(text)
+    assert nbytes > 0, log[-1500:]
+    m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", log)
+    regs = int(re.search(r"Used (\d+) registers", log).group(1))
+    assert regs <= 204 and int(m.group(2)) <= 64, log[-600:]
+
+
 def test_control_flow_stage_is_not_specialisable(F):
     name = next(n for n in sorted(exprs.CASES) if "if_else" in n)
     exprs.RNG = np.random.default_rng(1)
