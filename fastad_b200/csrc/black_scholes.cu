@@ -225,6 +225,50 @@ bs_kernel_fast_pf(size_t n, const double* __restrict__ S, const double* __restri
     if (PDL == PDL_EARLY && threadIdx.x == 0) cudaGridDependencySynchronize();     // the CTA retires only after the previous grid has
 }
 
+// Host-link variant (fadb_black_scholes_host on page-locked arrays, FADB_BS_HOST_WIDE=W): W = 2 or 4 consecutive options per
+// thread, every array moved with ONE 128- / 256-bit access per thread -- a warp instruction then covers 512 B / 1 KB of
+// contiguous host memory, so that the write path can form full-size PCIe payloads (with one option per thread a warp store is
+// two separate 128-byte lines).  Overwrite mode only (the host entry's); same bs_eval_fast, same bits.
+template <int W>
+__global__ void __launch_bounds__(256, 1)
+bs_kernel_host_wide(size_t n, const double* __restrict__ S, const double* __restrict__ K, const double* __restrict__ sigma,
+                    const double* __restrict__ tau, const double* __restrict__ r, BSOut out)
+{
+    __shared__ double s_tab[288 + 387];
+    for (int i = threadIdx.x; i < 256; i += 256) s_tab[i] = fm::kErfcx32_d[i];
+    if (threadIdx.x < 32) s_tab[256 + threadIdx.x] = fm::kExp2_32_d[threadIdx.x];
+    for (int i = threadIdx.x; i < 387; i += 256) s_tab[288 + i] = fm::kLogT_d[i];
+    __syncthreads();
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t nw = n / W;
+    for (size_t q = tid; q < nw; q += nthreads) {
+        const size_t i = q * W;
+        double in[5][W], res[8][W];
+        const double* src[5] = {S, K, sigma, tau, r};
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            if (W == 4) { const double4_t v = ldg256_stream(src[a] + i); for (int e = 0; e < 4; ++e) in[a][e] = v.v[e]; }
+            else { const double2 v = __ldg(reinterpret_cast<const double2*>(src[a] + i)); in[a][0] = v.x; in[a][W - 1] = v.y; }
+        }
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            const BSRes o = bs_eval_fast<true>(in[0][e], in[1][e], in[2][e], in[3][e], in[4][e], s_tab);
+            res[0][e] = o.call; res[1][e] = o.put; res[2][e] = o.cS; res[3][e] = o.cSig; res[4][e] = o.cR;
+            res[5][e] = o.pS; res[6][e] = o.pSig; res[7][e] = o.pR;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (W == 4) { double4_t v; for (int e = 0; e < 4; ++e) v.v[e] = res[k][e]; st256(out.p[k] + i, v); }
+            else *reinterpret_cast<double2*>(out.p[k] + i) = make_double2(res[k][0], res[k][W - 1]);
+        }
+    }
+    for (size_t i = nw * W + tid; i < n; i += nthreads) {
+        const BSRes o = bs_eval_fast<true>(__ldg(S + i), __ldg(K + i), __ldg(sigma + i), __ldg(tau + i), __ldg(r + i), s_tab);
+        bs_store1<false>(out, i, o);
+    }
+}
+
 // Diagnostic variants of bs_kernel_fast_pf (FADB_BS_VARIANT=40 / 41, never the default): the same grid, trip structure and
 // 13 streams with the arithmetic removed (MODE 1: what the memory system alone takes for this access pattern) and the same
 // arithmetic on cache-resident operands with the stores predicated off (MODE 2: what the SMs alone take).  Their two
@@ -487,6 +531,20 @@ int launch_black_scholes(Context& c, cudaStream_t st, size_t n, const double* S,
 #undef FADB_BS_TMA
         if (rc) return rc;
         c.launches++;
+        return FADB_OK;
+    }
+    static const int host_wide = [] { const char* e = getenv("FADB_BS_HOST_WIDE"); return e ? atoi(e) : 0; }();
+    bool wide_ok = host_wide == 2 || host_wide == 4;
+    if (host_wide == 4) {
+        uintptr_t bits = (uintptr_t)S | (uintptr_t)K | (uintptr_t)sigma | (uintptr_t)tau | (uintptr_t)r;
+        for (int k = 0; k < 8; ++k) bits |= (uintptr_t)out[k];
+        wide_ok = (bits & 31u) == 0;
+    }
+    if (host_mapped && ovw && vec_ok && wide_ok) {
+        if (host_wide == 4) bs_kernel_host_wide<4><<<host_grid, 256, 0, st>>>(n, S, K, sigma, tau, r, o);
+        else bs_kernel_host_wide<2><<<host_grid, 256, 0, st>>>(n, S, K, sigma, tau, r, o);
+        c.launches++;
+        FADB_CUDA(cudaGetLastError());
         return FADB_OK;
     }
 #define FADB_BS_LAUNCH(KERNEL)                                                                          \
