@@ -707,6 +707,23 @@ def run_ours(args):
         rows, cols = 1 << 20, 64
         Xh, yh, wt = synth.linreg_inputs(rows, cols)
         L.fadb_glm_enable.argtypes, L.fadb_glm_enable.restype = [C.c_int], C.c_int
+        # BASELINE config 4 with an intercept: normal(y, dot(X, w) + b, sigma) -- no longer the fixed regression shape (fast=3),
+        # but still one pass over X: the mean's map and the log-density run inside the tile kernel (fast=6)
+        for tag, glm in (("one_pass", 1), ("three_launch", 0)):
+            e = F.Expr()
+            Xc, yc = e.const(Xh), e.const(yh)
+            w, b, sg = e.var((wt + 0.05).reshape(cols, 1)), e.var(0.1), e.var(1.3)
+            e.bind(e.normal(yc, e.binary("add", e.dot(Xc, w), b), sg))
+            prev_glm = L.fadb_glm_enable(glm)
+
+            def li_step(i):
+                F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+            t = timed_loop(li_step, steps2, 3, world)
+            L.fadb_glm_enable(prev_glm)
+            add(f"expr_linreg_intercept_2^20x64_{tag}", 8 * rows * (cols + 1), t, steps2, rows, "rows",
+                {"note": "normal(y, dot(X, w) + b, sigma); algorithmic bytes = one pass over X + y"
+                         + ("" if glm else "; one-pass route off: gemv -> normal stage -> gemv^T")})
+            del e
         for tag, inner, glm in (("one_pass", False, 1), ("map_one_pass", True, 1), ("generic_dot", True, 0)):
             e = F.Expr()
             Xc, yc, w = e.const(Xh), e.const(yh), e.var((wt + 0.05).reshape(cols, 1))

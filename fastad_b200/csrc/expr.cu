@@ -322,14 +322,19 @@ struct GlmArgsHost {
     const double* lp_val[MAXL_JIT];
 };
 struct GlmFinish {
-    int nacc, cols, nscal;
+    int nacc, cols, nscal, term;
+    double n_total; const double* sig_ptr;   // T_NORMAL: the one sigma (device) and the row count
     double* w_adj; int w_mode;           // 0 none, 1 accumulate, 2 assign
     double* s_adj[MAXCH_JIT]; int s_ch[MAXCH_JIT]; int s_mode[MAXCH_JIT];
 };
 __global__ void glm_finish_kernel(GlmFinish f, const double* __restrict__ out, double* value)
 {
     const int t = threadIdx.x;
-    if (t == 0) value[0] = out[0];                                           // SumElemNode::feval (sum.hpp:156-160)
+    if (f.term == T_NORMAL) {
+        const double s = f.sig_ptr[0];
+        if (!(s > 0)) { if (t == 0) value[0] = -INFINITY; return; }         // normal.hpp:344: no adjoint update either
+        if (t == 0) value[0] = -0.5 * (out[0] / (s * s)) - f.n_total * log(s);   // normal.hpp:351-352
+    } else if (t == 0) value[0] = out[0];                                    // SumElemNode::feval (sum.hpp:156-160)
     if (t < f.nscal) {                                                       // VarView::beval of a scalar variable (var_view.hpp:91-94)
         const double g = out[f.s_ch[t]];
         f.s_adj[t][0] = f.s_mode[t] == 2 ? g : f.s_adj[t][0] + g;
@@ -820,6 +825,7 @@ struct fadb_expr {
     {
         static const bool off = getenv("FADB_NO_GLM") != nullptr;
         if (off || st.big || st.prog.size() > 48 || st.nch > 16 || st.N < 64 || st.N % 2 != 0) return;     // the TMA tile path needs an even row count
+        if (st.term == T_NORMAL && (st.sig_vec || !st.mu_vec || (!st.sig_is_const && st.sig_leaf < 0))) return;
         int ld = -1, nvec = 0;
         std::vector<int> slot(st.leaves.size(), -1);
         for (size_t l = 0; l < st.leaves.size(); ++l) {
@@ -901,7 +907,8 @@ struct fadb_expr {
         if (rc) return rc;
         c.launches++;
         GlmFinish f;
-        f.nacc = nacc; f.cols = cols; f.nscal = 0;
+        f.nacc = nacc; f.cols = cols; f.nscal = 0; f.term = st.term; f.n_total = (double)st.f_rows;
+        f.sig_ptr = st.sig_is_const ? st.d_sig : (st.sig_leaf >= 0 ? st.leaves[st.sig_leaf].val : nullptr);
         f.w_adj = ds.R.adj_mode ? ds.R.adj : nullptr; f.w_mode = ds.R.adj_mode;
         for (const LeafDesc& L : st.leaves)
             if (L.scalar && L.adj_mode != 0 && L.channel > 0 && f.nscal < MAXCH_JIT) {
@@ -977,6 +984,9 @@ struct fadb_expr {
                     st.f_sig = st.leaves[ls].val; st.f_sigadj = st.leaves[ls].adj_mode ? st.leaves[ls].adj : nullptr;
                 }
             }
+            // normal(y, f(dot(X, w), ...), sigma) with ONE sigma and a mean that is a map of the product (an intercept, a link
+            // function): the same one-pass tile kernel with the log-density as its terminal
+            if (st.fast == 0 && plan.size() == 2 && !st.sig_vec) detect_glm(st);
         }
     }
 

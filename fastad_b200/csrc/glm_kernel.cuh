@@ -1,4 +1,5 @@
-// glm_kernel.cuh — ONE pass over X for  sum(f(dot(X, w), row operands...))  (NVRTC only, csrc/jit.cu kind 1).
+// glm_kernel.cuh — ONE pass over X for  sum(f(dot(X, w), row operands...))  and  normal_adj_log_pdf(y, f(dot(X, w), ...), sigma)
+// with one sigma  (NVRTC only, csrc/jit.cu kind 1).
 //
 // Replaces the three launches DotNode::feval (dot.hpp:89-95, X streamed once) -> the elementwise stage with its
 // SumElemNode (sum.hpp:156-173) -> DotNode::beval (dot.hpp:96-104, X streamed AGAIN) by one sweep: with the root
@@ -47,7 +48,10 @@ __device__ __forceinline__ void gl_tma_load_2d(void* dst_smem, const GlmTensorMa
 
 // The stage program for ONE row: forward, then the adjoint sweep from the root seed.  t = the row's product (X w)_i,
 // lv = its row operands, sv = the scalar operands.  Same instruction semantics as stage_body (stage_kernel.cuh).
-__device__ __forceinline__ void glm_row(double t, const double (&lv)[GL_NV], const double (&sv)[GL_NL], double seed,
+// the ONE sigma of a normal terminal and what the row formulas need of it, formed once per thread (IEEE divisions)
+struct GlmSigma { double inv_s, inv_s_sq, inv_ss; bool valid; };
+
+__device__ __forceinline__ void glm_row(double t, const double (&lv)[GL_NV], const double (&sv)[GL_NL], double seed, const GlmSigma& sig,
                                         bool tally, double (&acc)[GL_ACC], double& adj)
 {
     double v[JIT_NINS], g[JIT_NINS], la[GL_NL];
@@ -86,7 +90,24 @@ __device__ __forceinline__ void glm_row(double t, const double (&lv)[GL_NV], con
     }
 #pragma unroll
     for (int k = 0; k < GL_NL; ++k) la[k] = 0.0;
-    g[JIT_ROOT] = seed;                                // SumElemNode::beval: every element gets the seed (sum.hpp:169-172)
+    double term_val;
+    bool valid = true;
+    if (JIT_TERM == T_NORMAL) {
+        // NormalAdjLogPDFNode with a per-row mean and ONE sigma (normal.hpp:304-381), formulas as in stage_body's terminal
+        const double x = v[JIT_NX], m = v[JIT_NM], d = x - m;
+        term_val = d * d;                              // squaredNorm, normal.hpp:351; the epilogue forms the value
+        valid = sig.valid;                             // normal.hpp:344: sigma <= 0 => -inf and no adjoint anywhere
+        const double c = seed * sig.inv_s_sq;
+        g[JIT_NX] += c * (m - x);                      // normal.hpp:371
+        g[JIT_NM] += c * d;                            // normal.hpp:370
+        // normal.hpp:365 per element, (d d) / (s s) as a product with the reciprocal formed once: the term only enters the
+        // REDUCED sigma adjoint (1e-12 class), the per-row mean adjoint above is formed exactly as the stage kernel forms it
+        g[JIT_NS] += seed * ((d * d) * sig.inv_ss - 1.) * sig.inv_s;
+    } else {
+        constexpr int root = JIT_ROOT < 0 ? 0 : JIT_ROOT;
+        term_val = v[root];
+        g[root] = seed;                                // SumElemNode::beval: every element gets the seed (sum.hpp:169-172)
+    }
 #pragma unroll
     for (int k = JIT_NINS - 1; k >= 0; --k) {
         const DIns I = JIT_PROG[k];
@@ -108,12 +129,12 @@ __device__ __forceinline__ void glm_row(double t, const double (&lv)[GL_NV], con
         default: break;                                // constants, comparisons: no adjoint
         }
     }
-    adj = la[GLM_DOT_LEAF];
+    adj = valid ? la[GLM_DOT_LEAF] : 0.0;
     if (tally) {
-        acc[0] += v[JIT_ROOT];
+        acc[0] += term_val;
 #pragma unroll
         for (int k = 0; k < JIT_NLEAVES; ++k)
-            if (JIT_LEAF[k].scalar && JIT_LEAF[k].adj_mode != 0 && JIT_LEAF[k].channel > 0) acc[JIT_LEAF[k].channel] += la[k];
+            if (JIT_LEAF[k].scalar && JIT_LEAF[k].adj_mode != 0 && JIT_LEAF[k].channel > 0) acc[JIT_LEAF[k].channel] += valid ? la[k] : 0.0;
     }
 }
 
@@ -132,6 +153,8 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cols = a.cols;
+    asm volatile("griddepcontrol.launch_dependents;");        // programmatic dependent launch, as the library's own kernels
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x < 64) w_s[threadIdx.x] = (int)threadIdx.x < cols ? a.w[threadIdx.x] : 0.0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < GL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
@@ -165,6 +188,15 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
     double sv[GL_NL];
 #pragma unroll
     for (int k = 0; k < GL_NL; ++k) sv[k] = (k < JIT_NLEAVES && JIT_LEAF[k].scalar) ? a.lp_val[k][0] : 0.0;
+    GlmSigma sig{1.0, 1.0, 1.0, true};
+    if (JIT_TERM == T_NORMAL) {
+        constexpr int ns = JIT_NS < 0 ? 0 : JIT_NS;
+        const double sg = JIT_PROG[ns].code == F_CONST ? JIT_PROG[ns].imm : sv[JIT_PROG[ns].leaf < 0 ? 0 : JIT_PROG[ns].leaf];
+        sig.valid = sg > 0;
+        sig.inv_s = 1. / sg;                            // normal.hpp:354-355
+        sig.inv_s_sq = sig.inv_s * sig.inv_s;
+        sig.inv_ss = 1. / (sg * sg);
+    }
     double g[GL_CPW];
 #pragma unroll
     for (int c = 0; c < GL_CPW; ++c) g[c] = 0.0;
@@ -216,8 +248,8 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
         const double2 p3 = *reinterpret_cast<const double2*>(pt + 3 * GL_ROWS + 2 * lane);
         par ^= 1;
         double a0, a1;
-        glm_row((p0.x + p1.x) + (p2.x + p3.x), lv0, sv, a.seed, warp == 0 && in0, acc, a0);
-        glm_row((p0.y + p1.y) + (p2.y + p3.y), lv1, sv, a.seed, warp == 0 && in1, acc, a1);
+        glm_row((p0.x + p1.x) + (p2.x + p3.x), lv0, sv, a.seed, sig, warp == 0 && in0, acc, a0);
+        glm_row((p0.y + p1.y) + (p2.y + p3.y), lv1, sv, a.seed, sig, warp == 0 && in1, acc, a1);
         if (!in0) a0 = 0.0;
         if (!in1) a1 = 0.0;
 #pragma unroll

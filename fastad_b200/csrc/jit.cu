@@ -52,6 +52,7 @@ struct Driver {
     CUresult (*occupancy)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*func_attr)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*func_set_attr)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*launch_ex)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;   // optional
     bool ok = false;
 };
 struct Entry { CUmodule mod = nullptr; CUfunction fn = nullptr; int per_sm = 1; int regs = 0, local_bytes = 0; bool failed = false; };
@@ -111,6 +112,7 @@ bool init_locked()
         g_why = "driver entry points unavailable";
         return false;
     }
+    drv("cuLaunchKernelEx", d.launch_ex);         // optional: programmatic dependent launch of the specialised kernels
     g_state = 1;
     return true;
 }
@@ -228,18 +230,31 @@ void jit_shutdown()
     g_cache.clear();
 }
 
+int jit_launch_params(const JitKernel& k, unsigned grid, unsigned block, size_t dyn_smem, cudaStream_t st, void** params);
 int jit_launch(const JitKernel& k, unsigned grid, unsigned block, cudaStream_t st, void* args_struct)
 {
     void* params[1] = {args_struct};
-    const CUresult r = g_drv.launch(reinterpret_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, 0, reinterpret_cast<CUstream>(st), params, nullptr);
-    if (r != CUDA_SUCCESS) { set_error("fastad_b200: launch of a specialised stage kernel failed (CUresult " + std::to_string((int)r) + ")"); return FADB_ERR_CUDA; }
-    ++g_launched;
-    return FADB_OK;
+    return jit_launch_params(k, grid, block, 0, st, params);
 }
 
 int jit_launch_params(const JitKernel& k, unsigned grid, unsigned block, size_t dyn_smem, cudaStream_t st, void** params)
 {
-    const CUresult r = g_drv.launch(reinterpret_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, (unsigned)dyn_smem, reinterpret_cast<CUstream>(st), params, nullptr);
+    CUresult r;
+    if (g_drv.launch_ex && pdl_enabled()) {
+        // the kernels start with griddepcontrol.launch_dependents / .wait: they may become resident while the previous kernel on
+        // the stream drains, and read nothing before it has completed (same contract as launch_pdl, common.cuh)
+        CUlaunchAttribute at[1];
+        at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        at[0].value.programmaticStreamSerializationAllowed = 1;
+        CUlaunchConfig cfg = {};
+        cfg.gridDimX = grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+        cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+        cfg.sharedMemBytes = (unsigned)dyn_smem;
+        cfg.hStream = reinterpret_cast<CUstream>(st);
+        cfg.attrs = at; cfg.numAttrs = 1;
+        r = g_drv.launch_ex(&cfg, reinterpret_cast<CUfunction>(k.fn), params, nullptr);
+    } else
+        r = g_drv.launch(reinterpret_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, (unsigned)dyn_smem, reinterpret_cast<CUstream>(st), params, nullptr);
     if (r != CUDA_SUCCESS) { set_error("fastad_b200: launch of a specialised kernel failed (CUresult " + std::to_string((int)r) + ")"); return FADB_ERR_CUDA; }
     ++g_launched;
     return FADB_OK;

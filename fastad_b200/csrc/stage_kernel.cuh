@@ -170,6 +170,12 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
     extern __shared__ double s_dyn[];
     __shared__ double s_red[32 * K_ACC];
     __shared__ bool s_last;
+#ifdef FADB_JIT
+    // programmatic dependent launch (jit.cu launches the specialised kernels with the attribute): the next launch on the
+    // stream may become resident now; nothing is read before the previous grid has completed and flushed
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 #ifndef FADB_JIT
     __shared__ LeafDesc s_leaf_sm[BIG ? 1 : MAXL];
     const LeafDesc* s_leaf = BIG ? a.leaves : s_leaf_sm;

@@ -169,6 +169,20 @@ def linreg_expr(rows, cols):
     return build
 
 
+def linreg_with_intercept(rows, cols, sigma=1.3, link=False, const_sigma=False):
+    def build(e):   # normal(y, dot(X, w) + b, sigma): C4 with an intercept (and optionally a link function on the mean)
+        import synth
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=13)
+        Xc, yc = e.const(X), e.const(y + 0.4)
+        w, b = e.var(w_true + 0.01), e.var(0.35)
+        sg = e.const(sigma) if const_sigma else e.var(sigma)
+        mean = e.binary("add", e.dot(Xc, w), b)
+        if link:
+            mean = e.binary("mul", e.const(3.0), e.unary("tanh", e.binary("mul", e.const(0.3), mean)))
+        return e.normal(yc, mean, sg), ([w, b] if const_sigma else [w, b, sg]), 0.8
+    return build
+
+
 def least_squares(rows, cols, flipped=False, x_var=False, inner=False):
     def build(e):   # README.md:640-662 batched: sum(pow<2>(y - dot(X, w))); X constant (or a variable: outer-product adjoint)
         import synth
@@ -565,6 +579,9 @@ CASES = {
     "least_squares_tall_generic": least_squares(6001, 19, inner=True),          # odd row count: gemv -> stage -> gemv^T
     "glm_least_squares_inner": least_squares(6000, 19, inner=True),            # even: the one-pass kernel (fast=6)
     "glm_logistic": glm_logistic(4160, 64),
+    "glm_linreg_intercept": linreg_with_intercept(4224, 64),
+    "glm_linreg_intercept_link_const_sigma": linreg_with_intercept(2050, 7, link=True, const_sigma=True),
+    "glm_linreg_intercept_invalid_sigma": linreg_with_intercept(1024, 5, sigma=-0.7),
     "glm_logistic_weighted_ragged": glm_logistic(4290, 5, weights=True),        # last tile holds 2 of 64 rows
     "glm_logistic_tiny": glm_logistic(66, 3),
     "least_squares_x_variable": least_squares(4500, 5, x_var=True),

@@ -137,7 +137,8 @@ def test_logpdf_root_seed_zero_leaves_producers_untouched(fb, engine):
     np.testing.assert_array_equal(e.adj(w), a1[0])
 
 
-@pytest.mark.parametrize("name", ["glm_logistic", "glm_logistic_weighted_ragged", "glm_logistic_tiny", "glm_least_squares_inner"])
+@pytest.mark.parametrize("name", ["glm_logistic", "glm_logistic_weighted_ragged", "glm_logistic_tiny", "glm_least_squares_inner",
+                                  "glm_linreg_intercept", "glm_linreg_intercept_link_const_sigma"])
 def test_one_pass_dot_map_sum_route(fb, name):
     # sum(f(dot(X, w), row constants, scalars)): ONE specialised launch (glm_kernel.cuh) + the scalar epilogue instead of
     # gemv -> stage -> gemv^T; value and adjoints against the oracle AND against the three-launch route of the same plan
@@ -167,6 +168,21 @@ def test_one_pass_dot_map_sum_route(fb, name):
     for k, (g, o, h) in enumerate(zip(res[True][1], oadj, res[False][1])):
         _close(g, 2.0 * np.asarray(o), 1e-11, f"{name} adj[{k}] (two sweeps)")
         _close(g, h, 1e-11, f"{name} adj[{k}] vs three-launch route")
+
+
+def test_one_pass_route_invalid_sigma(fb):
+    # normal(y, dot(X, w) + b, sigma) with sigma <= 0 through the one-pass kernel: -inf and NO adjoint (normal.hpp:344)
+    exprs.RNG = np.random.default_rng(20261019)
+    e = fb.Expr()
+    root, variables, seed = exprs.CASES["glm_linreg_intercept_invalid_sigma"](e)
+    e.bind(root)
+    assert "fast=6" in e.describe()
+    j0 = fb.jit_stats()
+    v = e.autodiff(seed)
+    assert fb.jit_stats()["launched"] - j0["launched"] == 1
+    assert v[0] == -np.inf
+    for x in variables:
+        assert np.all(e.adj(x) == 0.0)
 
 
 def test_one_pass_route_falls_back_on_unaligned_operands(fb):
