@@ -137,9 +137,8 @@ __device__ __forceinline__ void pdl_prologue()
 }
 inline bool pdl_enabled()
 {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("FADB_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
-    return on == 1;
+    static const bool on = [] { const char* e = getenv("FADB_NO_PDL"); return !(e && e[0] == '1'); }();   // thread-safe on first use
+    return on;
 }
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)

@@ -326,8 +326,7 @@ static int mlp3_launch(size_t batch, const double* X, const double* y, const dou
         FADB_CUDA(cudaGetLastError());
         return FADB_OK;
     }
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("FADB_MLP_VARIANT"); variant = e ? atoi(e) : -2; }
+    static const int variant = [] { const char* e = getenv("FADB_MLP_VARIANT"); return e ? atoi(e) : -2; }();
 #define FADB_MLP_LAUNCH(K)                                                                                     \
     FADB_CUDA(launch_pdl(K, resident_grid(*c, K, threads, 0, batch, threads), threads, 0, c->stream, batch, X, y, parm, \
                          g_mlp_ws[c->device], c->tickets + 5, grad, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, dev_loss, NoLink{}, red))
