@@ -600,12 +600,9 @@ struct fadb_expr {
     {
         st.big = (int)st.prog.size() > MAXS || (int)st.leaves.size() > MAXL;
         if (st.big && st.N > 1) {
-            // too large for the interpreter's fixed arrays: fine for a specialised kernel (no control flow)
-            bool cf = false;
-            for (const Ins& I : st.prog) cf = cf || I.op == I_JZ || I.op == I_JMP || I.op == I_PHI;
-            if (cf || (int)st.prog.size() > MAXS_JIT || (int)st.leaves.size() > MAXL_JIT) {
-                err = "a fused vector stage is limited to " + std::to_string(cf ? MAXS : MAXS_JIT) + " nodes and " +
-                      std::to_string(cf ? MAXL : MAXL_JIT) + " distinct leaves" + (cf ? " when it contains if_else" : "");
+            // too large for the interpreter's fixed arrays: fine for a specialised kernel (if_else included: jump watermark)
+            if ((int)st.prog.size() > MAXS_JIT || (int)st.leaves.size() > MAXL_JIT) {
+                err = "a fused vector stage is limited to " + std::to_string(MAXS_JIT) + " nodes and " + std::to_string(MAXL_JIT) + " distinct leaves";
                 return false;
             }
             st.big = false;
@@ -616,11 +613,7 @@ struct fadb_expr {
         for (auto& L : st.leaves)
             if (L.scalar && L.adj_mode != 0 && st.N > 1) L.channel = ch++;
         if (ch > MAXCH_JIT) { err = "expression stage needs more than " + std::to_string(MAXCH_JIT) + " reduction channels"; return false; }
-        if (ch > MAXCH) {
-            for (const Ins& I : st.prog)
-                if (I.op == I_JZ || I.op == I_JMP || I.op == I_PHI) { err = "an if_else stage is limited to " + std::to_string(MAXCH) + " reduction channels"; return false; }
-            st.jit_only = true;
-        }
+        if (ch > MAXCH) st.jit_only = true;
         st.nch = ch;
         return true;
     }
@@ -1200,13 +1193,17 @@ struct fadb_expr {
         char buf[64];
         // registers: 8 CTAs/SM (64 registers) is the measured optimum for small programs; larger ones spill there
         if (st.enc.size() > 64) o << "\n#ifndef FADB_JIT_MINB\n#define FADB_JIT_MINB " << (st.enc.size() > 128 ? 2 : 4) << "\n#endif";
+        bool cf = false;
+        for (const DIns& d : st.enc) cf = cf || d.code == F_JZ || d.code == F_JMP || d.code == F_PHI;
+        // if_else: the unrolled loops carry a jump watermark (stage_kernel.cuh); values stay live across the guarded regions, so
+        // the 64-register cap of small programs would spill (544 bytes on a 25-node nested case): 128 registers instead
+        if (cf) o << "\n#define JIT_HAS_CF 1" << (st.enc.size() <= 64 ? "\n#ifndef FADB_JIT_MINB\n#define FADB_JIT_MINB 4\n#endif" : "");
         o << "\n#define JIT_VEC " << jit_vec_width(st) << "\n#define JIT_NINS " << st.enc.size() << "\n#define JIT_NLEAVES " << st.leaves.size()
           << "\n#define JIT_MODE " << mode << "\n#define JIT_TERM " << st.term << "\n#define JIT_ROOT " << st.root
           << "\n#define JIT_NX " << st.nx << "\n#define JIT_NM " << st.nm << "\n#define JIT_NS " << st.ns
           << "\n#define JIT_MU_VEC " << st.mu_vec << "\n#define JIT_SIG_VEC " << st.sig_vec << "\n#define JIT_NCH " << st.nch
           << "\n__device__ constexpr DIns JIT_PROG[JIT_NINS] = {\n";
         for (const DIns& d : st.enc) {
-            if (d.code == F_JZ || d.code == F_JMP || d.code == F_PHI) return false;      // control flow: loops cannot unroll
             if (!std::isfinite(d.imm)) return false;
             snprintf(buf, sizeof buf, "%a", d.imm);                                      // hex float: exact
             o << "  {" << d.code << ", " << d.a << ", " << d.b << ", " << d.leaf << ", " << buf << "},\n";

@@ -94,6 +94,9 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #ifndef JIT_VEC
 #define JIT_VEC 1
 #endif
+#ifndef JIT_HAS_CF
+#define JIT_HAS_CF 0
+#endif
 #define K_LVAL(k) a.lp_val[k]
 #define K_LADJ(k) a.lp_adj[k]
 #define K_LEAF_SCALAR(k) JIT_LEAF[k].scalar
@@ -278,8 +281,17 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         }
 #endif
         // ------------------------------------------------ forward (feval)
+#if defined(FADB_JIT) && JIT_HAS_CF
+        // if_else in an UNROLLED program: the jumps of the interpreter (k = target) become a watermark -- instruction k runs
+        // iff k >= f_resume -- so that every instruction keeps its compile-time index (registers, folded switches) and the
+        // skipped branch costs one uniform compare per instruction.  Targets only grow along the program, nested or not.
+        int f_resume = 0;
+#endif
         K_UNROLL
         for (int k = 0; k < K_NINS; ++k) {
+#if defined(FADB_JIT) && JIT_HAS_CF
+            if (k < f_resume) continue;
+#endif
             const DIns I = K_INS(k);
             double r;
             switch (I.code) {
@@ -313,10 +325,14 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             case F_BINARY + FADB_AND: r = (V(I.a) != 0 && V(I.b) != 0) ? 1.0 : 0.0; break;
             case F_BINARY + FADB_OR: r = (V(I.a) != 0 || V(I.b) != 0) ? 1.0 : 0.0; break;
             case F_BINARY + 12: r = V(I.a) - 2 * V(I.b); break;           // MockBinary
-#ifndef FADB_JIT   // programs with control flow are not specialised (the loops below must unroll)
+#ifndef FADB_JIT
             // IfElseNode (if_else.hpp:64-68): the condition is a scalar, so the jump is uniform
             case F_JZ: r = 0.0; if (V(I.a) == 0.0) k = I.b - 1; break;
             case F_JMP: r = 0.0; k = I.b - 1; break;
+            case F_PHI: r = V(I.leaf) != 0.0 ? V(I.a) : V(I.b); break;
+#elif JIT_HAS_CF
+            case F_JZ: r = 0.0; if (V(I.a) == 0.0) f_resume = I.b; break;
+            case F_JMP: r = 0.0; f_resume = I.b; break;
             case F_PHI: r = V(I.leaf) != 0.0 ? V(I.a) : V(I.b); break;
 #endif
             default: {                                                     // OpEqNode::feval, eq.hpp:240-247
@@ -421,8 +437,14 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             } else {
                 G(K_ROOT) = sd;
             }
+#if defined(FADB_JIT) && JIT_HAS_CF
+            int b_lim = K_NINS;          // backward watermark: instruction k is swept iff k <= b_lim (IfElseNode::beval, if_else.hpp:70-78)
+#endif
             K_UNROLL
             for (int k = K_NINS - 1; k >= 0; --k) {
+#if defined(FADB_JIT) && JIT_HAS_CF
+                if (k > b_lim) continue;
+#endif
                 const DIns I = K_INS(k);
                 const double s = G(k);
                 switch (I.code) {
@@ -461,6 +483,13 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                     else G(I.b) += s;
                     break;
                 case F_JMP: if (V(I.a) == 0.0) k = I.leaf + 1; break;             // else was taken: skip the if branch
+                case F_JZ: break;
+#elif JIT_HAS_CF
+                case F_PHI:
+                    if (V(I.leaf) != 0.0) { G(I.a) += s; b_lim = (int)I.imm; }    // skip the else branch: resume at its JMP
+                    else G(I.b) += s;
+                    break;
+                case F_JMP: if (V(I.a) == 0.0) b_lim = I.leaf; break;             // else was taken: skip the if branch, resume at its JZ
                 case F_JZ: break;
 #endif
                 default: {                                                         // OpEqNode::beval, eq.hpp:249-271

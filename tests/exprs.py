@@ -336,6 +336,16 @@ def if_else_scalar(taken):
     return build
 
 
+def if_else_nested(n, c1, c2):
+    def build(e):   # nested IfElseNode over vector branches, large enough for the 4-elements-per-thread specialised form
+        a, b = e.var(c1), e.var(c2)
+        x, y = e.var(_vec(n, 0.2, 1.8)), e.var(_vec(n, 0.5, 1.5))
+        inner = e.if_else(e.binary("gt", b, e.const(0.0)), e.binary("mul", e.unary("sin", x), y), e.binary("div", x, y))
+        outer = e.if_else(e.binary("lt", a, e.const(1.0)), inner, e.binary("mul", e.unary("exp", e.binary("mul", a, x)), b))
+        return e.sum(e.binary("add", outer, e.binary("mul", a, y))), [a, b, x, y], 0.6
+    return build
+
+
 def if_else_logical(e):
     a, b, c = e.var(0.3), e.var(-1.2), e.var(2.0)
     cond = e.binary("land", e.binary("ge", a, e.const(0.0)), e.binary("lor", e.binary("gt", b, e.const(0.0)), e.binary("ne", c, a)))
@@ -532,6 +542,9 @@ CASES = {
     "if_else_taken": if_else_scalar(True),
     "if_else_not_taken": if_else_scalar(False),
     "if_else_logical": if_else_logical,
+    "if_else_nested_tt": if_else_nested(5003, 0.5, 0.7),
+    "if_else_nested_tf": if_else_nested(5003, 0.5, -0.7),
+    "if_else_nested_f": if_else_nested(4100, 1.5, 0.7),
     "opeq_scl_alias": opeq_scl_alias,
     "opeq_scl_noalias": opeq_scl_noalias,
     "opeq_vec_scl": opeq_vec_scl,

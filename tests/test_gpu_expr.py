@@ -288,15 +288,32 @@ def test_expr_specialised_kernel_disk_cache(tmp_path):
     assert outs[0][0] == outs[1][0]
 
 
-def test_expr_if_else_stays_on_the_interpreter(fb):
-    # control flow cannot be unrolled: the stage is not specialised, results still match the oracle
-    name = next(n for n in sorted(exprs.CASES) if "if_else" in n)
-    s0 = fb.jit_stats()
-    gv, _, _, _ = _run(exprs.CASES[name], fb.Expr)
-    ov, _, _, _ = _run(exprs.CASES[name], O.OracleExpr)
-    s1 = fb.jit_stats()
-    assert s1["failed"] == s0["failed"]
-    _close(gv, ov, 1e-12, name)
+@pytest.mark.parametrize("name", ["if_else_taken", "if_else_not_taken", "if_else_logical", "if_else_nested_tt", "if_else_nested_tf",
+                                  "if_else_nested_f"])
+def test_expr_if_else_runs_specialised(fb, name):
+    # control flow no longer pins a stage to the interpreter: the specialised kernel carries a jump watermark over its
+    # unrolled program; both engines must match the oracle (test_expr_matches_oracle) and each other to the bit
+    res = {}
+    for on in (True, False):
+        prev = fb.jit_enable(on)
+        try:
+            s0 = fb.jit_stats()
+            gv, gadj, _, _ = _run(exprs.CASES[name], fb.Expr)
+            s1 = fb.jit_stats()
+            res[on] = (gv, gadj, s1["launched"] - s0["launched"], s1["failed"] - s0["failed"])
+        finally:
+            fb.jit_enable(prev)
+    assert res[True][2] >= 1 and res[True][3] == 0, fb.lib().fadb_jit_diagnostics().decode()
+    assert res[False][2] == 0
+    ov, oadj, _, _ = _run(exprs.CASES[name], O.OracleExpr)
+    _close(res[True][0], ov, 1e-12, name)
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=1e-13)     # the 4-elements-per-thread form sums in another order
+    for a, b, o in zip(res[True][1], res[False][1], oadj):
+        if a.size > 1:
+            np.testing.assert_array_equal(a, b)
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-12)
+        _close(a, o, 1e-11, name)
 
 
 def test_expr_normal_invalid_sigma_generic_path(fb):
