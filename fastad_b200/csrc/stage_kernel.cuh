@@ -208,6 +208,15 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
 #pragma unroll
     for (int c = 0; c < K_ACC; ++c) acc[c] = 0.0;
     double p_nz = 1.0, p_zeros = 0.0;
+#ifdef FADB_JIT
+    // Broadcast scalars are read ONCE, ahead of the element loop: inside it the compiler must assume the adjoint stores may
+    // alias them, reloads them every trip and cannot hoist what depends on them alone (the reciprocal of a scalar divisor:
+    // 2 of the 3 reciprocals per element of sum(-0.5 pow<2>((x - c w0) / w1))).  A scalar that this stage assigns keeps
+    // its in-program read.
+    double sval[K_LSLOTS];
+    K_UNROLL
+    for (int k = 0; k < K_NLEAVES; ++k) sval[k] = (K_LEAF_SCALAR(k) && !K_LEAF_ASSIGNED(k)) ? K_LVAL(k)[0] : 0.0;
+#endif
 
     double v_loc[STORE == 0 ? K_SLOTS : 1], g_loc[STORE == 0 ? K_SLOTS : 1], l_loc[STORE == 0 ? K_LSLOTS : 1];
     const int vs = STORE == 1 ? (int)blockDim.x : 1;             // slot stride
@@ -296,7 +305,11 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             double r;
             switch (I.code) {
             case F_LEAF_V: r = K_LOADV(I.leaf); break;              // var_view.hpp:69
+#ifdef FADB_JIT
+            case F_LEAF_S: r = K_LEAF_ASSIGNED(I.leaf) ? K_LVAL(I.leaf)[0] : sval[I.leaf]; break;
+#else
             case F_LEAF_S: r = K_LVAL(I.leaf)[0]; break;
+#endif
             case F_CONST: r = I.imm; break;
             case F_EQ: {                                                   // eq.hpp:89-92
                 r = V(I.a);

@@ -149,6 +149,49 @@ def test_normal_invalid_sigma_full_width_undo(fb):
         np.testing.assert_array_equal(host(sa), osa)
 
 
+@pytest.mark.parametrize("case", range(30))
+def test_normal_vector_sigma_guard_random(fb, case):
+    # the optimistic pass + undo over random sizes, operand offsets (32-byte aligned or not), shapes and flags, with 0-3 invalid
+    # sigmas at random places.  Valid input: adjoint vectors bit for bit the oracle's.  Invalid input: -inf, and adjoints that
+    # started at zero read exactly zero again (undo of the default form, untouched in the strict form).
+    import torch
+    rng = np.random.default_rng(1000 + case)
+    n = int(rng.choice([1, 2, 3, 7, 64, 257, 1000, 4099, 70001]))
+    kind = ("vvv", "vsv")[case % 2]
+    flags = (0, fb.OVERWRITE_ADJ, fb.STRICT_SIGMA)[case % 3]
+    off = int(rng.integers(0, 4))
+    x, mu, sg = rng.normal(size=n), rng.normal(size=n if kind == "vvv" else 1), rng.uniform(0.5, 2.0, n)
+    nbad = int(rng.integers(0, 4)) if n > 3 else int(rng.integers(0, 2))
+    bad_at = rng.choice(n, size=min(nbad, n), replace=False)
+    sg[bad_at] = rng.choice([0.0, -1.0, -0.25], size=len(bad_at))
+    seed = float(rng.uniform(0.5, 1.5))
+
+    def devoff(a):
+        t = torch.zeros(len(a) + off, dtype=torch.float64, device="cuda")
+        t[off:] = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        return t[off:]
+    dx, dm, ds = devoff(x), devoff(mu), devoff(sg)
+    xa, ma, sa = devoff(np.zeros(n)), devoff(np.zeros(len(mu))), devoff(np.zeros(n))
+    v = fb.normal_lpdf(dx, dm, ds, xa, ma, sa, seed=seed, flags=flags)
+    oxa, oma, osa = np.zeros(n), np.zeros(len(mu)), np.zeros(n)
+    ov = O.normal_lpdf(x, mu, sg, oxa, oma, osa, seed=seed)
+    if len(bad_at):
+        assert v == -math.inf and ov == -math.inf
+        assert not bool(xa.any()) and not bool(ma.any()) and not bool(sa.any()), (case, kind, flags, n, off)
+    elif n == 1:       # the sss node (normal.hpp:141-171): scalar formulas, 4 ulp like the reference's own tests
+        assert rel(v, ov) <= REL_REDUCE
+        for g, o in ((xa, oxa), (ma, oma), (sa, osa)):
+            assert rel(host(g)[0], o[0]) <= 1e-15
+    else:
+        assert rel(v, ov) <= REL_REDUCE
+        np.testing.assert_array_equal(host(xa), oxa)
+        np.testing.assert_array_equal(host(sa), osa)
+        if kind == "vvv":
+            np.testing.assert_array_equal(host(ma), oma)
+        else:
+            assert rel(host(ma)[0], oma[0]) <= 1e-11
+
+
 @pytest.mark.parametrize("kind", ["vss", "vvs", "vsv", "vvv"])
 @pytest.mark.parametrize("n", [5, 1 << 10, (1 << 20) + 3])
 def test_normal_vs_oracle(fb, kind, n):
