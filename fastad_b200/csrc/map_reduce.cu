@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256)
 prod_reduce_kernel(size_t n, const double* __restrict__ x, double* partials, unsigned int* ticket,
                    double* out /* {prod of non-zeros, #zeros, value} */)
 {
+    pdl_prologue();
     __shared__ double sp[32], sz[32];
     __shared__ bool is_last;
     double p = 1.0, z = 0.0;
@@ -211,13 +212,17 @@ __global__ void __launch_bounds__(256)
 prod_scatter_kernel(size_t n, const double* __restrict__ x, double* x_adj, double seed, int overwrite,
                     const double* red)
 {
+    pdl_prologue();
     const double pnz = red[0], zeros = red[1], val = red[2];
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     // prod.hpp:194-207: zero element -> product of all the others; else seed * (prod / x_i)
     auto adj = [&](double v) { return (v == 0) ? seed * ((zeros > 1) ? 0.0 : pnz) : seed * div_guarded(val, v); };
     const size_t n4 = (aligned32(x) && aligned32(x_adj)) ? n / 4 : 0;
-    for (size_t q = tid; q < n4; q += nth) {
+    // BACKWARDS over x: the reduce pass that ran just before swept x upwards, so the top of x is what the L2 still holds
+    // (126 MB of it at 2^24 elements = 128 MiB): this pass starts where that one ended
+    for (size_t qf = tid; qf < n4; qf += nth) {
+        const size_t q = n4 - 1 - qf;
         const double4_t v = ldg256_stream(x + 4 * q);
         double4_t g;
 #pragma unroll
@@ -309,12 +314,12 @@ extern "C" int fadb_prod(size_t n, const double* x, double* x_adj, double seed, 
     double* red = c->scalars + 16;   // 3 doubles
     const int threads = 256;
     const int grid = resident_grid(*c, prod_reduce_kernel, threads, 0, n, threads);
-    prod_reduce_kernel<<<grid, threads, 0, c->stream>>>(n, x, c->partials, c->tickets + 3, red);
+    FADB_CUDA(launch_pdl(prod_reduce_kernel, grid, threads, 0, c->stream, n, x, c->partials, c->tickets + 3, red));
     c->launches++;
     FADB_CUDA(cudaGetLastError());
     if (x_adj && n > 0) {
-        prod_scatter_kernel<<<grid, threads, 0, c->stream>>>(n, x, x_adj, seed,
-                                                            (flags & FADB_OVERWRITE_ADJ) ? 1 : 0, red);
+        FADB_CUDA(launch_pdl(prod_scatter_kernel, grid, threads, 0, c->stream, n, x, x_adj, seed, (flags & FADB_OVERWRITE_ADJ) ? 1 : 0,
+                             static_cast<const double*>(red)));
         c->launches++;
         FADB_CUDA(cudaGetLastError());
     }
