@@ -77,7 +77,7 @@ struct Lp<FADB_BERNOULLI> {    // x, p
     __device__ __forceinline__ static void adj(double x, double p, double, double sd, bool, double& gx, double& gb, double& gc)
     {
         gx = 0.0; gc = 0.0;
-        gb = (x == 0 ? -sd : sd) / (x == 0 ? 1 - p : p);               // bernoulli.hpp:143-149, one division
+        gb = div_guarded(x == 0 ? -sd : sd, x == 0 ? 1 - p : p);       // bernoulli.hpp:143-149, one division (Newton reciprocal, <= 1 ulp)
     }
 };
 
