@@ -1631,6 +1631,22 @@ void fadb_expr_destroy(fadb_expr* e)
     delete e;
 }
 
+// Structural sharing of PURE nodes: the reference's expression objects hold their children by value, so a sub-expression
+// used twice (eta = dot(X, w) + b in two terms of a likelihood) reaches the builder as two identical sub-trees.  An identical
+// node -- same kind, same functor, same children -- is returned instead of a copy, as fadb_expr_var already does for views of the
+// same storage: the planner then sees ONE dot node read twice and plans its stage once.  Nodes with an identity of their own
+// (placeholder assignments, op=, glue) are never merged; elementwise nodes are re-lowered at every use anyway.
+static int find_pure(const fadb_expr* e, NodeKind kind, int fn, long pw, int c0, int c1)
+{
+    for (size_t k = 0; k < e->nodes.size(); ++k) {
+        const ENode& n = e->nodes[k];
+        if (n.kind != kind || n.fn != fn || n.pw != pw) continue;
+        if ((int)n.ch.size() != (c1 >= 0 ? 2 : 1) || n.ch[0] != c0 || (c1 >= 0 && n.ch[1] != c1)) continue;
+        return (int)k;
+    }
+    return -1;
+}
+
 int fadb_expr_var(fadb_expr* e, int shape, size_t rows, size_t cols, double* val, double* adj)
 {
     EXPR_REQUIRE(e, e && shape >= 0 && shape <= 2, "fadb_expr_var: bad arguments");
@@ -1646,6 +1662,8 @@ int fadb_expr_var(fadb_expr* e, int shape, size_t rows, size_t cols, double* val
 int fadb_expr_const_scalar(fadb_expr* e, double c)
 {
     EXPR_REQUIRE(e, e != nullptr, "fadb_expr_const_scalar: null expr");
+    for (size_t k = 0; k < e->nodes.size(); ++k)
+        if (e->nodes[k].kind == N_CONST_S && memcmp(&e->nodes[k].cval, &c, sizeof c) == 0) return (int)k;
     ENode n; n.kind = N_CONST_S; n.cval = c;
     return e->add(std::move(n));
 }
@@ -1653,6 +1671,10 @@ int fadb_expr_const_scalar(fadb_expr* e, double c)
 int fadb_expr_const_view(fadb_expr* e, int shape, size_t rows, size_t cols, const double* val)
 {
     EXPR_REQUIRE(e, e && shape >= 0 && shape <= 2, "fadb_expr_const_view: bad arguments");
+    for (size_t k = 0; k < e->nodes.size(); ++k) {
+        const ENode& m = e->nodes[k];
+        if (m.kind == N_CONST_V && val && m.val == val && m.shape == shape && m.rows == rows && m.cols == cols) return (int)k;
+    }
     ENode n; n.kind = N_CONST_V; n.shape = shape; n.rows = rows; n.cols = cols; n.val = val;
     return e->add(std::move(n));
 }
@@ -1676,6 +1698,7 @@ int fadb_expr_unary(fadb_expr* e, int op, int child)
 {
     EXPR_REQUIRE(e, e && e->ok(child) && valid_unary(op), "fadb_expr_unary: bad arguments");
     if (e->is_const_scalar(child)) return fadb_expr_const_scalar(e, host_unary(op, e->nodes[child].cval));
+    if (int k = find_pure(e, N_UNARY, op, 0, child, -1); k >= 0) return k;
     const ENode& c = e->nodes[child];
     ENode n; n.kind = N_UNARY; n.fn = op; n.shape = c.shape; n.rows = c.rows; n.cols = c.cols; n.ch = {child};
     return e->add(std::move(n));
@@ -1690,6 +1713,7 @@ int fadb_expr_binary(fadb_expr* e, int op, int lhs, int rhs)
     const ENode& r = e->nodes[rhs];
     if (l.size() != 1 && r.size() != 1)
         EXPR_REQUIRE(e, l.rows == r.rows && l.cols == r.cols, "binary node: operand shapes differ (binary.hpp:86-90)");
+    if (int k = find_pure(e, N_BINARY, op, 0, lhs, rhs); k >= 0) return k;
     const ENode& big = l.shape >= r.shape ? l : r;
     ENode n; n.kind = N_BINARY; n.fn = op; n.shape = big.shape;
     n.rows = std::max(l.rows, r.rows); n.cols = std::max(l.cols, r.cols); n.ch = {lhs, rhs};
@@ -1700,6 +1724,7 @@ int fadb_expr_pow(fadb_expr* e, long pw, int child)
 {
     EXPR_REQUIRE(e, e && e->ok(child) && pw > -32768 && pw < 32768, "fadb_expr_pow: exponent out of range");
     if (e->is_const_scalar(child)) return fadb_expr_const_scalar(e, host_pow(pw, e->nodes[child].cval));
+    if (int k = find_pure(e, N_POW, 0, pw, child, -1); k >= 0) return k;
     const ENode& c = e->nodes[child];
     ENode n; n.kind = N_POW; n.pw = pw; n.shape = c.shape; n.rows = c.rows; n.cols = c.cols; n.ch = {child};
     return e->add(std::move(n));
@@ -1748,6 +1773,7 @@ int fadb_expr_dot(fadb_expr* e, int lhs, int rhs)
     const ENode& l = e->nodes[lhs];
     const ENode& r = e->nodes[rhs];
     EXPR_REQUIRE(e, l.cols == r.rows, "dot: lhs.cols() != rhs.rows() (dot.hpp:86)");
+    if (int k = find_pure(e, N_DOT, 0, 0, lhs, rhs); k >= 0) return k;
     ENode n; n.kind = N_DOT; n.shape = r.shape == FADB_VEC ? FADB_VEC : FADB_MAT;
     n.rows = l.rows; n.cols = r.cols; n.ch = {lhs, rhs};
     return e->add(std::move(n));

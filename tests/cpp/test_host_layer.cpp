@@ -494,6 +494,61 @@ static void batched_models()
         fadb_jit_stats(j1);
         CHECK(j1[3] == j0[3]);                                // no stage kernel involved
     }
+    // ---- GLM shapes written with the reference's API take the one-pass route (fast=6): logistic regression with an intercept,
+    //      sum(y * eta - log(1 + exp(eta))), eta = dot(X, beta) + b, and normal(y, dot(X, beta) + b, sigma)
+    {
+        const size_t rows = 4096, cols = 3;
+        Var<double, mat> X(rows, cols);
+        Var<double, vec> y(rows), yn(rows);
+        std::vector<double> Xh(rows * cols), yh(rows), ynh(rows);
+        unsigned long long st = 12345;
+        auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return double(st >> 11) / double(1ull << 53); };
+        for (size_t j = 0; j < cols; ++j)
+            for (size_t i = 0; i < rows; ++i) { Xh[i + j * rows] = rnd() - 0.5; X.get()(i, j) = Xh[i + j * rows]; }
+        for (size_t i = 0; i < rows; ++i) { yh[i] = rnd() < 0.5 ? 0.0 : 1.0; ynh[i] = 2.0 * rnd(); y.get()(i) = yh[i]; yn.get()(i) = ynh[i]; }
+        X.upload(); y.upload(); yn.upload();
+        Var<double, vec> beta(cols);
+        beta.get() = {0.3, -0.2, 0.1};
+        Var<double> b(0.25), sigma(1.5);
+        auto Xc = ad::constant_view(X.data(), rows, cols);
+        auto eta = ad::dot(Xc, beta) + b;
+        auto ll = ad::bind(ad::sum(ad::constant_view(y.data(), rows) * eta - ad::log(1. + ad::exp(eta))));
+        unsigned long long j0[4], j1[4];
+        fadb_jit_stats(j0);
+        const unsigned long long l0 = fadb_launch_count();
+        const double v = ad::autodiff(ll);
+        fadb_jit_stats(j1);
+        CHECK(fadb_launch_count() - l0 == 2 && j1[3] == j0[3] + 1 && j1[2] == j0[2]);    // the tile kernel + its scalar epilogue
+        double ref = 0, gb = 0, g[3] = {0, 0, 0};
+        for (size_t i = 0; i < rows; ++i) {
+            double e = 0.25;
+            for (size_t j = 0; j < cols; ++j) e += Xh[i + j * rows] * (j == 0 ? 0.3 : j == 1 ? -0.2 : 0.1);
+            ref += yh[i] * e - std::log(1. + std::exp(e));
+            const double d = yh[i] - 1. / (1. + std::exp(-e));
+            gb += d;
+            for (size_t j = 0; j < cols; ++j) g[j] += d * Xh[i + j * rows];
+        }
+        CHECK_REL(v, ref, 1e-12);
+        CHECK_REL(b.get_adj(), gb, 1e-10);
+        for (size_t j = 0; j < cols; ++j) CHECK_REL(beta.get_adj()(j), g[j], 1e-10);
+
+        beta.reset_adj(); b.reset_adj();
+        auto nl = ad::bind(ad::normal_adj_log_pdf(ad::constant_view(yn.data(), rows), ad::dot(Xc, beta) + b, sigma));
+        fadb_jit_stats(j0);
+        const double vn = ad::autodiff(nl);
+        fadb_jit_stats(j1);
+        CHECK(j1[3] == j0[3] + 1 && j1[2] == j0[2]);
+        double ss = 0, gs_b = 0;
+        for (size_t i = 0; i < rows; ++i) {
+            double m = 0.25;
+            for (size_t j = 0; j < cols; ++j) m += Xh[i + j * rows] * (j == 0 ? 0.3 : j == 1 ? -0.2 : 0.1);
+            ss += (ynh[i] - m) * (ynh[i] - m);
+            gs_b += (ynh[i] - m) / (1.5 * 1.5);
+        }
+        CHECK_REL(vn, -0.5 * ss / (1.5 * 1.5) - double(rows) * std::log(1.5), 1e-12);
+        CHECK_REL(b.get_adj(), gs_b, 1e-10);
+        CHECK_REL(sigma.get_adj(), (ss / (1.5 * 1.5) - double(rows)) / 1.5, 1e-10);
+    }
     // ---- 12 scalar parameters broadcast into one vector stage (more reduction channels than the interpreter has)
     {
         const size_t n = 4321;
