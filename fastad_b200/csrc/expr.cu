@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <atomic>
 #include <map>
 #include <memory>
@@ -445,6 +446,8 @@ struct fadb_expr {
     unsigned flags = 0;
     std::string err;
     size_t cache_vals = 0, cache_adjs = 0;
+    std::map<std::array<long, 5>, int> pure_index;     // (kind, functor, exponent, child, child) -> node id, see find_pure()
+    size_t pure_indexed = 0;
 
     int add(ENode&& n) { nodes.push_back(std::move(n)); return (int)nodes.size() - 1; }
     bool ok(int id) const { return id >= 0 && id < (int)nodes.size(); }
@@ -1636,15 +1639,17 @@ void fadb_expr_destroy(fadb_expr* e)
 // node -- same kind, same functor, same children -- is returned instead of a copy, as fadb_expr_var already does for views of the
 // same storage: the planner then sees ONE dot node read twice and plans its stage once.  Nodes with an identity of their own
 // (placeholder assignments, op=, glue) are never merged; elementwise nodes are re-lowered at every use anyway.
-static int find_pure(const fadb_expr* e, NodeKind kind, int fn, long pw, int c0, int c1)
+static int find_pure(fadb_expr* e, NodeKind kind, int fn, long pw, int c0, int c1)
 {
-    for (size_t k = 0; k < e->nodes.size(); ++k) {
-        const ENode& n = e->nodes[k];
-        if (n.kind != kind || n.fn != fn || n.pw != pw) continue;
-        if ((int)n.ch.size() != (c1 >= 0 ? 2 : 1) || n.ch[0] != c0 || (c1 >= 0 && n.ch[1] != c1)) continue;
-        return (int)k;
+    // index built lazily over the nodes added since the last lookup: O(log n) per node, whatever the graph size
+    for (; e->pure_indexed < e->nodes.size(); ++e->pure_indexed) {
+        const ENode& n = e->nodes[e->pure_indexed];
+        if ((n.kind == N_UNARY || n.kind == N_BINARY || n.kind == N_POW || n.kind == N_DOT) && !n.ch.empty())
+            e->pure_index.emplace(std::array<long, 5>{(long)n.kind, (long)n.fn, n.pw, (long)n.ch[0], n.ch.size() > 1 ? (long)n.ch[1] : -1L},
+                                  (int)e->pure_indexed);
     }
-    return -1;
+    auto it = e->pure_index.find(std::array<long, 5>{(long)kind, (long)fn, pw, (long)c0, (long)c1});
+    return it == e->pure_index.end() ? -1 : it->second;
 }
 
 int fadb_expr_var(fadb_expr* e, int shape, size_t rows, size_t cols, double* val, double* adj)
