@@ -724,6 +724,25 @@ def run_ours(args):
                 {"note": "normal(y, dot(X, w) + b, sigma); algorithmic bytes = one pass over X + y"
                          + ("" if glm else "; one-pass route off: gemv -> normal stage -> gemv^T")})
             del e
+        # a posterior: the regression with intercept as log-likelihood plus three prior terms.  With the additive-root execution every
+        # term is swept once as a root of its own (the likelihood on the one-pass tile kernel); without it the likelihood runs
+        # gemv -> normal stage forward, then normal stage backward -> gemv^T after the root
+        for tag, on in (("per_term", 1), ("one_block", 0)):
+            e = F.Expr()
+            Xc, yc = e.const(Xh), e.const(yh)
+            w, b, sg = e.var((wt + 0.05).reshape(cols, 1)), e.var(0.1), e.var(1.3)
+            lik = e.normal(yc, e.binary("add", e.dot(Xc, w), b), sg)
+            pri = e.binary("add", e.normal(w, e.const(0.0), e.const(2.0)), e.normal(b, e.const(0.0), e.const(10.0)))
+            e.bind(e.binary("add", lik, e.binary("sub", pri, e.binary("mul", e.const(0.5), e.binary("mul", sg, sg)))))
+            prev_add = L.fadb_additive_root_enable(on)
+
+            def post_step(i):
+                F.check(L.fadb_expr_autodiff(e.h, 1.0, None, None))
+            t = timed_loop(post_step, steps2, 3, world)
+            L.fadb_additive_root_enable(prev_add)
+            add(f"expr_posterior_linreg_2^20x64_{tag}", 8 * rows * (cols + 1), t, steps2, rows, "rows",
+                {"note": "normal(y, dot(X, w) + b, s) + normal(w, 0, 2) + normal(b, 0, 10) - 0.5 s^2; algorithmic bytes = one pass over X + y"})
+            del e
         for tag, inner, glm in (("one_pass", False, 1), ("map_one_pass", True, 1), ("generic_dot", True, 0)):
             e = F.Expr()
             Xc, yc, w = e.const(Xh), e.const(yh), e.var((wt + 0.05).reshape(cols, 1))

@@ -436,6 +436,7 @@ struct Stage {
 using namespace fadb;
 
 static std::atomic<int> g_glm_enabled{1};     // fadb_glm_enable: the one-pass dot -> map -> sum route (A/B runs, tests)
+static std::atomic<int> g_additive_enabled{1};   // fadb_additive_root_enable: per-term execution of additive roots
 
 struct fadb_expr {
     std::vector<ENode> nodes;
@@ -916,28 +917,29 @@ struct fadb_expr {
         return FADB_OK;
     }
 
-    void detect_fast_paths()
+    // fast-path routing of the block plan[first..last] whose root is plan[last] (the whole plan, or one additive term of it)
+    void detect_fast_block(size_t first, size_t last)
     {
-        if (plan.empty()) return;
-        Stage& st = *plan.back();
+        const size_t nblk = last - first + 1;
+        Stage& st = *plan[last];
         st.fast = 0;
-        if (st.type != 0 || plan.size() > 2) return;
+        if (st.type != 0 || nblk > 2) return;
         int lf;
-        if (plan.size() == 2 && st.term != T_NORMAL && st.term != T_SUM) return;
+        if (nblk == 2 && st.term != T_NORMAL && st.term != T_SUM) return;
         // sum(pow<2>(y - dot(X, w))) or sum(pow<2>(dot(X, w) - y)), X and y constant: least squares, one pass over X
-        if (plan.size() == 2 && st.term == T_SUM) {
+        if (nblk == 2 && st.term == T_SUM) {
             if (detect_lsq(st)) return;
             detect_glm(st);
             return;
         }
-        if (plan.size() == 1 && st.term == T_SUM && st.prog.size() == 2 && st.root == 1 && leaf_only(st, 0, &lf) &&
+        if (nblk == 1 && st.term == T_SUM && st.prog.size() == 2 && st.root == 1 && leaf_only(st, 0, &lf) &&
             !st.leaves[lf].scalar && (st.prog[1].op == I_UNARY || st.prog[1].op == I_POW) && st.prog[1].a == 0) {
             st.fast = 1;
             st.f_op = st.prog[1].op == I_UNARY ? st.prog[1].fn : 1000 + st.prog[1].fn;
             st.f_x = st.leaves[lf].val; st.f_xadj = st.leaves[lf].adj_mode ? st.leaves[lf].adj : nullptr;
             return;
         }
-        if (st.term > T_NORMAL && plan.size() == 1) {
+        if (st.term > T_NORMAL && nblk == 1) {
             int lx, lb, lc = -1;
             const bool three = st.term != T_BERNOULLI;
             if (leaf_only(st, st.nx, &lx) && (!st.leaves[lx].scalar || st.N == 1) && leaf_only(st, st.nm, &lb) &&
@@ -957,7 +959,7 @@ struct fadb_expr {
             const bool x_leaf = leaf_only(st, st.nx, &lx) && (!st.leaves[lx].scalar || st.N == 1);
             const bool m_leaf = leaf_only(st, st.nm, &lm);
             const bool s_leaf = leaf_only(st, st.ns, &ls);
-            if (plan.size() == 1 && x_leaf && m_leaf && s_leaf && st.prog.size() == 3) {
+            if (nblk == 1 && x_leaf && m_leaf && s_leaf && st.prog.size() == 3) {
                 st.fast = 2;
                 st.f_shape = (st.mu_vec ? 1 : 0) | (st.sig_vec ? 2 : 0);
                 auto adj = [&](int l) { return st.leaves[l].adj_mode ? st.leaves[l].adj : nullptr; };
@@ -972,7 +974,7 @@ struct fadb_expr {
                 st.leaf_stage[Im.leaf] >= 0 && st.prog.size() == 3) {
                 Stage& ds = *plan[st.leaf_stage[Im.leaf]];
                 if (ds.type == 1 && ds.p == 1 && ds.L.stage < 0 && ds.R.stage < 0 && ds.L.adj_mode == 0 &&
-                    ds.k <= 64 && plan.size() == 2) {
+                    ds.k <= 64 && nblk == 2) {
                     st.fast = 3;
                     st.f_X = ds.L.val; st.f_w = ds.R.val; st.f_wadj = ds.R.adj_mode ? ds.R.adj : nullptr;
                     st.f_rows = ds.m; st.f_cols = ds.k;
@@ -982,8 +984,124 @@ struct fadb_expr {
             }
             // normal(y, f(dot(X, w), ...), sigma) with ONE sigma and a mean that is a map of the product (an intercept, a link
             // function): the same one-pass tile kernel with the log-density as its terminal
-            if (st.fast == 0 && plan.size() == 2 && !st.sig_vec) detect_glm(st);
+            if (st.fast == 0 && nblk == 2 && !st.sig_vec) detect_glm(st);
         }
+    }
+
+    // ---- additive roots.  A posterior is a SUM of terms (log-likelihood + log-priors, each a reduction of its own): the
+    // adjoint seed of every term is then known before anything is evaluated (the root's sweep only scales the root seed by
+    // constants), so each term can run as if it were a root of its own -- forward and adjoint sweep fused in ONE pass, routed to
+    // the single-pass kernels where its shape allows -- instead of a forward pass now and a backward pass after the root.
+    // Accepted root programs: a scalar stage of + , - , unary minus and * or / by constants over the term values.
+    struct TermBlock { int first, last, leaf; };
+    std::vector<TermBlock> blocks;          // empty: the plan is executed as one block
+    bool analyse_additive_root()
+    {
+        blocks.clear();
+        static const bool off = getenv("FADB_NO_ADDITIVE_ROOT") != nullptr;
+        if (off || plan.size() < 2) return false;
+        const Stage& rs = *plan.back();
+        if (rs.type != 0 || rs.N != 1 || rs.term != T_NONE || rs.big || !rs.assigned.empty()) return false;
+        std::vector<double> unused;
+        if (!root_term_seeds(rs, 1.0, unused)) return false;
+        std::vector<std::pair<int, int>> terms;             // (producer stage, leaf)
+        for (size_t l = 0; l < rs.leaves.size(); ++l)
+            if (rs.leaf_stage[l] >= 0) terms.push_back({rs.leaf_stage[l], (int)l});
+        if (terms.empty()) return false;
+        std::sort(terms.begin(), terms.end());
+        int prev = -1;
+        for (auto& t : terms) {
+            if (t.first == prev) return false;              // one producer stage, two leaves: not produced by the planner
+            blocks.push_back({prev + 1, t.first, t.second});
+            prev = t.first;
+        }
+        if (prev != (int)plan.size() - 2) { blocks.clear(); return false; }      // every stage below the root belongs to a term
+        // ... and to ONE term only: a stage is read by stages of its own block (its term last), a term by the root alone.
+        // Anything else (an earlier top-level statement, a placeholder shared between terms) keeps the one-block order.
+        const int last = (int)plan.size() - 1;
+        std::vector<std::vector<int>> readers(plan.size());
+        for (int j = 0; j <= last; ++j) {
+            const Stage& st = *plan[j];
+            if (!st.assigned.empty() || !st.eq_slot.empty()) { blocks.clear(); return false; }
+            if (st.type == 0) { for (int ps : st.leaf_stage) if (ps >= 0) readers[ps].push_back(j); }
+            else for (const OperandRef* r : {&st.L, &st.R, &st.S3}) if (r->stage >= 0) readers[r->stage].push_back(j);
+        }
+        for (const TermBlock& b : blocks)
+            for (int k = b.first; k <= b.last; ++k) {
+                if (readers[k].empty()) { blocks.clear(); return false; }
+                for (int j : readers[k])
+                    if (k == b.last ? j != last : (j < b.first || j > b.last)) { blocks.clear(); return false; }
+            }
+        return true;
+    }
+    // The root's adjoint sweep on the host: seeds[leaf] = what the root stage would hand to boundary leaf `leaf` for root seed
+    // `seed`, with the stage kernel's own operation order.  false: the program is not linear in its term values.
+    static bool root_term_seeds(const Stage& rs, double seed, std::vector<double>& seeds)
+    {
+        const size_t n = rs.prog.size();
+        // dep: the slot depends on a term value; isc / cv: the slot is a compile-time constant and its value.  What does not
+        // depend on a term (the root's own scalar leaves, whatever is done to them) is the root stage's own business.
+        std::vector<char> isc(n, 0), dep(n, 0);
+        std::vector<double> cv(n, 0.0), g(n, 0.0);
+        for (size_t k = 0; k < n; ++k) {
+            const Ins& I = rs.prog[k];
+            switch (I.op) {
+            case I_CONST: isc[k] = 1; cv[k] = I.imm; break;
+            case I_LEAF: dep[k] = rs.leaf_stage[I.leaf] >= 0; break;
+            case I_UNARY:
+                dep[k] = dep[I.a];
+                if (dep[k] && I.fn != FADB_NEG) return false;
+                if (I.fn == FADB_NEG) { isc[k] = isc[I.a]; cv[k] = -cv[I.a]; }
+                break;
+            case I_POW: if (dep[I.a]) return false; break;
+            case I_BINARY:
+                dep[k] = dep[I.a] || dep[I.b];
+                if (dep[k] && I.fn != FADB_ADD && I.fn != FADB_SUB && I.fn != FADB_MUL && I.fn != FADB_DIV) return false;
+                if (I.fn == FADB_ADD || I.fn == FADB_SUB || I.fn == FADB_MUL || I.fn == FADB_DIV) {
+                    isc[k] = isc[I.a] && isc[I.b];
+                    cv[k] = I.fn == FADB_ADD ? cv[I.a] + cv[I.b] : I.fn == FADB_SUB ? cv[I.a] - cv[I.b] : I.fn == FADB_MUL ? cv[I.a] * cv[I.b] : cv[I.a] / cv[I.b];
+                }
+                break;
+            default: return false;                            // placeholders, glue, if_else: one-block order
+            }
+        }
+        if (rs.root < 0 || rs.root >= (int)n) return false;
+        seeds.assign(rs.leaves.size(), 0.0);
+        g[rs.root] = seed;
+        for (int k = (int)n - 1; k >= 0; --k) {
+            const Ins& I = rs.prog[k];
+            if (!dep[k]) continue;                            // nothing below this slot is a term
+            const double sd = g[k];
+            switch (I.op) {
+            case I_LEAF: seeds[I.leaf] += sd; break;
+            case I_UNARY: g[I.a] += -sd; break;
+            case I_BINARY:
+                if (I.fn == FADB_ADD) { g[I.b] += sd; g[I.a] += sd; }
+                else if (I.fn == FADB_SUB) { g[I.b] += -sd; g[I.a] += sd; }
+                else if (I.fn == FADB_MUL) {
+                    if (dep[I.a] && dep[I.b]) return false;   // a product of two term values: the seeds depend on the values
+                    if (dep[I.a]) { if (!isc[I.b]) return false; g[I.a] += sd * cv[I.b]; }      // scaled by a run-time scalar: not known on the host
+                    else { if (!isc[I.a]) return false; g[I.b] += sd * cv[I.a]; }
+                } else {
+                    if (dep[I.b] || !isc[I.b]) return false;  // division by a term value or by a run-time scalar
+                    g[I.a] += sd / cv[I.b];
+                }
+                break;
+            default: break;
+            }
+        }
+        return true;
+    }
+
+    void detect_fast_paths()
+    {
+        if (plan.empty()) return;
+        for (auto& sp : plan) sp->fast = 0;
+        if (analyse_additive_root()) {
+            for (const TermBlock& b : blocks) detect_fast_block((size_t)b.first, (size_t)b.last);
+            return;
+        }
+        detect_fast_block(0, plan.size() - 1);
     }
 
     std::string describe() const
@@ -992,6 +1110,7 @@ struct fadb_expr {
         static const char* tn[] = {"store", "sum", "prod", "normal", "cauchy", "uniform", "bernoulli"};
         std::ostringstream o;
         o << "stages=" << plan.size() << " cache={" << cache_vals << "," << cache_adjs << "}\n";
+        if (!blocks.empty()) o << "additive root: " << blocks.size() << " term(s), each swept as a root of its own\n";
         for (size_t k = 0; k < plan.size(); ++k) {
             const Stage& st = *plan[k];
             if (st.type == 5) { o << "stage " << k << ": wishart p=" << st.m << " df=" << st.sig_const << "\n"; continue; }
@@ -1520,6 +1639,25 @@ struct fadb_expr {
     int execute(Context& c, int what, double seed, const double* seed_vec)
     {
         const int last = (int)plan.size() - 1;
+        if (what == 3 && !seed_vec && !blocks.empty() && g_additive_enabled.load()) {
+            // additive root: every term is a root of its own with a seed known now (analyse_additive_root)
+            Stage& rs = *plan[last];
+            std::vector<double> seeds;
+            if (root_term_seeds(rs, seed, seeds)) {
+                for (const TermBlock& b : blocks) {
+                    int rc = execute_range(c, 3, seeds[b.leaf], nullptr, b.first, b.last);
+                    if (rc) return rc;
+                }
+                // the root itself: its value from the term values, and the adjoints of scalar leaves it reads directly
+                return run_map(c, rs, M_FB, seed, nullptr, nullptr);
+            }
+        }
+        return execute_range(c, what, seed, seed_vec, 0, last);
+    }
+
+    // the block plan[first..last] with plan[last] as its root
+    int execute_range(Context& c, int what, double seed, const double* seed_vec, int first_stage, int last)
+    {
         Stage& rs = *plan[last];
         // A log-pdf root swept with seed 0 leaves EVERYTHING below it untouched (normal.hpp:160, cauchy.hpp:151,
         // uniform.hpp / bernoulli.hpp alike): no root sweep and no producer sweeps either -- their boundary adjoints
@@ -1529,9 +1667,9 @@ struct fadb_expr {
             if (!what) return FADB_OK;
         }
         const bool fast = rs.fast != 0 && what == 3 && !seed_vec && (rs.fast != 6 || glm_usable(c, rs));
-        const size_t first = (fast && (rs.fast == 3 || rs.fast == 5 || rs.fast == 6)) ? plan.size() : 0;   // linreg / least squares / one-pass map subsume their dot stage
-        if (what & 1) {
-            for (size_t k = first; k + 1 < plan.size(); ++k) {
+        const bool skip_producers = fast && (rs.fast == 3 || rs.fast == 5 || rs.fast == 6);   // linreg / least squares / one-pass map subsume their dot stage
+        if ((what & 1) && !skip_producers) {
+            for (int k = first_stage; k < last; ++k) {
                 Stage& st = *plan[k];
                 int rc = st.type != 0 ? run_dot(c, st, M_F, nullptr, 0) : run_map(c, st, M_F, 0, nullptr, nullptr);
                 if (rc) return rc;
@@ -1560,7 +1698,7 @@ struct fadb_expr {
         }
         if (rc) return rc;
         if (what & 2) {
-            for (int k = last - 1; k >= 0; --k) {
+            for (int k = last - 1; k >= first_stage; --k) {
                 Stage& st = *plan[k];
                 if (st.type != 0) rc = run_dot(c, st, M_B, nullptr, 0);
                 else rc = run_map(c, st, M_B, 0, st.out_size > 1 ? st.madj : nullptr, st.out_size > 1 ? nullptr : st.madj);
@@ -1930,6 +2068,7 @@ int fadb_expr_jit_program(fadb_expr* e, int stage, int mode, char* buf, size_t c
 }
 
 int fadb_glm_enable(int on) { return g_glm_enabled.exchange(on ? 1 : 0); }
+int fadb_additive_root_enable(int on) { return g_additive_enabled.exchange(on ? 1 : 0); }
 
 int fadb_expr_describe(fadb_expr* e, char* buf, size_t cap)
 {

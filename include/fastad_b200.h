@@ -389,6 +389,12 @@ int fadb_expr_jit_program(fadb_expr*, int stage, int mode, char* buf, size_t cap
  * inside the tile kernel, csrc/glm_kernel.cuh; `fast=6` in fadb_expr_describe) instead of gemv -> map -> gemv^T.
  * fadb_glm_enable(0) turns the route off (returns the previous setting); fadb_expr_jit_program(.., mode 6) is its program. */
 int fadb_glm_enable(int on);
+/* A root that is a SUM of terms (a posterior: log-likelihood + log-priors; +, -, unary minus, * or / by constants over the term
+ * values) hands every term a seed that is known before anything is evaluated: each term is then swept as a root of its own --
+ * forward and adjoint sweep fused in one pass, on the single-pass kernels where its shape allows (`additive root` in
+ * fadb_expr_describe) -- instead of a forward pass before and a backward pass after the root stage.
+ * fadb_additive_root_enable(0) restores the one-block order (returns the previous setting). */
+int fadb_additive_root_enable(int on);
 int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, char* log, size_t log_cap);
 
 #endif /* !__CUDACC_RTC__ */

@@ -183,6 +183,20 @@ def linreg_with_intercept(rows, cols, sigma=1.3, link=False, const_sigma=False):
     return build
 
 
+def posterior_linreg(rows, cols):
+    def build(e):   # a posterior: log-likelihood + log-priors.  normal(y | X w + b, s) + normal(w | 0, 2) + normal(b | 0.5, 10) - 0.5 * sum(s^2)
+        import synth
+        X, y, w_true = synth.linreg_inputs(rows, cols, seed=21)
+        w, b, sg = e.var(w_true + 0.02), e.var(0.3), e.var(1.2)
+        lik = e.normal(e.const(y + 0.3), e.binary("add", e.dot(e.const(X), w), b), sg)
+        pw = e.normal(w, e.const(0.0), e.const(2.0))
+        pb = e.normal(b, e.const(0.5), e.const(10.0))
+        ps = e.binary("mul", e.const(-0.5), e.binary("mul", sg, sg))
+        root = e.binary("add", e.binary("add", e.binary("add", lik, pw), pb), ps)
+        return root, [w, b, sg], 0.9
+    return build
+
+
 def least_squares(rows, cols, flipped=False, x_var=False, inner=False):
     def build(e):   # README.md:640-662 batched: sum(pow<2>(y - dot(X, w))); X constant (or a variable: outer-product adjoint)
         import synth
@@ -592,6 +606,8 @@ CASES = {
     "least_squares_tall_generic": least_squares(6001, 19, inner=True),          # odd row count: gemv -> stage -> gemv^T
     "glm_least_squares_inner": least_squares(6000, 19, inner=True),            # even: the one-pass kernel (fast=6)
     "glm_logistic": glm_logistic(4160, 64),
+    "posterior_linreg": posterior_linreg(4224, 16),
+    "posterior_linreg_odd_rows": posterior_linreg(4099, 5),
     "glm_linreg_intercept": linreg_with_intercept(4224, 64),
     "glm_linreg_intercept_link_const_sigma": linreg_with_intercept(2050, 7, link=True, const_sigma=True),
     "glm_linreg_intercept_invalid_sigma": linreg_with_intercept(1024, 5, sigma=-0.7),

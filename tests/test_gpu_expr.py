@@ -170,6 +170,30 @@ def test_one_pass_dot_map_sum_route(fb, name):
         _close(g, h, 1e-11, f"{name} adj[{k}] vs three-launch route")
 
 
+def test_additive_root_terms_run_as_roots(fb):
+    # log-likelihood + log-priors: each term is swept once (fused, seed known up front), the likelihood on the one-pass tile
+    # kernel; value and adjoints against the oracle come from test_expr_matches_oracle[posterior_linreg], here the launches
+    exprs.RNG = np.random.default_rng(20261019)
+    e = fb.Expr()
+    root, variables, seed = exprs.CASES["posterior_linreg"](e)
+    e.bind(root)
+    d = e.describe()
+    assert "additive root: 3 term(s)" in d and "fast=6" in d
+    e.autodiff(seed)                                     # first call compiles
+    l0 = fb.lib().fadb_launch_count()
+    v = e.autodiff(seed)
+    # tile kernel + its epilogue, two prior stages (one fused launch each), the root stage
+    assert fb.lib().fadb_launch_count() - l0 == 5, fb.lib().fadb_launch_count() - l0
+    exprs.RNG = np.random.default_rng(20261019)
+    oe = O.OracleExpr()
+    oroot, ovars, oseed = exprs.CASES["posterior_linreg"](oe)
+    oe.bind(oroot)
+    ov = oe.autodiff(oseed)
+    _close(v, ov, 1e-12, "posterior value")
+    for g, o in zip(variables, ovars):
+        _close(e.adj(g), 2.0 * np.asarray(oe.adj(o)), 1e-11, "posterior adjoints after two sweeps")
+
+
 def test_one_pass_route_invalid_sigma(fb):
     # normal(y, dot(X, w) + b, sigma) with sigma <= 0 through the one-pass kernel: -inf and NO adjoint (normal.hpp:344)
     exprs.RNG = np.random.default_rng(20261019)

@@ -73,6 +73,18 @@ def test_planner_scalar_broadcast_of_reduction(F):
     assert "(broadcast) <- stage 0" in d
 
 
+def test_planner_additive_root(F):
+    """A sum of terms (log-likelihood + priors): every term becomes a root of its own -- fused sweep with the seed known up
+    front, and the single-pass routes apply INSIDE the posterior (regression with intercept -> fast=6, leaf normal -> fast=2)."""
+    d, _ = _plan(F, exprs.CASES["posterior_linreg"])
+    assert "additive root: 3 term(s)" in d, d[:300]
+    assert "fast=6" in d and "dot 4224x16" in d
+    d, _ = _plan(F, exprs.CASES["sum_of_normals"])
+    assert "additive root: 2 term(s)" in d and "fast=2" in d
+    d, _ = _plan(F, exprs.CASES["vec_nested_sum"])          # w4 * w4 + sin(w4): not linear in the term
+    assert "additive root" not in d
+
+
 def test_planner_fast_paths(F):
     e = F.Expr(device=False)
     x = e.var(np.ones(64))
