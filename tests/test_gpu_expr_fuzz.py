@@ -96,10 +96,17 @@ class Gen:
             root, seed = e.sum(body), float(rng.uniform(0.5, 1.5))
         elif root_kind < 0.8:
             root, seed = e.normal(e.const(rng.uniform(0.5, 1.5, n)), body, spool[-1]), float(rng.uniform(0.5, 1.5))
-        else:
+        elif root_kind < 0.9:
             ph = e.var(np.zeros(n))
             variables.append(ph)
             root, seed = e.glue(e.eq(ph, body), e.sum(e.binary("mul", ph, ph))), float(rng.uniform(0.5, 1.5))
+        else:
+            # a posterior: likelihood-like term + prior terms, combined by +, - and constants (the additive-root execution)
+            lik = e.sum(body)
+            prior = e.normal(vec_vars[0], e.const(1.0), e.const(2.0))
+            pen = e.binary("mul", e.const(-0.5), e.binary("mul", spool[0], spool[0]))
+            root = e.binary("add", e.binary("sub", e.binary("mul", e.const(0.25), lik), e.unary("neg", prior)), pen)
+            seed = float(rng.uniform(0.5, 1.5))
         return root, variables, seed
 
 
@@ -117,7 +124,7 @@ def _close(a, b, what):
 
 
 @pytest.mark.parametrize("engine", ["specialised", "interpreter"])
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(60))
 def test_random_expression_matches_oracle(fb, engine, seed):
     n = (4100, 66, 4099, 128)[seed % 4]          # vector form / tiny / odd (no one-pass route, scalar tail) / even small
     prev = fb.jit_enable(engine == "specialised")
