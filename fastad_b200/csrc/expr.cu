@@ -851,7 +851,19 @@ struct fadb_expr {
         std::string base;
         if (!jit_program_text(st, M_FB, base)) return false;
         std::ostringstream o;
-        o << base << "#define GLM_DOT_LEAF " << st.g_dot_leaf << "\n#define GLM_NVEC " << st.g_nvec
+        // an expensive map is evaluated once per row (rows split over the consumer warps, adjoints through shared memory) instead
+        // of once per row and consumer warp: worth its extra barrier from roughly four transcendentals per row on (measured, tools/glm_probe.py)
+        int cost = 0;
+        for (const DIns& d : st.enc) {
+            if (d.code >= F_UNARY && d.code < F_BINARY) {
+                const int fn = d.code - F_UNARY;
+                cost += (fn == FADB_NEG || fn == FADB_SQUARE || fn == 16) ? 1 : fn == FADB_SQRT ? 12 : 30;
+            } else if (d.code == F_BINARY + FADB_DIV || d.code == F_POW || d.code == F_POW2) cost += 12;
+            else cost += 1;
+        }
+        static const char* split_env = getenv("FADB_GLM_SPLIT");
+        const bool split = split_env ? split_env[0] == '1' : cost > 100;     // 2^20 x 64: logistic (cost ~65) 0.099 vs 0.100 ms split; four transcendentals + erf 0.200 vs 0.135
+        o << base << "#define GLM_SPLIT " << (split ? 1 : 0) << "\n#define GLM_DOT_LEAF " << st.g_dot_leaf << "\n#define GLM_NVEC " << st.g_nvec
           << "\n__device__ constexpr int GLM_VEC_SLOT[JIT_NLEAVES] = {";
         for (size_t l = 0; l < st.g_vec_slot.size(); ++l) o << (l ? ", " : "") << st.g_vec_slot[l];
         o << "};\n";
@@ -861,7 +873,7 @@ struct fadb_expr {
     static size_t glm_smem_bytes(const Stage& st)
     {
         const size_t stage_bytes = 64 * 64 * 8 + (size_t)std::max(st.g_nvec, 1) * 64 * 8;
-        return 3 * stage_bytes + (64 + 2 * 4 * 64 + 64 + 32) * sizeof(double) + 2 * 3 * sizeof(unsigned long long);
+        return 3 * stage_bytes + (64 + 2 * 4 * 64 + 64 + 64 + 64) * sizeof(double) + 2 * 3 * sizeof(unsigned long long);
     }
 
     // can this call take the one-pass kernel?  (operands may have been rebound since the plan was made)

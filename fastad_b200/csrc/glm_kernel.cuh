@@ -15,7 +15,9 @@
 // Layout and pipeline are linreg_tma_kernel's: one producer warp issues ONE cp.async.bulk.tensor.2d per 64 x cols
 // tile (+ one bulk copy per row operand) into a 3-stage mbarrier ring; four consumer warps own 16 columns each,
 // lane l owns rows {2l, 2l+1}.  Every consumer warp evaluates f for the tile's 64 rows (each needs the row
-// adjoints for its own columns; the redundancy costs FP64 issue slots the memory-bound sweep does not use).
+// adjoints for its own columns; the redundancy costs FP64 issue slots the memory-bound sweep does not use) -- unless the map is
+// expensive (GLM_SPLIT, chosen by the host from the program's transcendental count): then warp q evaluates rows 16q .. 16q+15 only,
+// one row per lane, and the row adjoints travel through shared memory (one more barrier per tile, a quarter of the map work).
 #ifdef FADB_JIT
 namespace fadb {
 
@@ -26,6 +28,9 @@ constexpr int GL_NV = GLM_NVEC > 0 ? GLM_NVEC : 1;
 constexpr int GL_STAGE_BYTES = 64 * GL_ROWS * 8 + GL_NV * GL_ROWS * 8;
 constexpr int GL_ACC = JIT_NCH > 1 ? JIT_NCH : 1;     // channel 0: sum of the row values; 1..: adjoints of scalar variables
 constexpr int GL_NL = JIT_NLEAVES > 0 ? JIT_NLEAVES : 1;
+#ifndef GLM_SPLIT
+#define GLM_SPLIT 0
+#endif
 
 struct GlmArgs {
     unsigned long long rows;
@@ -146,8 +151,9 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
     double* w_s = reinterpret_cast<double*>(gl_smem + GL_STAGES * GL_STAGE_BYTES); // [64]
     double* pt_s = w_s + 64;                                                      // [2][4][GL_ROWS]
     double* g_s = pt_s + 2 * 4 * GL_ROWS;                                         // [64]
-    double* ch_s = g_s + 64;                                                      // [32] channel totals of the CTA
-    uint64_t* full = reinterpret_cast<uint64_t*>(ch_s + 32);                      // [GL_STAGES]
+    double* ch_s = g_s + 64;                                                      // [4][16] channel totals per consumer warp
+    double* a_s = ch_s + 64;                                                      // [GL_ROWS] row adjoints of the tile (GLM_SPLIT)
+    uint64_t* full = reinterpret_cast<uint64_t*>(a_s + GL_ROWS);                  // [GL_STAGES]
     uint64_t* empty = full + GL_STAGES;                                           // [GL_STAGES]
     __shared__ bool is_last;
 
@@ -228,6 +234,17 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
             lv0[q] = in0 ? y2.x : 1.0;
             lv1[q] = in1 ? y2.y : 1.0;
         }
+#if GLM_SPLIT
+        const int row_e = 16 * warp + (lane & 15);     // the row this lane evaluates (lanes 16..31 shadow lanes 0..15)
+        const bool in_e = tile * GL_ROWS + row_e < a.rows;
+        double lve[GL_NV];
+#pragma unroll
+        for (int q = 0; q < GL_NV; ++q) {
+            double yv = 1.0;
+            if (q < GLM_NVEC) yv = *reinterpret_cast<const double*>(base + 64 * GL_ROWS * 8 + q * GL_ROWS * 8 + row_e * 8);
+            lve[q] = in_e ? yv : 1.0;
+        }
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);     // the tile is in registers: free the slot
         if (++stage == GL_STAGES) { stage = 0; phase ^= 1; }
@@ -242,14 +259,29 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
         double* pt = pt_s + par * 4 * GL_ROWS;
         *reinterpret_cast<double2*>(pt + warp * GL_ROWS + 2 * lane) = make_double2(s0a + s0b, s1a + s1b);
         gl_consumer_bar();
+        double a0, a1;
+#if GLM_SPLIT
+        {
+            const double te = (pt[row_e] + pt[GL_ROWS + row_e]) + (pt[2 * GL_ROWS + row_e] + pt[3 * GL_ROWS + row_e]);
+            double ae;
+            glm_row(te, lve, sv, a.seed, sig, lane < 16 && in_e, acc, ae);
+            if (lane < 16) a_s[row_e] = in_e ? ae : 0.0;
+        }
+        par ^= 1;
+        gl_consumer_bar();                             // the tile's 64 row adjoints are in shared memory
+        {
+            const double2 a2 = *reinterpret_cast<const double2*>(a_s + 2 * lane);
+            a0 = a2.x; a1 = a2.y;
+        }
+#else
         const double2 p0 = *reinterpret_cast<const double2*>(pt + 2 * lane);
         const double2 p1 = *reinterpret_cast<const double2*>(pt + GL_ROWS + 2 * lane);
         const double2 p2 = *reinterpret_cast<const double2*>(pt + 2 * GL_ROWS + 2 * lane);
         const double2 p3 = *reinterpret_cast<const double2*>(pt + 3 * GL_ROWS + 2 * lane);
         par ^= 1;
-        double a0, a1;
         glm_row((p0.x + p1.x) + (p2.x + p3.x), lv0, sv, a.seed, sig, warp == 0 && in0, acc, a0);
         glm_row((p0.y + p1.y) + (p2.y + p3.y), lv1, sv, a.seed, sig, warp == 0 && in1, acc, a1);
+#endif
         if (!in0) a0 = 0.0;
         if (!in1) a1 = 0.0;
 #pragma unroll
@@ -261,17 +293,18 @@ fadb_glm_jit(GlmArgs a, const __grid_constant__ GlmTensorMap xmap)
         const double t = warp_sum(g[c]);
         if (lane == 0) g_s[warp * GL_CPW + c] = t;
     }
-    if (warp == 0) {
 #pragma unroll
-        for (int c = 0; c < GL_ACC; ++c) {
-            const double t = warp_sum(acc[c]);
-            if (lane == 0) ch_s[c] = t;
-        }
+    for (int c = 0; c < GL_ACC; ++c) {                 // every consumer warp tallied rows (GLM_SPLIT) or warp 0 alone did
+        const double t = warp_sum(acc[c]);
+        if (lane == 0) ch_s[warp * 16 + c] = t;
     }
     gl_consumer_bar();
     const int nslot = GL_ACC + cols;
     double* mine = a.cta_partials + (size_t)blockIdx.x * nslot;
-    if ((int)threadIdx.x < nslot) mine[threadIdx.x] = (int)threadIdx.x < GL_ACC ? ch_s[threadIdx.x] : g_s[threadIdx.x - GL_ACC];
+    if ((int)threadIdx.x < nslot)
+        mine[threadIdx.x] = (int)threadIdx.x < GL_ACC
+                                ? (ch_s[threadIdx.x] + ch_s[16 + threadIdx.x]) + (ch_s[32 + threadIdx.x] + ch_s[48 + threadIdx.x])
+                                : g_s[threadIdx.x - GL_ACC];
     gl_consumer_bar();
     if (threadIdx.x == 0) {       // ONE thread publishes the row: its fence is cumulative over the stores the barrier ordered before it
         __threadfence();
