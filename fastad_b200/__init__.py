@@ -63,6 +63,7 @@ SIGNATURES = {
     "fadb_normal_lpdf_finish": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_glm_enable": (_i, [_i]),
     "fadb_additive_root_enable": (_i, [_i]),
+    "fadb_jit_ring_enable": (_i, [_i]),
     "fadb_normal_lpdf_undo": (_i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _d, _u, _vp]),
     "fadb_normal_dense": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _dp]),
     "fadb_normal_dense_async": (_i, [_sz, _vp, _vp, _i, _vp, _vp, _vp, _vp, _d, _u, _i, _vp]),

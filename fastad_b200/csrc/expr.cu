@@ -405,6 +405,8 @@ struct Stage {
     std::vector<DIns> enc;         // device encoding of `prog` (also the text of the specialised kernel)
     JitKernel jit[4];              // specialised kernels by mode (M_F, M_B, M_FB), compiled on first use
     int jit_state[4] = {0, 0, 0, 0};   // 0 untried, 1 ready, -1 not specialisable / compile failed
+    JitKernel jit_ring[4];         // the same with the cp.async operand ring (stage_kernel.cuh, JIT_RING)
+    int jit_ring_state[4] = {0, 0, 0, 0};
     LeafDesc* d_leaves = nullptr;
     // Leaves that this stage READS from memory and later ASSIGNS (w op= expr, or a read of w ahead of `w = expr`):
     // a backward-only launch (M_B) recomputes the forward values, but the forward-only launch (M_F) has already
@@ -436,6 +438,7 @@ struct Stage {
 using namespace fadb;
 
 static std::atomic<int> g_glm_enabled{1};     // fadb_glm_enable: the one-pass dot -> map -> sum route (A/B runs, tests)
+static std::atomic<int> g_ring_enabled{1};    // fadb_jit_ring_enable: the cp.async operand ring of placeholder stages (A/B runs, tests)
 static std::atomic<int> g_additive_enabled{1};   // fadb_additive_root_enable: per-term execution of additive roots
 
 struct fadb_expr {
@@ -1320,9 +1323,43 @@ struct fadb_expr {
             if (d.code == F_EQ || d.code >= F_OPEQ) return 1;
         return any_vec ? 4 : 1;
     }
-    static bool jit_program_text(const Stage& st, int mode, std::string& out)
+    // The operand ring (stage_kernel.cuh, JIT_RING) serves the one-element form of per-element stages with placeholder
+    // stores: no op= (its stores feed later reads of the same leaf through memory) and no if_else.
+    static bool jit_ring_eligible(const Stage& st)
+    {
+        static const bool off = getenv("FADB_JIT_NO_RING") != nullptr;
+        if (off || !g_ring_enabled.load() || st.big || st.N < 4096 || jit_vec_width(st) != 1) return false;
+        bool any_vec = false;
+        for (const LeafDesc& l : st.leaves) any_vec = any_vec || !l.scalar;
+        for (const DIns& d : st.enc)
+            if (d.code >= F_OPEQ || d.code == F_JZ || d.code == F_JMP || d.code == F_PHI) return false;
+        return any_vec && st.pre.empty();
+    }
+    // A copy issued one trip early must not be overtaken by a store: every buffer the stage WRITES (placeholder values,
+    // adjoints, its own output) has to be disjoint from every other per-element buffer it touches.
+    static bool ring_buffers_disjoint(const Stage& st, const StageArgs& a)
+    {
+        struct Span { const char* lo; const char* hi; bool w; };
+        std::vector<Span> sp;
+        const size_t bytes = st.N * sizeof(double);
+        auto add = [&](const void* p, bool w) { if (p) sp.push_back({(const char*)p, (const char*)p + bytes, w}); };
+        for (size_t l = 0; l < st.leaves.size(); ++l) {
+            const LeafDesc& d = st.leaves[l];
+            if (d.scalar) continue;
+            add(a.lp_val[l], d.assigned != 0);
+            if (d.adj_mode) add(a.lp_adj[l], true);
+        }
+        add(a.out_vec, true);
+        add(a.seed_vec, false);
+        for (size_t i = 0; i < sp.size(); ++i)
+            for (size_t j = i + 1; j < sp.size(); ++j)
+                if ((sp[i].w || sp[j].w) && sp[i].lo < sp[j].hi && sp[j].lo < sp[i].hi) return false;
+        return true;
+    }
+    static bool jit_program_text(const Stage& st, int mode, std::string& out, bool ring = false)
     {
         if (st.big || st.enc.empty() || st.enc.size() > (size_t)MAXS_JIT || st.leaves.size() > (size_t)MAXL_JIT) return false;
+        if (ring && !jit_ring_eligible(st)) return false;
         std::ostringstream o;
         char buf[64];
         // registers: 8 CTAs/SM (64 registers) is the measured optimum for small programs; larger ones spill there
@@ -1337,12 +1374,37 @@ struct fadb_expr {
           << "\n#define JIT_NX " << st.nx << "\n#define JIT_NM " << st.nm << "\n#define JIT_NS " << st.ns
           << "\n#define JIT_MU_VEC " << st.mu_vec << "\n#define JIT_SIG_VEC " << st.sig_vec << "\n#define JIT_NCH " << st.nch
           << "\n__device__ constexpr DIns JIT_PROG[JIT_NINS] = {\n";
-        for (const DIns& d : st.enc) {
+        // ring form: a per-element read behind the leaf's assignment names the assigning instruction in `a` (-1: from memory)
+        const size_t nl = st.leaves.size();
+        std::vector<int> last_eq(nl, -1), rv(nl, -1), ra(nl, -1);
+        std::vector<char> reads_mem(nl, 0);
+        for (size_t k = 0; k < st.enc.size(); ++k) {
+            const DIns& d = st.enc[k];
             if (!std::isfinite(d.imm)) return false;
             snprintf(buf, sizeof buf, "%a", d.imm);                                      // hex float: exact
-            o << "  {" << d.code << ", " << d.a << ", " << d.b << ", " << d.leaf << ", " << buf << "},\n";
+            int fa = d.a;
+            if (ring && d.code == F_LEAF_V) {
+                fa = last_eq[d.leaf];
+                if (fa < 0) reads_mem[d.leaf] = 1;
+            }
+            if (ring && d.code == F_EQ && !st.leaves[d.leaf].scalar) last_eq[d.leaf] = (int)k;
+            o << "  {" << d.code << ", " << fa << ", " << d.b << ", " << d.leaf << ", " << buf << "},\n";
         }
-        o << "};\n__device__ constexpr JitLeaf JIT_LEAF[JIT_NLEAVES > 0 ? JIT_NLEAVES : 1] = {\n";
+        if (ring) {
+            int nrv = 0, nra = 0;
+            for (size_t l = 0; l < nl; ++l) {
+                if (st.leaves[l].scalar) continue;
+                if (reads_mem[l]) rv[l] = nrv++;
+                if (st.leaves[l].adj_mode == 1 && (mode & M_B)) ra[l] = nra++;
+            }
+            if (nrv + nra == 0 || nrv + nra + 1 > 40) return false;                      // 1 KB of shared memory per slot and CTA
+            o << "};\n#define JIT_RING 1\n#define JIT_NRV " << nrv << "\n#define JIT_NRA " << nra << "\n__device__ constexpr int JIT_RV[] = {";
+            for (size_t l = 0; l < nl; ++l) o << rv[l] << ", ";
+            o << "};\n__device__ constexpr int JIT_RA[] = {";
+            for (size_t l = 0; l < nl; ++l) o << ra[l] << ", ";
+            o << "};\n__device__ constexpr JitLeaf JIT_LEAF[JIT_NLEAVES > 0 ? JIT_NLEAVES : 1] = {\n";
+        } else
+            o << "};\n__device__ constexpr JitLeaf JIT_LEAF[JIT_NLEAVES > 0 ? JIT_NLEAVES : 1] = {\n";
         for (const LeafDesc& l : st.leaves)
             o << "  {" << l.scalar << ", " << l.adj_mode << ", " << l.channel << ", " << l.assigned << "},\n";
         if (st.leaves.empty()) o << "  {0, 0, -1, 0}\n";
@@ -1394,6 +1456,24 @@ struct fadb_expr {
             c.launches++;
             FADB_CUDA(cudaGetLastError());
             return FADB_OK;
+        }
+        if (jit_enabled() && st.jit_ring_state[mode] >= 0 && jit_ring_eligible(st) && ring_buffers_disjoint(st, a)) {
+            // the operand-ring form of the specialised kernel (placeholder stages), when no written operand overlaps another
+            if (st.jit_ring_state[mode] == 1 && st.jit_ring[mode].gen != jit_generation()) st.jit_ring_state[mode] = 0;
+            if (st.jit_ring_state[mode] == 0) {
+                std::string text;
+                st.jit_ring_state[mode] = (jit_program_text(st, mode, text, true) && jit_get(c, text, &st.jit_ring[mode]) == FADB_OK) ? 1 : -1;
+            }
+            if (st.jit_ring_state[mode] == 1) {
+                a.vec_ok = 1;
+                int grid = grid_for(c, st.N, st.jit_ring[mode].per_sm, 128);
+                const int kacc = std::max(st.nch, 3);
+                if ((size_t)grid * (kacc + 1) > (size_t)kMaxGrid * kPartialSlots) grid = kMaxGrid * kPartialSlots / (kacc + 1);
+                int rc = jit_launch(st.jit_ring[mode], (unsigned)grid, 128, c.stream, &a);
+                if (rc) return rc;
+                c.launches++;
+                return FADB_OK;
+            }
         }
         if (jit_enabled() && st.jit_state[mode] >= 0) {
             // specialised kernel of this stage program (jit.cu): compiled once per (program, mode, device)
@@ -2066,20 +2146,24 @@ int fadb_expr_jit_program(fadb_expr* e, int stage, int mode, char* buf, size_t c
 {
     EXPR_REQUIRE(e, e && buf && cap > 0, "fadb_expr_jit_program: null argument");
     EXPR_REQUIRE(e, e->planned, "fadb_expr_jit_program: plan first");
-    EXPR_REQUIRE(e, stage >= 0 && stage < (int)e->plan.size() && ((mode >= 1 && mode <= 3) || mode == 6), "fadb_expr_jit_program: bad stage or mode");
+    EXPR_REQUIRE(e, stage >= 0 && stage < (int)e->plan.size() && ((mode >= 1 && mode <= 3) || mode == 6 || (mode >= 9 && mode <= 11)),
+                 "fadb_expr_jit_program: bad stage or mode");
     Stage& st = *e->plan[stage];
     std::string text;
     if (st.type != 0) { set_error("fastad_b200: not an elementwise stage"); return FADB_ERR_UNSUPPORTED; }
     if (st.enc.empty()) fadb_expr::encode_stage(st);
     if (mode == 6) {         // the one-pass dot -> map -> sum kernel of a fast == 6 root stage
         if (st.fast != 6 || !fadb_expr::glm_program_text(st, text)) { set_error("fastad_b200: not a one-pass (fast=6) stage"); return FADB_ERR_UNSUPPORTED; }
-    } else if (!fadb_expr::jit_program_text(st, mode, text)) { set_error("fastad_b200: stage is not specialisable"); return FADB_ERR_UNSUPPORTED; }
+    } else if (!fadb_expr::jit_program_text(st, mode & 7, text, (mode & 8) != 0)) {      // mode | 8: the operand-ring form (JIT_RING)
+        set_error("fastad_b200: stage is not specialisable"); return FADB_ERR_UNSUPPORTED;
+    }
     if (text.size() + 1 > cap) { set_error("fastad_b200: buffer too small"); return FADB_ERR_ARG; }
     memcpy(buf, text.c_str(), text.size() + 1);
     return FADB_OK;
 }
 
 int fadb_glm_enable(int on) { return g_glm_enabled.exchange(on ? 1 : 0); }
+int fadb_jit_ring_enable(int on) { return g_ring_enabled.exchange(on ? 1 : 0); }
 int fadb_additive_root_enable(int on) { return g_additive_enabled.exchange(on ? 1 : 0); }
 
 int fadb_expr_describe(fadb_expr* e, char* buf, size_t cap)

@@ -97,6 +97,9 @@ struct JitLeaf { int scalar, adj_mode, channel, assigned; };   // the compile-ti
 #ifndef JIT_HAS_CF
 #define JIT_HAS_CF 0
 #endif
+#ifndef JIT_RING
+#define JIT_RING 0
+#endif
 #define K_LVAL(k) a.lp_val[k]
 #define K_LADJ(k) a.lp_adj[k]
 #define K_LEAF_SCALAR(k) JIT_LEAF[k].scalar
@@ -166,6 +169,27 @@ __device__ __forceinline__ double block_prod_all(double p, double* sm)
 //   0 = thread-local arrays (fallback), 1 = dynamic shared memory, laid out [slot][thread] so
 //   that a warp access is conflict-free (default: local arrays of this size spill through L1 into
 //   L2/DRAM -- ncu showed 3.6x the algorithmic DRAM writes), 2 = global scratch (BIG programs).
+#if defined(FADB_JIT) && JIT_RING
+// Operand ring of the one-element-per-thread form (stages with placeholder stores).  ncu on the Black-Scholes call
+// expression: half of all stall samples sat on TEN serialised global loads per element -- the operands at their first
+// use, every re-read of a placeholder behind its store (the compiler must assume the store aliases the other leaves), the
+// old adjoints of the three placeholders and of the three variables -- and `prefetch.global.L1` does not shorten them (L1 hit
+// rate 27 %).  Loading everything up front costs registers the 64-register budget does not have.  So the loads become
+// cp.async copies (global -> shared, no registers) issued ONE TRIP AHEAD into a per-thread slot column: values are copied
+// after the forward sweep of the previous trip has consumed its own, old adjoints (and the per-element seed) after its
+// write-back; a trip then waits on data that has been in flight for half a trip or more.  A placeholder read behind its
+// assignment takes the register of the assigning instruction.  Each thread reads only what it copied itself: no barriers.
+// The planner only emits JIT_RING for programs without op= / if_else, and the launch falls back to the plain kernel when
+// any written operand overlaps another one (expr.cu, ring_ok): a copy issued a trip early must not be overtaken by a store.
+__device__ __forceinline__ void ring_cp8(unsigned dst, const double* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ring_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ring_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+constexpr int RING_SLOTS = JIT_NRV + JIT_NRA + 1;       // values | old adjoints | the per-element seed
+#endif
+
 template <int STORE>
 __device__ __forceinline__ void stage_body(const StageArgs& a)
 {
@@ -217,6 +241,37 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
     K_UNROLL
     for (int k = 0; k < K_NLEAVES; ++k) sval[k] = (K_LEAF_SCALAR(k) && !K_LEAF_ASSIGNED(k)) ? K_LVAL(k)[0] : 0.0;
 #endif
+#if defined(FADB_JIT) && JIT_RING
+    __shared__ double s_ring[RING_SLOTS * 128];
+    double* const ring = s_ring + threadIdx.x;
+    unsigned ring_sa;
+    {
+        unsigned long long sa64;
+        asm("cvta.to.shared.u64 %0, %1;" : "=l"(sa64) : "l"(ring));
+        ring_sa = (unsigned)sa64;
+    }
+#define RINGV(k) ring[JIT_RV[k] * 128]
+#define RINGA(k) ring[(JIT_NRV + JIT_RA[k]) * 128]
+#define RING_ISSUE_VALS(j)                                                                                  \
+    do {                                                                                                    \
+        if ((j) < a.N) {                                                                                    \
+            K_UNROLL                                                                                        \
+            for (int k_ = 0; k_ < K_NLEAVES; ++k_)                                                          \
+                if (JIT_RV[k_] >= 0) ring_cp8(ring_sa + JIT_RV[k_] * 1024, K_LVAL(k_) + (j));               \
+        }                                                                                                   \
+        ring_commit();                                                                                      \
+    } while (0)
+#define RING_ISSUE_ADJS(j)                                                                                  \
+    do {                                                                                                    \
+        if ((K_MODE & M_B) && back && (j) < a.N) {                                                          \
+            K_UNROLL                                                                                        \
+            for (int k_ = 0; k_ < K_NLEAVES; ++k_)                                                          \
+                if (JIT_RA[k_] >= 0) ring_cp8(ring_sa + (JIT_NRV + JIT_RA[k_]) * 1024, K_LADJ(k_) + (j));   \
+            if (a.seed_vec) ring_cp8(ring_sa + (JIT_NRV + JIT_NRA) * 1024, a.seed_vec + (j));               \
+        }                                                                                                   \
+        ring_commit();                                                                                      \
+    } while (0)
+#endif
 
     double v_loc[STORE == 0 ? K_SLOTS : 1], g_loc[STORE == 0 ? K_SLOTS : 1], l_loc[STORE == 0 ? K_LSLOTS : 1];
     const int vs = STORE == 1 ? (int)blockDim.x : 1;             // slot stride
@@ -263,9 +318,15 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         const unsigned long long i = base + e;
         if (!full && i >= a.N) break;
 #else
+#if defined(FADB_JIT) && JIT_RING
+    RING_ISSUE_VALS(tid);
+    RING_ISSUE_ADJS(tid);
+#endif
     for (unsigned long long i = tid; i < a.N; i += nth) {
 #endif
-#if defined(FADB_JIT) && JIT_VEC == 1
+#if defined(FADB_JIT) && JIT_RING
+        ring_wait1();                       // this trip's values have landed (its old adjoints may still be in flight)
+#elif defined(FADB_JIT) && JIT_VEC == 1
         {   // One element per trip leaves a thread with too few bytes in flight (ncu on the 10-node chain:
             // long-scoreboard 13.3 of 20 stall cycles per issue, DRAM 37 %).  Start fetching the NEXT
             // trip's operand and adjoint lines now; prefetches hold no registers and merge with the loads.
@@ -304,7 +365,12 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             const DIns I = K_INS(k);
             double r;
             switch (I.code) {
+#if defined(FADB_JIT) && JIT_RING
+            // I.a >= 0: behind its assignment by instruction I.a (that register); else this thread's ring slot
+            case F_LEAF_V: r = I.a >= 0 ? V(I.a >= 0 ? I.a : 0) : (JIT_RV[I.leaf] >= 0 ? RINGV(I.leaf) : K_LOADV(I.leaf)); break;
+#else
             case F_LEAF_V: r = K_LOADV(I.leaf); break;              // var_view.hpp:69
+#endif
 #ifdef FADB_JIT
             case F_LEAF_S: r = K_LEAF_ASSIGNED(I.leaf) ? K_LVAL(I.leaf)[0] : sval[I.leaf]; break;
 #else
@@ -395,6 +461,11 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             if (!in_range) acc[0] += (p <= 0) ? (x == 0 ? 0.0 : -INFINITY) : (x == 1 ? 0.0 : -INFINITY);
             else acc[0] += x == 0 ? log(1 - p) : x == 1 ? log(p) : -INFINITY;
         } else if (fwd_out && a.out_vec) a.out_vec[i] = V(K_ROOT);
+#if defined(FADB_JIT) && JIT_RING
+        RING_ISSUE_VALS(i + nth);           // the forward sweep holds its operands in registers now
+        if (!back) { ring_commit(); continue; }
+        ring_wait1();                       // this trip's old adjoints and seed have landed
+#endif
         if (!back) continue;
 
         // ------------------------------------------------ adjoint sweep (beval)
@@ -402,7 +473,11 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         for (int k = 0; k < K_NINS; ++k) G(k) = 0.0;
         K_UNROLL
         for (int k = 0; k < K_NLEAVES; ++k) LA(k) = 0.0;
+#if defined(FADB_JIT) && JIT_RING
+        const double sd = a.seed_vec ? ring[(JIT_NRV + JIT_NRA) * 128] : seed_s;
+#else
         const double sd = a.seed_vec ? a.seed_vec[i] : seed_s;
+#endif
         if (!gated) {
             if (K_TERM == T_NORMAL) {
                 const double x = V(K_NX), m = V(K_NM), s = nrm_s, d = nrm_d;
@@ -465,7 +540,12 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
                 case F_CONST: break;
                 case F_EQ: {                                                                      // eq.hpp:101-107
                     if (K_LEAF_SCALAR(I.leaf) && a.N > 1) { G(I.a) += s + LA(I.leaf); break; }   // not produced by the planner
+#if defined(FADB_JIT) && JIT_RING
+                    const double tot = ((JIT_RA[I.leaf] >= 0 ? RINGA(I.leaf) : K_LADJ(I.leaf)[i]) + LA(I.leaf)) + s;
+                    if (JIT_RA[I.leaf] >= 0) RINGA(I.leaf) = tot;       // a second assignment of the same placeholder reads this
+#else
                     const double tot = (K_LADJ(I.leaf)[i] + LA(I.leaf)) + s;
+#endif
                     K_LADJ(I.leaf)[i] = tot;
                     LA(I.leaf) = 0.0;
                     G(I.a) += tot;
@@ -536,9 +616,16 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             la[k][e] = LA(k);                              // stored by the vector write-back below
 #else
             if (K_LEAF_ADJ_MODE(k) == 2) K_LADJ(k)[i] = LA(k);
+#if defined(FADB_JIT) && JIT_RING
+            else if (!gated) K_LADJ(k)[i] = (JIT_RA[k] >= 0 ? RINGA(k) : K_LADJ(k)[i]) + LA(k);
+#else
             else if (!gated) K_LADJ(k)[i] += LA(k);
 #endif
+#endif
         }
+#if defined(FADB_JIT) && JIT_RING
+        RING_ISSUE_ADJS(i + nth);
+#endif
 #if defined(FADB_JIT) && JIT_VEC > 1
         }   // e
         if (back) {

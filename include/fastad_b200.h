@@ -395,6 +395,13 @@ int fadb_glm_enable(int on);
  * fadb_expr_describe) -- instead of a forward pass before and a backward pass after the root stage.
  * fadb_additive_root_enable(0) restores the one-block order (returns the previous setting). */
 int fadb_additive_root_enable(int on);
+/* Per-element stages with placeholder stores (`c = expr` over vectors, reverse/core/eq.hpp:68-125; the vectorised
+ * example/black_scholes.cpp) run one element per thread; their specialised kernel fetches every operand, old adjoint and
+ * per-element seed one trip ahead with cp.async into a per-thread shared-memory column instead of ten serialised global
+ * loads per element (csrc/stage_kernel.cuh, JIT_RING).  Taken when no written operand of the stage overlaps another operand;
+ * fadb_jit_ring_enable(0) keeps the plain kernel (returns the previous setting); fadb_expr_jit_program(.., mode | 8) is
+ * its program text. */
+int fadb_jit_ring_enable(int on);
 int fadb_jit_compile_only(const char* program, size_t* cubin_bytes, char* log, size_t log_cap);
 
 #endif /* !__CUDACC_RTC__ */

@@ -103,6 +103,41 @@ def vec_placeholder_chain(n):
     return build
 
 
+def placeholder_sum(n):
+    def build(e):   # a reduction over a stage that assigns a placeholder (sum terminal + scalar channel + placeholder store)
+        x, a, s = e.var(_vec(n)), e.var(np.zeros(n)), e.var(0.8)
+        root = e.glue(e.eq(a, e.unary("log", x)),
+                      e.sum(e.binary("add", e.binary("mul", a, a), e.binary("mul", s, x))))
+        return root, [x, a, s], 1.0
+    return build
+
+
+def placeholder_reassigned(n):
+    def build(e):   # the same placeholder assigned twice, read between and after the assignments
+        x = e.var(_vec(n))
+        a, b = e.var(np.zeros(n)), e.var(np.zeros(n))
+        root = e.glue(e.eq(a, e.unary("log", x)),
+                      e.eq(b, e.binary("mul", a, a)),
+                      e.eq(a, e.binary("add", b, x)),
+                      e.binary("sub", e.unary("sin", a), e.binary("mul", b, x)))
+        return root, [x, a, b], _vec(n, -1, 1)
+    return build
+
+
+def placeholder_normal(n):
+    def build(e):   # log-pdf terminal fed by a placeholder: normal(y, a = w x, sigma)
+        x, y = e.const(_vec(n)), e.const(_vec(n))
+        w, sg, a = e.var(0.9), e.var(1.4), e.var(np.zeros(n))
+        return e.glue(e.eq(a, e.binary("mul", w, x)), e.normal(y, a, sg)), [w, sg, a], 1.0
+    return build
+
+
+# Not compared with the oracle: the reference's EqNode::beval reads the placeholder's STORAGE (eq.hpp:101-107), so a placeholder
+# assigned twice is differentiated with its last value throughout -- not a derivative of anything; the stage kernels keep
+# one value per assignment.  The case stays for the ring-vs-plain bit-identity test (two assignments of one ring slot).
+NO_ORACLE = {"placeholder_reassigned_ring"}
+
+
 def normal_with_expr_mean(n):
     def build(e):   # univariate regression: normal(y | alpha + beta * x, sigma)
         y, x = e.const(_vec(n, -1, 1)), e.const(_vec(n))
@@ -583,6 +618,13 @@ CASES = {
     "vec_root_vector_seed_4100": vec_root_with_vector_seed(4100),
     "vec_root_vector_seed": vec_root_with_vector_seed(2049),
     "vec_placeholder_chain": vec_placeholder_chain(1025),
+    # >= 4096 elements with placeholder stores: the cp.async operand ring of the specialised kernel (several trips per thread)
+    "placeholder_chain_ring": vec_placeholder_chain(333337),
+    "placeholder_sum_ring": placeholder_sum(200003),
+    "placeholder_reassigned_ring": placeholder_reassigned(170001),
+    "placeholder_normal_ring": placeholder_normal(160001),
+    "black_scholes_call_ring": black_scholes_vec(400003),
+    "black_scholes_put_ring_4099": black_scholes_vec(4099, put=True),
     "normal_expr_mean": normal_with_expr_mean(5001),
     "normal_vec_sigma_expr": normal_vec_sigma_expr(3000),
     "sum_of_normals": sum_of_normals(2000),

@@ -187,6 +187,39 @@ def test_stage_program_specialises_to_register_code(F, name):
     assert compiled >= 3
 
 
+@pytest.mark.parametrize("name", ["black_scholes_call_ring", "placeholder_chain_ring", "placeholder_reassigned_ring", "placeholder_sum_ring"])
+def test_operand_ring_form_of_a_placeholder_stage_compiles(F, name):
+    """Per-element stages with placeholder stores and >= 4096 elements: the operand-ring form (mode | 8; cp.async copies one
+    trip ahead into a per-thread shared-memory column, stage_kernel.cuh JIT_RING) compiles for sm_100a inside the 64-register
+    budget without spills; a read behind the placeholder's assignment names the assigning instruction instead of memory."""
+    import re
+    exprs.RNG = np.random.default_rng(1)
+    e = F.Expr(device=False)
+    root, _, _ = exprs.CASES[name](e)
+    e.plan(root)
+    for mode in (1, 2, 3):
+        text = e.jit_program(0, mode | 8)
+        assert "#define JIT_RING 1" in text and "JIT_RV[]" in text and "JIT_RA[]" in text
+        nrv, nra = int(re.search(r"JIT_NRV (\d+)", text).group(1)), int(re.search(r"JIT_NRA (\d+)", text).group(1))
+        assert nrv >= 1 and (nra >= 1) == (mode != 1)            # no old adjoints in a forward-only launch
+        plain = e.jit_program(0, mode)
+        assert "JIT_RING" not in plain
+        nbytes, log = F.jit_compile_only(text)
+        assert nbytes > 0, log[-800:]
+        m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", log)
+        assert m and int(m.group(2)) == 0 and int(m.group(1)) <= 48, log[-800:]
+        assert int(re.search(r"Used (\d+) registers", log).group(1)) <= 64
+        assert int(re.search(r"(\d+) bytes smem", log).group(1)) >= (nrv + nra + 1) * 1024
+    # small stages and stages without placeholder stores keep the plain forms
+    for other in ("black_scholes_call", "vec_sum_chain_100k"):
+        exprs.RNG = np.random.default_rng(1)
+        e2 = F.Expr(device=False)
+        r2, _, _ = exprs.CASES[other](e2)
+        e2.plan(r2)
+        with pytest.raises(F.FadbError):
+            e2.jit_program(0, 3 | 8)
+
+
 @pytest.mark.parametrize("name", ["glm_logistic", "glm_logistic_weighted_ragged", "glm_least_squares_inner", "glm_linreg_intercept",
                                   "glm_linreg_intercept_link_const_sigma"])
 def test_one_pass_dot_map_sum_kernel_compiles(F, name):
