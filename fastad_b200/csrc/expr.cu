@@ -1328,12 +1328,12 @@ struct fadb_expr {
     static bool jit_ring_eligible(const Stage& st)
     {
         static const bool off = getenv("FADB_JIT_NO_RING") != nullptr;
-        if (off || !g_ring_enabled.load() || st.big || st.N < 4096 || jit_vec_width(st) != 1) return false;
+        if (off || !g_ring_enabled.load() || st.big || st.N < 4096 || !st.pre.empty() || jit_vec_width(st) != 1) return false;
         bool any_vec = false;
         for (const LeafDesc& l : st.leaves) any_vec = any_vec || !l.scalar;
         for (const DIns& d : st.enc)
             if (d.code >= F_OPEQ || d.code == F_JZ || d.code == F_JMP || d.code == F_PHI) return false;
-        return any_vec && st.pre.empty();
+        return any_vec;
     }
     // A copy issued one trip early must not be overtaken by a store: every buffer the stage WRITES (placeholder values,
     // adjoints, its own output) has to be disjoint from every other per-element buffer it touches.
@@ -1398,7 +1398,8 @@ struct fadb_expr {
                 if (st.leaves[l].adj_mode == 1 && (mode & M_B)) ra[l] = nra++;
             }
             if (nrv + nra == 0 || nrv + nra + 1 > 40) return false;                      // 1 KB of shared memory per slot and CTA
-            o << "};\n#define JIT_RING 1\n#define JIT_NRV " << nrv << "\n#define JIT_NRA " << nra << "\n__device__ constexpr int JIT_RV[] = {";
+            o << "};\n#define JIT_RING 1\n#define JIT_NRV " << nrv << "\n#define JIT_NRA " << nra << "\n#define JIT_NRS " << (st.term == T_NONE ? 1 : 0)
+              << "\n__device__ constexpr int JIT_RV[] = {";
             for (size_t l = 0; l < nl; ++l) o << rv[l] << ", ";
             o << "};\n__device__ constexpr int JIT_RA[] = {";
             for (size_t l = 0; l < nl; ++l) o << ra[l] << ", ";

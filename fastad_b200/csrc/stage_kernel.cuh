@@ -187,7 +187,7 @@ __device__ __forceinline__ void ring_cp8(unsigned dst, const double* src)
 }
 __device__ __forceinline__ void ring_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ring_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-constexpr int RING_SLOTS = JIT_NRV + JIT_NRA + 1;       // values | old adjoints | the per-element seed
+constexpr int RING_SLOTS = JIT_NRV + JIT_NRA + JIT_NRS;     // values | old adjoints | the per-element seed (vector-valued stages)
 #endif
 
 template <int STORE>
@@ -267,7 +267,7 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
             K_UNROLL                                                                                        \
             for (int k_ = 0; k_ < K_NLEAVES; ++k_)                                                          \
                 if (JIT_RA[k_] >= 0) ring_cp8(ring_sa + (JIT_NRV + JIT_RA[k_]) * 1024, K_LADJ(k_) + (j));   \
-            if (a.seed_vec) ring_cp8(ring_sa + (JIT_NRV + JIT_NRA) * 1024, a.seed_vec + (j));               \
+            if (JIT_NRS && a.seed_vec) ring_cp8(ring_sa + (JIT_NRV + JIT_NRA) * 1024, a.seed_vec + (j));               \
         }                                                                                                   \
         ring_commit();                                                                                      \
     } while (0)
@@ -474,7 +474,7 @@ __device__ __forceinline__ void stage_body(const StageArgs& a)
         K_UNROLL
         for (int k = 0; k < K_NLEAVES; ++k) LA(k) = 0.0;
 #if defined(FADB_JIT) && JIT_RING
-        const double sd = a.seed_vec ? ring[(JIT_NRV + JIT_NRA) * 128] : seed_s;
+        const double sd = a.seed_vec ? (JIT_NRS ? ring[(JIT_NRV + JIT_NRA) * 128] : a.seed_vec[i]) : seed_s;
 #else
         const double sd = a.seed_vec ? a.seed_vec[i] : seed_s;
 #endif

@@ -625,6 +625,9 @@ CASES = {
     "placeholder_normal_ring": placeholder_normal(160001),
     "black_scholes_call_ring": black_scholes_vec(400003),
     "black_scholes_put_ring_4099": black_scholes_vec(4099, put=True),
+    # several trips per thread of the four-element form (no placeholder stores), full trips + a partial last one
+    "vec_sum_chain_1300003": vec_sum_chain(1300003),
+    "vec_root_vector_seed_1250001": vec_root_with_vector_seed(1250001),
     "normal_expr_mean": normal_with_expr_mean(5001),
     "normal_vec_sigma_expr": normal_vec_sigma_expr(3000),
     "sum_of_normals": sum_of_normals(2000),
