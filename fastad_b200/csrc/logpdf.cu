@@ -118,10 +118,13 @@ __device__ __forceinline__ void lp_rmw4(double* p, const double (&g)[4], int ove
 }
 
 // channels: 0 value sum, 1 scalar-b adjoint sum, 2 scalar-c adjoint sum, 3 #invalid
-template <int DIST, bool B_VEC, bool C_VEC>
-__global__ void __launch_bounds__(256)
+// VAR (bit 0: the old vector adjoints are loaded at the top of the trip, next to the operands, instead of at the
+// read-modify-write; bit 1: the NEXT trip's operands are loaded before this trip's arithmetic, register double-buffered)
+template <int DIST, bool B_VEC, bool C_VEC, int VAR>
+__global__ void __launch_bounds__(256, (VAR & 4) ? 4 : 1)
 lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] value, invalid, -, - */)
 {
+    constexpr bool EARLY = VAR & 1, PIPE = VAR & 2;
     __shared__ double s_logt[DIST == FADB_BERNOULLI ? 387 : 1];
     if (DIST == FADB_BERNOULLI) {           // constant data: copied before the dependency wait
         for (int i = threadIdx.x; i < 387; i += blockDim.x) s_logt[i] = fm::kLogT_d[i];
@@ -144,12 +147,32 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
                      (!a.x_adj || aligned32(a.x_adj)) && (!B_VEC || !a.b_adj || aligned32(a.b_adj)) &&
                      (!C_VEC || !a.c_adj || aligned32(a.c_adj));
     const size_t n4 = vec ? a.n / 4 : 0;
+    double4_t xv, bv, cv;
+    if (PIPE && tid < n4) {
+        xv = ldg256_stream(a.x + 4 * tid);
+        if (B_VEC) bv = ldg256_stream(a.b + 4 * tid);
+        if (C_VEC) cv = ldg256_stream(a.c + 4 * tid);
+    }
     for (size_t q = tid; q < n4; q += nth) {
         const size_t i = 4 * q;
-        const double4_t xv = ldg256_stream(a.x + i);
-        double4_t bv, cv;
-        if (B_VEC) bv = ldg256_stream(a.b + i);
-        if (C_VEC) cv = ldg256_stream(a.c + i);
+        double4_t xn, bn, cn;
+        if (PIPE) {
+            if (q + nth < n4) {
+                xn = ldg256_stream(a.x + i + 4 * nth);
+                if (B_VEC) bn = ldg256_stream(a.b + i + 4 * nth);
+                if (C_VEC) cn = ldg256_stream(a.c + i + 4 * nth);
+            }
+        } else {
+            xv = ldg256_stream(a.x + i);
+            if (B_VEC) bv = ldg256_stream(a.b + i);
+            if (C_VEC) cv = ldg256_stream(a.c + i);
+        }
+        double4_t ox, ob, oc;           // old adjoints, in flight during the arithmetic
+        if (EARLY && !a.overwrite) {
+            if (wx) ox = ld256(a.x_adj + i);
+            if (wb && B_VEC) ob = ld256(a.b_adj + i);
+            if (wc && C_VEC) oc = ld256(a.c_adj + i);
+        }
         double gx[4], gb[4], gc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -162,9 +185,18 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
             if (!B_VEC) acc[1] += gb[k];
             if (!C_VEC) acc[2] += gc[k];
         }
-        if (wx) lp_rmw4(a.x_adj + i, gx, a.overwrite);
-        if (wb && B_VEC) lp_rmw4(a.b_adj + i, gb, a.overwrite);
-        if (wc && C_VEC) lp_rmw4(a.c_adj + i, gc, a.overwrite);
+        if (EARLY && !a.overwrite) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ox.v[k] += gx[k]; ob.v[k] += gb[k]; oc.v[k] += gc[k]; }
+            if (wx) st256(a.x_adj + i, ox);
+            if (wb && B_VEC) st256(a.b_adj + i, ob);
+            if (wc && C_VEC) st256(a.c_adj + i, oc);
+        } else {
+            if (wx) lp_rmw4(a.x_adj + i, gx, a.overwrite);
+            if (wb && B_VEC) lp_rmw4(a.b_adj + i, gb, a.overwrite);
+            if (wc && C_VEC) lp_rmw4(a.c_adj + i, gc, a.overwrite);
+        }
+        if (PIPE) { xv = xn; bv = bn; cv = cn; }
     }
     for (size_t i = n4 * 4 + tid; i < a.n; i += nth) {
         const double x = a.x[i], b = B_VEC ? a.b[i] : bs, c = C_VEC ? a.c[i] : cs;
@@ -235,8 +267,21 @@ static int run_logpdf(Context& c, LpArgs a, unsigned flags, bool any_adj, double
         a.invalid_in = invalid;
     }
     const int threads = 256;
-    const int grid = resident_grid(c, lp_kernel<DIST, B_VEC, C_VEC>, threads, 0, (a.n + 3) / 4, threads);
-    FADB_CUDA(launch_pdl(lp_kernel<DIST, B_VEC, C_VEC>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 10, out));
+    // Bernoulli (32 B per element, the one log-pdf whose arithmetic is comparable to its memory time): ncu showed two exposed
+    // waits per trip, on the operands and on the old adjoints of the read-modify-write (25 % + 22 % of all stall samples).  Loading
+    // the old adjoints next to the operands leaves one: 0.206 -> 0.199 ms at 2^25 elements; double-buffering the operands as well
+    // (VAR 3, 80 registers) measured the same.  FADB_LP_VARIANT=0|3|5 selects a variant for A/B runs.
+    static const int var_env = getenv("FADB_LP_VARIANT") ? atoi(getenv("FADB_LP_VARIANT")) : -1;
+    const int var = DIST == FADB_BERNOULLI ? (var_env >= 0 ? (var_env & 7) : 5) : 0;
+#define FADB_LP_LAUNCH(V)                                                                                                       \
+    do {                                                                                                                        \
+        const int grid = resident_grid(c, lp_kernel<DIST, B_VEC, C_VEC, V>, threads, 0, (a.n + 3) / 4, threads);                \
+        FADB_CUDA(launch_pdl(lp_kernel<DIST, B_VEC, C_VEC, V>, grid, threads, 0, c.stream, a, c.partials, c.tickets + 10, out)); \
+    } while (0)
+    if (DIST == FADB_BERNOULLI && var == 5) FADB_LP_LAUNCH(DIST == FADB_BERNOULLI ? 5 : 0);
+    else if (DIST == FADB_BERNOULLI && var == 3) FADB_LP_LAUNCH(DIST == FADB_BERNOULLI ? 3 : 0);
+    else FADB_LP_LAUNCH(0);
+#undef FADB_LP_LAUNCH
     c.launches++;
     if (guarded && !(flags & FADB_STRICT_SIGMA)) {
         const int ugrid = resident_grid(c, lp_undo_kernel<DIST, B_VEC, C_VEC>, threads, 0, a.n, threads);
