@@ -67,6 +67,7 @@ struct CholSmem {
     double Tc[DB][2 * DB];                 // Tc[j][i] = l_ij (column j contiguous), zero for i >= 32
     double colbuf[2 * DB], rinv_s[DB];
     double P[CS_ROWS + CS_TOP + 8][DB + 1];// own rows first, then the top rows of the panel (+8 rows of slack)
+    int ready;                             // columns of the tile finished by warp 0 (phase B follows it column by column)
 };
 
 __global__ void __launch_bounds__(256)
@@ -77,6 +78,21 @@ dn_chol_step(int n, double* L, double* F, double* diag, int k0, int pc, double* 
     CholSmem& S = *reinterpret_cast<CholSmem*>(smem_raw);
     const int t = threadIdx.x, r = t & 31;
     const int top0 = k0 + DB, own0 = top0 + blockIdx.x * CS_ROWS, R = CS_ROWS + pc;
+    if (t == 0) S.ready = 0;
+    __syncthreads();
+    // C values of this thread (row i, columns jg*8 + 32*b + v), in flight during phases A and B
+    const int i = t & 63, jg = t >> 6, gi = own0 + i;
+    double cv[3][8];
+#pragma unroll
+    for (int bq = 0; bq < 3; ++bq)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int j = jg * 8 + bq * 32 + v, gj = top0 + j;
+            cv[bq][v] = (j < pc && gi < n && gi >= gj) ? L[gi + (size_t)gj * n] : 0.0;
+        }
+    // %globaltimer stamps of one step at n = 4000 (round 2): 8 us for the 32-pivot chain of phase A, THEN 4 us for the forward
+    // substitution of phase B, one thread per row.  B needs column j of the tile, not the tile: the row threads (warps 1..)
+    // now follow warp 0 column by column (S.ready) and finish a few hundred cycles after it.
     if (t < 32) {
         double row[DB];
 #pragma unroll
@@ -87,8 +103,8 @@ dn_chol_step(int n, double* L, double* F, double* diag, int k0, int pc, double* 
         S.colbuf[DB + r] = 0.0;
         bool bad = false;
         const bool writer = blockIdx.x == 0;
+        double p = __shfl_sync(0xffffffffu, row[0], 0);
         for (int j = 0; j < DB; ++j) {
-            const double p = __shfl_sync(0xffffffffu, row[0], j);
             bad |= !(p > 0);                                // llt.info() != Success, normal.hpp:660
             double y;
             asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
@@ -96,12 +112,18 @@ dn_chol_step(int n, double* L, double* F, double* diag, int k0, int pc, double* 
             y = y * fma(-h * y, y, 1.5);
             y = y * fma(-h * y, y, 1.5);
             const double lrj = (r >= j) ? row[0] * y : 0.0; // l_rj; the pivot lane gets p / sqrt(p)
+            // the NEXT pivot is lane j+1's a_(j+1)(j+1) - l_(j+1)j^2: formed from registers, ahead of the update sweep (the
+            // sweep computes the same fma through shared memory), so that its rsqrt chain starts without the round trip
+            const double own_next = fma(-lrj, lrj, row[1]);
+            p = __shfl_sync(0xffffffffu, own_next, (j + 1) & 31);
             S.colbuf[r] = lrj;
             S.Tc[j][r] = lrj;
             if (r == j) S.rinv_s[j] = y;
             if (writer && r >= j && k0 + r < n && k0 + j < n) F[(k0 + r) + (size_t)(k0 + j) * n] = lrj;
             if (writer && r == j && k0 + j < n) diag[k0 + j] = lrj;
             __syncwarp();
+            __threadfence_block();
+            if (r == 0) *reinterpret_cast<volatile int*>(&S.ready) = j + 1;
 #pragma unroll
             for (int c = 1; c < DB; ++c) row[c - 1] = fma(-lrj, S.colbuf[j + c], row[c]);
             row[DB - 1] = 0.0;
@@ -114,35 +136,28 @@ dn_chol_step(int n, double* L, double* F, double* diag, int k0, int pc, double* 
             const int g = rr < CS_ROWS ? own0 + rr : top0 + (rr - CS_ROWS);
             S.P[rr][cc] = (g < n && k0 + cc < n) ? L[g + (size_t)(k0 + cc) * n] : 0.0;
         }
-    }
-    // C values of this thread (row i, columns jg*8 + 32*b + v), in flight during phase B
-    const int i = t & 63, jg = t >> 6, gi = own0 + i;
-    double cv[3][8];
+        asm volatile("bar.sync 1, 224;" ::: "memory");      // the raw rows are staged (warps 1..7 only; warp 0 is factoring)
+        // B: forward substitution x L_kk^T = p, one row per thread, row in registers, one column behind warp 0
+        const int tt = t - 32;
+        if (tt < R) {
+            double pr[DB];
 #pragma unroll
-    for (int bq = 0; bq < 3; ++bq)
+            for (int q = 0; q < DB; ++q) pr[q] = S.P[tt][q];
+            const bool own = tt < CS_ROWS && own0 + tt < n;
+            for (int c = 0; c < DB; ++c) {
+                while (*reinterpret_cast<volatile int*>(&S.ready) <= c) __nanosleep(20);
+                __threadfence_block();
+                const double x = pr[0] * S.rinv_s[c];
+                S.P[tt][c] = x;
+                if (own && k0 + c < n) F[(own0 + tt) + (size_t)(k0 + c) * n] = x;
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int j = jg * 8 + bq * 32 + v, gj = top0 + j;
-            cv[bq][v] = (j < pc && gi < n && gi >= gj) ? L[gi + (size_t)gj * n] : 0.0;
+                for (int u = 1; u < DB; ++u) pr[u - 1] = fma(-x, S.Tc[c][c + u], pr[u]);
+                pr[DB - 1] = 0.0;
+            }
         }
+    }
     __syncthreads();
     if (own0 >= n && blockIdx.x > 0) return;
-    // B: forward substitution x L_kk^T = p, one row per thread, row in registers
-    if (t < R) {
-        double pr[DB];
-#pragma unroll
-        for (int q = 0; q < DB; ++q) pr[q] = S.P[t][q];
-        const bool own = t < CS_ROWS && own0 + t < n;
-        for (int c = 0; c < DB; ++c) {
-            const double x = pr[0] * S.rinv_s[c];
-            S.P[t][c] = x;
-            if (own && k0 + c < n) F[(own0 + t) + (size_t)(k0 + c) * n] = x;
-#pragma unroll
-            for (int u = 1; u < DB; ++u) pr[u - 1] = fma(-x, S.Tc[c][c + u], pr[u]);
-            pr[DB - 1] = 0.0;
-        }
-    }
-    __syncthreads();
     // C: rank-32 update of the rest of the outer panel, 8 columns (independent chains) at a time
     if (pc <= 0) return;
     double pr[DB];
