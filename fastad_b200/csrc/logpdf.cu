@@ -121,7 +121,7 @@ __device__ __forceinline__ void lp_rmw4(double* p, const double (&g)[4], int ove
 // VAR (bit 0: the old vector adjoints are loaded at the top of the trip, next to the operands, instead of at the
 // read-modify-write; bit 1: the NEXT trip's operands are loaded before this trip's arithmetic, register double-buffered)
 template <int DIST, bool B_VEC, bool C_VEC, int VAR>
-__global__ void __launch_bounds__(256, (VAR & 4) ? 4 : 1)
+__global__ void __launch_bounds__(256, (VAR & 2) ? 3 : 4)
 lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] value, invalid, -, - */)
 {
     constexpr bool EARLY = VAR & 1, PIPE = VAR & 2;
@@ -147,6 +147,30 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
                      (!a.x_adj || aligned32(a.x_adj)) && (!B_VEC || !a.b_adj || aligned32(a.b_adj)) &&
                      (!C_VEC || !a.c_adj || aligned32(a.c_adj));
     const size_t n4 = vec ? a.n / 4 : 0;
+    if (VAR == 0) {
+    for (size_t q = tid; q < n4; q += nth) {
+        const size_t i = 4 * q;
+        const double4_t xv = ldg256_stream(a.x + i);
+        double4_t bv, cv;
+        if (B_VEC) bv = ldg256_stream(a.b + i);
+        if (C_VEC) cv = ldg256_stream(a.c + i);
+        double gx[4], gb[4], gc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double b = B_VEC ? bv.v[k] : bs, c = C_VEC ? cv.v[k] : cs;
+            const bool ok = Lp<DIST>::valid(xv.v[k], b, c);
+            if (!ok) acc[3] += 1.0;
+            acc[0] += (ok || DIST == FADB_BERNOULLI) ? Lp<DIST>::term(xv.v[k], b, c, single, lt) : 0.0;
+            Lp<DIST>::adj(xv.v[k], b, c, a.seed, single, gx[k], gb[k], gc[k]);
+            if (!ok) gx[k] = gb[k] = gc[k] = 0.0;          // optimistic pass: an out-of-range element adds nothing
+            if (!B_VEC) acc[1] += gb[k];
+            if (!C_VEC) acc[2] += gc[k];
+        }
+        if (wx) lp_rmw4(a.x_adj + i, gx, a.overwrite);
+        if (wb && B_VEC) lp_rmw4(a.b_adj + i, gb, a.overwrite);
+        if (wc && C_VEC) lp_rmw4(a.c_adj + i, gc, a.overwrite);
+    }
+    } else {
     double4_t xv, bv, cv;
     if (PIPE && tid < n4) {
         xv = ldg256_stream(a.x + 4 * tid);
@@ -197,6 +221,7 @@ lp_kernel(LpArgs a, double* partials, unsigned int* ticket, double* out /* [4] v
             if (wc && C_VEC) lp_rmw4(a.c_adj + i, gc, a.overwrite);
         }
         if (PIPE) { xv = xn; bv = bn; cv = cn; }
+    }
     }
     for (size_t i = n4 * 4 + tid; i < a.n; i += nth) {
         const double x = a.x[i], b = B_VEC ? a.b[i] : bs, c = C_VEC ? a.c[i] : cs;
