@@ -509,8 +509,17 @@ __global__ void dn_sigma_adj(int n, const double* __restrict__ X, const double* 
     S_adj[idx] = overwrite ? g : S_adj[idx] + g;
 }
 
-// 128-wide tiles (8x8 outputs per thread) once they fill the GPU, 64-wide ones below that
-static inline bool big_tiles(const Context& c, long long tiles128) { return tiles128 >= (long long)c.sms; }
+// Tile size.  Round 1 took 128-wide tiles (8x8 outputs per thread, one CTA per SM) once they filled the GPU.  Phase timing in
+// round 2 (FADB_DENSE_TIMING=1, tools/dense_probe.py) says the 64-wide tile (3 CTAs per SM) is never slower and much faster when
+// K is short: at n = 4000 the rank-128 trailing updates of the Cholesky ran at 10 TFLOP/s on 128-wide tiles and at 15.7 on 64-wide
+// ones, the triangular-inversion levels 1.56 / 1.34 (mixed) / 1.20 ms, Y^T Y (K = n) 0.88 / 0.87 ms: 6.15 -> 5.30 ms for the whole
+// evaluation.  64 is the default; FADB_GEMM_TILE=128 restores the old rule for A/B runs.
+static inline bool big_tiles(const Context& c, long long tiles128, int k)
+{
+    static const int forced = getenv("FADB_GEMM_TILE") ? atoi(getenv("FADB_GEMM_TILE")) : 0;
+    (void)k;
+    return forced == 128 && tiles128 >= (long long)c.sms;
+}
 
 template <bool TA, bool TB>
 static void gemm(Context& c, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
@@ -518,7 +527,7 @@ static void gemm(Context& c, int m, int n, int k, double alpha, const double* A,
 {
     if (m <= 0 || n <= 0) return;
     const long long t128 = (long long)((m + 127) / 128) * ((n + 127) / 128) / (lower_only ? 2 : 1);
-    if (big_tiles(c, t128)) {
+    if (big_tiles(c, t128, k)) {
         dim3 grid((m + 127) / 128, (n + 127) / 128);
         if (use_dmma()) launch_pdl(dn_gemm_mma<128, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
         else launch_pdl(dn_gemm<128, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
@@ -613,8 +622,40 @@ static int ensure_dws(Context& c, size_t n, DenseWs** out)
 
 // Cholesky of the LOWER triangle of Sigma, then its explicit inverse: on return w->diag = L_ii,
 // w->X = Sigma^{-1} (full, symmetric), w->scal[0] != 0 if Sigma is not positive definite.
+// FADB_DENSE_TIMING=1: device time of the phases of one factorisation + inversion, printed to stderr (diagnostic)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    PhaseTimer(cudaStream_t s) : st(s) { static const bool e = getenv("FADB_DENSE_TIMING") != nullptr; on = e; mark("start"); }
+    void mark(const char* name)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+    ~PhaseTimer()
+    {
+        if (!on) return;
+        cudaEventSynchronize(ev.back());
+        fprintf(stderr, "[fadb dense]");
+        for (size_t k = 1; k < ev.size(); ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+            fprintf(stderr, " %s %.3f ms", names[k], ms);
+        }
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+};
+
 static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const double* Sigma)
 {
+    PhaseTimer pt(c->stream);
     const int nb = (N + DB - 1) / DB;
     const size_t nn = (size_t)N * N;
     const int eb = (int)((nn + 255) / 256);
@@ -639,15 +680,18 @@ static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const d
         if (m > 0) {
             const double* P = w->Y + Kend + (size_t)K0 * N;
             double* Ct = w->L + Kend + (size_t)Kend * N;
+            if (pt.on) pt.mark("steps");
             gemm<false, true>(*c, m, m, W, -1.0, P, N, P, N, 1.0, Ct, N, 0, 1);      // trailing -= P P^T (lower)
+            if (pt.on) pt.mark("syrk");
         }
     }
+    pt.mark("cholesky(steps+syrk)");
     // inverse, in place: Y <- Y^{-1} level by level up the halving tree, X <- Y^T Y (lower tiles, K from the diagonal)
     dn_tile_inverse<<<nb, 32, 0, st>>>(N, w->Y);
     c->launches++;
     for (const TrLevel& lv : tp->levels) {
         const long long t128 = (long long)((lv.max_n2 + 127) / 128) * ((lv.max_n1 + 127) / 128) * lv.count;
-        if (big_tiles(*c, t128)) {
+        if (big_tiles(*c, t128, lv.max_n1)) {
             dim3 grid((lv.max_n2 + 127) / 128, (lv.max_n1 + 127) / 128, lv.count);
             if (use_dmma()) {
                 launch_pdl(dn_trtri_level_mma<128>, grid, dim3(256), 0, st, N, w->Y, w->X, tp->dev + lv.first, 0);
@@ -668,9 +712,12 @@ static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const d
         }
         c->launches += 2;
     }
+    pt.mark("trtri");
     gemm<true, false>(*c, N, N, N, 1.0, w->Y, N, w->Y, N, 0.0, w->X, N, 3, 1);
+    pt.mark("YtY");
     dn_symmetrize<<<eb, 256, 0, st>>>(N, w->X);
     c->launches++;
+    pt.mark("symmetrize");
     return FADB_OK;
 }
 
