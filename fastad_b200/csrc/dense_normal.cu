@@ -735,8 +735,7 @@ static int spd_factor_inverse(Context* c, DenseWs* w, TrPlan* tp, int N, const d
 //    (FullPivLU::isInvertible's epsilon * n * max-pivot threshold; LDLT: det != 0) are applied to
 //    these pivots.  This path is simple rather than fast (2n launches).
 // stats[0] invalid flag, [1] prod of pivots (signed), [2] sum log|pivot|, [3] min|pivot|, [4] max|pivot|
-__global__ void __launch_bounds__(1024)
-gj_pivot_kernel(int n, double* W, int k, double* rowbuf, double* colbuf, int* perm, double* stats)
+__device__ __forceinline__ void gj_pivot_body(int n, double* W, int k, double* rowbuf, double* colbuf, int* perm, double* stats)
 {
     __shared__ double sval[32];
     __shared__ int sidx[32];
@@ -789,6 +788,11 @@ gj_pivot_kernel(int n, double* W, int k, double* rowbuf, double* colbuf, int* pe
         W[i + (size_t)k * n] = -f * rinv;
     }
 }
+__global__ void __launch_bounds__(1024)
+gj_pivot_kernel(int n, double* W, int k, double* rowbuf, double* colbuf, int* perm, double* stats)
+{
+    gj_pivot_body(n, W, k, rowbuf, colbuf, perm, stats);
+}
 
 __global__ void gj_update_kernel(int n, double* W, int k, const double* __restrict__ rowbuf, const double* __restrict__ colbuf)
 {
@@ -822,6 +826,50 @@ __global__ void gj_gather_kernel(int n, const double* __restrict__ W, const int*
     if (e >= (size_t)n * n) return;
     const int i = (int)(e % n), j = (int)(e / n);
     Out[e] = W[i + (size_t)idx[j] * n];
+}
+
+// Small matrices (n <= GJ_SMALL_MAX, what det / log_det see in statistical models): the WHOLE elimination, the column map and
+// the gather in ONE launch of one 1024-thread CTA with the matrix in SHARED memory (n^2 doubles <= 200 KB) -- 2n + 2 launches of
+// mostly idle grids otherwise.  Measured (tools/det_probe.py, log_det value + adjoint): n = 4 0.094 -> 0.06 ms, n = 64 0.97 ->
+// 0.3 ms.  With the matrix left in L2 a single CTA loses beyond n ~ 200 (n = 300: 9.0 against 4.5 ms), hence the shared-memory
+// bound.  Same pivot rule, same fma per element and the same order of the pivot statistics as the multi-launch path (it calls
+// the same gj_pivot_body), so results are bit-identical.
+constexpr int GJ_SMALL_MAX = 160;
+__global__ void __launch_bounds__(1024)
+gj_small_kernel(int n, const double* __restrict__ A, double* rowbuf, double* colbuf, int* perm, double* stats, int* idx, double* Out)
+{
+    extern __shared__ __align__(16) double s_W[];        // n x n, column-major
+    __shared__ double s_row[GJ_SMALL_MAX], s_col[GJ_SMALL_MAX];
+    __shared__ int s_idx[GJ_SMALL_MAX];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
+    for (int e = t; e < n * n; e += blockDim.x) s_W[e] = A[e];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        gj_pivot_body(n, s_W, k, s_row, s_col, perm, stats);
+        __syncthreads();
+        for (int j = wid; j < n; j += nw) {              // rank-1 update, one column per warp, rows along the lanes
+            if (j == k) continue;
+            const double rj = s_row[j];
+            double* col = s_W + (size_t)j * n;
+            for (int i = lane; i < n; i += 32) col[i] = fma(-s_col[i], rj, col[i]);
+        }
+        __syncthreads();
+    }
+    (void)rowbuf; (void)colbuf;
+    for (int j = t; j < n; j += blockDim.x) s_idx[j] = j;
+    __syncthreads();
+    if (t == 0)
+        for (int k = n - 1; k >= 0; --k) {
+            const int p = perm[k];
+            const int a = s_idx[k]; s_idx[k] = s_idx[p]; s_idx[p] = a;
+        }
+    __syncthreads();
+    for (int j = t; j < n; j += blockDim.x) idx[j] = s_idx[j];
+    for (int j = wid; j < n; j += nw) {
+        const double* src = s_W + (size_t)s_idx[j] * n;
+        double* dst = Out + (size_t)j * n;
+        for (int i = lane; i < n; i += 32) dst[i] = src[i];
+    }
 }
 
 // value of det / log_det.  policy 2 (LLT): from the Cholesky diagonal; else from the elimination stats.
@@ -971,6 +1019,19 @@ static int gj_inverse(Context* c, DenseWs* w, GjWs* g, int N, const double* A)
     const size_t nn = (size_t)N * N;
     cudaStream_t st = c->stream;
     FADB_CUDA(cudaMemsetAsync(w->scal, 0, 8 * sizeof(double), st));
+    static const bool small_ok = [] { const char* e = getenv("FADB_GJ_SMALL"); return !(e && e[0] == '0'); }();   // =0: A/B runs
+    if (small_ok && N <= GJ_SMALL_MAX) {
+        static bool attr_set[kMaxDevices] = {false};
+        if (!attr_set[c->device]) {
+            FADB_CUDA(cudaFuncSetAttribute(gj_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(GJ_SMALL_MAX * GJ_SMALL_MAX * sizeof(double))));
+            attr_set[c->device] = true;
+        }
+        gj_small_kernel<<<1, 1024, nn * sizeof(double), st>>>(N, A, w->d, w->z, g->perm, w->scal, g->idx, w->X);
+        c->launches++;
+        FADB_CUDA(cudaGetLastError());
+        return FADB_OK;
+    }
     FADB_CUDA(cudaMemcpyAsync(w->L, A, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
     dim3 ugrid((N + 127) / 128, (N + 15) / 16);
     for (int k = 0; k < N; ++k) {

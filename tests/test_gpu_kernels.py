@@ -807,8 +807,11 @@ def test_det_reference_goldens(fb, policy, log):
     assert np.abs(host(Aa).reshape(4, 4, order="F") - 2 * want).max() <= 6e-13
 
 
-@pytest.mark.parametrize("policy,n", [("fullpivlu", 1), ("fullpivlu", 5), ("fullpivlu", 67), ("fullpivlu", 300),
-                                      ("ldlt", 33), ("ldlt", 150), ("llt", 31), ("llt", 130), ("llt", 500)])
+# n <= 160: the whole elimination in one launch of one CTA, matrix in shared memory (gj_small_kernel); above: pivot + update
+# launches per column
+@pytest.mark.parametrize("policy,n", [("fullpivlu", 1), ("fullpivlu", 5), ("fullpivlu", 67), ("fullpivlu", 160), ("fullpivlu", 161),
+                                      ("fullpivlu", 300), ("ldlt", 33), ("ldlt", 150), ("ldlt", 170), ("llt", 31), ("llt", 130),
+                                      ("llt", 500)])
 def test_det_vs_oracle(fb, policy, n):
     rng = np.random.default_rng(n)
     if policy == "fullpivlu":
@@ -826,6 +829,20 @@ def test_det_vs_oracle(fb, policy, n):
         assert rel(v, ov) <= 1e-10, (policy, n, log)
         oa = e.adj(a)
         np.testing.assert_allclose(host(Aa), oa, rtol=1e-7, atol=1e-10 * np.abs(oa).max())
+
+
+def test_det_single_launch_path_is_bit_identical_to_the_launch_chain():
+    # same pivot rule, same fma per element: tools/det_probe.py prints the value and a digest of the adjoint; one process per
+    # setting (the switch is read once)
+    import hashlib, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for small in ("1", "0"):
+        p = subprocess.run([sys.executable, os.path.join(root, "tools", "det_probe.py"), "97", "160"], capture_output=True, text=True,
+                           env=dict(os.environ, FADB_GJ_SMALL=small), timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append([l for l in p.stdout.splitlines() if l.startswith("digest")])
+    assert outs[0] == outs[1] and len(outs[0]) == 4, outs
 
 
 def test_det_invalid_leaves_adjoint_untouched(fb):
