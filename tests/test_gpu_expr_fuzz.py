@@ -142,3 +142,80 @@ def test_random_expression_matches_oracle(fb, engine, seed):
     _close(gv, ov, f"seed {seed} value\n{ge.describe()}")
     for k, (g, o) in enumerate(zip(gadj, oadj)):
         _close(g, o, f"seed {seed} adj[{k}]\n{ge.describe()}")
+
+
+class PlaceholderGen:
+    """Random programs of the reference's placeholder idiom over vectors (`c_k = f_k(leaves, c_1 .. c_{k-1})`, glued, then a
+    root that reads the placeholders): the stages the operand ring of the specialised kernel serves (stage_kernel.cuh, JIT_RING).
+    Each placeholder is assigned once."""
+
+    def __init__(self, seed, n):
+        self.rng = np.random.default_rng(1000 + seed)
+        self.n = n
+
+    def build(self, e):
+        rng, n = self.rng, self.n
+        vec_vars = [e.var(rng.uniform(0.6, 1.6, n)) for _ in range(int(rng.integers(1, 4)))]
+        scl_vars = [e.var(float(rng.uniform(0.7, 1.4)))]
+        consts = [e.const(rng.uniform(0.5, 1.5, n)) for _ in range(int(rng.integers(1, 3)))]
+        pool = list(vec_vars) + consts
+
+        def bounded(x):
+            return e.binary("add", e.const(1.0), e.binary("mul", e.const(0.5), e.unary("tanh", x)))
+
+        def pick():
+            return pool[int(rng.integers(len(pool)))]
+
+        def expr():
+            kind = rng.random()
+            if kind < 0.4:
+                return bounded(e.unary(UNARY_SAFE[int(rng.integers(len(UNARY_SAFE)))], pick()))
+            if kind < 0.5:
+                return bounded(e.unary(UNARY_POS[int(rng.integers(len(UNARY_POS)))], pick()))
+            op = ("add", "sub", "mul", "div")[int(rng.integers(4))]
+            a = scl_vars[0] if rng.random() < 0.2 else pick()
+            return bounded(e.binary(op, a, pick()))
+
+        holders, assigns = [], []
+        for _ in range(int(rng.integers(1, 4))):
+            ph = e.var(np.zeros(n))
+            assigns.append(e.eq(ph, expr()))
+            holders.append(ph)
+            pool.append(ph)                       # later expressions (and the root) read the placeholder
+        body = e.binary("sub", e.binary("mul", holders[-1], pick()), e.binary("mul", e.const(0.3), holders[0]))
+        variables = vec_vars + scl_vars + holders
+        if rng.random() < 0.5:
+            return e.glue(*assigns, body), variables, rng.uniform(-1, 1, n)          # vector-valued root, per-element seed
+        return e.glue(*assigns, e.sum(body)), variables, float(rng.uniform(0.5, 1.5))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_placeholder_program_on_the_operand_ring(fb, seed):
+    # several trips per thread (the specialised kernel's grid holds 151 552 threads), an odd element count; against the oracle,
+    # and bit for bit against the plain kernel of the same program
+    n = 320001 if seed % 3 else 4099
+    res = {}
+    for ring in (1, 0):
+        prev = fb.lib().fadb_jit_ring_enable(ring)
+        try:
+            e = fb.Expr()
+            root, variables, s = PlaceholderGen(seed, n).build(e)
+            e.bind(root)
+            j0 = fb.jit_stats()
+            v = e.autodiff(s)
+            assert fb.jit_stats()["failed"] == j0["failed"], fb.lib().fadb_jit_diagnostics().decode()
+            res[ring] = (np.asarray(v).reshape(-1).copy(), [np.asarray(e.adj(x)).reshape(-1).copy() for x in variables],
+                         [np.asarray(e.value(x)).reshape(-1).copy() for x in variables], e.describe())
+        finally:
+            fb.lib().fadb_jit_ring_enable(prev)
+    oe = O.OracleExpr()
+    root, variables, s = PlaceholderGen(seed, n).build(oe)
+    oe.bind(root)
+    ov = np.asarray(oe.autodiff(s)).reshape(-1)
+    _close(res[1][0], ov, f"seed {seed} value\n{res[1][3]}")
+    for k, x in enumerate(variables):
+        _close(res[1][1][k], np.asarray(oe.adj(x)).reshape(-1), f"seed {seed} adj[{k}]\n{res[1][3]}")
+        _close(res[1][2][k], np.asarray(oe.value(x)).reshape(-1), f"seed {seed} val[{k}]\n{res[1][3]}")
+    np.testing.assert_array_equal(res[1][0], res[0][0])
+    for a, b in zip(res[1][1] + res[1][2], res[0][1] + res[0][2]):
+        np.testing.assert_array_equal(a, b)
