@@ -403,7 +403,16 @@ dn_gemm_mma(int m, int n, int k, double alpha, const double* __restrict__ A, int
             double beta, double* C, int ldc, int kmode, int lower_only)
 {
     pdl_prologue();
-    gemm_tile_mma<BT, TA, TB>(blockIdx.x, blockIdx.y, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
+    int bi = blockIdx.x, bj = blockIdx.y;
+    if (lower_only && gridDim.y == 1) {
+        // triangular launch (square products only): CTA b is tile (bi, bj), bj <= bi, b = bi (bi + 1) / 2 + bj -- the upper half
+        // of a square grid is CTAs that start only to return (1800 of 3600 per rank-128 update at n = 4000)
+        bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+        while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+        while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+        bj = (int)blockIdx.x - bi * (bi + 1) / 2;
+    }
+    gemm_tile_mma<BT, TA, TB>(bi, bj, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
 }
 
 // FADB_GEMM_DMMA=0 selects the DFMA register-tiled kernels everywhere (A/B runs); default: tensor cores
@@ -533,6 +542,8 @@ static void gemm(Context& c, int m, int n, int k, double alpha, const double* A,
         else launch_pdl(dn_gemm<128, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
     } else {
         dim3 grid((m + 63) / 64, (n + 63) / 64);
+        static const bool tri = [] { const char* e = getenv("FADB_GEMM_TRI"); return !(e && e[0] == '0'); }();       // =0: A/B runs
+        if (tri && lower_only && m == n && use_dmma() && grid.x > 1) grid = dim3(grid.x * (grid.x + 1) / 2, 1);
         if (use_dmma()) launch_pdl(dn_gemm_mma<64, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
         else launch_pdl(dn_gemm<64, TA, TB>, grid, dim3(256), 0, c.stream, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kmode, lower_only);
     }
